@@ -1,0 +1,156 @@
+"""ctypes binding of libb200gen.so (the C-ABI declared in include/b200gen.h).
+
+The library is the product: if it is missing, cannot be loaded or the device is not sm_100-class, every op
+raises — there is no CPU or PyTorch fallback anywhere in this package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "lib" / "libb200gen.so"
+
+B200_OK, B200_EINVAL, B200_ENOTSUP, B200_ECUDA, B200_ENODEV = 0, -1, -2, -3, -4
+DT_BF16, DT_F32 = 0, 1
+ACT_NONE, ACT_RELU, ACT_SILU = 0, 1, 2
+PRED_EPSILON, PRED_SAMPLE, PRED_V = 0, 1, 2
+IGEMM_MAX_SEG = 128
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+class IgemmSeg(C.Structure):
+    _fields_ = [("src", C.c_int8), ("dw", C.c_int8), ("dh", C.c_int8), ("dd", C.c_int8),
+                ("c0", C.c_uint16), ("nchunks", C.c_uint16)]
+
+
+class IgemmParams(C.Structure):
+    _fields_ = [
+        ("a_ptr", C.c_void_p * 2), ("a_C", C.c_int32 * 2), ("a_pitch", C.c_int32 * 2),
+        ("in_N", C.c_int32), ("in_D", C.c_int32), ("in_H", C.c_int32), ("in_W", C.c_int32),
+        ("stride_d", C.c_int32), ("stride_h", C.c_int32), ("stride_w", C.c_int32),
+        ("w_ptr", C.c_void_p), ("w_rows", C.c_int32), ("w_pitch", C.c_int32), ("w_K", C.c_int32),
+        ("w_bstride", C.c_int64), ("w_batched", C.c_int32), ("n_seg", C.c_int32),
+        ("seg", IgemmSeg * IGEMM_MAX_SEG),
+        ("out_ptr", C.c_void_p), ("out_dtype", C.c_int32),
+        ("out_N", C.c_int32), ("out_D", C.c_int32), ("out_H", C.c_int32), ("out_W", C.c_int32),
+        ("cout", C.c_int32), ("out_cols", C.c_int32),
+        ("out_sN", C.c_int64), ("out_sD", C.c_int64), ("out_sH", C.c_int64), ("out_sW", C.c_int64),
+        ("bias", C.c_void_p), ("rowvec", C.c_void_p), ("rowvec_bstride", C.c_int64), ("row_bias", C.c_void_p),
+        ("act1", C.c_int32), ("scale", C.c_float),
+        ("res_ptr", C.c_void_p), ("res_dtype", C.c_int32),
+        ("res_sN", C.c_int64), ("res_sD", C.c_int64), ("res_sH", C.c_int64), ("res_sW", C.c_int64),
+        ("act2", C.c_int32), ("impl", C.c_int32),
+    ]
+
+
+class GnStatsParams(C.Structure):
+    _fields_ = [("x_ptr", C.c_void_p * 2), ("x_C", C.c_int32 * 2), ("x_pitch", C.c_int32 * 2),
+                ("N", C.c_int32), ("spatial", C.c_int64), ("groups", C.c_int32), ("eps", C.c_float),
+                ("gamma", C.c_void_p), ("beta", C.c_void_p), ("partial", C.c_void_p), ("affine", C.c_void_p)]
+
+
+class GnApplyParams(C.Structure):
+    _fields_ = [("x_ptr", C.c_void_p * 2), ("x_C", C.c_int32 * 2), ("x_pitch", C.c_int32 * 2),
+                ("N", C.c_int32), ("spatial", C.c_int64), ("affine", C.c_void_p), ("act", C.c_int32),
+                ("y_ptr", C.c_void_p), ("y_pitch", C.c_int32)]
+
+
+class DdimCoef(C.Structure):
+    _fields_ = [("sqrt_alpha_prod_t", C.c_float), ("sqrt_beta_prod_t", C.c_float),
+                ("sqrt_alpha_prod_prev", C.c_float), ("dir_coef", C.c_float), ("sigma", C.c_float),
+                ("clip_min", C.c_float), ("clip_max", C.c_float),
+                ("prediction_type", C.c_int32), ("clip", C.c_int32)]
+
+
+class DdpmCoef(C.Structure):
+    _fields_ = [("sqrt_alpha_prod_t", C.c_float), ("sqrt_beta_prod_t", C.c_float),
+                ("coef_x0", C.c_float), ("coef_xt", C.c_float), ("sigma", C.c_float),
+                ("clip_min", C.c_float), ("clip_max", C.c_float), ("min_log", C.c_float), ("max_log", C.c_float),
+                ("var_mode", C.c_int32), ("prediction_type", C.c_int32), ("clip", C.c_int32)]
+
+
+class PndmCoef(C.Structure):
+    _fields_ = [("w", C.c_float * 4), ("n_hist", C.c_int32), ("sample_coeff", C.c_float), ("eps_coeff", C.c_float),
+                ("v_alpha", C.c_float), ("v_beta", C.c_float), ("prediction_type", C.c_int32)]
+
+
+_P, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+
+# name -> argtypes (restype is int unless listed in _RESTYPES); mirrors include/b200gen.h exactly
+SIGNATURES = {
+    "b200_last_error_string": [],
+    "b200_version": [],
+    "b200_device_check": [],
+    "b200_sm_count": [],
+    "b200_igemm": [C.POINTER(IgemmParams), _P],
+    "b200_groupnorm_workspace_bytes": [_I32, _I64, _I32],
+    "b200_groupnorm_stats": [C.POINTER(GnStatsParams), _P],
+    "b200_groupnorm_apply": [C.POINTER(GnApplyParams), _P],
+    "b200_layernorm": [_P, _I64, _I32, _I32, _P, _P, _F, _P, _I32, _P],
+    "b200_nchw_to_nhwc": [_P, _I32, _I32, _I64, _P, _I32, _P],
+    "b200_nhwc_to_nchw": [_P, _I32, _I32, _I32, _I64, _I32, _P, _P],
+    "b200_upsample_nearest2x": [_P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P],
+    "b200_avgpool2": [_P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P],
+    "b200_axpy_bf16": [_P, _P, _F, _P, _I64, _P],
+    "b200_geglu": [_P, _I64, _I32, _I32, _P, _I32, _P],
+    "b200_softmax_rows": [_P, _I64, _I32, _I64, _P, _I64, _P],
+    "b200_attention_small": [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _F, _P],
+    "b200_timestep_embedding": [_P, _I32, _I32, _F, _P, _P],
+    "b200_small_linear": [_P, _I32, _I32, _P, _P, _I32, _I32, _I32, _P, _P],
+    "b200_ddim_step": [_P, _P, _P, C.POINTER(DdimCoef), _P, _P, _I64, _P],
+    "b200_ddpm_step": [_P, _P, _P, _P, C.POINTER(DdpmCoef), _P, _P, _I64, _P],
+    "b200_pndm_step": [C.POINTER(_P), _P, C.POINTER(PndmCoef), _P, _P, _I64, _P],
+    "b200_add_noise": [_P, _P, _P, _P, _F, _I32, _I64, _P, _P],
+    "b200_vq_argmin_gather": [_P, _I64, _I32, _I32, _P, _I32, _P, _P, _I32, _P, _I32, _P, _P, _P],
+    "b200_vq_gather": [_P, _I64, _P, _I32, _I32, _P, _I32, _P],
+}
+_RESTYPES = {"b200_last_error_string": C.c_char_p, "b200_groupnorm_workspace_bytes": C.c_int64}
+
+_lib = None
+_device_ok = False
+
+
+def load():
+    """Load the shared library (no GPU needed) and bind every symbol the header declares."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise B200Error(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(generativemodels_b200/csrc/build.sh). There is no fallback path.")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export it
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, C.c_int)
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().b200_last_error_string().decode("utf-8", "replace")
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise B200Error(f"{what} failed with code {rc}: {last_error()}")
+
+
+def require_device():
+    """Fail loudly unless the current CUDA device is sm_100-class."""
+    global _device_ok
+    lib = load()
+    if not _device_ok:
+        import torch
+
+        if not torch.cuda.is_available():
+            raise B200Error("generativemodels_b200 needs a CUDA device (sm_100a); none is visible and there is no CPU path")
+        check(lib.b200_device_check(), "b200_device_check")
+        _device_ok = True
+    return lib

@@ -1,0 +1,95 @@
+// Small-shape attention on CUDA cores: softmax(scale * Q K^T) V with an online softmax, one warp per query row.
+//
+// Serves the shapes the tensor-core path is not built for: the test-suite head dims (2, 4, 8 ...), and
+// cross-attention over a handful of context tokens (S = 1 in the classifier-free-guidance tutorial), where the
+// whole problem is a few MFLOP.  Reference arithmetic: CrossAttention._attention
+// (diffusion_model_unet.py:136-153) and AttentionBlock.forward (406-416): scores = scale * q.k, softmax over
+// keys, probabilities times values.  Heads are channel slices [h*dh, (h+1)*dh) of the packed [B, T, H*dh] rows
+// (reshape_heads_to_batch_dim, 107-116), so no head transpose is ever materialised.
+#include "common.cuh"
+
+namespace b200 {
+
+template <int R>   // R = ceil(dh / 32) registers per lane
+__global__ void attention_small_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
+                                       const __nv_bfloat16* __restrict__ v, __nv_bfloat16* __restrict__ out, int B,
+                                       int T, int S, int heads, int dh, int q_pitch, int k_pitch, int v_pitch,
+                                       int o_pitch, float scale) {
+  const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long total = (long long)B * heads * T;
+  if (wid >= total) return;
+  const int lane = threadIdx.x & 31;
+  const int t = (int)(wid % T);
+  const int h = (int)((wid / T) % heads);
+  const int b = (int)(wid / ((long long)T * heads));
+  const __nv_bfloat16* qr = q + ((long long)b * T + t) * q_pitch + h * dh;
+  float qreg[R], acc[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int d = lane + 32 * r;
+    qreg[r] = d < dh ? __bfloat162float(qr[d]) * scale : 0.f;
+    acc[r] = 0.f;
+  }
+  float mx = -INFINITY, denom = 0.f;
+  const __nv_bfloat16* kb = k + (long long)b * S * k_pitch + h * dh;
+  const __nv_bfloat16* vb = v + (long long)b * S * v_pitch + h * dh;
+  for (int s = 0; s < S; ++s) {
+    const __nv_bfloat16* kr = kb + (long long)s * k_pitch;
+    float dot = 0.f;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int d = lane + 32 * r;
+      if (d < dh) dot = fmaf(qreg[r], __bfloat162float(kr[d]), dot);
+    }
+    dot = warp_sum(dot);
+    const float nmx = fmaxf(mx, dot);
+    const float corr = __expf(mx - nmx);      // exp(-inf) = 0 on the first key
+    const float p = __expf(dot - nmx);
+    denom = denom * corr + p;
+    const __nv_bfloat16* vr = vb + (long long)s * v_pitch;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int d = lane + 32 * r;
+      if (d < dh) acc[r] = acc[r] * corr + p * __bfloat162float(vr[d]);
+    }
+    mx = nmx;
+  }
+  const float inv = 1.0f / denom;
+  __nv_bfloat16* orow = out + ((long long)b * T + t) * o_pitch + h * dh;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int d = lane + 32 * r;
+    if (d < dh) orow[d] = __float2bfloat16_rn(acc[r] * inv);
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_attention_small(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t T,
+                                    int32_t S, int32_t heads, int32_t dh, int32_t q_pitch, int32_t k_pitch,
+                                    int32_t v_pitch, int32_t o_pitch, float scale, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(q && k && v && out && B >= 1 && T >= 1 && S >= 1 && heads >= 1 && dh >= 1, "attention_small: bad arguments");
+  B200_CHECK_ARG(dh <= 1024, "attention_small: head_dim %d > 1024", dh);
+  const long long total = (long long)B * heads * T;
+  const int wpb = 8;
+  const long long blocks = (total + wpb - 1) / wpb;
+  B200_CHECK_ARG(blocks < (1ll << 31), "attention_small: too many rows");
+  const __nv_bfloat16* qq = reinterpret_cast<const __nv_bfloat16*>(q);
+  const __nv_bfloat16* kk = reinterpret_cast<const __nv_bfloat16*>(k);
+  const __nv_bfloat16* vv = reinterpret_cast<const __nv_bfloat16*>(v);
+  __nv_bfloat16* oo = reinterpret_cast<__nv_bfloat16*>(out);
+#define LAUNCH(R) attention_small_kernel<R><<<(unsigned)blocks, wpb * 32, 0, stream>>>( \
+      qq, kk, vv, oo, B, T, S, heads, dh, q_pitch, k_pitch, v_pitch, o_pitch, scale)
+  if (dh <= 32) LAUNCH(1);
+  else if (dh <= 64) LAUNCH(2);
+  else if (dh <= 128) LAUNCH(4);
+  else if (dh <= 256) LAUNCH(8);
+  else if (dh <= 512) LAUNCH(16);
+  else LAUNCH(32);
+#undef LAUNCH
+  B200_LAUNCH_CHECK("attention_small_kernel");
+  return B200_OK;
+}

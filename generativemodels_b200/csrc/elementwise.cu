@@ -1,0 +1,470 @@
+// HBM-bound helpers of the sampling path: layout conversion on the API edge, resampling, GEGLU, row softmax,
+// time embedding, GEMV-class linears and the fused scheduler updates.  All are single-pass, coalesced and
+// (where the layout allows) 128-bit vectorised; none of them has data reuse worth staging in shared memory
+// except the two transposes.
+#include "common.cuh"
+
+namespace b200 {
+
+// ------------------------------------------------------------------------------------------------
+// NC[D]HW fp32 <-> NDHWC bf16: 32x32 shared-memory tile transpose (coalesced on both sides).
+// ------------------------------------------------------------------------------------------------
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int C, long long spatial,
+                                    __nv_bfloat16* __restrict__ y, int pitch) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const long long s0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const float* xb = x + (long long)n * C * spatial;
+  __nv_bfloat16* yb = y + (long long)n * spatial * pitch;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j;
+    const long long s = s0 + threadIdx.x;
+    tile[j][threadIdx.x] = (c < C && s < spatial) ? xb[(long long)c * spatial + s] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const long long s = s0 + j;
+    const int c = c0 + threadIdx.x;
+    if (s < spatial && c < pitch) yb[s * pitch + c] = __float2bfloat16_rn(tile[threadIdx.x][j]);
+  }
+}
+
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, int C, long long spatial, int pitch,
+                                    float* __restrict__ y) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const long long s0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const T* xb = x + (long long)n * spatial * pitch;
+  float* yb = y + (long long)n * C * spatial;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const long long s = s0 + j;
+    const int c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (s < spatial && c < C) {
+      if constexpr (sizeof(T) == 2) v = __bfloat162float(xb[s * pitch + c]);
+      else v = xb[s * pitch + c];
+    }
+    tile[j][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j;
+    const long long s = s0 + threadIdx.x;
+    if (c < C && s < spatial) yb[(long long)c * spatial + s] = tile[threadIdx.x][j];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// nearest x2 upsample / 2x average pool on channels-last bf16; one thread per (output voxel, 8 channels)
+// ------------------------------------------------------------------------------------------------
+__global__ void upsample2x_kernel(const uint4* __restrict__ x, int N, int D, int H, int W, int pv, int dims,
+                                  uint4* __restrict__ y) {
+  const int OD = dims == 3 ? 2 * D : D, OH = 2 * H, OW = 2 * W;
+  const long long total = (long long)N * OD * OH * OW * pv;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long t = idx;
+    const int v = (int)(t % pv); t /= pv;
+    const int ow = (int)(t % OW); t /= OW;
+    const int oh = (int)(t % OH); t /= OH;
+    const int od = (int)(t % OD); t /= OD;
+    const int n = (int)t;
+    const int id = dims == 3 ? od >> 1 : od;
+    y[idx] = __ldg(x + ((((long long)n * D + id) * H + (oh >> 1)) * W + (ow >> 1)) * pv + v);
+  }
+}
+
+__global__ void avgpool2_kernel(const uint4* __restrict__ x, int N, int D, int H, int W, int pv, int dims,
+                                uint4* __restrict__ y) {
+  const int OD = dims == 3 ? D / 2 : D, OH = H / 2, OW = W / 2;
+  const int kd = dims == 3 ? 2 : 1;
+  const float inv = 1.0f / (float)(kd * 4);
+  const long long total = (long long)N * OD * OH * OW * pv;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long t = idx;
+    const int v = (int)(t % pv); t /= pv;
+    const int ow = (int)(t % OW); t /= OW;
+    const int oh = (int)(t % OH); t /= OH;
+    const int od = (int)(t % OD); t /= OD;
+    const int n = (int)t;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int a = 0; a < kd; ++a)
+      for (int b = 0; b < 2; ++b)
+        for (int c = 0; c < 2; ++c) {
+          const int id = dims == 3 ? od * 2 + a : od;
+          uint4 q = __ldg(x + ((((long long)n * D + id) * H + (oh * 2 + b)) * W + (ow * 2 + c)) * pv + v);
+          float f[8];
+          unpack8(q, f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += f[j];
+        }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] *= inv;
+    y[idx] = pack8(acc);
+  }
+}
+
+__global__ void axpy_bf16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, float alpha,
+                                 uint4* __restrict__ y, long long nvec) {
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < nvec;
+       idx += (long long)gridDim.x * blockDim.x) {
+    float fa[8], fb[8];
+    unpack8(__ldg(a + idx), fa);
+    unpack8(__ldg(b + idx), fb);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) fa[j] = fmaf(alpha, fb[j], fa[j]);
+    y[idx] = pack8(fa);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GEGLU: y = x[:, :H] * gelu_erf(x[:, H:])
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+__global__ void geglu_kernel(const __nv_bfloat16* __restrict__ x, long long M, int H, int x_pitch,
+                             __nv_bfloat16* __restrict__ y, int y_pitch) {
+  const int HV = H / 8;
+  const long long total = M * HV;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long m = idx / HV;
+    const int h = (int)(idx % HV) * 8;
+    float a[8], g[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x + m * x_pitch + h)), a);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x + m * x_pitch + H + h)), g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] *= gelu_erf(g[j]);
+    *reinterpret_cast<uint4*>(y + m * y_pitch + h) = pack8(a);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row softmax: fp32 scores -> bf16 probabilities. TPR threads cooperate on one row.
+// ------------------------------------------------------------------------------------------------
+template <int TPR>
+__global__ void softmax_rows_kernel(const float* __restrict__ s, long long M, int S, long long s_pitch,
+                                    __nv_bfloat16* __restrict__ p, long long p_pitch) {
+  constexpr int RPB = 256 / TPR;
+  const long long row = (long long)blockIdx.x * RPB + threadIdx.x / TPR;
+  const int t = threadIdx.x % TPR;
+  __shared__ float red[8];
+  const bool live = row < M;
+  const float* sr = s + (live ? row : 0) * s_pitch;
+  float mx = -INFINITY;
+  if (live)
+    for (int c = t; c < S; c += TPR) mx = fmaxf(mx, sr[c]);
+  mx = warp_max(mx);
+  if constexpr (TPR > 32) {
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
+    __syncthreads();
+  }
+  float sum = 0.f;
+  if (live)
+    for (int c = t; c < S; c += TPR) sum += __expf(sr[c] - mx);
+  sum = warp_sum(sum);
+  if constexpr (TPR > 32) {
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum += red[i];
+  }
+  if (!live) return;
+  const float inv = 1.0f / sum;
+  __nv_bfloat16* pr = p + row * p_pitch;
+  for (int c = t; c < S; c += TPR) pr[c] = __float2bfloat16_rn(__expf(sr[c] - mx) * inv);
+  for (long long c = S + t; c < p_pitch; c += TPR) pr[c] = __float2bfloat16_rn(0.f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// time embedding + GEMV-class linear
+// ------------------------------------------------------------------------------------------------
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, int N, int dim, float max_period,
+                                          float* __restrict__ emb) {
+  const int half = dim / 2;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * dim) return;
+  const int n = idx / dim, i = idx % dim;
+  float v = 0.f;
+  if (i < 2 * half) {
+    const int k = i < half ? i : i - half;
+    // exponent = -ln(max_period) * k, freq = exp(exponent / half): same operation order as the reference
+    const float freq = expf((-logf(max_period) * (float)k) / (float)half);
+    const float arg = t[n] * freq;
+    v = i < half ? cosf(arg) : sinf(arg);
+  }
+  emb[idx] = v;
+}
+
+// one warp per output feature; loops over the (few) rows
+__global__ void small_linear_kernel(const float* __restrict__ x, int M, int K, const float* __restrict__ W,
+                                    const float* __restrict__ b, int O, int act_in, int act_out,
+                                    float* __restrict__ y) {
+  const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (o >= O) return;
+  const int lane = threadIdx.x & 31;
+  const float* w = W + (long long)o * K;
+  for (int m = 0; m < M; ++m) {
+    const float* xr = x + (long long)m * K;
+    float acc = 0.f;
+    for (int k = lane; k < K; k += 32) acc = fmaf(apply_act(xr[k], act_in), __ldg(w + k), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) y[(long long)m * O + o] = apply_act(acc + (b ? b[o] : 0.f), act_out);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// scheduler steps
+// ------------------------------------------------------------------------------------------------
+__global__ void ddim_step_kernel(const float* __restrict__ eps_in, const float* __restrict__ x,
+                                 const float* __restrict__ noise, b200_ddim_coef c,
+                                 float* __restrict__ prev, float* __restrict__ x0_out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float m = eps_in[i], s = x[i];
+    float x0, eps;
+    if (c.prediction_type == B200_PRED_EPSILON) {
+      x0 = (s - c.sqrt_beta_prod_t * m) / c.sqrt_alpha_prod_t;
+      eps = m;
+    } else if (c.prediction_type == B200_PRED_SAMPLE) {
+      x0 = m;
+      eps = (s - c.sqrt_alpha_prod_t * x0) / c.sqrt_beta_prod_t;
+    } else {
+      x0 = c.sqrt_alpha_prod_t * s - c.sqrt_beta_prod_t * m;
+      eps = c.sqrt_alpha_prod_t * m + c.sqrt_beta_prod_t * s;
+    }
+    if (c.clip) x0 = fminf(fmaxf(x0, c.clip_min), c.clip_max);
+    float p = c.sqrt_alpha_prod_prev * x0 + c.dir_coef * eps;
+    if (noise) p += c.sigma * noise[i];
+    prev[i] = p;
+    if (x0_out) x0_out[i] = x0;
+  }
+}
+
+__global__ void ddpm_step_kernel(const float* __restrict__ eps_in, const float* __restrict__ x,
+                                 const float* __restrict__ noise, const float* __restrict__ pred_var,
+                                 b200_ddpm_coef c, float* __restrict__ prev, float* __restrict__ x0_out,
+                                 long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float m = eps_in[i], s = x[i];
+    float x0;
+    if (c.prediction_type == B200_PRED_EPSILON) x0 = (s - c.sqrt_beta_prod_t * m) / c.sqrt_alpha_prod_t;
+    else if (c.prediction_type == B200_PRED_SAMPLE) x0 = m;
+    else x0 = c.sqrt_alpha_prod_t * s - c.sqrt_beta_prod_t * m;
+    if (c.clip) x0 = fminf(fmaxf(x0, c.clip_min), c.clip_max);
+    float p = c.coef_x0 * x0 + c.coef_xt * s;
+    if (noise) {
+      float sig = c.sigma;
+      if (c.var_mode == 1) sig = sqrtf(pred_var[i]);
+      else if (c.var_mode == 2) {
+        const float frac = (pred_var[i] + 1.0f) / 2.0f;
+        sig = sqrtf(frac * c.max_log + (1.0f - frac) * c.min_log);
+      }
+      p += sig * noise[i];
+    }
+    prev[i] = p;
+    if (x0_out) x0_out[i] = x0;
+  }
+}
+
+struct PndmPtrs { const float* h[4]; };
+
+__global__ void pndm_step_kernel(PndmPtrs hp, const float* __restrict__ x, b200_pndm_coef c,
+                                 float* __restrict__ prev, float* __restrict__ eps_out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float e = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (k < c.n_hist) e = fmaf(c.w[k], hp.h[k][i], e);
+    if (eps_out) eps_out[i] = e;
+    if (prev) {
+      const float s = x[i];
+      if (c.prediction_type == B200_PRED_V) e = c.v_alpha * e + c.v_beta * s;
+      prev[i] = c.sample_coeff * s - c.eps_coeff * e;
+    }
+  }
+}
+
+__global__ void add_noise_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
+                                 const float* __restrict__ ca, const float* __restrict__ cb, float sign_b,
+                                 long long per_sample, float* __restrict__ out) {
+  const int n = blockIdx.y;
+  const float a = ca[n], b = cb[n] * sign_b;
+  const long long base = (long long)n * per_sample;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per_sample;
+       i += (long long)gridDim.x * blockDim.x)
+    out[base + i] = a * x0[base + i] + b * noise[base + i];
+}
+
+static unsigned grid_for(long long work, int threads = 256, int waves = 8) {
+  long long b = (work + threads - 1) / threads;
+  const long long cap = (long long)waves * sm_count();
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_nchw_to_nhwc(const float* x, int32_t N, int32_t C, int64_t spatial, void* y, int32_t pitch,
+                                 void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(x && y && N >= 1 && C >= 1 && spatial >= 1 && pitch >= C, "nchw_to_nhwc: bad arguments");
+  const long long bx = (spatial + 31) / 32;
+  B200_CHECK_ARG(bx < (1ll << 31) && N <= 65535, "nchw_to_nhwc: extent too large");
+  dim3 grid((unsigned)bx, (pitch + 31) / 32, N);
+  nchw_to_nhwc_kernel<<<grid, dim3(32, 8), 0, stream>>>(x, C, spatial, reinterpret_cast<__nv_bfloat16*>(y), pitch);
+  B200_LAUNCH_CHECK("nchw_to_nhwc_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_nhwc_to_nchw(const void* x, int32_t x_dtype, int32_t N, int32_t C, int64_t spatial,
+                                 int32_t pitch, float* y, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(x && y && N >= 1 && C >= 1 && spatial >= 1 && pitch >= C, "nhwc_to_nchw: bad arguments");
+  const long long bx = (spatial + 31) / 32;
+  B200_CHECK_ARG(bx < (1ll << 31) && N <= 65535, "nhwc_to_nchw: extent too large");
+  dim3 grid((unsigned)bx, (C + 31) / 32, N);
+  if (x_dtype == B200_DT_BF16)
+    nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, dim3(32, 8), 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), C, spatial, pitch, y);
+  else
+    nhwc_to_nchw_kernel<float><<<grid, dim3(32, 8), 0, stream>>>(reinterpret_cast<const float*>(x), C, spatial, pitch, y);
+  B200_LAUNCH_CHECK("nhwc_to_nchw_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_upsample_nearest2x(const void* x, int32_t N, int32_t D, int32_t H, int32_t W, int32_t pitch,
+                                       int32_t dims, void* y, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(x && y && pitch % 8 == 0 && (dims == 2 || dims == 3), "upsample2x: bad arguments");
+  const long long total = (long long)N * (dims == 3 ? 2 * D : D) * 2 * H * 2 * W * (pitch / 8);
+  upsample2x_kernel<<<grid_for(total), 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), N, D, H, W, pitch / 8, dims,
+                                                        reinterpret_cast<uint4*>(y));
+  B200_LAUNCH_CHECK("upsample2x_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_avgpool2(const void* x, int32_t N, int32_t D, int32_t H, int32_t W, int32_t pitch, int32_t dims,
+                             void* y, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(x && y && pitch % 8 == 0 && (dims == 2 || dims == 3), "avgpool2: bad arguments");
+  const long long total = (long long)N * (dims == 3 ? D / 2 : D) * (H / 2) * (W / 2) * (pitch / 8);
+  if (total == 0) return B200_OK;
+  avgpool2_kernel<<<grid_for(total), 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), N, D, H, W, pitch / 8, dims,
+                                                      reinterpret_cast<uint4*>(y));
+  B200_LAUNCH_CHECK("avgpool2_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_axpy_bf16(const void* a, const void* b, float alpha, void* y, int64_t n, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(a && b && y && n % 8 == 0, "axpy_bf16: element count must be a multiple of 8");
+  if (n == 0) return B200_OK;
+  axpy_bf16_kernel<<<grid_for(n / 8), 256, 0, stream>>>(reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b),
+                                                       alpha, reinterpret_cast<uint4*>(y), n / 8);
+  B200_LAUNCH_CHECK("axpy_bf16_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_geglu(const void* x, int64_t M, int32_t H, int32_t x_pitch, void* y, int32_t y_pitch,
+                          void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(x && y && H % 8 == 0 && x_pitch % 8 == 0 && y_pitch % 8 == 0 && x_pitch >= 2 * H && y_pitch >= H,
+                 "geglu: bad arguments");
+  geglu_kernel<<<grid_for(M * (H / 8)), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), M, H, x_pitch,
+                                                         reinterpret_cast<__nv_bfloat16*>(y), y_pitch);
+  B200_LAUNCH_CHECK("geglu_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_softmax_rows(const float* s, int64_t M, int32_t S, int64_t s_pitch, void* p, int64_t p_pitch,
+                                 void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(s && p && M >= 1 && S >= 1 && s_pitch >= S && p_pitch >= S, "softmax_rows: bad arguments");
+  __nv_bfloat16* pp = reinterpret_cast<__nv_bfloat16*>(p);
+  if (S <= 1024) {
+    const long long blocks = (M + 7) / 8;
+    B200_CHECK_ARG(blocks < (1ll << 31), "softmax_rows: too many rows");
+    softmax_rows_kernel<32><<<(unsigned)blocks, 256, 0, stream>>>(s, M, S, s_pitch, pp, p_pitch);
+  } else {
+    B200_CHECK_ARG(M < (1ll << 31), "softmax_rows: too many rows");
+    softmax_rows_kernel<256><<<(unsigned)M, 256, 0, stream>>>(s, M, S, s_pitch, pp, p_pitch);
+  }
+  B200_LAUNCH_CHECK("softmax_rows_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_timestep_embedding(const float* t, int32_t N, int32_t dim, float max_period, float* emb,
+                                       void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(t && emb && N >= 1 && dim >= 1, "timestep_embedding: bad arguments");
+  timestep_embedding_kernel<<<(N * dim + 255) / 256, 256, 0, stream>>>(t, N, dim, max_period, emb);
+  B200_LAUNCH_CHECK("timestep_embedding_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_small_linear(const float* x, int32_t M, int32_t K, const float* W, const float* b, int32_t O,
+                                 int32_t act_in, int32_t act_out, float* y, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(x && W && y && M >= 1 && M <= 4096 && K >= 1 && O >= 1, "small_linear: bad arguments");
+  small_linear_kernel<<<(O + 7) / 8, 256, 0, stream>>>(x, M, K, W, b, O, act_in, act_out, y);
+  B200_LAUNCH_CHECK("small_linear_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_ddim_step(const float* model_out, const float* sample, const float* noise, const b200_ddim_coef* c,
+                              float* prev_sample, float* pred_x0, int64_t n, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(model_out && sample && c && prev_sample && n >= 1, "ddim_step: bad arguments");
+  ddim_step_kernel<<<grid_for(n), 256, 0, stream>>>(model_out, sample, noise, *c, prev_sample, pred_x0, n);
+  B200_LAUNCH_CHECK("ddim_step_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_ddpm_step(const float* model_out, const float* sample, const float* noise, const float* pred_var,
+                              const b200_ddpm_coef* c, float* prev_sample, float* pred_x0, int64_t n, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(model_out && sample && c && prev_sample && n >= 1, "ddpm_step: bad arguments");
+  B200_CHECK_ARG(c->var_mode == 0 || pred_var, "ddpm_step: learned variance needs pred_var");
+  ddpm_step_kernel<<<grid_for(n), 256, 0, stream>>>(model_out, sample, noise, pred_var, *c, prev_sample, pred_x0, n);
+  B200_LAUNCH_CHECK("ddpm_step_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_pndm_step(const float* const* hist, const float* sample, const b200_pndm_coef* c, float* prev_sample,
+                              float* eps_out, int64_t n, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(hist && c && c->n_hist >= 1 && c->n_hist <= 4 && n >= 1, "pndm_step: bad arguments");
+  B200_CHECK_ARG(prev_sample == nullptr || sample != nullptr, "pndm_step: prev_sample needs sample");
+  PndmPtrs hp;
+  for (int k = 0; k < 4; ++k) hp.h[k] = k < c->n_hist ? hist[k] : nullptr;
+  for (int k = 0; k < c->n_hist; ++k) B200_CHECK_ARG(hp.h[k], "pndm_step: null history tensor %d", k);
+  pndm_step_kernel<<<grid_for(n), 256, 0, stream>>>(hp, sample, *c, prev_sample, eps_out, n);
+  B200_LAUNCH_CHECK("pndm_step_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_add_noise(const float* x0, const float* noise, const float* ca, const float* cb, float sign_b,
+                              int32_t N, int64_t per_sample, float* out, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(x0 && noise && ca && cb && out && N >= 1 && N <= 65535 && per_sample >= 1, "add_noise: bad arguments");
+  dim3 grid(grid_for(per_sample, 256, 4), N);
+  add_noise_kernel<<<grid, 256, 0, stream>>>(x0, noise, ca, cb, sign_b, per_sample, out);
+  B200_LAUNCH_CHECK("add_noise_kernel");
+  return B200_OK;
+}

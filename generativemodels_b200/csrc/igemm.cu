@@ -1,0 +1,699 @@
+// Implicit-GEMM convolution / GEMM on Blackwell tcgen05 tensor cores.
+//
+// Replaces every dense contraction of the reference sampling path (the cuDNN / cuBLAS calls behind
+// monai Convolution, nn.Linear, torch.baddbmm/bmm — see include/b200gen.h for the call sites).
+//
+// Design (B200-first, not a translation of any library kernel):
+//   * activations live in HBM as channels-last bf16; a CTA tile is a BW x BH x BD box of 128 output
+//     voxels x BN output channels.  For every filter tap and every 64-channel chunk the producer
+//     thread issues ONE tiled-TMA box load of the shifted input box: out-of-range coordinates
+//     (the zero padding, ragged edges, channel tails) are zero-filled by the TMA unit, stride-2
+//     convolutions use the tensor map's traversal stride.  No im2col buffer ever exists.
+//   * the box lands in shared memory as a 128-row x 128-byte SWIZZLE_128B K-major tile — exactly the
+//     canonical UMMA operand layout — and one elected thread issues tcgen05.mma (M=128, N=BN, K=16)
+//     accumulating in TMEM.  Weights are a K-major [Cout][taps*Cin] bf16 matrix, also TMA-staged.
+//   * warp-specialised persistent kernel: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc),
+//     warps 2..5 = epilogue.  smem ring of STAGES {A,B} tiles (full/empty mbarriers), TMEM
+//     accumulator double-buffered (2 x BN columns) so the epilogue of tile i overlaps the main loop
+//     of tile i+1.
+//   * fused epilogue straight out of TMEM: +bias, +per-sample row vector (time embedding),
+//     activation, scale, +residual, activation, bf16/fp32 store with arbitrary voxel strides
+//     (so transposed-conv phases and channel-slice outputs need no extra pass).
+#include "common.cuh"
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <mutex>
+#include <stdlib.h>
+#include <string.h>
+
+namespace b200 {
+
+static constexpr int kBM = 128;           // rows (output voxels) per tile == UMMA_M
+static constexpr int kBK = 64;            // channels per K chunk == 128 bytes of bf16 == swizzle span
+static constexpr int kABytes = kBM * kBK * 2;
+static constexpr int kThreads = 192;      // 6 warps: TMA, MMA, 4 x epilogue
+
+struct SegDev {
+  int8_t src, dw, dh, dd;
+  uint16_t c0, nchunks;
+};
+
+struct IgemmDev {
+  alignas(64) CUtensorMap tmA[2];
+  alignas(64) CUtensorMap tmB;
+  // raw views for the cross-check kernel
+  const __nv_bfloat16* a_ptr[2];
+  int a_C[2], a_pitch[2];
+  int in_N, in_D, in_H, in_W;
+  const __nv_bfloat16* w_ptr;
+  int w_rows, w_K, w_pitch;
+  long long w_bstride;
+  int w_batched;
+  // geometry
+  int n_seg, num_k_chunks;
+  int sd, sh, sw;
+  int N, OD, OH, OW;
+  int BW, BH, BD, bw_log2, bh_log2;
+  int tiles_w, tiles_h, tiles_d, tiles_n, num_tiles;
+  // epilogue
+  void* out_ptr;
+  int out_dtype, cout, out_cols, out_vec;
+  long long out_sN, out_sD, out_sH, out_sW;
+  const float* bias;
+  const float* rowvec;
+  long long rowvec_bstride;
+  const float* row_bias;
+  int act1, act2;
+  float scale;
+  const void* res_ptr;
+  int res_dtype, res_vec;
+  long long res_sN, res_sD, res_sH, res_sW;
+  SegDev seg[B200_IGEMM_MAX_SEG];
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c0,
+                                            int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c0,
+                                            int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4, [16,30) leading byte offset >> 4 (unused for swizzled K-major: 1),
+//   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024), [46,48) version = 1, [61,64) layout = 2.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// kind::f16 instruction descriptor: c=f32 (bit4), a=bf16 (bit7), b=bf16 (bit10), K-major both,
+// N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
+         (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------
+// Fused epilogue for CH consecutive columns of one output row (shared by both kernels).
+// ------------------------------------------------------------------------------------------------
+template <int CH>
+__device__ __forceinline__ void epilogue_row(const IgemmDev& p, float* v, int nb, int ow, long long out_off,
+                                             long long res_off, int col0) {
+  // bias + per-sample row vector (+ per-row bias for transposed-operand GEMMs)
+  const float rb = p.row_bias ? __ldg(p.row_bias + ow) : 0.f;
+#pragma unroll
+  for (int j = 0; j < CH; ++j) {
+    int col = col0 + j;
+    float add = rb;
+    if (col < p.cout) {
+      if (p.bias) add += __ldg(p.bias + col);
+      if (p.rowvec) add += __ldg(p.rowvec + (long long)nb * p.rowvec_bstride + col);
+    }
+    float x = v[j] + add;
+    x = apply_act(x, p.act1);
+    v[j] = x * p.scale;
+  }
+  if (p.res_ptr) {
+    if (p.res_dtype == B200_DT_BF16) {
+      const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(p.res_ptr) + res_off + col0;
+      if (p.res_vec) {
+#pragma unroll
+        for (int g = 0; g < CH / 8; ++g) {
+          if (col0 + g * 8 < p.out_cols) {
+            uint4 t = __ldg(reinterpret_cast<const uint4*>(r + g * 8));
+            float f[8];
+            unpack8(t, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[g * 8 + j] += f[j];
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < CH; ++j)
+          if (col0 + j < p.out_cols) v[j] += __bfloat162float(r[j]);
+      }
+    } else {
+      const float* r = reinterpret_cast<const float*>(p.res_ptr) + res_off + col0;
+      if (p.res_vec) {
+#pragma unroll
+        for (int g = 0; g < CH / 4; ++g) {
+          if (col0 + g * 4 < p.out_cols) {
+            float4 t = __ldg(reinterpret_cast<const float4*>(r + g * 4));
+            v[g * 4 + 0] += t.x; v[g * 4 + 1] += t.y; v[g * 4 + 2] += t.z; v[g * 4 + 3] += t.w;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < CH; ++j)
+          if (col0 + j < p.out_cols) v[j] += r[j];
+      }
+    }
+  }
+  if (p.act2 != B200_ACT_NONE) {
+#pragma unroll
+    for (int j = 0; j < CH; ++j) v[j] = apply_act(v[j], p.act2);
+  }
+  // columns in [cout, out_cols) are padding: force exact zeros
+#pragma unroll
+  for (int j = 0; j < CH; ++j)
+    if (col0 + j >= p.cout) v[j] = 0.f;
+
+  if (p.out_dtype == B200_DT_BF16) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out_ptr) + out_off + col0;
+    if (p.out_vec) {
+#pragma unroll
+      for (int g = 0; g < CH / 8; ++g)
+        if (col0 + g * 8 < p.out_cols) *reinterpret_cast<uint4*>(o + g * 8) = pack8(v + g * 8);
+    } else {
+#pragma unroll
+      for (int j = 0; j < CH; ++j)
+        if (col0 + j < p.out_cols) o[j] = __float2bfloat16_rn(v[j]);
+    }
+  } else {
+    float* o = reinterpret_cast<float*>(p.out_ptr) + out_off + col0;
+    if (p.out_vec) {
+#pragma unroll
+      for (int g = 0; g < CH / 4; ++g)
+        if (col0 + g * 4 < p.out_cols)
+          *reinterpret_cast<float4*>(o + g * 4) =
+              make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < CH; ++j)
+        if (col0 + j < p.out_cols) o[j] = v[j];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The tcgen05 kernel
+// ------------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_constant__ IgemmDev p) {
+  constexpr int kBBytes = BN * kBK * 2;
+  constexpr int kStageBytes = kABytes + kBBytes;
+  constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;   // power of two for BN in {16..256}
+  constexpr int CH = (BN >= 32) ? 32 : 16;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "r"((uint32_t)kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int num_k = p.num_k_chunks;
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        int t = tile;
+        const int nt = t % p.tiles_n; t /= p.tiles_n;
+        const int wt = t % p.tiles_w; t /= p.tiles_w;
+        const int ht = t % p.tiles_h; t /= p.tiles_h;
+        const int dt = t % p.tiles_d; t /= p.tiles_d;
+        const int nb = t;
+        const int iw0 = wt * p.BW * p.sw, ih0 = ht * p.BH * p.sh, id0 = dt * p.BD * p.sd;
+        const int n0 = nt * BN;
+        const int wb = p.w_batched ? nb : 0;
+        int kglob = 0;
+        for (int s = 0; s < p.n_seg; ++s) {
+          const SegDev sg = p.seg[s];
+          const CUtensorMap* tm = &p.tmA[sg.src];
+          const int cw = iw0 + sg.dw, ch = ih0 + sg.dh, cd = id0 + sg.dd;
+          for (int c = 0; c < sg.nchunks; ++c, ++kglob) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t a_dst = smem_base + stage * kStageBytes;
+            mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
+            tma_load_5d(tm, full_bar(stage), a_dst, (sg.c0 + c) * kBK, cw, ch, cd, nb);
+            tma_load_3d(&p.tmB, full_bar(stage), a_dst + kABytes, kglob * kBK, n0, wb);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(kBM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(tempty_bar(buf), acc_phase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * BN;
+        for (int k = 0; k < num_k; ++k) {
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_base + stage * kStageBytes;
+          const uint64_t adesc = make_smem_desc(a_addr);
+          const uint64_t bdesc = make_smem_desc(a_addr + kABytes);
+#pragma unroll
+          for (int kk = 0; kk < kBK / 16; ++kk) {
+            // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in >>4 units
+            umma_bf16(d_tmem, adesc + 2u * kk, bdesc + 2u * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+          }
+          tcgen05_commit(empty_bar(stage));
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        tcgen05_commit(tfull_bar(buf));
+      }
+    }
+  } else {
+    // ============================== epilogue warps ==============================
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int r = q * 32 + lane;            // row of the tile
+    const int rw = r & (p.BW - 1);
+    const int rh = (r >> p.bw_log2) & (p.BH - 1);
+    const int rd = r >> (p.bw_log2 + p.bh_log2);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      int t = tile;
+      const int nt = t % p.tiles_n; t /= p.tiles_n;
+      const int wt = t % p.tiles_w; t /= p.tiles_w;
+      const int ht = t % p.tiles_h; t /= p.tiles_h;
+      const int dt = t % p.tiles_d; t /= p.tiles_d;
+      const int nb = t;
+      const int ow = wt * p.BW + rw, oh = ht * p.BH + rh, od = dt * p.BD + rd;
+      const bool row_ok = (ow < p.OW) && (oh < p.OH) && (od < p.OD);
+      const long long out_off = nb * p.out_sN + od * p.out_sD + oh * p.out_sH + ow * p.out_sW;
+      const long long res_off = nb * p.res_sN + od * p.res_sD + oh * p.res_sH + ow * p.res_sW;
+      const int n0 = nt * BN;
+
+      const int buf = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(tfull_bar(buf), acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += CH) {
+        uint32_t raw[CH];
+        if constexpr (CH == 32) tmem_ld32(taddr + c0, raw);
+        else tmem_ld16(taddr + c0, raw);
+        tmem_ld_wait();
+        if (row_ok && n0 + c0 < p.out_cols) {
+          float v[CH];
+#pragma unroll
+          for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(raw[j]);
+          epilogue_row<CH>(p, v, nb, ow, out_off, res_off, n0 + c0);
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(buf));
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)kTmemCols)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CUDA-core cross-check kernel: same parameters, same zero-fill semantics, same epilogue.
+// One thread per (output voxel, 16-column group).  Used by tests and for debugging only.
+// ------------------------------------------------------------------------------------------------
+__global__ void igemm_check_kernel(const __grid_constant__ IgemmDev p) {
+  const long long rows = (long long)p.N * p.OD * p.OH * p.OW;
+  const int col_groups = (p.out_cols + 15) / 16;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * col_groups) return;
+  const int cg = (int)(idx % col_groups);
+  long long m = idx / col_groups;
+  const int ow = (int)(m % p.OW); m /= p.OW;
+  const int oh = (int)(m % p.OH); m /= p.OH;
+  const int od = (int)(m % p.OD); m /= p.OD;
+  const int nb = (int)m;
+  float acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+  const int wb = p.w_batched ? nb : 0;
+  const __nv_bfloat16* wbase = p.w_ptr + (long long)wb * p.w_bstride;
+  int kglob = 0;
+  for (int s = 0; s < p.n_seg; ++s) {
+    const SegDev sg = p.seg[s];
+    const int iw = ow * p.sw + sg.dw, ih = oh * p.sh + sg.dh, id = od * p.sd + sg.dd;
+    const bool inb = iw >= 0 && iw < p.in_W && ih >= 0 && ih < p.in_H && id >= 0 && id < p.in_D;
+    const __nv_bfloat16* a = p.a_ptr[sg.src] +
+        ((((long long)nb * p.in_D + id) * p.in_H + ih) * p.in_W + iw) * p.a_pitch[sg.src];
+    for (int c = 0; c < sg.nchunks; ++c, ++kglob) {
+      if (!inb) continue;
+      for (int e = 0; e < kBK; ++e) {
+        const int ch = (sg.c0 + c) * kBK + e;
+        const int kk = kglob * kBK + e;
+        if (ch >= p.a_C[sg.src] || kk >= p.w_K) break;
+        const float av = __bfloat162float(a[ch]);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int col = cg * 16 + j;
+          if (col < p.w_rows) acc[j] += av * __bfloat162float(wbase[(long long)col * p.w_pitch + kk]);
+        }
+      }
+    }
+  }
+  const long long out_off = nb * p.out_sN + od * p.out_sD + oh * p.out_sH + ow * p.out_sW;
+  const long long res_off = nb * p.res_sN + od * p.res_sD + oh * p.res_sH + ow * p.res_sW;
+  epilogue_row<16>(p, acc, nb, ow, out_off, res_off, cg * 16);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled g_encode = nullptr;
+static std::once_flag g_encode_once;
+
+static void load_encode() {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+      qres == cudaDriverEntryPointSuccess)
+    g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
+}
+
+static int ilog2(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+
+struct TileShape { int bw, bh, bd; };
+
+// choose the 128-voxel box that wastes the fewest rows on this output extent
+static TileShape choose_tile(int OW, int OH, int OD, int sw, int sh, int sd) {
+  static const TileShape cands[] = {{128, 1, 1}, {64, 2, 1}, {32, 4, 1}, {16, 8, 1}, {8, 16, 1},
+                                    {4, 32, 1},  {32, 2, 2}, {16, 4, 2}, {8, 8, 2},  {16, 2, 4},
+                                    {8, 4, 4},   {4, 8, 4},  {4, 4, 8},  {8, 2, 8},  {2, 8, 8},
+                                    {4, 2, 16},  {2, 4, 16}, {2, 2, 32}, {1, 1, 128}, {1, 128, 1},
+                                    {2, 64, 1},  {1, 8, 16}, {1, 16, 8}};
+  double best = 1e30;
+  TileShape bt = cands[0];
+  for (const TileShape& c : cands) {
+    if (c.bw * sw > 256 || c.bh * sh > 256 || c.bd * sd > 256) continue;
+    double tw = (double)((OW + c.bw - 1) / c.bw) * c.bw;
+    double th = (double)((OH + c.bh - 1) / c.bh) * c.bh;
+    double td = (double)((OD + c.bd - 1) / c.bd) * c.bd;
+    double cost = tw * th * td;
+    // prefer long contiguous runs along W on ties
+    cost *= (1.0 + 1e-3 * (7 - ilog2(c.bw)));
+    if (cost < best) { best = cost; bt = c; }
+  }
+  return bt;
+}
+
+template <int BN, int STAGES>
+static int launch_tc(const IgemmDev& d, cudaStream_t stream) {
+  constexpr int kStageBytes = kABytes + BN * kBK * 2;
+  constexpr int smem = STAGES * kStageBytes + 1024 + 256;
+  static bool attr_done = false;
+  if (!attr_done) {
+    B200_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   smem));
+    attr_done = true;
+  }
+  int grid = d.num_tiles < sm_count() ? d.num_tiles : sm_count();
+  igemm_tc_kernel<BN, STAGES><<<grid, kThreads, smem, stream>>>(d);
+  B200_LAUNCH_CHECK("igemm_tc_kernel");
+  return B200_OK;
+}
+
+static int env_impl() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200_IGEMM_IMPL");
+    v = (e && strcmp(e, "check") == 0) ? 1 : 0;
+  }
+  return v;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_igemm(const b200_igemm_params* p, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(p != nullptr, "igemm: null params");
+  B200_CHECK_ARG(p->a_ptr[0] && p->w_ptr && p->out_ptr, "igemm: null tensor pointer");
+  B200_CHECK_ARG(p->n_seg >= 1 && p->n_seg <= B200_IGEMM_MAX_SEG, "igemm: n_seg=%d out of range", p->n_seg);
+  B200_CHECK_ARG(p->in_N >= 1 && p->in_D >= 1 && p->in_H >= 1 && p->in_W >= 1, "igemm: bad input extent");
+  B200_CHECK_ARG(p->out_N == p->in_N && p->out_D >= 1 && p->out_H >= 1 && p->out_W >= 1, "igemm: bad output extent");
+  B200_CHECK_ARG(p->cout >= 1 && p->out_cols >= p->cout, "igemm: bad cout/out_cols");
+  B200_CHECK_ARG(p->w_pitch % 8 == 0 && p->w_rows >= 1, "igemm: weight pitch must be a multiple of 8");
+  B200_CHECK_ARG(((uintptr_t)p->w_ptr & 15) == 0, "igemm: weight pointer not 16-byte aligned");
+  B200_CHECK_ARG(p->stride_d >= 1 && p->stride_d <= 8 && p->stride_h >= 1 && p->stride_h <= 8 &&
+                 p->stride_w >= 1 && p->stride_w <= 8, "igemm: stride out of range");
+  for (int s = 0; s < 2; ++s) {
+    if (!p->a_ptr[s]) continue;
+    B200_CHECK_ARG(p->a_pitch[s] % 8 == 0 && p->a_C[s] >= 1 && p->a_C[s] <= p->a_pitch[s],
+                   "igemm: source %d channel pitch %d / extent %d invalid", s, p->a_pitch[s], p->a_C[s]);
+    B200_CHECK_ARG(((uintptr_t)p->a_ptr[s] & 15) == 0, "igemm: source %d not 16-byte aligned", s);
+  }
+  std::call_once(g_encode_once, load_encode);
+  if (!g_encode) { set_error("igemm: cuTensorMapEncodeTiled entry point unavailable"); return B200_ECUDA; }
+
+  IgemmDev d;
+  memset(&d, 0, sizeof(d));
+  int kchunks = 0;
+  for (int s = 0; s < p->n_seg; ++s) {
+    const b200_igemm_seg& sg = p->seg[s];
+    B200_CHECK_ARG(sg.src == 0 || (sg.src == 1 && p->a_ptr[1]), "igemm: segment %d uses missing source", s);
+    B200_CHECK_ARG(sg.nchunks >= 1, "igemm: segment %d has no chunks", s);
+    d.seg[s].src = sg.src; d.seg[s].dw = sg.dw; d.seg[s].dh = sg.dh; d.seg[s].dd = sg.dd;
+    d.seg[s].c0 = sg.c0; d.seg[s].nchunks = sg.nchunks;
+    kchunks += sg.nchunks;
+  }
+  const int w_K = p->w_K > 0 ? p->w_K : p->w_pitch;   // K elements past w_K read as zero
+  B200_CHECK_ARG(w_K <= p->w_pitch, "igemm: w_K %d exceeds the row pitch %d", w_K, p->w_pitch);
+  d.n_seg = p->n_seg;
+  d.num_k_chunks = kchunks;
+  for (int s = 0; s < 2; ++s) {
+    d.a_ptr[s] = reinterpret_cast<const __nv_bfloat16*>(p->a_ptr[s]);
+    d.a_C[s] = p->a_C[s];
+    d.a_pitch[s] = p->a_pitch[s];
+  }
+  d.in_N = p->in_N; d.in_D = p->in_D; d.in_H = p->in_H; d.in_W = p->in_W;
+  d.w_ptr = reinterpret_cast<const __nv_bfloat16*>(p->w_ptr);
+  d.w_rows = p->w_rows; d.w_K = w_K; d.w_pitch = p->w_pitch;
+  d.w_bstride = p->w_bstride; d.w_batched = p->w_batched;
+  d.sd = p->stride_d; d.sh = p->stride_h; d.sw = p->stride_w;
+  d.N = p->out_N; d.OD = p->out_D; d.OH = p->out_H; d.OW = p->out_W;
+  d.out_ptr = p->out_ptr; d.out_dtype = p->out_dtype; d.cout = p->cout; d.out_cols = p->out_cols;
+  d.out_sN = p->out_sN; d.out_sD = p->out_sD; d.out_sH = p->out_sH; d.out_sW = p->out_sW;
+  d.bias = p->bias; d.rowvec = p->rowvec; d.rowvec_bstride = p->rowvec_bstride; d.row_bias = p->row_bias;
+  d.act1 = p->act1; d.act2 = p->act2; d.scale = p->scale;
+  d.res_ptr = p->res_ptr; d.res_dtype = p->res_dtype;
+  d.res_sN = p->res_sN; d.res_sD = p->res_sD; d.res_sH = p->res_sH; d.res_sW = p->res_sW;
+  {
+    const int g = (p->out_dtype == B200_DT_BF16) ? 8 : 4;
+    const int esz = (p->out_dtype == B200_DT_BF16) ? 2 : 4;
+    d.out_vec = (p->out_cols % g == 0) && (p->out_sN % g == 0) && (p->out_sD % g == 0) &&
+                (p->out_sH % g == 0) && (p->out_sW % g == 0) && (((uintptr_t)p->out_ptr) % 16 == 0);
+    (void)esz;
+  }
+  if (p->res_ptr) {
+    const int g = (p->res_dtype == B200_DT_BF16) ? 8 : 4;
+    d.res_vec = (p->out_cols % g == 0) && (p->res_sN % g == 0) && (p->res_sD % g == 0) &&
+                (p->res_sH % g == 0) && (p->res_sW % g == 0) && (((uintptr_t)p->res_ptr) % 16 == 0);
+  }
+
+  const int impl = p->impl ? p->impl : env_impl();
+  if (impl == 1) {
+    const long long rows = (long long)d.N * d.OD * d.OH * d.OW;
+    const long long total = rows * ((d.out_cols + 15) / 16);
+    const int threads = 128;
+    const long long blocks = (total + threads - 1) / threads;
+    B200_CHECK_ARG(blocks < (1ll << 31), "igemm(check): problem too large");
+    igemm_check_kernel<<<(unsigned)blocks, threads, 0, stream>>>(d);
+    B200_LAUNCH_CHECK("igemm_check_kernel");
+    return B200_OK;
+  }
+
+  // ---- tile geometry ----
+  const TileShape ts = choose_tile(d.OW, d.OH, d.OD, d.sw, d.sh, d.sd);
+  d.BW = ts.bw; d.BH = ts.bh; d.BD = ts.bd;
+  d.bw_log2 = ilog2(ts.bw); d.bh_log2 = ilog2(ts.bh);
+  d.tiles_w = (d.OW + ts.bw - 1) / ts.bw;
+  d.tiles_h = (d.OH + ts.bh - 1) / ts.bh;
+  d.tiles_d = (d.OD + ts.bd - 1) / ts.bd;
+  const long long m_tiles = (long long)d.tiles_w * d.tiles_h * d.tiles_d * d.N;
+
+  // N tile: as wide as the output needs, but narrower when the grid would not fill the SMs
+  const int cols16 = ((p->out_cols + 15) / 16) * 16;
+  int BN = cols16 <= 16 ? 16 : cols16 <= 32 ? 32 : cols16 <= 64 ? 64 : cols16 <= 128 ? 128 : 256;
+  while (BN > 64 && m_tiles * ((cols16 + BN - 1) / BN) < sm_count() && kchunks >= 8) BN >>= 1;
+  d.tiles_n = (cols16 + BN - 1) / BN;
+  const long long ntiles = m_tiles * d.tiles_n;
+  B200_CHECK_ARG(ntiles < (1ll << 31), "igemm: too many tiles");
+  d.num_tiles = (int)ntiles;
+
+  // ---- tensor maps ----
+  for (int s = 0; s < 2; ++s) {
+    if (!p->a_ptr[s]) continue;
+    cuuint64_t dims[5] = {(cuuint64_t)p->a_C[s], (cuuint64_t)p->in_W, (cuuint64_t)p->in_H,
+                          (cuuint64_t)p->in_D, (cuuint64_t)p->in_N};
+    const cuuint64_t pb = (cuuint64_t)p->a_pitch[s] * 2;
+    cuuint64_t strides[4] = {pb, pb * p->in_W, pb * p->in_W * p->in_H,
+                             pb * p->in_W * p->in_H * p->in_D};
+    cuuint32_t box[5] = {(cuuint32_t)kBK, (cuuint32_t)(ts.bw * d.sw), (cuuint32_t)(ts.bh * d.sh),
+                         (cuuint32_t)(ts.bd * d.sd), 1};
+    cuuint32_t estr[5] = {1, (cuuint32_t)d.sw, (cuuint32_t)d.sh, (cuuint32_t)d.sd, 1};
+    CUresult r = g_encode(&d.tmA[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(p->a_ptr[s]),
+                          dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("igemm: cuTensorMapEncodeTiled(A%d) failed with %d (C=%d pitch=%d in=%dx%dx%dx%d box=%ux%ux%u)",
+                s, (int)r, p->a_C[s], p->a_pitch[s], p->in_N, p->in_D, p->in_H, p->in_W, box[1], box[2], box[3]);
+      return B200_ECUDA;
+    }
+  }
+  if (!p->a_ptr[1]) d.tmA[1] = d.tmA[0];
+  {
+    const int wbn = p->w_batched ? p->in_N : 1;
+    cuuint64_t dims[3] = {(cuuint64_t)w_K, (cuuint64_t)p->w_rows, (cuuint64_t)wbn};
+    cuuint64_t bs = p->w_bstride ? (cuuint64_t)p->w_bstride * 2 : (cuuint64_t)p->w_rows * p->w_pitch * 2;
+    cuuint64_t strides[2] = {(cuuint64_t)p->w_pitch * 2, bs};
+    B200_CHECK_ARG(bs % 16 == 0, "igemm: weight batch stride not 16-byte aligned");
+    cuuint32_t box[3] = {(cuuint32_t)kBK, (cuuint32_t)BN, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode(&d.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(p->w_ptr), dims,
+                          strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("igemm: cuTensorMapEncodeTiled(W) failed with %d (K=%d rows=%d pitch=%d)", (int)r, w_K,
+                p->w_rows, p->w_pitch);
+      return B200_ECUDA;
+    }
+  }
+
+  switch (BN) {
+    case 16:  return launch_tc<16, 8>(d, stream);
+    case 32:  return launch_tc<32, 8>(d, stream);
+    case 64:  return launch_tc<64, 8>(d, stream);
+    case 128: return launch_tc<128, 6>(d, stream);
+    default:  return launch_tc<256, 4>(d, stream);
+  }
+}

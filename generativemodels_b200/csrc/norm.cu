@@ -1,0 +1,307 @@
+// GroupNorm (+SiLU) and LayerNorm on channels-last bf16 (HBM-bound; 128-bit coalesced accesses).
+//
+// Reference arithmetic: nn.GroupNorm(num_groups, C, eps, affine=True) followed by nn.SiLU in
+// ResnetBlock.forward (diffusion_model_unet.py:669-696), AttentionBlock (372, 418-422), the output head
+// (1853-1855) and the AutoencoderKL ResBlock/AttentionBlock (autoencoderkl.py:139-146, 229); nn.LayerNorm in
+// BasicTransformerBlock (diffusion_model_unet.py:221-223).
+//
+// GroupNorm is split in two phases so that neither pass re-reads more than it must:
+//   stats : every block reduces a slab of voxels to per-channel (sum, sumsq) partials in fp32;
+//           a tiny finalize kernel folds partials -> group mean / rstd in fp64 and emits the per-(n, c)
+//           affine pair a = rstd * gamma, b = beta - mean * a.
+//   apply : y = silu(a * x + b), one read + one write, optionally reading a virtual concat of two tensors
+//           (the up-path torch.cat at diffusion_model_unet.py:1232/1340/1461 is never materialised raw).
+#include "common.cuh"
+
+namespace b200 {
+
+static constexpr int kGnMaxChunks = 512;
+
+// ---- stats --------------------------------------------------------------------------------------
+// grid = (chunks, N); block = CV * rows threads, CV = C_total / VEC channel vectors.
+template <int VEC>
+__global__ void gn_partial_kernel(const __nv_bfloat16* __restrict__ x0, const __nv_bfloat16* __restrict__ x1,
+                                  int C0, int C1, int pitch0, int pitch1, long long spatial,
+                                  long long vox_per_chunk, float* __restrict__ partial) {
+  const int C = C0 + C1;
+  const int CV = C / VEC;
+  const int rows = blockDim.x / CV;
+  const int cv = threadIdx.x % CV;
+  const int row = threadIdx.x / CV;
+  const int n = blockIdx.y;
+  const int chunk = blockIdx.x;
+  const long long s0 = (long long)chunk * vox_per_chunk;
+  long long s1 = s0 + vox_per_chunk;
+  if (s1 > spatial) s1 = spatial;
+
+  const int c = cv * VEC;
+  const __nv_bfloat16* src;
+  int pitch;
+  int cc;
+  if (c < C0) { src = x0; pitch = pitch0; cc = c; }
+  else        { src = x1; pitch = pitch1; cc = c - C0; }
+  src += (long long)n * spatial * pitch + cc;
+
+  float sum[VEC], sq[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) { sum[j] = 0.f; sq[j] = 0.f; }
+
+  if (row < rows) {
+    for (long long s = s0 + row; s < s1; s += rows) {
+      float f[VEC];
+      if constexpr (VEC == 8) {
+        uint4 v = __ldg(reinterpret_cast<const uint4*>(src + s * pitch));
+        unpack8(v, f);
+      } else {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) f[j] = __bfloat162float(src[s * pitch + j]);
+      }
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) { sum[j] += f[j]; sq[j] = fmaf(f[j], f[j], sq[j]); }
+    }
+  }
+  // reduce the `rows` threads that share a channel vector through shared memory
+  extern __shared__ float sm[];   // [rows][C][2]
+  if (row < rows) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      sm[((long long)row * C + c + j) * 2 + 0] = sum[j];
+      sm[((long long)row * C + c + j) * 2 + 1] = sq[j];
+    }
+  }
+  __syncthreads();
+  float* out = partial + (((long long)n * gridDim.x + chunk) * C) * 2;
+  for (int i = threadIdx.x; i < C * 2; i += blockDim.x) {
+    float acc = 0.f;
+    for (int r = 0; r < rows; ++r) acc += sm[(long long)r * C * 2 + i];
+    out[i] = acc;
+  }
+}
+
+// grid = (groups, N); folds the partials of one group in fp64 and writes the affine pairs.
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, int chunks, int C, int groups,
+                                   long long spatial, float eps, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ affine) {
+  const int g = blockIdx.x, n = blockIdx.y;
+  const int cpg = C / groups;
+  double s = 0.0, q = 0.0;
+  for (int i = threadIdx.x; i < chunks * cpg; i += blockDim.x) {
+    const int ch = i / cpg, c = g * cpg + i % cpg;
+    const float* p = partial + (((long long)n * chunks + ch) * C + c) * 2;
+    s += (double)p[0];
+    q += (double)p[1];
+  }
+  __shared__ double ss[32], sq[32];
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { ss[w] = s; sq[w] = q; }
+  __syncthreads();
+  if (w == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    s = l < nw ? ss[l] : 0.0;
+    q = l < nw ? sq[l] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (l == 0) { ss[0] = s; sq[0] = q; }
+  }
+  __syncthreads();
+  const double cnt = (double)spatial * cpg;
+  const double mean = ss[0] / cnt;
+  double var = sq[0] / cnt - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  for (int j = threadIdx.x; j < cpg; j += blockDim.x) {
+    const int c = g * cpg + j;
+    const float a = rstd * gamma[c];
+    affine[((long long)n * C + c) * 2 + 0] = a;
+    affine[((long long)n * C + c) * 2 + 1] = beta[c] - (float)mean * a;
+  }
+}
+
+// ---- apply --------------------------------------------------------------------------------------
+// grid = (blocks, N); grid-stride over (voxel, channel-vector) of one sample.
+template <int VEC>
+__global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, const __nv_bfloat16* __restrict__ x1,
+                                int C0, int C1, int pitch0, int pitch1, long long spatial,
+                                const float* __restrict__ affine, int act, __nv_bfloat16* __restrict__ y,
+                                int y_pitch) {
+  extern __shared__ float sm[];   // [C][2]
+  const int C = C0 + C1;
+  const int n = blockIdx.y;
+  for (int i = threadIdx.x; i < C * 2; i += blockDim.x) sm[i] = affine[(long long)n * C * 2 + i];
+  __syncthreads();
+  const int CV = C / VEC;
+  const long long total = spatial * CV;
+  const __nv_bfloat16* b0 = x0 + (long long)n * spatial * pitch0;
+  const __nv_bfloat16* b1 = x1 ? x1 + (long long)n * spatial * pitch1 : nullptr;
+  __nv_bfloat16* by = y + (long long)n * spatial * y_pitch;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long s = idx / CV;
+    const int c = (int)(idx % CV) * VEC;
+    const __nv_bfloat16* src = (c < C0) ? b0 + s * pitch0 + c : b1 + s * pitch1 + (c - C0);
+    float f[VEC];
+    if constexpr (VEC == 8) {
+      uint4 v = __ldg(reinterpret_cast<const uint4*>(src));
+      unpack8(v, f);
+    } else {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) f[j] = __bfloat162float(src[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      float t = fmaf(f[j], sm[(c + j) * 2], sm[(c + j) * 2 + 1]);
+      f[j] = (act == B200_ACT_SILU) ? silu_f(t) : t;
+    }
+    __nv_bfloat16* dst = by + s * y_pitch + c;
+    if constexpr (VEC == 8) {
+      *reinterpret_cast<uint4*>(dst) = pack8(f);
+    } else {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) dst[j] = __float2bfloat16_rn(f[j]);
+    }
+  }
+}
+
+// zero the pad channels [C, pitch) of a channels-last tensor (only when pitch > C)
+__global__ void zero_pad_channels_kernel(__nv_bfloat16* y, long long rows, int C, int pitch) {
+  const int padw = pitch - C;
+  const long long total = rows * padw;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    y[(idx / padw) * pitch + C + idx % padw] = __float2bfloat16_rn(0.f);
+  }
+}
+
+// ---- LayerNorm: one warp per row ----------------------------------------------------------------
+__global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long M, int C, int x_pitch,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                 __nv_bfloat16* __restrict__ y, int y_pitch) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  const __nv_bfloat16* xr = x + row * x_pitch;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += __bfloat162float(xr[c]);
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float d = __bfloat162float(xr[c]) - mean;
+    q = fmaf(d, d, q);
+  }
+  const float rstd = rsqrtf(warp_sum(q) / C + eps);
+  __nv_bfloat16* yr = y + row * y_pitch;
+  for (int c = lane; c < C; c += 32) {
+    const float v = (__bfloat162float(xr[c]) - mean) * rstd * gamma[c] + beta[c];
+    yr[c] = __float2bfloat16_rn(v);
+  }
+  for (int c = C + lane; c < y_pitch; c += 32) yr[c] = __float2bfloat16_rn(0.f);
+}
+
+static int gn_chunks(int N, long long spatial, int rows) {
+  long long want = (4ll * sm_count() + N - 1) / N;
+  long long maxc = (spatial + rows * 8 - 1) / (rows * 8);   // at least 8 iterations per thread
+  if (maxc < 1) maxc = 1;
+  long long c = want < maxc ? want : maxc;
+  if (c > kGnMaxChunks) c = kGnMaxChunks;
+  if (c < 1) c = 1;
+  return (int)c;
+}
+
+static void gn_block_shape(int C, bool vec_ok, int& vec, int& cv, int& rows) {
+  vec = vec_ok ? 8 : 1;
+  cv = C / vec;
+  rows = 256 / cv;
+  if (rows < 1) rows = 1;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int64_t b200_groupnorm_workspace_bytes(int32_t N, int64_t spatial, int32_t C_total) {
+  (void)spatial;
+  return (int64_t)N * kGnMaxChunks * C_total * 2 * sizeof(float);
+}
+
+extern "C" int b200_groupnorm_stats(const b200_gn_stats_params* p, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(p && p->x_ptr[0] && p->gamma && p->beta && p->partial && p->affine, "gn_stats: null pointer");
+  const int C0 = p->x_C[0], C1 = p->x_ptr[1] ? p->x_C[1] : 0;
+  const int C = C0 + C1;
+  B200_CHECK_ARG(p->groups >= 1 && C % p->groups == 0, "gn_stats: %d channels not divisible by %d groups", C, p->groups);
+  B200_CHECK_ARG(p->N >= 1 && p->spatial >= 1, "gn_stats: empty input");
+  int vec, cv, rows;
+  const bool vec_ok = C0 % 8 == 0 && C1 % 8 == 0 && p->x_pitch[0] % 8 == 0 && (C1 == 0 || p->x_pitch[1] % 8 == 0) &&
+                      ((uintptr_t)p->x_ptr[0] % 16 == 0) && (C1 == 0 || (uintptr_t)p->x_ptr[1] % 16 == 0);
+  gn_block_shape(C, vec_ok, vec, cv, rows);
+  B200_CHECK_ARG(cv <= 1024, "gn_stats: too many channels (%d)", C);
+  const int chunks = gn_chunks(p->N, p->spatial, rows);
+  const long long vpc = (p->spatial + chunks - 1) / chunks;
+  const int threads = cv * rows;
+  const size_t smem = (size_t)rows * C * 2 * sizeof(float);
+  dim3 grid(chunks, p->N);
+  const __nv_bfloat16* x0 = reinterpret_cast<const __nv_bfloat16*>(p->x_ptr[0]);
+  const __nv_bfloat16* x1 = reinterpret_cast<const __nv_bfloat16*>(p->x_ptr[1]);
+  if (vec == 8)
+    gn_partial_kernel<8><<<grid, threads, smem, stream>>>(x0, x1, C0, C1, p->x_pitch[0], p->x_pitch[1], p->spatial, vpc, p->partial);
+  else
+    gn_partial_kernel<1><<<grid, threads, smem, stream>>>(x0, x1, C0, C1, p->x_pitch[0], p->x_pitch[1], p->spatial, vpc, p->partial);
+  B200_LAUNCH_CHECK("gn_partial_kernel");
+  gn_finalize_kernel<<<dim3(p->groups, p->N), 128, 0, stream>>>(p->partial, chunks, C, p->groups, p->spatial, p->eps,
+                                                                p->gamma, p->beta, p->affine);
+  B200_LAUNCH_CHECK("gn_finalize_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_groupnorm_apply(const b200_gn_apply_params* p, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(p && p->x_ptr[0] && p->affine && p->y_ptr, "gn_apply: null pointer");
+  const int C0 = p->x_C[0], C1 = p->x_ptr[1] ? p->x_C[1] : 0;
+  const int C = C0 + C1;
+  B200_CHECK_ARG(p->y_pitch >= C, "gn_apply: y_pitch %d < C %d", p->y_pitch, C);
+  const int vec = (C0 % 8 == 0 && C1 % 8 == 0 && p->x_pitch[0] % 8 == 0 && (C1 == 0 || p->x_pitch[1] % 8 == 0) &&
+                   p->y_pitch % 8 == 0 && ((uintptr_t)p->x_ptr[0] % 16 == 0) &&
+                   (C1 == 0 || (uintptr_t)p->x_ptr[1] % 16 == 0) && ((uintptr_t)p->y_ptr % 16 == 0)) ? 8 : 1;
+  const long long total = p->spatial * (C / vec);
+  long long blocks = (total + 255) / 256;
+  const long long cap = (8ll * sm_count() + p->N - 1) / p->N;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  dim3 grid((unsigned)blocks, p->N);
+  const size_t smem = (size_t)C * 2 * sizeof(float);
+  const __nv_bfloat16* x0 = reinterpret_cast<const __nv_bfloat16*>(p->x_ptr[0]);
+  const __nv_bfloat16* x1 = reinterpret_cast<const __nv_bfloat16*>(p->x_ptr[1]);
+  __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(p->y_ptr);
+  if (vec == 8)
+    gn_apply_kernel<8><<<grid, 256, smem, stream>>>(x0, x1, C0, C1, p->x_pitch[0], p->x_pitch[1], p->spatial, p->affine, p->act, y, p->y_pitch);
+  else
+    gn_apply_kernel<1><<<grid, 256, smem, stream>>>(x0, x1, C0, C1, p->x_pitch[0], p->x_pitch[1], p->spatial, p->affine, p->act, y, p->y_pitch);
+  B200_LAUNCH_CHECK("gn_apply_kernel");
+  if (p->y_pitch > C) {
+    const long long rows = (long long)p->N * p->spatial;
+    long long zb = (rows * (p->y_pitch - C) + 255) / 256;
+    if (zb > 4ll * sm_count()) zb = 4ll * sm_count();
+    zero_pad_channels_kernel<<<(unsigned)zb, 256, 0, stream>>>(y, rows, C, p->y_pitch);
+    B200_LAUNCH_CHECK("zero_pad_channels_kernel");
+  }
+  return B200_OK;
+}
+
+extern "C" int b200_layernorm(const void* x, int64_t M, int32_t C, int32_t x_pitch, const float* gamma,
+                              const float* beta, float eps, void* y, int32_t y_pitch, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(x && y && gamma && beta && M >= 1 && C >= 1, "layernorm: bad arguments");
+  const int wpb = 8;
+  const long long blocks = (M + wpb - 1) / wpb;
+  B200_CHECK_ARG(blocks < (1ll << 31), "layernorm: too many rows");
+  layernorm_kernel<<<(unsigned)blocks, wpb * 32, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), M, C, x_pitch,
+                                                             gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(y), y_pitch);
+  B200_LAUNCH_CHECK("layernorm_kernel");
+  return B200_OK;
+}

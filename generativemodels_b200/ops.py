@@ -1,0 +1,575 @@
+"""Host-side operators: thin, allocation-only wrappers that turn torch tensors into C-ABI calls.
+
+PyTorch here is plumbing (device memory, streams, RNG); every FLOP of the sampling path runs in libb200gen.so.
+Internal activation format: :class:`CL` — channels-last bf16 ``[N, D, H, W, pitch]`` (2-D images have D == 1),
+``pitch`` = channels rounded up to 8 (the 16-byte TMA stride granule).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Sequence
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_NONE, ACT_RELU, ACT_SILU, DT_BF16, DT_F32, DdimCoef, DdpmCoef, GnApplyParams, GnStatsParams,
+                   IgemmParams, PndmCoef, check)
+
+__all__ = ["CL", "to_cl", "from_cl", "PackedConv", "PackedConvTranspose", "PackedLinear", "conv", "conv_transpose",
+           "linear", "groupnorm", "layernorm", "upsample_nearest2x", "avgpool2", "axpy", "geglu", "attention",
+           "timestep_embedding", "small_linear", "ACT_NONE", "ACT_RELU", "ACT_SILU"]
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+@dataclass
+class CL:
+    """Channels-last bf16 activation: ``t`` is ``[N, D, H, W, pitch]`` contiguous, ``C`` valid channels."""
+    t: torch.Tensor
+    C: int
+    spatial_dims: int = 2
+
+    @property
+    def N(self) -> int: return self.t.shape[0]
+    @property
+    def D(self) -> int: return self.t.shape[1]
+    @property
+    def H(self) -> int: return self.t.shape[2]
+    @property
+    def W(self) -> int: return self.t.shape[3]
+    @property
+    def pitch(self) -> int: return self.t.shape[4]
+    @property
+    def spatial(self) -> int: return self.t.shape[1] * self.t.shape[2] * self.t.shape[3]
+
+    def like(self, C_: int | None = None, dims: Sequence[int] | None = None) -> "CL":
+        C_ = self.C if C_ is None else C_
+        d = (self.D, self.H, self.W) if dims is None else tuple(dims)
+        t = torch.empty((self.N, *d, round_up(C_, 8)), dtype=torch.bfloat16, device=self.t.device)
+        return CL(t, C_, self.spatial_dims)
+
+
+def new_cl(N: int, dims: Sequence[int], C_: int, device, spatial_dims: int) -> CL:
+    t = torch.empty((N, *dims, round_up(C_, 8)), dtype=torch.bfloat16, device=device)
+    return CL(t, C_, spatial_dims)
+
+
+# --------------------------------------------------------------------------------------------------
+# API-edge layout conversion
+# --------------------------------------------------------------------------------------------------
+def to_cl(x: torch.Tensor) -> CL:
+    """NC[D]HW float tensor -> channels-last bf16 (pad channels zero)."""
+    lib = _lib.require_device()
+    if x.dim() not in (4, 5):
+        raise ValueError(f"expected a 4-D or 5-D NC[D]HW tensor, got shape {tuple(x.shape)}")
+    sd = x.dim() - 2
+    x = x.contiguous().float()
+    N, C_ = x.shape[0], x.shape[1]
+    dims = (1, *x.shape[2:]) if sd == 2 else tuple(x.shape[2:])
+    out = new_cl(N, dims, C_, x.device, sd)
+    sp = dims[0] * dims[1] * dims[2]
+    check(lib.b200_nchw_to_nhwc(x.data_ptr(), N, C_, sp, out.t.data_ptr(), out.pitch, _stream()), "b200_nchw_to_nhwc")
+    return out
+
+
+def from_cl(a: CL, dtype=torch.float32) -> torch.Tensor:
+    lib = _lib.require_device()
+    shape = (a.N, a.C, a.H, a.W) if a.spatial_dims == 2 else (a.N, a.C, a.D, a.H, a.W)
+    y = torch.empty(shape, dtype=torch.float32, device=a.t.device)
+    check(lib.b200_nhwc_to_nchw(a.t.data_ptr(), DT_BF16, a.N, a.C, a.spatial, a.pitch, y.data_ptr(), _stream()),
+          "b200_nhwc_to_nchw")
+    return y if dtype == torch.float32 else y.to(dtype)
+
+
+def from_cl_f32(t: torch.Tensor, C_: int, spatial_dims: int) -> torch.Tensor:
+    """fp32 channels-last [N, D, H, W, pitch] -> NC[D]HW fp32."""
+    lib = _lib.require_device()
+    N, D, H, W, P = t.shape
+    shape = (N, C_, H, W) if spatial_dims == 2 else (N, C_, D, H, W)
+    y = torch.empty(shape, dtype=torch.float32, device=t.device)
+    check(lib.b200_nhwc_to_nchw(t.data_ptr(), DT_F32, N, C_, D * H * W, P, y.data_ptr(), _stream()), "b200_nhwc_to_nchw")
+    return y
+
+
+# --------------------------------------------------------------------------------------------------
+# weight packing (one-time, cached by the modules; not on the per-step path)
+# --------------------------------------------------------------------------------------------------
+def _pack_taps(blocks: list[torch.Tensor], rows: int) -> torch.Tensor:
+    """blocks: list of [Cout, Cs] fp32 matrices -> bf16 [rows_pad, sum ceil64(Cs)] K-major."""
+    cols = []
+    for b in blocks:
+        cs = b.shape[1]
+        pad = round_up(cs, 64) - cs
+        cols.append(torch.nn.functional.pad(b, (0, pad)) if pad else b)
+    w = torch.cat(cols, dim=1)
+    rpad = round_up(rows, 16) - rows
+    if rpad:
+        w = torch.nn.functional.pad(w, (0, 0, 0, rpad))
+    return w.to(torch.bfloat16).contiguous()
+
+
+class PackedConv:
+    """K-major bf16 weight matrix + tap table for one nn.Conv{2,3}d.
+
+    ``splits`` are the channel counts of the (up to two) input tensors the conv reads — the virtual concat of
+    the UNet up path.  ``padding`` is ``(lo, hi)`` per spatial dim (asymmetric for the AutoencoderKL downsampler,
+    autoencoderkl.py:107-120).
+    """
+
+    def __init__(self, weight: torch.Tensor, bias: torch.Tensor | None, stride: int | Sequence[int],
+                 padding, splits: Sequence[int] | None = None):
+        w = weight.detach().float()
+        sd = w.dim() - 2
+        self.spatial_dims = sd
+        self.cout, cin = w.shape[0], w.shape[1]
+        k = tuple(w.shape[2:])
+        if sd == 2:
+            w = w.unsqueeze(2)
+            k = (1, *k)
+        self.k = k
+        st = (stride,) * sd if isinstance(stride, int) else tuple(stride)
+        self.stride = (1, *st) if sd == 2 else st
+        if isinstance(padding, int):
+            padding = [(padding, padding)] * sd
+        padding = [(p, p) if isinstance(p, int) else tuple(p) for p in padding]
+        self.pad = [(0, 0), *padding] if sd == 2 else padding
+        self.splits = list(splits) if splits else [cin]
+        if sum(self.splits) != cin or len(self.splits) > 2:
+            raise ValueError(f"channel splits {self.splits} do not match weight in_channels {cin}")
+        blocks, segs = [], []
+        for a in range(k[0]):
+            for b in range(k[1]):
+                for c in range(k[2]):
+                    off = 0
+                    for s, cs in enumerate(self.splits):
+                        blocks.append(w[:, off:off + cs, a, b, c])
+                        segs.append((s, c - self.pad[2][0], b - self.pad[1][0], a - self.pad[0][0], 0,
+                                     round_up(cs, 64) // 64))
+                        off += cs
+        if len(segs) > _lib.IGEMM_MAX_SEG:
+            raise ValueError(f"convolution needs {len(segs)} taps; the kernel supports {_lib.IGEMM_MAX_SEG}")
+        self.w = _pack_taps(blocks, self.cout)
+        self.segs = segs
+        self.bias = None if bias is None else bias.detach().float().contiguous()
+
+    def out_dims(self, D: int, H: int, W: int) -> tuple[int, int, int]:
+        i = (D, H, W)
+        return tuple((i[d] + self.pad[d][0] + self.pad[d][1] - self.k[d]) // self.stride[d] + 1 for d in range(3))
+
+
+class PackedLinear:
+    """nn.Linear weight [O, K] -> K-major bf16 (already K-major; only padded and cast)."""
+
+    def __init__(self, weight: torch.Tensor, bias: torch.Tensor | None):
+        w = weight.detach().float()
+        self.cout, self.K = w.shape
+        self.w = _pack_taps([w], self.cout)
+        self.segs = [(0, 0, 0, 0, 0, round_up(self.K, 64) // 64)]
+        self.bias = None if bias is None else bias.detach().float().contiguous()
+        self.stride = (1, 1, 1)
+
+
+class PackedConvTranspose:
+    """nn.ConvTranspose{2,3}d as one stride-1 implicit GEMM per output phase (out = i*s - p + k)."""
+
+    def __init__(self, weight: torch.Tensor, bias: torch.Tensor | None, stride: int, padding: int,
+                 output_padding: int):
+        w = weight.detach().float()           # [Cin, Cout, k...]
+        sd = w.dim() - 2
+        self.spatial_dims = sd
+        self.cin, self.cout = w.shape[0], w.shape[1]
+        k = tuple(w.shape[2:])
+        if sd == 2:
+            w = w.unsqueeze(2)
+            k = (1, *k)
+        self.k = k
+        self.s = (1, stride, stride) if sd == 2 else (stride,) * 3
+        self.p = (0, padding, padding) if sd == 2 else (padding,) * 3
+        self.op = (0, output_padding, output_padding) if sd == 2 else (output_padding,) * 3
+        self.bias = None if bias is None else bias.detach().float().contiguous()
+        nch = round_up(self.cin, 64) // 64
+        self.phases = []
+        for rd in range(self.s[0]):
+            for rh in range(self.s[1]):
+                for rw in range(self.s[2]):
+                    r = (rd, rh, rw)
+                    taps = [[(kk, (r[d] + self.p[d] - kk) // self.s[d]) for kk in range(k[d])
+                             if (r[d] + self.p[d] - kk) % self.s[d] == 0] for d in range(3)]
+                    blocks, segs = [], []
+                    for (a, oa) in taps[0]:
+                        for (b, ob) in taps[1]:
+                            for (c, oc) in taps[2]:
+                                blocks.append(w[:, :, a, b, c].t())      # [Cout, Cin]
+                                segs.append((0, oc, ob, oa, 0, nch))
+                    if not segs:
+                        continue
+                    self.phases.append((r, _pack_taps(blocks, self.cout), segs))
+
+    def out_dims(self, D: int, H: int, W: int) -> tuple[int, int, int]:
+        i = (D, H, W)
+        return tuple((i[d] - 1) * self.s[d] - 2 * self.p[d] + self.k[d] + self.op[d] for d in range(3))
+
+
+# --------------------------------------------------------------------------------------------------
+# implicit GEMM launcher
+# --------------------------------------------------------------------------------------------------
+def _fill_segs(p: IgemmParams, segs) -> None:
+    p.n_seg = len(segs)
+    for i, (src, dw, dh, dd, c0, nch) in enumerate(segs):
+        s = p.seg[i]
+        s.src, s.dw, s.dh, s.dd, s.c0, s.nchunks = src, dw, dh, dd, c0, nch
+
+
+def igemm_raw(p: IgemmParams) -> None:
+    lib = _lib.require_device()
+    check(lib.b200_igemm(C.byref(p), _stream()), "b200_igemm")
+
+
+def _conv_params(srcs: Sequence[CL], w: torch.Tensor, segs, stride, out_t: torch.Tensor, out_dims, cout: int,
+                 out_dtype: int, bias, rowvec, act1: int, scale: float, res: torch.Tensor | None, res_dtype: int,
+                 act2: int, out_elem_off: int = 0, out_strides=None, res_strides=None, impl: int = 0) -> IgemmParams:
+    p = IgemmParams()
+    a0 = srcs[0]
+    for i, a in enumerate(srcs):
+        if (a.N, a.D, a.H, a.W) != (a0.N, a0.D, a0.H, a0.W):
+            raise ValueError("concatenated inputs must share batch and spatial extent")
+        p.a_ptr[i] = a.t.data_ptr()
+        p.a_C[i] = a.C
+        p.a_pitch[i] = a.pitch
+    p.in_N, p.in_D, p.in_H, p.in_W = a0.N, a0.D, a0.H, a0.W
+    p.stride_d, p.stride_h, p.stride_w = stride
+    p.w_ptr = w.data_ptr()
+    p.w_rows, p.w_pitch, p.w_K = w.shape[0], w.shape[1], 0
+    p.w_bstride, p.w_batched = 0, 0
+    _fill_segs(p, segs)
+    esz = 2 if out_dtype == DT_BF16 else 4
+    p.out_ptr = out_t.data_ptr() + out_elem_off * esz
+    p.out_dtype = out_dtype
+    p.out_N = a0.N
+    p.out_D, p.out_H, p.out_W = out_dims
+    P = out_t.shape[-1]
+    p.cout, p.out_cols = cout, P
+    if out_strides is None:
+        OD, OH, OW = out_t.shape[1:4]
+        out_strides = (OD * OH * OW * P, OH * OW * P, OW * P, P)
+    p.out_sN, p.out_sD, p.out_sH, p.out_sW = out_strides
+    p.bias = _ptr(bias)
+    if rowvec is not None:
+        p.rowvec = rowvec.data_ptr()
+        p.rowvec_bstride = rowvec.stride(0) if rowvec.shape[0] > 1 else 0
+    p.act1, p.scale, p.act2 = act1, scale, act2
+    if res is not None:
+        p.res_ptr = res.data_ptr() + (out_elem_off * (2 if res_dtype == DT_BF16 else 4))
+        p.res_dtype = res_dtype
+        if res_strides is None:
+            RP = res.shape[-1]
+            RD, RH, RW = res.shape[1:4]
+            res_strides = (RD * RH * RW * RP, RH * RW * RP, RW * RP, RP)
+        p.res_sN, p.res_sD, p.res_sH, p.res_sW = res_strides
+    p.impl = impl
+    return p
+
+
+def conv(srcs: CL | Sequence[CL], pc: PackedConv, *, rowvec: torch.Tensor | None = None, act1: int = ACT_NONE,
+         scale: float = 1.0, residual: CL | None = None, act2: int = ACT_NONE, out_f32: bool = False,
+         impl: int = 0) -> CL | torch.Tensor:
+    """Fused convolution: act2(residual + scale * act1(conv(cat(srcs)) + bias + rowvec[n])).
+
+    Returns a :class:`CL` (bf16) or, with ``out_f32``, an fp32 channels-last tensor ``[N, D, H, W, round_up(C, 4)]``.
+    """
+    if isinstance(srcs, CL):
+        srcs = [srcs]
+    if [a.C for a in srcs] != pc.splits:
+        raise ValueError(f"conv inputs have channels {[a.C for a in srcs]} but weights were packed for {pc.splits}")
+    a0 = srcs[0]
+    od = pc.out_dims(a0.D, a0.H, a0.W)
+    if min(od) < 1:
+        raise ValueError(f"convolution output would be empty for input {(a0.D, a0.H, a0.W)}")
+    if out_f32:
+        out_t = torch.empty((a0.N, *od, round_up(pc.cout, 4)), dtype=torch.float32, device=a0.t.device)
+        out = out_t
+    else:
+        out = new_cl(a0.N, od, pc.cout, a0.t.device, a0.spatial_dims)
+        out_t = out.t
+    if residual is not None and tuple(residual.t.shape[:4]) != tuple(out_t.shape[:4]):
+        raise ValueError("residual shape mismatch")
+    p = _conv_params(srcs, pc.w, pc.segs, pc.stride, out_t, od, pc.cout, DT_F32 if out_f32 else DT_BF16, pc.bias,
+                     rowvec, act1, scale, None if residual is None else residual.t, DT_BF16, act2, impl=impl)
+    igemm_raw(p)
+    return out
+
+
+def conv_transpose(src: CL, pt: PackedConvTranspose, *, act1: int = ACT_NONE, impl: int = 0) -> CL:
+    od = pt.out_dims(src.D, src.H, src.W)
+    out = new_cl(src.N, od, pt.cout, src.t.device, src.spatial_dims)
+    P = out.pitch
+    full = (od[0] * od[1] * od[2] * P, od[1] * od[2] * P, od[2] * P, P)
+    for (r, w, segs) in pt.phases:
+        cnt = tuple((od[d] - r[d] + pt.s[d] - 1) // pt.s[d] for d in range(3))
+        if min(cnt) < 1:
+            continue
+        off = r[0] * full[1] + r[1] * full[2] + r[2] * full[3]
+        strides = (full[0], full[1] * pt.s[0], full[2] * pt.s[1], full[3] * pt.s[2])
+        p = _conv_params([src], w, segs, (1, 1, 1), out.t, cnt, pt.cout, DT_BF16, pt.bias, None, act1, 1.0, None,
+                         DT_BF16, ACT_NONE, out_elem_off=off, out_strides=strides, impl=impl)
+        igemm_raw(p)
+    return out
+
+
+def as_rows(t: torch.Tensor, C_: int) -> CL:
+    """View a bf16 [..., pitch] tensor as a token matrix CL [1, 1, 1, M, pitch]."""
+    P = t.shape[-1]
+    return CL(t.reshape(1, 1, 1, -1, P), C_, 2)
+
+
+def linear(x: CL, pl: PackedLinear, *, residual: CL | None = None, act1: int = ACT_NONE, out_f32: bool = False,
+           impl: int = 0):
+    """y = x @ W^T + b over the channel dim of any CL (rows = voxels)."""
+    if x.C != pl.K:
+        raise ValueError(f"linear expects {pl.K} input features, got {x.C}")
+    if out_f32:
+        out_t = torch.empty((*x.t.shape[:4], round_up(pl.cout, 4)), dtype=torch.float32, device=x.t.device)
+        out = out_t
+    else:
+        out = x.like(pl.cout)
+        out_t = out.t
+    p = _conv_params([x], pl.w, pl.segs, (1, 1, 1), out_t, (x.D, x.H, x.W), pl.cout, DT_F32 if out_f32 else DT_BF16,
+                     pl.bias, None, act1, 1.0, None if residual is None else residual.t, DT_BF16, ACT_NONE, impl=impl)
+    igemm_raw(p)
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# normalisation
+# --------------------------------------------------------------------------------------------------
+def groupnorm(srcs: CL | Sequence[CL], groups: int, eps: float, gamma: torch.Tensor, beta: torch.Tensor,
+              act: int = ACT_NONE) -> CL:
+    """GroupNorm (+SiLU) over the virtual channel-concat of ``srcs``; returns one dense CL."""
+    lib = _lib.require_device()
+    if isinstance(srcs, CL):
+        srcs = [srcs]
+    a0 = srcs[0]
+    Ct = sum(a.C for a in srcs)
+    if Ct % groups != 0:
+        raise ValueError(f"GroupNorm: {Ct} channels not divisible by {groups} groups")
+    dev = a0.t.device
+    ws = torch.empty(lib.b200_groupnorm_workspace_bytes(a0.N, a0.spatial, Ct) // 4, dtype=torch.float32, device=dev)
+    affine = torch.empty((a0.N, Ct, 2), dtype=torch.float32, device=dev)
+    sp = GnStatsParams()
+    ap = GnApplyParams()
+    for i, a in enumerate(srcs):
+        sp.x_ptr[i] = ap.x_ptr[i] = a.t.data_ptr()
+        sp.x_C[i] = ap.x_C[i] = a.C
+        sp.x_pitch[i] = ap.x_pitch[i] = a.pitch
+    sp.N = ap.N = a0.N
+    sp.spatial = ap.spatial = a0.spatial
+    sp.groups, sp.eps = groups, eps
+    g32 = gamma if gamma.dtype == torch.float32 else gamma.float()
+    b32 = beta if beta.dtype == torch.float32 else beta.float()
+    sp.gamma, sp.beta = g32.data_ptr(), b32.data_ptr()
+    sp.partial, sp.affine = ws.data_ptr(), affine.data_ptr()
+    check(lib.b200_groupnorm_stats(C.byref(sp), _stream()), "b200_groupnorm_stats")
+    out = a0.like(Ct)
+    ap.affine, ap.act = affine.data_ptr(), act
+    ap.y_ptr, ap.y_pitch = out.t.data_ptr(), out.pitch
+    check(lib.b200_groupnorm_apply(C.byref(ap), _stream()), "b200_groupnorm_apply")
+    return out
+
+
+def layernorm(x: CL, gamma: torch.Tensor, beta: torch.Tensor, eps: float) -> CL:
+    lib = _lib.require_device()
+    out = x.like()
+    M = x.N * x.spatial
+    check(lib.b200_layernorm(x.t.data_ptr(), M, x.C, x.pitch, gamma.data_ptr(), beta.data_ptr(), eps, out.t.data_ptr(),
+                             out.pitch, _stream()), "b200_layernorm")
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# resampling / elementwise
+# --------------------------------------------------------------------------------------------------
+def upsample_nearest2x(x: CL) -> CL:
+    lib = _lib.require_device()
+    sd = x.spatial_dims
+    dims = (x.D * 2 if sd == 3 else x.D, x.H * 2, x.W * 2)
+    out = x.like(dims=dims)
+    check(lib.b200_upsample_nearest2x(x.t.data_ptr(), x.N, x.D, x.H, x.W, x.pitch, sd, out.t.data_ptr(), _stream()),
+          "b200_upsample_nearest2x")
+    return out
+
+
+def avgpool2(x: CL) -> CL:
+    lib = _lib.require_device()
+    sd = x.spatial_dims
+    dims = (x.D // 2 if sd == 3 else x.D, x.H // 2, x.W // 2)
+    out = x.like(dims=dims)
+    check(lib.b200_avgpool2(x.t.data_ptr(), x.N, x.D, x.H, x.W, x.pitch, sd, out.t.data_ptr(), _stream()),
+          "b200_avgpool2")
+    return out
+
+
+def axpy(a: CL, b: CL, alpha: float = 1.0, inplace: bool = False) -> CL:
+    """a + alpha * b (same shape)."""
+    lib = _lib.require_device()
+    if a.t.shape != b.t.shape:
+        raise ValueError(f"axpy shape mismatch {tuple(a.t.shape)} vs {tuple(b.t.shape)}")
+    out = a if inplace else a.like()
+    check(lib.b200_axpy_bf16(a.t.data_ptr(), b.t.data_ptr(), alpha, out.t.data_ptr(), a.t.numel(), _stream()),
+          "b200_axpy_bf16")
+    return out
+
+
+def geglu(x: CL) -> CL:
+    lib = _lib.require_device()
+    Hh = x.C // 2
+    out = x.like(Hh)
+    M = x.N * x.spatial
+    check(lib.b200_geglu(x.t.data_ptr(), M, Hh, x.pitch, out.t.data_ptr(), out.pitch, _stream()), "b200_geglu")
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# attention
+# --------------------------------------------------------------------------------------------------
+_TC_ATTN_MIN_S = 64
+_ATTN_CHUNK_BYTES = 6 << 30   # fp32 score slab per query chunk
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, dh: int, scale: float,
+              vt: torch.Tensor | None = None) -> torch.Tensor:
+    """softmax(scale * Q K^T) V on packed [B, T, pitch] bf16 rows (heads are channel slices).
+
+    Tensor-core path (head_dim % 64 == 0, S >= 64): per (batch, head) QK^T -> fp32 scores, row softmax -> bf16
+    probabilities, PV — the two GEMMs run on the tcgen05 implicit-GEMM kernel, queries are processed in slabs so
+    the score matrix never exceeds a few GB (T = 89 600 in the 3-D config).  ``vt`` must then hold V^T
+    ``[B, H*dh, S_pitch]`` (produced for free by swapping the operands of the V projection).
+    Everything else runs on the CUDA-core online-softmax kernel.
+    """
+    lib = _lib.require_device()
+    B, T, qp = q.shape
+    S = k.shape[1]
+    out = torch.empty((B, T, round_up(heads * dh, 8)), dtype=torch.bfloat16, device=q.device)
+    use_tc = (dh % 64 == 0) and S >= _TC_ATTN_MIN_S and vt is not None
+    if not use_tc:
+        if out.shape[2] > heads * dh:
+            out.zero_()
+        check(lib.b200_attention_small(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, T, S, heads, dh,
+                                       qp, k.shape[2], v.shape[2], out.shape[2], scale, _stream()),
+              "b200_attention_small")
+        return out
+    Sp = round_up(S, 8)
+    chunk = max(128, min(T, (_ATTN_CHUNK_BYTES // (4 * Sp)) // 128 * 128))
+    scores = torch.empty((min(chunk, T), Sp), dtype=torch.float32, device=q.device)
+    probs = torch.empty((min(chunk, T), Sp), dtype=torch.bfloat16, device=q.device)
+    nk = round_up(dh, 64) // 64
+    ns = round_up(S, 64) // 64
+    for b in range(B):
+        for h in range(heads):
+            for t0 in range(0, T, chunk):
+                tc = min(chunk, T - t0)
+                # scores = scale * Q_h K_h^T   (A = Q rows, "weights" = K rows, both K-major over dh)
+                p = IgemmParams()
+                p.a_ptr[0] = q.data_ptr() + ((b * T + t0) * qp + h * dh) * 2
+                p.a_C[0], p.a_pitch[0] = dh, qp
+                p.in_N, p.in_D, p.in_H, p.in_W = 1, 1, 1, tc
+                p.stride_d = p.stride_h = p.stride_w = 1
+                p.w_ptr = k.data_ptr() + (b * S * k.shape[2] + h * dh) * 2
+                p.w_rows, p.w_pitch, p.w_K = S, k.shape[2], dh
+                _fill_segs(p, [(0, 0, 0, 0, 0, nk)])
+                p.out_ptr, p.out_dtype = scores.data_ptr(), DT_F32
+                p.out_N, p.out_D, p.out_H, p.out_W = 1, 1, 1, tc
+                p.cout, p.out_cols = S, Sp
+                p.out_sN, p.out_sD, p.out_sH, p.out_sW = tc * Sp, tc * Sp, tc * Sp, Sp
+                p.act1, p.scale, p.act2 = ACT_NONE, scale, ACT_NONE
+                igemm_raw(p)
+                check(lib.b200_softmax_rows(scores.data_ptr(), tc, S, Sp, probs.data_ptr(), Sp, _stream()),
+                      "b200_softmax_rows")
+                # out = P V   (A = P rows over S, "weights" = V^T rows over S)
+                p2 = IgemmParams()
+                p2.a_ptr[0] = probs.data_ptr()
+                p2.a_C[0], p2.a_pitch[0] = S, Sp
+                p2.in_N, p2.in_D, p2.in_H, p2.in_W = 1, 1, 1, tc
+                p2.stride_d = p2.stride_h = p2.stride_w = 1
+                vtp = vt.shape[2]
+                p2.w_ptr = vt.data_ptr() + ((b * heads * dh + h * dh) * vtp) * 2
+                p2.w_rows, p2.w_pitch, p2.w_K = dh, vtp, S
+                _fill_segs(p2, [(0, 0, 0, 0, 0, ns)])
+                op = out.shape[2]
+                p2.out_ptr, p2.out_dtype = out.data_ptr() + ((b * T + t0) * op + h * dh) * 2, DT_BF16
+                p2.out_N, p2.out_D, p2.out_H, p2.out_W = 1, 1, 1, tc
+                p2.cout, p2.out_cols = dh, dh
+                p2.out_sN, p2.out_sD, p2.out_sH, p2.out_sW = tc * op, tc * op, tc * op, op
+                p2.act1, p2.scale, p2.act2 = ACT_NONE, 1.0, ACT_NONE
+                igemm_raw(p2)
+    return out
+
+
+def linear_transposed(x: torch.Tensor, C_in: int, pl: PackedLinear) -> torch.Tensor:
+    """V^T = W x^T + b:  x is [B, S, pitch] bf16 rows; returns [B, O, round_up(S, 8)] bf16.
+
+    The projection weight plays the A operand (rows = output features) and the activations play the K-major
+    "weight" operand, so the transposed value matrix costs no extra pass.
+    """
+    B, S, xp = x.shape
+    O = pl.cout
+    Sp = round_up(S, 8)
+    out = torch.empty((B, O, Sp), dtype=torch.bfloat16, device=x.device)
+    if Sp > S:
+        out.zero_()
+    nk = round_up(C_in, 64) // 64
+    for b in range(B):
+        p = IgemmParams()
+        p.a_ptr[0] = pl.w.data_ptr()
+        p.a_C[0], p.a_pitch[0] = C_in, pl.w.shape[1]
+        p.in_N, p.in_D, p.in_H, p.in_W = 1, 1, 1, O
+        p.stride_d = p.stride_h = p.stride_w = 1
+        p.w_ptr = x.data_ptr() + b * S * xp * 2
+        p.w_rows, p.w_pitch, p.w_K = S, xp, C_in
+        _fill_segs(p, [(0, 0, 0, 0, 0, nk)])
+        p.out_ptr, p.out_dtype = out.data_ptr() + b * O * Sp * 2, DT_BF16
+        p.out_N, p.out_D, p.out_H, p.out_W = 1, 1, 1, O
+        p.cout, p.out_cols = S, Sp
+        p.out_sN, p.out_sD, p.out_sH, p.out_sW = O * Sp, O * Sp, O * Sp, Sp
+        p.act1, p.scale, p.act2 = ACT_NONE, 1.0, ACT_NONE
+        p.row_bias = _ptr(pl.bias)       # the linear's bias is per output ROW in this orientation
+        igemm_raw(p)
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# time embedding
+# --------------------------------------------------------------------------------------------------
+def timestep_embedding(t: torch.Tensor, dim: int, max_period: float = 10000.0) -> torch.Tensor:
+    lib = _lib.require_device()
+    t = t.contiguous().float()
+    emb = torch.empty((t.shape[0], dim), dtype=torch.float32, device=t.device)
+    check(lib.b200_timestep_embedding(t.data_ptr(), t.shape[0], dim, max_period, emb.data_ptr(), _stream()),
+          "b200_timestep_embedding")
+    return emb
+
+
+def small_linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None, act_in: int = ACT_NONE,
+                 act_out: int = ACT_NONE) -> torch.Tensor:
+    """fp32 GEMV-class linear for the time-embedding path (M = batch rows)."""
+    lib = _lib.require_device()
+    x = x.contiguous().float()
+    M, K = x.shape
+    O = weight.shape[0]
+    y = torch.empty((M, O), dtype=torch.float32, device=x.device)
+    w = weight if weight.dtype == torch.float32 and weight.is_contiguous() else weight.detach().float().contiguous()
+    b = None if bias is None else (bias if bias.dtype == torch.float32 else bias.detach().float())
+    check(lib.b200_small_linear(x.data_ptr(), M, K, w.data_ptr(), _ptr(b), O, act_in, act_out, y.data_ptr(), _stream()),
+          "b200_small_linear")
+    return y

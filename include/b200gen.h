@@ -1,0 +1,255 @@
+/*
+ * b200gen.h — C-ABI of libb200gen.so: the sm_100a kernels behind the MONAI-GenerativeModels
+ * diffusion *sampling* hot path.  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions (inner boundary)
+ *   - every entry point returns 0 on success or a negative B200_E* code; b200_last_error_string()
+ *     gives the detail for the calling thread.  Nothing throws, exits, allocates device memory or
+ *     synchronises the stream: all work is enqueued on `stream` (a cudaStream_t passed as void*).
+ *   - activations are channels-last ("NDHWC") bf16 unless a dtype field says otherwise; a 2-D image
+ *     is D == 1; a token matrix [M, C] is D == H == 1, W == M.  The channel pitch of every bf16
+ *     activation is a multiple of 8 elements (16 bytes, the TMA global-stride granule).
+ *   - each function cites the reference code (file:line under /root/reference) whose arithmetic it
+ *     replaces.  The Python host (generativemodels_b200/) binds these with ctypes.
+ */
+#ifndef B200GEN_H_
+#define B200GEN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK        0
+#define B200_EINVAL   -1   /* bad shape / alignment / null pointer                    */
+#define B200_ENOTSUP  -2   /* valid request this build has no kernel for              */
+#define B200_ECUDA    -3   /* CUDA runtime / driver error, see b200_last_error_string */
+#define B200_ENODEV   -4   /* device is not compute capability 10.x                   */
+
+#define B200_DT_BF16 0
+#define B200_DT_F32  1
+
+#define B200_ACT_NONE 0
+#define B200_ACT_RELU 1
+#define B200_ACT_SILU 2
+
+#define B200_IGEMM_MAX_SEG 128
+
+const char* b200_last_error_string(void);
+int b200_version(void);
+/* 0 iff the current CUDA device is sm_100-class (fails loudly elsewhere: there is no fallback). */
+int b200_device_check(void);
+int b200_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Implicit-GEMM on tcgen05 tensor cores (TMA-staged NDHWC tiles, accumulators in TMEM).
+ * One kernel family serves every dense contraction on the path:
+ *   - nn.Conv2d/3d k in {1,3,4}, stride {1,2}, symmetric or asymmetric zero padding
+ *     (monai Convolution call sites: diffusion_model_unet.py:277,303,510,555,625,645,659,1748,1857;
+ *      autoencoderkl.py:54-73,109,147-176; vqvae.py:61-77,127-162; controlnet.py:55-104,274-364)
+ *   - nn.ConvTranspose k4 s2 p1 as one launch per output phase (vqvae.py:220-260)
+ *   - channel-concat inputs read from two tensors (torch.cat at diffusion_model_unet.py:1232,1340,1461)
+ *   - nn.Linear / q,k,v projections / GEGLU linears (diffusion_model_unet.py:98-103,211,379-381)
+ *   - attention QK^T and PV as batched GEMMs (diffusion_model_unet.py:143-153,406-416)
+ * out[n, od, oh, ow, co] = act2( residual + scale * act1( bias[co] + rowvec[n, co] + row_bias[ow] +
+ *        sum_seg sum_c  A_src(seg)[n, od*sd + seg.dd, oh*sh + seg.dh, ow*sw + seg.dw, seg.c0*64 + c]
+ *                        * W[wb, co, kbase(seg) + c] ) )
+ * with out-of-range A coordinates / channels and W rows read as zero (TMA OOB fill).
+ * kbase(seg) = 64 * (number of 64-channel chunks of all earlier segments).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int8_t  src;        /* which A tensor (0 or 1)                               */
+  int8_t  dw, dh, dd; /* input offset of this tap, in input elements            */
+  uint16_t c0;        /* first 64-channel chunk of the source read by this tap  */
+  uint16_t nchunks;   /* number of 64-channel chunks                            */
+} b200_igemm_seg;
+
+typedef struct {
+  /* A: up to two bf16 NDHWC sources sharing N and the spatial extent */
+  const void* a_ptr[2];
+  int32_t a_C[2];      /* valid channels of each source                          */
+  int32_t a_pitch[2];  /* elements between consecutive voxels (>= a_C, % 8 == 0) */
+  int32_t in_N, in_D, in_H, in_W;
+  int32_t stride_d, stride_h, stride_w;   /* conv stride (1 or 2)               */
+  /* W: bf16 [w_batch][w_rows][w_pitch], K-major, w_pitch % 64 == 0             */
+  const void* w_ptr;
+  int32_t w_rows;       /* valid rows (>= cout)                                  */
+  int32_t w_pitch;      /* elements per row                                      */
+  int32_t w_K;          /* valid K extent of a row (0 = w_pitch); reads past it are 0 */
+  int64_t w_bstride;    /* elements between weight batches; 0 = shared weights   */
+  int32_t w_batched;    /* 1: sample n uses weight batch n                       */
+  int32_t n_seg;
+  b200_igemm_seg seg[B200_IGEMM_MAX_SEG];
+  /* output */
+  void*   out_ptr;
+  int32_t out_dtype;    /* B200_DT_BF16 / B200_DT_F32                            */
+  int32_t out_N, out_D, out_H, out_W;
+  int32_t cout;         /* valid output channels                                 */
+  int32_t out_cols;     /* channels stored per voxel (>= cout; extras get 0)     */
+  int64_t out_sN, out_sD, out_sH, out_sW;   /* element strides; channel stride 1 */
+  /* epilogue */
+  const float* bias;    /* [cout] or NULL                                        */
+  const float* rowvec;  /* [N or 1][rowvec_ld] fp32 per-sample vector or NULL    */
+  int64_t rowvec_bstride; /* elements between samples (0 broadcasts)             */
+  const float* row_bias; /* [out_W] fp32 added per output row (GEMM-shaped calls: out_D == out_H == 1) or NULL */
+  int32_t act1;
+  float   scale;        /* applied after act1                                    */
+  const void* res_ptr;  /* residual, same logical shape as out, or NULL          */
+  int32_t res_dtype;
+  int64_t res_sN, res_sD, res_sH, res_sW;
+  int32_t act2;
+  int32_t impl;         /* 0 = tcgen05 kernel, 1 = CUDA-core cross-check kernel  */
+} b200_igemm_params;
+
+int b200_igemm(const b200_igemm_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * GroupNorm (+SiLU) on NDHWC bf16, optionally over the virtual concat of two tensors.
+ * Replaces nn.GroupNorm + nn.SiLU in ResnetBlock / AttentionBlock / out head
+ * (diffusion_model_unet.py:623-624,643,671,684, 372, 1853-1855; autoencoderkl.py:139-146,229).
+ * Two phases: per-block partial sums -> per-(n,c) affine (a = rstd*gamma, b = beta - mean*a).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* x_ptr[2];   /* bf16 NDHWC sources (second may be NULL)      */
+  int32_t x_C[2];         /* valid channels                               */
+  int32_t x_pitch[2];     /* channel pitch                                */
+  int32_t N;
+  int64_t spatial;        /* D*H*W voxels per sample                      */
+  int32_t groups;
+  float   eps;
+  const float* gamma;     /* [C0+C1]                                      */
+  const float* beta;      /* [C0+C1]                                      */
+  float*  partial;        /* workspace: b200_groupnorm_workspace_bytes()  */
+  float*  affine;         /* out: [N][C0+C1][2] (a, b) fp32               */
+} b200_gn_stats_params;
+int64_t b200_groupnorm_workspace_bytes(int32_t N, int64_t spatial, int32_t C_total);
+int b200_groupnorm_stats(const b200_gn_stats_params* p, void* stream);
+
+typedef struct {
+  const void* x_ptr[2];
+  int32_t x_C[2];
+  int32_t x_pitch[2];
+  int32_t N;
+  int64_t spatial;
+  const float* affine;    /* [N][C][2] from b200_groupnorm_stats          */
+  int32_t act;            /* B200_ACT_NONE / B200_ACT_SILU                */
+  void*   y_ptr;          /* bf16 NDHWC, channel pitch y_pitch            */
+  int32_t y_pitch;
+} b200_gn_apply_params;
+int b200_groupnorm_apply(const b200_gn_apply_params* p, void* stream);
+
+/* nn.LayerNorm over the last dim of a bf16 [M, C] matrix (diffusion_model_unet.py:221-223). */
+int b200_layernorm(const void* x, int64_t M, int32_t C, int32_t x_pitch, const float* gamma,
+                   const float* beta, float eps, void* y, int32_t y_pitch, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Layout / resampling / elementwise helpers on the API edge and between fused ops.
+ * ---------------------------------------------------------------------------------------------- */
+/* NC[D]HW fp32 -> NDHWC bf16 (channel pitch `pitch`, pad channels zeroed) and back. */
+int b200_nchw_to_nhwc(const float* x, int32_t N, int32_t C, int64_t spatial, void* y, int32_t pitch,
+                      void* stream);
+int b200_nhwc_to_nchw(const void* x, int32_t x_dtype, int32_t N, int32_t C, int64_t spatial,
+                      int32_t pitch, float* y, void* stream);
+/* F.interpolate(scale_factor=2, mode="nearest") (diffusion_model_unet.py:578; autoencoderkl.py:84). */
+int b200_upsample_nearest2x(const void* x, int32_t N, int32_t D, int32_t H, int32_t W, int32_t pitch,
+                            int32_t dims /*2 or 3*/, void* y, void* stream);
+/* nn.AvgPool{2,3}d(kernel=2, stride=2) (diffusion_model_unet.py:522). */
+int b200_avgpool2(const void* x, int32_t N, int32_t D, int32_t H, int32_t W, int32_t pitch,
+                  int32_t dims, void* y, void* stream);
+/* y = a + alpha * b on bf16 buffers of n elements (ControlNet residual adds,
+ * diffusion_model_unet.py:1917-1925,1931-1932; controlnet.py:405-407,433-434). */
+int b200_axpy_bf16(const void* a, const void* b, float alpha, void* y, int64_t n, void* stream);
+/* GEGLU: y[m, j] = x[m, j] * gelu_erf(x[m, H + j])  (monai MLPBlock act="GEGLU",
+ * diffusion_model_unet.py:211). x: [M, 2H] pitch x_pitch; y: [M, H] pitch y_pitch. */
+int b200_geglu(const void* x, int64_t M, int32_t H, int32_t x_pitch, void* y, int32_t y_pitch,
+               void* stream);
+/* softmax over rows of an fp32 [M, S] score matrix -> bf16 probabilities [M, p_pitch]
+ * (attention_scores.softmax(dim=-1), diffusion_model_unet.py:150,412). Pad columns are zeroed. */
+int b200_softmax_rows(const float* s, int64_t M, int32_t S, int64_t s_pitch, void* p, int64_t p_pitch,
+                      void* stream);
+
+/* Small-shape attention on CUDA cores (any head_dim <= 256, any S); used for the test-suite
+ * head dims (2..8) and for cross-attention with a handful of context tokens.
+ * q: [B, T, H*dh] bf16 pitch q_pitch; k, v: [B, S, H*dh]; out: [B, T, H*dh].
+ * (CrossAttention._attention, diffusion_model_unet.py:136-153; AttentionBlock 406-416.) */
+int b200_attention_small(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t T,
+                         int32_t S, int32_t heads, int32_t dh, int32_t q_pitch, int32_t k_pitch,
+                         int32_t v_pitch, int32_t o_pitch, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Time embedding path (diffusion_model_unet.py:461-485, 1759-1767, 1888-1902; ResnetBlock 641,686).
+ * ---------------------------------------------------------------------------------------------- */
+/* emb[n, :] = [cos(t_n f_i) ..., sin(t_n f_i) ...], f_i = exp(-ln(max_period) i / half), zero-pad if odd */
+int b200_timestep_embedding(const float* t, int32_t N, int32_t dim, float max_period, float* emb,
+                            void* stream);
+/* y[m, o] = act_out( b[o] + sum_k act_in(x[m, k]) W[o, k] ), fp32, M <= 64 rows (GEMV-class). */
+int b200_small_linear(const float* x, int32_t M, int32_t K, const float* W, const float* b, int32_t O,
+                      int32_t act_in, int32_t act_out, float* y, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Scheduler steps: one fused elementwise pass each (fp32 tensors of n elements).
+ * ---------------------------------------------------------------------------------------------- */
+#define B200_PRED_EPSILON  0
+#define B200_PRED_SAMPLE   1
+#define B200_PRED_V        2
+/* DDIMScheduler.step (ddim.py:156-237): coefficients computed on the host exactly as the reference
+ * does (0-dim fp32 tensor arithmetic) and passed by value. noise may be NULL (eta == 0). */
+typedef struct {
+  float sqrt_alpha_prod_t, sqrt_beta_prod_t;   /* alpha_prod_t**0.5, beta_prod_t**0.5            */
+  float sqrt_alpha_prod_prev, dir_coef;        /* alpha_prod_t_prev**0.5, (1-a_prev-var)**0.5    */
+  float sigma;                                 /* eta * variance**0.5                            */
+  float clip_min, clip_max;                    /* clip_sample_values (ddim.py:213-216)           */
+  int32_t prediction_type, clip;
+} b200_ddim_coef;
+int b200_ddim_step(const float* model_out, const float* sample, const float* noise,
+                   const b200_ddim_coef* c, float* prev_sample, float* pred_x0, int64_t n, void* stream);
+/* DDPMScheduler.step (ddpm.py:191-252): mean = c_x0 * clamp(x0) + c_xt * x_t, + sigma * noise. */
+typedef struct {
+  float sqrt_alpha_prod_t, sqrt_beta_prod_t;
+  float coef_x0, coef_xt;      /* pred_original_sample_coeff, current_sample_coeff (ddpm.py:235-236) */
+  float sigma;                 /* variance ** 0.5 for the fixed variance types (ddpm.py:158-189)     */
+  float clip_min, clip_max;
+  float min_log, max_log;      /* learned_range: variance = frac*max_log + (1-frac)*min_log          */
+  int32_t var_mode;            /* 0 fixed (sigma), 1 learned (pred_var), 2 learned_range             */
+  int32_t prediction_type, clip;
+} b200_ddpm_coef;
+/* noise == NULL at t == 0 (no noise is added, ddpm.py:243); pred_var only for learned variance. */
+int b200_ddpm_step(const float* model_out, const float* sample, const float* noise, const float* pred_var,
+                   const b200_ddpm_coef* c, float* prev_sample, float* pred_x0, int64_t n, void* stream);
+/* PNDMScheduler._get_prev_sample after the linear-multistep combine (pndm.py:261-273, 293-315):
+ * eps = sum_i w[i] * hist[i] (up to 4 history tensors), prev = sample_coeff*sample - eps_coeff*eps.
+ * eps_out (optional) receives the combined model output; prev_sample may be NULL (PRK accumulation,
+ * pndm.py:204-224). v-prediction pre-mix per pndm.py:304-305. */
+typedef struct {
+  float w[4];
+  int32_t n_hist;
+  float sample_coeff, eps_coeff;
+  float v_alpha, v_beta;  /* alpha_prod_t**0.5, beta_prod_t**0.5 for v-prediction */
+  int32_t prediction_type;
+} b200_pndm_coef;
+int b200_pndm_step(const float* const* hist, const float* sample, const b200_pndm_coef* c,
+                   float* prev_sample, float* eps_out, int64_t n, void* stream);
+/* Scheduler.add_noise / get_velocity (scheduler.py:169-200) with per-sample coefficients. */
+int b200_add_noise(const float* x0, const float* noise, const float* ca, const float* cb, float sign_b,
+                   int32_t N, int64_t per_sample, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Vector quantiser (vector_quantizer.py:86-138): nearest codebook row under
+ * d = |x|^2 + |e|^2 - 2 x.e (fp32), first index wins ties; writes int64 indices and optionally the
+ * gathered rows.  x: fp32 [M, D] (channels-last); codebook fp32 [K, D].
+ * ---------------------------------------------------------------------------------------------- */
+/* Optional outputs (NULL to skip): q_bf16 rows (pitch q_pitch, pad zeroed) for the decoder; q_f32 [M, D] with the
+ * straight-through rounding x + (q - x) when ste != 0 (vector_quantizer.py:186) else q; sqerr_sum += sum (q-x)^2
+ * (commitment loss numerator, 183); hist[k] += count (perplexity, 212-218). */
+int b200_vq_argmin_gather(const float* x, int64_t M, int32_t D, int32_t x_pitch, const float* codebook,
+                          int32_t K, int64_t* indices, void* q_bf16, int32_t q_pitch, float* q_f32,
+                          int32_t ste, double* sqerr_sum, int32_t* hist, void* stream);
+/* nn.Embedding gather for decode_samples (vqvae.py:445-450): idx int64 [M] -> bf16 rows. */
+int b200_vq_gather(const int64_t* indices, int64_t M, const float* codebook, int32_t K, int32_t D,
+                   void* q_bf16, int32_t q_pitch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200GEN_H_ */

@@ -1,0 +1,158 @@
+"""CPU tests of the host-side logic in generativemodels_b200.ops: weight packing, tap tables, asymmetric padding,
+stride, transposed-conv phases, virtual concat, GEMM/attention parameter blocks.  The C-ABI call is replaced by
+tests/igemm_emulator.py (a literal reading of include/b200gen.h), so what is verified here is exactly the struct the
+GPU kernel receives.  Kernel arithmetic itself is covered by the -m gpu tests."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from generativemodels_b200 import ops
+from tests import igemm_emulator
+
+
+@pytest.fixture(autouse=True)
+def _emulated(monkeypatch):
+    monkeypatch.setattr(ops, "igemm_raw", igemm_emulator.emulate)
+
+
+def bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+def cl_cpu(x):
+    """NC[D]HW fp32 -> CL on CPU (test-only stand-in for the layout kernel)."""
+    sd = x.dim() - 2
+    t = x.movedim(1, -1)
+    if sd == 2:
+        t = t.unsqueeze(1)
+    C_ = x.shape[1]
+    P = ops.round_up(C_, 8)
+    t = F.pad(t, (0, P - C_)).to(torch.bfloat16).contiguous()
+    return ops.CL(t, C_, sd)
+
+
+def nchw(a, f32=False, C_=None):
+    C_ = a.C if C_ is None else C_
+    t = (a if f32 else a.t)[..., :C_].float()
+    sd = 3 if f32 is True and False else None
+    return t
+
+
+def back(a):
+    t = a.t[..., : a.C].float()
+    if a.spatial_dims == 2:
+        t = t.squeeze(1)
+    return t.movedim(-1, 1)
+
+
+def close(a, b, tol=1.5e-2):
+    err = (a - b).norm() / (b.norm() + 1e-12)
+    assert err < tol, f"rel err {err:.3e}"
+
+
+CASES = [
+    (2, 2, 20, 24, (9, 7), 3, 1, 1), (2, 1, 3, 8, (6, 6), 3, 1, 1), (2, 1, 70, 5, (5, 8), 1, 1, 0),
+    (3, 1, 12, 16, (4, 5, 6), 3, 1, 1), (2, 1, 16, 16, (9, 11), 3, 2, 1), (3, 1, 8, 8, (6, 6, 7), 3, 2, 1),
+    (3, 1, 8, 12, (6, 8, 6), 4, 2, 1), (2, 1, 130, 16, (4, 4), 3, 1, 1),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[str(c) for c in CASES])
+def test_conv_host_logic(case):
+    sd, N, Cin, Cout, sp, k, s, p = case
+    torch.manual_seed(0)
+    x = torch.randn(N, Cin, *sp)
+    w = torch.randn(Cout, Cin, *([k] * sd)) / math.sqrt(Cin * k ** sd)
+    b = torch.randn(Cout)
+    conv = F.conv2d if sd == 2 else F.conv3d
+    ref = conv(bf(x), bf(w), b, stride=s, padding=p)
+    out = ops.conv(cl_cpu(x), ops.PackedConv(w, b, s, p))
+    assert tuple(back(out).shape) == tuple(ref.shape)
+    close(back(out), ref)
+    assert out.t[..., out.C:].abs().sum() == 0
+
+
+def test_asym_pad_host_logic():
+    for sd, sp in ((2, (8, 10)), (3, (4, 6, 5))):
+        x = torch.randn(1, 16, *sp)
+        w = torch.randn(16, 16, *([3] * sd)) / 10
+        conv = F.conv2d if sd == 2 else F.conv3d
+        ref = conv(F.pad(bf(x), (0, 1) * sd), bf(w), None, stride=2)
+        out = ops.conv(cl_cpu(x), ops.PackedConv(w, None, 2, [(0, 1)] * sd))
+        assert tuple(back(out).shape) == tuple(ref.shape)
+        close(back(out), ref)
+
+
+def test_concat_epilogue_host_logic():
+    torch.manual_seed(1)
+    N, C0, C1, Cout, sp = 2, 24, 8, 20, (3, 4, 5)
+    x0, x1 = torch.randn(N, C0, *sp), torch.randn(N, C1, *sp)
+    w = torch.randn(Cout, C0 + C1, 3, 3, 3) / 20
+    b, temb, res = torch.randn(Cout), torch.randn(N, Cout), torch.randn(N, Cout, *sp)
+    ref = F.conv3d(torch.cat([bf(x0), bf(x1)], 1), bf(w), b, padding=1) + temb[:, :, None, None, None]
+    ref = F.relu(bf(res) + 0.5 * F.silu(ref))
+    pc = ops.PackedConv(w, b, 1, 1, splits=[C0, C1])
+    out = ops.conv([cl_cpu(x0), cl_cpu(x1)], pc, rowvec=temb, act1=ops.ACT_SILU, scale=0.5, residual=cl_cpu(res),
+                   act2=ops.ACT_RELU)
+    close(back(out), ref)
+    out32 = ops.conv([cl_cpu(x0), cl_cpu(x1)], pc, rowvec=temb[:1], out_f32=True)
+    ref32 = F.conv3d(torch.cat([bf(x0), bf(x1)], 1), bf(w), b, padding=1) + temb[:1, :, None, None, None]
+    close(out32[..., :Cout].movedim(-1, 1), ref32, 1e-3)
+
+
+@pytest.mark.parametrize("sd,sp,k,s,p,op", [(2, (5, 6), 4, 2, 1, 0), (3, (3, 4, 5), 4, 2, 1, 0), (2, (4, 4), 3, 2, 1, 1)])
+def test_conv_transpose_host_logic(sd, sp, k, s, p, op):
+    torch.manual_seed(2)
+    x = torch.randn(2, 12, *sp)
+    w = torch.randn(12, 10, *([k] * sd)) / 5
+    b = torch.randn(10)
+    convt = F.conv_transpose2d if sd == 2 else F.conv_transpose3d
+    ref = F.relu(convt(bf(x), bf(w), b, stride=s, padding=p, output_padding=op))
+    out = ops.conv_transpose(cl_cpu(x), ops.PackedConvTranspose(w, b, s, p, op), act1=ops.ACT_RELU)
+    assert tuple(back(out).shape) == tuple(ref.shape)
+    close(back(out), ref)
+
+
+def test_linear_and_transposed_host_logic():
+    torch.manual_seed(3)
+    M, K, O = 37, 40, 24
+    x = torch.randn(1, K, 1, M)
+    w, b = torch.randn(O, K) / 6, torch.randn(O)
+    ref = F.linear(bf(x)[0, :, 0].t(), bf(w), b)
+    pl = ops.PackedLinear(w, b)
+    a = cl_cpu(x)
+    out = ops.linear(a, pl)
+    close(out.t[0, 0, 0, :, :O].float(), ref)
+    vt = ops.linear_transposed(a.t.reshape(1, M, -1), K, pl)
+    close(vt[0, :, :M].float(), ref.t())
+
+
+def test_attention_tc_host_logic(monkeypatch):
+    """The tensor-core attention parameter blocks (QK^T, PV with V^T) — softmax emulated on CPU."""
+    torch.manual_seed(4)
+    B, T, heads, dh = 2, 70, 2, 64
+    Cc = heads * dh
+    q, k, v = (torch.randn(B, T, Cc) for _ in range(3))
+
+    class FakeLib:
+        def b200_softmax_rows(self, s, M, S, sp, p, pp, stream):
+            import ctypes as C
+            import numpy as np
+            sc = np.ctypeslib.as_array(C.cast(s, C.POINTER(C.c_float)), shape=(M * sp,)).reshape(M, sp)[:, :S]
+            e = np.exp(sc - sc.max(1, keepdims=True))
+            pr = e / e.sum(1, keepdims=True)
+            dst = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint16)), shape=(M * pp,)).reshape(M, pp)
+            dst[:] = 0
+            dst[:, :S] = igemm_emulator._f32_to_bf16(pr.astype(np.float32)).reshape(M, S)
+            return 0
+
+    monkeypatch.setattr(ops._lib, "require_device", lambda: FakeLib())
+    monkeypatch.setattr(ops, "_stream", lambda: 0)
+    qb, kb, vb = (t.to(torch.bfloat16).contiguous() for t in (q, k, v))
+    vt = F.pad(vb.transpose(1, 2), (0, ops.round_up(T, 8) - T)).contiguous()
+    out = ops.attention(qb, kb, None, heads, dh, 1 / math.sqrt(dh), vt=vt)
+    qh, kh, vh = (bf(t).view(B, T, heads, dh).transpose(1, 2) for t in (q, k, v))
+    ref = (torch.softmax(qh @ kh.transpose(-1, -2) / math.sqrt(dh), -1) @ vh).transpose(1, 2).reshape(B, T, Cc)
+    close(out[..., :Cc].float(), ref, 2e-2)

@@ -1,0 +1,319 @@
+"""Op-level parity of every CUDA kernel (called through the C-ABI) against plain fp32 CPU arithmetic.
+
+The checker for one op is the reference's own arithmetic: torch CPU fp32 functional ops (what the reference
+executes on CPU) applied to the SAME bf16-rounded inputs the kernel sees.  Tolerances: the
+kernels take bf16 operands and accumulate in fp32, so a result differs from the fp32 checker only by the final
+bf16 rounding of the output (rel 2^-8) plus accumulation-order noise -> atol/rtol 2e-2 on O(1) data; fp32-out
+paths are held to 2e-3; integer outputs (VQ indices) are exact outside fp32 near-ties.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+def rel_err(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item(), (a - b).abs().max().item()
+
+
+def assert_close(a, b, tol, what):
+    r, m = rel_err(a, b)
+    scale = b.float().abs().max().item() + 1e-6
+    assert r < tol and m < 4 * tol * scale + 1e-5, f"{what}: rel-L2 {r:.3e}, max-abs {m:.3e} (scale {scale:.3e})"
+
+
+def _ops():
+    from generativemodels_b200 import ops
+    return ops
+
+
+def to_cl_ref(x):
+    """NC[D]HW fp32 (cpu) -> CL on cuda via the library's own layout kernel."""
+    ops = _ops()
+    return ops.to_cl(x.cuda())
+
+
+# ------------------------------------------------------------------------------------------------ layout
+@pytest.mark.parametrize("shape", [(2, 3, 9, 7), (1, 1, 5, 6, 7), (2, 40, 4, 4, 5), (1, 256, 16, 16)])
+def test_layout_roundtrip(cuda_device, shape):
+    ops = _ops()
+    x = torch.randn(shape)
+    a = ops.to_cl(x.cuda())
+    sd = len(shape) - 2
+    ref = bf(x).movedim(1, -1)
+    if sd == 2:
+        ref = ref.unsqueeze(1)
+    got = a.t[..., : shape[1]].float().cpu()
+    assert torch.equal(got, ref)
+    assert a.t[..., shape[1]:].abs().sum().item() == 0
+    back = ops.from_cl(a).cpu()
+    assert torch.equal(back, bf(x))
+
+
+# ------------------------------------------------------------------------------------------------ igemm / conv
+CONV_CASES = [
+    # (spatial_dims, N, Cin, Cout, in_spatial, k, stride, padding)
+    (2, 1, 64, 64, (16, 16), 3, 1, 1),
+    (2, 2, 128, 256, (33, 17), 3, 1, 1),
+    (2, 1, 96, 48, (20, 12), 3, 1, 1),
+    (2, 2, 3, 32, (16, 16), 3, 1, 1),
+    (2, 1, 32, 3, (16, 16), 3, 1, 1),
+    (2, 1, 64, 64, (8, 8), 1, 1, 0),
+    (2, 1, 512, 512, (16, 16), 3, 1, 1),
+    (3, 1, 64, 64, (8, 8, 8), 3, 1, 1),
+    (3, 1, 96, 160, (9, 20, 12), 3, 1, 1),
+    (3, 2, 1, 32, (6, 10, 12), 3, 1, 1),
+    (3, 1, 32, 1, (6, 10, 12), 3, 1, 1),
+    (3, 1, 256, 256, (8, 16, 16), 3, 1, 1),
+    (2, 1, 64, 64, (16, 16), 3, 2, 1),
+    (2, 1, 128, 128, (17, 31), 3, 2, 1),
+    (3, 1, 64, 96, (8, 12, 16), 3, 2, 1),
+    (3, 1, 32, 64, (8, 8, 8), 4, 2, 1),
+    (2, 1, 8, 8, (4, 4), 3, 1, 1),
+    (3, 1, 8, 16, (4, 4, 4), 3, 1, 1),
+]
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["check", "tcgen05"])
+@pytest.mark.parametrize("case", CONV_CASES, ids=[str(c) for c in CONV_CASES])
+def test_conv(cuda_device, case, impl):
+    ops = _ops()
+    sd, N, Cin, Cout, sp, k, s, p = case
+    torch.manual_seed(hash(case) % 1000)
+    x = torch.randn(N, Cin, *sp)
+    w = torch.randn(Cout, Cin, *([k] * sd)) / math.sqrt(Cin * k ** sd)
+    b = torch.randn(Cout)
+    conv = F.conv2d if sd == 2 else F.conv3d
+    ref = conv(bf(x), bf(w), b, stride=s, padding=p)
+    pc = ops.PackedConv(w.cuda(), b.cuda(), s, p)
+    out = ops.conv(ops.to_cl(x.cuda()), pc, impl=impl)
+    got = ops.from_cl(out)
+    assert tuple(got.shape) == tuple(ref.shape)
+    assert_close(got, ref, 1e-2, f"conv {case} impl={impl}")
+
+
+def test_conv_asym_pad(cuda_device):
+    """AutoencoderKL Downsample: F.pad (0,1) per dim then k3 s2 p0 (autoencoderkl.py:107-120)."""
+    ops = _ops()
+    for sd, sp in ((2, (16, 18)), (3, (8, 10, 12))):
+        x = torch.randn(1, 64, *sp)
+        w = torch.randn(64, 64, *([3] * sd)) / math.sqrt(64 * 3 ** sd)
+        b = torch.randn(64)
+        conv = F.conv2d if sd == 2 else F.conv3d
+        ref = conv(F.pad(bf(x), (0, 1) * sd), bf(w), b, stride=2, padding=0)
+        pc = ops.PackedConv(w.cuda(), b.cuda(), 2, [(0, 1)] * sd)
+        got = ops.from_cl(ops.conv(ops.to_cl(x.cuda()), pc))
+        assert tuple(got.shape) == tuple(ref.shape)
+        assert_close(got, ref, 1e-2, f"asym-pad conv {sd}d")
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["check", "tcgen05"])
+def test_conv_concat_epilogue(cuda_device, impl):
+    """Two-source (virtual concat) conv with the full epilogue: bias + temb row vector, SiLU, scale, residual, ReLU."""
+    ops = _ops()
+    torch.manual_seed(3)
+    N, C0, C1, Cout, sp = 2, 64, 32, 96, (6, 10, 12)
+    x0, x1 = torch.randn(N, C0, *sp), torch.randn(N, C1, *sp)
+    w = torch.randn(Cout, C0 + C1, 3, 3, 3) / math.sqrt((C0 + C1) * 27)
+    b = torch.randn(Cout)
+    temb = torch.randn(N, Cout)
+    res = torch.randn(N, Cout, *sp)
+    ref = F.conv3d(torch.cat([bf(x0), bf(x1)], 1), bf(w), b, padding=1) + temb[:, :, None, None, None]
+    ref = F.relu(bf(res) + 0.5 * F.silu(ref))
+    pc = ops.PackedConv(w.cuda(), b.cuda(), 1, 1, splits=[C0, C1])
+    out = ops.conv([ops.to_cl(x0.cuda()), ops.to_cl(x1.cuda())], pc, rowvec=temb.cuda(), act1=ops.ACT_SILU,
+                   scale=0.5, residual=ops.to_cl(res.cuda()), act2=ops.ACT_RELU, impl=impl)
+    assert_close(ops.from_cl(out), ref, 1e-2, "concat conv + epilogue")
+    # batch-broadcast row vector and fp32 output
+    out32 = ops.conv([ops.to_cl(x0.cuda()), ops.to_cl(x1.cuda())], pc, rowvec=temb[:1].cuda(), out_f32=True, impl=impl)
+    ref32 = F.conv3d(torch.cat([bf(x0), bf(x1)], 1), bf(w), b, padding=1) + temb[:1, :, None, None, None]
+    got32 = ops.from_cl_f32(out32, Cout, 3)
+    assert_close(got32, ref32, 2e-3, "concat conv fp32 out")
+
+
+@pytest.mark.parametrize("sd,sp", [(2, (8, 12)), (3, (4, 6, 8))])
+def test_conv_transpose(cuda_device, sd, sp):
+    """VQVAE decoder upsampling: ConvTranspose k4 s2 p1 (+ReLU) as per-phase implicit GEMMs (vqvae.py:220-260)."""
+    ops = _ops()
+    torch.manual_seed(5)
+    Cin, Cout = 64, 48
+    x = torch.randn(2, Cin, *sp)
+    w = torch.randn(Cin, Cout, *([4] * sd)) / math.sqrt(Cin * 2 ** sd)
+    b = torch.randn(Cout)
+    convt = F.conv_transpose2d if sd == 2 else F.conv_transpose3d
+    ref = F.relu(convt(bf(x), bf(w), b, stride=2, padding=1, output_padding=0))
+    pt = ops.PackedConvTranspose(w.cuda(), b.cuda(), 2, 1, 0)
+    got = ops.from_cl(ops.conv_transpose(ops.to_cl(x.cuda()), pt, act1=ops.ACT_RELU))
+    assert tuple(got.shape) == tuple(ref.shape)
+    assert_close(got, ref, 1e-2, f"conv_transpose {sd}d")
+
+
+@pytest.mark.parametrize("M,K,O", [(256, 64, 64), (1000, 320, 512), (77, 40, 24), (4096, 1024, 16), (130, 2048, 256)])
+def test_linear(cuda_device, M, K, O):
+    ops = _ops()
+    torch.manual_seed(M)
+    x = torch.randn(1, K, 1, M)          # NCHW with W = rows
+    w = torch.randn(O, K) / math.sqrt(K)
+    b = torch.randn(O)
+    ref = F.linear(bf(x)[0, :, 0].t(), bf(w), b)     # [M, O]
+    pl = ops.PackedLinear(w.cuda(), b.cuda())
+    out = ops.linear(ops.to_cl(x.cuda()), pl)
+    got = out.t[0, 0, 0, :, :O].float().cpu()
+    assert_close(got, ref, 1e-2, f"linear {M}x{K}x{O}")
+
+
+# ------------------------------------------------------------------------------------------------ norms
+@pytest.mark.parametrize("shape,groups", [((2, 64, 9, 7), 32), ((1, 256, 6, 10, 12), 32), ((2, 8, 4, 4), 4),
+                                            ((1, 96, 5, 5, 5), 32), ((1, 4, 8, 8), 2)])
+def test_groupnorm_silu(cuda_device, shape, groups):
+    ops = _ops()
+    torch.manual_seed(1)
+    x = torch.randn(shape) * 2 + 0.5
+    g, b = torch.randn(shape[1]), torch.randn(shape[1])
+    ref = F.silu(F.group_norm(bf(x), groups, g, b, eps=1e-6))
+    out = ops.groupnorm(ops.to_cl(x.cuda()), groups, 1e-6, g.cuda(), b.cuda(), act=ops.ACT_SILU)
+    assert_close(ops.from_cl(out), ref, 1e-2, f"groupnorm {shape}")
+
+
+def test_groupnorm_concat(cuda_device):
+    """GroupNorm over a virtual concat whose groups straddle the two tensors (768 = 512 + 256, 24 ch / group)."""
+    ops = _ops()
+    torch.manual_seed(2)
+    x0, x1 = torch.randn(1, 512, 4, 5, 6), torch.randn(1, 256, 4, 5, 6) + 1.0
+    g, b = torch.randn(768), torch.randn(768)
+    ref = F.group_norm(torch.cat([bf(x0), bf(x1)], 1), 32, g, b, eps=1e-6)
+    out = ops.groupnorm([ops.to_cl(x0.cuda()), ops.to_cl(x1.cuda())], 32, 1e-6, g.cuda(), b.cuda())
+    assert_close(ops.from_cl(out), ref, 1e-2, "groupnorm concat")
+
+
+def test_layernorm_geglu(cuda_device):
+    ops = _ops()
+    torch.manual_seed(4)
+    M, Cc = 300, 256
+    x = torch.randn(1, Cc, 1, M) * 3
+    g, b = torch.randn(Cc), torch.randn(Cc)
+    ref = F.layer_norm(bf(x)[0, :, 0].t(), (Cc,), g, b, 1e-5)
+    out = ops.layernorm(ops.to_cl(x.cuda()), g.cuda(), b.cuda(), 1e-5)
+    assert_close(out.t[0, 0, 0, :, :Cc], ref, 1e-2, "layernorm")
+    xa = bf(x)[0, :, 0].t()
+    a, gate = xa.chunk(2, -1)
+    refg = a * F.gelu(gate)
+    outg = ops.geglu(ops.to_cl(x.cuda()))
+    assert_close(outg.t[0, 0, 0, :, : Cc // 2], refg, 1e-2, "geglu")
+
+
+# ------------------------------------------------------------------------------------------------ resampling
+def test_resample(cuda_device):
+    ops = _ops()
+    for shape in ((2, 16, 5, 6), (1, 24, 3, 4, 5)):
+        x = torch.randn(shape)
+        up = ops.from_cl(ops.upsample_nearest2x(ops.to_cl(x.cuda()))).cpu()
+        assert torch.equal(up, F.interpolate(bf(x), scale_factor=2.0, mode="nearest"))
+    for shape in ((2, 16, 6, 8), (1, 24, 4, 6, 8)):
+        x = torch.randn(shape)
+        pool = F.avg_pool2d if len(shape) == 4 else F.avg_pool3d
+        got = ops.from_cl(ops.avgpool2(ops.to_cl(x.cuda())))
+        assert_close(got, pool(bf(x), 2, 2), 1e-2, "avgpool2")
+    a, b = torch.randn(1, 16, 4, 4), torch.randn(1, 16, 4, 4)
+    got = ops.from_cl(ops.axpy(ops.to_cl(a.cuda()), ops.to_cl(b.cuda()), 0.75))
+    assert_close(got, bf(a) + 0.75 * bf(b), 1e-2, "axpy")
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def _attn_ref(q, k, v, heads, dh, scale):
+    B, T, _ = q.shape
+    S = k.shape[1]
+    qh = q.view(B, T, heads, dh).transpose(1, 2)
+    kh = k.view(B, S, heads, dh).transpose(1, 2)
+    vh = v.view(B, S, heads, dh).transpose(1, 2)
+    p = torch.softmax(scale * qh @ kh.transpose(-1, -2), dim=-1)
+    return (p @ vh).transpose(1, 2).reshape(B, T, heads * dh)
+
+
+@pytest.mark.parametrize("B,T,S,heads,dh", [(2, 64, 64, 2, 4), (1, 16, 16, 1, 8), (2, 100, 3, 1, 256), (1, 50, 1, 2, 64)])
+def test_attention_small(cuda_device, B, T, S, heads, dh):
+    ops = _ops()
+    torch.manual_seed(7)
+    Cc = heads * dh
+    P = (Cc + 7) // 8 * 8
+    q, k, v = torch.randn(B, T, Cc), torch.randn(B, S, Cc), torch.randn(B, S, Cc)
+    ref = _attn_ref(bf(q), bf(k), bf(v), heads, dh, 1 / math.sqrt(dh))
+    pad = lambda t: F.pad(t, (0, P - Cc)).to(torch.bfloat16).cuda().contiguous()
+    out = ops.attention(pad(q), pad(k), pad(v), heads, dh, 1 / math.sqrt(dh))
+    assert_close(out[..., :Cc], ref, 1e-2, "attention_small")
+
+
+@pytest.mark.parametrize("B,T,heads,dh", [(1, 256, 1, 256), (2, 200, 1, 512), (1, 1024, 2, 64)])
+def test_attention_tensorcore(cuda_device, B, T, heads, dh):
+    """QK^T / softmax / PV on the tcgen05 GEMM path, V^T produced by the operand-swapped projection."""
+    ops = _ops()
+    torch.manual_seed(8)
+    Cc = heads * dh
+    x = torch.randn(B, T, Cc)
+    wq, wk, wv = (torch.randn(Cc, Cc) / math.sqrt(Cc) for _ in range(3))
+    bv = torch.randn(Cc)
+    xb = bf(x)
+    q, k, v = F.linear(xb, bf(wq)), F.linear(xb, bf(wk)), F.linear(xb, bf(wv), bv)
+    ref = _attn_ref(bf(q), bf(k), bf(v), heads, dh, 1 / math.sqrt(dh))
+    xc = ops.CL(x.to(torch.bfloat16).cuda().reshape(B, 1, 1, T, Cc), Cc, 2)
+    plq, plk = ops.PackedLinear(wq.cuda(), None), ops.PackedLinear(wk.cuda(), None)
+    plv = ops.PackedLinear(wv.cuda(), bv.cuda())
+    qg = ops.linear(xc, plq).t.reshape(B, T, -1)
+    kg = ops.linear(xc, plk).t.reshape(B, T, -1)
+    vt = ops.linear_transposed(xc.t.reshape(B, T, Cc), Cc, plv)
+    assert_close(vt[:, :, :T].transpose(1, 2), bf(v), 1e-2, "V^T projection")
+    out = ops.attention(qg, kg, None, heads, dh, 1 / math.sqrt(dh), vt=vt)
+    assert_close(out[..., :Cc], ref, 2e-2, "attention tensor-core")
+
+
+# ------------------------------------------------------------------------------------------------ time embedding
+def test_timestep_embedding_and_small_linear(cuda_device):
+    ops = _ops()
+    t = torch.tensor([0.0, 1.0, 250.0, 999.0])
+    for dim in (32, 33, 256):
+        half = dim // 2
+        exponent = -math.log(10000) * torch.arange(0, half, dtype=torch.float32)
+        freqs = torch.exp(exponent / half)
+        args = t[:, None] * freqs[None]
+        ref = torch.cat([torch.cos(args), torch.sin(args)], -1)
+        if dim % 2:
+            ref = F.pad(ref, (0, 1))
+        got = ops.timestep_embedding(t.cuda(), dim).cpu()
+        assert (got - ref).abs().max().item() < 2e-4
+    x = torch.randn(3, 100)
+    w, b = torch.randn(70, 100) / 10, torch.randn(70)
+    ref = F.silu(F.linear(F.silu(x), w, b))
+    got = ops.small_linear(x.cuda(), w.cuda(), b.cuda(), ops.ACT_SILU, ops.ACT_SILU).cpu()
+    assert (got - ref).abs().max().item() < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ perf smoke (prints)
+def test_conv_perf_probe(cuda_device, capsys):
+    """Not a benchmark: one warm conv at a C3-like tile mix to catch gross slowness early (printed with -s)."""
+    ops = _ops()
+    x = torch.randn(1, 256, 16, 112, 80)
+    w = torch.randn(256, 256, 3, 3, 3) / 80
+    pc = ops.PackedConv(w.cuda(), None, 1, 1)
+    a = ops.to_cl(x.cuda())
+    for _ in range(2):
+        ops.conv(a, pc)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        ops.conv(a, pc)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    flops = 2 * 16 * 112 * 80 * 256 * 256 * 27
+    with capsys.disabled():
+        print(f"\n[perf-probe] conv3d 256->256 k3 @16x112x80: {ms:.3f} ms, {flops / ms / 1e9:.1f} TFLOP/s")
+    assert ms > 0
