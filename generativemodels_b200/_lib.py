@@ -87,6 +87,7 @@ SIGNATURES = {
     "b200_version": [],
     "b200_device_check": [],
     "b200_sm_count": [],
+    "b200_abi_sizeof": [C.c_int],
     "b200_igemm": [C.POINTER(IgemmParams), _P],
     "b200_groupnorm_workspace_bytes": [_I32, _I64, _I32],
     "b200_groupnorm_stats": [C.POINTER(GnStatsParams), _P],
@@ -129,6 +130,11 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the .so does not export it
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, C.c_int)
+    for which, struct in enumerate((IgemmParams, GnStatsParams, GnApplyParams, DdimCoef, DdpmCoef, PndmCoef, IgemmSeg)):
+        c_size = lib.b200_abi_sizeof(which)
+        if c_size != C.sizeof(struct):
+            raise B200Error(f"ABI mismatch: {struct.__name__} is {C.sizeof(struct)} bytes in Python but {c_size} in "
+                            f"{LIB_PATH.name}; rebuild the library (generativemodels_b200/csrc/build.sh)")
     _lib = lib
     return lib
 

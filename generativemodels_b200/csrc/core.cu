@@ -50,3 +50,16 @@ extern "C" int b200_device_check(void) {
   }
   return B200_OK;
 }
+
+extern "C" int b200_abi_sizeof(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(b200_igemm_params);
+    case 1: return (int)sizeof(b200_gn_stats_params);
+    case 2: return (int)sizeof(b200_gn_apply_params);
+    case 3: return (int)sizeof(b200_ddim_coef);
+    case 4: return (int)sizeof(b200_ddpm_coef);
+    case 5: return (int)sizeof(b200_pndm_coef);
+    case 6: return (int)sizeof(b200_igemm_seg);
+    default: return -1;
+  }
+}

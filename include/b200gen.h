@@ -41,6 +41,9 @@ int b200_version(void);
 /* 0 iff the current CUDA device is sm_100-class (fails loudly elsewhere: there is no fallback). */
 int b200_device_check(void);
 int b200_sm_count(void);
+/* sizeof() of the parameter structs below, for binding-layer ABI checks:
+ * 0 igemm_params, 1 gn_stats_params, 2 gn_apply_params, 3 ddim_coef, 4 ddpm_coef, 5 pndm_coef, 6 igemm_seg. */
+int b200_abi_sizeof(int which);
 
 /* ------------------------------------------------------------------------------------------------
  * Implicit-GEMM on tcgen05 tensor cores (TMA-staged NDHWC tiles, accumulators in TMEM).

@@ -82,8 +82,13 @@ CONV_CASES = [
 ]
 
 
+def _case_id(c):
+    sd, N, Cin, Cout, sp, k, s, p = c
+    return f"conv{sd}d_n{N}_{Cin}to{Cout}_" + "x".join(map(str, sp)) + f"_k{k}s{s}p{p}"
+
+
 @pytest.mark.parametrize("impl", [1, 0], ids=["check", "tcgen05"])
-@pytest.mark.parametrize("case", CONV_CASES, ids=[str(c) for c in CONV_CASES])
+@pytest.mark.parametrize("case", CONV_CASES, ids=[_case_id(c) for c in CONV_CASES])
 def test_conv(cuda_device, case, impl):
     ops = _ops()
     sd, N, Cin, Cout, sp, k, s, p = case
