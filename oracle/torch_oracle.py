@@ -479,7 +479,7 @@ def noise_schedule(name: str, num_train_timesteps: int, **kw) -> torch.Tensor:
         ac = torch.cos(((x / num_train_timesteps) + s) / (1 + s) * torch.pi * 0.5) ** 2
         ac /= ac[0].item()
         alphas = torch.clip(ac[1:] / ac[:-1], 0.0001, 0.9999)
-        return 1.0 - alphas
+        return 1.0 - alphas, alphas, ac[:-1]          # the cosine schedule returns the triple (scheduler.py:83-89)
     raise ValueError(f"unknown schedule {name}")
 
 
@@ -488,9 +488,13 @@ class SchedulerTables:
 
     def __init__(self, num_train_timesteps=1000, schedule="linear_beta", **schedule_args):
         self.num_train_timesteps = num_train_timesteps
-        self.betas = noise_schedule(schedule, num_train_timesteps, **schedule_args)
-        self.alphas = 1.0 - self.betas
-        self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
+        ns = noise_schedule(schedule, num_train_timesteps, **schedule_args)
+        if isinstance(ns, tuple):
+            self.betas, self.alphas, self.alphas_cumprod = ns
+        else:
+            self.betas = ns
+            self.alphas = 1.0 - self.betas
+            self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
         self.one = torch.tensor(1.0)
 
 

@@ -1,0 +1,89 @@
+"""Small model configurations shared by the golden-vector generator and the parity tests.
+
+Each entry: constructor kwargs in the reference's own vocabulary + the oracle cfg derived from them.  Channels are
+multiples of 8 (and of the group count) so the CUDA path runs its vectorised kernels; sizes are chosen so the CPU
+oracle finishes in well under a second per forward.
+"""
+
+UNET_CASES = {
+    "unet2d_attn": dict(spatial_dims=2, in_channels=1, out_channels=1, num_res_blocks=1, num_channels=(32, 64, 64),
+                        attention_levels=(False, True, True), norm_num_groups=8, num_head_channels=(0, 32, 64)),
+    "unet3d_attn": dict(spatial_dims=3, in_channels=1, out_channels=1, num_res_blocks=(1, 2), num_channels=(32, 64),
+                        attention_levels=(False, True), norm_num_groups=8, num_head_channels=(0, 64)),
+    "unet2d_small_heads": dict(spatial_dims=2, in_channels=3, out_channels=3, num_res_blocks=1, num_channels=(16, 16),
+                               attention_levels=(True, True), norm_num_groups=8, num_head_channels=4),
+    "unet2d_cross": dict(spatial_dims=2, in_channels=3, out_channels=3, num_res_blocks=1, num_channels=(32, 64),
+                         attention_levels=(False, True), norm_num_groups=8, num_head_channels=(0, 32),
+                         with_conditioning=True, cross_attention_dim=8, transformer_num_layers=1),
+    "unet2d_updown_class": dict(spatial_dims=2, in_channels=2, out_channels=2, num_res_blocks=1, num_channels=(16, 32),
+                                attention_levels=(False, True), norm_num_groups=8, num_head_channels=16,
+                                resblock_updown=True, num_class_embeds=5),
+}
+UNET_INPUTS = {
+    "unet2d_attn": dict(shape=(2, 1, 16, 16)),
+    "unet3d_attn": dict(shape=(1, 1, 8, 12, 8)),
+    "unet2d_small_heads": dict(shape=(2, 3, 8, 8)),
+    "unet2d_cross": dict(shape=(2, 3, 16, 16), context=(2, 3, 8)),
+    "unet2d_updown_class": dict(shape=(2, 2, 16, 16), classes=True),
+}
+
+CONTROLNET_CASE = dict(spatial_dims=2, in_channels=3, num_res_blocks=1, num_channels=(32, 64),
+                       attention_levels=(False, True), norm_num_groups=8, num_head_channels=(0, 32),
+                       with_conditioning=True, cross_attention_dim=8, conditioning_embedding_in_channels=1,
+                       conditioning_embedding_num_channels=(16,))
+
+AEKL_CASES = {
+    "aekl2d": dict(spatial_dims=2, in_channels=1, out_channels=1, num_channels=(16, 32), latent_channels=3,
+                   num_res_blocks=(1, 1), norm_num_groups=8, attention_levels=(False, False),
+                   with_encoder_nonlocal_attn=False, with_decoder_nonlocal_attn=False),
+    "aekl3d_attn": dict(spatial_dims=3, in_channels=1, out_channels=1, num_channels=(16, 16), latent_channels=4,
+                        num_res_blocks=(1, 1), norm_num_groups=8, attention_levels=(False, True),
+                        with_encoder_nonlocal_attn=True, with_decoder_nonlocal_attn=True),
+    "aekl2d_convT": dict(spatial_dims=2, in_channels=1, out_channels=1, num_channels=(16, 32), latent_channels=3,
+                         num_res_blocks=(1, 1), norm_num_groups=8, attention_levels=(False, False),
+                         with_encoder_nonlocal_attn=False, with_decoder_nonlocal_attn=False, use_convtranspose=True),
+}
+AEKL_INPUTS = {"aekl2d": (2, 1, 16, 16), "aekl3d_attn": (1, 1, 8, 8, 8), "aekl2d_convT": (1, 1, 16, 16)}
+
+VQVAE_CASES = {
+    "vqvae3d": dict(spatial_dims=3, in_channels=1, out_channels=1, num_channels=(16, 16), num_res_channels=16,
+                    num_res_layers=1, downsample_parameters=((2, 4, 1, 1),) * 2,
+                    upsample_parameters=((2, 4, 1, 1, 0),) * 2, num_embeddings=32, embedding_dim=8),
+    "vqvae2d": dict(spatial_dims=2, in_channels=1, out_channels=1, num_channels=(16, 32), num_res_channels=(16, 32),
+                    num_res_layers=2, downsample_parameters=((2, 4, 1, 1),) * 2,
+                    upsample_parameters=((2, 4, 1, 1, 0),) * 2, num_embeddings=64, embedding_dim=16),
+}
+VQVAE_INPUTS = {"vqvae3d": (1, 1, 16, 16, 16), "vqvae2d": (2, 1, 32, 32)}
+
+
+def head_channels_tuple(kw):
+    n = len(kw["num_channels"])
+    nhc = kw.get("num_head_channels", 8)
+    return tuple(nhc) if isinstance(nhc, (tuple, list)) else (nhc,) * n
+
+
+def unet_oracle_cfg(kw):
+    return dict(num_head_channels=head_channels_tuple(kw), norm_num_groups=kw.get("norm_num_groups", 32),
+                norm_eps=kw.get("norm_eps", 1e-6), with_conditioning=kw.get("with_conditioning", False))
+
+
+def aekl_oracle_cfg(kw):
+    return dict(norm_num_groups=kw.get("norm_num_groups", 32), norm_eps=kw.get("norm_eps", 1e-6),
+                use_convtranspose=kw.get("use_convtranspose", False))
+
+
+def vqvae_oracle_cfg(kw):
+    return dict(downsample_parameters=kw["downsample_parameters"], upsample_parameters=kw["upsample_parameters"],
+                commitment_cost=kw.get("commitment_cost", 0.25), output_act=kw.get("output_act"))
+
+
+def randomize_zero_params(module, std=0.02, seed=1):
+    """zero_module() leaves conv2 / proj_out / out convs all-zero; redraw them so parity tests are not vacuous
+    (SURVEY.md §7 'reference quirks')."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for p in module.parameters():
+            if p.numel() > 0 and float(p.abs().max()) == 0.0:
+                p.copy_(torch.randn(p.shape, generator=g) * std)
+    return module

@@ -1,0 +1,166 @@
+"""Pin oracle/torch_oracle.py against the UNMODIFIED reference (imported from /root/reference on the MONAI shim).
+Runs only where the reference tree exists (the build container); the GPU box relies on tests/golden fixtures."""
+import pytest
+import torch
+
+from oracle import ref_import
+from oracle import torch_oracle as O
+from tests.golden import configs as G
+
+pytestmark = pytest.mark.skipif(not ref_import.available(), reason="/root/reference not present")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    ref_import.import_reference()
+    import generative.networks.nets as nets
+    import generative.networks.schedulers as sch
+    return nets, sch
+
+
+def _close(a, b, tol=2e-5):
+    err = (a - b).abs().max().item()
+    assert err <= tol * max(1.0, b.abs().max().item()), f"max abs err {err:.3e}"
+
+
+@pytest.mark.parametrize("name", list(G.UNET_CASES))
+def test_unet(ref, name):
+    nets, _ = ref
+    kw = G.UNET_CASES[name]
+    torch.manual_seed(0)
+    m = G.randomize_zero_params(nets.DiffusionModelUNet(**kw)).eval()
+    inp = G.UNET_INPUTS[name]
+    torch.manual_seed(1)
+    x = torch.randn(inp["shape"])
+    t = torch.randint(0, 1000, (inp["shape"][0],)).long()
+    ctx = torch.randn(inp["context"]) if "context" in inp else None
+    cls = torch.randint(0, 5, (inp["shape"][0],)) if inp.get("classes") else None
+    with torch.no_grad():
+        want = m(x, t, context=ctx, class_labels=cls)
+        got = O.unet_forward(m.state_dict(), G.unet_oracle_cfg(kw), x, t, context=ctx, class_labels=cls)
+    _close(got, want)
+
+
+def test_controlnet(ref):
+    nets, _ = ref
+    kw = G.CONTROLNET_CASE
+    torch.manual_seed(0)
+    cn = G.randomize_zero_params(nets.ControlNet(**kw)).eval()
+    ukw = {k: v for k, v in kw.items() if not k.startswith("conditioning_embedding")}
+    un = G.randomize_zero_params(nets.DiffusionModelUNet(out_channels=3, **ukw)).eval()
+    torch.manual_seed(2)
+    x, cond, ctx = torch.randn(2, 3, 16, 16), torch.rand(2, 1, 16, 16), torch.randn(2, 1, 8)
+    t = torch.tensor([10, 500]).long()
+    cfg = G.unet_oracle_cfg(kw)
+    with torch.no_grad():
+        d_w, m_w = cn(x, t, cond, conditioning_scale=0.7, context=ctx)
+        d_g, m_g = O.controlnet_forward(cn.state_dict(), cfg, x, t, cond, 0.7, ctx)
+        for a, b in zip(d_g, d_w):
+            _close(a, b)
+        _close(m_g, m_w)
+        want = un(x, t, context=ctx, down_block_additional_residuals=d_w, mid_block_additional_residual=m_w)
+        got = O.unet_forward(un.state_dict(), cfg, x, t, context=ctx, down_block_additional_residuals=d_g,
+                             mid_block_additional_residual=m_g)
+    _close(got, want)
+
+
+@pytest.mark.parametrize("name", list(G.AEKL_CASES))
+def test_autoencoderkl(ref, name):
+    nets, _ = ref
+    kw = G.AEKL_CASES[name]
+    torch.manual_seed(0)
+    m = nets.AutoencoderKL(**kw).eval()
+    torch.manual_seed(3)
+    x = torch.randn(G.AEKL_INPUTS[name])
+    cfg = G.aekl_oracle_cfg(kw)
+    with torch.no_grad():
+        mu_w, sig_w = m.encode(x)
+        mu_g, sig_g = O.autoencoderkl_encode(m.state_dict(), cfg, x)
+        _close(mu_g, mu_w)
+        _close(sig_g, sig_w)
+        _close(O.autoencoderkl_decode(m.state_dict(), cfg, mu_w), m.decode(mu_w))
+
+
+@pytest.mark.parametrize("name", list(G.VQVAE_CASES))
+def test_vqvae(ref, name):
+    nets, _ = ref
+    kw = G.VQVAE_CASES[name]
+    torch.manual_seed(0)
+    m = nets.VQVAE(**kw).eval()
+    torch.manual_seed(4)
+    x = torch.rand(G.VQVAE_INPUTS[name])
+    cfg = G.vqvae_oracle_cfg(kw)
+    sd = m.state_dict()
+    with torch.no_grad():
+        rec_w, loss_w = m(x)
+        idx_w = m.index_quantize(x)
+        rec_g, loss_g, idx_g = O.vqvae_forward(sd, cfg, x)
+        assert torch.equal(idx_g, idx_w)
+        _close(rec_g, rec_w)
+        _close(loss_g, loss_w)
+        _close(O.vqvae_decode(sd, cfg, O.vq_embed(sd["quantizer.quantizer.embedding.weight"], idx_w)),
+               m.decode_samples(idx_w))
+        _close(O.vq_forward(sd["quantizer.quantizer.embedding.weight"], m.encode(x))[3], m.quantizer.perplexity)
+
+
+SCHED = [
+    ("ddim", dict(num_train_timesteps=1000, schedule="linear_beta", beta_start=0.0015, beta_end=0.0195), 50),
+    ("ddim", dict(num_train_timesteps=1000, schedule="scaled_linear_beta", beta_start=0.0005, beta_end=0.0195,
+                  clip_sample=False), 50),
+    ("ddim", dict(num_train_timesteps=100, prediction_type="v_prediction", set_alpha_to_one=False, steps_offset=1), 10),
+    # (cosine has alphas_cumprod[0] == 1 exactly: t = 0 divides by zero in the reference itself, so offset by 1)
+    ("ddim", dict(num_train_timesteps=100, prediction_type="sample", schedule="cosine", steps_offset=1,
+                  set_alpha_to_one=False), 7),
+    ("ddpm", dict(num_train_timesteps=1000), 4),
+    ("ddpm", dict(num_train_timesteps=100, variance_type="fixed_large", prediction_type="v_prediction",
+                  schedule="sigmoid_beta"), 10),
+    ("pndm", dict(num_train_timesteps=1000, skip_prk_steps=True), 20),
+    ("pndm", dict(num_train_timesteps=1000, skip_prk_steps=False), 20),
+    ("pndm", dict(num_train_timesteps=100, skip_prk_steps=False, prediction_type="v_prediction",
+                  set_alpha_to_one=True, steps_offset=1), 10),
+]
+
+
+@pytest.mark.parametrize("kind,kw,steps", SCHED, ids=[f"{k}-{i}" for i, (k, _, _) in enumerate(SCHED)])
+def test_scheduler_trajectory(ref, kind, kw, steps):
+    """Identical model-output sequence through the reference scheduler and the restated one: every step equal."""
+    _, sch = ref
+    R = {"ddim": sch.DDIMScheduler, "ddpm": sch.DDPMScheduler, "pndm": sch.PNDMScheduler}[kind](**kw)
+    M = {"ddim": O.DDIMOracle, "ddpm": O.DDPMOracle, "pndm": O.PNDMOracle}[kind](**kw)
+    R.set_timesteps(steps)
+    M.set_timesteps(steps)
+    assert torch.equal(R.timesteps, M.timesteps)
+    assert torch.equal(R.alphas_cumprod, M.alphas_cumprod)
+    torch.manual_seed(5)
+    xr = xm = torch.randn(2, 3, 8, 8)
+    for t in R.timesteps:
+        eps = torch.tanh(xr * 0.7 + 0.01 * float(t))      # any deterministic stand-in for the network
+        epsm = torch.tanh(xm * 0.7 + 0.01 * float(t))
+        if kind == "ddpm":
+            gr, gm = torch.Generator().manual_seed(int(t)), torch.Generator().manual_seed(int(t))
+            xr, _ = R.step(eps, int(t), xr, generator=gr)
+            xm, _ = M.step(epsm, int(t), xm, generator=gm)
+        else:
+            xr, _ = R.step(eps, int(t), xr)
+            xm, _ = M.step(epsm, int(t), xm)
+        assert torch.equal(xr, xm), f"diverged at t={int(t)}"
+
+
+def test_inferer_sample(ref):
+    nets, sch = ref
+    from generative.inferers import DiffusionInferer
+    kw = G.UNET_CASES["unet2d_attn"]
+    torch.manual_seed(0)
+    m = G.randomize_zero_params(nets.DiffusionModelUNet(**kw)).eval()
+    skw = dict(num_train_timesteps=1000, schedule="linear_beta", beta_start=0.0015, beta_end=0.0195)
+    R, M = sch.DDIMScheduler(**skw), O.DDIMOracle(**skw)
+    R.set_timesteps(5)
+    M.set_timesteps(5)
+    torch.manual_seed(7)
+    noise = torch.randn(1, 1, 16, 16)
+    cfg = G.unet_oracle_cfg(kw)
+    sd = m.state_dict()
+    with torch.no_grad():
+        want = DiffusionInferer(R).sample(input_noise=noise, diffusion_model=m, scheduler=R, verbose=False)
+        got = O.diffusion_sample(lambda x, t, c: O.unet_forward(sd, cfg, x, t, context=c), M, noise)
+    _close(got, want, 1e-4)
