@@ -98,6 +98,7 @@ SIGNATURES = {
     "b200_upsample_nearest2x": [_P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P],
     "b200_avgpool2": [_P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P],
     "b200_axpy_bf16": [_P, _P, _F, _P, _I64, _P],
+    "b200_copy_channels": [_P, _I32, _I32, _P, _I32, _I32, _I64, _P],
     "b200_geglu": [_P, _I64, _I32, _I32, _P, _I32, _P],
     "b200_softmax_rows": [_P, _I64, _I32, _I64, _P, _I64, _P],
     "b200_attention_small": [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _F, _P],
@@ -106,6 +107,9 @@ SIGNATURES = {
     "b200_ddim_step": [_P, _P, _P, C.POINTER(DdimCoef), _P, _P, _I64, _P],
     "b200_ddpm_step": [_P, _P, _P, _P, C.POINTER(DdpmCoef), _P, _P, _I64, _P],
     "b200_pndm_step": [C.POINTER(_P), _P, C.POINTER(PndmCoef), _P, _P, _I64, _P],
+    "b200_exp_half_clamped": [_P, _F, _F, _P, _I64, _P],
+    "b200_scale_f32": [_P, _F, _F, _P, _I64, _P],
+    "b200_fma_f32": [_P, _P, _P, _P, _I64, _P],
     "b200_add_noise": [_P, _P, _P, _P, _F, _I32, _I64, _P, _P],
     "b200_vq_argmin_gather": [_P, _I64, _I32, _I32, _P, _I32, _P, _P, _I32, _P, _I32, _P, _P, _P],
     "b200_vq_gather": [_P, _I64, _P, _I32, _I32, _P, _I32, _P],

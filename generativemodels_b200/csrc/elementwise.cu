@@ -123,6 +123,21 @@ __global__ void axpy_bf16_kernel(const uint4* __restrict__ a, const uint4* __res
   }
 }
 
+__global__ void copy_channels_kernel(const __nv_bfloat16* __restrict__ src, int C, int src_pitch,
+                                     __nv_bfloat16* __restrict__ dst, int dst_pitch, int dst_off, long long rows, int vec) {
+  const int per_row = C / vec;
+  const long long total = rows * per_row;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx / per_row;
+    const int c = (int)(idx % per_row) * vec;
+    if (vec == 8)
+      *reinterpret_cast<uint4*>(dst + r * dst_pitch + dst_off + c) = __ldg(reinterpret_cast<const uint4*>(src + r * src_pitch + c));
+    else
+      dst[r * dst_pitch + dst_off + c] = src[r * src_pitch + c];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // GEGLU: y = x[:, :H] * gelu_erf(x[:, H:])
 // ------------------------------------------------------------------------------------------------
@@ -309,6 +324,22 @@ __global__ void add_noise_kernel(const float* __restrict__ x0, const float* __re
     out[base + i] = a * x0[base + i] + b * noise[base + i];
 }
 
+__global__ void exp_half_clamped_kernel(const float* __restrict__ x, float lo, float hi, float* __restrict__ y, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = expf(fminf(fmaxf(x[i], lo), hi) / 2.0f);
+}
+
+__global__ void fma_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
+                               float* __restrict__ y, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = a[i] + b[i] * c[i];
+}
+
+__global__ void scale_f32_kernel(const float* __restrict__ x, float mul, float div, float* __restrict__ y, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = x[i] * mul / div;
+}
+
 static unsigned grid_for(long long work, int threads = 256, int waves = 8) {
   long long b = (work + threads - 1) / threads;
   const long long cap = (long long)waves * sm_count();
@@ -378,6 +409,18 @@ extern "C" int b200_axpy_bf16(const void* a, const void* b, float alpha, void* y
   axpy_bf16_kernel<<<grid_for(n / 8), 256, 0, stream>>>(reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b),
                                                        alpha, reinterpret_cast<uint4*>(y), n / 8);
   B200_LAUNCH_CHECK("axpy_bf16_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_copy_channels(const void* src, int32_t C, int32_t src_pitch, void* dst, int32_t dst_pitch,
+                                  int32_t dst_off, int64_t rows, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(src && dst && C >= 1 && src_pitch >= C && dst_pitch >= dst_off + C && rows >= 1, "copy_channels: bad arguments");
+  const int vec = (C % 8 == 0 && src_pitch % 8 == 0 && dst_pitch % 8 == 0 && dst_off % 8 == 0 &&
+                   ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0)) ? 8 : 1;
+  copy_channels_kernel<<<grid_for(rows * (C / vec)), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(src), C, src_pitch,
+                                                                     reinterpret_cast<__nv_bfloat16*>(dst), dst_pitch, dst_off, rows, vec);
+  B200_LAUNCH_CHECK("copy_channels_kernel");
   return B200_OK;
 }
 
@@ -466,5 +509,29 @@ extern "C" int b200_add_noise(const float* x0, const float* noise, const float* 
   dim3 grid(grid_for(per_sample, 256, 4), N);
   add_noise_kernel<<<grid, 256, 0, stream>>>(x0, noise, ca, cb, sign_b, per_sample, out);
   B200_LAUNCH_CHECK("add_noise_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_exp_half_clamped(const float* log_var, float lo, float hi, float* sigma, int64_t n, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(log_var && sigma && n >= 1, "exp_half_clamped: bad arguments");
+  exp_half_clamped_kernel<<<grid_for(n), 256, 0, stream>>>(log_var, lo, hi, sigma, n);
+  B200_LAUNCH_CHECK("exp_half_clamped_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_fma_f32(const float* a, const float* b, const float* c, float* out, int64_t n, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(a && b && c && out && n >= 1, "fma_f32: bad arguments");
+  fma_f32_kernel<<<grid_for(n), 256, 0, stream>>>(a, b, c, out, n);
+  B200_LAUNCH_CHECK("fma_f32_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_scale_f32(const float* x, float mul, float div, float* out, int64_t n, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(x && out && n >= 1 && div != 0.f, "scale_f32: bad arguments");
+  scale_f32_kernel<<<grid_for(n), 256, 0, stream>>>(x, mul, div, out, n);
+  B200_LAUNCH_CHECK("scale_f32_kernel");
   return B200_OK;
 }

@@ -1,0 +1,2 @@
+from .inferer import (ControlNetDiffusionInferer, ControlNetLatentDiffusionInferer, DiffusionInferer,  # noqa: F401
+                      LatentDiffusionInferer)

@@ -1,0 +1,250 @@
+"""Sampling drivers with the interface of generative/inferers/inferer.py: DiffusionInferer (30-143),
+LatentDiffusionInferer (323-487), ControlNetDiffusionInferer (561-707), ControlNetLatentDiffusionInferer (856-1038).
+
+The loops are the reference's: one network forward + one ``scheduler.step`` per timestep, the sample travelling
+between them as an NC[D]HW fp32 CUDA tensor.  What differs is underneath — each forward is the fused-kernel UNet, each
+step one elementwise kernel, and ControlNet residuals are handed to the UNet as channels-last handles without a
+layout round trip.  ``get_likelihood`` (a training/evaluation path) is not implemented yet.
+"""
+from __future__ import annotations
+
+from abc import ABC, abstractmethod
+from collections.abc import Callable
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..networks.nets import VQVAE, ControlNet
+
+try:  # tqdm is optional, like in the reference
+    from tqdm import tqdm
+    has_tqdm = True
+except Exception:  # pragma: no cover
+    has_tqdm = False
+
+
+class Inferer(ABC):
+    """Minimal stand-in for monai.inferers.Inferer (an ABC with ``__call__``)."""
+
+    @abstractmethod
+    def __call__(self, inputs, network, *args, **kwargs):
+        raise NotImplementedError
+
+
+def _check_mode(mode: str) -> None:
+    if mode not in ["crossattn", "concat"]:
+        raise NotImplementedError(f"{mode} condition is not supported")
+
+
+def _progress(scheduler, verbose: bool):
+    return tqdm(scheduler.timesteps) if (verbose and has_tqdm) else iter(scheduler.timesteps)
+
+
+def _spatial_pad(img: torch.Tensor, size) -> torch.Tensor:
+    """monai SpatialPad (symmetric, zero) on a channel-first item without batch dim."""
+    sp = img.shape[1:]
+    pads = []
+    for d in reversed(range(len(sp))):
+        tot = max(size[d] - sp[d], 0)
+        pads += [tot // 2, tot - tot // 2]
+    return torch.nn.functional.pad(img, pads)
+
+
+def _center_crop(img: torch.Tensor, roi) -> torch.Tensor:
+    """monai CenterSpatialCrop on a channel-first item; non-positive roi entries keep the dim."""
+    sl = [slice(None)]
+    for d, n in enumerate(img.shape[1:]):
+        r = n if roi[d] <= 0 else min(roi[d], n)
+        start = max(n // 2 - r // 2, 0)
+        sl.append(slice(start, start + r))
+    return img[tuple(sl)]
+
+
+class DiffusionInferer(Inferer):
+    """inferer.py:30-143."""
+
+    def __init__(self, scheduler: nn.Module) -> None:
+        Inferer.__init__(self)
+        self.scheduler = scheduler
+
+    def __call__(self, inputs: torch.Tensor, diffusion_model: Callable[..., torch.Tensor], noise: torch.Tensor,
+                 timesteps: torch.Tensor, condition: torch.Tensor | None = None, mode: str = "crossattn",
+                 seg: torch.Tensor | None = None) -> torch.Tensor:
+        """Training-style forward (inferer.py:44-81): add noise at per-sample timesteps, predict."""
+        _check_mode(mode)
+        noisy_image = self.scheduler.add_noise(original_samples=inputs, noise=noise, timesteps=timesteps)
+        if mode == "concat":
+            noisy_image = torch.cat([noisy_image, condition], dim=1)
+            condition = None
+        return diffusion_model(x=noisy_image, timesteps=timesteps, context=condition)
+
+    @torch.no_grad()
+    def sample(self, input_noise: torch.Tensor, diffusion_model: Callable[..., torch.Tensor],
+               scheduler: Callable[..., torch.Tensor] | None = None, save_intermediates: bool | None = False,
+               intermediate_steps: int | None = 100, conditioning: torch.Tensor | None = None,
+               mode: str = "crossattn", verbose: bool = True, seg: torch.Tensor | None = None):
+        _check_mode(mode)
+        if not scheduler:
+            scheduler = self.scheduler
+        image = input_noise
+        intermediates = []
+        for t in _progress(scheduler, verbose):
+            ts = torch.Tensor((t,)).to(input_noise.device)
+            if mode == "concat":
+                model_output = diffusion_model(torch.cat([image, conditioning], dim=1), timesteps=ts, context=None)
+            else:
+                model_output = diffusion_model(image, timesteps=ts, context=conditioning)
+            image, _ = scheduler.step(model_output, t, image)
+            if save_intermediates and t % intermediate_steps == 0:
+                intermediates.append(image)
+        return (image, intermediates) if save_intermediates else image
+
+    def get_likelihood(self, *args, **kwargs):
+        raise NotImplementedError("get_likelihood is a training/evaluation path outside the sampling hot path "
+                                  "(SURVEY.md §8f); it is not implemented on the B200 kernels yet")
+
+
+class _LatentMixin:
+    def _init_latent(self, scale_factor, ldm_latent_shape, autoencoder_latent_shape):
+        self.scale_factor = scale_factor
+        if (ldm_latent_shape is None) ^ (autoencoder_latent_shape is None):
+            raise ValueError("If ldm_latent_shape is None, autoencoder_latent_shape must be None" "and vice versa.")
+        self.ldm_latent_shape = ldm_latent_shape
+        self.autoencoder_latent_shape = autoencoder_latent_shape
+
+    def _encode_latent(self, inputs, autoencoder_model, quantized):
+        with torch.no_grad():
+            if isinstance(autoencoder_model, VQVAE):
+                latent = autoencoder_model.encode_stage_2_inputs(inputs, quantized=quantized)
+            else:
+                latent = autoencoder_model.encode_stage_2_inputs(inputs)
+            latent = ops.scale_f32(latent, self.scale_factor)
+        if self.ldm_latent_shape is not None:
+            latent = torch.stack([_spatial_pad(i, self.ldm_latent_shape) for i in latent], 0)
+        return latent
+
+    def _decode_latent(self, latent, autoencoder_model):
+        if self.autoencoder_latent_shape is not None:
+            latent = torch.stack([_center_crop(i, self.autoencoder_latent_shape) for i in latent], 0)
+        return autoencoder_model.decode_stage_2_outputs(ops.scale_f32(latent, 1.0 / self.scale_factor, divide_by=self.scale_factor))
+
+
+class LatentDiffusionInferer(DiffusionInferer, _LatentMixin):
+    """inferer.py:323-487."""
+
+    def __init__(self, scheduler: nn.Module, scale_factor: float = 1.0, ldm_latent_shape: list | None = None,
+                 autoencoder_latent_shape: list | None = None) -> None:
+        super().__init__(scheduler=scheduler)
+        self._init_latent(scale_factor, ldm_latent_shape, autoencoder_latent_shape)
+
+    def __call__(self, inputs: torch.Tensor, autoencoder_model, diffusion_model, noise: torch.Tensor,
+                 timesteps: torch.Tensor, condition: torch.Tensor | None = None, mode: str = "crossattn",
+                 seg: torch.Tensor | None = None, quantized: bool = True) -> torch.Tensor:
+        latent = self._encode_latent(inputs, autoencoder_model, quantized)
+        return super().__call__(inputs=latent, diffusion_model=diffusion_model, noise=noise, timesteps=timesteps,
+                                condition=condition, mode=mode)
+
+    @torch.no_grad()
+    def sample(self, input_noise: torch.Tensor, autoencoder_model, diffusion_model,
+               scheduler: Callable[..., torch.Tensor] | None = None, save_intermediates: bool | None = False,
+               intermediate_steps: int | None = 100, conditioning: torch.Tensor | None = None,
+               mode: str = "crossattn", verbose: bool = True, seg: torch.Tensor | None = None):
+        outputs = super().sample(input_noise=input_noise, diffusion_model=diffusion_model, scheduler=scheduler,
+                                 save_intermediates=save_intermediates, intermediate_steps=intermediate_steps,
+                                 conditioning=conditioning, mode=mode, verbose=verbose)
+        latent, latent_intermediates = outputs if save_intermediates else (outputs, [])
+        image = self._decode_latent(latent, autoencoder_model)
+        if save_intermediates:
+            return image, [self._decode_latent(l, autoencoder_model) for l in latent_intermediates]
+        return image
+
+
+class ControlNetDiffusionInferer(DiffusionInferer):
+    """inferer.py:561-707."""
+
+    def __init__(self, scheduler: nn.Module) -> None:
+        Inferer.__init__(self)
+        self.scheduler = scheduler
+
+    def __call__(self, inputs: torch.Tensor, diffusion_model, controlnet, noise: torch.Tensor,
+                 timesteps: torch.Tensor, cn_cond: torch.Tensor, condition: torch.Tensor | None = None,
+                 mode: str = "crossattn", seg: torch.Tensor | None = None) -> torch.Tensor:
+        _check_mode(mode)
+        noisy_image = self.scheduler.add_noise(original_samples=inputs, noise=noise, timesteps=timesteps)
+        if mode == "concat":
+            noisy_image = torch.cat([noisy_image, condition], dim=1)
+            condition = None
+        down, mid = _run_controlnet(controlnet, noisy_image, timesteps, cn_cond, condition)
+        return diffusion_model(x=noisy_image, timesteps=timesteps, context=condition,
+                               down_block_additional_residuals=down, mid_block_additional_residual=mid)
+
+    @torch.no_grad()
+    def sample(self, input_noise: torch.Tensor, diffusion_model, controlnet, cn_cond: torch.Tensor,
+               scheduler: Callable[..., torch.Tensor] | None = None, save_intermediates: bool | None = False,
+               intermediate_steps: int | None = 100, conditioning: torch.Tensor | None = None,
+               mode: str = "crossattn", verbose: bool = True, seg: torch.Tensor | None = None):
+        _check_mode(mode)
+        if not scheduler:
+            scheduler = self.scheduler
+        image = input_noise
+        intermediates = []
+        for t in _progress(scheduler, verbose):
+            if mode == "concat":
+                model_input, context_ = torch.cat([image, conditioning], dim=1), None
+            else:
+                model_input, context_ = image, conditioning
+            ts = torch.Tensor((t,)).to(input_noise.device)
+            down, mid = _run_controlnet(controlnet, model_input, ts, cn_cond, context_)
+            model_output = diffusion_model(model_input, timesteps=ts, context=context_,
+                                           down_block_additional_residuals=down, mid_block_additional_residual=mid)
+            image, _ = scheduler.step(model_output, t, image)
+            if save_intermediates and t % intermediate_steps == 0:
+                intermediates.append(image)
+        return (image, intermediates) if save_intermediates else image
+
+
+def _run_controlnet(controlnet, x, timesteps, cn_cond, context):
+    if isinstance(controlnet, ControlNet):      # keep the residuals channels-last between the two networks
+        return controlnet(x=x, timesteps=timesteps, controlnet_cond=cn_cond, context=context, _internal=True)
+    return controlnet(x=x, timesteps=timesteps, controlnet_cond=cn_cond, context=context)
+
+
+class ControlNetLatentDiffusionInferer(ControlNetDiffusionInferer, _LatentMixin):
+    """inferer.py:856-1038."""
+
+    def __init__(self, scheduler: nn.Module, scale_factor: float = 1.0, ldm_latent_shape: list | None = None,
+                 autoencoder_latent_shape: list | None = None) -> None:
+        super().__init__(scheduler=scheduler)
+        self._init_latent(scale_factor, ldm_latent_shape, autoencoder_latent_shape)
+
+    def _match_cond(self, cn_cond: torch.Tensor, spatial) -> torch.Tensor:
+        """Conditioning image resized to the latent grid (inferer.py:915-917 / 1001-1003)."""
+        if tuple(cn_cond.shape[2:]) != tuple(spatial):
+            cn_cond = torch.nn.functional.interpolate(cn_cond, tuple(spatial))
+        return cn_cond
+
+    def __call__(self, inputs: torch.Tensor, autoencoder_model, diffusion_model, controlnet, noise: torch.Tensor,
+                 timesteps: torch.Tensor, cn_cond: torch.Tensor, condition: torch.Tensor | None = None,
+                 mode: str = "crossattn", seg: torch.Tensor | None = None, quantized: bool = True) -> torch.Tensor:
+        latent = self._encode_latent(inputs, autoencoder_model, quantized)
+        cn_cond = self._match_cond(cn_cond, latent.shape[2:])
+        return super().__call__(inputs=latent, diffusion_model=diffusion_model, controlnet=controlnet, noise=noise,
+                                timesteps=timesteps, cn_cond=cn_cond, condition=condition, mode=mode)
+
+    @torch.no_grad()
+    def sample(self, input_noise: torch.Tensor, autoencoder_model, diffusion_model, controlnet,
+               cn_cond: torch.Tensor, scheduler: Callable[..., torch.Tensor] | None = None,
+               save_intermediates: bool | None = False, intermediate_steps: int | None = 100,
+               conditioning: torch.Tensor | None = None, mode: str = "crossattn", verbose: bool = True,
+               seg: torch.Tensor | None = None):
+        cn_cond = self._match_cond(cn_cond, input_noise.shape[2:])
+        outputs = super().sample(input_noise=input_noise, diffusion_model=diffusion_model, controlnet=controlnet,
+                                 cn_cond=cn_cond, scheduler=scheduler, save_intermediates=save_intermediates,
+                                 intermediate_steps=intermediate_steps, conditioning=conditioning, mode=mode,
+                                 verbose=verbose)
+        latent, latent_intermediates = outputs if save_intermediates else (outputs, [])
+        image = self._decode_latent(latent, autoencoder_model)
+        if save_intermediates:
+            return image, [self._decode_latent(l, autoencoder_model) for l in latent_intermediates]
+        return image

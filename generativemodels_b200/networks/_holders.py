@@ -1,0 +1,110 @@
+"""Parameter holders shared by the network modules.
+
+The modules keep the reference's module tree and ``state_dict`` keys by holding their parameters in
+ordinary ``torch.nn`` layers that are never *called*: ``forward`` hands the weights — repacked once into the K-major
+bf16 layout the tcgen05 kernel wants and cached against the parameter's version — to the C-ABI operators.
+"""
+from __future__ import annotations
+
+from typing import Sequence
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..ops import CL
+
+
+def _key(*params):
+    return tuple((p.data_ptr(), p._version, p.device) if p is not None else None for p in params)
+
+
+class _Cached:
+    """Mixin: cache of packed weights keyed by (data_ptr, version, device, extra)."""
+
+    def _cached(self, extra, params, build):
+        cache = self.__dict__.setdefault("_pack_cache", {})
+        k = (extra, _key(*params))
+        hit = cache.get(extra)
+        if hit is None or hit[0] != k:
+            hit = (k, build())
+            cache[extra] = hit
+        return hit[1]
+
+
+def _same_padding(kernel_size: int, dilation: int = 1) -> int:
+    return (kernel_size - 1) // 2 * dilation
+
+
+class Convolution(nn.Module, _Cached):
+    """Holder with the key layout of ``monai.networks.blocks.Convolution``: child ``conv`` is the nn.Conv /
+    nn.ConvTranspose whose parameters are used (monai semantics restated in SURVEY.md §8c: padding=None -> same
+    padding, output_padding=None -> stride - 1).  ``act`` is the ADN activation ("RELU") applied in the epilogue."""
+
+    def __init__(self, spatial_dims: int, in_channels: int, out_channels: int, strides: int = 1, kernel_size: int = 3,
+                 padding: int | None = None, dilation: int = 1, bias: bool = True, conv_only: bool = True,
+                 is_transposed: bool = False, output_padding: int | None = None, act: str | None = None, **_ignored):
+        super().__init__()
+        self.spatial_dims, self.in_channels, self.out_channels = spatial_dims, in_channels, out_channels
+        self.strides, self.kernel_size, self.dilation = strides, kernel_size, dilation
+        self.padding = _same_padding(kernel_size, dilation) if padding is None else padding
+        self.is_transposed = is_transposed
+        if dilation != 1:
+            raise NotImplementedError("dilated convolutions are not on the sampling path")
+        if is_transposed:
+            self.output_padding = strides - 1 if output_padding is None else output_padding
+            ctor = nn.ConvTranspose2d if spatial_dims == 2 else nn.ConvTranspose3d
+            self.conv = ctor(in_channels, out_channels, kernel_size, stride=strides, padding=self.padding,
+                             output_padding=self.output_padding, bias=bias)
+        else:
+            ctor = nn.Conv2d if spatial_dims == 2 else nn.Conv3d
+            self.conv = ctor(in_channels, out_channels, kernel_size, stride=strides, padding=self.padding, bias=bias)
+        self.act = ops.ACT_NONE if (conv_only or act is None) else {"RELU": ops.ACT_RELU, "SILU": ops.ACT_SILU}[
+            str(act).upper()]
+
+    def packed(self, splits: Sequence[int] | None = None, padding=None):
+        pad = self.padding if padding is None else padding
+        extra = ("conv", tuple(splits) if splits else None, str(pad))
+        if self.is_transposed:
+            return self._cached(extra, (self.conv.weight, self.conv.bias), lambda: ops.PackedConvTranspose(
+                self.conv.weight, self.conv.bias, self.strides, self.padding, self.output_padding))
+        return self._cached(extra, (self.conv.weight, self.conv.bias), lambda: ops.PackedConv(
+            self.conv.weight, self.conv.bias, self.strides, pad, splits=splits))
+
+    def forward(self, x: CL | Sequence[CL], **epilogue):
+        if self.is_transposed:
+            return ops.conv_transpose(x, self.packed(), act1=self.act)
+        srcs = [x] if isinstance(x, CL) else list(x)
+        if self.act != ops.ACT_NONE:
+            epilogue.setdefault("act1", self.act)
+        return ops.conv(srcs, self.packed([a.C for a in srcs]), **epilogue)
+
+
+class LinearHolder(_Cached):
+    """Packs an nn.Linear for the tensor-core GEMM path (the nn.Linear itself lives in the owning module)."""
+
+    def __init__(self, lin: nn.Linear):
+        self.lin = lin
+
+    def packed(self) -> ops.PackedLinear:
+        return self._cached("lin", (self.lin.weight, self.lin.bias),
+                            lambda: ops.PackedLinear(self.lin.weight, self.lin.bias))
+
+
+def packed_linear(owner: nn.Module, name: str) -> ops.PackedLinear:
+    holders = owner.__dict__.setdefault("_lin_holders", {})
+    h = holders.get(name)
+    lin = getattr(owner, name) if "." not in name else owner.get_submodule(name)
+    if h is None or h.lin is not lin:
+        h = holders[name] = LinearHolder(lin)
+    return h.packed()
+
+
+def f32(p: torch.Tensor) -> torch.Tensor:
+    return p if p.dtype == torch.float32 else p.float()
+
+
+def require_cuda(x: torch.Tensor, module: nn.Module):
+    if not x.is_cuda:
+        raise RuntimeError(f"{type(module).__name__}: generativemodels_b200 runs on sm_100a CUDA devices only "
+                           "(input tensor is on the CPU and there is no CPU path)")

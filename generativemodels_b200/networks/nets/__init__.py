@@ -1,0 +1,4 @@
+from .autoencoderkl import AutoencoderKL  # noqa: F401
+from .controlnet import ControlNet  # noqa: F401
+from .diffusion_model_unet import DiffusionModelUNet  # noqa: F401
+from .vqvae import VQVAE  # noqa: F401

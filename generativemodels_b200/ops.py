@@ -431,6 +431,66 @@ def axpy(a: CL, b: CL, alpha: float = 1.0, inplace: bool = False) -> CL:
     return out
 
 
+def concat(srcs: Sequence[CL]) -> CL:
+    """Materialised channel concat (only used where an identity skip needs the raw concatenated tensor)."""
+    lib = _lib.require_device()
+    a0 = srcs[0]
+    out = a0.like(sum(a.C for a in srcs))
+    rows = a0.N * a0.spatial
+    off = 0
+    for a in srcs:
+        check(lib.b200_copy_channels(a.t.data_ptr(), a.C, a.pitch, out.t.data_ptr(), out.pitch, off, rows, _stream()),
+              "b200_copy_channels")
+        off += a.C
+    if out.pitch > off:
+        out.t[..., off:].zero_()
+    return out
+
+
+def add_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """a + b for small fp32 tensors (time + class embedding), via the fused linear-combination kernel."""
+    lib = _lib.require_device()
+    a = a.contiguous().float()
+    b = b.contiguous().float()
+    out = torch.empty_like(a)
+    c = PndmCoef()
+    c.w[0], c.w[1], c.n_hist = 1.0, 1.0, 2
+    hist = (C.c_void_p * 2)(a.data_ptr(), b.data_ptr())
+    check(lib.b200_pndm_step(hist, None, C.byref(c), None, out.data_ptr(), a.numel(), _stream()), "b200_pndm_step")
+    return out
+
+
+def exp_half_clamped(x: torch.Tensor, lo: float, hi: float) -> torch.Tensor:
+    lib = _lib.require_device()
+    x = x.contiguous().float()
+    y = torch.empty_like(x)
+    check(lib.b200_exp_half_clamped(x.data_ptr(), lo, hi, y.data_ptr(), x.numel(), _stream()), "b200_exp_half_clamped")
+    return y
+
+
+def scale_f32(x: torch.Tensor, mul: float = 1.0, divide_by: float | None = None) -> torch.Tensor:
+    """x * mul, or x / divide_by when ``divide_by`` is given (exact division, like the reference's ``latent / s``)."""
+    if divide_by is not None:
+        mul, div = 1.0, float(divide_by)
+    else:
+        div = 1.0
+    if mul == 1.0 and div == 1.0:
+        return x
+    lib = _lib.require_device()
+    x32 = x.contiguous().float()
+    y = torch.empty_like(x32)
+    check(lib.b200_scale_f32(x32.data_ptr(), float(mul), div, y.data_ptr(), x32.numel(), _stream()), "b200_scale_f32")
+    return y if x.dtype == torch.float32 else y.to(x.dtype)
+
+
+def fma_f32(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor) -> torch.Tensor:
+    lib = _lib.require_device()
+    a, b, c = (t.contiguous().float() for t in (a, b, c))
+    y = torch.empty_like(a)
+    check(lib.b200_fma_f32(a.data_ptr(), b.data_ptr(), c.data_ptr(), y.data_ptr(), a.numel(), _stream()), "b200_fma_f32")
+    return y
+
+
 def geglu(x: CL) -> CL:
     lib = _lib.require_device()
     Hh = x.C // 2
@@ -448,14 +508,15 @@ _ATTN_CHUNK_BYTES = 6 << 30   # fp32 score slab per query chunk
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, dh: int, scale: float,
-              vt: torch.Tensor | None = None) -> torch.Tensor:
+              vt: torch.Tensor | None = None, residual: torch.Tensor | None = None) -> torch.Tensor:
     """softmax(scale * Q K^T) V on packed [B, T, pitch] bf16 rows (heads are channel slices).
 
     Tensor-core path (head_dim % 64 == 0, S >= 64): per (batch, head) QK^T -> fp32 scores, row softmax -> bf16
     probabilities, PV — the two GEMMs run on the tcgen05 implicit-GEMM kernel, queries are processed in slabs so
     the score matrix never exceeds a few GB (T = 89 600 in the 3-D config).  ``vt`` must then hold V^T
     ``[B, H*dh, S_pitch]`` (produced for free by swapping the operands of the V projection).
-    Everything else runs on the CUDA-core online-softmax kernel.
+    Everything else runs on the CUDA-core online-softmax kernel.  ``residual`` ([B, T, pitch] bf16) is added in
+    the PV epilogue on the tensor-core path only (callers add it themselves otherwise).
     """
     lib = _lib.require_device()
     B, T, qp = q.shape
@@ -463,6 +524,8 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, dh:
     out = torch.empty((B, T, round_up(heads * dh, 8)), dtype=torch.bfloat16, device=q.device)
     use_tc = (dh % 64 == 0) and S >= _TC_ATTN_MIN_S and vt is not None
     if not use_tc:
+        if residual is not None:
+            raise ValueError("residual fusion is only available on the tensor-core attention path")
         if out.shape[2] > heads * dh:
             out.zero_()
         check(lib.b200_attention_small(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, T, S, heads, dh,
@@ -512,6 +575,10 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, dh:
                 p2.cout, p2.out_cols = dh, dh
                 p2.out_sN, p2.out_sD, p2.out_sH, p2.out_sW = tc * op, tc * op, tc * op, op
                 p2.act1, p2.scale, p2.act2 = ACT_NONE, 1.0, ACT_NONE
+                if residual is not None:
+                    rp = residual.shape[2]
+                    p2.res_ptr, p2.res_dtype = residual.data_ptr() + ((b * T + t0) * rp + h * dh) * 2, DT_BF16
+                    p2.res_sN, p2.res_sD, p2.res_sH, p2.res_sW = tc * rp, tc * rp, tc * rp, rp
                 igemm_raw(p2)
     return out
 

@@ -1,0 +1,2 @@
+from .component_store import ComponentStore  # noqa: F401
+from .misc import unsqueeze_left, unsqueeze_right  # noqa: F401

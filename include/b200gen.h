@@ -163,6 +163,10 @@ int b200_avgpool2(const void* x, int32_t N, int32_t D, int32_t H, int32_t W, int
 /* y = a + alpha * b on bf16 buffers of n elements (ControlNet residual adds,
  * diffusion_model_unet.py:1917-1925,1931-1932; controlnet.py:405-407,433-434). */
 int b200_axpy_bf16(const void* a, const void* b, float alpha, void* y, int64_t n, void* stream);
+/* Copy C channels of every row of a channels-last bf16 tensor into columns [dst_off, dst_off + C) of another
+ * (materialises torch.cat([a, b], dim=1) only where a raw concatenated tensor is really needed). */
+int b200_copy_channels(const void* src, int32_t C, int32_t src_pitch, void* dst, int32_t dst_pitch, int32_t dst_off,
+                       int64_t rows, void* stream);
 /* GEGLU: y[m, j] = x[m, j] * gelu_erf(x[m, H + j])  (monai MLPBlock act="GEGLU",
  * diffusion_model_unet.py:211). x: [M, 2H] pitch x_pitch; y: [M, H] pitch y_pitch. */
 int b200_geglu(const void* x, int64_t M, int32_t H, int32_t x_pitch, void* y, int32_t y_pitch,
@@ -233,6 +237,12 @@ typedef struct {
 } b200_pndm_coef;
 int b200_pndm_step(const float* const* hist, const float* sample, const b200_pndm_coef* c,
                    float* prev_sample, float* eps_out, int64_t n, void* stream);
+/* AutoencoderKL.encode tail (autoencoderkl.py:731-734): sigma = exp(clamp(log_var, lo, hi) / 2), fp32. */
+int b200_exp_half_clamped(const float* log_var, float lo, float hi, float* sigma, int64_t n, void* stream);
+/* out = x * mul / div, fp32 (latent scale_factor handling, inferer.py:385, 472-475). */
+int b200_scale_f32(const float* x, float mul, float div, float* out, int64_t n, void* stream);
+/* AutoencoderKL.sampling (autoencoderkl.py:751-752): out = a + b * c elementwise, fp32. */
+int b200_fma_f32(const float* a, const float* b, const float* c, float* out, int64_t n, void* stream);
 /* Scheduler.add_noise / get_velocity (scheduler.py:169-200) with per-sample coefficients. */
 int b200_add_noise(const float* x0, const float* noise, const float* ca, const float* cb, float sign_b,
                    int32_t N, int64_t per_sample, float* out, void* stream);

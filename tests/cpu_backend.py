@@ -1,0 +1,296 @@
+"""TEST-ONLY CPU stand-in for libb200gen.so: every C-ABI entry point re-implemented with numpy/torch on HOST pointers,
+following include/b200gen.h literally.  Installing it lets the `-m "not gpu"` suite drive the real host code
+(generativemodels_b200: modules, weight packing, schedulers, inferers, ctypes marshalling) end to end on a machine
+without a GPU.  It is never importable from the product package and proves nothing about the CUDA kernels — those are
+covered by the -m gpu tests against the oracle."""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from generativemodels_b200 import _lib, ops
+from tests import igemm_emulator as E
+
+
+def _obj(ref):
+    return ref._obj if hasattr(ref, "_obj") else ref
+
+
+def _np(ptr, count, ctype):
+    if not ptr:
+        return None
+    return np.ctypeslib.as_array(C.cast(int(ptr), C.POINTER(ctype)), shape=(int(count),))
+
+
+def f32(ptr, count):
+    a = _np(ptr, count, C.c_float)
+    return None if a is None else torch.from_numpy(a)
+
+
+def bf16(ptr, count):
+    a = _np(ptr, count, C.c_uint16)
+    return None if a is None else torch.from_numpy(a.view(np.int16)).view(torch.bfloat16)
+
+
+def i64(ptr, count):
+    a = _np(ptr, count, C.c_int64)
+    return None if a is None else torch.from_numpy(a)
+
+
+def _act(x, a):
+    return F.relu(x) if a == _lib.ACT_RELU else F.silu(x) if a == _lib.ACT_SILU else x
+
+
+class FakeLib:
+    def b200_igemm(self, p, stream):
+        E.emulate(_obj(p))
+        return 0
+
+    def b200_groupnorm_workspace_bytes(self, N, spatial, C_):
+        return 16
+
+    def b200_nchw_to_nhwc(self, x, N, C_, sp, y, pitch, stream):
+        src = f32(x, N * C_ * sp).view(N, C_, sp)
+        dst = bf16(y, N * sp * pitch).view(N, sp, pitch)
+        dst.zero_()
+        dst[:, :, :C_] = src.transpose(1, 2).to(torch.bfloat16)
+        return 0
+
+    def b200_nhwc_to_nchw(self, x, dt, N, C_, sp, pitch, y, stream):
+        src = (bf16 if dt == _lib.DT_BF16 else f32)(x, N * sp * pitch).view(N, sp, pitch)
+        f32(y, N * C_ * sp).view(N, C_, sp).copy_(src[:, :, :C_].float().transpose(1, 2))
+        return 0
+
+    def _gather_src(self, p):
+        xs = []
+        for i in range(2):
+            if p.x_ptr[i]:
+                xs.append(bf16(p.x_ptr[i], p.N * p.spatial * p.x_pitch[i]).view(p.N, p.spatial, p.x_pitch[i])
+                          [:, :, : p.x_C[i]].float())
+        return torch.cat(xs, 2)
+
+    def b200_groupnorm_stats(self, p, stream):
+        p = _obj(p)
+        x = self._gather_src(p)                       # [N, S, C]
+        N, S, Cc = x.shape
+        g = x.view(N, S, p.groups, Cc // p.groups)
+        mean = g.mean(dim=(1, 3), keepdim=True)
+        var = g.var(dim=(1, 3), unbiased=False, keepdim=True)
+        rstd = (var + p.eps).rsqrt()
+        gamma, beta = f32(p.gamma, Cc), f32(p.beta, Cc)
+        a = (rstd.expand(N, 1, p.groups, Cc // p.groups).reshape(N, Cc)) * gamma
+        b = beta - (mean.expand(N, 1, p.groups, Cc // p.groups).reshape(N, Cc)) * a
+        f32(p.affine, N * Cc * 2).view(N, Cc, 2).copy_(torch.stack([a, b], -1))
+        return 0
+
+    def b200_groupnorm_apply(self, p, stream):
+        p = _obj(p)
+        x = self._gather_src(p)
+        N, S, Cc = x.shape
+        ab = f32(p.affine, N * Cc * 2).view(N, 1, Cc, 2)
+        y = _act(x * ab[..., 0] + ab[..., 1], p.act)
+        dst = bf16(p.y_ptr, N * S * p.y_pitch).view(N, S, p.y_pitch)
+        dst.zero_()
+        dst[:, :, :Cc] = y.to(torch.bfloat16)
+        return 0
+
+    def b200_layernorm(self, x, M, C_, xp, g, b, eps, y, yp, stream):
+        src = bf16(x, M * xp).view(M, xp)[:, :C_].float()
+        out = F.layer_norm(src, (C_,), f32(g, C_), f32(b, C_), eps)
+        dst = bf16(y, M * yp).view(M, yp)
+        dst.zero_()
+        dst[:, :C_] = out.to(torch.bfloat16)
+        return 0
+
+    def b200_upsample_nearest2x(self, x, N, D, H, W, pitch, dims, y, stream):
+        src = bf16(x, N * D * H * W * pitch).view(N, D, H, W, pitch)
+        o = src.repeat_interleave(2, 2).repeat_interleave(2, 3)
+        if dims == 3:
+            o = o.repeat_interleave(2, 1)
+        bf16(y, o.numel()).view(o.shape).copy_(o)
+        return 0
+
+    def b200_avgpool2(self, x, N, D, H, W, pitch, dims, y, stream):
+        src = bf16(x, N * D * H * W * pitch).view(N, D, H, W, pitch).float().permute(0, 4, 1, 2, 3)
+        o = F.avg_pool3d(src, (2, 2, 2) if dims == 3 else (1, 2, 2)).permute(0, 2, 3, 4, 1).contiguous()
+        bf16(y, o.numel()).view(o.shape).copy_(o.to(torch.bfloat16))
+        return 0
+
+    def b200_axpy_bf16(self, a, b, alpha, y, n, stream):
+        out = (bf16(a, n).float() + alpha * bf16(b, n).float()).to(torch.bfloat16)
+        bf16(y, n).copy_(out)
+        return 0
+
+    def b200_copy_channels(self, src, C_, sp, dst, dp, off, rows, stream):
+        bf16(dst, rows * dp).view(rows, dp)[:, off:off + C_] = bf16(src, rows * sp).view(rows, sp)[:, :C_]
+        return 0
+
+    def b200_geglu(self, x, M, H, xp, y, yp, stream):
+        src = bf16(x, M * xp).view(M, xp).float()
+        out = src[:, :H] * F.gelu(src[:, H:2 * H])
+        dst = bf16(y, M * yp).view(M, yp)
+        dst[:, :H] = out.to(torch.bfloat16)
+        return 0
+
+    def b200_softmax_rows(self, s, M, S, sp, p, pp, stream):
+        sc = f32(s, M * sp).view(M, sp)[:, :S]
+        dst = bf16(p, M * pp).view(M, pp)
+        dst.zero_()
+        dst[:, :S] = torch.softmax(sc, -1).to(torch.bfloat16)
+        return 0
+
+    def b200_attention_small(self, q, k, v, o, B, T, S, heads, dh, qp, kp, vp, op, scale, stream):
+        Cc = heads * dh
+        qq = bf16(q, B * T * qp).view(B, T, qp)[:, :, :Cc].float().view(B, T, heads, dh).transpose(1, 2)
+        kk = bf16(k, B * S * kp).view(B, S, kp)[:, :, :Cc].float().view(B, S, heads, dh).transpose(1, 2)
+        vv = bf16(v, B * S * vp).view(B, S, vp)[:, :, :Cc].float().view(B, S, heads, dh).transpose(1, 2)
+        out = (torch.softmax(scale * qq @ kk.transpose(-1, -2), -1) @ vv).transpose(1, 2).reshape(B, T, Cc)
+        bf16(o, B * T * op).view(B, T, op)[:, :, :Cc] = out.to(torch.bfloat16)
+        return 0
+
+    def b200_timestep_embedding(self, t, N, dim, max_period, emb, stream):
+        half = dim // 2
+        tt = f32(t, N)
+        exponent = -math.log(max_period) * torch.arange(0, half, dtype=torch.float32)
+        args = tt[:, None] * torch.exp(exponent / half)[None]
+        e = torch.cat([torch.cos(args), torch.sin(args)], -1)
+        if dim % 2:
+            e = F.pad(e, (0, 1))
+        f32(emb, N * dim).view(N, dim).copy_(e)
+        return 0
+
+    def b200_small_linear(self, x, M, K, W, b, O_, act_in, act_out, y, stream):
+        out = F.linear(_act(f32(x, M * K).view(M, K), act_in), f32(W, O_ * K).view(O_, K), f32(b, O_))
+        f32(y, M * O_).view(M, O_).copy_(_act(out, act_out))
+        return 0
+
+    def b200_ddim_step(self, m, s, nz, c, prev, x0o, n, stream):
+        c = _obj(c)
+        mm, ss = f32(m, n), f32(s, n)
+        if c.prediction_type == _lib.PRED_EPSILON:
+            x0, eps = (ss - c.sqrt_beta_prod_t * mm) / c.sqrt_alpha_prod_t, mm
+        elif c.prediction_type == _lib.PRED_SAMPLE:
+            x0 = mm
+            eps = (ss - c.sqrt_alpha_prod_t * x0) / c.sqrt_beta_prod_t
+        else:
+            x0 = c.sqrt_alpha_prod_t * ss - c.sqrt_beta_prod_t * mm
+            eps = c.sqrt_alpha_prod_t * mm + c.sqrt_beta_prod_t * ss
+        if c.clip:
+            x0 = x0.clamp(c.clip_min, c.clip_max)
+        p = c.sqrt_alpha_prod_prev * x0 + c.dir_coef * eps
+        if nz:
+            p = p + c.sigma * f32(nz, n)
+        f32(prev, n).copy_(p)
+        if x0o:
+            f32(x0o, n).copy_(x0)
+        return 0
+
+    def b200_ddpm_step(self, m, s, nz, pv, c, prev, x0o, n, stream):
+        c = _obj(c)
+        mm, ss = f32(m, n), f32(s, n)
+        if c.prediction_type == _lib.PRED_EPSILON:
+            x0 = (ss - c.sqrt_beta_prod_t * mm) / c.sqrt_alpha_prod_t
+        elif c.prediction_type == _lib.PRED_SAMPLE:
+            x0 = mm
+        else:
+            x0 = c.sqrt_alpha_prod_t * ss - c.sqrt_beta_prod_t * mm
+        if c.clip:
+            x0 = x0.clamp(c.clip_min, c.clip_max)
+        p = c.coef_x0 * x0 + c.coef_xt * ss
+        if nz:
+            sig = c.sigma
+            if c.var_mode == 1:
+                sig = f32(pv, n).sqrt()
+            elif c.var_mode == 2:
+                frac = (f32(pv, n) + 1) / 2
+                sig = (frac * c.max_log + (1 - frac) * c.min_log).sqrt()
+            p = p + sig * f32(nz, n)
+        f32(prev, n).copy_(p)
+        if x0o:
+            f32(x0o, n).copy_(x0)
+        return 0
+
+    def b200_pndm_step(self, hist, s, c, prev, eps_out, n, stream):
+        c = _obj(c)
+        e = torch.zeros(n)
+        for k in range(c.n_hist):
+            e = e + c.w[k] * f32(hist[k], n)
+        if eps_out:
+            f32(eps_out, n).copy_(e)
+        if prev:
+            ss = f32(s, n)
+            if c.prediction_type == _lib.PRED_V:
+                e = c.v_alpha * e + c.v_beta * ss
+            f32(prev, n).copy_(c.sample_coeff * ss - c.eps_coeff * e)
+        return 0
+
+    def b200_add_noise(self, x0, nz, ca, cb, sign_b, N, per, out, stream):
+        a, b = f32(ca, N)[:, None], f32(cb, N)[:, None] * sign_b
+        f32(out, N * per).view(N, per).copy_(a * f32(x0, N * per).view(N, per) + b * f32(nz, N * per).view(N, per))
+        return 0
+
+    def b200_exp_half_clamped(self, x, lo, hi, y, n, stream):
+        f32(y, n).copy_(torch.exp(f32(x, n).clamp(lo, hi) / 2))
+        return 0
+
+    def b200_fma_f32(self, a, b, c, y, n, stream):
+        f32(y, n).copy_(f32(a, n) + f32(b, n) * f32(c, n))
+        return 0
+
+    def b200_scale_f32(self, x, mul, div, y, n, stream):
+        f32(y, n).copy_(f32(x, n) * mul / div)
+        return 0
+
+    def b200_vq_argmin_gather(self, x, M, D, xp, cb, K, idx, q16, qp, q32, ste, sq, hist, stream):
+        xx = f32(x, M * xp).view(M, xp)[:, :D]
+        cbk = f32(cb, K * D).view(K, D)
+        d = (xx ** 2).sum(1, keepdim=True) + (cbk.t() ** 2).sum(0, keepdim=True) - 2 * xx @ cbk.t()
+        ii = torch.max(-d, 1)[1]
+        i64(idx, M).copy_(ii)
+        qv = cbk[ii]
+        if q16:
+            dst = bf16(q16, M * qp).view(M, qp)
+            dst.zero_()
+            dst[:, :D] = qv.to(torch.bfloat16)
+        if q32:
+            f32(q32, M * D).view(M, D).copy_(xx + (qv - xx) if ste else qv)
+        if sq:
+            _np(sq, 1, C.c_double)[0] += float(((qv - xx).double() ** 2).sum())
+        if hist:
+            h = _np(hist, K, C.c_int32)
+            h += np.bincount(ii.numpy(), minlength=K).astype(np.int32)
+        return 0
+
+    def b200_vq_gather(self, idx, M, cb, K, D, q16, qp, stream):
+        dst = bf16(q16, M * qp).view(M, qp)
+        dst.zero_()
+        dst[:, :D] = f32(cb, K * D).view(K, D)[i64(idx, M)].to(torch.bfloat16)
+        return 0
+
+
+def install(monkeypatch):
+    """Route the product's C-ABI calls to the CPU stand-in and lift its CUDA-only guards (tests only)."""
+    fake = FakeLib()
+    monkeypatch.setattr(_lib, "require_device", lambda: fake)
+    monkeypatch.setattr(ops, "_stream", lambda: 0)
+    monkeypatch.setattr(ops, "igemm_raw", E.emulate)
+    import generativemodels_b200.networks._holders as H
+    import generativemodels_b200.networks.nets.autoencoderkl as A
+    import generativemodels_b200.networks.nets.controlnet as CN
+    import generativemodels_b200.networks.nets.diffusion_model_unet as U
+    import generativemodels_b200.networks.nets.vqvae as V
+    import generativemodels_b200.networks.schedulers.scheduler as S
+    import generativemodels_b200.networks.schedulers.ddim as S1
+    import generativemodels_b200.networks.schedulers.ddpm as S2
+    import generativemodels_b200.networks.schedulers.pndm as S3
+    for mod in (H, A, CN, U, V):
+        monkeypatch.setattr(mod, "require_cuda", lambda x, m: None, raising=False)
+
+    def prep(*tensors):
+        return [None if t is None else (t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous())
+                for t in tensors]
+    for mod in (S, S1, S2, S3):
+        monkeypatch.setattr(mod, "_prep", prep, raising=False)
+    return fake

@@ -1,0 +1,366 @@
+"""Parity of the CUDA path (through the reference-facing nn.Module / Inferer API) against
+  (1) the committed golden vectors = outputs of the UNMODIFIED reference (tests/golden/*.pt), and
+  (2) the CPU oracle (oracle/torch_oracle.py) on seeded models at sizes it finishes in seconds.
+
+Tolerances (stated per north_star): the kernels compute bf16 x bf16 -> fp32 with bf16 activations between ops, the
+checker is fp32 end to end, so a network forward is held to a relative L2 error of 2e-2 (observed ~3e-3) and a
+multi-step sampler trajectory to 5e-2; scheduler steps are fp32 elementwise and held to 1e-5; VQ indices are
+bit-exact except at fp32 near-ties (gap between best and second-best code below 1e-4 relative), which are counted.
+"""
+import math
+from pathlib import Path
+
+import pytest
+import torch
+
+from oracle import torch_oracle as O
+from tests.golden import configs as G
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).resolve().parent / "golden"
+FWD_TOL, TRAJ_TOL = 2e-2, 5e-2
+
+
+def load(name):
+    return torch.load(GOLD / f"{name}.pt", weights_only=False)
+
+
+def rel(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+def check(a, b, tol, what):
+    assert tuple(a.shape) == tuple(b.shape), f"{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
+    r = rel(a, b)
+    assert math.isfinite(r) and r < tol, f"{what}: relative L2 error {r:.3e} >= {tol}"
+    return r
+
+
+def nets():
+    import generativemodels_b200.networks.nets as N
+    return N
+
+
+def cuda(t):
+    return None if t is None else t.cuda()
+
+
+# ------------------------------------------------------------------------------------------------ golden (reference)
+def test_unet_golden(cuda_device):
+    for name in ("g_unet2d", "g_unet3d_cross"):
+        fx = load(name)
+        m = nets().DiffusionModelUNet(**fx["kwargs"]).cuda().eval()
+        m.load_state_dict(fx["state_dict"])
+        y = m(cuda(fx["x"]), cuda(fx["t"]), context=cuda(fx["context"]))
+        check(y, fx["y"], FWD_TOL, name)
+
+
+def test_samplers_golden(cuda_device):
+    """DiffusionInferer.sample with DDIM / PNDM / DDPM against the reference's own trajectories."""
+    from generativemodels_b200.inferers import DiffusionInferer
+    from generativemodels_b200.networks.schedulers import DDIMScheduler, DDPMScheduler, PNDMScheduler
+    fx = load("g_unet2d")
+    m = nets().DiffusionModelUNet(**fx["kwargs"]).cuda().eval()
+    m.load_state_dict(fx["state_dict"])
+    noise = fx["noise"].cuda()
+    s = DDIMScheduler(**fx["ddim_kwargs"])
+    s.set_timesteps(fx["ddim_steps"])
+    check(DiffusionInferer(s).sample(noise, m, s, verbose=False), fx["ddim_sample"], TRAJ_TOL, "ddim sample")
+    p = PNDMScheduler(**fx["pndm_kwargs"])
+    p.set_timesteps(fx["pndm_steps"])
+    check(DiffusionInferer(p).sample(noise, m, p, verbose=False), fx["pndm_sample"], TRAJ_TOL, "pndm sample")
+    d = DDPMScheduler(**fx["ddpm_kwargs"])
+    d.set_timesteps(fx["ddpm_steps"])
+    torch.manual_seed(fx["ddpm_seed"])     # same CPU noise stream as the reference run
+    check(DiffusionInferer(d).sample(noise, m, d, verbose=False), fx["ddpm_sample"], TRAJ_TOL, "ddpm sample")
+
+
+def test_controlnet_golden(cuda_device):
+    from generativemodels_b200.inferers import ControlNetDiffusionInferer
+    fx = load("g_controlnet")
+    cn = nets().ControlNet(**fx["kwargs"]).cuda().eval()
+    cn.load_state_dict(fx["cn_state_dict"])
+    un = nets().DiffusionModelUNet(**fx["unet_kwargs"]).cuda().eval()
+    un.load_state_dict(fx["unet_state_dict"])
+    x, t, cond, ctx = (cuda(fx[k]) for k in ("x", "t", "cond", "context"))
+    down, mid = cn(x, t, cond, conditioning_scale=fx["scale"], context=ctx)
+    assert len(down) == len(fx["down"])
+    for i, (a, b) in enumerate(zip(down, fx["down"])):
+        check(a, b, FWD_TOL, f"controlnet down[{i}]")
+    check(mid, fx["mid"], FWD_TOL, "controlnet mid")
+    y = un(x, t, context=ctx, down_block_additional_residuals=down, mid_block_additional_residual=mid)
+    check(y, fx["y"], FWD_TOL, "unet + controlnet residuals")
+
+
+def test_autoencoderkl_and_ldm_golden(cuda_device):
+    from generativemodels_b200.inferers import LatentDiffusionInferer
+    from generativemodels_b200.networks.schedulers import DDIMScheduler
+    fx = load("g_aekl2d")
+    ae = nets().AutoencoderKL(**fx["kwargs"]).cuda().eval()
+    ae.load_state_dict(fx["state_dict"])
+    mu, sigma = ae.encode(fx["x"].cuda())
+    check(mu, fx["mu"], FWD_TOL, "aekl mu")
+    check(sigma, fx["sigma"], FWD_TOL, "aekl sigma")
+    check(ae.decode(fx["mu"].cuda()), fx["rec"], FWD_TOL, "aekl decode")
+    un = nets().DiffusionModelUNet(**fx["latent_unet_kwargs"]).cuda().eval()
+    un.load_state_dict(fx["latent_unet_state_dict"])
+    s = DDIMScheduler(**fx["ddim_kwargs"])
+    s.set_timesteps(fx["ddim_steps"])
+    inf = LatentDiffusionInferer(s, scale_factor=fx["scale_factor"])
+    img = inf.sample(fx["latent_noise"].cuda(), ae, un, s, verbose=False)
+    check(img, fx["ldm_sample"], TRAJ_TOL, "latent diffusion sample")
+
+
+def _index_mismatch_report(idx, idx_ref, codebook, flat):
+    """exact outside fp32 near-ties: returns (#hard mismatches, #near-tie flips)."""
+    bad = (idx.cpu().flatten() != idx_ref.cpu().flatten())
+    if not bad.any():
+        return 0, 0
+    margin = O.vq_index_margin(codebook.cpu(), flat.cpu())
+    scale = (flat.cpu().double() ** 2).sum(1) + 1e-12
+    near = (margin / scale) < 1e-4
+    return int((bad & ~near).sum()), int((bad & near).sum())
+
+
+def test_vqvae_golden(cuda_device):
+    fx = load("g_vqvae3d")
+    m = nets().VQVAE(**fx["kwargs"]).cuda().eval()
+    m.load_state_dict(fx["state_dict"])
+    x = fx["x"].cuda()
+    z = m.encode(x)
+    check(z, fx["z"], FWD_TOL, "vqvae encode")
+    cb = fx["state_dict"]["quantizer.quantizer.embedding.weight"]
+    # quantiser on the reference's own z: indices must be bit-exact
+    q, loss, idx = m.quantizer.quantizer(fx["z"].cuda())
+    flat = fx["z"].permute(0, 2, 3, 4, 1).reshape(-1, cb.shape[1])
+    hard, near = _index_mismatch_report(idx, fx["idx"], cb, flat)
+    assert hard == 0, f"{hard} VQ indices differ outside near-ties ({near} near-tie flips)"
+    check(m.decode_samples(fx["idx"].cuda()), fx["dec_from_idx"], FWD_TOL, "vqvae decode_samples")
+    rec, loss = m(x)
+    # encoder runs in bf16, so a few vectors may cross a cell boundary: compare the decode statistically
+    check(rec, fx["rec"], 6e-2, "vqvae forward")
+    assert abs(float(loss) - float(fx["loss"])) < 0.05 * abs(float(fx["loss"])) + 1e-4
+
+
+def test_vq_reference_known_answer(cuda_device):
+    """tests/test_vector_quantizer.py:45-62 of the reference, through the CUDA kernel."""
+    from generativemodels_b200.networks.layers import EMAQuantizer
+    fx = load("g_vq_ema_case")
+    q = EMAQuantizer(spatial_dims=2, num_embeddings=2, embedding_dim=2, epsilon=0, decay=0).cuda().eval()
+    q.embedding.weight.data.copy_(fx["codebook"])
+    _, _, idx = q(fx["x"].cuda())
+    assert torch.equal(idx.cpu(), fx["idx"])
+
+
+# ------------------------------------------------------------------------------------------------ oracle (seeded)
+@pytest.mark.parametrize("name", list(G.UNET_CASES))
+def test_unet_vs_oracle(cuda_device, name):
+    kw = G.UNET_CASES[name]
+    torch.manual_seed(0)
+    m = G.randomize_zero_params(nets().DiffusionModelUNet(**kw)).eval()
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    inp = G.UNET_INPUTS[name]
+    torch.manual_seed(1)
+    x = torch.randn(inp["shape"])
+    t = torch.randint(0, 1000, (inp["shape"][0],)).long()
+    ctx = torch.randn(inp["context"]) if "context" in inp else None
+    cls = torch.randint(0, 5, (inp["shape"][0],)) if inp.get("classes") else None
+    want = O.unet_forward(sd, G.unet_oracle_cfg(kw), x, t, context=ctx, class_labels=cls)
+    got = m.cuda()(x.cuda(), t.cuda(), context=cuda(ctx), class_labels=cuda(cls))
+    check(got, want, FWD_TOL, name)
+    # single float timestep broadcast over the batch, as DiffusionInferer.sample passes it (inferer.py:129)
+    t1 = torch.Tensor((500,))
+    want1 = O.unet_forward(sd, G.unet_oracle_cfg(kw), x, t1, context=ctx, class_labels=cls)
+    got1 = m(x.cuda(), t1.cuda(), context=cuda(ctx), class_labels=cuda(cls))
+    check(got1, want1, FWD_TOL, name + " (broadcast timestep)")
+
+
+@pytest.mark.parametrize("name", list(G.AEKL_CASES))
+def test_autoencoderkl_vs_oracle(cuda_device, name):
+    kw = G.AEKL_CASES[name]
+    torch.manual_seed(0)
+    m = nets().AutoencoderKL(**kw).eval()
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    torch.manual_seed(3)
+    x = torch.randn(G.AEKL_INPUTS[name])
+    cfg = G.aekl_oracle_cfg(kw)
+    mu_w, sig_w = O.autoencoderkl_encode(sd, cfg, x)
+    m = m.cuda()
+    mu, sig = m.encode(x.cuda())
+    check(mu, mu_w, FWD_TOL, name + " mu")
+    check(sig, sig_w, FWD_TOL, name + " sigma")
+    check(m.decode(mu_w.cuda()), O.autoencoderkl_decode(sd, cfg, mu_w), FWD_TOL, name + " decode")
+
+
+@pytest.mark.parametrize("name", list(G.VQVAE_CASES))
+def test_vqvae_vs_oracle(cuda_device, name):
+    kw = G.VQVAE_CASES[name]
+    torch.manual_seed(0)
+    m = nets().VQVAE(**kw).eval()
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    cfg = G.vqvae_oracle_cfg(kw)
+    torch.manual_seed(4)
+    x = torch.rand(G.VQVAE_INPUTS[name])
+    z_w = O.vqvae_encode(sd, cfg, x)
+    m = m.cuda()
+    check(m.encode(x.cuda()), z_w, FWD_TOL, name + " encode")
+    cb = sd["quantizer.quantizer.embedding.weight"]
+    flat, idx_w = O.vq_quantize(cb, z_w)
+    q, loss, idx = m.quantizer.quantizer(z_w.cuda())
+    hard, near = _index_mismatch_report(idx, idx_w, cb, flat)
+    assert hard == 0, f"{hard} VQ indices differ outside near-ties ({near} near-tie flips)"
+    q_w, loss_w, _, perp_w = O.vq_forward(cb, z_w, kw.get("commitment_cost", 0.25))
+    if near == 0:
+        assert torch.equal(q.cpu(), q_w), "straight-through values must be bit-identical when indices agree"
+    assert abs(float(loss) - float(loss_w)) < 1e-5 * max(1.0, abs(float(loss_w)))
+    loss2, _ = m.quantizer(z_w.cuda())
+    assert abs(float(m.quantizer.perplexity) - float(perp_w)) < 1e-3 * float(perp_w) + 1e-4
+    check(m.decode(q_w.cuda()), O.vqvae_decode(sd, cfg, q_w), FWD_TOL, name + " decode")
+    check(m.decode_stage_2_outputs(z_w.cuda()), O.vqvae_decode(sd, cfg, q_w), FWD_TOL, name + " stage-2 decode")
+
+
+def test_vq_large_exact(cuda_device):
+    """C4-sized quantiser problem (M = 32768, K = 256, D = 32): bit-exact indices vs the oracle outside near-ties."""
+    from generativemodels_b200.networks.layers import EMAQuantizer
+    torch.manual_seed(9)
+    q = EMAQuantizer(spatial_dims=3, num_embeddings=256, embedding_dim=32).eval()
+    cb = q.embedding.weight.detach().clone()
+    z = torch.randn(1, 32, 32, 32, 32) * 0.7
+    flat, idx_w = O.vq_quantize(cb, z)
+    _, _, idx = q.cuda()(z.cuda())
+    hard, near = _index_mismatch_report(idx, idx_w, cb, flat)
+    assert hard == 0 and near <= 8, f"hard={hard} near-tie flips={near} of {idx_w.numel()}"
+
+
+# ------------------------------------------------------------------------------------------------ schedulers
+def _sched_pairs():
+    from generativemodels_b200.networks import schedulers as S
+    return {"ddim": (S.DDIMScheduler, O.DDIMOracle), "ddpm": (S.DDPMScheduler, O.DDPMOracle),
+            "pndm": (S.PNDMScheduler, O.PNDMOracle)}
+
+
+SCHED = [
+    ("ddim", dict(num_train_timesteps=1000, schedule="linear_beta", beta_start=0.0015, beta_end=0.0195), 50),
+    ("ddim", dict(num_train_timesteps=1000, schedule="scaled_linear_beta", beta_start=0.0005, beta_end=0.0195,
+                  clip_sample=False), 50),
+    ("ddim", dict(num_train_timesteps=100, prediction_type="v_prediction", set_alpha_to_one=False, steps_offset=1), 10),
+    ("ddim", dict(num_train_timesteps=100, prediction_type="sample", schedule="cosine", steps_offset=1,
+                  set_alpha_to_one=False), 7),
+    ("ddpm", dict(num_train_timesteps=1000), 4),
+    ("ddpm", dict(num_train_timesteps=100, variance_type="fixed_large", prediction_type="v_prediction",
+                  schedule="sigmoid_beta"), 10),
+    ("pndm", dict(num_train_timesteps=1000, skip_prk_steps=True), 20),
+    ("pndm", dict(num_train_timesteps=1000, skip_prk_steps=False), 20),
+    ("pndm", dict(num_train_timesteps=100, skip_prk_steps=False, prediction_type="v_prediction",
+                  set_alpha_to_one=True, steps_offset=1), 10),
+]
+
+
+@pytest.mark.parametrize("kind,kw,steps", SCHED, ids=[f"{k}-{i}" for i, (k, _, _) in enumerate(SCHED)])
+def test_scheduler_trajectory(cuda_device, kind, kw, steps):
+    """Same stand-in model output through the fused-kernel scheduler and the oracle: every step within 1e-5."""
+    P, M = _sched_pairs()[kind]
+    p, m = P(**kw), M(**kw)
+    p.set_timesteps(steps)
+    m.set_timesteps(steps)
+    assert torch.equal(p.timesteps.cpu(), m.timesteps)
+    assert torch.equal(p.alphas_cumprod, m.alphas_cumprod)
+    torch.manual_seed(5)
+    xm = torch.randn(2, 3, 8, 8)
+    xp = xm.cuda()
+    for t in m.timesteps:
+        epsm = torch.tanh(xm * 0.7 + 0.01 * float(t))
+        epsp = torch.tanh(xp * 0.7 + 0.01 * float(t))
+        if kind == "ddpm":
+            gm, gp = torch.Generator().manual_seed(int(t)), torch.Generator().manual_seed(int(t))
+            xm, x0m = m.step(epsm, int(t), xm, generator=gm)
+            xp, x0p = p.step(epsp, int(t), xp, generator=gp)
+        else:
+            xm, x0m = m.step(epsm, int(t), xm)
+            xp, x0p = p.step(epsp, int(t), xp)
+        err = (xp.cpu() - xm).abs().max().item()
+        assert err < 1e-5 * max(1.0, xm.abs().max().item()), f"{kind} diverged at t={int(t)}: {err:.3e}"
+        if x0m is not None and x0p is not None:
+            assert (x0p.cpu() - x0m).abs().max().item() < 1e-5 * max(1.0, x0m.abs().max().item())
+
+
+def test_ddim_eta_and_reversed_and_noise_ops(cuda_device):
+    from generativemodels_b200.networks.schedulers import DDIMScheduler
+    kw = dict(num_train_timesteps=1000)
+    p, m = DDIMScheduler(**kw), O.DDIMOracle(**kw)
+    p.set_timesteps(10)
+    m.set_timesteps(10)
+    torch.manual_seed(6)
+    x, eps = torch.randn(2, 1, 8, 8), torch.randn(2, 1, 8, 8)
+    want, _ = m.step(eps, 500, x, eta=0.5, generator=torch.Generator().manual_seed(3))
+    got, _ = p.step(eps.cuda(), 500, x.cuda(), eta=0.5, generator=torch.Generator().manual_seed(3))
+    assert (got.cpu() - want).abs().max().item() < 1e-5
+    # add_noise / get_velocity (scheduler.py:169-200)
+    t = torch.tensor([10, 900])
+    acp = m.alphas_cumprod
+    sa, sb = (acp[t] ** 0.5)[:, None, None, None], ((1 - acp[t]) ** 0.5)[:, None, None, None]
+    assert (p.add_noise(x.cuda(), eps.cuda(), t).cpu() - (sa * x + sb * eps)).abs().max().item() < 1e-6
+    assert (p.get_velocity(x.cuda(), eps.cuda(), t).cpu() - (sa * eps - sb * x)).abs().max().item() < 1e-6
+    # reversed step: closed form (ddim.py:239-301)
+    nt = 500 + 100
+    a_t, a_n = acp[500], acp[nt]
+    x0 = (x - (1 - a_t) ** 0.5 * eps) / a_t ** 0.5
+    x0 = torch.clamp(x0, -1, 1)
+    want_r = a_n ** 0.5 * x0 + (1 - a_n) ** 0.5 * eps
+    got_r, got_x0 = p.reversed_step(eps.cuda(), 500, x.cuda())
+    assert (got_r.cpu() - want_r).abs().max().item() < 1e-5
+    assert (got_x0.cpu() - x0).abs().max().item() < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ inferers vs oracle
+def test_inferers_vs_oracle(cuda_device):
+    from generativemodels_b200.inferers import ControlNetDiffusionInferer, DiffusionInferer
+    from generativemodels_b200.networks.schedulers import DDIMScheduler
+    # concat conditioning through DiffusionInferer
+    kw = dict(spatial_dims=2, in_channels=3, out_channels=1, num_res_blocks=1, num_channels=(32, 64),
+              attention_levels=(False, True), norm_num_groups=8, num_head_channels=(0, 64))
+    torch.manual_seed(0)
+    m = G.randomize_zero_params(nets().DiffusionModelUNet(**kw)).eval()
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    cfg = G.unet_oracle_cfg(kw)
+    skw = dict(num_train_timesteps=1000, schedule="scaled_linear_beta", beta_start=0.0005, beta_end=0.0195,
+               clip_sample=False)
+    so, sp = O.DDIMOracle(**skw), DDIMScheduler(**skw)
+    so.set_timesteps(4)
+    sp.set_timesteps(4)
+    torch.manual_seed(2)
+    noise, cond = torch.randn(2, 1, 16, 16), torch.randn(2, 2, 16, 16)
+    want = O.diffusion_sample(lambda x, t, c: O.unet_forward(sd, cfg, x, t, context=c), so, noise, cond, mode="concat")
+    got = DiffusionInferer(sp).sample(noise.cuda(), m.cuda(), sp, conditioning=cond.cuda(), mode="concat", verbose=False)
+    check(got, want, TRAJ_TOL, "DiffusionInferer concat")
+    with pytest.raises(NotImplementedError):
+        DiffusionInferer(sp).sample(noise.cuda(), m, sp, mode="nope", verbose=False)
+
+    # ControlNet inferer (crossattn), 3 DDIM steps
+    ckw = G.CONTROLNET_CASE
+    torch.manual_seed(0)
+    cn = G.randomize_zero_params(nets().ControlNet(**ckw)).eval()
+    ukw = {k: v for k, v in ckw.items() if not k.startswith("conditioning_embedding")}
+    un = G.randomize_zero_params(nets().DiffusionModelUNet(out_channels=3, **ukw)).eval()
+    csd = {k: v.clone() for k, v in cn.state_dict().items()}
+    usd = {k: v.clone() for k, v in un.state_dict().items()}
+    ccfg = G.unet_oracle_cfg(ckw)
+    so.set_timesteps(3)
+    sp.set_timesteps(3)
+    torch.manual_seed(3)
+    noise, cnc, ctx = torch.randn(2, 3, 16, 16), torch.rand(2, 1, 16, 16), torch.randn(2, 1, 8)
+    want = O.controlnet_sample(
+        lambda x, t, c, d, mm: O.unet_forward(usd, ccfg, x, t, context=c, down_block_additional_residuals=d,
+                                              mid_block_additional_residual=mm),
+        lambda x, t, cc, c: O.controlnet_forward(csd, ccfg, x, t, cc, 1.0, c), so, noise, cnc, ctx)
+    got = ControlNetDiffusionInferer(sp).sample(noise.cuda(), un.cuda(), cn.cuda(), cnc.cuda(), sp,
+                                                conditioning=ctx.cuda(), verbose=False)
+    check(got, want, TRAJ_TOL, "ControlNetDiffusionInferer")
+
+
+def test_no_cpu_path(cuda_device):
+    m = nets().DiffusionModelUNet(2, 1, 1, num_res_blocks=1, num_channels=(8, 8), attention_levels=(False, False),
+                                  norm_num_groups=4).cuda()
+    with pytest.raises(RuntimeError):
+        m(torch.randn(1, 1, 8, 8), torch.tensor([1]))
