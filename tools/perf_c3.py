@@ -1,5 +1,8 @@
 """Dev probe (not the bench): one C3 UNet forward at a chosen volume with a per-operator time breakdown."""
 import argparse
+import sys
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 import collections
 import time
 
