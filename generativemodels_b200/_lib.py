@@ -44,7 +44,7 @@ class IgemmParams(C.Structure):
         ("act1", C.c_int32), ("scale", C.c_float),
         ("res_ptr", C.c_void_p), ("res_dtype", C.c_int32),
         ("res_sN", C.c_int64), ("res_sD", C.c_int64), ("res_sH", C.c_int64), ("res_sW", C.c_int64),
-        ("act2", C.c_int32), ("impl", C.c_int32),
+        ("act2", C.c_int32), ("stat_ptr", C.c_void_p), ("impl", C.c_int32),
     ]
 
 
@@ -101,6 +101,7 @@ SIGNATURES = {
     "b200_copy_channels": [_P, _I32, _I32, _P, _I32, _I32, _I64, _P],
     "b200_geglu": [_P, _I64, _I32, _I32, _P, _I32, _P],
     "b200_softmax_rows": [_P, _I64, _I32, _I64, _P, _I64, _P],
+    "b200_softmax_rows_partials": [_P, _I64, _I32, _I64, _P, _I32, _P, _I64, _P],
     "b200_attention_small": [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _F, _P],
     "b200_timestep_embedding": [_P, _I32, _I32, _F, _P, _P],
     "b200_small_linear": [_P, _I32, _I32, _P, _P, _I32, _I32, _I32, _P, _P],

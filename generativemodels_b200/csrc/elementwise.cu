@@ -202,6 +202,58 @@ __global__ void softmax_rows_kernel(const float* __restrict__ s, long long M, in
   for (long long c = S + t; c < p_pitch; c += TPR) pr[c] = __float2bfloat16_rn(0.f);
 }
 
+// One-pass variant: the score GEMM's epilogue already left (max, sum exp) per 256-column tile of every row, so the
+// row maximum and denominator come from a few hundred partials and the scores are read exactly once.
+__global__ void softmax_rows_partials_kernel(const float* __restrict__ s, int S, long long s_pitch,
+                                             const float2* __restrict__ part, int n_tiles,
+                                             __nv_bfloat16* __restrict__ p, long long p_pitch) {
+  const long long row = blockIdx.x;
+  const int t = threadIdx.x;
+  __shared__ float red[8];
+  const float2* pr = part + row * n_tiles;
+  float mx = -INFINITY;
+  for (int i = t; i < n_tiles; i += 256) mx = fmaxf(mx, pr[i].x);
+  mx = warp_max(mx);
+  if ((t & 31) == 0) red[t >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int i = t; i < n_tiles; i += 256) {
+    const float2 q = pr[i];
+    if (q.x > -INFINITY) sum += q.y * __expf(q.x - mx);
+  }
+  sum = warp_sum(sum);
+  if ((t & 31) == 0) red[t >> 5] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum += red[i];
+  const float inv = 1.0f / sum;
+  const float* sr = s + row * s_pitch;
+  __nv_bfloat16* po = p + row * p_pitch;
+  const bool vec = (s_pitch % 4 == 0) && (p_pitch % 4 == 0) && ((reinterpret_cast<uintptr_t>(s) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(p) & 7) == 0);
+  if (vec) {
+    const int S4 = S / 4;
+    for (int c = t; c < S4; c += 256) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(sr) + c);
+      __nv_bfloat162 lo = __floats2bfloat162_rn(__expf(v.x - mx) * inv, __expf(v.y - mx) * inv);
+      __nv_bfloat162 hi = __floats2bfloat162_rn(__expf(v.z - mx) * inv, __expf(v.w - mx) * inv);
+      uint2 o;
+      o.x = *reinterpret_cast<uint32_t*>(&lo);
+      o.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(po + 4 * (long long)c) = o;
+    }
+    for (int c = S4 * 4 + t; c < S; c += 256) po[c] = __float2bfloat16_rn(__expf(sr[c] - mx) * inv);
+  } else {
+    for (int c = t; c < S; c += 256) po[c] = __float2bfloat16_rn(__expf(sr[c] - mx) * inv);
+  }
+  for (long long c = S + t; c < p_pitch; c += 256) po[c] = __float2bfloat16_rn(0.f);
+}
+
 // ------------------------------------------------------------------------------------------------
 // time embedding + GEMV-class linear
 // ------------------------------------------------------------------------------------------------
@@ -449,6 +501,17 @@ extern "C" int b200_softmax_rows(const float* s, int64_t M, int32_t S, int64_t s
     softmax_rows_kernel<256><<<(unsigned)M, 256, 0, stream>>>(s, M, S, s_pitch, pp, p_pitch);
   }
   B200_LAUNCH_CHECK("softmax_rows_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_softmax_rows_partials(const float* s, int64_t M, int32_t S, int64_t s_pitch, const float* partials,
+                                          int32_t n_tiles, void* p, int64_t p_pitch, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(s && p && partials && M >= 1 && M < (1ll << 31) && S >= 1 && s_pitch >= S && p_pitch >= S && n_tiles >= 1,
+                 "softmax_rows_partials: bad arguments");
+  softmax_rows_partials_kernel<<<(unsigned)M, 256, 0, stream>>>(s, S, s_pitch, reinterpret_cast<const float2*>(partials),
+                                                               n_tiles, reinterpret_cast<__nv_bfloat16*>(p), p_pitch);
+  B200_LAUNCH_CHECK("softmax_rows_partials_kernel");
   return B200_OK;
 }
 

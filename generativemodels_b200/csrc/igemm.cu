@@ -57,7 +57,8 @@ struct IgemmDev {
   int tiles_w, tiles_h, tiles_d, tiles_n, num_tiles;
   // epilogue
   void* out_ptr;
-  int out_dtype, cout, out_cols, out_vec;
+  int out_dtype, cout, out_cols, out_vec, out_staged;
+  float* stat_ptr;          // optional [rows][tiles_n][2] (max, sum exp) per row and column tile
   long long out_sN, out_sD, out_sH, out_sW;
   const float* bias;
   const float* rowvec;
@@ -180,8 +181,8 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // Fused epilogue for CH consecutive columns of one output row (shared by both kernels).
 // ------------------------------------------------------------------------------------------------
 template <int CH>
-__device__ __forceinline__ void epilogue_row(const IgemmDev& p, float* v, int nb, int ow, long long out_off,
-                                             long long res_off, int col0) {
+__device__ __forceinline__ void epilogue_math(const IgemmDev& p, float* v, int nb, int ow, long long res_off,
+                                              int col0) {
   // bias + per-sample row vector (+ per-row bias for transposed-operand GEMMs)
   const float rb = p.row_bias ? __ldg(p.row_bias + ow) : 0.f;
 #pragma unroll
@@ -240,7 +241,11 @@ __device__ __forceinline__ void epilogue_row(const IgemmDev& p, float* v, int nb
 #pragma unroll
   for (int j = 0; j < CH; ++j)
     if (col0 + j >= p.cout) v[j] = 0.f;
+}
 
+// each thread stores its own row segment (good when consecutive rows are adjacent in memory: conv outputs)
+template <int CH>
+__device__ __forceinline__ void store_direct(const IgemmDev& p, const float* v, long long out_off, int col0) {
   if (p.out_dtype == B200_DT_BF16) {
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out_ptr) + out_off + col0;
     if (p.out_vec) {
@@ -268,6 +273,42 @@ __device__ __forceinline__ void epilogue_row(const IgemmDev& p, float* v, int nb
   }
 }
 
+template <int CH>
+__device__ __forceinline__ void epilogue_row(const IgemmDev& p, float* v, int nb, int ow, long long out_off,
+                                             long long res_off, int col0) {
+  epilogue_math<CH>(p, v, nb, ow, res_off, col0);
+  store_direct<CH>(p, v, out_off, col0);
+}
+
+// Row-coalesced store for wide row-major outputs (GEMM-shaped calls whose rows are far apart in memory, e.g. the
+// 89 600-column attention score matrix): the warp's 32 x CH tile goes through a padded shared-memory tile so that
+// every store instruction writes one contiguous CH-element row segment instead of 32 scattered 16-byte pieces.
+template <int CH>
+__device__ __forceinline__ void store_staged(const IgemmDev& p, const float* v, float* tile /*[32][CH+1]*/,
+                                             bool row_ok, long long out_off, int col0, int lane) {
+  constexpr int LD = CH + 1;
+#pragma unroll
+  for (int j = 0; j < CH; ++j) tile[lane * LD + j] = v[j];
+  __syncwarp();
+  const unsigned okmask = __ballot_sync(0xffffffffu, row_ok);
+  const int col = col0 + (lane % CH);
+  const bool col_ok = col < p.out_cols;
+  constexpr int ROWS_PER_IT = 32 / CH;      // CH == 32 -> 1 row per instruction, CH == 16 -> 2 rows
+#pragma unroll 4
+  for (int rr = 0; rr < 32; rr += ROWS_PER_IT) {
+    const int r = rr + lane / CH;
+    const long long off = __shfl_sync(0xffffffffu, out_off, r);
+    if (((okmask >> r) & 1u) && col_ok) {
+      const float x = tile[r * LD + (lane % CH)];
+      if (p.out_dtype == B200_DT_BF16)
+        reinterpret_cast<__nv_bfloat16*>(p.out_ptr)[off + col] = __float2bfloat16_rn(x);
+      else
+        reinterpret_cast<float*>(p.out_ptr)[off + col] = x;
+    }
+  }
+  __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------------
 // The tcgen05 kernel
 // ------------------------------------------------------------------------------------------------
@@ -286,6 +327,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
   auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
   auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  float* stage_tiles = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));   // 4 x [32][CH+1]
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -404,18 +446,41 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
       mbar_wait(tfull_bar(buf), acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
+      float run_max = -INFINITY, run_sum = 0.f;
+      float* my_tile = stage_tiles + (warp - 2) * (32 * (CH + 1));
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += CH) {
+        if (n0 + c0 >= p.out_cols) break;             // warp-uniform
         uint32_t raw[CH];
         if constexpr (CH == 32) tmem_ld32(taddr + c0, raw);
         else tmem_ld16(taddr + c0, raw);
         tmem_ld_wait();
-        if (row_ok && n0 + c0 < p.out_cols) {
-          float v[CH];
+        float v[CH];
 #pragma unroll
-          for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(raw[j]);
-          epilogue_row<CH>(p, v, nb, ow, out_off, res_off, n0 + c0);
+        for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(raw[j]);
+        if (row_ok) epilogue_math<CH>(p, v, nb, ow, res_off, n0 + c0);
+        if (p.stat_ptr && row_ok) {
+          // online (max, sum exp) over this row's valid columns of the tile: softmax partials for the row pass
+          float cmax = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < CH; ++j)
+            if (n0 + c0 + j < p.cout) cmax = fmaxf(cmax, v[j]);
+          if (cmax > -INFINITY) {
+            const float nm = fmaxf(run_max, cmax);
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+              if (n0 + c0 + j < p.cout) acc += __expf(v[j] - nm);
+            run_sum = run_sum * __expf(run_max - nm) + acc;
+            run_max = nm;
+          }
         }
+        if (p.out_staged) store_staged<CH>(p, v, my_tile, row_ok, out_off, n0 + c0, lane);
+        else if (row_ok) store_direct<CH>(p, v, out_off, n0 + c0);
+      }
+      if (p.stat_ptr && row_ok) {
+        float2* st = reinterpret_cast<float2*>(p.stat_ptr) + ((long long)ow * p.tiles_n + nt);
+        *st = make_float2(run_max, run_sum);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -527,7 +592,7 @@ static TileShape choose_tile(int OW, int OH, int OD, int sw, int sh, int sd) {
 template <int BN, int STAGES>
 static int launch_tc(const IgemmDev& d, cudaStream_t stream) {
   constexpr int kStageBytes = kABytes + BN * kBK * 2;
-  constexpr int smem = STAGES * kStageBytes + 1024 + 256;
+  constexpr int smem = STAGES * kStageBytes + 1024 + 256 + 4 * 32 * 33 * 4;
   static bool attr_done = false;
   if (!attr_done) {
     B200_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -613,6 +678,14 @@ extern "C" int b200_igemm(const b200_igemm_params* p, void* stream_v) {
                 (p->out_sH % g == 0) && (p->out_sW % g == 0) && (((uintptr_t)p->out_ptr) % 16 == 0);
     (void)esz;
   }
+  {
+    // rows far apart in memory (wide row-major GEMM outputs): stage the tile through smem for coalesced row stores
+    const long long esz = (p->out_dtype == B200_DT_BF16) ? 2 : 4;
+    d.out_staged = (p->out_sW * esz > 2048) ? 1 : 0;
+  }
+  d.stat_ptr = p->stat_ptr;
+  if (p->stat_ptr)
+    B200_CHECK_ARG(p->out_N == 1 && p->out_D == 1 && p->out_H == 1, "igemm: stat_ptr needs a GEMM-shaped call");
   if (p->res_ptr) {
     const int g = (p->res_dtype == B200_DT_BF16) ? 8 : 4;
     d.res_vec = (p->out_cols % g == 0) && (p->res_sN % g == 0) && (p->res_sD % g == 0) &&
@@ -643,7 +716,8 @@ extern "C" int b200_igemm(const b200_igemm_params* p, void* stream_v) {
   // N tile: as wide as the output needs, but narrower when the grid would not fill the SMs
   const int cols16 = ((p->out_cols + 15) / 16) * 16;
   int BN = cols16 <= 16 ? 16 : cols16 <= 32 ? 32 : cols16 <= 64 ? 64 : cols16 <= 128 ? 128 : 256;
-  while (BN > 64 && m_tiles * ((cols16 + BN - 1) / BN) < sm_count() && kchunks >= 8) BN >>= 1;
+  if (p->stat_ptr) BN = 256;      // the caller sizes the partials buffer for 256-column tiles
+  while (!p->stat_ptr && BN > 64 && m_tiles * ((cols16 + BN - 1) / BN) < sm_count() && kchunks >= 8) BN >>= 1;
   d.tiles_n = (cols16 + BN - 1) / BN;
   const long long ntiles = m_tiles * d.tiles_n;
   B200_CHECK_ARG(ntiles < (1ll << 31), "igemm: too many tiles");

@@ -536,6 +536,8 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, dh:
     chunk = max(128, min(T, (_ATTN_CHUNK_BYTES // (4 * Sp)) // 128 * 128))
     scores = torch.empty((min(chunk, T), Sp), dtype=torch.float32, device=q.device)
     probs = torch.empty((min(chunk, T), Sp), dtype=torch.bfloat16, device=q.device)
+    n_tiles = (Sp + 255) // 256
+    partials = torch.empty((min(chunk, T), n_tiles, 2), dtype=torch.float32, device=q.device)
     nk = round_up(dh, 64) // 64
     ns = round_up(S, 64) // 64
     for b in range(B):
@@ -556,9 +558,10 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, dh:
                 p.cout, p.out_cols = S, Sp
                 p.out_sN, p.out_sD, p.out_sH, p.out_sW = tc * Sp, tc * Sp, tc * Sp, Sp
                 p.act1, p.scale, p.act2 = ACT_NONE, scale, ACT_NONE
+                p.stat_ptr = partials.data_ptr()     # epilogue leaves (max, sum exp) per 256-column tile
                 igemm_raw(p)
-                check(lib.b200_softmax_rows(scores.data_ptr(), tc, S, Sp, probs.data_ptr(), Sp, _stream()),
-                      "b200_softmax_rows")
+                check(lib.b200_softmax_rows_partials(scores.data_ptr(), tc, S, Sp, partials.data_ptr(), n_tiles,
+                                                     probs.data_ptr(), Sp, _stream()), "b200_softmax_rows_partials")
                 # out = P V   (A = P rows over S, "weights" = V^T rows over S)
                 p2 = IgemmParams()
                 p2.a_ptr[0] = probs.data_ptr()

@@ -102,6 +102,8 @@ typedef struct {
   int32_t res_dtype;
   int64_t res_sN, res_sD, res_sH, res_sW;
   int32_t act2;
+  float*  stat_ptr;     /* optional softmax partials: [out_W][ceil(out_cols/256)][2] = (max, sum exp(v - max)) of every
+                           256-column tile of every output row (GEMM-shaped calls only); NULL to skip            */
   int32_t impl;         /* 0 = tcgen05 kernel, 1 = CUDA-core cross-check kernel  */
 } b200_igemm_params;
 
@@ -175,6 +177,9 @@ int b200_geglu(const void* x, int64_t M, int32_t H, int32_t x_pitch, void* y, in
  * (attention_scores.softmax(dim=-1), diffusion_model_unet.py:150,412). Pad columns are zeroed. */
 int b200_softmax_rows(const float* s, int64_t M, int32_t S, int64_t s_pitch, void* p, int64_t p_pitch,
                       void* stream);
+/* Same result in ONE pass over the scores, given the per-(row, 256-column tile) partials b200_igemm wrote. */
+int b200_softmax_rows_partials(const float* s, int64_t M, int32_t S, int64_t s_pitch, const float* partials,
+                               int32_t n_tiles, void* p, int64_t p_pitch, void* stream);
 
 /* Small-shape attention on CUDA cores (any head_dim <= 256, any S); used for the test-suite
  * head dims (2..8) and for cross-attention with a handful of context tokens.

@@ -141,6 +141,16 @@ class FakeLib:
         dst[:, :S] = torch.softmax(sc, -1).to(torch.bfloat16)
         return 0
 
+    def b200_softmax_rows_partials(self, s, M, S, sp, part, n_tiles, p, pp, stream):
+        sc = f32(s, M * sp).view(M, sp)[:, :S]
+        pt = f32(part, M * n_tiles * 2).view(M, n_tiles, 2)
+        mx = pt[:, :, 0].max(1)[0]
+        den = (pt[:, :, 1] * torch.exp(pt[:, :, 0] - mx[:, None])).nan_to_num(0.0).sum(1)
+        dst = bf16(p, M * pp).view(M, pp)
+        dst.zero_()
+        dst[:, :S] = (torch.exp(sc - mx[:, None]) / den[:, None]).to(torch.bfloat16)
+        return 0
+
     def b200_attention_small(self, q, k, v, o, B, T, S, heads, dh, qp, kp, vp, op, scale, stream):
         Cc = heads * dh
         qq = bf16(q, B * T * qp).view(B, T, qp)[:, :, :Cc].float().view(B, T, heads, dh).transpose(1, 2)

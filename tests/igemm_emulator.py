@@ -95,6 +95,18 @@ def emulate(p: IgemmParams) -> None:
         rb = _f32_view(p.row_bias, OW).copy()
         v += rb[None, None, None, :, None]
     v = _act(v, p.act1) * np.float32(p.scale)
+    if p.stat_ptr:       # softmax partials per 256-column tile (GEMM-shaped calls): (max, sum exp(v - max))
+        nt = (cols + 255) // 256
+        st = _f32_view(p.stat_ptr, OW * nt * 2).reshape(OW, nt, 2)
+        rows2d = v.reshape(OW, cols)
+        for t in range(nt):
+            seg = rows2d[:, t * 256:min((t + 1) * 256, p.cout)]
+            if seg.shape[1] == 0:
+                st[:, t, 0], st[:, t, 1] = -np.inf, 0.0
+                continue
+            mx = seg.max(1)
+            st[:, t, 0] = mx
+            st[:, t, 1] = np.exp(seg - mx[:, None]).sum(1)
 
     def strided_index(sN, sD, sH, sW):
         n = np.arange(N)[:, None, None, None, None]

@@ -137,6 +137,10 @@ def test_attention_tc_host_logic(monkeypatch):
     q, k, v = (torch.randn(B, T, Cc) for _ in range(3))
 
     class FakeLib:
+        def b200_softmax_rows_partials(self, s, M, S, sp, part, n_tiles, p, pp, stream):
+            from tests.cpu_backend import FakeLib as F2
+            return F2().b200_softmax_rows_partials(s, M, S, sp, part, n_tiles, p, pp, stream)
+
         def b200_softmax_rows(self, s, M, S, sp, p, pp, stream):
             import ctypes as C
             import numpy as np

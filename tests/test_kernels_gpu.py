@@ -161,7 +161,8 @@ def test_conv_transpose(cuda_device, sd, sp):
     assert_close(got, ref, 1e-2, f"conv_transpose {sd}d")
 
 
-@pytest.mark.parametrize("M,K,O", [(256, 64, 64), (1000, 320, 512), (77, 40, 24), (4096, 1024, 16), (130, 2048, 256)])
+@pytest.mark.parametrize("M,K,O", [(256, 64, 64), (1000, 320, 512), (77, 40, 24), (4096, 1024, 16), (130, 2048, 256),
+                                   (300, 128, 2048), (129, 64, 1100)])
 def test_linear(cuda_device, M, K, O):
     ops = _ops()
     torch.manual_seed(M)
@@ -256,7 +257,7 @@ def test_attention_small(cuda_device, B, T, S, heads, dh):
     assert_close(out[..., :Cc], ref, 1e-2, "attention_small")
 
 
-@pytest.mark.parametrize("B,T,heads,dh", [(1, 256, 1, 256), (2, 200, 1, 512), (1, 1024, 2, 64)])
+@pytest.mark.parametrize("B,T,heads,dh", [(1, 256, 1, 256), (2, 200, 1, 512), (1, 1024, 2, 64), (1, 2300, 1, 128)])
 def test_attention_tensorcore(cuda_device, B, T, heads, dh):
     """QK^T / softmax / PV on the tcgen05 GEMM path, V^T produced by the operand-swapped projection."""
     ops = _ops()
