@@ -60,6 +60,13 @@ class GnApplyParams(C.Structure):
                 ("y_ptr", C.c_void_p), ("y_pitch", C.c_int32)]
 
 
+class FlashParams(C.Structure):
+    _fields_ = [("q", C.c_void_p), ("k", C.c_void_p), ("vt", C.c_void_p), ("out", C.c_void_p), ("res", C.c_void_p),
+                ("B", C.c_int32), ("T", C.c_int32), ("S", C.c_int32), ("heads", C.c_int32), ("dh", C.c_int32),
+                ("q_pitch", C.c_int32), ("k_pitch", C.c_int32), ("vt_pitch", C.c_int32), ("out_pitch", C.c_int32),
+                ("res_pitch", C.c_int32), ("scale", C.c_float)]
+
+
 class DdimCoef(C.Structure):
     _fields_ = [("sqrt_alpha_prod_t", C.c_float), ("sqrt_beta_prod_t", C.c_float),
                 ("sqrt_alpha_prod_prev", C.c_float), ("dir_coef", C.c_float), ("sigma", C.c_float),
@@ -102,6 +109,7 @@ SIGNATURES = {
     "b200_geglu": [_P, _I64, _I32, _I32, _P, _I32, _P],
     "b200_softmax_rows": [_P, _I64, _I32, _I64, _P, _I64, _P],
     "b200_softmax_rows_partials": [_P, _I64, _I32, _I64, _P, _I32, _P, _I64, _P],
+    "b200_attention_flash": [C.POINTER(FlashParams), _P],
     "b200_attention_small": [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _F, _P],
     "b200_timestep_embedding": [_P, _I32, _I32, _F, _P, _P],
     "b200_small_linear": [_P, _I32, _I32, _P, _P, _I32, _I32, _I32, _P, _P],
@@ -135,7 +143,8 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the .so does not export it
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, C.c_int)
-    for which, struct in enumerate((IgemmParams, GnStatsParams, GnApplyParams, DdimCoef, DdpmCoef, PndmCoef, IgemmSeg)):
+    for which, struct in enumerate((IgemmParams, GnStatsParams, GnApplyParams, DdimCoef, DdpmCoef, PndmCoef, IgemmSeg,
+                                    FlashParams)):
         c_size = lib.b200_abi_sizeof(which)
         if c_size != C.sizeof(struct):
             raise B200Error(f"ABI mismatch: {struct.__name__} is {C.sizeof(struct)} bytes in Python but {c_size} in "

@@ -60,6 +60,7 @@ extern "C" int b200_abi_sizeof(int which) {
     case 4: return (int)sizeof(b200_ddpm_coef);
     case 5: return (int)sizeof(b200_pndm_coef);
     case 6: return (int)sizeof(b200_igemm_seg);
+    case 7: return (int)sizeof(b200_flash_params);
     default: return -1;
   }
 }

@@ -1,0 +1,470 @@
+// Flash-style attention on tcgen05 for the large-T self-attention of the 3-D UNet (T = S = 89 600, one head of 512)
+// and every other head_dim in {64, 128, 256, 512} with S >= 64.
+//
+// Replaces torch.baddbmm -> softmax -> torch.bmm (diffusion_model_unet.py:143-153, 406-416; autoencoderkl.py:261-269),
+// which materialise the T x S score matrix (29.9 GiB fp32 at T = 89 600).  Here the scores never leave the SM:
+//
+//   work item = (batch, head, 128-query tile, 256-wide slice of the value/output dimension)
+//   per 64-key block:   S  = Q K^T        tcgen05.mma  M=128 N=64,  K = head_dim in 64-wide chunks   -> TMEM (2 buffers)
+//                       P  = exp2(S*c - m) (fp32, online max / sum per row, one thread per row)      -> smem (bf16, 2 buffers)
+//                       O += P V          tcgen05.mma  M=128 N<=256, K=64                              -> TMEM (256 columns)
+//   epilogue:           out = O / l (+ residual), bf16
+//
+// A 128 x 512 fp32 accumulator would fill all 512 TMEM columns, so for head_dim 512 the output dimension is split in two
+// 256-wide slices handled by two work items that each recompute S (1.5x the QK^T FLOPs, but no score traffic at all).
+// The running maximum is only raised when it grows by more than 2^8 (lazy rescale), so rewriting O in TMEM is rare.
+//
+// Warp roles (192 threads): warp 0 = TMA producer (Q once per item, K chunks through a 4-stage ring, V^T tile),
+// warp 1 = MMA issuer, warps 2..5 = softmax + epilogue (thread <-> TMEM lane <-> query row).
+#include "common.cuh"
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <mutex>
+
+namespace b200 {
+
+struct FlashDev {
+  alignas(64) CUtensorMap tmQ;    // [B][T][C]      box (64 ch, 128 rows)
+  alignas(64) CUtensorMap tmK;    // [B][S][C]      box (64 ch, 64 rows)
+  alignas(64) CUtensorMap tmVt;   // [B][C][S]      box (64 keys, DV rows)
+  int B, T, S, heads, dh, d_chunks, dv, n_dv;
+  int q_tiles, n_items, n_kv;
+  float scale_log2;
+  __nv_bfloat16* out;
+  long long out_bstride, out_pitch;
+  const __nv_bfloat16* res;
+  long long res_bstride, res_pitch;
+};
+
+namespace fa {
+
+static constexpr int kThreads = 192;
+static constexpr int kBM = 128, kBKV = 64, kKStages = 4;
+static constexpr int kQChunkBytes = kBM * 64 * 2;      // 16 KB
+static constexpr int kKStageBytes = kBKV * 64 * 2;     // 8 KB
+static constexpr int kPBytes = kBM * kBKV * 2;         // 16 KB
+static constexpr float kRescaleThreshold = 8.0f;       // log2 domain
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {      // K-major, SWIZZLE_128B, 8-row groups 1024 B apart
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+__device__ __forceinline__ uint32_t idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+struct Item { int b, h, qt, dvi; };
+__device__ __forceinline__ Item decode(const FlashDev& p, int item) {
+  Item it;
+  it.dvi = item % p.n_dv; item /= p.n_dv;
+  it.qt = item % p.q_tiles; item /= p.q_tiles;
+  it.h = item % p.heads;
+  it.b = item / p.heads;
+  return it;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_constant__ FlashDev p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = base;
+  const uint32_t sK = sQ + p.d_chunks * kQChunkBytes;
+  const uint32_t sV = sK + kKStages * kKStageBytes;
+  const uint32_t sP = sV + p.dv * kBKV * 2;
+  const uint32_t bars = sP + 2 * kPBytes;
+  // barrier slots (8 bytes each)
+  const uint32_t q_full = bars, q_empty = bars + 8;
+  auto k_full = [&](int s) { return bars + 16 + 8u * s; };
+  auto k_empty = [&](int s) { return bars + 16 + 8u * (kKStages + s); };
+  const uint32_t v_full = bars + 16 + 8u * (2 * kKStages), v_empty = v_full + 8;
+  auto s_full = [&](int b) { return v_empty + 8 + 8u * b; };
+  auto s_empty = [&](int b) { return v_empty + 24 + 8u * b; };
+  auto p_full = [&](int b) { return v_empty + 40 + 8u * b; };
+  auto p_empty = [&](int b) { return v_empty + 56 + 8u * b; };
+  const uint32_t o_full = v_empty + 72, o_empty = o_full + 8;
+  const uint32_t tmem_slot = o_empty + 8;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    mbar_init(q_full, 1); mbar_init(q_empty, 1);
+    for (int s = 0; s < kKStages; ++s) { mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); }
+    mbar_init(v_full, 1); mbar_init(v_empty, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(s_full(b), 1); mbar_init(s_empty(b), 4);
+      mbar_init(p_full(b), 4); mbar_init(p_empty(b), 1);
+    }
+    mbar_init(o_full, 1); mbar_init(o_empty, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  const uint32_t tO = tmem;              // columns [0, 256)
+  const uint32_t tS = tmem + 256;        // two 64-column score buffers
+
+  const int n_kv = p.n_kv;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      int kst = 0; uint32_t kph = 0;
+      uint32_t vcount = 0, icount = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++icount) {
+        const Item it = decode(p, item);
+        const int ch0 = it.h * p.dh;
+        // Q tile: reused by every key block of the item
+        mbar_wait(q_empty, (icount & 1) ^ 1u);
+        mbar_expect_tx(q_full, p.d_chunks * kQChunkBytes);
+        for (int c = 0; c < p.d_chunks; ++c)
+          tma_load_3d(&p.tmQ, q_full, sQ + c * kQChunkBytes, ch0 + c * 64, it.qt * kBM, it.b);
+        // order matches the MMA warp's consumption: K_0, K_1, V_0, K_2, V_1, ...
+        for (int j = 0; j <= n_kv; ++j) {
+          if (j < n_kv) {
+            for (int c = 0; c < p.d_chunks; ++c) {
+              mbar_wait(k_empty(kst), kph ^ 1u);
+              mbar_expect_tx(k_full(kst), kKStageBytes);
+              tma_load_3d(&p.tmK, k_full(kst), sK + kst * kKStageBytes, ch0 + c * 64, j * kBKV, it.b);
+              if (++kst == kKStages) { kst = 0; kph ^= 1u; }
+            }
+          }
+          if (j >= 1) {
+            mbar_wait(v_empty, (vcount & 1) ^ 1u);
+            mbar_expect_tx(v_full, p.dv * kBKV * 2);
+            tma_load_3d(&p.tmVt, v_full, sV, (j - 1) * kBKV, ch0 + it.dvi * p.dv, it.b);
+            ++vcount;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      const uint32_t idesc_s = idesc_bf16(kBM, kBKV);
+      const uint32_t idesc_o = idesc_bf16(kBM, p.dv);
+      int kst = 0; uint32_t kph = 0;
+      uint32_t scount = 0;      // number of S blocks issued so far (global across items)
+      uint32_t pvcount = 0;     // number of PV blocks issued so far
+      uint32_t icount = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++icount) {
+        mbar_wait(q_full, icount & 1);
+        mbar_wait(o_empty, (icount & 1) ^ 1u);        // previous item's epilogue has drained O
+        fence_after();
+        for (int j = 0; j <= n_kv; ++j) {
+          if (j < n_kv) {
+            const int sb = scount & 1;
+            mbar_wait(s_empty(sb), ((scount >> 1) & 1) ^ 1u);
+            fence_after();
+            const uint32_t d_s = tS + sb * kBKV;
+            for (int c = 0; c < p.d_chunks; ++c) {
+              mbar_wait(k_full(kst), kph);
+              fence_after();
+              const uint64_t adesc = smem_desc(sQ + c * kQChunkBytes);
+              const uint64_t bdesc = smem_desc(sK + kst * kKStageBytes);
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                umma_bf16(d_s, adesc + 2u * kk, bdesc + 2u * kk, idesc_s, (c | kk) != 0 ? 1u : 0u);
+              umma_commit(k_empty(kst));
+              if (++kst == kKStages) { kst = 0; kph ^= 1u; }
+            }
+            umma_commit(s_full(sb));
+            ++scount;
+          }
+          if (j >= 1) {
+            const int pb = pvcount & 1;
+            mbar_wait(p_full(pb), (pvcount >> 1) & 1);
+            mbar_wait(v_full, pvcount & 1);
+            fence_after();
+            const uint64_t adesc = smem_desc(sP + pb * kPBytes);
+            const uint64_t bdesc = smem_desc(sV);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_bf16(tO, adesc + 2u * kk, bdesc + 2u * kk, idesc_o, (j > 1 || kk > 0) ? 1u : 0u);
+            umma_commit(v_empty);
+            umma_commit(p_empty(pb));
+            ++pvcount;
+          }
+        }
+        umma_commit(o_full);
+        umma_commit(q_empty);
+      }
+    }
+  } else {
+    // =========================== softmax + epilogue warps ===========================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    uint32_t scount = 0, icount = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++icount) {
+      const Item it = decode(p, item);
+      float m_used = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < n_kv; ++j, ++scount) {
+        const int sb = scount & 1;
+        mbar_wait(s_full(sb), (scount >> 1) & 1);
+        fence_after();
+        uint32_t raw[64];
+        tmem_ld32(tS + lane_addr + sb * kBKV, raw);
+        tmem_ld32(tS + lane_addr + sb * kBKV + 32, raw + 32);
+        tmem_ld_wait();
+        fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_empty(sb));     // S buffer may be overwritten by block j + 2
+        const int kv_valid = p.S - j * kBKV;          // columns >= kv_valid are TMA zero-fill
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 64; ++c) {
+          float s = __uint_as_float(raw[c]) * p.scale_log2;
+          if (c >= kv_valid) s = -INFINITY;
+          raw[c] = __float_as_uint(s);
+          mx = fmaxf(mx, s);
+        }
+        // lazy rescale: only raise the reference maximum when it would grow by more than 2^8
+        const bool need = (mx > m_used + kRescaleThreshold);
+        const float m_new = need ? mx : m_used;
+        const float factor = (need && m_used > -INFINITY) ? exp2f(m_used - m_new) : 1.0f;
+        const unsigned any = __ballot_sync(0xffffffffu, need && m_used > -INFINITY);
+        // P buffer (j & 1 of this item's sequence == scount & 1) must have been consumed by PV of block j - 2
+        if (scount >= 2) mbar_wait(p_empty(sb), ((scount >> 1) & 1) ^ 1u);
+        if (any) {
+          // O holds blocks < j; PV of block j - 1 must have completed before it is rewritten
+          if (j >= 1) {
+            const uint32_t prev = scount - 1;
+            mbar_wait(p_empty(prev & 1), (prev >> 1) & 1);
+          }
+          fence_after();
+          for (int c0 = 0; c0 < p.dv; c0 += 32) {
+            uint32_t o[32];
+            tmem_ld32(tO + lane_addr + c0, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * factor);
+            tmem_st32(tO + lane_addr + c0, o);
+          }
+          tmem_st_wait();
+          fence_before();
+        }
+        l_run *= factor;
+        m_used = m_new;
+        float lsum = 0.f;
+        // P (bf16) into the K-major SWIZZLE_128B tile the PV MMA reads as its A operand: row r at r * 128 bytes,
+        // 16-byte chunk index XOR (r & 7)
+        uint8_t* prow = smem_raw + (sP + sb * kPBytes - smem_u32(smem_raw)) + row * 128;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          float f[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float pe = exp2f(__uint_as_float(raw[ch * 8 + e]) - m_used);
+            f[e] = pe;
+            lsum += pe;
+          }
+          *reinterpret_cast<uint4*>(prow + ((ch ^ (row & 7)) << 4)) = pack8(f);
+        }
+        l_run += lsum;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full(sb));
+      }
+      // ---- epilogue: O / l (+ residual) -> bf16 ----
+      mbar_wait(o_full, icount & 1);
+      fence_after();
+      const int t = it.qt * kBM + row;
+      const bool ok = t < p.T;
+      const float inv = 1.0f / l_run;
+      const long long col0 = (long long)it.h * p.dh + (long long)it.dvi * p.dv;
+      __nv_bfloat16* orow = p.out + it.b * p.out_bstride + (long long)t * p.out_pitch + col0;
+      const __nv_bfloat16* rrow = p.res ? p.res + it.b * p.res_bstride + (long long)t * p.res_pitch + col0 : nullptr;
+      for (int c0 = 0; c0 < p.dv; c0 += 32) {
+        uint32_t o[32];
+        tmem_ld32(tO + lane_addr + c0, o);
+        tmem_ld_wait();
+        if (ok) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(o[g * 8 + e]) * inv;
+            if (rrow) {
+              float rf[8];
+              unpack8(__ldg(reinterpret_cast<const uint4*>(rrow + c0 + g * 8)), rf);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] += rf[e];
+            }
+            *reinterpret_cast<uint4*>(orow + c0 + g * 8) = pack8(f);
+          }
+        }
+      }
+      fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty);
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+static PFN_cuTensorMapEncodeTiled g_encode = nullptr;
+static std::once_flag g_once;
+static void load_encode() {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+      qres == cudaDriverEntryPointSuccess)
+    g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
+}
+
+static int encode3(CUtensorMap* tm, const void* ptr, cuuint64_t d0, cuuint64_t d1, cuuint64_t d2, cuuint64_t s1_bytes,
+                   cuuint64_t s2_bytes, cuuint32_t b0, cuuint32_t b1, const char* what) {
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {s1_bytes, s2_bytes};
+  cuuint32_t box[3] = {b0, b1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("attention_flash: cuTensorMapEncodeTiled(%s) failed with %d", what, (int)r);
+    return B200_ECUDA;
+  }
+  return B200_OK;
+}
+
+}  // namespace fa
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_attention_flash(const b200_flash_params* a, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(a && a->q && a->k && a->vt && a->out, "attention_flash: null pointer");
+  B200_CHECK_ARG(a->B >= 1 && a->T >= 1 && a->S >= 1 && a->heads >= 1, "attention_flash: bad extents");
+  B200_CHECK_ARG(a->dh == 64 || a->dh == 128 || a->dh == 256 || a->dh == 512,
+                 "attention_flash: head_dim %d not in {64,128,256,512}", a->dh);
+  B200_CHECK_ARG(a->q_pitch % 8 == 0 && a->k_pitch % 8 == 0 && a->vt_pitch % 8 == 0 && a->out_pitch % 8 == 0,
+                 "attention_flash: pitches must be multiples of 8 elements");
+  B200_CHECK_ARG(((uintptr_t)a->q & 15) == 0 && ((uintptr_t)a->k & 15) == 0 && ((uintptr_t)a->vt & 15) == 0 &&
+                 ((uintptr_t)a->out & 15) == 0 && ((uintptr_t)a->res & 15) == 0, "attention_flash: 16-byte alignment");
+  B200_CHECK_ARG(!a->res || a->res_pitch % 8 == 0, "attention_flash: residual pitch must be a multiple of 8");
+  std::call_once(fa::g_once, fa::load_encode);
+  if (!fa::g_encode) { set_error("attention_flash: cuTensorMapEncodeTiled unavailable"); return B200_ECUDA; }
+
+  FlashDev d;
+  memset(&d, 0, sizeof(d));
+  const int C = a->heads * a->dh;
+  d.B = a->B; d.T = a->T; d.S = a->S; d.heads = a->heads; d.dh = a->dh;
+  d.d_chunks = a->dh / 64;
+  d.dv = a->dh < 256 ? a->dh : 256;
+  d.n_dv = a->dh / d.dv;
+  d.q_tiles = (a->T + fa::kBM - 1) / fa::kBM;
+  d.n_kv = (a->S + fa::kBKV - 1) / fa::kBKV;
+  const long long items = (long long)a->B * a->heads * d.q_tiles * d.n_dv;
+  B200_CHECK_ARG(items < (1ll << 31), "attention_flash: too many work items");
+  d.n_items = (int)items;
+  d.scale_log2 = a->scale * 1.4426950408889634f;
+  d.out = reinterpret_cast<__nv_bfloat16*>(a->out);
+  d.out_pitch = a->out_pitch; d.out_bstride = (long long)a->T * a->out_pitch;
+  d.res = reinterpret_cast<const __nv_bfloat16*>(a->res);
+  d.res_pitch = a->res_pitch; d.res_bstride = (long long)a->T * a->res_pitch;
+  int rc;
+  if ((rc = fa::encode3(&d.tmQ, a->q, C, a->T, a->B, (cuuint64_t)a->q_pitch * 2, (cuuint64_t)a->T * a->q_pitch * 2, 64,
+                        fa::kBM, "Q"))) return rc;
+  if ((rc = fa::encode3(&d.tmK, a->k, C, a->S, a->B, (cuuint64_t)a->k_pitch * 2, (cuuint64_t)a->S * a->k_pitch * 2, 64,
+                        fa::kBKV, "K"))) return rc;
+  if ((rc = fa::encode3(&d.tmVt, a->vt, a->S, C, a->B, (cuuint64_t)a->vt_pitch * 2, (cuuint64_t)C * a->vt_pitch * 2,
+                        fa::kBKV, d.dv, "V^T"))) return rc;
+
+  const int smem = d.d_chunks * fa::kQChunkBytes + fa::kKStages * fa::kKStageBytes + d.dv * fa::kBKV * 2 +
+                   2 * fa::kPBytes + 1024 + 256;
+  static int attr = 0;
+  if (smem > attr) {
+    B200_CUDA(cudaFuncSetAttribute(fa::flash_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = smem;
+  }
+  const int grid = d.n_items < sm_count() ? d.n_items : sm_count();
+  fa::flash_attn_kernel<<<grid, fa::kThreads, smem, stream>>>(d);
+  B200_LAUNCH_CHECK("flash_attn_kernel");
+  return B200_OK;
+}

@@ -504,6 +504,8 @@ def geglu(x: CL) -> CL:
 # attention
 # --------------------------------------------------------------------------------------------------
 _TC_ATTN_MIN_S = 64
+_FLASH_HEAD_DIMS = (64, 128, 256, 512)
+_FORCE_UNFUSED_ATTENTION = False      # tests flip this to cover the GEMM + softmax + GEMM path
 _ATTN_CHUNK_BYTES = 6 << 30   # fp32 score slab per query chunk
 
 
@@ -511,10 +513,11 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, dh:
               vt: torch.Tensor | None = None, residual: torch.Tensor | None = None) -> torch.Tensor:
     """softmax(scale * Q K^T) V on packed [B, T, pitch] bf16 rows (heads are channel slices).
 
-    Tensor-core path (head_dim % 64 == 0, S >= 64): per (batch, head) QK^T -> fp32 scores, row softmax -> bf16
-    probabilities, PV — the two GEMMs run on the tcgen05 implicit-GEMM kernel, queries are processed in slabs so
-    the score matrix never exceeds a few GB (T = 89 600 in the 3-D config).  ``vt`` must then hold V^T
-    ``[B, H*dh, S_pitch]`` (produced for free by swapping the operands of the V projection).
+    Tensor-core paths (head_dim % 64 == 0, S >= 64; ``vt`` must hold V^T ``[B, H*dh, S_pitch]``, produced for free
+    by swapping the operands of the V projection):
+      * head_dim in {64, 128, 256, 512}: the flash-style tcgen05 kernel — scores stay in TMEM, online softmax;
+      * other multiples of 64 (e.g. 768): per (batch, head) QK^T -> fp32 scores (+ softmax partials from the GEMM
+        epilogue), one-pass row softmax -> bf16, PV, in query slabs so the score matrix never exceeds a few GB.
     Everything else runs on the CUDA-core online-softmax kernel.  ``residual`` ([B, T, pitch] bf16) is added in
     the PV epilogue on the tensor-core path only (callers add it themselves otherwise).
     """
@@ -531,6 +534,18 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, dh:
         check(lib.b200_attention_small(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, T, S, heads, dh,
                                        qp, k.shape[2], v.shape[2], out.shape[2], scale, _stream()),
               "b200_attention_small")
+        return out
+    if dh in _FLASH_HEAD_DIMS and not _FORCE_UNFUSED_ATTENTION:
+        fp = _lib.FlashParams()
+        fp.q, fp.k, fp.vt, fp.out = q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr()
+        fp.res = _ptr(residual)
+        fp.B, fp.T, fp.S, fp.heads, fp.dh = B, T, S, heads, dh
+        fp.q_pitch, fp.k_pitch, fp.vt_pitch, fp.out_pitch = qp, k.shape[2], vt.shape[2], out.shape[2]
+        fp.res_pitch = 0 if residual is None else residual.shape[2]
+        fp.scale = scale
+        if out.shape[2] > heads * dh:
+            out.zero_()
+        check(lib.b200_attention_flash(C.byref(fp), _stream()), "b200_attention_flash")
         return out
     Sp = round_up(S, 8)
     chunk = max(128, min(T, (_ATTN_CHUNK_BYTES // (4 * Sp)) // 128 * 128))

@@ -42,7 +42,8 @@ int b200_version(void);
 int b200_device_check(void);
 int b200_sm_count(void);
 /* sizeof() of the parameter structs below, for binding-layer ABI checks:
- * 0 igemm_params, 1 gn_stats_params, 2 gn_apply_params, 3 ddim_coef, 4 ddpm_coef, 5 pndm_coef, 6 igemm_seg. */
+ * 0 igemm_params, 1 gn_stats_params, 2 gn_apply_params, 3 ddim_coef, 4 ddpm_coef, 5 pndm_coef, 6 igemm_seg,
+ * 7 flash_params. */
 int b200_abi_sizeof(int which);
 
 /* ------------------------------------------------------------------------------------------------
@@ -180,6 +181,18 @@ int b200_softmax_rows(const float* s, int64_t M, int32_t S, int64_t s_pitch, voi
 /* Same result in ONE pass over the scores, given the per-(row, 256-column tile) partials b200_igemm wrote. */
 int b200_softmax_rows_partials(const float* s, int64_t M, int32_t S, int64_t s_pitch, const float* partials,
                                int32_t n_tiles, void* p, int64_t p_pitch, void* stream);
+
+/* Flash-style attention on tcgen05 (scores stay in TMEM; online softmax; head_dim in {64,128,256,512}, any T, S).
+ * q: [B][T][q_pitch], k: [B][S][k_pitch] bf16 rows with heads as channel slices [h*dh, (h+1)*dh);
+ * vt: V transposed, [B][heads*dh][vt_pitch] (key index contiguous); out / res: [B][T][pitch] bf16; res may be NULL.
+ * out[b,t,h*dh+c] = sum_s softmax_s(scale * q.k)[s] * v[s,c] (+ res).   (diffusion_model_unet.py:143-153, 406-416) */
+typedef struct {
+  const void* q; const void* k; const void* vt; void* out; const void* res;
+  int32_t B, T, S, heads, dh;
+  int32_t q_pitch, k_pitch, vt_pitch, out_pitch, res_pitch;
+  float scale;
+} b200_flash_params;
+int b200_attention_flash(const b200_flash_params* p, void* stream);
 
 /* Small-shape attention on CUDA cores (any head_dim <= 256, any S); used for the test-suite
  * head dims (2..8) and for cross-attention with a handful of context tokens.

@@ -151,6 +151,20 @@ class FakeLib:
         dst[:, :S] = (torch.exp(sc - mx[:, None]) / den[:, None]).to(torch.bfloat16)
         return 0
 
+    def b200_attention_flash(self, a, stream):
+        a = _obj(a)
+        B, T, S, heads, dh = a.B, a.T, a.S, a.heads, a.dh
+        Cc = heads * dh
+        qq = bf16(a.q, B * T * a.q_pitch).view(B, T, a.q_pitch)[:, :, :Cc].float().view(B, T, heads, dh).transpose(1, 2)
+        kk = bf16(a.k, B * S * a.k_pitch).view(B, S, a.k_pitch)[:, :, :Cc].float().view(B, S, heads, dh).transpose(1, 2)
+        vv = bf16(a.vt, B * Cc * a.vt_pitch).view(B, Cc, a.vt_pitch)[:, :, :S].float().transpose(1, 2)
+        vv = vv.reshape(B, S, heads, dh).transpose(1, 2)
+        out = (torch.softmax(a.scale * qq @ kk.transpose(-1, -2), -1) @ vv).transpose(1, 2).reshape(B, T, Cc)
+        if a.res:
+            out = out + bf16(a.res, B * T * a.res_pitch).view(B, T, a.res_pitch)[:, :, :Cc].float()
+        bf16(a.out, B * T * a.out_pitch).view(B, T, a.out_pitch)[:, :, :Cc] = out.to(torch.bfloat16)
+        return 0
+
     def b200_attention_small(self, q, k, v, o, B, T, S, heads, dh, qp, kp, vp, op, scale, stream):
         Cc = heads * dh
         qq = bf16(q, B * T * qp).view(B, T, qp)[:, :, :Cc].float().view(B, T, heads, dh).transpose(1, 2)

@@ -15,7 +15,7 @@ ROOT = Path(__file__).resolve().parents[1]
 def test_library_exports_every_declared_symbol():
     header = (ROOT / "include" / "b200gen.h").read_text()
     declared = set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", header))
-    declared -= {"b200_igemm_seg", "b200_igemm_params"}
+    declared -= {"b200_igemm_seg", "b200_igemm_params", "b200_flash_params"}
     lib = _lib.load()
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in b200gen.h but not exported by libb200gen.so"
@@ -27,7 +27,7 @@ def test_struct_sizes_match():
     lib = _lib.load()
     import ctypes as C
     for which, struct in enumerate((_lib.IgemmParams, _lib.GnStatsParams, _lib.GnApplyParams, _lib.DdimCoef,
-                                    _lib.DdpmCoef, _lib.PndmCoef, _lib.IgemmSeg)):
+                                    _lib.DdpmCoef, _lib.PndmCoef, _lib.IgemmSeg, _lib.FlashParams)):
         assert lib.b200_abi_sizeof(which) == C.sizeof(struct)
 
 

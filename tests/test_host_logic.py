@@ -154,6 +154,7 @@ def test_attention_tc_host_logic(monkeypatch):
 
     monkeypatch.setattr(ops._lib, "require_device", lambda: FakeLib())
     monkeypatch.setattr(ops, "_stream", lambda: 0)
+    monkeypatch.setattr(ops, "_FORCE_UNFUSED_ATTENTION", True)     # this test covers the GEMM + softmax + GEMM blocks
     qb, kb, vb = (t.to(torch.bfloat16).contiguous() for t in (q, k, v))
     vt = F.pad(vb.transpose(1, 2), (0, ops.round_up(T, 8) - T)).contiguous()
     out = ops.attention(qb, kb, None, heads, dh, 1 / math.sqrt(dh), vt=vt)

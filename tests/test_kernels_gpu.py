@@ -257,10 +257,14 @@ def test_attention_small(cuda_device, B, T, S, heads, dh):
     assert_close(out[..., :Cc], ref, 1e-2, "attention_small")
 
 
-@pytest.mark.parametrize("B,T,heads,dh", [(1, 256, 1, 256), (2, 200, 1, 512), (1, 1024, 2, 64), (1, 2300, 1, 128)])
-def test_attention_tensorcore(cuda_device, B, T, heads, dh):
-    """QK^T / softmax / PV on the tcgen05 GEMM path, V^T produced by the operand-swapped projection."""
+@pytest.mark.parametrize("unfused", [False, True], ids=["flash", "unfused"])
+@pytest.mark.parametrize("B,T,heads,dh", [(1, 256, 1, 256), (2, 200, 1, 512), (1, 1024, 2, 64), (1, 2300, 1, 128),
+                                          (1, 700, 1, 512)])
+def test_attention_tensorcore(cuda_device, B, T, heads, dh, unfused, monkeypatch):
+    """Flash-style tcgen05 attention (scores in TMEM) and the GEMM + softmax + GEMM path, V^T produced by the
+    operand-swapped projection, against fp32 softmax(QK^T)V on the same bf16-rounded q, k, v."""
     ops = _ops()
+    monkeypatch.setattr(ops, "_FORCE_UNFUSED_ATTENTION", unfused)
     torch.manual_seed(8)
     Cc = heads * dh
     x = torch.randn(B, T, Cc)
@@ -276,8 +280,25 @@ def test_attention_tensorcore(cuda_device, B, T, heads, dh):
     kg = ops.linear(xc, plk).t.reshape(B, T, -1)
     vt = ops.linear_transposed(xc.t.reshape(B, T, Cc), Cc, plv)
     assert_close(vt[:, :, :T].transpose(1, 2), bf(v), 1e-2, "V^T projection")
-    out = ops.attention(qg, kg, None, heads, dh, 1 / math.sqrt(dh), vt=vt)
-    assert_close(out[..., :Cc], ref, 2e-2, "attention tensor-core")
+    res = torch.randn(B, T, Cc)
+    out = ops.attention(qg, kg, None, heads, dh, 1 / math.sqrt(dh), vt=vt, residual=res.to(torch.bfloat16).cuda())
+    assert_close(out[..., :Cc], ref + bf(res), 2e-2, "attention tensor-core")
+
+
+def test_attention_flash_rescale(cuda_device):
+    """Keys whose scores grow along the sequence force the running maximum up by far more than 2^8 several times,
+    exercising the lazy O-rescale path (tcgen05.ld / tcgen05.st on the accumulator)."""
+    ops = _ops()
+    torch.manual_seed(11)
+    B, T, S, dh = 1, 300, 1000, 256
+    q = torch.randn(B, T, dh)
+    k = torch.randn(B, S, dh) * torch.linspace(0.2, 6.0, S)[None, :, None]
+    v = torch.randn(B, S, dh)
+    scale = 1 / math.sqrt(dh)
+    ref = _attn_ref(bf(q), bf(k), bf(v), 1, dh, scale)
+    vt = v.to(torch.bfloat16).transpose(1, 2).contiguous().cuda()
+    out = ops.attention(q.to(torch.bfloat16).cuda(), k.to(torch.bfloat16).cuda(), None, 1, dh, scale, vt=vt)
+    assert_close(out[..., :dh], ref, 2e-2, "flash attention with rescale")
 
 
 # ------------------------------------------------------------------------------------------------ time embedding
