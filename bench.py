@@ -67,10 +67,32 @@ def build_model_state(seed=0):
 # ---------------------------------------------------------------------------------------------------------------
 # reference / CPU arm: the oracle port of the reference's CPU path
 # ---------------------------------------------------------------------------------------------------------------
+def pick_cpu_threads():
+    """All host cores are available to the reference arm, but oneDNN convolutions of this size often run slower when
+    heavily oversubscribed across sockets; time a representative conv at a few thread counts and keep the fastest."""
+    import torch
+    import torch.nn.functional as F
+    ncpu = os.cpu_count() or 1
+    cands = sorted({c for c in (ncpu, ncpu // 2, 64, 32, 16, 8) if 1 <= c <= ncpu}, reverse=True)
+    x, w = torch.randn(1, 256, 16, 20, 16), torch.randn(256, 256, 3, 3, 3)
+    best, best_t = cands[0], float("inf")
+    for c in cands:
+        torch.set_num_threads(c)
+        F.conv3d(x, w, padding=1)
+        t0 = time.perf_counter()
+        for _ in range(2):
+            F.conv3d(x, w, padding=1)
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = c, dt
+    torch.set_num_threads(best)
+    return best
+
+
 def cpu_steps(model, steps: int, warmup: int):
     import torch
     from oracle import torch_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
+    pick_cpu_threads()
     sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
     cfg = dict(num_head_channels=C3["num_head_channels"], norm_num_groups=32, norm_eps=1e-6, with_conditioning=False)
     sched = O.DDIMOracle(**C3_SCHED)

@@ -127,6 +127,12 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct Item { int b, h, qt, dvi; };
 __device__ __forceinline__ Item decode(const FlashDev& p, int item) {
   Item it;
@@ -289,14 +295,24 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
         __syncwarp();
         if (lane == 0) mbar_arrive(s_empty(sb));     // S buffer may be overwritten by block j + 2
         const int kv_valid = p.S - j * kBKV;          // columns >= kv_valid are TMA zero-fill
-        float mx = -INFINITY;
+        // row maximum with 8 independent chains (one warp per scheduler here: instruction-level parallelism is the
+        // only latency hiding there is); raw[] keeps the UNSCALED scores, the scale is folded into the exp2 FFMA
+        float mx8[8];
 #pragma unroll
-        for (int c = 0; c < 64; ++c) {
-          float s = __uint_as_float(raw[c]) * p.scale_log2;
-          if (c >= kv_valid) s = -INFINITY;
-          raw[c] = __float_as_uint(s);
-          mx = fmaxf(mx, s);
+        for (int e = 0; e < 8; ++e) mx8[e] = -INFINITY;
+        if (kv_valid >= kBKV) {
+#pragma unroll
+          for (int c = 0; c < 64; ++c) mx8[c & 7] = fmaxf(mx8[c & 7], __uint_as_float(raw[c]));
+        } else {
+#pragma unroll
+          for (int c = 0; c < 64; ++c) {
+            const float sv = c < kv_valid ? __uint_as_float(raw[c]) : -INFINITY;
+            raw[c] = __float_as_uint(sv);
+            mx8[c & 7] = fmaxf(mx8[c & 7], sv);
+          }
         }
+        const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
+                               fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7]))) * p.scale_log2;
         // lazy rescale: only raise the reference maximum when it would grow by more than 2^8
         const bool need = (mx > m_used + kRescaleThreshold);
         const float m_new = need ? mx : m_used;
@@ -324,21 +340,24 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
         }
         l_run *= factor;
         m_used = m_new;
-        float lsum = 0.f;
         // P (bf16) into the K-major SWIZZLE_128B tile the PV MMA reads as its A operand: row r at r * 128 bytes,
-        // 16-byte chunk index XOR (r & 7)
+        // 16-byte chunk index XOR (r & 7).  p = 2^(s * c - m): one FFMA + one MUFU.EX2 per element, 8 sum chains.
         uint8_t* prow = smem_raw + (sP + sb * kPBytes - smem_u32(smem_raw)) + row * 128;
+        const float neg_m = -m_used;
+        float sum8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sum8[e] = 0.f;
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) {
           float f[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            const float pe = exp2f(__uint_as_float(raw[ch * 8 + e]) - m_used);
-            f[e] = pe;
-            lsum += pe;
+            f[e] = ex2_approx(fmaf(__uint_as_float(raw[ch * 8 + e]), p.scale_log2, neg_m));
+            sum8[e] += f[e];
           }
           *reinterpret_cast<uint4*>(prow + ((ch ^ (row & 7)) << 4)) = pack8(f);
         }
+        const float lsum = ((sum8[0] + sum8[1]) + (sum8[2] + sum8[3])) + ((sum8[4] + sum8[5]) + (sum8[6] + sum8[7]));
         l_run += lsum;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
         __syncwarp();
