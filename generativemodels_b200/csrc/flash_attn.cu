@@ -127,6 +127,19 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// One lane of a fully converged warp.  Issuing TMA / tcgen05 instructions under `if (elect_one())` instead of
+// `if (lane == 0)` lets the compiler keep their operands in uniform registers without a per-instruction
+// elect-and-loop sequence (the single-thread MMA issue rate bounds this kernel: its MMAs are only N = 64 wide).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xFFFFFFFF;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -191,8 +204,8 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
   const int n_kv = p.n_kv;
 
   if (warp == 0) {
-    // =========================== TMA producer ===========================
-    if (lane == 0) {
+    // =========================== TMA producer (whole warp runs the loop; one elected lane issues) =====
+    {
       int kst = 0; uint32_t kph = 0;
       uint32_t vcount = 0, icount = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++icount) {
@@ -200,31 +213,40 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
         const int ch0 = it.h * p.dh;
         // Q tile: reused by every key block of the item
         mbar_wait(q_empty, (icount & 1) ^ 1u);
-        mbar_expect_tx(q_full, p.d_chunks * kQChunkBytes);
-        for (int c = 0; c < p.d_chunks; ++c)
-          tma_load_3d(&p.tmQ, q_full, sQ + c * kQChunkBytes, ch0 + c * 64, it.qt * kBM, it.b);
+        if (elect_one()) {
+          mbar_expect_tx(q_full, p.d_chunks * kQChunkBytes);
+          for (int c = 0; c < p.d_chunks; ++c)
+            tma_load_3d(&p.tmQ, q_full, sQ + c * kQChunkBytes, ch0 + c * 64, it.qt * kBM, it.b);
+        }
+        __syncwarp();
         // order matches the MMA warp's consumption: K_0, K_1, V_0, K_2, V_1, ...
         for (int j = 0; j <= n_kv; ++j) {
           if (j < n_kv) {
             for (int c = 0; c < p.d_chunks; ++c) {
               mbar_wait(k_empty(kst), kph ^ 1u);
-              mbar_expect_tx(k_full(kst), kKStageBytes);
-              tma_load_3d(&p.tmK, k_full(kst), sK + kst * kKStageBytes, ch0 + c * 64, j * kBKV, it.b);
+              if (elect_one()) {
+                mbar_expect_tx(k_full(kst), kKStageBytes);
+                tma_load_3d(&p.tmK, k_full(kst), sK + kst * kKStageBytes, ch0 + c * 64, j * kBKV, it.b);
+              }
+              __syncwarp();
               if (++kst == kKStages) { kst = 0; kph ^= 1u; }
             }
           }
           if (j >= 1) {
             mbar_wait(v_empty, (vcount & 1) ^ 1u);
-            mbar_expect_tx(v_full, p.dv * kBKV * 2);
-            tma_load_3d(&p.tmVt, v_full, sV, (j - 1) * kBKV, ch0 + it.dvi * p.dv, it.b);
+            if (elect_one()) {
+              mbar_expect_tx(v_full, p.dv * kBKV * 2);
+              tma_load_3d(&p.tmVt, v_full, sV, (j - 1) * kBKV, ch0 + it.dvi * p.dv, it.b);
+            }
+            __syncwarp();
             ++vcount;
           }
         }
       }
     }
   } else if (warp == 1) {
-    // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    // =========================== MMA issuer (whole warp runs the loop; one elected lane issues) ========
+    {
       const uint32_t idesc_s = idesc_bf16(kBM, kBKV);
       const uint32_t idesc_o = idesc_bf16(kBM, p.dv);
       int kst = 0; uint32_t kph = 0;
@@ -244,15 +266,18 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
             for (int c = 0; c < p.d_chunks; ++c) {
               mbar_wait(k_full(kst), kph);
               fence_after();
-              const uint64_t adesc = smem_desc(sQ + c * kQChunkBytes);
-              const uint64_t bdesc = smem_desc(sK + kst * kKStageBytes);
+              if (elect_one()) {
+                const uint64_t adesc = smem_desc(sQ + c * kQChunkBytes);
+                const uint64_t bdesc = smem_desc(sK + kst * kKStageBytes);
 #pragma unroll
-              for (int kk = 0; kk < 4; ++kk)
-                umma_bf16(d_s, adesc + 2u * kk, bdesc + 2u * kk, idesc_s, (c | kk) != 0 ? 1u : 0u);
-              umma_commit(k_empty(kst));
+                for (int kk = 0; kk < 4; ++kk)
+                  umma_bf16(d_s, adesc + 2u * kk, bdesc + 2u * kk, idesc_s, (c | kk) != 0 ? 1u : 0u);
+                umma_commit(k_empty(kst));
+                if (c == p.d_chunks - 1) umma_commit(s_full(sb));
+              }
+              __syncwarp();
               if (++kst == kKStages) { kst = 0; kph ^= 1u; }
             }
-            umma_commit(s_full(sb));
             ++scount;
           }
           if (j >= 1) {
@@ -260,18 +285,23 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
             mbar_wait(p_full(pb), (pvcount >> 1) & 1);
             mbar_wait(v_full, pvcount & 1);
             fence_after();
-            const uint64_t adesc = smem_desc(sP + pb * kPBytes);
-            const uint64_t bdesc = smem_desc(sV);
+            if (elect_one()) {
+              const uint64_t adesc = smem_desc(sP + pb * kPBytes);
+              const uint64_t bdesc = smem_desc(sV);
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              umma_bf16(tO, adesc + 2u * kk, bdesc + 2u * kk, idesc_o, (j > 1 || kk > 0) ? 1u : 0u);
-            umma_commit(v_empty);
-            umma_commit(p_empty(pb));
+              for (int kk = 0; kk < 4; ++kk)
+                umma_bf16(tO, adesc + 2u * kk, bdesc + 2u * kk, idesc_o, (j > 1 || kk > 0) ? 1u : 0u);
+              umma_commit(v_empty);
+              umma_commit(p_empty(pb));
+              if (j == n_kv) {
+                umma_commit(o_full);
+                umma_commit(q_empty);
+              }
+            }
+            __syncwarp();
             ++pvcount;
           }
         }
-        umma_commit(o_full);
-        umma_commit(q_empty);
       }
     }
   } else {

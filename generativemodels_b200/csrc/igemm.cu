@@ -115,6 +115,17 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* tm, uint32_t bar,
       "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// One lane of a fully converged warp (elect.sync): the whole warp runs the role loop and only the asynchronous
+// issue instructions are guarded, so their operands stay in uniform registers without per-instruction elect loops.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xFFFFFFFF;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tcgen05_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
@@ -361,7 +372,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
 
   if (warp == 0) {
     // ============================== TMA producer ==============================
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -381,10 +392,13 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
           const int cw = iw0 + sg.dw, ch = ih0 + sg.dh, cd = id0 + sg.dd;
           for (int c = 0; c < sg.nchunks; ++c, ++kglob) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
-            const uint32_t a_dst = smem_base + stage * kStageBytes;
-            mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
-            tma_load_5d(tm, full_bar(stage), a_dst, (sg.c0 + c) * kBK, cw, ch, cd, nb);
-            tma_load_3d(&p.tmB, full_bar(stage), a_dst + kABytes, kglob * kBK, n0, wb);
+            if (elect_one()) {
+              const uint32_t a_dst = smem_base + stage * kStageBytes;
+              mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
+              tma_load_5d(tm, full_bar(stage), a_dst, (sg.c0 + c) * kBK, cw, ch, cd, nb);
+              tma_load_3d(&p.tmB, full_bar(stage), a_dst + kABytes, kglob * kBK, n0, wb);
+            }
+            __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
         }
@@ -392,7 +406,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
     }
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = make_idesc(kBM, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -406,18 +420,21 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
         for (int k = 0; k < num_k; ++k) {
           mbar_wait(full_bar(stage), phase);
           tcgen05_fence_after();
-          const uint32_t a_addr = smem_base + stage * kStageBytes;
-          const uint64_t adesc = make_smem_desc(a_addr);
-          const uint64_t bdesc = make_smem_desc(a_addr + kABytes);
+          if (elect_one()) {
+            const uint32_t a_addr = smem_base + stage * kStageBytes;
+            const uint64_t adesc = make_smem_desc(a_addr);
+            const uint64_t bdesc = make_smem_desc(a_addr + kABytes);
 #pragma unroll
-          for (int kk = 0; kk < kBK / 16; ++kk) {
-            // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in >>4 units
-            umma_bf16(d_tmem, adesc + 2u * kk, bdesc + 2u * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+            for (int kk = 0; kk < kBK / 16; ++kk) {
+              // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in >>4 units
+              umma_bf16(d_tmem, adesc + 2u * kk, bdesc + 2u * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+            }
+            tcgen05_commit(empty_bar(stage));
+            if (k == num_k - 1) tcgen05_commit(tfull_bar(buf));
           }
-          tcgen05_commit(empty_bar(stage));
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        tcgen05_commit(tfull_bar(buf));
       }
     }
   } else {
