@@ -6,15 +6,17 @@
 //
 //   work item = (batch, head, 128-query tile, 256-wide slice of the value/output dimension)
 //   per 64-key block:   S  = Q K^T        tcgen05.mma  M=128 N=64,  K = head_dim in 64-wide chunks   -> TMEM (2 buffers)
-//                       P  = exp2(S*c - m) (fp32, online max / sum per row, one thread per row)      -> smem (bf16, 2 buffers)
-//                       O += P V          tcgen05.mma  M=128 N<=256, K=64                              -> TMEM (256 columns)
+//                       P  = exp2(S*c - m) (fp32, online max / sum per row, one thread per row)      -> TMEM (bf16x2, 2 buffers)
+//                       O += P V          tcgen05.mma  M=128 N<=256, K=64, A operand read from TMEM     -> TMEM (256 columns)
 //   epilogue:           out = O / l (+ residual), bf16
 //
 // A 128 x 512 fp32 accumulator would fill all 512 TMEM columns, so for head_dim 512 the output dimension is split in two
 // 256-wide slices handled by two work items that each recompute S (1.5x the QK^T FLOPs, but no score traffic at all).
 // The running maximum is only raised when it grows by more than 2^8 (lazy rescale), so rewriting O in TMEM is rare.
 //
-// Warp roles (192 threads): warp 0 = TMA producer (Q once per item, K chunks through a 4-stage ring, V^T tile),
+// P lives in tensor memory (like the scores) so that all shared memory not holding Q goes to the K ring: the kernel is
+// bound by TMA latency x bytes in flight, not by the tensor pipe (Q alone is 128 KB at head_dim 512).
+// Warp roles (192 threads): warp 0 = TMA producer (Q once per item, K chunks through an 8-stage ring, V^T tile),
 // warp 1 = MMA issuer, warps 2..5 = softmax + epilogue (thread <-> TMEM lane <-> query row).
 #include "common.cuh"
 #include <cuda.h>
@@ -39,10 +41,9 @@ struct FlashDev {
 namespace fa {
 
 static constexpr int kThreads = 192;
-static constexpr int kBM = 128, kBKV = 64, kKStages = 4;
+static constexpr int kBM = 128, kBKV = 64, kKStages = 8;
 static constexpr int kQChunkBytes = kBM * 64 * 2;      // 16 KB
 static constexpr int kKStageBytes = kBKV * 64 * 2;     // 8 KB
-static constexpr int kPBytes = kBM * kBKV * 2;         // 16 KB
 static constexpr float kRescaleThreshold = 8.0f;       // log2 domain
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -69,6 +70,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
+// role warps (TMA / MMA): one lane polls, the warp re-converges — 32 lanes spinning on the same barrier word only
+// steal issue slots and shared-memory bandwidth from the epilogue / softmax warps
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+  __syncwarp();
+}
 __device__ __forceinline__ void tma_load_3d(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
@@ -87,6 +94,15 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// A operand from tensor memory (row = lane, two bf16 per 32-bit column), B from shared memory
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {      // K-major, SWIZZLE_128B, 8-row groups 1024 B apart
@@ -162,8 +178,7 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
   const uint32_t sQ = base;
   const uint32_t sK = sQ + p.d_chunks * kQChunkBytes;
   const uint32_t sV = sK + kKStages * kKStageBytes;
-  const uint32_t sP = sV + p.dv * kBKV * 2;
-  const uint32_t bars = sP + 2 * kPBytes;
+  const uint32_t bars = sV + p.dv * kBKV * 2;
   // barrier slots (8 bytes each)
   const uint32_t q_full = bars, q_empty = bars + 8;
   auto k_full = [&](int s) { return bars + 16 + 8u * s; };
@@ -200,6 +215,7 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
   const uint32_t tmem = *tmem_slot_ptr;
   const uint32_t tO = tmem;              // columns [0, 256)
   const uint32_t tS = tmem + 256;        // two 64-column score buffers
+  const uint32_t tP = tmem + 384;        // two 32-column probability buffers (bf16 pairs)
 
   const int n_kv = p.n_kv;
 
@@ -212,7 +228,7 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
         const Item it = decode(p, item);
         const int ch0 = it.h * p.dh;
         // Q tile: reused by every key block of the item
-        mbar_wait(q_empty, (icount & 1) ^ 1u);
+        mbar_wait_warp(q_empty, (icount & 1) ^ 1u);
         if (elect_one()) {
           mbar_expect_tx(q_full, p.d_chunks * kQChunkBytes);
           for (int c = 0; c < p.d_chunks; ++c)
@@ -223,7 +239,7 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
         for (int j = 0; j <= n_kv; ++j) {
           if (j < n_kv) {
             for (int c = 0; c < p.d_chunks; ++c) {
-              mbar_wait(k_empty(kst), kph ^ 1u);
+              mbar_wait_warp(k_empty(kst), kph ^ 1u);
               if (elect_one()) {
                 mbar_expect_tx(k_full(kst), kKStageBytes);
                 tma_load_3d(&p.tmK, k_full(kst), sK + kst * kKStageBytes, ch0 + c * 64, j * kBKV, it.b);
@@ -233,7 +249,7 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
             }
           }
           if (j >= 1) {
-            mbar_wait(v_empty, (vcount & 1) ^ 1u);
+            mbar_wait_warp(v_empty, (vcount & 1) ^ 1u);
             if (elect_one()) {
               mbar_expect_tx(v_full, p.dv * kBKV * 2);
               tma_load_3d(&p.tmVt, v_full, sV, (j - 1) * kBKV, ch0 + it.dvi * p.dv, it.b);
@@ -254,17 +270,17 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
       uint32_t pvcount = 0;     // number of PV blocks issued so far
       uint32_t icount = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++icount) {
-        mbar_wait(q_full, icount & 1);
-        mbar_wait(o_empty, (icount & 1) ^ 1u);        // previous item's epilogue has drained O
+        mbar_wait_warp(q_full, icount & 1);
+        mbar_wait_warp(o_empty, (icount & 1) ^ 1u);        // previous item's epilogue has drained O
         fence_after();
         for (int j = 0; j <= n_kv; ++j) {
           if (j < n_kv) {
             const int sb = scount & 1;
-            mbar_wait(s_empty(sb), ((scount >> 1) & 1) ^ 1u);
+            mbar_wait_warp(s_empty(sb), ((scount >> 1) & 1) ^ 1u);
             fence_after();
             const uint32_t d_s = tS + sb * kBKV;
             for (int c = 0; c < p.d_chunks; ++c) {
-              mbar_wait(k_full(kst), kph);
+              mbar_wait_warp(k_full(kst), kph);
               fence_after();
               if (elect_one()) {
                 const uint64_t adesc = smem_desc(sQ + c * kQChunkBytes);
@@ -282,15 +298,15 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
           }
           if (j >= 1) {
             const int pb = pvcount & 1;
-            mbar_wait(p_full(pb), (pvcount >> 1) & 1);
-            mbar_wait(v_full, pvcount & 1);
+            mbar_wait_warp(p_full(pb), (pvcount >> 1) & 1);
+            mbar_wait_warp(v_full, pvcount & 1);
             fence_after();
             if (elect_one()) {
-              const uint64_t adesc = smem_desc(sP + pb * kPBytes);
+              const uint32_t a_tmem = tP + pb * 32;          // 16 bf16 = 8 columns per K step
               const uint64_t bdesc = smem_desc(sV);
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk)
-                umma_bf16(tO, adesc + 2u * kk, bdesc + 2u * kk, idesc_o, (j > 1 || kk > 0) ? 1u : 0u);
+                umma_bf16_ts(tO, a_tmem + 8u * kk, bdesc + 2u * kk, idesc_o, (j > 1 || kk > 0) ? 1u : 0u);
               umma_commit(v_empty);
               umma_commit(p_empty(pb));
               if (j == n_kv) {
@@ -370,26 +386,28 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
         }
         l_run *= factor;
         m_used = m_new;
-        // P (bf16) into the K-major SWIZZLE_128B tile the PV MMA reads as its A operand: row r at r * 128 bytes,
-        // 16-byte chunk index XOR (r & 7).  p = 2^(s * c - m): one FFMA + one MUFU.EX2 per element, 8 sum chains.
-        uint8_t* prow = smem_raw + (sP + sb * kPBytes - smem_u32(smem_raw)) + row * 128;
+        // P (bf16 pairs) into tensor memory, where the PV MMA reads it as its A operand: this thread owns row `row`
+        // (= TMEM lane), word w holds keys 2w (low half) and 2w + 1.  p = 2^(s * c - m): one FFMA + one MUFU.EX2
+        // per element, 8 independent sum chains.
         const float neg_m = -m_used;
         float sum8[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) sum8[e] = 0.f;
+        uint32_t pw[32];
 #pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-          float f[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            f[e] = ex2_approx(fmaf(__uint_as_float(raw[ch * 8 + e]), p.scale_log2, neg_m));
-            sum8[e] += f[e];
-          }
-          *reinterpret_cast<uint4*>(prow + ((ch ^ (row & 7)) << 4)) = pack8(f);
+        for (int w = 0; w < 32; ++w) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(raw[2 * w]), p.scale_log2, neg_m));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(raw[2 * w + 1]), p.scale_log2, neg_m));
+          sum8[(2 * w) & 7] += p0;
+          sum8[(2 * w + 1) & 7] += p1;
+          __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
+          pw[w] = *reinterpret_cast<uint32_t*>(&h);
         }
+        tmem_st32(tP + lane_addr + sb * 32, pw);
+        tmem_st_wait();
         const float lsum = ((sum8[0] + sum8[1]) + (sum8[2] + sum8[3])) + ((sum8[4] + sum8[5]) + (sum8[6] + sum8[7]));
         l_run += lsum;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
+        fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full(sb));
       }
@@ -505,8 +523,7 @@ extern "C" int b200_attention_flash(const b200_flash_params* a, void* stream_v) 
   if ((rc = fa::encode3(&d.tmVt, a->vt, a->S, C, a->B, (cuuint64_t)a->vt_pitch * 2, (cuuint64_t)C * a->vt_pitch * 2,
                         fa::kBKV, d.dv, "V^T"))) return rc;
 
-  const int smem = d.d_chunks * fa::kQChunkBytes + fa::kKStages * fa::kKStageBytes + d.dv * fa::kBKV * 2 +
-                   2 * fa::kPBytes + 1024 + 256;
+  const int smem = d.d_chunks * fa::kQChunkBytes + fa::kKStages * fa::kKStageBytes + d.dv * fa::kBKV * 2 + 1024 + 256;
   static int attr = 0;
   if (smem > attr) {
     B200_CUDA(cudaFuncSetAttribute(fa::flash_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

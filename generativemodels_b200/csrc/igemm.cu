@@ -99,6 +99,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
+// role warps (TMA / MMA): one lane polls, the warp re-converges — 32 lanes spinning on the same barrier word only
+// steal issue slots and shared-memory bandwidth from the epilogue / softmax warps
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+  __syncwarp();
+}
 __device__ __forceinline__ void tma_load_5d(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c0,
                                             int c1, int c2, int c3, int c4) {
   asm volatile(
@@ -391,7 +397,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
           const CUtensorMap* tm = &p.tmA[sg.src];
           const int cw = iw0 + sg.dw, ch = ih0 + sg.dh, cd = id0 + sg.dd;
           for (int c = 0; c < sg.nchunks; ++c, ++kglob) {
-            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_wait_warp(empty_bar(stage), phase ^ 1u);
             if (elect_one()) {
               const uint32_t a_dst = smem_base + stage * kStageBytes;
               mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
@@ -414,11 +420,11 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         const int buf = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(tempty_bar(buf), acc_phase ^ 1u);
+        mbar_wait_warp(tempty_bar(buf), acc_phase ^ 1u);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + buf * BN;
         for (int k = 0; k < num_k; ++k) {
-          mbar_wait(full_bar(stage), phase);
+          mbar_wait_warp(full_bar(stage), phase);
           tcgen05_fence_after();
           if (elect_one()) {
             const uint32_t a_addr = smem_base + stage * kStageBytes;
