@@ -41,9 +41,11 @@ struct FlashDev {
 namespace fa {
 
 static constexpr int kThreads = 192;
-static constexpr int kBM = 128, kBKV = 64, kKStages = 8;
+static constexpr int kBM = 128, kBKV = 64;
+static constexpr int kKRingBytes = 64 * 1024;           // K ring: 4 stages x 2 chunks (or 8 x 1 for head_dim 64)
+static constexpr int kMaxKStages = 8;
 static constexpr int kQChunkBytes = kBM * 64 * 2;      // 16 KB
-static constexpr int kKStageBytes = kBKV * 64 * 2;     // 8 KB
+static constexpr int kKChunkBytes = kBKV * 64 * 2;     // 8 KB: 64 keys x 64 channels
 static constexpr float kRescaleThreshold = 8.0f;       // log2 domain
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -114,6 +116,11 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {      // K-major, 
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// the same descriptor split in its loop-invariant high word and an address-dependent low word, so the issue loop
+// only does 32-bit immediate adds
+static constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint64_t desc64(uint32_t lo) { return (static_cast<uint64_t>(kDescHi) << 32) | lo; }
 __device__ __forceinline__ uint32_t idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
@@ -172,18 +179,23 @@ __device__ __forceinline__ Item decode(const FlashDev& p, int item) {
   return it;
 }
 
+template <int DCH>      // head_dim / 64
 __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_constant__ FlashDev p) {
+  constexpr int CPS = DCH >= 2 ? 2 : 1;               // 64-channel K chunks per ring stage
+  constexpr int NSTEP = DCH / CPS;                    // ring stages consumed per key block
+  constexpr int kKStages = kKRingBytes / (CPS * kKChunkBytes);
+  constexpr int kKStageBytes = CPS * kKChunkBytes;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = base;
-  const uint32_t sK = sQ + p.d_chunks * kQChunkBytes;
-  const uint32_t sV = sK + kKStages * kKStageBytes;
+  const uint32_t sK = sQ + DCH * kQChunkBytes;
+  const uint32_t sV = sK + kKRingBytes;
   const uint32_t bars = sV + p.dv * kBKV * 2;
   // barrier slots (8 bytes each)
   const uint32_t q_full = bars, q_empty = bars + 8;
   auto k_full = [&](int s) { return bars + 16 + 8u * s; };
-  auto k_empty = [&](int s) { return bars + 16 + 8u * (kKStages + s); };
-  const uint32_t v_full = bars + 16 + 8u * (2 * kKStages), v_empty = v_full + 8;
+  auto k_empty = [&](int s) { return bars + 16 + 8u * (kMaxKStages + s); };
+  const uint32_t v_full = bars + 16 + 8u * (2 * kMaxKStages), v_empty = v_full + 8;
   auto s_full = [&](int b) { return v_empty + 8 + 8u * b; };
   auto s_empty = [&](int b) { return v_empty + 24 + 8u * b; };
   auto p_full = [&](int b) { return v_empty + 40 + 8u * b; };
@@ -230,19 +242,24 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
         // Q tile: reused by every key block of the item
         mbar_wait_warp(q_empty, (icount & 1) ^ 1u);
         if (elect_one()) {
-          mbar_expect_tx(q_full, p.d_chunks * kQChunkBytes);
-          for (int c = 0; c < p.d_chunks; ++c)
+          mbar_expect_tx(q_full, DCH * kQChunkBytes);
+#pragma unroll
+          for (int c = 0; c < DCH; ++c)
             tma_load_3d(&p.tmQ, q_full, sQ + c * kQChunkBytes, ch0 + c * 64, it.qt * kBM, it.b);
         }
         __syncwarp();
         // order matches the MMA warp's consumption: K_0, K_1, V_0, K_2, V_1, ...
         for (int j = 0; j <= n_kv; ++j) {
           if (j < n_kv) {
-            for (int c = 0; c < p.d_chunks; ++c) {
+#pragma unroll
+            for (int step = 0; step < NSTEP; ++step) {
               mbar_wait_warp(k_empty(kst), kph ^ 1u);
               if (elect_one()) {
                 mbar_expect_tx(k_full(kst), kKStageBytes);
-                tma_load_3d(&p.tmK, k_full(kst), sK + kst * kKStageBytes, ch0 + c * 64, j * kBKV, it.b);
+#pragma unroll
+                for (int cc = 0; cc < CPS; ++cc)
+                  tma_load_3d(&p.tmK, k_full(kst), sK + kst * kKStageBytes + cc * kKChunkBytes,
+                              ch0 + (step * CPS + cc) * 64, j * kBKV, it.b);
               }
               __syncwarp();
               if (++kst == kKStages) { kst = 0; kph ^= 1u; }
@@ -265,6 +282,7 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
     {
       const uint32_t idesc_s = idesc_bf16(kBM, kBKV);
       const uint32_t idesc_o = idesc_bf16(kBM, p.dv);
+      const uint32_t q_lo = desc_lo(sQ), k_lo = desc_lo(sK), v_lo = desc_lo(sV);
       int kst = 0; uint32_t kph = 0;
       uint32_t scount = 0;      // number of S blocks issued so far (global across items)
       uint32_t pvcount = 0;     // number of PV blocks issued so far
@@ -279,17 +297,22 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
             mbar_wait_warp(s_empty(sb), ((scount >> 1) & 1) ^ 1u);
             fence_after();
             const uint32_t d_s = tS + sb * kBKV;
-            for (int c = 0; c < p.d_chunks; ++c) {
+#pragma unroll
+            for (int step = 0; step < NSTEP; ++step) {
               mbar_wait_warp(k_full(kst), kph);
               fence_after();
               if (elect_one()) {
-                const uint64_t adesc = smem_desc(sQ + c * kQChunkBytes);
-                const uint64_t bdesc = smem_desc(sK + kst * kKStageBytes);
+                const uint32_t b_lo = k_lo + kst * (kKStageBytes >> 4);
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-                  umma_bf16(d_s, adesc + 2u * kk, bdesc + 2u * kk, idesc_s, (c | kk) != 0 ? 1u : 0u);
+                for (int cc = 0; cc < CPS; ++cc) {
+#pragma unroll
+                  for (int kk = 0; kk < 4; ++kk)
+                    umma_bf16(d_s, desc64(q_lo + (step * CPS + cc) * (kQChunkBytes >> 4) + 2 * kk),
+                              desc64(b_lo + cc * (kKChunkBytes >> 4) + 2 * kk), idesc_s,
+                              (step | cc | kk) != 0 ? 1u : 0u);
+                }
                 umma_commit(k_empty(kst));
-                if (c == p.d_chunks - 1) umma_commit(s_full(sb));
+                if (step == NSTEP - 1) umma_commit(s_full(sb));
               }
               __syncwarp();
               if (++kst == kKStages) { kst = 0; kph ^= 1u; }
@@ -303,10 +326,9 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
             fence_after();
             if (elect_one()) {
               const uint32_t a_tmem = tP + pb * 32;          // 16 bf16 = 8 columns per K step
-              const uint64_t bdesc = smem_desc(sV);
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk)
-                umma_bf16_ts(tO, a_tmem + 8u * kk, bdesc + 2u * kk, idesc_o, (j > 1 || kk > 0) ? 1u : 0u);
+                umma_bf16_ts(tO, a_tmem + 8u * kk, desc64(v_lo + 2 * kk), idesc_o, (j > 1 || kk > 0) ? 1u : 0u);
               umma_commit(v_empty);
               umma_commit(p_empty(pb));
               if (j == n_kv) {
@@ -523,14 +545,24 @@ extern "C" int b200_attention_flash(const b200_flash_params* a, void* stream_v) 
   if ((rc = fa::encode3(&d.tmVt, a->vt, a->S, C, a->B, (cuuint64_t)a->vt_pitch * 2, (cuuint64_t)C * a->vt_pitch * 2,
                         fa::kBKV, d.dv, "V^T"))) return rc;
 
-  const int smem = d.d_chunks * fa::kQChunkBytes + fa::kKStages * fa::kKStageBytes + d.dv * fa::kBKV * 2 + 1024 + 256;
-  static int attr = 0;
-  if (smem > attr) {
-    B200_CUDA(cudaFuncSetAttribute(fa::flash_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr = smem;
-  }
+  const int smem = d.d_chunks * fa::kQChunkBytes + fa::kKRingBytes + d.dv * fa::kBKV * 2 + 1024 + 256;
   const int grid = d.n_items < sm_count() ? d.n_items : sm_count();
-  fa::flash_attn_kernel<<<grid, fa::kThreads, smem, stream>>>(d);
+#define B200_FLASH_LAUNCH(DCH)                                                                                        \
+  do {                                                                                                                \
+    static bool attr_done = false;                                                                                    \
+    if (!attr_done) {                                                                                                 \
+      B200_CUDA(cudaFuncSetAttribute(fa::flash_attn_kernel<DCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+      attr_done = true;                                                                                               \
+    }                                                                                                                 \
+    fa::flash_attn_kernel<DCH><<<grid, fa::kThreads, smem, stream>>>(d);                                              \
+  } while (0)
+  switch (d.d_chunks) {
+    case 1: B200_FLASH_LAUNCH(1); break;
+    case 2: B200_FLASH_LAUNCH(2); break;
+    case 4: B200_FLASH_LAUNCH(4); break;
+    default: B200_FLASH_LAUNCH(8); break;
+  }
+#undef B200_FLASH_LAUNCH
   B200_LAUNCH_CHECK("flash_attn_kernel");
   return B200_OK;
 }
