@@ -311,7 +311,11 @@ def run_b200(args):
                        "l2": "per-step working set (tens of GB of activations) >> 126 MB L2; no explicit flush",
                        "finite_output": finite},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tf if peak_tf else None, "traffic": None,
+                         "frac": achieved / peak_tf if peak_tf else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel (the 256->256
+                         # 3x3x3 conv at 160x224x160; algorithmic 5.88e9 B) from the ncu --set full capture in
+                         # profiles/r1_ncu_igemm_conv256_fullres_details.txt
+                         "traffic": 8.11e9,
                          "kernel": "igemm_tc_kernel<256,4> (3x3x3 convolutions)", "peak_source": which + " sustained bf16",
                          "share_of_step": conv_ms / ms_total if ms_total else None,
                          "launches_timed": len(conv_events)},
