@@ -71,6 +71,16 @@ class Convolution(nn.Module, _Cached):
         return self._cached(extra, (self.conv.weight, self.conv.bias), lambda: ops.PackedConv(
             self.conv.weight, self.conv.bias, self.strides, pad, splits=splits))
 
+    def packed_upsample(self) -> ops.PackedUpsampleConv:
+        return self._cached(("up2x",), (self.conv.weight, self.conv.bias),
+                            lambda: ops.PackedUpsampleConv(self.conv.weight, self.conv.bias))
+
+    def forward_upsampled(self, x: CL) -> CL:
+        """conv(nearest_upsample_x2(x)) for a k3 s1 p1 convolution, as phase convolutions on the low-res input."""
+        if self.is_transposed or self.kernel_size != 3 or self.strides != 1 or self.padding != 1:
+            return self.forward(ops.upsample_nearest2x(x))
+        return ops.conv_upsample2x(x, self.packed_upsample())
+
     def forward(self, x: CL | Sequence[CL], **epilogue):
         if self.is_transposed:
             return ops.conv_transpose(x, self.packed(), act1=self.act)

@@ -31,7 +31,7 @@ class Upsample(nn.Module):
     def forward(self, x: CL) -> CL:
         if self.use_convtranspose:
             return self.conv(x)
-        return self.conv(ops.upsample_nearest2x(x))
+        return self.conv.forward_upsampled(x)
 
 
 class Downsample(nn.Module):

@@ -218,8 +218,9 @@ class Upsample(nn.Module):
     def forward(self, x: CL, emb=None) -> CL:
         if x.C != self.num_channels:
             raise ValueError("Input channels should be equal to num_channels")
-        x = ops.upsample_nearest2x(x)
-        return self.conv(x) if self.use_conv else x
+        if self.use_conv:
+            return self.conv.forward_upsampled(x)      # upsample folded into the conv: no 8x larger intermediate
+        return ops.upsample_nearest2x(x)
 
 
 class ResnetBlock(nn.Module):

@@ -222,6 +222,64 @@ class PackedConvTranspose:
         return tuple((i[d] - 1) * self.s[d] - 2 * self.p[d] + self.k[d] + self.op[d] for d in range(3))
 
 
+class PackedUpsampleConv:
+    """nearest x2 upsample followed by a k3 p1 convolution (Upsample blocks, diffusion_model_unet.py:574-586,
+    autoencoderkl.py:79-93) WITHOUT materialising the 4x/8x larger tensor: for each output phase (o = 2i + p per
+    dim) the three taps read only two distinct input voxels, so the op is 4 (2-D) / 8 (3-D) stride-1 convolutions
+    with 2-tap kernels on the low-resolution input whose weights are sums of the original taps
+        p = 0:  in[i-1] * w0 + in[i] * (w1 + w2)         p = 1:  in[i] * (w0 + w1) + in[i+1] * w2
+    each writing its phase of the output with doubled strides.  27 -> 8 taps per output voxel (3.4x fewer FLOPs).
+    Zero padding of the upsampled tensor maps to the TMA zero fill at in[-1] / in[n]."""
+
+    _TAPS = {0: ((-1, (0,)), (0, (1, 2))), 1: ((0, (0, 1)), (1, (2,)))}
+
+    def __init__(self, weight: torch.Tensor, bias: torch.Tensor | None):
+        w = weight.detach().float()
+        sd = w.dim() - 2
+        if tuple(w.shape[2:]) != (3,) * sd:
+            raise ValueError("PackedUpsampleConv expects a 3^d kernel")
+        self.spatial_dims = sd
+        self.cout, self.cin = w.shape[0], w.shape[1]
+        if sd == 2:
+            w = w.unsqueeze(2)
+        self.bias = None if bias is None else bias.detach().float().contiguous()
+        nch = round_up(self.cin, 64) // 64
+        self.phases = []
+        d_phases = (0, 1) if sd == 3 else (None,)
+        for pd in d_phases:
+            for ph in (0, 1):
+                for pw in (0, 1):
+                    td = self._TAPS[pd] if pd is not None else ((0, (0,)),)
+                    blocks, segs = [], []
+                    for (od, kds) in td:
+                        for (oh, khs) in self._TAPS[ph]:
+                            for (ow, kws) in self._TAPS[pw]:
+                                ws = 0
+                                for a in kds:
+                                    for b in khs:
+                                        for c in kws:
+                                            ws = ws + w[:, :, a, b, c]
+                                blocks.append(ws)
+                                segs.append((0, ow, oh, od, 0, nch))
+                    self.phases.append(((pd or 0, ph, pw), _pack_taps(blocks, self.cout), segs))
+
+
+def conv_upsample2x(src: CL, pu: PackedUpsampleConv, impl: int = 0) -> CL:
+    sd = src.spatial_dims
+    od = (src.D * 2 if sd == 3 else src.D, src.H * 2, src.W * 2)
+    out = new_cl(src.N, od, pu.cout, src.t.device, sd)
+    P = out.pitch
+    full = (od[0] * od[1] * od[2] * P, od[1] * od[2] * P, od[2] * P, P)
+    sdd = 2 if sd == 3 else 1
+    for (r, w, segs) in pu.phases:
+        off = r[0] * full[1] + r[1] * full[2] + r[2] * full[3]
+        strides = (full[0], full[1] * sdd, full[2] * 2, full[3] * 2)
+        p = _conv_params([src], w, segs, (1, 1, 1), out.t, (src.D, src.H, src.W), pu.cout, DT_BF16, pu.bias, None,
+                         ACT_NONE, 1.0, None, DT_BF16, ACT_NONE, out_elem_off=off, out_strides=strides, impl=impl)
+        igemm_raw(p)
+    return out
+
+
 # --------------------------------------------------------------------------------------------------
 # implicit GEMM launcher
 # --------------------------------------------------------------------------------------------------

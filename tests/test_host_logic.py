@@ -115,6 +115,20 @@ def test_conv_transpose_host_logic(sd, sp, k, s, p, op):
     close(back(out), ref)
 
 
+@pytest.mark.parametrize("sd,sp", [(2, (5, 6)), (3, (3, 4, 5))])
+def test_upsample_conv_host_logic(sd, sp):
+    """nearest x2 + k3 conv folded into per-phase 2-tap convolutions == F.interpolate + F.conv."""
+    torch.manual_seed(5)
+    x = torch.randn(2, 12, *sp)
+    w = torch.randn(10, 12, *([3] * sd)) / 6
+    b = torch.randn(10)
+    conv = F.conv2d if sd == 2 else F.conv3d
+    ref = conv(F.interpolate(bf(x), scale_factor=2.0, mode="nearest"), w, b, padding=1)   # fp32 weights: the fold
+    out = ops.conv_upsample2x(cl_cpu(x), ops.PackedUpsampleConv(w, b))                  # sums taps before bf16
+    assert tuple(back(out).shape) == tuple(ref.shape)
+    close(back(out), ref)
+
+
 def test_linear_and_transposed_host_logic():
     torch.manual_seed(3)
     M, K, O = 37, 40, 24

@@ -161,6 +161,21 @@ def test_conv_transpose(cuda_device, sd, sp):
     assert_close(got, ref, 1e-2, f"conv_transpose {sd}d")
 
 
+@pytest.mark.parametrize("sd,sp", [(2, (9, 12)), (3, (5, 6, 8))])
+def test_conv_upsample2x(cuda_device, sd, sp):
+    """Upsample block: F.interpolate(x2, nearest) + k3 conv as per-phase 2-tap tcgen05 convolutions."""
+    ops = _ops()
+    torch.manual_seed(6)
+    x = torch.randn(2, 64, *sp)
+    w = torch.randn(96, 64, *([3] * sd)) / math.sqrt(64 * 3 ** sd)
+    b = torch.randn(96)
+    conv = F.conv2d if sd == 2 else F.conv3d
+    ref = conv(F.interpolate(bf(x), scale_factor=2.0, mode="nearest"), w, b, padding=1)
+    got = ops.from_cl(ops.conv_upsample2x(ops.to_cl(x.cuda()), ops.PackedUpsampleConv(w.cuda(), b.cuda())))
+    assert tuple(got.shape) == tuple(ref.shape)
+    assert_close(got, ref, 1e-2, f"conv_upsample2x {sd}d")
+
+
 @pytest.mark.parametrize("M,K,O", [(256, 64, 64), (1000, 320, 512), (77, 40, 24), (4096, 1024, 16), (130, 2048, 256),
                                    (300, 128, 2048), (129, 64, 1100)])
 def test_linear(cuda_device, M, K, O):
