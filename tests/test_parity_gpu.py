@@ -364,3 +364,25 @@ def test_no_cpu_path(cuda_device):
                                   norm_num_groups=4).cuda()
     with pytest.raises(RuntimeError):
         m(torch.randn(1, 1, 8, 8), torch.tensor([1]))
+
+
+def test_cuda_graph_replay_matches_eager(cuda_device):
+    """generativemodels_b200.cuda_graph.graphed(): captured replay is bit-identical to the eager forward and can be
+    driven by DiffusionInferer.sample unchanged."""
+    from generativemodels_b200.cuda_graph import graphed
+    from generativemodels_b200.inferers import DiffusionInferer
+    from generativemodels_b200.networks.schedulers import DDIMScheduler
+    kw = G.UNET_CASES["unet2d_attn"]
+    torch.manual_seed(0)
+    m = G.randomize_zero_params(nets().DiffusionModelUNet(**kw)).cuda().eval()
+    g = graphed(m)
+    torch.manual_seed(1)
+    x = torch.randn(2, 1, 16, 16).cuda()
+    for t in (900.0, 20.0):
+        ts = torch.Tensor((t,)).cuda()
+        assert torch.equal(g(x, timesteps=ts).clone(), m(x, timesteps=ts))
+    s = DDIMScheduler(num_train_timesteps=1000)
+    s.set_timesteps(4)
+    a = DiffusionInferer(s).sample(x, m, s, verbose=False)
+    b = DiffusionInferer(s).sample(x, g, s, verbose=False)
+    assert torch.equal(a, b)

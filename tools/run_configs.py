@@ -40,10 +40,14 @@ un = redraw(DiffusionModelUNet(2, 3, 3, num_res_blocks=2, num_channels=(128, 256
 s = DDIMScheduler(1000, "linear_beta", beta_start=0.0015, beta_end=0.0195)
 s.set_timesteps(50)
 inf = LatentDiffusionInferer(s, scale_factor=1.0)
-for N in (1, 8):
+from generativemodels_b200.cuda_graph import graphed
+ung = graphed(un)
+for N in (1, 8, 32):
     noise = torch.randn(N, 3, 64, 64).cuda()
     t = timed(lambda: inf.sample(noise, ae, un, s, verbose=False), 2)
     print(f"C2 LDM DDIM-50 N={N}: {t*1e3:.1f} ms/call, {N/t:.2f} samples/s, {N*65536/t/1e6:.3f} Mpixel/s")
+    t = timed(lambda: inf.sample(noise, ae, ung, s, verbose=False), 2)
+    print(f"C2 LDM DDIM-50 N={N} (CUDA graph): {t*1e3:.1f} ms/call, {N/t:.2f} samples/s, {N*65536/t/1e6:.3f} Mpixel/s")
 
 # ---- C4: 3-D VQVAE (256,256), K=256, D=32, 1x128^3 ----
 vq = VQVAE(3, 1, 1, num_channels=(256, 256), num_res_channels=256, num_res_layers=2,
