@@ -33,13 +33,6 @@ def cl_cpu(x):
     return ops.CL(t, C_, sd)
 
 
-def nchw(a, f32=False, C_=None):
-    C_ = a.C if C_ is None else C_
-    t = (a if f32 else a.t)[..., :C_].float()
-    sd = 3 if f32 is True and False else None
-    return t
-
-
 def back(a):
     t = a.t[..., : a.C].float()
     if a.spatial_dims == 2:
