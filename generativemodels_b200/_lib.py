@@ -81,6 +81,12 @@ class DdpmCoef(C.Structure):
                 ("var_mode", C.c_int32), ("prediction_type", C.c_int32), ("clip", C.c_int32)]
 
 
+class KlCoef(C.Structure):
+    _fields_ = [("sqrt_alpha_prod_t", C.c_float), ("sqrt_beta_prod_t", C.c_float), ("coef_x0", C.c_float),
+                ("coef_xt", C.c_float), ("log_pred_var", C.c_float), ("log_post_var", C.c_float),
+                ("bin_width", C.c_float), ("prediction_type", C.c_int32), ("clip", C.c_int32), ("is_t0", C.c_int32)]
+
+
 class PndmCoef(C.Structure):
     _fields_ = [("w", C.c_float * 4), ("n_hist", C.c_int32), ("sample_coeff", C.c_float), ("eps_coeff", C.c_float),
                 ("v_alpha", C.c_float), ("v_beta", C.c_float), ("prediction_type", C.c_int32)]
@@ -115,6 +121,7 @@ SIGNATURES = {
     "b200_small_linear": [_P, _I32, _I32, _P, _P, _I32, _I32, _I32, _P, _P],
     "b200_ddim_step": [_P, _P, _P, C.POINTER(DdimCoef), _P, _P, _I64, _P],
     "b200_ddpm_step": [_P, _P, _P, _P, C.POINTER(DdpmCoef), _P, _P, _I64, _P],
+    "b200_ddpm_kl": [_P, _P, _P, C.POINTER(KlCoef), _P, _P, _I32, _I64, _P],
     "b200_pndm_step": [C.POINTER(_P), _P, C.POINTER(PndmCoef), _P, _P, _I64, _P],
     "b200_exp_half_clamped": [_P, _F, _F, _P, _I64, _P],
     "b200_scale_f32": [_P, _F, _F, _P, _I64, _P],
@@ -144,7 +151,7 @@ def load():
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, C.c_int)
     for which, struct in enumerate((IgemmParams, GnStatsParams, GnApplyParams, DdimCoef, DdpmCoef, PndmCoef, IgemmSeg,
-                                    FlashParams)):
+                                    FlashParams, KlCoef)):
         c_size = lib.b200_abi_sizeof(which)
         if c_size != C.sizeof(struct):
             raise B200Error(f"ABI mismatch: {struct.__name__} is {C.sizeof(struct)} bytes in Python but {c_size} in "

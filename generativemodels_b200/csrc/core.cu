@@ -61,6 +61,7 @@ extern "C" int b200_abi_sizeof(int which) {
     case 5: return (int)sizeof(b200_pndm_coef);
     case 6: return (int)sizeof(b200_igemm_seg);
     case 7: return (int)sizeof(b200_flash_params);
+    case 8: return (int)sizeof(b200_kl_coef);
     default: return -1;
   }
 }

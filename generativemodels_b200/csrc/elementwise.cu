@@ -346,6 +346,59 @@ __global__ void ddpm_step_kernel(const float* __restrict__ eps_in, const float* 
   }
 }
 
+// tanh approximation of the standard normal CDF used by the reference (inferer.py:279-283)
+__device__ __forceinline__ float approx_normal_cdf(float x) {
+  return 0.5f * (1.0f + tanhf(0.7978845608028654f * (x + 0.044715f * x * x * x)));
+}
+
+__global__ void ddpm_kl_kernel(const float* __restrict__ x0, const float* __restrict__ xt,
+                               const float* __restrict__ mo, b200_kl_coef c, float* __restrict__ kl_out,
+                               double* __restrict__ sample_sum, long long per_sample) {
+  const int n = blockIdx.y;
+  const long long base = (long long)n * per_sample;
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per_sample;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float a = x0[base + i], s = xt[base + i], m = mo[base + i];
+    float p0;
+    if (c.prediction_type == B200_PRED_EPSILON) p0 = (s - c.sqrt_beta_prod_t * m) / c.sqrt_alpha_prod_t;
+    else if (c.prediction_type == B200_PRED_SAMPLE) p0 = m;
+    else p0 = c.sqrt_alpha_prod_t * s - c.sqrt_beta_prod_t * m;
+    if (c.clip) p0 = fminf(fmaxf(p0, -1.0f), 1.0f);
+    const float pred_mean = c.coef_x0 * p0 + c.coef_xt * s;
+    float kl;
+    if (c.is_t0) {
+      // -log p(x_0 | x_1): discretised Gaussian (inferer.py:285-321)
+      const float centered = a - pred_mean;
+      const float inv_stdv = expf(-0.5f * c.log_pred_var);
+      const float cdf_plus = approx_normal_cdf(inv_stdv * (centered + c.bin_width / 2));
+      const float cdf_min = approx_normal_cdf(inv_stdv * (centered - c.bin_width / 2));
+      float lp;
+      if (a < -0.999f) lp = logf(fmaxf(cdf_plus, 1e-12f));
+      else if (a > 0.999f) lp = logf(fmaxf(1.0f - cdf_min, 1e-12f));
+      else lp = logf(fmaxf(cdf_plus - cdf_min, 1e-12f));
+      kl = -lp;
+    } else {
+      const float post_mean = c.coef_x0 * a + c.coef_xt * s;
+      const float d = post_mean - pred_mean;
+      kl = 0.5f * (-1.0f + c.log_pred_var - c.log_post_var + expf(c.log_post_var - c.log_pred_var) +
+                   d * d * expf(-c.log_pred_var));
+    }
+    if (kl_out) kl_out[base + i] = kl;
+    acc += kl;
+  }
+  __shared__ double red[8];
+  double d = (double)acc;
+  for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = d;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    atomicAdd(sample_sum + n, t);
+  }
+}
+
 struct PndmPtrs { const float* h[4]; };
 
 __global__ void pndm_step_kernel(PndmPtrs hp, const float* __restrict__ x, b200_pndm_coef c,
@@ -596,5 +649,15 @@ extern "C" int b200_scale_f32(const float* x, float mul, float div, float* out, 
   B200_CHECK_ARG(x && out && n >= 1 && div != 0.f, "scale_f32: bad arguments");
   scale_f32_kernel<<<grid_for(n), 256, 0, stream>>>(x, mul, div, out, n);
   B200_LAUNCH_CHECK("scale_f32_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_ddpm_kl(const float* x0, const float* xt, const float* model_out, const b200_kl_coef* c, float* kl_out,
+                            double* sample_sum, int32_t N, int64_t per_sample, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(x0 && xt && model_out && c && sample_sum && N >= 1 && N <= 65535 && per_sample >= 1, "ddpm_kl: bad arguments");
+  dim3 grid(grid_for(per_sample, 256, 4), N);
+  ddpm_kl_kernel<<<grid, 256, 0, stream>>>(x0, xt, model_out, *c, kl_out, sample_sum, per_sample);
+  B200_LAUNCH_CHECK("ddpm_kl_kernel");
   return B200_OK;
 }

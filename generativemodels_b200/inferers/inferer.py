@@ -4,7 +4,7 @@ LatentDiffusionInferer (323-487), ControlNetDiffusionInferer (561-707), ControlN
 The loops are the reference's: one network forward + one ``scheduler.step`` per timestep, the sample travelling
 between them as an NC[D]HW fp32 CUDA tensor.  What differs is underneath — each forward is the fused-kernel UNet, each
 step one elementwise kernel, and ControlNet residuals are handed to the UNet as channels-last handles without a
-layout round trip.  ``get_likelihood`` (a training/evaluation path) is not implemented yet.
+layout round trip.  ``get_likelihood`` runs the same networks and one fused KL kernel per step.
 """
 from __future__ import annotations
 
@@ -100,9 +100,92 @@ class DiffusionInferer(Inferer):
                 intermediates.append(image)
         return (image, intermediates) if save_intermediates else image
 
-    def get_likelihood(self, *args, **kwargs):
-        raise NotImplementedError("get_likelihood is a training/evaluation path outside the sampling hot path "
-                                  "(SURVEY.md §8f); it is not implemented on the B200 kernels yet")
+    @torch.no_grad()
+    def get_likelihood(self, inputs: torch.Tensor, diffusion_model: Callable[..., torch.Tensor],
+                       scheduler: Callable[..., torch.Tensor] | None = None, save_intermediates: bool | None = False,
+                       conditioning: torch.Tensor | None = None, mode: str = "crossattn",
+                       original_input_range: tuple | None = (0, 255), scaled_input_range: tuple | None = (0, 1),
+                       verbose: bool = True, seg: torch.Tensor | None = None):
+        """Variational lower bound per sample (inferer.py:145-277): for every timestep add noise, run the network,
+        and accumulate the KL between the true posterior and the predicted one (decoder NLL at t = 0).  The whole
+        per-step tail — predicted x0, clip, both means, KL / discretised-Gaussian term, per-sample mean — is one
+        fused kernel (b200_ddpm_kl).  Fixed-variance DDPM schedulers (the reference's learned-variance branch
+        evaluates ``if predicted_variance`` on a tensor and cannot run)."""
+        import ctypes as C
+
+        from .. import _lib
+
+        if not scheduler:
+            scheduler = self.scheduler
+        if scheduler._get_name() != "DDPMScheduler":
+            raise NotImplementedError(f"Likelihood computation is only compatible with DDPMScheduler,"
+                                      f" you are using {scheduler._get_name()}")
+        _check_mode(mode)
+        if scheduler.variance_type in ["learned", "learned_range"]:
+            raise NotImplementedError("get_likelihood with a learned variance is not supported")
+        lib = _lib.require_device()
+        x0 = inputs.contiguous().float()
+        N = x0.shape[0]
+        per = x0.numel() // N
+        noise = torch.randn_like(inputs).to(inputs.device)
+        total_kl = torch.zeros(N, device=inputs.device)
+        intermediates = []
+        bin_width = (scaled_input_range[1] - scaled_input_range[0]) / (original_input_range[1] - original_input_range[0])
+        for t in _progress(scheduler, verbose):
+            t = int(t)
+            timesteps = torch.full(inputs.shape[:1], t, device=inputs.device).long()
+            noisy_image = self.scheduler.add_noise(original_samples=inputs, noise=noise, timesteps=timesteps)
+            if mode == "concat":
+                model_output = diffusion_model(torch.cat([noisy_image, conditioning], dim=1), timesteps=timesteps,
+                                               context=None)
+            else:
+                model_output = diffusion_model(x=noisy_image, timesteps=timesteps, context=conditioning)
+            a_t = scheduler.alphas_cumprod[t]
+            a_prev = scheduler.alphas_cumprod[t - 1] if t > 0 else scheduler.one
+            b_t, b_prev = 1 - a_t, 1 - a_prev
+            c = _lib.KlCoef()
+            c.sqrt_alpha_prod_t, c.sqrt_beta_prod_t = float(a_t ** 0.5), float(b_t ** 0.5)
+            c.coef_x0 = float((a_prev ** 0.5 * scheduler.betas[t]) / b_t)
+            c.coef_xt = float(scheduler.alphas[t] ** 0.5 * b_prev / b_t)
+            log_post = torch.log(scheduler._get_variance(timestep=t, predicted_variance=None))
+            c.log_post_var = c.log_pred_var = float(log_post)
+            c.bin_width = float(bin_width)
+            c.prediction_type = {"epsilon": _lib.PRED_EPSILON, "sample": _lib.PRED_SAMPLE,
+                                 "v_prediction": _lib.PRED_V}[str(scheduler.prediction_type)]
+            c.clip, c.is_t0 = int(bool(scheduler.clip_sample)), int(t == 0)
+            xt = noisy_image.contiguous().float()
+            mo = model_output.contiguous().float()
+            kl = torch.empty_like(x0) if save_intermediates else None
+            ssum = torch.zeros(N, dtype=torch.float64, device=inputs.device)
+            _lib.check(lib.b200_ddpm_kl(x0.data_ptr(), xt.data_ptr(), mo.data_ptr(), C.byref(c),
+                                        None if kl is None else kl.data_ptr(), ssum.data_ptr(), N, per, ops._stream()),
+                       "b200_ddpm_kl")
+            total_kl += (ssum / per).float()
+            if save_intermediates:
+                intermediates.append(kl.cpu())
+        return (total_kl, intermediates) if save_intermediates else total_kl
+
+    def _approx_standard_normal_cdf(self, x):
+        """inferer.py:279-283 (tanh approximation; the reference's only value-level unit test pins it vs scipy)."""
+        import math
+        return 0.5 * (1.0 + torch.tanh(math.sqrt(2.0 / math.pi) * (x + 0.044715 * torch.pow(x, 3))))
+
+    def _get_decoder_log_likelihood(self, inputs: torch.Tensor, means: torch.Tensor, log_scales: torch.Tensor,
+                                    original_input_range: tuple | None = (0, 255),
+                                    scaled_input_range: tuple | None = (0, 1)) -> torch.Tensor:
+        """inferer.py:285-321, kept as a plain tensor expression for API parity (get_likelihood itself uses the
+        fused kernel)."""
+        assert inputs.shape == means.shape
+        bin_width = (scaled_input_range[1] - scaled_input_range[0]) / (original_input_range[1] - original_input_range[0])
+        centered_x = inputs - means
+        inv_stdv = torch.exp(-log_scales)
+        cdf_plus = self._approx_standard_normal_cdf(inv_stdv * (centered_x + bin_width / 2))
+        cdf_min = self._approx_standard_normal_cdf(inv_stdv * (centered_x - bin_width / 2))
+        log_cdf_plus = torch.log(cdf_plus.clamp(min=1e-12))
+        log_one_minus_cdf_min = torch.log((1.0 - cdf_min).clamp(min=1e-12))
+        cdf_delta = cdf_plus - cdf_min
+        return torch.where(inputs < -0.999, log_cdf_plus,
+                           torch.where(inputs > 0.999, log_one_minus_cdf_min, torch.log(cdf_delta.clamp(min=1e-12))))
 
 
 class _LatentMixin:

@@ -43,7 +43,7 @@ int b200_device_check(void);
 int b200_sm_count(void);
 /* sizeof() of the parameter structs below, for binding-layer ABI checks:
  * 0 igemm_params, 1 gn_stats_params, 2 gn_apply_params, 3 ddim_coef, 4 ddpm_coef, 5 pndm_coef, 6 igemm_seg,
- * 7 flash_params. */
+ * 7 flash_params, 8 kl_coef. */
 int b200_abi_sizeof(int which);
 
 /* ------------------------------------------------------------------------------------------------
@@ -242,6 +242,19 @@ typedef struct {
 /* noise == NULL at t == 0 (no noise is added, ddpm.py:243); pred_var only for learned variance. */
 int b200_ddpm_step(const float* model_out, const float* sample, const float* noise, const float* pred_var,
                    const b200_ddpm_coef* c, float* prev_sample, float* pred_x0, int64_t n, void* stream);
+/* One timestep of DiffusionInferer.get_likelihood (inferer.py:205-265, 279-321), fused: from x_0 (inputs), x_t
+ * (noisy) and the model output compute the predicted and posterior means, then the per-element KL between the two
+ * normals (t > 0) or the discretised-Gaussian decoder negative log-likelihood (t == 0); kl_out (optional) receives
+ * the per-element term, sample_sum[n] += sum over the sample's elements (fp64).  Fixed-variance schedulers. */
+typedef struct {
+  float sqrt_alpha_prod_t, sqrt_beta_prod_t;
+  float coef_x0, coef_xt;              /* shared by the predicted mean (ddpm.py:235-240) and _get_mean (133-156)   */
+  float log_pred_var, log_post_var;    /* log of the (fixed) predicted / posterior variance                        */
+  float bin_width;                     /* (scaled range) / (original range), decoder term only                     */
+  int32_t prediction_type, clip, is_t0;
+} b200_kl_coef;
+int b200_ddpm_kl(const float* x0, const float* xt, const float* model_out, const b200_kl_coef* c, float* kl_out,
+                 double* sample_sum, int32_t N, int64_t per_sample, void* stream);
 /* PNDMScheduler._get_prev_sample after the linear-multistep combine (pndm.py:261-273, 293-315):
  * eps = sum_i w[i] * hist[i] (up to 4 history tensors), prev = sample_coeff*sample - eps_coeff*eps.
  * eps_out (optional) receives the combined model output; prev_sample may be NULL (PRK accumulation,

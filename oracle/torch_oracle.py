@@ -716,3 +716,62 @@ def controlnet_sample(unet_fn, controlnet_fn, scheduler, input_noise, cn_cond, c
         out = unet_fn(image, ts, conditioning, down, mid)
         image, _ = scheduler.step(out, int(t), image)
     return image
+
+
+def approx_standard_normal_cdf(x):
+    """inferer.py:279-283."""
+    return 0.5 * (1.0 + torch.tanh(torch.sqrt(torch.Tensor([2.0 / math.pi])) * (x + 0.044715 * torch.pow(x, 3))))
+
+
+def decoder_log_likelihood(inputs, means, log_scales, original_input_range=(0, 255), scaled_input_range=(0, 1)):
+    """DiffusionInferer._get_decoder_log_likelihood (inferer.py:285-321)."""
+    bin_width = (scaled_input_range[1] - scaled_input_range[0]) / (original_input_range[1] - original_input_range[0])
+    centered_x = inputs - means
+    inv_stdv = torch.exp(-log_scales)
+    cdf_plus = approx_standard_normal_cdf(inv_stdv * (centered_x + bin_width / 2))
+    cdf_min = approx_standard_normal_cdf(inv_stdv * (centered_x - bin_width / 2))
+    log_cdf_plus = torch.log(cdf_plus.clamp(min=1e-12))
+    log_one_minus_cdf_min = torch.log((1.0 - cdf_min).clamp(min=1e-12))
+    cdf_delta = cdf_plus - cdf_min
+    return torch.where(inputs < -0.999, log_cdf_plus,
+                       torch.where(inputs > 0.999, log_one_minus_cdf_min, torch.log(cdf_delta.clamp(min=1e-12))))
+
+
+def get_likelihood(model_fn, scheduler: DDPMOracle, inputs, noise, conditioning=None,
+                   original_input_range=(0, 255), scaled_input_range=(0, 1)):
+    """DiffusionInferer.get_likelihood (inferer.py:145-277), crossattn mode, fixed variance; ``noise`` is passed in
+    (the reference draws torch.randn_like(inputs)) so that both sides of a parity test see the same draw."""
+    total_kl = torch.zeros(inputs.shape[0])
+    acp = scheduler.alphas_cumprod
+    for t in scheduler.timesteps:
+        t = int(t)
+        ts = torch.full(inputs.shape[:1], t).long()
+        sa = (acp[ts] ** 0.5)[(...,) + (None,) * (inputs.dim() - 1)]
+        sb = ((1 - acp[ts]) ** 0.5)[(...,) + (None,) * (inputs.dim() - 1)]
+        noisy = sa * inputs + sb * noise                                  # Scheduler.add_noise (scheduler.py:169-189)
+        out = model_fn(noisy, ts, conditioning)
+        a_t = acp[t]
+        a_prev = acp[t - 1] if t > 0 else scheduler.one
+        b_t, b_prev = 1 - a_t, 1 - a_prev
+        if scheduler.prediction_type == "epsilon":
+            x0 = (noisy - b_t ** 0.5 * out) / a_t ** 0.5
+        elif scheduler.prediction_type == "sample":
+            x0 = out
+        else:
+            x0 = (a_t ** 0.5) * noisy - (b_t ** 0.5) * out
+        if scheduler.clip_sample:
+            x0 = torch.clamp(x0, -1, 1)
+        c0 = (a_prev ** 0.5 * scheduler.betas[t]) / b_t
+        ct = scheduler.alphas[t] ** 0.5 * b_prev / b_t
+        predicted_mean = c0 * x0 + ct * noisy
+        posterior_mean = c0 * inputs + ct * noisy                           # DDPMScheduler._get_mean (ddpm.py:133-156)
+        log_post = torch.log(scheduler._variance(t))
+        log_pred = log_post
+        if t == 0:
+            kl = -decoder_log_likelihood(inputs, predicted_mean, 0.5 * log_pred, original_input_range,
+                                         scaled_input_range)
+        else:
+            kl = 0.5 * (-1.0 + log_pred - log_post + torch.exp(log_post - log_pred)
+                        + ((posterior_mean - predicted_mean) ** 2) * torch.exp(-log_pred))
+        total_kl += kl.view(kl.shape[0], -1).mean(axis=1)
+    return total_kl

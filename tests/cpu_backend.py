@@ -236,6 +236,31 @@ class FakeLib:
             f32(x0o, n).copy_(x0)
         return 0
 
+    def b200_ddpm_kl(self, x0, xt, mo, c, kl_out, ssum, N, per, stream):
+        from oracle import torch_oracle as O
+        c = _obj(c)
+        a, s_, m = (f32(p, N * per).view(N, per) for p in (x0, xt, mo))
+        if c.prediction_type == _lib.PRED_EPSILON:
+            p0 = (s_ - c.sqrt_beta_prod_t * m) / c.sqrt_alpha_prod_t
+        elif c.prediction_type == _lib.PRED_SAMPLE:
+            p0 = m
+        else:
+            p0 = c.sqrt_alpha_prod_t * s_ - c.sqrt_beta_prod_t * m
+        if c.clip:
+            p0 = p0.clamp(-1, 1)
+        pred = c.coef_x0 * p0 + c.coef_xt * s_
+        if c.is_t0:
+            bw = c.bin_width
+            kl = -O.decoder_log_likelihood(a, pred, torch.tensor(0.5 * c.log_pred_var), (0, 1), (0, bw))
+        else:
+            post = c.coef_x0 * a + c.coef_xt * s_
+            kl = 0.5 * (-1.0 + c.log_pred_var - c.log_post_var + math.exp(c.log_post_var - c.log_pred_var)
+                        + (post - pred) ** 2 * math.exp(-c.log_pred_var))
+        if kl_out:
+            f32(kl_out, N * per).view(N, per).copy_(kl)
+        _np(ssum, N, C.c_double)[:] += kl.double().sum(1).numpy()
+        return 0
+
     def b200_pndm_step(self, hist, s, c, prev, eps_out, n, stream):
         c = _obj(c)
         e = torch.zeros(n)

@@ -27,7 +27,7 @@ def test_struct_sizes_match():
     lib = _lib.load()
     import ctypes as C
     for which, struct in enumerate((_lib.IgemmParams, _lib.GnStatsParams, _lib.GnApplyParams, _lib.DdimCoef,
-                                    _lib.DdpmCoef, _lib.PndmCoef, _lib.IgemmSeg, _lib.FlashParams)):
+                                    _lib.DdpmCoef, _lib.PndmCoef, _lib.IgemmSeg, _lib.FlashParams, _lib.KlCoef)):
         assert lib.b200_abi_sizeof(which) == C.sizeof(struct)
 
 

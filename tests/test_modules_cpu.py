@@ -172,3 +172,27 @@ def test_vq_ema_training_composite():
     layer(x)
     assert all(layer.embedding.weight[0] != w0)
     assert all(layer.embedding.weight[1] == w1)
+
+
+def test_get_likelihood_vs_oracle_cpu(monkeypatch):
+    """DiffusionInferer.get_likelihood (fused KL kernel per step) against the oracle's restatement, same noise draw."""
+    from generativemodels_b200.inferers import DiffusionInferer
+    from generativemodels_b200.networks.schedulers import DDIMScheduler, DDPMScheduler
+    fx = load("g_unet2d")
+    m = nets().DiffusionModelUNet(**fx["kwargs"]).eval()
+    m.load_state_dict(fx["state_dict"])
+    sd, cfg = fx["state_dict"], G.unet_oracle_cfg(fx["kwargs"])
+    s, so = DDPMScheduler(num_train_timesteps=10), O.DDPMOracle(num_train_timesteps=10)
+    s.set_timesteps(10)
+    so.set_timesteps(10)
+    torch.manual_seed(21)
+    x = torch.rand(2, 1, 8, 8) * 2 - 1
+    noise = torch.randn(2, 1, 8, 8)
+    monkeypatch.setattr(torch, "randn_like", lambda t: noise.clone())
+    got, inter = DiffusionInferer(s).get_likelihood(x, m, s, save_intermediates=True, verbose=False)
+    want = O.get_likelihood(lambda xx, tt, c: O.unet_forward(sd, cfg, xx, tt, context=c), so, x, noise)
+    assert got.shape == (2,) and len(inter) == 10 and inter[0].shape == x.shape
+    assert torch.allclose(got, want, rtol=5e-2, atol=1e-3), (got, want)
+    with pytest.raises(NotImplementedError):
+        d = DDIMScheduler(num_train_timesteps=10)
+        DiffusionInferer(d).get_likelihood(x, m, d, verbose=False)

@@ -164,3 +164,27 @@ def test_inferer_sample(ref):
         want = DiffusionInferer(R).sample(input_noise=noise, diffusion_model=m, scheduler=R, verbose=False)
         got = O.diffusion_sample(lambda x, t, c: O.unet_forward(sd, cfg, x, t, context=c), M, noise)
     _close(got, want, 1e-4)
+
+
+@pytest.mark.parametrize("ptype,clip", [("epsilon", True), ("v_prediction", False), ("sample", True)])
+def test_get_likelihood(ref, monkeypatch, ptype, clip):
+    """Oracle get_likelihood vs the reference's DiffusionInferer.get_likelihood (inferer.py:145-277), same noise."""
+    nets, sch = ref
+    from generative.inferers import DiffusionInferer
+    kw = G.UNET_CASES["unet2d_attn"]
+    torch.manual_seed(0)
+    m = G.randomize_zero_params(nets.DiffusionModelUNet(**kw)).eval()
+    skw = dict(num_train_timesteps=12, prediction_type=ptype, clip_sample=clip)
+    R, M = sch.DDPMScheduler(**skw), O.DDPMOracle(**skw)
+    R.set_timesteps(12)
+    M.set_timesteps(12)
+    torch.manual_seed(5)
+    x = torch.rand(2, 1, 16, 16) * 2 - 1
+    x[0, 0, 0, :4] = torch.tensor([-1.0, 1.0, -0.9995, 0.9995])          # both edge bins of the discretised decoder
+    noise = torch.randn(2, 1, 16, 16)
+    monkeypatch.setattr(torch, "randn_like", lambda t: noise.clone())
+    cfg, sd = G.unet_oracle_cfg(kw), m.state_dict()
+    with torch.no_grad():
+        want = DiffusionInferer(R).get_likelihood(inputs=x, diffusion_model=m, scheduler=R, verbose=False)
+        got = O.get_likelihood(lambda xx, t, c: O.unet_forward(sd, cfg, xx, t, context=c), M, x, noise)
+    _close(got, want, 1e-4)

@@ -359,6 +359,71 @@ def test_inferers_vs_oracle(cuda_device):
     check(got, want, TRAJ_TOL, "ControlNetDiffusionInferer")
 
 
+@pytest.mark.parametrize("ptype,clip", [("epsilon", True), ("v_prediction", False)])
+def test_get_likelihood_vs_oracle(cuda_device, monkeypatch, ptype, clip):
+    """DiffusionInferer.get_likelihood (inferer.py:145-277): network forward + fused b200_ddpm_kl per timestep."""
+    from generativemodels_b200.inferers import DiffusionInferer
+    from generativemodels_b200.networks.schedulers import DDPMScheduler
+    kw = G.UNET_CASES["unet2d_attn"]
+    torch.manual_seed(0)
+    m = G.randomize_zero_params(nets().DiffusionModelUNet(**kw)).eval()
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    cfg = G.unet_oracle_cfg(kw)
+    skw = dict(num_train_timesteps=12, prediction_type=ptype, clip_sample=clip)
+    so, sp = O.DDPMOracle(**skw), DDPMScheduler(**skw)
+    so.set_timesteps(12)
+    sp.set_timesteps(12)
+    torch.manual_seed(5)
+    x = torch.rand(2, 1, 16, 16) * 2 - 1
+    x[0, 0, 0, :4] = torch.tensor([-1.0, 1.0, -0.9995, 0.9995])
+    noise = torch.randn(2, 1, 16, 16)
+    monkeypatch.setattr(torch, "randn_like", lambda t: noise.clone().to(t.device))
+    want = O.get_likelihood(lambda xx, t, c: O.unet_forward(sd, cfg, xx, t, context=c), so, x, noise)
+    got, inter = DiffusionInferer(sp).get_likelihood(x.cuda(), m.cuda(), sp, save_intermediates=True, verbose=False)
+    assert len(inter) == 12 and inter[0].shape == x.shape
+    # bf16 network output inside a KL whose late-timestep terms scale the mean error by 1/variance
+    assert torch.allclose(got.cpu(), want, rtol=5e-2, atol=2e-3), (got, want)
+
+
+def test_ddpm_kl_kernel_exact(cuda_device):
+    """b200_ddpm_kl alone (fp32 in, fp32 out) against the oracle's closed forms, all three prediction types, t>0 / t=0."""
+    import ctypes as C
+    from generativemodels_b200 import _lib
+    lib = _lib.require_device()
+    torch.manual_seed(1)
+    N, per = 3, 1000
+    x0 = (torch.rand(N, per) * 2 - 1)
+    x0[0, :4] = torch.tensor([-1.0, 1.0, -0.9995, 0.9995])
+    xt, mo = torch.randn(N, per), torch.randn(N, per)
+    for pt, name in ((_lib.PRED_EPSILON, "eps"), (_lib.PRED_SAMPLE, "sample"), (_lib.PRED_V, "v")):
+        for t0 in (0, 1):
+            c = _lib.KlCoef()
+            c.sqrt_alpha_prod_t, c.sqrt_beta_prod_t, c.coef_x0, c.coef_xt = 0.9, 0.43589, 0.3, 0.68
+            c.log_pred_var = c.log_post_var = -3.2
+            c.bin_width, c.prediction_type, c.clip, c.is_t0 = 1.0 / 255, pt, 1, t0
+            if pt == _lib.PRED_EPSILON:
+                p0 = (xt - c.sqrt_beta_prod_t * mo) / c.sqrt_alpha_prod_t
+            elif pt == _lib.PRED_SAMPLE:
+                p0 = mo
+            else:
+                p0 = c.sqrt_alpha_prod_t * xt - c.sqrt_beta_prod_t * mo
+            p0 = p0.clamp(-1, 1)
+            pred, post = c.coef_x0 * p0 + c.coef_xt * xt, c.coef_x0 * x0 + c.coef_xt * xt
+            if t0:
+                want = -O.decoder_log_likelihood(x0, pred, torch.tensor(0.5 * c.log_pred_var))
+            else:
+                want = 0.5 * (-1.0 + 1.0 + (post - pred) ** 2 * torch.exp(torch.tensor(-c.log_pred_var)))
+            kl = torch.empty(N, per, device="cuda")
+            ss = torch.zeros(N, dtype=torch.float64, device="cuda")
+            gx0, gxt, gmo = x0.cuda(), xt.cuda(), mo.cuda()
+            _lib.check(lib.b200_ddpm_kl(gx0.data_ptr(), gxt.data_ptr(), gmo.data_ptr(), C.byref(c),
+                                        kl.data_ptr(), ss.data_ptr(), N, per, None), "b200_ddpm_kl")
+            torch.cuda.synchronize()
+            err = (kl.cpu() - want).abs() / (1 + want.abs())
+            assert err.max().item() < 2e-4, (name, t0, err.max().item())
+            assert torch.allclose(ss.cpu(), want.double().sum(1), rtol=1e-4), (name, t0)
+
+
 def test_no_cpu_path(cuda_device):
     m = nets().DiffusionModelUNet(2, 1, 1, num_res_blocks=1, num_channels=(8, 8), attention_levels=(False, False),
                                   norm_num_groups=4).cuda()
