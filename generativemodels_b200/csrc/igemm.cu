@@ -57,7 +57,7 @@ struct IgemmDev {
   int tiles_w, tiles_h, tiles_d, tiles_n, num_tiles;
   // epilogue
   void* out_ptr;
-  int out_dtype, cout, out_cols, out_vec, out_staged;
+  int out_dtype, cout, out_cols, out_vec, out_staged, out_v256;
   float* stat_ptr;          // optional [rows][tiles_n][2] (max, sum exp) per row and column tile
   long long out_sN, out_sD, out_sH, out_sW;
   const float* bias;
@@ -67,7 +67,7 @@ struct IgemmDev {
   int act1, act2;
   float scale;
   const void* res_ptr;
-  int res_dtype, res_vec;
+  int res_dtype, res_vec, res_v256;
   long long res_sN, res_sD, res_sH, res_sW;
   SegDev seg[B200_IGEMM_MAX_SEG];
 };
@@ -290,6 +290,91 @@ __device__ __forceinline__ void store_direct(const IgemmDev& p, const float* v, 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Fast epilogue (full CH-column chunks of vector-aligned outputs): the general path above re-derives bias / row-vector
+// addresses, activation switches and bounds per ELEMENT (~55 instructions per output value — with one epilogue warp
+// per scheduler that made the epilogue, not the tensor pipe, the critical path of every K <= 7k convolution).  Here
+// the additive vector comes from shared memory (filled once per (sample, column tile)), the activation switches are
+// hoisted out of the element loops and the residual / output move as 256-bit (or 128-bit) vectors.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldg256(const void* ptr, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(ptr));
+}
+__device__ __forceinline__ void stg256(void* ptr, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(a.x), "r"(a.y), "r"(a.z),
+               "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+template <int CH>
+__device__ __forceinline__ void act_inplace(float* v, int act) {
+  if (act == B200_ACT_NONE) return;
+  if (act == B200_ACT_SILU) {
+#pragma unroll
+    for (int j = 0; j < CH; ++j) v[j] = silu_f(v[j]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.0f);
+  }
+}
+// residual prefetch for one row chunk (bf16, 16-byte aligned): CH/8 uint4
+template <int CH>
+__device__ __forceinline__ void load_res_fast(const IgemmDev& p, uint4* rv, long long res_off, int col0) {
+  const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(p.res_ptr) + res_off + col0;
+  if (p.res_v256) {
+#pragma unroll
+    for (int g = 0; g < CH / 16; ++g) ldg256(r + g * 16, rv[2 * g], rv[2 * g + 1]);
+  } else {
+#pragma unroll
+    for (int g = 0; g < CH / 8; ++g) rv[g] = __ldg(reinterpret_cast<const uint4*>(r + g * 8));
+  }
+}
+template <int CH>
+__device__ __forceinline__ void epilogue_fast(const IgemmDev& p, const uint32_t* raw, const float* addv,
+                                              const uint4* rv, long long out_off, int col0) {
+  float v[CH];
+#pragma unroll
+  for (int j = 0; j < CH; j += 4) {
+    const float4 a = *reinterpret_cast<const float4*>(addv + j);
+    v[j] = __uint_as_float(raw[j]) + a.x;
+    v[j + 1] = __uint_as_float(raw[j + 1]) + a.y;
+    v[j + 2] = __uint_as_float(raw[j + 2]) + a.z;
+    v[j + 3] = __uint_as_float(raw[j + 3]) + a.w;
+  }
+  act_inplace<CH>(v, p.act1);
+  if (p.scale != 1.0f) {
+#pragma unroll
+    for (int j = 0; j < CH; ++j) v[j] *= p.scale;
+  }
+  if (p.res_ptr) {
+#pragma unroll
+    for (int g = 0; g < CH / 8; ++g) {
+      float f[8];
+      unpack8(rv[g], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[g * 8 + j] += f[j];
+    }
+  }
+  act_inplace<CH>(v, p.act2);
+  if (p.out_dtype == B200_DT_BF16) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out_ptr) + out_off + col0;
+    if (p.out_v256) {
+#pragma unroll
+      for (int g = 0; g < CH / 16; ++g) stg256(o + g * 16, pack8(v + g * 16), pack8(v + g * 16 + 8));
+    } else {
+#pragma unroll
+      for (int g = 0; g < CH / 8; ++g) *reinterpret_cast<uint4*>(o + g * 8) = pack8(v + g * 8);
+    }
+  } else {
+    float* o = reinterpret_cast<float*>(p.out_ptr) + out_off + col0;
+#pragma unroll
+    for (int g = 0; g < CH / 4; ++g)
+      *reinterpret_cast<float4*>(o + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+  }
+}
+
 template <int CH>
 __device__ __forceinline__ void epilogue_row(const IgemmDev& p, float* v, int nb, int ow, long long out_off,
                                              long long res_off, int col0) {
@@ -345,6 +430,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
   auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
   float* stage_tiles = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));   // 4 x [32][CH+1]
+  float* add_tiles = stage_tiles + 4 * 32 * 33;                                                      // 4 x [BN]
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -446,6 +532,10 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
     const int rw = r & (p.BW - 1);
     const int rh = (r >> p.bw_log2) & (p.BH - 1);
     const int rd = r >> (p.bw_log2 + p.bh_log2);
+    float* addv = add_tiles + (warp - 2) * BN;
+    int add_key = -1;
+    const bool fast_ok = p.out_vec && !p.out_staged && !p.stat_ptr && !p.row_bias &&
+                         (!p.res_ptr || (p.res_vec && p.res_dtype == B200_DT_BF16));
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       int t = tile;
@@ -460,6 +550,22 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
       const long long res_off = nb * p.res_sN + od * p.res_sD + oh * p.res_sH + ow * p.res_sW;
       const int n0 = nt * BN;
 
+      if (fast_ok && add_key != nb * p.tiles_n + nt) {
+        // bias + per-sample row vector of this (sample, column tile): shared by all rows, refreshed only on change
+        add_key = nb * p.tiles_n + nt;
+        __syncwarp();
+        for (int c = lane; c < BN; c += 32) {
+          const int col = n0 + c;
+          float a = 0.f;
+          if (col < p.cout) {
+            if (p.bias) a += __ldg(p.bias + col);
+            if (p.rowvec) a += __ldg(p.rowvec + (long long)nb * p.rowvec_bstride + col);
+          }
+          addv[c] = a;
+        }
+        __syncwarp();
+      }
+
       const int buf = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(tfull_bar(buf), acc_phase);
@@ -470,6 +576,16 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += CH) {
         if (n0 + c0 >= p.out_cols) break;             // warp-uniform
+        if (fast_ok && n0 + c0 + CH <= p.cout) {      // warp-uniform: a full chunk of real columns
+          uint4 rv[CH / 8];
+          if (p.res_ptr && row_ok) load_res_fast<CH>(p, rv, res_off, n0 + c0);   // in flight during the TMEM read
+          uint32_t raw[CH];
+          if constexpr (CH == 32) tmem_ld32(taddr + c0, raw);
+          else tmem_ld16(taddr + c0, raw);
+          tmem_ld_wait();
+          if (row_ok) epilogue_fast<CH>(p, raw, addv + c0, rv, out_off, n0 + c0);
+          continue;
+        }
         uint32_t raw[CH];
         if constexpr (CH == 32) tmem_ld32(taddr + c0, raw);
         else tmem_ld16(taddr + c0, raw);
@@ -611,7 +727,7 @@ static TileShape choose_tile(int OW, int OH, int OD, int sw, int sh, int sd) {
 template <int BN, int STAGES>
 static int launch_tc(const IgemmDev& d, cudaStream_t stream) {
   constexpr int kStageBytes = kABytes + BN * kBK * 2;
-  constexpr int smem = STAGES * kStageBytes + 1024 + 256 + 4 * 32 * 33 * 4;
+  constexpr int smem = STAGES * kStageBytes + 1024 + 256 + 4 * 32 * 33 * 4 + 4 * BN * 4;
   static bool attr_done = false;
   if (!attr_done) {
     B200_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -696,6 +812,9 @@ extern "C" int b200_igemm(const b200_igemm_params* p, void* stream_v) {
     d.out_vec = (p->out_cols % g == 0) && (p->out_sN % g == 0) && (p->out_sD % g == 0) &&
                 (p->out_sH % g == 0) && (p->out_sW % g == 0) && (((uintptr_t)p->out_ptr) % 16 == 0);
     (void)esz;
+    d.out_v256 = d.out_vec && p->out_dtype == B200_DT_BF16 && (p->out_cols % 16 == 0) && (p->out_sN % 16 == 0) &&
+                 (p->out_sD % 16 == 0) && (p->out_sH % 16 == 0) && (p->out_sW % 16 == 0) &&
+                 (((uintptr_t)p->out_ptr) % 32 == 0);
   }
   {
     // rows far apart in memory (wide row-major GEMM outputs): stage the tile through smem for coalesced row stores
@@ -709,6 +828,9 @@ extern "C" int b200_igemm(const b200_igemm_params* p, void* stream_v) {
     const int g = (p->res_dtype == B200_DT_BF16) ? 8 : 4;
     d.res_vec = (p->out_cols % g == 0) && (p->res_sN % g == 0) && (p->res_sD % g == 0) &&
                 (p->res_sH % g == 0) && (p->res_sW % g == 0) && (((uintptr_t)p->res_ptr) % 16 == 0);
+    d.res_v256 = d.res_vec && p->res_dtype == B200_DT_BF16 && (p->out_cols % 16 == 0) && (p->res_sN % 16 == 0) &&
+                 (p->res_sD % 16 == 0) && (p->res_sH % 16 == 0) && (p->res_sW % 16 == 0) &&
+                 (((uintptr_t)p->res_ptr) % 32 == 0);
   }
 
   const int impl = p->impl ? p->impl : env_impl();

@@ -111,6 +111,16 @@ class DiffusionInferer(Inferer):
         per-step tail — predicted x0, clip, both means, KL / discretised-Gaussian term, per-sample mean — is one
         fused kernel (b200_ddpm_kl).  Fixed-variance DDPM schedulers (the reference's learned-variance branch
         evaluates ``if predicted_variance`` on a tensor and cannot run)."""
+        def predict(noisy_image, timesteps):
+            if mode == "concat":
+                return diffusion_model(torch.cat([noisy_image, conditioning], dim=1), timesteps=timesteps, context=None)
+            return diffusion_model(x=noisy_image, timesteps=timesteps, context=conditioning)
+
+        return self._likelihood_loop(inputs, predict, scheduler, save_intermediates, mode, original_input_range,
+                                     scaled_input_range, verbose)
+
+    def _likelihood_loop(self, inputs, predict, scheduler, save_intermediates, mode, original_input_range,
+                         scaled_input_range, verbose):
         import ctypes as C
 
         from .. import _lib
@@ -135,11 +145,7 @@ class DiffusionInferer(Inferer):
             t = int(t)
             timesteps = torch.full(inputs.shape[:1], t, device=inputs.device).long()
             noisy_image = self.scheduler.add_noise(original_samples=inputs, noise=noise, timesteps=timesteps)
-            if mode == "concat":
-                model_output = diffusion_model(torch.cat([noisy_image, conditioning], dim=1), timesteps=timesteps,
-                                               context=None)
-            else:
-                model_output = diffusion_model(x=noisy_image, timesteps=timesteps, context=conditioning)
+            model_output = predict(noisy_image, timesteps)
             a_t = scheduler.alphas_cumprod[t]
             a_prev = scheduler.alphas_cumprod[t - 1] if t > 0 else scheduler.one
             b_t, b_prev = 1 - a_t, 1 - a_prev
@@ -207,6 +213,20 @@ class _LatentMixin:
             latent = torch.stack([_spatial_pad(i, self.ldm_latent_shape) for i in latent], 0)
         return latent
 
+    @staticmethod
+    def _check_resample(resample_latent_likelihoods, resample_interpolation_mode):
+        if resample_latent_likelihoods and resample_interpolation_mode not in ("nearest", "bilinear", "trilinear"):
+            raise ValueError(f"resample_interpolation mode should be either nearest, bilinear, or trilinear,"
+                             f" got {resample_interpolation_mode}")
+
+    @staticmethod
+    def _resample_maps(outputs, size, save_intermediates, resample_latent_likelihoods, resample_interpolation_mode):
+        """KL maps upsampled to the image grid (inferer.py:557-562); a host-side post-processing of saved maps."""
+        if save_intermediates and resample_latent_likelihoods:
+            resizer = nn.Upsample(size=tuple(size), mode=resample_interpolation_mode)
+            outputs = (outputs[0], [resizer(x) for x in outputs[1]])
+        return outputs
+
     def _decode_latent(self, latent, autoencoder_model):
         if self.autoencoder_latent_shape is not None:
             latent = torch.stack([_center_crop(i, self.autoencoder_latent_shape) for i in latent], 0)
@@ -241,6 +261,24 @@ class LatentDiffusionInferer(DiffusionInferer, _LatentMixin):
         if save_intermediates:
             return image, [self._decode_latent(l, autoencoder_model) for l in latent_intermediates]
         return image
+
+
+    @torch.no_grad()
+    def get_likelihood(self, inputs: torch.Tensor, autoencoder_model, diffusion_model,
+                       scheduler: Callable[..., torch.Tensor] | None = None, save_intermediates: bool | None = False,
+                       conditioning: torch.Tensor | None = None, mode: str = "crossattn",
+                       original_input_range: tuple | None = (0, 255), scaled_input_range: tuple | None = (0, 1),
+                       verbose: bool = True, resample_latent_likelihoods: bool = False,
+                       resample_interpolation_mode: str = "nearest", seg: torch.Tensor | None = None,
+                       quantized: bool = True):
+        """Likelihood of the latent representation (inferer.py:489-562)."""
+        self._check_resample(resample_latent_likelihoods, resample_interpolation_mode)
+        latents = self._encode_latent(inputs, autoencoder_model, quantized)
+        outputs = super().get_likelihood(inputs=latents, diffusion_model=diffusion_model, scheduler=scheduler,
+                                         save_intermediates=save_intermediates, conditioning=conditioning, mode=mode,
+                                         verbose=verbose)
+        return self._resample_maps(outputs, inputs.shape[2:], save_intermediates, resample_latent_likelihoods,
+                                   resample_interpolation_mode)
 
 
 class ControlNetDiffusionInferer(DiffusionInferer):
@@ -287,6 +325,28 @@ class ControlNetDiffusionInferer(DiffusionInferer):
         return (image, intermediates) if save_intermediates else image
 
 
+    @torch.no_grad()
+    def get_likelihood(self, inputs: torch.Tensor, diffusion_model, controlnet, cn_cond: torch.Tensor,
+                       scheduler: Callable[..., torch.Tensor] | None = None, save_intermediates: bool | None = False,
+                       conditioning: torch.Tensor | None = None, mode: str = "crossattn",
+                       original_input_range: tuple | None = (0, 255), scaled_input_range: tuple | None = (0, 1),
+                       verbose: bool = True, seg: torch.Tensor | None = None):
+        """inferer.py:710-853: as DiffusionInferer.get_likelihood with the ControlNet residuals fed to the UNet.  (The
+        reference's concat branch overwrites ``conditioning`` inside the loop and fails on its second step; here the
+        concatenation is per step, as in ``sample``.)"""
+        def predict(noisy_image, timesteps):
+            if mode == "concat":
+                model_input, context_ = torch.cat([noisy_image, conditioning], dim=1), None
+            else:
+                model_input, context_ = noisy_image, conditioning
+            down, mid = _run_controlnet(controlnet, model_input, timesteps, cn_cond, context_)
+            return diffusion_model(model_input, timesteps=timesteps, context=context_,
+                                   down_block_additional_residuals=down, mid_block_additional_residual=mid)
+
+        return self._likelihood_loop(inputs, predict, scheduler, save_intermediates, mode, original_input_range,
+                                     scaled_input_range, verbose)
+
+
 def _run_controlnet(controlnet, x, timesteps, cn_cond, context):
     if isinstance(controlnet, ControlNet):      # keep the residuals channels-last between the two networks
         return controlnet(x=x, timesteps=timesteps, controlnet_cond=cn_cond, context=context, _internal=True)
@@ -331,3 +391,21 @@ class ControlNetLatentDiffusionInferer(ControlNetDiffusionInferer, _LatentMixin)
         if save_intermediates:
             return image, [self._decode_latent(l, autoencoder_model) for l in latent_intermediates]
         return image
+
+    @torch.no_grad()
+    def get_likelihood(self, inputs: torch.Tensor, autoencoder_model, diffusion_model, controlnet,
+                       cn_cond: torch.Tensor, scheduler: Callable[..., torch.Tensor] | None = None,
+                       save_intermediates: bool | None = False, conditioning: torch.Tensor | None = None,
+                       mode: str = "crossattn", original_input_range: tuple | None = (0, 255),
+                       scaled_input_range: tuple | None = (0, 1), verbose: bool = True,
+                       resample_latent_likelihoods: bool = False, resample_interpolation_mode: str = "nearest",
+                       seg: torch.Tensor | None = None, quantized: bool = True):
+        """inferer.py:1041-1124."""
+        self._check_resample(resample_latent_likelihoods, resample_interpolation_mode)
+        latents = self._encode_latent(inputs, autoencoder_model, quantized)
+        cn_cond = self._match_cond(cn_cond, latents.shape[2:])
+        outputs = super().get_likelihood(inputs=latents, diffusion_model=diffusion_model, controlnet=controlnet,
+                                         cn_cond=cn_cond, scheduler=scheduler, save_intermediates=save_intermediates,
+                                         conditioning=conditioning, mode=mode, verbose=verbose)
+        return self._resample_maps(outputs, inputs.shape[2:], save_intermediates, resample_latent_likelihoods,
+                                   resample_interpolation_mode)

@@ -196,3 +196,36 @@ def test_get_likelihood_vs_oracle_cpu(monkeypatch):
     with pytest.raises(NotImplementedError):
         d = DDIMScheduler(num_train_timesteps=10)
         DiffusionInferer(d).get_likelihood(x, m, d, verbose=False)
+
+
+def test_likelihood_variants_host_logic_cpu():
+    """Latent / ControlNet / ControlNet-latent get_likelihood plumbing (inferer.py:489-562, 710-853, 1041-1124):
+    encode -> scale -> shared KL loop -> optional resampling of the KL maps, through the CPU stand-in."""
+    from generativemodels_b200.inferers import (ControlNetDiffusionInferer, ControlNetLatentDiffusionInferer,
+                                                LatentDiffusionInferer)
+    from generativemodels_b200.networks.schedulers import DDPMScheduler
+    ae = nets().AutoencoderKL(spatial_dims=2, in_channels=1, out_channels=1, num_channels=(4, 4), latent_channels=3,
+                              attention_levels=[False, False], num_res_blocks=1, with_encoder_nonlocal_attn=False,
+                              with_decoder_nonlocal_attn=False, norm_num_groups=4).eval()
+    base = dict(spatial_dims=2, in_channels=3, num_channels=[4, 4], norm_num_groups=4, attention_levels=[False, False],
+                num_res_blocks=1, num_head_channels=4)
+    un = G.randomize_zero_params(nets().DiffusionModelUNet(out_channels=3, **base)).eval()
+    cn = G.randomize_zero_params(nets().ControlNet(conditioning_embedding_num_channels=[16],
+                                                   conditioning_embedding_in_channels=1, **base)).eval()
+    s = DDPMScheduler(num_train_timesteps=4)
+    s.set_timesteps(4)
+    img, mask = torch.randn(1, 1, 8, 8), torch.randn(1, 1, 8, 8)
+    lik, inter = LatentDiffusionInferer(s, 1.0).get_likelihood(img, ae, un, s, save_intermediates=True, verbose=False)
+    assert lik.shape == (1,) and len(inter) == 4 and inter[0].shape == (1, 3, 4, 4)
+    lik, inter = LatentDiffusionInferer(s, 1.0).get_likelihood(img, ae, un, s, save_intermediates=True, verbose=False,
+                                                               resample_latent_likelihoods=True)
+    assert inter[0].shape == (1, 3, 8, 8)
+    with pytest.raises(ValueError):
+        LatentDiffusionInferer(s, 1.0).get_likelihood(img, ae, un, s, resample_latent_likelihoods=True,
+                                                      resample_interpolation_mode="cubic", verbose=False)
+    lik, inter = ControlNetLatentDiffusionInferer(s, 1.0).get_likelihood(
+        img, ae, un, cn, mask, s, save_intermediates=True, resample_latent_likelihoods=True, verbose=False)
+    assert torch.isfinite(lik).all() and inter[0].shape == (1, 3, 8, 8)
+    lat = torch.randn(1, 3, 4, 4)
+    lik = ControlNetDiffusionInferer(s).get_likelihood(lat, un, cn, torch.randn(1, 1, 4, 4), s, verbose=False)
+    assert lik.shape == (1,) and torch.isfinite(lik).all()

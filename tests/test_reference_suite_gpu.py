@@ -218,6 +218,16 @@ def test_inferer_cases(cuda_device, sd_):
     pred = DiffusionInferer(s)(inputs=torch.randn(shape).cuda(), diffusion_model=m, noise=noise,
                                timesteps=torch.randint(0, 1000, (2,)).cuda())
     assert pred.shape == shape
+    # test_get_likelihood (138-151) and test_normal_cdf (153-162)
+    s = DDPMScheduler(num_train_timesteps=10)
+    s.set_timesteps(10)
+    lik, inter = DiffusionInferer(s).get_likelihood(inputs=torch.randn(shape).cuda(), diffusion_model=m, scheduler=s,
+                                                    save_intermediates=True, verbose=False)
+    assert inter[0].shape == shape and lik.shape[0] == shape[0] and torch.isfinite(lik).all() and len(inter) == 10
+    from scipy.stats import norm
+    x = torch.linspace(-10, 10, 20)
+    torch.testing.assert_close(DiffusionInferer(s)._approx_standard_normal_cdf(x).double(),
+                               torch.from_numpy(norm.cdf(x.numpy())), atol=1e-3, rtol=1e-5)
 
 
 def test_latent_inferer_cases(cuda_device):
@@ -250,3 +260,103 @@ def test_latent_inferer_cases(cuda_device):
     inf2 = LatentDiffusionInferer(s, scale_factor=1.0, ldm_latent_shape=[8, 8], autoencoder_latent_shape=[4, 4])
     sample = inf2.sample(torch.randn(1, 3, 8, 8).cuda(), ae, un, s, verbose=False)
     assert sample.shape == (1, 1, 8, 8)
+    # test_get_likelihoods (438-489) / test_resample_likelihoods (492-545), both stage-1 families
+    img = torch.randn(1, 1, 8, 8).cuda()
+    for stage1, lat_shape in ((ae, (1, 3, 4, 4)), (vq, (1, 3, 2, 2))):
+        for quantized in (True, False):
+            lik, inter = inf.get_likelihood(inputs=img, autoencoder_model=stage1, diffusion_model=un, scheduler=s,
+                                            save_intermediates=True, quantized=quantized, verbose=False)
+            assert len(inter) == 10 and inter[0].shape == lat_shape and torch.isfinite(lik).all()
+        lik, inter = inf.get_likelihood(inputs=img, autoencoder_model=stage1, diffusion_model=un, scheduler=s,
+                                        save_intermediates=True, resample_latent_likelihoods=True, verbose=False)
+        assert len(inter) == 10 and inter[0].shape[2:] == img.shape[2:]
+    with pytest.raises(ValueError):
+        inf.get_likelihood(inputs=img, autoencoder_model=ae, diffusion_model=un, scheduler=s, verbose=False,
+                           resample_latent_likelihoods=True, resample_interpolation_mode="cubic")
+
+
+@pytest.mark.parametrize("sd_", [2, 3])
+def test_controlnet_inferer_cases(cuda_device, sd_):
+    """tests/test_controlnet_inferers.py:30-80 (CNDM_TEST_CASES) — call, DDPM/DDIM sample with intermediates,
+    crossattn / concat conditioning, get_likelihood (568-590)."""
+    from generativemodels_b200.inferers import ControlNetDiffusionInferer
+    from generativemodels_b200.networks.schedulers import DDIMScheduler, DDPMScheduler
+    base = dict(spatial_dims=sd_, in_channels=1, num_channels=[8], norm_num_groups=8, attention_levels=[True],
+                num_res_blocks=1, num_head_channels=8)
+    cnkw = dict(conditioning_embedding_num_channels=[16], conditioning_embedding_in_channels=1)
+    shape = (2, 1, 8, 8) if sd_ == 2 else (2, 1, 8, 8, 8)
+    m = G.randomize_zero_params(nets().DiffusionModelUNet(out_channels=1, **base)).cuda().eval()
+    cn = G.randomize_zero_params(nets().ControlNet(**base, **cnkw)).cuda().eval()
+    x, mask, noise = (torch.randn(shape).cuda() for _ in range(3))
+    s = DDPMScheduler(num_train_timesteps=10)
+    s.set_timesteps(10)
+    inf = ControlNetDiffusionInferer(s)
+    pred = inf(inputs=x, diffusion_model=m, controlnet=cn, noise=noise, timesteps=torch.randint(0, 10, (2,)).cuda(),
+               cn_cond=mask)
+    assert pred.shape == shape
+    sample, inter = inf.sample(input_noise=noise, diffusion_model=m, controlnet=cn, cn_cond=mask, scheduler=s,
+                               save_intermediates=True, intermediate_steps=1, verbose=False)
+    assert sample.shape == shape and len(inter) == 10 and torch.isfinite(sample).all()
+    d = DDIMScheduler(num_train_timesteps=1000)
+    d.set_timesteps(10)
+    sample, inter = inf.sample(input_noise=noise, diffusion_model=m, controlnet=cn, cn_cond=mask, scheduler=d,
+                               save_intermediates=True, intermediate_steps=100, verbose=False)
+    assert sample.shape == shape and len(inter) == 10
+    lik, inter = inf.get_likelihood(inputs=x, diffusion_model=m, controlnet=cn, cn_cond=mask, scheduler=s,
+                                    save_intermediates=True, verbose=False)
+    assert inter[0].shape == shape and lik.shape[0] == shape[0] and torch.isfinite(lik).all()
+    # crossattn and concat conditioning (539-566, 603-640)
+    ckw = dict(base, with_conditioning=True, cross_attention_dim=3)
+    mc = G.randomize_zero_params(nets().DiffusionModelUNet(out_channels=1, **ckw)).cuda().eval()
+    cc = G.randomize_zero_params(nets().ControlNet(**ckw, **cnkw)).cuda().eval()
+    out = inf.sample(input_noise=noise, diffusion_model=mc, controlnet=cc, cn_cond=mask, scheduler=d,
+                     conditioning=torch.randn(2, 1, 3).cuda(), verbose=False)
+    assert out.shape == shape
+    kkw = dict(base, in_channels=2)
+    mk = G.randomize_zero_params(nets().DiffusionModelUNet(out_channels=1, **kkw)).cuda().eval()
+    ck = G.randomize_zero_params(nets().ControlNet(**kkw, **cnkw)).cuda().eval()
+    out = inf.sample(input_noise=noise, diffusion_model=mk, controlnet=ck, cn_cond=mask, scheduler=d,
+                     conditioning=torch.randn(shape).cuda(), mode="concat", verbose=False)
+    assert out.shape == shape
+    lik = inf.get_likelihood(inputs=x, diffusion_model=mk, controlnet=ck, cn_cond=mask, scheduler=s,
+                             conditioning=torch.randn(shape).cuda(), mode="concat", verbose=False)
+    assert lik.shape == (2,) and torch.isfinite(lik).all()
+
+
+def test_controlnet_latent_inferer_cases(cuda_device):
+    """tests/test_controlnet_inferers.py:643-970 (LATENT_CNDM_TEST_CASES): prediction, sample, likelihood and
+    resampled likelihood maps with an AutoencoderKL / VQVAE first stage; the ControlNet mask is given at image
+    resolution and resized to the latent grid."""
+    from generativemodels_b200.inferers import ControlNetLatentDiffusionInferer
+    from generativemodels_b200.networks.schedulers import DDPMScheduler
+    ae = nets().AutoencoderKL(spatial_dims=2, in_channels=1, out_channels=1, num_channels=(4, 4), latent_channels=3,
+                              attention_levels=[False, False], num_res_blocks=1, with_encoder_nonlocal_attn=False,
+                              with_decoder_nonlocal_attn=False, norm_num_groups=4).cuda().eval()
+    vq = nets().VQVAE(spatial_dims=2, in_channels=1, out_channels=1, num_channels=[4, 4], num_res_layers=1,
+                      num_res_channels=[4, 4], downsample_parameters=((2, 4, 1, 1),) * 2,
+                      upsample_parameters=((2, 4, 1, 1, 0),) * 2, num_embeddings=16, embedding_dim=3).cuda().eval()
+    base = dict(spatial_dims=2, in_channels=3, num_channels=[4, 4], norm_num_groups=4, attention_levels=[False, False],
+                num_res_blocks=1, num_head_channels=4)
+    un = G.randomize_zero_params(nets().DiffusionModelUNet(out_channels=3, **base)).cuda().eval()
+    cn = G.randomize_zero_params(nets().ControlNet(conditioning_embedding_num_channels=[16],
+                                                   conditioning_embedding_in_channels=1, **base)).cuda().eval()
+    s = DDPMScheduler(num_train_timesteps=10)
+    s.set_timesteps(10)
+    inf = ControlNetLatentDiffusionInferer(s, scale_factor=1.0)
+    img, mask = torch.randn(1, 1, 8, 8).cuda(), torch.randn(1, 1, 8, 8).cuda()
+    for stage1, lat in ((ae, (1, 3, 4, 4)), (vq, (1, 3, 2, 2))):
+        noise = torch.randn(lat).cuda()
+        pred = inf(inputs=img, autoencoder_model=stage1, diffusion_model=un, controlnet=cn, noise=noise,
+                   timesteps=torch.randint(0, 10, (1,)).cuda(), cn_cond=mask)
+        assert pred.shape == lat
+        sample, inter = inf.sample(input_noise=noise, autoencoder_model=stage1, diffusion_model=un, controlnet=cn,
+                                   cn_cond=mask, scheduler=s, save_intermediates=True, intermediate_steps=1,
+                                   verbose=False)
+        assert sample.shape == img.shape and len(inter) == 10 and inter[0].shape == img.shape
+        lik, inter = inf.get_likelihood(inputs=img, autoencoder_model=stage1, diffusion_model=un, controlnet=cn,
+                                        cn_cond=mask, scheduler=s, save_intermediates=True, verbose=False)
+        assert len(inter) == 10 and inter[0].shape == lat and torch.isfinite(lik).all()
+        lik, inter = inf.get_likelihood(inputs=img, autoencoder_model=stage1, diffusion_model=un, controlnet=cn,
+                                        cn_cond=mask, scheduler=s, save_intermediates=True,
+                                        resample_latent_likelihoods=True, verbose=False)
+        assert inter[0].shape[2:] == img.shape[2:]

@@ -75,3 +75,30 @@ if a.breakdown:
     for n in sorted(acc, key=lambda k: -acc[k]):
         print(f"  {n:20s} {acc[n]:9.1f} ms  x{cnt[n]:4d}  {100 * acc[n] / tot:5.1f}%")
     print(f"  total {tot:.1f} ms")
+
+if a.breakdown:
+    # per-launch view of the implicit-GEMM kernel: executed FLOPs (64-channel chunks as issued) and rate
+    groups = collections.OrderedDict()
+    raw = ops.igemm_raw
+
+    def timed_raw(p):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        raw(p)
+        e1.record()
+        e1.synchronize()
+        M = p.out_N * p.out_D * p.out_H * p.out_W
+        K = 64 * sum(p.seg[i].nchunks for i in range(p.n_seg))
+        key = (p.out_N, p.out_D, p.out_H, p.out_W, p.cout, p.n_seg, K, p.w_batched, p.out_dtype, bool(p.res_ptr), bool(p.stat_ptr))
+        g = groups.setdefault(key, [0, 0.0, 2.0 * M * p.cout * K])
+        g[0] += 1
+        g[1] += e0.elapsed_time(e1)
+
+    ops.igemm_raw = timed_raw
+    y = m(x, t)
+    torch.cuda.synchronize()
+    ops.igemm_raw = raw
+    print("  igemm launches grouped by shape: N,OD,OH,OW,cout,n_seg,K,batched,odt,res,stat | count | ms total | TFLOP/s")
+    for k, (c, ms, fl) in sorted(groups.items(), key=lambda kv: -kv[1][1]):
+        print(f"  {str(k):64s} x{c:3d} {ms:8.2f} ms  {fl * c / ms / 1e9:8.1f} TF/s")
+    print(f"  igemm total {sum(g[1] for g in groups.values()):.1f} ms")
