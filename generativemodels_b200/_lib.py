@@ -64,7 +64,8 @@ class FlashParams(C.Structure):
     _fields_ = [("q", C.c_void_p), ("k", C.c_void_p), ("vt", C.c_void_p), ("out", C.c_void_p), ("res", C.c_void_p),
                 ("B", C.c_int32), ("T", C.c_int32), ("S", C.c_int32), ("heads", C.c_int32), ("dh", C.c_int32),
                 ("q_pitch", C.c_int32), ("k_pitch", C.c_int32), ("vt_pitch", C.c_int32), ("out_pitch", C.c_int32),
-                ("res_pitch", C.c_int32), ("scale", C.c_float)]
+                ("res_pitch", C.c_int32), ("scale", C.c_float),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64)]
 
 
 class DdimCoef(C.Structure):
@@ -116,6 +117,7 @@ SIGNATURES = {
     "b200_softmax_rows": [_P, _I64, _I32, _I64, _P, _I64, _P],
     "b200_softmax_rows_partials": [_P, _I64, _I32, _I64, _P, _I32, _P, _I64, _P],
     "b200_attention_flash": [C.POINTER(FlashParams), _P],
+    "b200_attention_flash_workspace_bytes": [C.POINTER(FlashParams)],
     "b200_attention_small": [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _F, _P],
     "b200_timestep_embedding": [_P, _I32, _I32, _F, _P, _P],
     "b200_small_linear": [_P, _I32, _I32, _P, _P, _I32, _I32, _I32, _P, _P],
@@ -130,7 +132,8 @@ SIGNATURES = {
     "b200_vq_argmin_gather": [_P, _I64, _I32, _I32, _P, _I32, _P, _P, _I32, _P, _I32, _P, _P, _P],
     "b200_vq_gather": [_P, _I64, _P, _I32, _I32, _P, _I32, _P],
 }
-_RESTYPES = {"b200_last_error_string": C.c_char_p, "b200_groupnorm_workspace_bytes": C.c_int64}
+_RESTYPES = {"b200_last_error_string": C.c_char_p, "b200_groupnorm_workspace_bytes": C.c_int64,
+             "b200_attention_flash_workspace_bytes": C.c_int64}
 
 _lib = None
 _device_ok = False

@@ -29,6 +29,7 @@ struct FlashDev {
   alignas(64) CUtensorMap tmQ;    // [B][T][C]      box (64 ch, 128 rows)
   alignas(64) CUtensorMap tmK;    // [B][S][C]      box (64 ch, 64 rows)
   alignas(64) CUtensorMap tmVt;   // [B][C][S]      box (64 keys, DV rows)
+  alignas(64) CUtensorMap tmP;    // [grid][128][S_pad] probability slabs (replay variant), box (64 keys, 128 rows)
   int B, T, S, heads, dh, d_chunks, dv, n_dv;
   int q_tiles, n_items, n_kv;
   float scale_log2;
@@ -36,6 +37,10 @@ struct FlashDev {
   long long out_bstride, out_pitch;
   const __nv_bfloat16* res;
   long long res_bstride, res_pitch;
+  __nv_bfloat16* pslab;           // replay workspace: [grid][128][p_pitch]
+  long long p_pitch;
+  float* ev_fac;                  // [grid][4 warps][n_kv][32] logged rescale factors
+  int* ev_blk;                    // [grid][4 warps][n_kv]     block index of each logged rescale
 };
 
 namespace fa {
@@ -170,21 +175,41 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 struct Item { int b, h, qt, dvi; };
+template <bool REPLAY>
 __device__ __forceinline__ Item decode(const FlashDev& p, int item) {
   Item it;
-  it.dvi = item % p.n_dv; item /= p.n_dv;
+  if constexpr (REPLAY) {
+    it.dvi = 0;                       // both output slices are handled inside the item (two passes)
+  } else {
+    it.dvi = item % p.n_dv; item /= p.n_dv;
+  }
   it.qt = item % p.q_tiles; item /= p.q_tiles;
   it.h = item % p.heads;
   it.b = item / p.heads;
   return it;
 }
 
-template <int DCH>      // head_dim / 64
+__device__ __forceinline__ void stg256(void* ptr, const uint32_t* w) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+               "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
+
+// REPLAY (head_dim 512 with a workspace): instead of recomputing S = Q K^T and the softmax for the second 256-wide
+// output slice, pass 1 also writes its probability tiles P (bf16, exactly the values its own PV MMAs consume) to a
+// per-CTA slab in global memory, and pass 2 streams them back through TMA as the shared-memory A operand of
+// O2 += P V2 — a pure GEMM stream with no QK^T and no exponentials (2/3 of the recompute variant's tensor work).
+// The rare lazy-rescale events of pass 1 are logged per warp (block index + per-row factor) and replayed on O2 at
+// the same block positions, so both slices see bit-identical P and the same normaliser l.
+template <int DCH, bool REPLAY>      // DCH = head_dim / 64
 __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_constant__ FlashDev p) {
   constexpr int CPS = DCH >= 2 ? 2 : 1;               // 64-channel K chunks per ring stage
   constexpr int NSTEP = DCH / CPS;                    // ring stages consumed per key block
   constexpr int kKStages = kKRingBytes / (CPS * kKChunkBytes);
   constexpr int kKStageBytes = CPS * kKChunkBytes;
+  constexpr int kRStageBytes = kQChunkBytes + 256 * kBKV * 2;     // replay stage: P tile (16 KB) + V^T slice (32 KB)
+  static_assert(!REPLAY || (DCH == 8 && kKStages * kRStageBytes <= DCH * kQChunkBytes + kKRingBytes + 256 * kBKV * 2),
+                "replay stages overlay the Q / K / V regions");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = base;
@@ -201,8 +226,11 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
   auto p_full = [&](int b) { return v_empty + 40 + 8u * b; };
   auto p_empty = [&](int b) { return v_empty + 56 + 8u * b; };
   const uint32_t o_full = v_empty + 72, o_empty = o_full + 8;
-  const uint32_t tmem_slot = o_empty + 8;
+  const uint32_t p1_done = o_empty + 8;       // REPLAY: the softmax warps have written (and fenced) all P tiles
+  const uint32_t r_done = p1_done + 8;        // REPLAY: every pass-2 MMA has completed (stage buffers free)
+  const uint32_t tmem_slot = r_done + 8;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  volatile int* ev_flags = reinterpret_cast<volatile int*>(tmem_slot_ptr + 2);   // REPLAY: [4] "this warp logged rescales"
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -214,6 +242,7 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
       mbar_init(p_full(b), 4); mbar_init(p_empty(b), 1);
     }
     mbar_init(o_full, 1); mbar_init(o_empty, 4);
+    mbar_init(p1_done, 4); mbar_init(r_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -237,10 +266,11 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
       int kst = 0; uint32_t kph = 0;
       uint32_t vcount = 0, icount = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++icount) {
-        const Item it = decode(p, item);
+        const Item it = decode<REPLAY>(p, item);
         const int ch0 = it.h * p.dh;
         // Q tile: reused by every key block of the item
-        mbar_wait_warp(q_empty, (icount & 1) ^ 1u);
+        if constexpr (REPLAY) mbar_wait_warp(r_done, (icount & 1) ^ 1u);      // previous item's replay stages drained
+        else mbar_wait_warp(q_empty, (icount & 1) ^ 1u);
         if (elect_one()) {
           mbar_expect_tx(q_full, DCH * kQChunkBytes);
 #pragma unroll
@@ -275,6 +305,23 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
             ++vcount;
           }
         }
+        if constexpr (REPLAY) {
+          // ---- pass 2: stream P tiles (this CTA's slab) and the second V^T slice through 48 KB stages that overlay
+          //      the Q / K / V regions: all pass-1 MMAs have completed (q_empty) and all P tiles are visible ----
+          mbar_wait_warp(q_empty, icount & 1);
+          mbar_wait_warp(p1_done, icount & 1);
+          for (int j = 0; j < n_kv; ++j) {
+            mbar_wait_warp(k_empty(kst), kph ^ 1u);
+            if (elect_one()) {
+              const uint32_t st = sQ + kst * kRStageBytes;
+              mbar_expect_tx(k_full(kst), kRStageBytes);
+              tma_load_3d(&p.tmP, k_full(kst), st, j * kBKV, 0, blockIdx.x);
+              tma_load_3d(&p.tmVt, k_full(kst), st + kQChunkBytes, j * kBKV, ch0 + 256, it.b);
+            }
+            __syncwarp();
+            if (++kst == kKStages) { kst = 0; kph ^= 1u; }
+          }
+        }
       }
     }
   } else if (warp == 1) {
@@ -286,10 +333,11 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
       int kst = 0; uint32_t kph = 0;
       uint32_t scount = 0;      // number of S blocks issued so far (global across items)
       uint32_t pvcount = 0;     // number of PV blocks issued so far
-      uint32_t icount = 0;
+      uint32_t icount = 0, ocount = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++icount) {
         mbar_wait_warp(q_full, icount & 1);
-        mbar_wait_warp(o_empty, (icount & 1) ^ 1u);        // previous item's epilogue has drained O
+        mbar_wait_warp(o_empty, (ocount & 1) ^ 1u);        // previous epilogue has drained O
+        ++ocount;
         fence_after();
         for (int j = 0; j <= n_kv; ++j) {
           if (j < n_kv) {
@@ -340,6 +388,37 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
             ++pvcount;
           }
         }
+        if constexpr (REPLAY) {
+          // ---- pass 2: O2 += P_j V2_j with both operands from shared memory; the softmax warps only gate each
+          //      block through p_full (after replaying a logged rescale on O2, if any) ----
+          mbar_wait_warp(p1_done, icount & 1);             // rescale flags of the four softmax warps are visible
+          const bool gated = (ev_flags[0] | ev_flags[1] | ev_flags[2] | ev_flags[3]) != 0;
+          mbar_wait_warp(o_empty, (ocount & 1) ^ 1u);      // pass-1 epilogue has drained O
+          ++ocount;
+          fence_after();
+          for (int j = 0; j < n_kv; ++j) {
+            const int pb = pvcount & 1;
+            mbar_wait_warp(k_full(kst), kph);
+            if (gated) mbar_wait_warp(p_full(pb), (pvcount >> 1) & 1);
+            fence_after();
+            if (elect_one()) {
+              const uint32_t a_lo = q_lo + kst * (kRStageBytes >> 4);
+              const uint32_t b_lo = a_lo + (kQChunkBytes >> 4);
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                umma_bf16(tO, desc64(a_lo + 2 * kk), desc64(b_lo + 2 * kk), idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+              umma_commit(k_empty(kst));
+              if (gated) umma_commit(p_empty(pb));
+              if (j == n_kv - 1) {
+                umma_commit(o_full);
+                umma_commit(r_done);
+              }
+            }
+            __syncwarp();
+            if (++kst == kKStages) { kst = 0; kph ^= 1u; }
+            if (gated) ++pvcount;
+          }
+        }
       }
     }
   } else {
@@ -347,11 +426,19 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    uint32_t scount = 0, icount = 0;
+    uint32_t scount = 0;       // S buffers consumed (pass 1 blocks)
+    uint32_t pcount = 0;       // P hand-offs to the MMA warp (pass 1 and pass 2 blocks)
+    uint32_t ocount = 0;       // epilogues done
+    uint32_t icount = 0;
+    // REPLAY: this CTA's probability slab and this warp's rescale log
+    __nv_bfloat16* slab_row = REPLAY ? p.pslab + ((long long)blockIdx.x * kBM + row) * p.p_pitch : nullptr;
+    float* ev_fac = REPLAY ? p.ev_fac + ((long long)blockIdx.x * 4 + q) * (long long)n_kv * 32 : nullptr;
+    int* ev_blk = REPLAY ? p.ev_blk + ((long long)blockIdx.x * 4 + q) * (long long)n_kv : nullptr;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++icount) {
-      const Item it = decode(p, item);
+      const Item it = decode<REPLAY>(p, item);
       float m_used = -INFINITY, l_run = 0.f;
-      for (int j = 0; j < n_kv; ++j, ++scount) {
+      int n_ev = 0;
+      for (int j = 0; j < n_kv; ++j, ++scount, ++pcount) {
         const int sb = scount & 1;
         mbar_wait(s_full(sb), (scount >> 1) & 1);
         fence_after();
@@ -386,12 +473,13 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
         const float m_new = need ? mx : m_used;
         const float factor = (need && m_used > -INFINITY) ? exp2f(m_used - m_new) : 1.0f;
         const unsigned any = __ballot_sync(0xffffffffu, need && m_used > -INFINITY);
-        // P buffer (j & 1 of this item's sequence == scount & 1) must have been consumed by PV of block j - 2
-        if (scount >= 2) mbar_wait(p_empty(sb), ((scount >> 1) & 1) ^ 1u);
+        // P buffer pb must have been consumed by the PV MMA two hand-offs ago
+        const int pb = pcount & 1;
+        if (pcount >= 2) mbar_wait(p_empty(pb), ((pcount >> 1) & 1) ^ 1u);
         if (any) {
           // O holds blocks < j; PV of block j - 1 must have completed before it is rewritten
           if (j >= 1) {
-            const uint32_t prev = scount - 1;
+            const uint32_t prev = pcount - 1;
             mbar_wait(p_empty(prev & 1), (prev >> 1) & 1);
           }
           fence_after();
@@ -405,6 +493,11 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
           }
           tmem_st_wait();
           fence_before();
+          if constexpr (REPLAY) {
+            ev_fac[(long long)n_ev * 32 + lane] = factor;
+            if (lane == 0) ev_blk[n_ev] = j;
+            ++n_ev;
+          }
         }
         l_run *= factor;
         m_used = m_new;
@@ -425,46 +518,99 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
           __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
           pw[w] = *reinterpret_cast<uint32_t*>(&h);
         }
-        tmem_st32(tP + lane_addr + sb * 32, pw);
+        tmem_st32(tP + lane_addr + pb * 32, pw);
+        if constexpr (REPLAY) {
+          // the same 64 probabilities to this row of the slab (128 contiguous bytes), for pass 2
+          __nv_bfloat16* dst = slab_row + (long long)j * kBKV;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) stg256(dst + g * 16, pw + g * 8);
+        }
         tmem_st_wait();
         const float lsum = ((sum8[0] + sum8[1]) + (sum8[2] + sum8[3])) + ((sum8[4] + sum8[5]) + (sum8[6] + sum8[7]));
         l_run += lsum;
         fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(p_full(sb));
+        if (lane == 0) mbar_arrive(p_full(pb));
       }
-      // ---- epilogue: O / l (+ residual) -> bf16 ----
-      mbar_wait(o_full, icount & 1);
-      fence_after();
+      if constexpr (REPLAY) {
+        // make the slab visible to the TMA (async proxy) reads of pass 2, then release the producer
+        if (lane == 0) ev_flags[q] = n_ev > 0 ? 1 : 0;
+        __threadfence();
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p1_done);
+      }
+      bool gated = false;
+      if constexpr (REPLAY) {
+        mbar_wait(p1_done, icount & 1);
+        gated = (ev_flags[0] | ev_flags[1] | ev_flags[2] | ev_flags[3]) != 0;
+      }
+      const float inv = 1.0f / l_run;
       const int t = it.qt * kBM + row;
       const bool ok = t < p.T;
-      const float inv = 1.0f / l_run;
-      const long long col0 = (long long)it.h * p.dh + (long long)it.dvi * p.dv;
-      __nv_bfloat16* orow = p.out + it.b * p.out_bstride + (long long)t * p.out_pitch + col0;
-      const __nv_bfloat16* rrow = p.res ? p.res + it.b * p.res_bstride + (long long)t * p.res_pitch + col0 : nullptr;
-      for (int c0 = 0; c0 < p.dv; c0 += 32) {
-        uint32_t o[32];
-        tmem_ld32(tO + lane_addr + c0, o);
-        tmem_ld_wait();
-        if (ok) {
+#pragma unroll 1
+      for (int pass = 0; pass < (REPLAY ? 2 : 1); ++pass) {
+        if (pass == 1 && gated) {
+          // ---- pass 2 of an item in which some warp logged a rescale: every block is gated through p_full (after
+          //      replaying this warp's own rescales on O2); items without rescales run pass 2 ungated ----
+          int e_next = 0;
+          int next_blk = (n_ev > 0) ? ev_blk[0] : 0x7fffffff;
+          for (int j = 0; j < n_kv; ++j, ++pcount) {
+            const int pb = pcount & 1;
+            if (pcount >= 2) mbar_wait(p_empty(pb), ((pcount >> 1) & 1) ^ 1u);
+            if (j == next_blk) {                      // warp-uniform; j >= 1 by construction
+              const uint32_t prev = pcount - 1;
+              mbar_wait(p_empty(prev & 1), (prev >> 1) & 1);
+              fence_after();
+              const float factor = ev_fac[(long long)e_next * 32 + lane];
+              for (int c0 = 0; c0 < p.dv; c0 += 32) {
+                uint32_t o[32];
+                tmem_ld32(tO + lane_addr + c0, o);
+                tmem_ld_wait();
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float f[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(o[g * 8 + e]) * inv;
-            if (rrow) {
-              float rf[8];
-              unpack8(__ldg(reinterpret_cast<const uint4*>(rrow + c0 + g * 8)), rf);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] += rf[e];
+                for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * factor);
+                tmem_st32(tO + lane_addr + c0, o);
+              }
+              tmem_st_wait();
+              fence_before();
+              ++e_next;
+              next_blk = (e_next < n_ev) ? ev_blk[e_next] : 0x7fffffff;
             }
-            *reinterpret_cast<uint4*>(orow + c0 + g * 8) = pack8(f);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full(pb));
           }
         }
+        // ---- epilogue: O / l (+ residual) -> bf16 ----
+        mbar_wait(o_full, ocount & 1);
+        ++ocount;
+        fence_after();
+        const long long col0 = (long long)it.h * p.dh + (long long)(REPLAY ? pass : it.dvi) * p.dv;
+        __nv_bfloat16* orow = p.out + it.b * p.out_bstride + (long long)t * p.out_pitch + col0;
+        const __nv_bfloat16* rrow = p.res ? p.res + it.b * p.res_bstride + (long long)t * p.res_pitch + col0 : nullptr;
+        for (int c0 = 0; c0 < p.dv; c0 += 32) {
+          uint32_t o[32];
+          tmem_ld32(tO + lane_addr + c0, o);
+          tmem_ld_wait();
+          if (ok) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(o[g * 8 + e]) * inv;
+              if (rrow) {
+                float rf[8];
+                unpack8(__ldg(reinterpret_cast<const uint4*>(rrow + c0 + g * 8)), rf);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] += rf[e];
+              }
+              *reinterpret_cast<uint4*>(orow + c0 + g * 8) = pack8(f);
+            }
+          }
+        }
+        fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(o_empty);
       }
-      fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(o_empty);
     }
   }
   fence_before();
@@ -501,10 +647,31 @@ static int encode3(CUtensorMap* tm, const void* ptr, cuuint64_t d0, cuuint64_t d
   return B200_OK;
 }
 
+struct ReplayPlan { int grid, n_kv; long long slab_bytes, fac_bytes, blk_bytes, total; };
+static ReplayPlan replay_plan(const b200_flash_params* a) {
+  ReplayPlan r;
+  memset(&r, 0, sizeof(r));
+  if (a->dh != 512) return r;
+  const long long q_tiles = (a->T + kBM - 1) / kBM;
+  const long long items = (long long)a->B * a->heads * q_tiles;
+  r.grid = (int)(items < sm_count() ? items : sm_count());
+  r.n_kv = (a->S + kBKV - 1) / kBKV;
+  r.slab_bytes = (long long)r.grid * kBM * r.n_kv * kBKV * 2;
+  r.fac_bytes = (long long)r.grid * 4 * r.n_kv * 32 * 4;
+  r.blk_bytes = (((long long)r.grid * 4 * r.n_kv * 4) + 255) / 256 * 256;
+  r.total = r.slab_bytes + r.fac_bytes + r.blk_bytes;
+  return r;
+}
+
 }  // namespace fa
 }  // namespace b200
 
 using namespace b200;
+
+extern "C" int64_t b200_attention_flash_workspace_bytes(const b200_flash_params* a) {
+  if (!a || a->B < 1 || a->T < 1 || a->S < 1 || a->heads < 1) return 0;
+  return fa::replay_plan(a).total;
+}
 
 extern "C" int b200_attention_flash(const b200_flash_params* a, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
@@ -529,7 +696,14 @@ extern "C" int b200_attention_flash(const b200_flash_params* a, void* stream_v) 
   d.n_dv = a->dh / d.dv;
   d.q_tiles = (a->T + fa::kBM - 1) / fa::kBM;
   d.n_kv = (a->S + fa::kBKV - 1) / fa::kBKV;
-  const long long items = (long long)a->B * a->heads * d.q_tiles * d.n_dv;
+  const fa::ReplayPlan rp = fa::replay_plan(a);
+  const bool replay = a->dh == 512 && a->workspace != nullptr;
+  if (replay) {
+    B200_CHECK_ARG(a->workspace_bytes >= rp.total, "attention_flash: workspace of %lld bytes, need %lld",
+                   (long long)a->workspace_bytes, rp.total);
+    B200_CHECK_ARG(((uintptr_t)a->workspace & 255) == 0, "attention_flash: workspace must be 256-byte aligned");
+  }
+  const long long items = (long long)a->B * a->heads * d.q_tiles * (replay ? 1 : d.n_dv);
   B200_CHECK_ARG(items < (1ll << 31), "attention_flash: too many work items");
   d.n_items = (int)items;
   d.scale_log2 = a->scale * 1.4426950408889634f;
@@ -545,22 +719,36 @@ extern "C" int b200_attention_flash(const b200_flash_params* a, void* stream_v) 
   if ((rc = fa::encode3(&d.tmVt, a->vt, a->S, C, a->B, (cuuint64_t)a->vt_pitch * 2, (cuuint64_t)C * a->vt_pitch * 2,
                         fa::kBKV, d.dv, "V^T"))) return rc;
 
-  const int smem = d.d_chunks * fa::kQChunkBytes + fa::kKRingBytes + d.dv * fa::kBKV * 2 + 1024 + 256;
+  const int smem = d.d_chunks * fa::kQChunkBytes + fa::kKRingBytes + d.dv * fa::kBKV * 2 + 1024 + 512;
   const int grid = d.n_items < sm_count() ? d.n_items : sm_count();
-#define B200_FLASH_LAUNCH(DCH)                                                                                        \
+  if (replay) {
+    B200_CHECK_ARG(grid == rp.grid && d.n_kv == rp.n_kv, "attention_flash: internal replay plan mismatch");
+    uint8_t* ws = static_cast<uint8_t*>(a->workspace);
+    d.pslab = reinterpret_cast<__nv_bfloat16*>(ws);
+    d.p_pitch = (long long)d.n_kv * fa::kBKV;
+    d.ev_fac = reinterpret_cast<float*>(ws + rp.slab_bytes);
+    d.ev_blk = reinterpret_cast<int*>(ws + rp.slab_bytes + rp.fac_bytes);
+    if ((rc = fa::encode3(&d.tmP, d.pslab, (cuuint64_t)d.p_pitch, fa::kBM, grid, (cuuint64_t)d.p_pitch * 2,
+                          (cuuint64_t)fa::kBM * d.p_pitch * 2, fa::kBKV, fa::kBM, "P slab"))) return rc;
+  }
+#define B200_FLASH_LAUNCH(DCH, RP)                                                                                    \
   do {                                                                                                                \
     static bool attr_done = false;                                                                                    \
     if (!attr_done) {                                                                                                 \
-      B200_CUDA(cudaFuncSetAttribute(fa::flash_attn_kernel<DCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+      B200_CUDA(cudaFuncSetAttribute(fa::flash_attn_kernel<DCH, RP>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                     smem));                                                                          \
       attr_done = true;                                                                                               \
     }                                                                                                                 \
-    fa::flash_attn_kernel<DCH><<<grid, fa::kThreads, smem, stream>>>(d);                                              \
+    fa::flash_attn_kernel<DCH, RP><<<grid, fa::kThreads, smem, stream>>>(d);                                          \
   } while (0)
   switch (d.d_chunks) {
-    case 1: B200_FLASH_LAUNCH(1); break;
-    case 2: B200_FLASH_LAUNCH(2); break;
-    case 4: B200_FLASH_LAUNCH(4); break;
-    default: B200_FLASH_LAUNCH(8); break;
+    case 1: B200_FLASH_LAUNCH(1, false); break;
+    case 2: B200_FLASH_LAUNCH(2, false); break;
+    case 4: B200_FLASH_LAUNCH(4, false); break;
+    default:
+      if (replay) B200_FLASH_LAUNCH(8, true);
+      else B200_FLASH_LAUNCH(8, false);
+      break;
   }
 #undef B200_FLASH_LAUNCH
   B200_LAUNCH_CHECK("flash_attn_kernel");

@@ -564,6 +564,7 @@ def geglu(x: CL) -> CL:
 _TC_ATTN_MIN_S = 64
 _FLASH_HEAD_DIMS = (64, 128, 256, 512)
 _FORCE_UNFUSED_ATTENTION = False      # tests flip this to cover the GEMM + softmax + GEMM path
+_FLASH_REPLAY = True                  # tests flip this to compare the replay and recompute variants of head_dim 512
 _ATTN_CHUNK_BYTES = 6 << 30   # fp32 score slab per query chunk
 
 
@@ -603,6 +604,12 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, dh:
         fp.scale = scale
         if out.shape[2] > heads * dh:
             out.zero_()
+        ws = None
+        if _FLASH_REPLAY:
+            need = int(lib.b200_attention_flash_workspace_bytes(C.byref(fp)))
+            if need:        # head_dim 512: probability tiles are written once and replayed for the second output half
+                ws = torch.empty(need, dtype=torch.uint8, device=q.device)
+                fp.workspace, fp.workspace_bytes = ws.data_ptr(), need
         check(lib.b200_attention_flash(C.byref(fp), _stream()), "b200_attention_flash")
         return out
     Sp = round_up(S, 8)

@@ -191,8 +191,15 @@ typedef struct {
   int32_t B, T, S, heads, dh;
   int32_t q_pitch, k_pitch, vt_pitch, out_pitch, res_pitch;
   float scale;
+  /* Optional device scratch for head_dim 512 (whose 128 x 512 fp32 output tile does not fit tensor memory beside the
+   * scores): with at least b200_attention_flash_workspace_bytes() bytes the kernel computes every probability tile
+   * once and replays it for the second half of the output channels; with NULL it recomputes the scores instead
+   * (same result up to bf16 rounding of identical P values, 1.5x the tensor work).  Other head dims ignore it. */
+  void* workspace; int64_t workspace_bytes;
 } b200_flash_params;
 int b200_attention_flash(const b200_flash_params* p, void* stream);
+/* bytes of scratch the call described by p can use (0 when none is needed); pointer fields are not read */
+int64_t b200_attention_flash_workspace_bytes(const b200_flash_params* p);
 
 /* Small-shape attention on CUDA cores (any head_dim <= 256, any S); used for the test-suite
  * head dims (2..8) and for cross-attention with a handful of context tokens.

@@ -151,6 +151,9 @@ class FakeLib:
         dst[:, :S] = (torch.exp(sc - mx[:, None]) / den[:, None]).to(torch.bfloat16)
         return 0
 
+    def b200_attention_flash_workspace_bytes(self, a):
+        return 0
+
     def b200_attention_flash(self, a, stream):
         a = _obj(a)
         B, T, S, heads, dh = a.B, a.T, a.S, a.heads, a.dh

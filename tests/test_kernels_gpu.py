@@ -274,7 +274,7 @@ def test_attention_small(cuda_device, B, T, S, heads, dh):
 
 @pytest.mark.parametrize("unfused", [False, True], ids=["flash", "unfused"])
 @pytest.mark.parametrize("B,T,heads,dh", [(1, 256, 1, 256), (2, 200, 1, 512), (1, 1024, 2, 64), (1, 2300, 1, 128),
-                                          (1, 700, 1, 512)])
+                                          (1, 700, 1, 512), (1, 600, 2, 512)])
 def test_attention_tensorcore(cuda_device, B, T, heads, dh, unfused, monkeypatch):
     """Flash-style tcgen05 attention (scores in TMEM) and the GEMM + softmax + GEMM path, V^T produced by the
     operand-swapped projection, against fp32 softmax(QK^T)V on the same bf16-rounded q, k, v."""
@@ -300,12 +300,15 @@ def test_attention_tensorcore(cuda_device, B, T, heads, dh, unfused, monkeypatch
     assert_close(out[..., :Cc], ref + bf(res), 2e-2, "attention tensor-core")
 
 
-def test_attention_flash_rescale(cuda_device):
+@pytest.mark.parametrize("dh,replay", [(256, True), (512, True), (512, False)], ids=["d256", "d512-replay", "d512-recompute"])
+def test_attention_flash_rescale(cuda_device, monkeypatch, dh, replay):
     """Keys whose scores grow along the sequence force the running maximum up by far more than 2^8 several times,
-    exercising the lazy O-rescale path (tcgen05.ld / tcgen05.st on the accumulator)."""
+    exercising the lazy O-rescale path (tcgen05.ld / tcgen05.st on the accumulator) and, for head_dim 512 with a
+    workspace, the logged-rescale replay on the second output half (gated pass 2)."""
     ops = _ops()
+    monkeypatch.setattr(ops, "_FLASH_REPLAY", replay)
     torch.manual_seed(11)
-    B, T, S, dh = 1, 300, 1000, 256
+    B, T, S = 1, 300, 1000
     q = torch.randn(B, T, dh)
     k = torch.randn(B, S, dh) * torch.linspace(0.2, 6.0, S)[None, :, None]
     v = torch.randn(B, S, dh)
@@ -314,6 +317,28 @@ def test_attention_flash_rescale(cuda_device):
     vt = v.to(torch.bfloat16).transpose(1, 2).contiguous().cuda()
     out = ops.attention(q.to(torch.bfloat16).cuda(), k.to(torch.bfloat16).cuda(), None, 1, dh, scale, vt=vt)
     assert_close(out[..., :dh], ref, 2e-2, "flash attention with rescale")
+
+
+def test_attention_flash_replay_matches_recompute(cuda_device, monkeypatch):
+    """head_dim 512: the probability-replay variant (P tiles written once, streamed back for output channels
+    256..511) against the recompute variant on a multi-item, multi-batch, ragged problem (T, S not multiples of the
+    tiles; more work items than SMs so slabs and rescale logs are reused across items)."""
+    ops = _ops()
+    torch.manual_seed(12)
+    B, T, S, dh = 2, 128 * 90 + 37, 1000 + 21, 512
+    q, k, v = torch.randn(B, T, dh), torch.randn(B, S, dh), torch.randn(B, S, dh)
+    k[:, 500:] *= 3.0                                     # a few late rescales in some rows
+    res = torch.randn(B, T, dh).to(torch.bfloat16).cuda()
+    args = (q.to(torch.bfloat16).cuda(), k.to(torch.bfloat16).cuda(), None, 1, dh, 1 / math.sqrt(dh))
+    vt = F.pad(v.to(torch.bfloat16).transpose(1, 2), (0, (-S) % 8)).contiguous().cuda()
+    monkeypatch.setattr(ops, "_FLASH_REPLAY", True)
+    a = ops.attention(*args, vt=vt, residual=res).float().cpu()
+    monkeypatch.setattr(ops, "_FLASH_REPLAY", False)
+    b = ops.attention(*args, vt=vt, residual=res).float().cpu()
+    assert torch.equal(a[..., :256], b[..., :256])          # pass 1 is the same code
+    assert_close(a[..., 256:], b[..., 256:], 1e-2, "replayed half vs recomputed half")
+    ref = _attn_ref(bf(q[:1, :256]), bf(k[:1]), bf(v[:1]), 1, dh, 1 / math.sqrt(dh)) + res[:1, :256].float().cpu()
+    assert_close(a[:1, :256], ref, 2e-2, "replay vs fp32 reference")
 
 
 # ------------------------------------------------------------------------------------------------ time embedding
