@@ -116,6 +116,8 @@ SIGNATURES = {
     "b200_geglu": [_P, _I64, _I32, _I32, _P, _I32, _P],
     "b200_softmax_rows": [_P, _I64, _I32, _I64, _P, _I64, _P],
     "b200_softmax_rows_partials": [_P, _I64, _I32, _I64, _P, _I32, _P, _I64, _P],
+    "b200_tap_gather": [_P, _I32, _I32, _P, _P, _I32, _P],
+    "b200_tap_sum": [_P, _I32, _P, _I32, _P, _P, _I32, _I32, _P],
     "b200_attention_flash": [C.POINTER(FlashParams), _P],
     "b200_attention_flash_workspace_bytes": [C.POINTER(FlashParams)],
     "b200_attention_small": [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _F, _P],

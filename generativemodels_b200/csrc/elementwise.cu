@@ -453,6 +453,79 @@ static unsigned grid_for(long long work, int threads = 256, int waves = 8) {
   return (unsigned)b;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Tap reformulations of the two degenerate convolutions of the UNet (conv_in: 1 -> C, out: C -> 1): both are
+// HBM-bound, but as 27-tap implicit GEMMs they pad K (or N) 2-60x.  tap_gather builds the tiny im2col matrix
+// X2[v][tap * Cin + c] so that conv_in becomes ONE 64-wide K chunk; tap_sum evaluates
+// out[v][co] = b[co] + sum_tap Y[v + off(tap)][tap * Cout + co] after a 1x1x1 GEMM Y = x W2^T that reads x once.
+// ------------------------------------------------------------------------------------------------
+struct TapGeom {
+  int N, D, H, W, OD, OH, OW, kd, kh, kw, sd, sh, sw, pd, ph, pw;
+};
+
+__global__ void tap_gather_kernel(const __nv_bfloat16* __restrict__ x, int C, int x_pitch, TapGeom g,
+                                  __nv_bfloat16* __restrict__ out, int out_pitch) {
+  const int taps = g.kd * g.kh * g.kw;
+  const long long total = (long long)g.N * g.OD * g.OH * g.OW * out_pitch;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(i % out_pitch);
+    long long v = i / out_pitch;
+    __nv_bfloat16 val = __float2bfloat16_rn(0.f);
+    if (col < taps * C) {
+      const int tap = col / C, c = col - tap * C;
+      const int cw = tap % g.kw, bh = (tap / g.kw) % g.kh, ad = tap / (g.kw * g.kh);
+      const int ow = (int)(v % g.OW); long long t = v / g.OW;
+      const int oh = (int)(t % g.OH); t /= g.OH;
+      const int od = (int)(t % g.OD); const int n = (int)(t / g.OD);
+      const int iw = ow * g.sw + cw - g.pw, ih = oh * g.sh + bh - g.ph, id = od * g.sd + ad - g.pd;
+      if (iw >= 0 && iw < g.W && ih >= 0 && ih < g.H && id >= 0 && id < g.D)
+        val = x[((((long long)n * g.D + id) * g.H + ih) * g.W + iw) * x_pitch + c];
+    }
+    out[i] = val;
+  }
+}
+
+template <int COUT>
+__global__ void tap_sum_kernel(const float* __restrict__ y, int y_pitch, TapGeom g, const float* __restrict__ bias,
+                               void* __restrict__ out, int out_pitch, int out_dtype) {
+  const long long total = (long long)g.N * g.OD * g.OH * g.OW;
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < total;
+       v += (long long)gridDim.x * blockDim.x) {
+    const int ow = (int)(v % g.OW); long long t = v / g.OW;
+    const int oh = (int)(t % g.OH); t /= g.OH;
+    const int od = (int)(t % g.OD); const int n = (int)(t / g.OD);
+    float acc[COUT];
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) acc[co] = bias ? bias[co] : 0.f;
+    for (int a = 0; a < g.kd; ++a) {
+      const int id = od + a - g.pd;
+      if (id < 0 || id >= g.D) continue;
+      for (int b = 0; b < g.kh; ++b) {
+        const int ih = oh + b - g.ph;
+        if (ih < 0 || ih >= g.H) continue;
+        const float* row = y + (((long long)n * g.D + id) * g.H + ih) * g.W * y_pitch + ((a * g.kh + b) * g.kw) * COUT;
+#pragma unroll 3
+        for (int c = 0; c < g.kw; ++c) {
+          const int iw = ow + c - g.pw;
+          if (iw < 0 || iw >= g.W) continue;
+          const float* src = row + (long long)iw * y_pitch + c * COUT;
+#pragma unroll
+          for (int co = 0; co < COUT; ++co) acc[co] += __ldg(src + co);
+        }
+      }
+    }
+    if (out_dtype == B200_DT_BF16) {
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + v * out_pitch;
+      for (int co = 0; co < out_pitch; ++co) o[co] = __float2bfloat16_rn(co < COUT ? acc[co < COUT ? co : 0] : 0.f);
+    } else {
+      float* o = reinterpret_cast<float*>(out) + v * out_pitch;
+      for (int co = 0; co < out_pitch; ++co) o[co] = co < COUT ? acc[co < COUT ? co : 0] : 0.f;
+    }
+  }
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -514,6 +587,46 @@ extern "C" int b200_axpy_bf16(const void* a, const void* b, float alpha, void* y
   axpy_bf16_kernel<<<grid_for(n / 8), 256, 0, stream>>>(reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b),
                                                        alpha, reinterpret_cast<uint4*>(y), n / 8);
   B200_LAUNCH_CHECK("axpy_bf16_kernel");
+  return B200_OK;
+}
+
+
+static bool tap_geom_ok(const b200::TapGeom& g) {
+  return g.N >= 1 && g.D >= 1 && g.H >= 1 && g.W >= 1 && g.OD >= 1 && g.OH >= 1 && g.OW >= 1 && g.kd >= 1 &&
+         g.kh >= 1 && g.kw >= 1 && g.sd >= 1 && g.sh >= 1 && g.sw >= 1 && g.pd >= 0 && g.ph >= 0 && g.pw >= 0;
+}
+
+extern "C" int b200_tap_gather(const void* x, int32_t C, int32_t x_pitch, const int32_t* geom, void* out,
+                               int32_t out_pitch, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(x && out && geom && C >= 1 && x_pitch >= C, "tap_gather: bad arguments");
+  b200::TapGeom g;
+  memcpy(&g, geom, sizeof(g));
+  B200_CHECK_ARG(tap_geom_ok(g) && out_pitch >= g.kd * g.kh * g.kw * C, "tap_gather: bad geometry");
+  const long long total = (long long)g.N * g.OD * g.OH * g.OW * out_pitch;
+  tap_gather_kernel<<<grid_for(total), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), C, x_pitch, g,
+                                                        reinterpret_cast<__nv_bfloat16*>(out), out_pitch);
+  B200_LAUNCH_CHECK("tap_gather_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_tap_sum(const float* y, int32_t y_pitch, const int32_t* geom, int32_t cout, const float* bias,
+                            void* out, int32_t out_pitch, int32_t out_dtype, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(y && out && geom && cout >= 1 && cout <= 4 && out_pitch >= cout, "tap_sum: 1 <= cout <= 4");
+  b200::TapGeom g;
+  memcpy(&g, geom, sizeof(g));
+  B200_CHECK_ARG(tap_geom_ok(g) && g.sd == 1 && g.sh == 1 && g.sw == 1 && y_pitch >= g.kd * g.kh * g.kw * cout,
+                 "tap_sum: bad geometry (stride must be 1)");
+  const long long total = (long long)g.N * g.OD * g.OH * g.OW;
+  const unsigned grid = grid_for(total);
+  switch (cout) {
+    case 1: tap_sum_kernel<1><<<grid, 256, 0, stream>>>(y, y_pitch, g, bias, out, out_pitch, out_dtype); break;
+    case 2: tap_sum_kernel<2><<<grid, 256, 0, stream>>>(y, y_pitch, g, bias, out, out_pitch, out_dtype); break;
+    case 3: tap_sum_kernel<3><<<grid, 256, 0, stream>>>(y, y_pitch, g, bias, out, out_pitch, out_dtype); break;
+    default: tap_sum_kernel<4><<<grid, 256, 0, stream>>>(y, y_pitch, g, bias, out, out_pitch, out_dtype); break;
+  }
+  B200_LAUNCH_CHECK("tap_sum_kernel");
   return B200_OK;
 }
 

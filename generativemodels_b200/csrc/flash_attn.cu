@@ -90,6 +90,12 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* tm, uint32_t bar,
       "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* tm, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -310,9 +316,17 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
           //      the Q / K / V regions: all pass-1 MMAs have completed (q_empty) and all P tiles are visible ----
           mbar_wait_warp(q_empty, icount & 1);
           mbar_wait_warp(p1_done, icount & 1);
+          // the slab comes back from HBM (148 slabs of 128 x S probabilities never fit L2): pull the tiles into L2
+          // kPrefetch blocks ahead of the 4-stage shared-memory pipeline so that its loads see L2 latency only
+          constexpr int kPrefetch = 24;
+          if (elect_one()) {
+            for (int j = 0; j < kPrefetch && j < n_kv; ++j) tma_prefetch_3d(&p.tmP, j * kBKV, 0, blockIdx.x);
+          }
+          __syncwarp();
           for (int j = 0; j < n_kv; ++j) {
             mbar_wait_warp(k_empty(kst), kph ^ 1u);
             if (elect_one()) {
+              if (j + kPrefetch < n_kv) tma_prefetch_3d(&p.tmP, (j + kPrefetch) * kBKV, 0, blockIdx.x);
               const uint32_t st = sQ + kst * kRStageBytes;
               mbar_expect_tx(k_full(kst), kRStageBytes);
               tma_load_3d(&p.tmP, k_full(kst), st, j * kBKV, 0, blockIdx.x);

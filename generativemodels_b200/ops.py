@@ -163,6 +163,21 @@ class PackedConv:
         self.w = _pack_taps(blocks, self.cout)
         self.segs = segs
         self.bias = None if bias is None else bias.detach().float().contiguous()
+        # Degenerate ends of the UNet (see b200_tap_gather / b200_tap_sum): with very few input channels the taps
+        # are folded into ONE 64-wide K chunk; with very few output channels the taps become GEMM columns.
+        taps = k[0] * k[1] * k[2]
+        self.tap_in = self.tap_out = None
+        if taps > 1 and len(self.splits) == 1 and taps * cin <= 64:
+            w2 = w.permute(0, 2, 3, 4, 1).reshape(self.cout, taps * cin)              # [co][tap*cin + c]
+            self.tap_in = PackedLinear(w2, bias)
+        elif (taps > 1 and len(self.splits) == 1 and self.cout <= 4 and taps * self.cout <= 128 and cin >= 64
+              and self.stride == (1, 1, 1)):
+            w2 = w.permute(2, 3, 4, 0, 1).reshape(taps * self.cout, cin)               # [tap*cout + co][c]
+            self.tap_out = PackedLinear(w2, None)
+
+    def geom(self, N: int, D: int, H: int, W: int):
+        od = self.out_dims(D, H, W)
+        return (C.c_int32 * 16)(N, D, H, W, *od, *self.k, *self.stride, self.pad[0][0], self.pad[1][0], self.pad[2][0])
 
     def out_dims(self, D: int, H: int, W: int) -> tuple[int, int, int]:
         i = (D, H, W)
@@ -280,6 +295,9 @@ def conv_upsample2x(src: CL, pu: PackedUpsampleConv, impl: int = 0) -> CL:
     return out
 
 
+_TAP_MIN_ROWS = 1 << 15       # below this the extra launch costs more than the padded implicit GEMM
+
+
 # --------------------------------------------------------------------------------------------------
 # implicit GEMM launcher
 # --------------------------------------------------------------------------------------------------
@@ -363,6 +381,30 @@ def conv(srcs: CL | Sequence[CL], pc: PackedConv, *, rowvec: torch.Tensor | None
         out_t = out.t
     if residual is not None and tuple(residual.t.shape[:4]) != tuple(out_t.shape[:4]):
         raise ValueError("residual shape mismatch")
+    rows = a0.N * od[0] * od[1] * od[2]
+    if impl == 0 and rows >= _TAP_MIN_ROWS and pc.tap_in is not None:
+        # conv_in-like: im2col of the few input channels (one bf16 row of <= 64 values per output voxel), then the
+        # ordinary fused GEMM epilogue
+        lib = _lib.require_device()
+        Kp = round_up(pc.tap_in.K, 8)
+        x2 = torch.empty((a0.N, *od, Kp), dtype=torch.bfloat16, device=a0.t.device)
+        check(lib.b200_tap_gather(a0.t.data_ptr(), a0.C, a0.pitch, pc.geom(a0.N, a0.D, a0.H, a0.W), x2.data_ptr(), Kp,
+                                  _stream()), "b200_tap_gather")
+        pl = pc.tap_in
+        p = _conv_params([CL(x2, pl.K, a0.spatial_dims)], pl.w, pl.segs, (1, 1, 1), out_t, od, pc.cout,
+                         DT_F32 if out_f32 else DT_BF16, pl.bias, rowvec, act1, scale,
+                         None if residual is None else residual.t, DT_BF16, act2)
+        igemm_raw(p)
+        return out
+    if (impl == 0 and rows >= _TAP_MIN_ROWS and pc.tap_out is not None and rowvec is None and residual is None
+            and act1 == ACT_NONE and act2 == ACT_NONE and scale == 1.0):
+        # out-conv-like: Y[v][tap*cout+co] = x[v] . w[co, :, tap] reads x once; the taps are summed afterwards
+        lib = _lib.require_device()
+        y = linear(a0, pc.tap_out, out_f32=True)
+        check(lib.b200_tap_sum(y.data_ptr(), y.shape[-1], pc.geom(a0.N, a0.D, a0.H, a0.W), pc.cout, _ptr(pc.bias),
+                               out_t.data_ptr(), out_t.shape[-1], DT_F32 if out_f32 else DT_BF16, _stream()),
+              "b200_tap_sum")
+        return out
     p = _conv_params(srcs, pc.w, pc.segs, pc.stride, out_t, od, pc.cout, DT_F32 if out_f32 else DT_BF16, pc.bias,
                      rowvec, act1, scale, None if residual is None else residual.t, DT_BF16, act2, impl=impl)
     igemm_raw(p)

@@ -170,6 +170,17 @@ int b200_axpy_bf16(const void* a, const void* b, float alpha, void* y, int64_t n
  * (materialises torch.cat([a, b], dim=1) only where a raw concatenated tensor is really needed). */
 int b200_copy_channels(const void* src, int32_t C, int32_t src_pitch, void* dst, int32_t dst_pitch, int32_t dst_off,
                        int64_t rows, void* stream);
+/* Tap reformulations for the degenerate convolutions at either end of the UNet (DiffusionModelUNet.conv_in with one
+ * input channel, .out[2] with one output channel; diffusion_model_unet.py:1744-1752, 1856-1867).
+ * geom = {N, D, H, W, OD, OH, OW, kd, kh, kw, sd, sh, sw, pd, ph, pw} (input extent, output extent, kernel, stride,
+ * low-side zero padding).
+ * tap_gather: out[v][tap*C + c] = x[in_voxel(v, tap)][c] (zero outside the input), v over N*OD*OH*OW, bf16 rows.
+ * tap_sum:    out[v][co] = bias[co] + sum_tap y[v + off(tap)][tap*cout + co], y fp32 rows over the INPUT grid
+ *             (stride 1, cout <= 4); out bf16 or fp32, columns [cout, out_pitch) zeroed. */
+int b200_tap_gather(const void* x, int32_t C, int32_t x_pitch, const int32_t* geom, void* out, int32_t out_pitch,
+                    void* stream);
+int b200_tap_sum(const float* y, int32_t y_pitch, const int32_t* geom, int32_t cout, const float* bias, void* out,
+                 int32_t out_pitch, int32_t out_dtype, void* stream);
 /* GEGLU: y[m, j] = x[m, j] * gelu_erf(x[m, H + j])  (monai MLPBlock act="GEGLU",
  * diffusion_model_unet.py:211). x: [M, 2H] pitch x_pitch; y: [M, H] pitch y_pitch. */
 int b200_geglu(const void* x, int64_t M, int32_t H, int32_t x_pitch, void* y, int32_t y_pitch,

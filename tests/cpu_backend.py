@@ -123,6 +123,48 @@ class FakeLib:
         bf16(y, n).copy_(out)
         return 0
 
+    @staticmethod
+    def _geom(g):
+        return [int(v) for v in (g if not hasattr(g, "_obj") else g._obj)][:16]
+
+    def b200_tap_gather(self, x, C_, xp, geom, out, op, stream):
+        N, D, H, W, OD, OH, OW, kd, kh, kw, sd, sh, sw, pd, ph, pw = self._geom(geom)
+        src = bf16(x, N * D * H * W * xp).view(N, D, H, W, xp)[..., :C_].float()
+        big = F.pad(src, (0, 0, pw, kw + sw * OW, ph, kh + sh * OH, pd, kd + sd * OD))     # generous high-side zeros
+        dst = bf16(out, N * OD * OH * OW * op).view(N, OD, OH, OW, op)
+        dst.zero_()
+        tap = 0
+        for a in range(kd):
+            for b in range(kh):
+                for c in range(kw):
+                    win = big[:, a:a + sd * OD:sd, b:b + sh * OH:sh, c:c + sw * OW:sw, :]
+                    dst[..., tap * C_:(tap + 1) * C_] = win.to(torch.bfloat16)
+                    tap += 1
+        return 0
+
+    def b200_tap_sum(self, y, yp, geom, cout, bias, out, op, odt, stream):
+        N, D, H, W, OD, OH, OW, kd, kh, kw, sd, sh, sw, pd, ph, pw = self._geom(geom)
+        yy = f32(y, N * D * H * W * yp).view(N, D, H, W, yp)
+        big = F.pad(yy, (0, 0, pw, kw + OW, ph, kh + OH, pd, kd + OD))
+        acc = torch.zeros(N, OD, OH, OW, cout)
+        if bias:
+            acc += f32(bias, cout)
+        tap = 0
+        for a in range(kd):
+            for b in range(kh):
+                for c in range(kw):
+                    acc += big[:, a:a + OD, b:b + OH, c:c + OW, tap * cout:(tap + 1) * cout]
+                    tap += 1
+        if odt == _lib.DT_BF16:
+            dst = bf16(out, N * OD * OH * OW * op).view(N, OD, OH, OW, op)
+            dst.zero_()
+            dst[..., :cout] = acc.to(torch.bfloat16)
+        else:
+            dst = f32(out, N * OD * OH * OW * op).view(N, OD, OH, OW, op)
+            dst.zero_()
+            dst[..., :cout] = acc
+        return 0
+
     def b200_copy_channels(self, src, C_, sp, dst, dp, off, rows, stream):
         bf16(dst, rows * dp).view(rows, dp)[:, off:off + C_] = bf16(src, rows * sp).view(rows, sp)[:, :C_]
         return 0

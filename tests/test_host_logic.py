@@ -67,6 +67,38 @@ def test_conv_host_logic(case):
     assert out.t[..., out.C:].abs().sum() == 0
 
 
+@pytest.mark.parametrize("sd,Cin,Cout,sp,k,s,p,kw", [
+    (3, 1, 16, (6, 7, 5), 3, 1, 1, {}), (2, 3, 24, (9, 8), 3, 1, 1, dict(act1=2)), (3, 2, 16, (8, 8, 6), 3, 2, 1, {}),
+    (3, 64, 1, (5, 6, 7), 3, 1, 1, dict(out_f32=True)), (2, 72, 3, (9, 7), 3, 1, 1, {}), (3, 64, 2, (4, 4, 4), 3, 1, 1, {}),
+])
+def test_tap_reformulations_host_logic(monkeypatch, sd, Cin, Cout, sp, k, s, p, kw):
+    """conv_in-like (few input channels -> b200_tap_gather + one-chunk GEMM) and out-conv-like (few output channels ->
+    1x1 GEMM with taps as columns + b200_tap_sum) routes of ops.conv against F.conv (diffusion_model_unet.py:1744-1752,
+    1856-1867), forced on for small shapes."""
+    from tests import cpu_backend
+    cpu_backend.install(monkeypatch)
+    monkeypatch.setattr(ops, "_TAP_MIN_ROWS", 1)
+    torch.manual_seed(3)
+    x = torch.randn(2, Cin, *sp)
+    w = torch.randn(Cout, Cin, *([k] * sd)) / math.sqrt(Cin * k ** sd)
+    b = torch.randn(Cout)
+    pc = ops.PackedConv(w, b, s, p)
+    assert (pc.tap_in is not None) == (Cin * k ** sd <= 64) and (pc.tap_out is not None) == (Cout <= 4 and Cin >= 64)
+    conv = F.conv2d if sd == 2 else F.conv3d
+    ref = conv(bf(x), bf(w), b, stride=s, padding=p)
+    if kw.get("act1") == 2:
+        ref = F.silu(ref)
+    out = ops.conv(cl_cpu(x), pc, **kw)
+    if kw.get("out_f32"):
+        got = out[..., :Cout].movedim(-1, 1)
+        assert out[..., Cout:].abs().sum() == 0
+    else:
+        got = back(out)
+        assert out.t[..., out.C:].abs().sum() == 0
+    assert tuple(got.shape) == tuple(ref.shape)
+    close(got, ref)
+
+
 def test_asym_pad_host_logic():
     for sd, sp in ((2, (8, 10)), (3, (4, 6, 5))):
         x = torch.randn(1, 16, *sp)

@@ -105,6 +105,43 @@ def test_conv(cuda_device, case, impl):
     assert_close(got, ref, 1e-2, f"conv {case} impl={impl}")
 
 
+@pytest.mark.parametrize("sd,N,Cin,Cout,sp,s", [
+    (3, 1, 1, 256, (40, 36, 44), 1), (2, 2, 3, 64, (200, 190), 1), (3, 2, 2, 32, (65, 60, 81), 2),
+    (3, 1, 256, 1, (40, 36, 44), 1), (2, 2, 128, 3, (200, 190), 1), (3, 1, 64, 4, (20, 30, 61), 1),
+])
+def test_conv_tap_reformulations(cuda_device, sd, N, Cin, Cout, sp, s):
+    """Degenerate ends of the UNet above the row threshold: conv_in-like layers go through b200_tap_gather + a
+    one-chunk GEMM, out-conv-like layers through a 1x1 GEMM (taps as columns) + b200_tap_sum; compared with F.conv
+    and with the plain 27-tap implicit GEMM (the CUDA-core cross-check implementation, impl=1)."""
+    ops = _ops()
+    torch.manual_seed(13)
+    x = torch.randn(N, Cin, *sp)
+    w = torch.randn(Cout, Cin, *([3] * sd)) / math.sqrt(Cin * 3 ** sd)
+    b = torch.randn(Cout)
+    conv = F.conv2d if sd == 2 else F.conv3d
+    ref = conv(bf(x), bf(w), b, stride=s, padding=1)
+    pc = ops.PackedConv(w.cuda(), b.cuda(), s, 1)
+    assert (pc.tap_in is not None) != (pc.tap_out is not None)
+    xc = ops.to_cl(x.cuda())
+    rows = ref.numel() // Cout
+    assert rows >= ops._TAP_MIN_ROWS
+    got = ops.from_cl(ops.conv(xc, pc))
+    assert tuple(got.shape) == tuple(ref.shape)
+    assert_close(got, ref, 1e-2, "tap-reformulated conv vs F.conv")
+    plain = ops.from_cl(ops.conv(xc, pc, impl=1))
+    assert_close(got, plain, 1e-2, "tap-reformulated conv vs plain implicit GEMM")
+    if pc.tap_out is not None:
+        o32 = ops.conv(xc, pc, out_f32=True)
+        assert_close(ops.from_cl_f32(o32, Cout, sd), ref, 3e-3, "tap_sum fp32 output")
+        assert o32[..., Cout:].abs().sum().item() == 0
+    else:
+        temb = torch.randn(N, Cout)
+        res = torch.randn_like(ref)
+        o = ops.conv(xc, pc, rowvec=temb.cuda(), act1=ops.ACT_SILU, residual=ops.to_cl(res.cuda()))
+        ref2 = bf(res) + F.silu(ref + temb.view(N, Cout, *([1] * sd)))
+        assert_close(ops.from_cl(o), ref2, 1e-2, "tap_gather conv with fused epilogue")
+
+
 def test_conv_asym_pad(cuda_device):
     """AutoencoderKL Downsample: F.pad (0,1) per dim then k3 s2 p0 (autoencoderkl.py:107-120)."""
     ops = _ops()
