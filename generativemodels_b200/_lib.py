@@ -45,6 +45,7 @@ class IgemmParams(C.Structure):
         ("res_ptr", C.c_void_p), ("res_dtype", C.c_int32),
         ("res_sN", C.c_int64), ("res_sD", C.c_int64), ("res_sH", C.c_int64), ("res_sW", C.c_int64),
         ("act2", C.c_int32), ("stat_ptr", C.c_void_p), ("impl", C.c_int32),
+        ("gn_partial", C.c_void_p), ("gn_slots", C.c_int32), ("gn_slot0", C.c_int32),
     ]
 
 
@@ -105,6 +106,7 @@ SIGNATURES = {
     "b200_igemm": [C.POINTER(IgemmParams), _P],
     "b200_groupnorm_workspace_bytes": [_I32, _I64, _I32],
     "b200_groupnorm_stats": [C.POINTER(GnStatsParams), _P],
+    "b200_groupnorm_from_partials": [C.POINTER(GnStatsParams), _P, _P, _P],
     "b200_groupnorm_apply": [C.POINTER(GnApplyParams), _P],
     "b200_layernorm": [_P, _I64, _I32, _I32, _P, _P, _F, _P, _I32, _P],
     "b200_nchw_to_nhwc": [_P, _I32, _I32, _I64, _P, _I32, _P],

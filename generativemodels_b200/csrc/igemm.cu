@@ -59,6 +59,8 @@ struct IgemmDev {
   void* out_ptr;
   int out_dtype, cout, out_cols, out_vec, out_staged, out_v256;
   float* stat_ptr;          // optional [rows][tiles_n][2] (max, sum exp) per row and column tile
+  float* gn_partial;        // optional [N][gn_slots][cout/8][2] (sum, sum of squares) of the bf16 outputs, 8-channel groups
+  int gn_slots, gn_slot0;
   long long out_sN, out_sD, out_sH, out_sW;
   const float* bias;
   const float* rowvec;
@@ -333,7 +335,7 @@ __device__ __forceinline__ void load_res_fast(const IgemmDev& p, uint4* rv, long
 }
 template <int CH>
 __device__ __forceinline__ void epilogue_fast(const IgemmDev& p, const uint32_t* raw, const float* addv,
-                                              const uint4* rv, long long out_off, int col0) {
+                                              const uint4* rv, long long out_off, int col0, float* gs) {
   float v[CH];
 #pragma unroll
   for (int j = 0; j < CH; j += 4) {
@@ -360,12 +362,26 @@ __device__ __forceinline__ void epilogue_fast(const IgemmDev& p, const uint32_t*
   act_inplace<CH>(v, p.act2);
   if (p.out_dtype == B200_DT_BF16) {
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out_ptr) + out_off + col0;
+    uint4 pk[CH / 8];
+#pragma unroll
+    for (int g = 0; g < CH / 8; ++g) pk[g] = pack8(v + g * 8);
     if (p.out_v256) {
 #pragma unroll
-      for (int g = 0; g < CH / 16; ++g) stg256(o + g * 16, pack8(v + g * 16), pack8(v + g * 16 + 8));
+      for (int g = 0; g < CH / 16; ++g) stg256(o + g * 16, pk[2 * g], pk[2 * g + 1]);
     } else {
 #pragma unroll
-      for (int g = 0; g < CH / 8; ++g) *reinterpret_cast<uint4*>(o + g * 8) = pack8(v + g * 8);
+      for (int g = 0; g < CH / 8; ++g) *reinterpret_cast<uint4*>(o + g * 8) = pk[g];
+    }
+    if constexpr (CH == 32) {
+      if (gs) {   // GroupNorm partials of the values as stored (bf16-rounded), one 8-channel group per 16-byte vector
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float f[8];
+          unpack8(pk[g], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { gs[g] += f[j]; gs[4 + g] = fmaf(f[j], f[j], gs[4 + g]); }
+        }
+      }
     }
   } else {
     float* o = reinterpret_cast<float*>(p.out_ptr) + out_off + col0;
@@ -536,6 +552,25 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
     int add_key = -1;
     const bool fast_ok = p.out_vec && !p.out_staged && !p.stat_ptr && !p.row_bias &&
                          (!p.res_ptr || (p.res_vec && p.res_dtype == B200_DT_BF16));
+    // GroupNorm partial sums for the consumer of this tensor: per warp [BN/8 groups][sum, sumsq] in shared memory
+    // (aliases the staged-store tiles, which this mode excludes), flushed to this warp's private global slot
+    // whenever the (sample, column tile) changes and at the end — deterministic, no atomics.
+    float* gacc = stage_tiles + (warp - 2) * (32 * 33);
+    const bool gn_on = (p.gn_partial != nullptr);
+    int gn_nb = -1, gn_n0 = 0;
+    auto gn_flush = [&]() {
+      if (gn_nb >= 0) {
+        float* dst = p.gn_partial +
+                     (((long long)gn_nb * p.gn_slots + p.gn_slot0 + blockIdx.x * 4 + (warp - 2)) * (p.cout >> 3)) * 2 +
+                     (gn_n0 >> 3) * 2;
+        for (int e = lane; e < (BN >> 3) * 2; e += 32) {
+          if (gn_n0 + (e >> 1) * 8 < p.cout) dst[e] += gacc[e];
+        }
+      }
+      for (int e = lane; e < (BN >> 3) * 2; e += 32) gacc[e] = 0.f;
+      __syncwarp();
+    };
+    if (gn_on) gn_flush();
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       int t = tile;
@@ -551,6 +586,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
       const int n0 = nt * BN;
 
       if (fast_ok && add_key != nb * p.tiles_n + nt) {
+        if (gn_on) { gn_flush(); gn_nb = nb; gn_n0 = n0; }
         // bias + per-sample row vector of this (sample, column tile): shared by all rows, refreshed only on change
         add_key = nb * p.tiles_n + nt;
         __syncwarp();
@@ -583,7 +619,35 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
           if constexpr (CH == 32) tmem_ld32(taddr + c0, raw);
           else tmem_ld16(taddr + c0, raw);
           tmem_ld_wait();
-          if (row_ok) epilogue_fast<CH>(p, raw, addv + c0, rv, out_off, n0 + c0);
+          float gs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          if (row_ok) epilogue_fast<CH>(p, raw, addv + c0, rv, out_off, n0 + c0, gn_on ? gs : nullptr);
+          if constexpr (CH == 32) {
+            if (gn_on) {
+              // 8 values x 32 lanes -> one total per lane: transpose-reduce over lane bits 4,3,2, butterfly over 1,0;
+              // the lane then holds statistic (lane >> 4) of group 2 * bit3 + bit2 of this 32-column chunk
+              float a[4], b[2];
+              bool hi = (lane & 16) != 0;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float send = hi ? gs[i] : gs[4 + i], keep = hi ? gs[4 + i] : gs[i];
+                a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+              }
+              hi = (lane & 8) != 0;
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                const float send = hi ? a[i] : a[2 + i], keep = hi ? a[2 + i] : a[i];
+                b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+              }
+              hi = (lane & 4) != 0;
+              float c = (hi ? b[1] : b[0]) + __shfl_xor_sync(0xffffffffu, hi ? b[0] : b[1], 4);
+              c += __shfl_xor_sync(0xffffffffu, c, 2);
+              c += __shfl_xor_sync(0xffffffffu, c, 1);
+              if ((lane & 3) == 0) {
+                const int grp = (c0 >> 3) + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                gacc[grp * 2 + (lane >> 4)] += c;
+              }
+            }
+          }
           continue;
         }
         uint32_t raw[CH];
@@ -621,6 +685,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(buf));
     }
+    if (gn_on) { __syncwarp(); gn_flush(); }
   }
 
   tcgen05_fence_before();
@@ -724,6 +789,28 @@ static TileShape choose_tile(int OW, int OH, int OD, int sw, int sh, int sd) {
   return bt;
 }
 
+// GroupNorm partials for the cross-check implementation: (sum, sumsq) of the stored bf16 outputs per 8-channel
+// group, accumulated into slot gn_slot0 (fp32 atomics: test path only).
+__global__ void gn8_partial_check_kernel(const __grid_constant__ IgemmDev p) {
+  const long long rows = (long long)p.N * p.OD * p.OH * p.OW;
+  const int groups = p.cout >> 3;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * groups) return;
+  const int g = (int)(idx % groups);
+  long long m = idx / groups;
+  const int ow = (int)(m % p.OW); m /= p.OW;
+  const int oh = (int)(m % p.OH); m /= p.OH;
+  const int od = (int)(m % p.OD); m /= p.OD;
+  const int nb = (int)m;
+  const __nv_bfloat16* o = reinterpret_cast<const __nv_bfloat16*>(p.out_ptr) + nb * p.out_sN + od * p.out_sD +
+                           oh * p.out_sH + ow * p.out_sW + g * 8;
+  float s = 0.f, q = 0.f;
+  for (int j = 0; j < 8; ++j) { const float f = __bfloat162float(o[j]); s += f; q = fmaf(f, f, q); }
+  float* dst = p.gn_partial + (((long long)nb * p.gn_slots + p.gn_slot0) * groups + g) * 2;
+  atomicAdd(dst, s);
+  atomicAdd(dst + 1, q);
+}
+
 template <int BN, int STAGES>
 static int launch_tc(const IgemmDev& d, cudaStream_t stream) {
   constexpr int kStageBytes = kABytes + BN * kBK * 2;
@@ -821,6 +908,13 @@ extern "C" int b200_igemm(const b200_igemm_params* p, void* stream_v) {
     const long long esz = (p->out_dtype == B200_DT_BF16) ? 2 : 4;
     d.out_staged = (p->out_sW * esz > 2048) ? 1 : 0;
   }
+  d.gn_partial = p->gn_partial; d.gn_slots = p->gn_slots; d.gn_slot0 = p->gn_slot0;
+  if (p->gn_partial) {
+    // the partials ride on the vectorised epilogue: every column chunk must be a full 32-wide bf16 vector chunk
+    B200_CHECK_ARG(p->out_dtype == B200_DT_BF16 && p->cout % 32 == 0 && d.out_vec && !d.out_staged && !p->stat_ptr &&
+                   !p->row_bias && p->gn_slot0 >= 0 && p->gn_slot0 + 4 * sm_count() <= p->gn_slots,
+                   "igemm: gn_partial needs a bf16 vector-aligned output with cout %% 32 == 0 and 4 x SM-count slots");
+  }
   d.stat_ptr = p->stat_ptr;
   if (p->stat_ptr)
     B200_CHECK_ARG(p->out_N == 1 && p->out_D == 1 && p->out_H == 1, "igemm: stat_ptr needs a GEMM-shaped call");
@@ -831,6 +925,8 @@ extern "C" int b200_igemm(const b200_igemm_params* p, void* stream_v) {
     d.res_v256 = d.res_vec && p->res_dtype == B200_DT_BF16 && (p->out_cols % 16 == 0) && (p->res_sN % 16 == 0) &&
                  (p->res_sD % 16 == 0) && (p->res_sH % 16 == 0) && (p->res_sW % 16 == 0) &&
                  (((uintptr_t)p->res_ptr) % 32 == 0);
+    B200_CHECK_ARG(!p->gn_partial || (d.res_vec && p->res_dtype == B200_DT_BF16),
+                   "igemm: gn_partial needs a vector-aligned bf16 residual");
   }
 
   const int impl = p->impl ? p->impl : env_impl();
@@ -842,6 +938,11 @@ extern "C" int b200_igemm(const b200_igemm_params* p, void* stream_v) {
     B200_CHECK_ARG(blocks < (1ll << 31), "igemm(check): problem too large");
     igemm_check_kernel<<<(unsigned)blocks, threads, 0, stream>>>(d);
     B200_LAUNCH_CHECK("igemm_check_kernel");
+    if (d.gn_partial) {
+      const long long tot = rows * (d.cout >> 3);
+      gn8_partial_check_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(d);
+      B200_LAUNCH_CHECK("gn8_partial_check_kernel");
+    }
     return B200_OK;
   }
 

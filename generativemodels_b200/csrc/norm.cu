@@ -123,6 +123,61 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, int chunks
   }
 }
 
+
+// ---- finalize from igemm-epilogue partials ----------------------------------------------------------
+// partial_i[n][slot][C_i/8][2]; consumer group g spans cpg channels = cpg/8 producer groups of one source.
+__global__ void gn_finalize_partials_kernel(const float* __restrict__ p0, const float* __restrict__ p1, int slots0,
+                                            int slots1, int C0, int C1, int groups, long long spatial, float eps,
+                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                            float* __restrict__ affine) {
+  const int g = blockIdx.x, n = blockIdx.y;
+  const int C = C0 + C1;
+  const int cpg = C / groups;
+  const int c_first = g * cpg;
+  const float* src;
+  int slots, g8_total, g8_first;
+  if (c_first < C0) { src = p0; slots = slots0; g8_total = C0 >> 3; g8_first = c_first >> 3; }
+  else { src = p1; slots = slots1; g8_total = C1 >> 3; g8_first = (c_first - C0) >> 3; }
+  const int sub = cpg >> 3;
+  double s = 0.0, q = 0.0;
+  for (int i = threadIdx.x; i < slots * sub; i += blockDim.x) {
+    const int slot = i / sub, j = i - slot * sub;
+    const float* e = src + (((long long)n * slots + slot) * g8_total + g8_first + j) * 2;
+    s += (double)e[0];
+    q += (double)e[1];
+  }
+  __shared__ double ss[32], sq[32];
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { ss[w] = s; sq[w] = q; }
+  __syncthreads();
+  if (w == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    s = l < nw ? ss[l] : 0.0;
+    q = l < nw ? sq[l] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (l == 0) { ss[0] = s; sq[0] = q; }
+  }
+  __syncthreads();
+  const double cnt = (double)spatial * cpg;
+  const double mean = ss[0] / cnt;
+  double var = sq[0] / cnt - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  for (int j = threadIdx.x; j < cpg; j += blockDim.x) {
+    const int c = c_first + j;
+    const float a = rstd * gamma[c];
+    affine[((long long)n * C + c) * 2 + 0] = a;
+    affine[((long long)n * C + c) * 2 + 1] = beta[c] - (float)mean * a;
+  }
+}
+
 // ---- apply --------------------------------------------------------------------------------------
 // grid = (chunks, N); block = CV * rows threads.  A thread owns one 8-channel vector for its whole slab, so its
 // affine pairs live in registers and the inner loop is: 128-bit load, 8 FMA, 8 SiLU, 128-bit store (no index
@@ -290,6 +345,23 @@ extern "C" int b200_groupnorm_stats(const b200_gn_stats_params* p, void* stream_
   gn_finalize_kernel<<<dim3(p->groups, p->N), 128, 0, stream>>>(p->partial, chunks, C, p->groups, p->spatial, p->eps,
                                                                 p->gamma, p->beta, p->affine);
   B200_LAUNCH_CHECK("gn_finalize_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_groupnorm_from_partials(const b200_gn_stats_params* p, const float* const partial[2],
+                                            const int32_t slots[2], void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(p && partial && slots && partial[0] && p->gamma && p->beta && p->affine, "groupnorm_from_partials: null pointer");
+  const int C0 = p->x_C[0], C1 = partial[1] ? p->x_C[1] : 0;
+  const int C = C0 + C1;
+  B200_CHECK_ARG(p->N >= 1 && p->spatial >= 1 && p->groups >= 1 && C % p->groups == 0, "groupnorm_from_partials: bad shape");
+  const int cpg = C / p->groups;
+  B200_CHECK_ARG(cpg % 8 == 0 && C0 % cpg == 0 && C0 % 8 == 0 && C1 % 8 == 0 && slots[0] >= 1 && (!C1 || slots[1] >= 1),
+                 "groupnorm_from_partials: groups of %d channels do not tile the 8-channel partials", cpg);
+  dim3 grid(p->groups, p->N);
+  gn_finalize_partials_kernel<<<grid, 256, 0, stream>>>(partial[0], partial[1], slots[0], C1 ? slots[1] : 0, C0, C1,
+                                                        p->groups, p->spatial, p->eps, p->gamma, p->beta, p->affine);
+  B200_LAUNCH_CHECK("gn_finalize_partials_kernel");
   return B200_OK;
 }
 

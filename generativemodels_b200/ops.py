@@ -40,6 +40,8 @@ class CL:
     t: torch.Tensor
     C: int
     spatial_dims: int = 2
+    # GroupNorm partial sums the producing convolution left behind: fp32 [N, slots, C/8, 2] (see b200_igemm gn_partial)
+    gn: torch.Tensor | None = None
 
     @property
     def N(self) -> int: return self.t.shape[0]
@@ -286,16 +288,38 @@ def conv_upsample2x(src: CL, pu: PackedUpsampleConv, impl: int = 0) -> CL:
     P = out.pitch
     full = (od[0] * od[1] * od[2] * P, od[1] * od[2] * P, od[2] * P, P)
     sdd = 2 if sd == 3 else 1
-    for (r, w, segs) in pu.phases:
+    part = _gn_partial_for(out, src.N * src.D * src.H * src.W, 8, launches=len(pu.phases))
+    for i, (r, w, segs) in enumerate(pu.phases):
         off = r[0] * full[1] + r[1] * full[2] + r[2] * full[3]
         strides = (full[0], full[1] * sdd, full[2] * 2, full[3] * 2)
         p = _conv_params([src], w, segs, (1, 1, 1), out.t, (src.D, src.H, src.W), pu.cout, DT_BF16, pu.bias, None,
                          ACT_NONE, 1.0, None, DT_BF16, ACT_NONE, out_elem_off=off, out_strides=strides, impl=impl)
+        if part is not None:          # every phase launch owns its own range of slots
+            p.gn_partial, p.gn_slots, p.gn_slot0 = part.data_ptr(), part.shape[1], i * _gn_slots()
         igemm_raw(p)
     return out
 
 
 _TAP_MIN_ROWS = 1 << 15       # below this the extra launch costs more than the padded implicit GEMM
+_GN_FUSE_MIN_ROWS = 1 << 15   # below this a separate statistics pass is cheaper than the zero-fill + wider reduce
+_GN_FUSE = True
+_SM_COUNT = None
+
+
+def _gn_slots(launches: int = 1) -> int:
+    global _SM_COUNT
+    if _SM_COUNT is None:
+        _SM_COUNT = int(_lib.require_device().b200_sm_count())
+    return 4 * _SM_COUNT * launches
+
+
+def _gn_partial_for(out: CL, rows: int, n_seg: int, launches: int = 1) -> torch.Tensor | None:
+    """Zero-filled partial-sum buffer if this output is worth instrumenting: a heavy (>= 8 tap) convolution writing a
+    large bf16 tensor whose channel count tiles the 32-column epilogue chunks."""
+    if not _GN_FUSE or rows < _GN_FUSE_MIN_ROWS or n_seg < 8 or out.C % 32 != 0 or out.pitch != out.C:
+        return None
+    out.gn = torch.zeros((out.N, _gn_slots(launches), out.C // 8, 2), dtype=torch.float32, device=out.t.device)
+    return out.gn
 
 
 # --------------------------------------------------------------------------------------------------
@@ -407,6 +431,10 @@ def conv(srcs: CL | Sequence[CL], pc: PackedConv, *, rowvec: torch.Tensor | None
         return out
     p = _conv_params(srcs, pc.w, pc.segs, pc.stride, out_t, od, pc.cout, DT_F32 if out_f32 else DT_BF16, pc.bias,
                      rowvec, act1, scale, None if residual is None else residual.t, DT_BF16, act2, impl=impl)
+    if not out_f32:
+        part = _gn_partial_for(out, rows, len(pc.segs))
+        if part is not None:
+            p.gn_partial, p.gn_slots, p.gn_slot0 = part.data_ptr(), part.shape[1], 0
     igemm_raw(p)
     return out
 
@@ -465,7 +493,6 @@ def groupnorm(srcs: CL | Sequence[CL], groups: int, eps: float, gamma: torch.Ten
     if Ct % groups != 0:
         raise ValueError(f"GroupNorm: {Ct} channels not divisible by {groups} groups")
     dev = a0.t.device
-    ws = torch.empty(lib.b200_groupnorm_workspace_bytes(a0.N, a0.spatial, Ct) // 4, dtype=torch.float32, device=dev)
     affine = torch.empty((a0.N, Ct, 2), dtype=torch.float32, device=dev)
     sp = GnStatsParams()
     ap = GnApplyParams()
@@ -479,8 +506,17 @@ def groupnorm(srcs: CL | Sequence[CL], groups: int, eps: float, gamma: torch.Ten
     g32 = gamma if gamma.dtype == torch.float32 else gamma.float()
     b32 = beta if beta.dtype == torch.float32 else beta.float()
     sp.gamma, sp.beta = g32.data_ptr(), b32.data_ptr()
-    sp.partial, sp.affine = ws.data_ptr(), affine.data_ptr()
-    check(lib.b200_groupnorm_stats(C.byref(sp), _stream()), "b200_groupnorm_stats")
+    sp.affine = affine.data_ptr()
+    cpg = Ct // groups
+    if _GN_FUSE and all(a.gn is not None for a in srcs) and cpg % 8 == 0 and srcs[0].C % cpg == 0:
+        # the producers already summed their outputs (8-channel groups) while writing them: no pass over the data
+        parts = (C.c_void_p * 2)(*[a.gn.data_ptr() for a in srcs], *([None] * (2 - len(srcs))))
+        slots = (C.c_int32 * 2)(*[a.gn.shape[1] for a in srcs], *([0] * (2 - len(srcs))))
+        check(lib.b200_groupnorm_from_partials(C.byref(sp), parts, slots, _stream()), "b200_groupnorm_from_partials")
+    else:
+        ws = torch.empty(lib.b200_groupnorm_workspace_bytes(a0.N, a0.spatial, Ct) // 4, dtype=torch.float32, device=dev)
+        sp.partial = ws.data_ptr()
+        check(lib.b200_groupnorm_stats(C.byref(sp), _stream()), "b200_groupnorm_stats")
     out = a0.like(Ct)
     ap.affine, ap.act = affine.data_ptr(), act
     ap.y_ptr, ap.y_pitch = out.t.data_ptr(), out.pitch
@@ -526,6 +562,7 @@ def axpy(a: CL, b: CL, alpha: float = 1.0, inplace: bool = False) -> CL:
     if a.t.shape != b.t.shape:
         raise ValueError(f"axpy shape mismatch {tuple(a.t.shape)} vs {tuple(b.t.shape)}")
     out = a if inplace else a.like()
+    out.gn = None
     check(lib.b200_axpy_bf16(a.t.data_ptr(), b.t.data_ptr(), alpha, out.t.data_ptr(), a.t.numel(), _stream()),
           "b200_axpy_bf16")
     return out

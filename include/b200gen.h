@@ -106,6 +106,13 @@ typedef struct {
   float*  stat_ptr;     /* optional softmax partials: [out_W][ceil(out_cols/256)][2] = (max, sum exp(v - max)) of every
                            256-column tile of every output row (GEMM-shaped calls only); NULL to skip            */
   int32_t impl;         /* 0 = tcgen05 kernel, 1 = CUDA-core cross-check kernel  */
+  /* Optional GroupNorm partial sums for whoever normalises this output next (nn.GroupNorm after every conv of the
+   * ResnetBlock, diffusion_model_unet.py:623-684): gn_partial[n][slot][cout/8][2] += (sum, sum of squares) of the
+   * stored bf16 values per 8-channel group; the kernel uses slots [gn_slot0, gn_slot0 + 4 * SM count) of the
+   * gn_slots per sample, the caller zero-fills the buffer and b200_groupnorm_from_partials reduces it.
+   * Needs a bf16, 16-byte-aligned output with cout % 32 == 0.  NULL to skip. */
+  float*  gn_partial;
+  int32_t gn_slots, gn_slot0;
 } b200_igemm_params;
 
 int b200_igemm(const b200_igemm_params* p, void* stream);
@@ -131,6 +138,12 @@ typedef struct {
 } b200_gn_stats_params;
 int64_t b200_groupnorm_workspace_bytes(int32_t N, int64_t spatial, int32_t C_total);
 int b200_groupnorm_stats(const b200_gn_stats_params* p, void* stream);
+/* The same affine table from partial sums that b200_igemm left while it wrote the tensor(s) (see gn_partial there),
+ * so the statistics pass over the activations disappears: source i contributes partial[i] = [N][slots[i]][x_C[i]/8][2].
+ * x_ptr of p is not read; every group of the virtual concat must be a whole number of 8-channel producer groups
+ * inside one source ((C0+C1)/groups % 8 == 0 and C0 % ((C0+C1)/groups) == 0). */
+int b200_groupnorm_from_partials(const b200_gn_stats_params* p, const float* const partial[2],
+                                 const int32_t slots[2], void* stream);
 
 typedef struct {
   const void* x_ptr[2];

@@ -85,6 +85,30 @@ class FakeLib:
         f32(p.affine, N * Cc * 2).view(N, Cc, 2).copy_(torch.stack([a, b], -1))
         return 0
 
+    def b200_groupnorm_from_partials(self, p, partial, slots, stream):
+        p = _obj(p)
+        ptrs = [int(v) if v else 0 for v in partial]
+        sl = [int(v) for v in slots]
+        N, G = p.N, p.groups
+        Cs = [p.x_C[0]] + ([p.x_C[1]] if ptrs[1] else [])
+        Cc = sum(Cs)
+        cpg = Cc // G
+        assert cpg % 8 == 0 and Cs[0] % cpg == 0
+        sums = []
+        for ptr, nslot, Ci in zip(ptrs, sl, Cs):
+            part = f32(ptr, N * nslot * (Ci // 8) * 2).view(N, nslot, Ci // 8, 2).double().sum(1)     # [N, Ci/8, 2]
+            sums.append(part.view(N, Ci // cpg, cpg // 8, 2).sum(2))
+        tot = torch.cat(sums, 1)                                                                      # [N, G, 2]
+        cnt = float(p.spatial) * cpg
+        mean = tot[..., 0] / cnt
+        var = (tot[..., 1] / cnt - mean * mean).clamp_min(0)
+        rstd = (var + p.eps).rsqrt()
+        gamma, beta = f32(p.gamma, Cc), f32(p.beta, Cc)
+        a = rstd.float().repeat_interleave(cpg, 1) * gamma
+        b = beta - mean.float().repeat_interleave(cpg, 1) * a
+        f32(p.affine, N * Cc * 2).view(N, Cc, 2).copy_(torch.stack([a, b], -1))
+        return 0
+
     def b200_groupnorm_apply(self, p, stream):
         p = _obj(p)
         x = self._gather_src(p)
@@ -192,6 +216,9 @@ class FakeLib:
         dst.zero_()
         dst[:, :S] = (torch.exp(sc - mx[:, None]) / den[:, None]).to(torch.bfloat16)
         return 0
+
+    def b200_sm_count(self):
+        return 2
 
     def b200_attention_flash_workspace_bytes(self, a):
         return 0

@@ -99,6 +99,52 @@ def test_tap_reformulations_host_logic(monkeypatch, sd, Cin, Cout, sp, k, s, p, 
     close(got, ref)
 
 
+def test_groupnorm_from_conv_partials_host_logic(monkeypatch):
+    """GroupNorm statistics taken from the partial sums the producing convolutions leave behind (b200_igemm gn_partial
+    -> b200_groupnorm_from_partials) against the ordinary two-pass GroupNorm: single source, virtual concat of two
+    producers with different channel counts (groups of 24 = 3 producer groups), the 8-phase upsample convolution,
+    and invalidation by an in-place update."""
+    from tests import cpu_backend
+    cpu_backend.install(monkeypatch)
+    monkeypatch.setattr(ops, "_GN_FUSE_MIN_ROWS", 1)
+    torch.manual_seed(5)
+    x = torch.randn(2, 16, 5, 6, 4)
+    mk = lambda co, ci: ops.PackedConv(torch.randn(co, ci, 3, 3, 3) / math.sqrt(ci * 27), torch.randn(co), 1, 1)
+    a = ops.conv(cl_cpu(x), mk(64, 16))
+    b = ops.conv(cl_cpu(x), mk(32, 16))
+    assert a.gn is not None and tuple(a.gn.shape) == (2, ops._gn_slots(), 8, 2) and b.gn is not None
+
+    def both(srcs, groups):
+        Ct = sum(t.C for t in srcs)
+        g, be = torch.randn(Ct), torch.randn(Ct)
+        fused = ops.groupnorm(srcs, groups, 1e-5, g, be, act=ops.ACT_SILU)
+        monkeypatch.setattr(ops, "_GN_FUSE", False)
+        plain = ops.groupnorm(srcs, groups, 1e-5, g, be, act=ops.ACT_SILU)
+        monkeypatch.setattr(ops, "_GN_FUSE", True)
+        close(back(fused), back(plain), 1e-2)
+        ref = F.silu(F.group_norm(torch.cat([back(t) for t in srcs], 1), groups, g, be, 1e-5))
+        close(back(fused), ref, 1e-2)
+
+    calls = []
+    real = cpu_backend.FakeLib.b200_groupnorm_from_partials
+    monkeypatch.setattr(cpu_backend.FakeLib, "b200_groupnorm_from_partials",
+                        lambda self, *args: (calls.append(1), real(self, *args))[1])
+    both([a], 8)                  # 8 channels per group = one producer group
+    both([a], 2)                  # 32 channels per group
+    both([a, b], 4)               # concat 96 channels, groups of 24 (64 % 24 != 0 -> falls back to the full pass)
+    assert len(calls) == 2
+    both([a, b], 6)               # groups of 16: 4 groups in a, 2 in b -> fused
+    assert len(calls) == 3
+    up = ops.conv_upsample2x(a, ops.PackedUpsampleConv(torch.randn(32, 64, 3, 3, 3) / 40, torch.randn(32)))
+    assert up.gn is not None and up.gn.shape[1] == 8 * ops._gn_slots()
+    both([up], 4)
+    assert len(calls) == 4
+    c = ops.axpy(a, a, 0.5, inplace=True)
+    assert c.gn is None           # an in-place update invalidates the producer's sums
+    both([c], 8)
+    assert len(calls) == 4
+
+
 def test_asym_pad_host_logic():
     for sd, sp in ((2, (8, 10)), (3, (4, 6, 5))):
         x = torch.randn(1, 16, *sp)

@@ -142,6 +142,47 @@ def test_conv_tap_reformulations(cuda_device, sd, N, Cin, Cout, sp, s):
         assert_close(ops.from_cl(o), ref2, 1e-2, "tap_gather conv with fused epilogue")
 
 
+@pytest.mark.parametrize("impl", [0, 1], ids=["tcgen05", "check"])
+def test_conv_groupnorm_partials(cuda_device, monkeypatch, impl):
+    """The epilogue's GroupNorm partial sums (b200_igemm gn_partial): per-sample (sum, sumsq) of the stored bf16 outputs
+    per 8-channel group, for a plain conv with residual, a 512-channel conv (two 256-column tiles), a two-sample
+    batch and the 8-phase upsample conv; then GroupNorm from those partials against the two-pass GroupNorm."""
+    ops = _ops()
+    monkeypatch.setattr(ops, "_GN_FUSE_MIN_ROWS", 1)
+    torch.manual_seed(17)
+
+    def check_partials(out):
+        t = out.t.float().cpu()[..., :out.C]                                  # [N, D, H, W, C]
+        g = t.reshape(t.shape[0], -1, out.C // 8, 8).double()
+        want = torch.stack([g.sum((1, 3)), (g * g).sum((1, 3))], -1)        # [N, C/8, 2]
+        got = out.gn.double().sum(1).cpu()
+        err = (got - want).abs() / (want.abs() + 1.0)
+        assert err.max().item() < 2e-4, err.max().item()
+
+    def gn_both(srcs, groups):
+        Ct = sum(a.C for a in srcs)
+        g, b = torch.randn(Ct).cuda(), torch.randn(Ct).cuda()
+        fused = ops.from_cl(ops.groupnorm(srcs, groups, 1e-6, g, b, act=ops.ACT_SILU))
+        monkeypatch.setattr(ops, "_GN_FUSE", False)
+        plain = ops.from_cl(ops.groupnorm(srcs, groups, 1e-6, g, b, act=ops.ACT_SILU))
+        monkeypatch.setattr(ops, "_GN_FUSE", True)
+        assert_close(fused, plain.float().cpu(), 1e-2, "GroupNorm from conv partials vs two-pass")
+
+    x = ops.to_cl(torch.randn(2, 64, 9, 20, 17).cuda())
+    mk = lambda co, ci: ops.PackedConv((torch.randn(co, ci, 3, 3, 3) / math.sqrt(ci * 27)).cuda(), torch.randn(co).cuda(), 1, 1)
+    res = ops.to_cl(torch.randn(2, 256, 9, 20, 17).cuda())
+    a = ops.conv(x, mk(256, 64), rowvec=torch.randn(2, 256).cuda(), act1=ops.ACT_NONE, residual=res, impl=impl)
+    b = ops.conv(x, mk(512, 64), impl=impl)
+    assert a.gn is not None and b.gn is not None
+    check_partials(a)
+    check_partials(b)
+    gn_both([a], 32)
+    gn_both([b, a], 32)           # 768 channels -> groups of 24 spanning 3 producer groups each
+    up = ops.conv_upsample2x(a, ops.PackedUpsampleConv((torch.randn(256, 256, 3, 3, 3) / 80).cuda(), torch.randn(256).cuda()), impl=impl)
+    check_partials(up)
+    gn_both([up], 32)
+
+
 def test_conv_asym_pad(cuda_device):
     """AutoencoderKL Downsample: F.pad (0,1) per dim then k3 s2 p0 (autoencoderkl.py:107-120)."""
     ops = _ops()

@@ -15,8 +15,10 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--shape", default="160,224,160")
 ap.add_argument("--iters", type=int, default=2)
 ap.add_argument("--breakdown", type=int, default=1)
+ap.add_argument("--gnfuse", type=int, default=1)
 a = ap.parse_args()
 shape = tuple(int(v) for v in a.shape.split(","))
+ops._GN_FUSE = bool(a.gnfuse)
 
 torch.manual_seed(0)
 m = DiffusionModelUNet(spatial_dims=3, in_channels=1, out_channels=1, num_channels=(256, 256, 512),
