@@ -14,7 +14,7 @@ LIB_PATH = _HERE / "lib" / "libb200gen.so"
 
 B200_OK, B200_EINVAL, B200_ENOTSUP, B200_ECUDA, B200_ENODEV = 0, -1, -2, -3, -4
 DT_BF16, DT_F32 = 0, 1
-ACT_NONE, ACT_RELU, ACT_SILU = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_SILU, ACT_LEAKYRELU = 0, 1, 2, 3
 PRED_EPSILON, PRED_SAMPLE, PRED_V = 0, 1, 2
 IGEMM_MAX_SEG = 128
 
@@ -107,6 +107,8 @@ SIGNATURES = {
     "b200_groupnorm_workspace_bytes": [_I32, _I64, _I32],
     "b200_groupnorm_stats": [C.POINTER(GnStatsParams), _P],
     "b200_groupnorm_from_partials": [C.POINTER(GnStatsParams), _P, _P, _P],
+    "b200_spade_apply": [C.POINTER(GnApplyParams), _P, _I32, _P, _P],
+    "b200_resize_nearest": [_P, _I32, _I32, _I32, _I32, _I32, _P, _I32, _I32, _I32, _P],
     "b200_groupnorm_apply": [C.POINTER(GnApplyParams), _P],
     "b200_layernorm": [_P, _I64, _I32, _I32, _P, _P, _F, _P, _I32, _P],
     "b200_nchw_to_nhwc": [_P, _I32, _I32, _I64, _P, _I32, _P],

@@ -52,6 +52,9 @@ static constexpr int kMaxKStages = 8;
 static constexpr int kQChunkBytes = kBM * 64 * 2;      // 16 KB
 static constexpr int kKChunkBytes = kBKV * 64 * 2;     // 8 KB: 64 keys x 64 channels
 static constexpr float kRescaleThreshold = 8.0f;       // log2 domain
+// The chain S_j -> softmax -> P_j -> PV_j is a latency chain (TMEM read, barrier hand-offs, TMEM write); the tensor pipe
+// only stays busy if independent work is queued behind it: QK^T runs kLookahead blocks ahead of PV.
+static constexpr int kSBuf = 3, kLookahead = 2;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -207,6 +210,12 @@ __device__ __forceinline__ void stg256(void* ptr, const uint32_t* w) {
 // O2 += P V2 — a pure GEMM stream with no QK^T and no exponentials (2/3 of the recompute variant's tensor work).
 // The rare lazy-rescale events of pass 1 are logged per warp (block index + per-row factor) and replayed on O2 at
 // the same block positions, so both slices see bit-identical P and the same normaliser l.
+#ifdef FA_TIMING
+#define FA_T(i) do { long long fa_now = clock64(); fa_acc[i] += fa_now - fa_last; fa_last = fa_now; } while (0)
+#else
+#define FA_T(i) do { } while (0)
+#endif
+
 template <int DCH, bool REPLAY>      // DCH = head_dim / 64
 __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_constant__ FlashDev p) {
   constexpr int CPS = DCH >= 2 ? 2 : 1;               // 64-channel K chunks per ring stage
@@ -227,11 +236,11 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
   auto k_full = [&](int s) { return bars + 16 + 8u * s; };
   auto k_empty = [&](int s) { return bars + 16 + 8u * (kMaxKStages + s); };
   const uint32_t v_full = bars + 16 + 8u * (2 * kMaxKStages), v_empty = v_full + 8;
-  auto s_full = [&](int b) { return v_empty + 8 + 8u * b; };
-  auto s_empty = [&](int b) { return v_empty + 24 + 8u * b; };
-  auto p_full = [&](int b) { return v_empty + 40 + 8u * b; };
-  auto p_empty = [&](int b) { return v_empty + 56 + 8u * b; };
-  const uint32_t o_full = v_empty + 72, o_empty = o_full + 8;
+  auto s_full = [&](int b) { return v_empty + 8 + 8u * b; };       // kSBuf score buffers
+  auto s_empty = [&](int b) { return v_empty + 32 + 8u * b; };
+  auto p_full = [&](int b) { return v_empty + 56 + 8u * b; };
+  auto p_empty = [&](int b) { return v_empty + 72 + 8u * b; };
+  const uint32_t o_full = v_empty + 88, o_empty = o_full + 8;
   const uint32_t p1_done = o_empty + 8;       // REPLAY: the softmax warps have written (and fenced) all P tiles
   const uint32_t r_done = p1_done + 8;        // REPLAY: every pass-2 MMA has completed (stage buffers free)
   const uint32_t tmem_slot = r_done + 8;
@@ -243,10 +252,8 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
     mbar_init(q_full, 1); mbar_init(q_empty, 1);
     for (int s = 0; s < kKStages; ++s) { mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); }
     mbar_init(v_full, 1); mbar_init(v_empty, 1);
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(s_full(b), 1); mbar_init(s_empty(b), 4);
-      mbar_init(p_full(b), 4); mbar_init(p_empty(b), 1);
-    }
+    for (int b = 0; b < kSBuf; ++b) { mbar_init(s_full(b), 1); mbar_init(s_empty(b), 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(p_full(b), 4); mbar_init(p_empty(b), 1); }
     mbar_init(o_full, 1); mbar_init(o_empty, 4);
     mbar_init(p1_done, 4); mbar_init(r_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -261,8 +268,8 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
   fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
   const uint32_t tO = tmem;              // columns [0, 256)
-  const uint32_t tS = tmem + 256;        // two 64-column score buffers
-  const uint32_t tP = tmem + 384;        // two 32-column probability buffers (bf16 pairs)
+  const uint32_t tS = tmem + 256;        // kSBuf = 3 score buffers of 64 columns
+  const uint32_t tP = tmem + 448;        // two 32-column probability buffers (bf16 pairs): 512 columns in all
 
   const int n_kv = p.n_kv;
 
@@ -284,8 +291,8 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
             tma_load_3d(&p.tmQ, q_full, sQ + c * kQChunkBytes, ch0 + c * 64, it.qt * kBM, it.b);
         }
         __syncwarp();
-        // order matches the MMA warp's consumption: K_0, K_1, V_0, K_2, V_1, ...
-        for (int j = 0; j <= n_kv; ++j) {
+        // order matches the MMA warp's consumption: K_0, K_1, K_2, V_0, K_3, V_1, ...
+        for (int j = 0; j < n_kv + kLookahead; ++j) {
           if (j < n_kv) {
 #pragma unroll
             for (int step = 0; step < NSTEP; ++step) {
@@ -301,11 +308,11 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
               if (++kst == kKStages) { kst = 0; kph ^= 1u; }
             }
           }
-          if (j >= 1) {
+          if (j >= kLookahead) {
             mbar_wait_warp(v_empty, (vcount & 1) ^ 1u);
             if (elect_one()) {
               mbar_expect_tx(v_full, p.dv * kBKV * 2);
-              tma_load_3d(&p.tmVt, v_full, sV, (j - 1) * kBKV, ch0 + it.dvi * p.dv, it.b);
+              tma_load_3d(&p.tmVt, v_full, sV, (j - kLookahead) * kBKV, ch0 + it.dvi * p.dv, it.b);
             }
             __syncwarp();
             ++vcount;
@@ -346,17 +353,18 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
       const uint32_t q_lo = desc_lo(sQ), k_lo = desc_lo(sK), v_lo = desc_lo(sV);
       int kst = 0; uint32_t kph = 0;
       uint32_t scount = 0;      // number of S blocks issued so far (global across items)
-      uint32_t pvcount = 0;     // number of PV blocks issued so far
+      uint32_t pvcount = 0;     // number of P hand-offs consumed so far (pass 1 blocks + gated pass-2 blocks)
+      uint32_t vcount = 0;      // number of V^T tiles consumed from the single-tile buffer (pass 1 only)
       uint32_t icount = 0, ocount = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++icount) {
         mbar_wait_warp(q_full, icount & 1);
         mbar_wait_warp(o_empty, (ocount & 1) ^ 1u);        // previous epilogue has drained O
         ++ocount;
         fence_after();
-        for (int j = 0; j <= n_kv; ++j) {
+        for (int j = 0; j < n_kv + kLookahead; ++j) {
           if (j < n_kv) {
-            const int sb = scount & 1;
-            mbar_wait_warp(s_empty(sb), ((scount >> 1) & 1) ^ 1u);
+            const int sb = scount % kSBuf;
+            mbar_wait_warp(s_empty(sb), ((scount / kSBuf) & 1) ^ 1u);
             fence_after();
             const uint32_t d_s = tS + sb * kBKV;
 #pragma unroll
@@ -381,25 +389,27 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
             }
             ++scount;
           }
-          if (j >= 1) {
+          if (j >= kLookahead) {
             const int pb = pvcount & 1;
             mbar_wait_warp(p_full(pb), (pvcount >> 1) & 1);
-            mbar_wait_warp(v_full, pvcount & 1);
+            mbar_wait_warp(v_full, vcount & 1);
             fence_after();
             if (elect_one()) {
               const uint32_t a_tmem = tP + pb * 32;          // 16 bf16 = 8 columns per K step
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk)
-                umma_bf16_ts(tO, a_tmem + 8u * kk, desc64(v_lo + 2 * kk), idesc_o, (j > 1 || kk > 0) ? 1u : 0u);
+                umma_bf16_ts(tO, a_tmem + 8u * kk, desc64(v_lo + 2 * kk), idesc_o,
+                             (j > kLookahead || kk > 0) ? 1u : 0u);
               umma_commit(v_empty);
               umma_commit(p_empty(pb));
-              if (j == n_kv) {
+              if (j == n_kv + kLookahead - 1) {
                 umma_commit(o_full);
                 umma_commit(q_empty);
               }
             }
             __syncwarp();
             ++pvcount;
+            ++vcount;
           }
         }
         if constexpr (REPLAY) {
@@ -440,6 +450,9 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+#ifdef FA_TIMING
+    long long fa_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, fa_last = clock64();
+#endif
     uint32_t scount = 0;       // S buffers consumed (pass 1 blocks)
     uint32_t pcount = 0;       // P hand-offs to the MMA warp (pass 1 and pass 2 blocks)
     uint32_t ocount = 0;       // epilogues done
@@ -453,9 +466,11 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
       float m_used = -INFINITY, l_run = 0.f;
       int n_ev = 0;
       for (int j = 0; j < n_kv; ++j, ++scount, ++pcount) {
-        const int sb = scount & 1;
-        mbar_wait(s_full(sb), (scount >> 1) & 1);
+        const int sb = scount % kSBuf;
+        FA_T(0);
+        mbar_wait(s_full(sb), (scount / kSBuf) & 1);
         fence_after();
+        FA_T(1);
         uint32_t raw[64];
         tmem_ld32(tS + lane_addr + sb * kBKV, raw);
         tmem_ld32(tS + lane_addr + sb * kBKV + 32, raw + 32);
@@ -463,6 +478,7 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
         fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(s_empty(sb));     // S buffer may be overwritten by block j + 2
+        FA_T(2);
         const int kv_valid = p.S - j * kBKV;          // columns >= kv_valid are TMA zero-fill
         // row maximum with 8 independent chains (one warp per scheduler here: instruction-level parallelism is the
         // only latency hiding there is); raw[] keeps the UNSCALED scores, the scale is folded into the exp2 FFMA
@@ -489,7 +505,9 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
         const unsigned any = __ballot_sync(0xffffffffu, need && m_used > -INFINITY);
         // P buffer pb must have been consumed by the PV MMA two hand-offs ago
         const int pb = pcount & 1;
+        FA_T(3);
         if (pcount >= 2) mbar_wait(p_empty(pb), ((pcount >> 1) & 1) ^ 1u);
+        FA_T(4);
         if (any) {
           // O holds blocks < j; PV of block j - 1 must have completed before it is rewritten
           if (j >= 1) {
@@ -532,6 +550,7 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
           __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
           pw[w] = *reinterpret_cast<uint32_t*>(&h);
         }
+        FA_T(5);
         tmem_st32(tP + lane_addr + pb * 32, pw);
         if constexpr (REPLAY) {
           // the same 64 probabilities to this row of the slab (128 contiguous bytes), for pass 2
@@ -545,7 +564,13 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
         fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full(pb));
+        FA_T(6);
       }
+#ifdef FA_TIMING
+      if (blockIdx.x == 0 && warp == 2 && lane == 0 && item == blockIdx.x && REPLAY) {
+        for (int i = 0; i < 8; ++i) p.ev_fac[(long long)gridDim.x * 4 * n_kv * 32 - 8 + i] = (float)fa_acc[i];
+      }
+#endif
       if constexpr (REPLAY) {
         // make the slab visible to the TMA (async proxy) reads of pass 2, then release the producer
         if (lane == 0) ev_flags[q] = n_ev > 0 ? 1 : 0;

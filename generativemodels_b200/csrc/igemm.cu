@@ -316,6 +316,9 @@ __device__ __forceinline__ void act_inplace(float* v, int act) {
   if (act == B200_ACT_SILU) {
 #pragma unroll
     for (int j = 0; j < CH; ++j) v[j] = silu_f(v[j]);
+  } else if (act == B200_ACT_LEAKYRELU) {
+#pragma unroll
+    for (int j = 0; j < CH; ++j) v[j] = v[j] > 0.0f ? v[j] : 0.01f * v[j];
   } else {
 #pragma unroll
     for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.0f);

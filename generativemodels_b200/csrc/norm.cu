@@ -267,6 +267,68 @@ __global__ void zero_pad_channels_kernel(__nv_bfloat16* y, long long rows, int C
   }
 }
 
+
+// ---- SPADE modulation -----------------------------------------------------------------------------
+// one thread per (voxel, 8-channel vector) when everything is 16-byte aligned, else per (voxel, channel)
+template <int VEC>
+__global__ void spade_apply_kernel(const __nv_bfloat16* __restrict__ x0, const __nv_bfloat16* __restrict__ x1, int C0,
+                                   int C1, int pitch0, int pitch1, long long spatial, int N,
+                                   const float* __restrict__ affine, const __nv_bfloat16* __restrict__ gb, int gb_pitch,
+                                   const float* __restrict__ gb_affine, int act, __nv_bfloat16* __restrict__ y,
+                                   int y_pitch) {
+  const int C = C0 + C1;
+  const int CV = C / VEC;
+  const long long total = (long long)N * spatial * CV;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % CV) * VEC;
+    const long long row = i / CV;
+    const int n = (int)(row / spatial);
+    const __nv_bfloat16* src = c < C0 ? x0 + row * pitch0 + c : x1 + row * pitch1 + (c - C0);
+    const __nv_bfloat16* g = gb + row * gb_pitch + c;
+    float xv[VEC], gv[VEC], tv[VEC];
+    if constexpr (VEC == 8) {
+      unpack8(__ldg(reinterpret_cast<const uint4*>(src)), xv);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(g)), gv);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(g + C)), tv);
+    } else {
+      xv[0] = __bfloat162float(src[0]); gv[0] = __bfloat162float(g[0]); tv[0] = __bfloat162float(g[C]);
+    }
+    const float* ax = affine + ((long long)n * C + c) * 2;
+    const float* ag = gb_affine + ((long long)n * 2 * C + c) * 2;
+    const float* at = gb_affine + ((long long)n * 2 * C + C + c) * 2;
+    float out[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const float nx = fmaf(xv[j], ax[2 * j], ax[2 * j + 1]);
+      const float gg = fmaf(gv[j], ag[2 * j], ag[2 * j + 1]);
+      const float tt = fmaf(tv[j], at[2 * j], at[2 * j + 1]);
+      out[j] = apply_act(fmaf(nx, 1.0f + gg, tt), act);
+    }
+    __nv_bfloat16* dst = y + row * y_pitch + c;
+    if constexpr (VEC == 8) *reinterpret_cast<uint4*>(dst) = pack8(out);
+    else dst[0] = __float2bfloat16_rn(out[0]);
+  }
+}
+
+__global__ void resize_nearest_kernel(const __nv_bfloat16* __restrict__ x, int N, int D, int H, int W, int pitch,
+                                      __nv_bfloat16* __restrict__ y, int OD, int OH, int OW) {
+  const long long total = (long long)N * OD * OH * OW * pitch;
+  const float sd = (float)D / OD, sh = (float)H / OH, sw = (float)W / OW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % pitch);
+    long long t = i / pitch;
+    const int ow = (int)(t % OW); t /= OW;
+    const int oh = (int)(t % OH); t /= OH;
+    const int od = (int)(t % OD);
+    const int n = (int)(t / OD);
+    const int iw = min((int)floorf(ow * sw), W - 1), ih = min((int)floorf(oh * sh), H - 1),
+              id = min((int)floorf(od * sd), D - 1);
+    y[i] = x[((((long long)n * D + id) * H + ih) * W + iw) * pitch + c];
+  }
+}
+
 // ---- LayerNorm: one warp per row ----------------------------------------------------------------
 __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long M, int C, int x_pitch,
                                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
@@ -401,6 +463,55 @@ extern "C" int b200_groupnorm_apply(const b200_gn_apply_params* p, void* stream_
     zero_pad_channels_kernel<<<(unsigned)zb, 256, 0, stream>>>(y, rows, C, p->y_pitch);
     B200_LAUNCH_CHECK("zero_pad_channels_kernel");
   }
+  return B200_OK;
+}
+
+extern "C" int b200_spade_apply(const b200_gn_apply_params* p, const void* gb, int32_t gb_pitch, const float* gb_affine,
+                                void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(p && p->x_ptr[0] && p->affine && p->y_ptr && gb && gb_affine, "spade_apply: null pointer");
+  const int C0 = p->x_C[0], C1 = p->x_ptr[1] ? p->x_C[1] : 0;
+  const int C = C0 + C1;
+  B200_CHECK_ARG(p->y_pitch >= C && gb_pitch >= 2 * C && p->N >= 1 && p->spatial >= 1, "spade_apply: bad shape");
+  const bool vec = C0 % 8 == 0 && C1 % 8 == 0 && p->x_pitch[0] % 8 == 0 && (C1 == 0 || p->x_pitch[1] % 8 == 0) &&
+                   p->y_pitch % 8 == 0 && gb_pitch % 8 == 0 && ((uintptr_t)p->x_ptr[0] % 16 == 0) &&
+                   (C1 == 0 || (uintptr_t)p->x_ptr[1] % 16 == 0) && ((uintptr_t)p->y_ptr % 16 == 0) &&
+                   ((uintptr_t)gb % 16 == 0);
+  const long long total = (long long)p->N * p->spatial * (C / (vec ? 8 : 1));
+  long long blocks = (total + 255) / 256;
+  if (blocks > 16ll * sm_count()) blocks = 16ll * sm_count();
+  const __nv_bfloat16* x0 = reinterpret_cast<const __nv_bfloat16*>(p->x_ptr[0]);
+  const __nv_bfloat16* x1 = reinterpret_cast<const __nv_bfloat16*>(p->x_ptr[1]);
+  const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(gb);
+  __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(p->y_ptr);
+  if (vec)
+    spade_apply_kernel<8><<<(unsigned)blocks, 256, 0, stream>>>(x0, x1, C0, C1, p->x_pitch[0], p->x_pitch[1], p->spatial,
+                                                                p->N, p->affine, g, gb_pitch, gb_affine, p->act, y, p->y_pitch);
+  else
+    spade_apply_kernel<1><<<(unsigned)blocks, 256, 0, stream>>>(x0, x1, C0, C1, p->x_pitch[0], p->x_pitch[1], p->spatial,
+                                                                p->N, p->affine, g, gb_pitch, gb_affine, p->act, y, p->y_pitch);
+  B200_LAUNCH_CHECK("spade_apply_kernel");
+  if (p->y_pitch > C) {
+    const long long rows = (long long)p->N * p->spatial;
+    long long zb = (rows * (p->y_pitch - C) + 255) / 256;
+    if (zb > 4ll * sm_count()) zb = 4ll * sm_count();
+    zero_pad_channels_kernel<<<(unsigned)zb, 256, 0, stream>>>(y, rows, C, p->y_pitch);
+    B200_LAUNCH_CHECK("zero_pad_channels_kernel");
+  }
+  return B200_OK;
+}
+
+extern "C" int b200_resize_nearest(const void* x, int32_t N, int32_t D, int32_t H, int32_t W, int32_t pitch, void* y,
+                                   int32_t OD, int32_t OH, int32_t OW, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(x && y && N >= 1 && D >= 1 && H >= 1 && W >= 1 && OD >= 1 && OH >= 1 && OW >= 1 && pitch >= 1,
+                 "resize_nearest: bad arguments");
+  const long long total = (long long)N * OD * OH * OW * pitch;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 16ll * sm_count()) blocks = 16ll * sm_count();
+  resize_nearest_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), N, D, H, W, pitch,
+                                                             reinterpret_cast<__nv_bfloat16*>(y), OD, OH, OW);
+  B200_LAUNCH_CHECK("resize_nearest_kernel");
   return B200_OK;
 }
 

@@ -14,8 +14,10 @@ from collections.abc import Callable
 import torch
 import torch.nn as nn
 
+from functools import partial
+
 from .. import ops
-from ..networks.nets import VQVAE, ControlNet
+from ..networks.nets import VQVAE, ControlNet, SPADEAutoencoderKL, SPADEDiffusionModelUNet
 
 try:  # tqdm is optional, like in the reference
     from tqdm import tqdm
@@ -35,6 +37,11 @@ class Inferer(ABC):
 def _check_mode(mode: str) -> None:
     if mode not in ["crossattn", "concat"]:
         raise NotImplementedError(f"{mode} condition is not supported")
+
+
+def _with_seg(diffusion_model, seg):
+    """SPADE networks take the segmentation map as an extra argument (inferer.py:121-125, 210-214, 445-446)."""
+    return partial(diffusion_model, seg=seg) if isinstance(diffusion_model, SPADEDiffusionModelUNet) else diffusion_model
 
 
 def _progress(scheduler, verbose: bool):
@@ -73,6 +80,7 @@ class DiffusionInferer(Inferer):
                  seg: torch.Tensor | None = None) -> torch.Tensor:
         """Training-style forward (inferer.py:44-81): add noise at per-sample timesteps, predict."""
         _check_mode(mode)
+        diffusion_model = _with_seg(diffusion_model, seg)
         noisy_image = self.scheduler.add_noise(original_samples=inputs, noise=noise, timesteps=timesteps)
         if mode == "concat":
             noisy_image = torch.cat([noisy_image, condition], dim=1)
@@ -87,6 +95,7 @@ class DiffusionInferer(Inferer):
         _check_mode(mode)
         if not scheduler:
             scheduler = self.scheduler
+        diffusion_model = _with_seg(diffusion_model, seg)
         image = input_noise
         intermediates = []
         for t in _progress(scheduler, verbose):
@@ -111,6 +120,8 @@ class DiffusionInferer(Inferer):
         per-step tail — predicted x0, clip, both means, KL / discretised-Gaussian term, per-sample mean — is one
         fused kernel (b200_ddpm_kl).  Fixed-variance DDPM schedulers (the reference's learned-variance branch
         evaluates ``if predicted_variance`` on a tensor and cannot run)."""
+        diffusion_model = _with_seg(diffusion_model, seg)
+
         def predict(noisy_image, timesteps):
             if mode == "concat":
                 return diffusion_model(torch.cat([noisy_image, conditioning], dim=1), timesteps=timesteps, context=None)
@@ -227,10 +238,13 @@ class _LatentMixin:
             outputs = (outputs[0], [resizer(x) for x in outputs[1]])
         return outputs
 
-    def _decode_latent(self, latent, autoencoder_model):
+    def _decode_latent(self, latent, autoencoder_model, seg=None):
         if self.autoencoder_latent_shape is not None:
             latent = torch.stack([_center_crop(i, self.autoencoder_latent_shape) for i in latent], 0)
-        return autoencoder_model.decode_stage_2_outputs(ops.scale_f32(latent, 1.0 / self.scale_factor, divide_by=self.scale_factor))
+        decode = autoencoder_model.decode_stage_2_outputs
+        if isinstance(autoencoder_model, SPADEAutoencoderKL):          # inferer.py:473-474
+            decode = partial(autoencoder_model.decode_stage_2_outputs, seg=seg)
+        return decode(ops.scale_f32(latent, 1.0 / self.scale_factor, divide_by=self.scale_factor))
 
 
 class LatentDiffusionInferer(DiffusionInferer, _LatentMixin):
@@ -246,20 +260,25 @@ class LatentDiffusionInferer(DiffusionInferer, _LatentMixin):
                  seg: torch.Tensor | None = None, quantized: bool = True) -> torch.Tensor:
         latent = self._encode_latent(inputs, autoencoder_model, quantized)
         return super().__call__(inputs=latent, diffusion_model=diffusion_model, noise=noise, timesteps=timesteps,
-                                condition=condition, mode=mode)
+                                condition=condition, mode=mode, seg=seg)
 
     @torch.no_grad()
     def sample(self, input_noise: torch.Tensor, autoencoder_model, diffusion_model,
                scheduler: Callable[..., torch.Tensor] | None = None, save_intermediates: bool | None = False,
                intermediate_steps: int | None = 100, conditioning: torch.Tensor | None = None,
                mode: str = "crossattn", verbose: bool = True, seg: torch.Tensor | None = None):
+        if isinstance(autoencoder_model, SPADEAutoencoderKL) and isinstance(diffusion_model, SPADEDiffusionModelUNet) \
+                and autoencoder_model.decoder.label_nc != diffusion_model.label_nc:
+            raise ValueError(f"If both autoencoder_model and diffusion_model implement SPADE, the number of semantic"
+                             f"labels for each must be compatible. Got {autoencoder_model.decoder.label_nc} and "
+                             f"{diffusion_model.label_nc}")                                    # inferer.py:431-440
         outputs = super().sample(input_noise=input_noise, diffusion_model=diffusion_model, scheduler=scheduler,
                                  save_intermediates=save_intermediates, intermediate_steps=intermediate_steps,
-                                 conditioning=conditioning, mode=mode, verbose=verbose)
+                                 conditioning=conditioning, mode=mode, verbose=verbose, seg=seg)
         latent, latent_intermediates = outputs if save_intermediates else (outputs, [])
-        image = self._decode_latent(latent, autoencoder_model)
+        image = self._decode_latent(latent, autoencoder_model, seg)
         if save_intermediates:
-            return image, [self._decode_latent(l, autoencoder_model) for l in latent_intermediates]
+            return image, [self._decode_latent(l, autoencoder_model, seg) for l in latent_intermediates]
         return image
 
 
@@ -276,7 +295,7 @@ class LatentDiffusionInferer(DiffusionInferer, _LatentMixin):
         latents = self._encode_latent(inputs, autoencoder_model, quantized)
         outputs = super().get_likelihood(inputs=latents, diffusion_model=diffusion_model, scheduler=scheduler,
                                          save_intermediates=save_intermediates, conditioning=conditioning, mode=mode,
-                                         verbose=verbose)
+                                         verbose=verbose, seg=seg)
         return self._resample_maps(outputs, inputs.shape[2:], save_intermediates, resample_latent_likelihoods,
                                    resample_interpolation_mode)
 
@@ -297,8 +316,9 @@ class ControlNetDiffusionInferer(DiffusionInferer):
             noisy_image = torch.cat([noisy_image, condition], dim=1)
             condition = None
         down, mid = _run_controlnet(controlnet, noisy_image, timesteps, cn_cond, condition)
-        return diffusion_model(x=noisy_image, timesteps=timesteps, context=condition,
-                               down_block_additional_residuals=down, mid_block_additional_residual=mid)
+        return _with_seg(diffusion_model, seg)(x=noisy_image, timesteps=timesteps, context=condition,
+                                               down_block_additional_residuals=down,
+                                               mid_block_additional_residual=mid)
 
     @torch.no_grad()
     def sample(self, input_noise: torch.Tensor, diffusion_model, controlnet, cn_cond: torch.Tensor,
@@ -308,6 +328,7 @@ class ControlNetDiffusionInferer(DiffusionInferer):
         _check_mode(mode)
         if not scheduler:
             scheduler = self.scheduler
+        diffusion_model = _with_seg(diffusion_model, seg)
         image = input_noise
         intermediates = []
         for t in _progress(scheduler, verbose):
@@ -334,6 +355,8 @@ class ControlNetDiffusionInferer(DiffusionInferer):
         """inferer.py:710-853: as DiffusionInferer.get_likelihood with the ControlNet residuals fed to the UNet.  (The
         reference's concat branch overwrites ``conditioning`` inside the loop and fails on its second step; here the
         concatenation is per step, as in ``sample``.)"""
+        diffusion_model = _with_seg(diffusion_model, seg)
+
         def predict(noisy_image, timesteps):
             if mode == "concat":
                 model_input, context_ = torch.cat([noisy_image, conditioning], dim=1), None
@@ -373,7 +396,7 @@ class ControlNetLatentDiffusionInferer(ControlNetDiffusionInferer, _LatentMixin)
         latent = self._encode_latent(inputs, autoencoder_model, quantized)
         cn_cond = self._match_cond(cn_cond, latent.shape[2:])
         return super().__call__(inputs=latent, diffusion_model=diffusion_model, controlnet=controlnet, noise=noise,
-                                timesteps=timesteps, cn_cond=cn_cond, condition=condition, mode=mode)
+                                timesteps=timesteps, cn_cond=cn_cond, condition=condition, mode=mode, seg=seg)
 
     @torch.no_grad()
     def sample(self, input_noise: torch.Tensor, autoencoder_model, diffusion_model, controlnet,
@@ -385,11 +408,11 @@ class ControlNetLatentDiffusionInferer(ControlNetDiffusionInferer, _LatentMixin)
         outputs = super().sample(input_noise=input_noise, diffusion_model=diffusion_model, controlnet=controlnet,
                                  cn_cond=cn_cond, scheduler=scheduler, save_intermediates=save_intermediates,
                                  intermediate_steps=intermediate_steps, conditioning=conditioning, mode=mode,
-                                 verbose=verbose)
+                                 verbose=verbose, seg=seg)
         latent, latent_intermediates = outputs if save_intermediates else (outputs, [])
-        image = self._decode_latent(latent, autoencoder_model)
+        image = self._decode_latent(latent, autoencoder_model, seg)
         if save_intermediates:
-            return image, [self._decode_latent(l, autoencoder_model) for l in latent_intermediates]
+            return image, [self._decode_latent(l, autoencoder_model, seg) for l in latent_intermediates]
         return image
 
     @torch.no_grad()
@@ -406,6 +429,6 @@ class ControlNetLatentDiffusionInferer(ControlNetDiffusionInferer, _LatentMixin)
         cn_cond = self._match_cond(cn_cond, latents.shape[2:])
         outputs = super().get_likelihood(inputs=latents, diffusion_model=diffusion_model, controlnet=controlnet,
                                          cn_cond=cn_cond, scheduler=scheduler, save_intermediates=save_intermediates,
-                                         conditioning=conditioning, mode=mode, verbose=verbose)
+                                         conditioning=conditioning, mode=mode, verbose=verbose, seg=seg)
         return self._resample_maps(outputs, inputs.shape[2:], save_intermediates, resample_latent_likelihoods,
                                    resample_interpolation_mode)

@@ -59,7 +59,8 @@ class Convolution(nn.Module, _Cached):
         else:
             ctor = nn.Conv2d if spatial_dims == 2 else nn.Conv3d
             self.conv = ctor(in_channels, out_channels, kernel_size, stride=strides, padding=self.padding, bias=bias)
-        self.act = ops.ACT_NONE if (conv_only or act is None) else {"RELU": ops.ACT_RELU, "SILU": ops.ACT_SILU}[
+        self.act = ops.ACT_NONE if (conv_only or act is None) else {"RELU": ops.ACT_RELU, "SILU": ops.ACT_SILU,
+                                                                            "LEAKYRELU": ops.ACT_LEAKYRELU}[
             str(act).upper()]
 
     def packed(self, splits: Sequence[int] | None = None, padding=None):

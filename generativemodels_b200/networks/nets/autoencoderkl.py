@@ -10,6 +10,7 @@ import torch.nn as nn
 
 from ... import ops
 from ...ops import ACT_NONE, ACT_SILU, CL
+from ..blocks.spade_norm import SPADE
 from .._holders import Convolution, require_cuda
 from .diffusion_model_unet import _sdp, ensure_tuple_rep
 
@@ -53,14 +54,23 @@ class ResBlock(nn.Module):
     """autoencoderkl.py:125-193 (GroupNorm+SiLU+conv twice, 1x1 nin_shortcut when channels change)."""
 
     def __init__(self, spatial_dims: int, in_channels: int, norm_num_groups: int, norm_eps: float,
-                 out_channels: int) -> None:
+                 out_channels: int, label_nc: int | None = None, spade_intermediate_channels: int = 128) -> None:
         super().__init__()
         self.in_channels = in_channels
         self.out_channels = in_channels if out_channels is None else out_channels
-        self.norm1 = nn.GroupNorm(num_groups=norm_num_groups, num_channels=in_channels, eps=norm_eps, affine=True)
+        self.spade = label_nc is not None
+
+        def make_norm(ch):
+            if self.spade:     # SPADEResBlock (spade_autoencoderkl.py:72-107): GroupNorm without affine, default eps
+                return SPADE(label_nc=label_nc, norm_nc=ch, norm="GROUP",
+                             norm_params={"num_groups": norm_num_groups, "affine": False},
+                             hidden_channels=spade_intermediate_channels, kernel_size=3, spatial_dims=spatial_dims)
+            return nn.GroupNorm(num_groups=norm_num_groups, num_channels=ch, eps=norm_eps, affine=True)
+
+        self.norm1 = make_norm(in_channels)
         self.conv1 = Convolution(spatial_dims, self.in_channels, self.out_channels, strides=1, kernel_size=3,
                                  padding=1)
-        self.norm2 = nn.GroupNorm(num_groups=norm_num_groups, num_channels=out_channels, eps=norm_eps, affine=True)
+        self.norm2 = make_norm(out_channels)
         self.conv2 = Convolution(spatial_dims, self.out_channels, self.out_channels, strides=1, kernel_size=3,
                                  padding=1)
         if self.in_channels != self.out_channels:
@@ -69,10 +79,16 @@ class ResBlock(nn.Module):
         else:
             self.nin_shortcut = nn.Identity()
 
-    def forward(self, x: CL) -> CL:
-        n1, n2 = self.norm1, self.norm2
-        h = self.conv1(ops.groupnorm(x, n1.num_groups, n1.eps, n1.weight, n1.bias, act=ACT_SILU))
-        h = ops.groupnorm(h, n2.num_groups, n2.eps, n2.weight, n2.bias, act=ACT_SILU)
+    def _norm(self, norm, x, seg):
+        if self.spade:
+            if seg is None:
+                raise ValueError("a SPADE ResBlock needs the segmentation map (seg)")
+            return norm(x, seg, act=ACT_SILU)
+        return ops.groupnorm(x, norm.num_groups, norm.eps, norm.weight, norm.bias, act=ACT_SILU)
+
+    def forward(self, x: CL, seg=None) -> CL:
+        h = self.conv1(self._norm(self.norm1, x, seg))
+        h = self._norm(self.norm2, h, seg)
         skip = x if isinstance(self.nin_shortcut, nn.Identity) else self.nin_shortcut(x)
         return self.conv2(h, residual=skip)
 
@@ -98,11 +114,13 @@ class AttentionBlock(nn.Module):
         return _sdp(self, h, h, self.num_heads, self.num_channels // self.num_heads, self.scale, x, True)
 
 
-def _run_blocks(blocks: nn.ModuleList, x: CL, out_f32_last: bool):
+def _run_blocks(blocks: nn.ModuleList, x: CL, out_f32_last: bool, seg=None):
     n = len(blocks)
     for i, block in enumerate(blocks):
         if isinstance(block, nn.GroupNorm):      # bare GroupNorm before the last conv: no activation
             x = ops.groupnorm(x, block.num_groups, block.eps, block.weight, block.bias, act=ACT_NONE)
+        elif isinstance(block, ResBlock) and block.spade:
+            x = block(x, seg)
         elif i == n - 1 and out_f32_last:
             x = block(x, out_f32=True)
         else:
@@ -156,8 +174,11 @@ class Decoder(nn.Module):
     def __init__(self, spatial_dims: int, num_channels: Sequence[int], in_channels: int, out_channels: int,
                  num_res_blocks: Sequence[int], norm_num_groups: int, norm_eps: float,
                  attention_levels: Sequence[bool], with_nonlocal_attn: bool = True,
-                 use_flash_attention: bool = False, use_convtranspose: bool = False) -> None:
+                 use_flash_attention: bool = False, use_convtranspose: bool = False, label_nc: int | None = None,
+                 spade_intermediate_channels: int = 128) -> None:
         super().__init__()
+        spade = dict(label_nc=label_nc, spade_intermediate_channels=spade_intermediate_channels)
+        self.label_nc = label_nc
         self.spatial_dims, self.num_channels, self.in_channels = spatial_dims, num_channels, in_channels
         self.out_channels, self.num_res_blocks = out_channels, num_res_blocks
         self.norm_num_groups, self.norm_eps, self.attention_levels = norm_num_groups, norm_eps, attention_levels
@@ -165,10 +186,10 @@ class Decoder(nn.Module):
         blocks: list[nn.Module] = [Convolution(spatial_dims, in_channels, rev_ch[0], strides=1, kernel_size=3,
                                                padding=1)]
         if with_nonlocal_attn is True:
-            blocks.append(ResBlock(spatial_dims, rev_ch[0], norm_num_groups, norm_eps, rev_ch[0]))
+            blocks.append(ResBlock(spatial_dims, rev_ch[0], norm_num_groups, norm_eps, rev_ch[0], **spade))
             blocks.append(AttentionBlock(spatial_dims, rev_ch[0], norm_num_groups=norm_num_groups, norm_eps=norm_eps,
                                          use_flash_attention=use_flash_attention))
-            blocks.append(ResBlock(spatial_dims, rev_ch[0], norm_num_groups, norm_eps, rev_ch[0]))
+            blocks.append(ResBlock(spatial_dims, rev_ch[0], norm_num_groups, norm_eps, rev_ch[0], **spade))
         rev_attn = list(reversed(attention_levels))
         rev_res = list(reversed(num_res_blocks))
         block_out_ch = rev_ch[0]
@@ -177,7 +198,7 @@ class Decoder(nn.Module):
             block_out_ch = rev_ch[i]
             is_final_block = i == len(num_channels) - 1
             for _ in range(rev_res[i]):
-                blocks.append(ResBlock(spatial_dims, block_in_ch, norm_num_groups, norm_eps, block_out_ch))
+                blocks.append(ResBlock(spatial_dims, block_in_ch, norm_num_groups, norm_eps, block_out_ch, **spade))
                 block_in_ch = block_out_ch
                 if rev_attn[i]:
                     blocks.append(AttentionBlock(spatial_dims, block_in_ch, norm_num_groups=norm_num_groups,
@@ -188,8 +209,8 @@ class Decoder(nn.Module):
         blocks.append(Convolution(spatial_dims, block_in_ch, out_channels, strides=1, kernel_size=3, padding=1))
         self.blocks = nn.ModuleList(blocks)
 
-    def forward(self, x: CL):
-        return _run_blocks(self.blocks, x, out_f32_last=True)
+    def forward(self, x: CL, seg=None):
+        return _run_blocks(self.blocks, x, out_f32_last=True, seg=seg)
 
 
 class AutoencoderKL(nn.Module):
@@ -200,7 +221,8 @@ class AutoencoderKL(nn.Module):
                  attention_levels: Sequence[bool] = (False, False, True, True), latent_channels: int = 3,
                  norm_num_groups: int = 32, norm_eps: float = 1e-6, with_encoder_nonlocal_attn: bool = True,
                  with_decoder_nonlocal_attn: bool = True, use_flash_attention: bool = False,
-                 use_checkpointing: bool = False, use_convtranspose: bool = False) -> None:
+                 use_checkpointing: bool = False, use_convtranspose: bool = False, _label_nc: int | None = None,
+                 _spade_intermediate_channels: int = 128) -> None:
         super().__init__()
         if any((out_channel % norm_num_groups) != 0 for out_channel in num_channels):
             raise ValueError("AutoencoderKL expects all num_channels being multiple of norm_num_groups")
@@ -217,7 +239,7 @@ class AutoencoderKL(nn.Module):
                                use_flash_attention)
         self.decoder = Decoder(spatial_dims, num_channels, latent_channels, out_channels, num_res_blocks,
                                norm_num_groups, norm_eps, attention_levels, with_decoder_nonlocal_attn,
-                               use_flash_attention, use_convtranspose)
+                               use_flash_attention, use_convtranspose, _label_nc, _spade_intermediate_channels)
         self.quant_conv_mu = Convolution(spatial_dims, latent_channels, latent_channels, strides=1, kernel_size=1,
                                          padding=0)
         self.quant_conv_log_sigma = Convolution(spatial_dims, latent_channels, latent_channels, strides=1,
@@ -247,8 +269,11 @@ class AutoencoderKL(nn.Module):
 
     @torch.no_grad()
     def decode(self, z: torch.Tensor) -> torch.Tensor:
+        return self._decode(z, None)
+
+    def _decode(self, z: torch.Tensor, seg) -> torch.Tensor:
         require_cuda(z, self)
-        y = self.decoder(self.post_quant_conv(ops.to_cl(z)))
+        y = self.decoder(self.post_quant_conv(ops.to_cl(z)), seg)
         out = ops.from_cl_f32(y, self.out_channels, self.spatial_dims)
         return out if z.dtype == torch.float32 else out.to(z.dtype)
 

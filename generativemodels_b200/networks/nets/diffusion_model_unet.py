@@ -19,6 +19,7 @@ import torch.nn as nn
 
 from ... import ops
 from ...ops import ACT_NONE, ACT_SILU, CL
+from ..blocks.spade_norm import SPADE
 from .._holders import Convolution, f32, packed_linear, require_cuda
 
 __all__ = ["DiffusionModelUNet"]
@@ -224,17 +225,28 @@ class Upsample(nn.Module):
 
 
 class ResnetBlock(nn.Module):
-    """diffusion_model_unet.py:589-696."""
+    """diffusion_model_unet.py:589-696; with ``label_nc`` the two norms are SPADE blocks and this is
+    SPADEResnetBlock (spade_diffusion_model_unet.py:72-200; same keys, ``forward(x, emb, seg)``)."""
 
     def __init__(self, spatial_dims: int, in_channels: int, temb_channels: int, out_channels: int | None = None,
-                 up: bool = False, down: bool = False, norm_num_groups: int = 32, norm_eps: float = 1e-6) -> None:
+                 up: bool = False, down: bool = False, norm_num_groups: int = 32, norm_eps: float = 1e-6,
+                 label_nc: int | None = None, spade_intermediate_channels: int = 128) -> None:
         super().__init__()
         self.spatial_dims = spatial_dims
         self.channels = in_channels
         self.emb_channels = temb_channels
         self.out_channels = out_channels or in_channels
         self.up, self.down = up, down
-        self.norm1 = nn.GroupNorm(num_groups=norm_num_groups, num_channels=in_channels, eps=norm_eps, affine=True)
+        self.spade = label_nc is not None
+
+        def make_norm(ch):
+            if self.spade:
+                return SPADE(label_nc=label_nc, norm_nc=ch, norm="GROUP",
+                             norm_params={"num_groups": norm_num_groups, "eps": norm_eps, "affine": True},
+                             hidden_channels=spade_intermediate_channels, kernel_size=3, spatial_dims=spatial_dims)
+            return nn.GroupNorm(num_groups=norm_num_groups, num_channels=ch, eps=norm_eps, affine=True)
+
+        self.norm1 = make_norm(in_channels)
         self.nonlinearity = nn.SiLU()
         self.conv1 = Convolution(spatial_dims, in_channels, self.out_channels, strides=1, kernel_size=3, padding=1)
         self.upsample = self.downsample = None
@@ -243,8 +255,7 @@ class ResnetBlock(nn.Module):
         elif down:
             self.downsample = Downsample(spatial_dims, in_channels, use_conv=False)
         self.time_emb_proj = nn.Linear(temb_channels, self.out_channels)
-        self.norm2 = nn.GroupNorm(num_groups=norm_num_groups, num_channels=self.out_channels, eps=norm_eps,
-                                  affine=True)
+        self.norm2 = make_norm(self.out_channels)
         self.conv2 = zero_module(Convolution(spatial_dims, self.out_channels, self.out_channels, strides=1,
                                              kernel_size=3, padding=1))
         if self.out_channels == in_channels:
@@ -253,10 +264,16 @@ class ResnetBlock(nn.Module):
             self.skip_connection = Convolution(spatial_dims, in_channels, self.out_channels, strides=1, kernel_size=1,
                                                padding=0)
 
-    def forward(self, x: CL | Sequence[CL], emb: torch.Tensor) -> CL:
+    def _norm(self, norm, srcs, seg):
+        if self.spade:
+            if seg is None:
+                raise ValueError("a SPADE ResnetBlock needs the segmentation map (seg)")
+            return norm(srcs, seg, act=ACT_SILU)
+        return ops.groupnorm(srcs, norm.num_groups, norm.eps, norm.weight, norm.bias, act=ACT_SILU)
+
+    def forward(self, x: CL | Sequence[CL], emb: torch.Tensor, seg=None) -> CL:
         srcs = [x] if isinstance(x, CL) else list(x)
-        n1, n2 = self.norm1, self.norm2
-        h = ops.groupnorm(srcs, n1.num_groups, n1.eps, n1.weight, n1.bias, act=ACT_SILU)
+        h = self._norm(self.norm1, srcs, seg)
         if self.up or self.down:
             if len(srcs) != 1:
                 raise ValueError("resampling ResnetBlock takes a single input tensor")
@@ -265,7 +282,7 @@ class ResnetBlock(nn.Module):
             h = resample(h)
         temb = ops.small_linear(emb, self.time_emb_proj.weight, self.time_emb_proj.bias, act_in=ACT_SILU)
         h = self.conv1(h, rowvec=temb)
-        h = ops.groupnorm(h, n2.num_groups, n2.eps, n2.weight, n2.bias, act=ACT_SILU)
+        h = self._norm(self.norm2, [h], seg)
         if isinstance(self.skip_connection, nn.Identity):
             skip = srcs[0] if len(srcs) == 1 else ops.concat(srcs)
         else:
@@ -413,12 +430,12 @@ class _UpBase(nn.Module):
     ResnetBlock, whose GroupNorm and 1x1 skip conv read both tensors."""
 
     def forward(self, hidden_states: CL, res_hidden_states_list: list[CL], temb: torch.Tensor,
-                context: CL | None = None) -> CL:
+                context: CL | None = None, seg=None) -> CL:
         attentions = self._modules.get("attentions")      # absent on the plain UpBlock
         for i, resnet in enumerate(self.resnets):
             res_hidden_states = res_hidden_states_list[-1]
             res_hidden_states_list = res_hidden_states_list[:-1]
-            hidden_states = resnet([hidden_states, res_hidden_states], temb)
+            hidden_states = resnet([hidden_states, res_hidden_states], temb, seg)
             if attentions is not None:
                 attn = attentions[i]
                 hidden_states = attn(hidden_states, context=context) if isinstance(attn, SpatialTransformer) \
@@ -429,24 +446,27 @@ class _UpBase(nn.Module):
 
 
 def _up_resnets(spatial_dims, in_channels, prev_output_channel, out_channels, temb_channels, num_res_blocks,
-                norm_num_groups, norm_eps):
+                norm_num_groups, norm_eps, label_nc=None, spade_intermediate_channels=128):
     resnets = []
     for i in range(num_res_blocks):
         res_skip_channels = in_channels if (i == num_res_blocks - 1) else out_channels
         resnet_in_channels = prev_output_channel if i == 0 else out_channels
         resnets.append(ResnetBlock(spatial_dims, resnet_in_channels + res_skip_channels, temb_channels, out_channels,
-                                   norm_num_groups=norm_num_groups, norm_eps=norm_eps))
+                                   norm_num_groups=norm_num_groups, norm_eps=norm_eps, label_nc=label_nc,
+                                   spade_intermediate_channels=spade_intermediate_channels))
     return resnets
 
 
 class UpBlock(_UpBase):
     def __init__(self, spatial_dims: int, in_channels: int, prev_output_channel: int, out_channels: int,
                  temb_channels: int, num_res_blocks: int = 1, norm_num_groups: int = 32, norm_eps: float = 1e-6,
-                 add_upsample: bool = True, resblock_updown: bool = False) -> None:
+                 add_upsample: bool = True, resblock_updown: bool = False, label_nc: int | None = None,
+                 spade_intermediate_channels: int = 128) -> None:
         super().__init__()
         self.resblock_updown = resblock_updown
         self.resnets = nn.ModuleList(_up_resnets(spatial_dims, in_channels, prev_output_channel, out_channels,
-                                                 temb_channels, num_res_blocks, norm_num_groups, norm_eps))
+                                                 temb_channels, num_res_blocks, norm_num_groups, norm_eps, label_nc,
+                                                 spade_intermediate_channels))
         self.upsampler = _upsampler(spatial_dims, out_channels, temb_channels, norm_num_groups, norm_eps,
                                     resblock_updown) if add_upsample else None
 
@@ -455,11 +475,13 @@ class AttnUpBlock(_UpBase):
     def __init__(self, spatial_dims: int, in_channels: int, prev_output_channel: int, out_channels: int,
                  temb_channels: int, num_res_blocks: int = 1, norm_num_groups: int = 32, norm_eps: float = 1e-6,
                  add_upsample: bool = True, resblock_updown: bool = False, num_head_channels: int = 1,
-                 use_flash_attention: bool = False) -> None:
+                 use_flash_attention: bool = False, label_nc: int | None = None,
+                 spade_intermediate_channels: int = 128) -> None:
         super().__init__()
         self.resblock_updown = resblock_updown
         self.resnets = nn.ModuleList(_up_resnets(spatial_dims, in_channels, prev_output_channel, out_channels,
-                                                 temb_channels, num_res_blocks, norm_num_groups, norm_eps))
+                                                 temb_channels, num_res_blocks, norm_num_groups, norm_eps, label_nc,
+                                                 spade_intermediate_channels))
         self.attentions = nn.ModuleList([
             AttentionBlock(spatial_dims, out_channels, num_head_channels, norm_num_groups, norm_eps,
                            use_flash_attention) for _ in range(num_res_blocks)])
@@ -473,11 +495,13 @@ class CrossAttnUpBlock(_UpBase):
                  add_upsample: bool = True, resblock_updown: bool = False, num_head_channels: int = 1,
                  transformer_num_layers: int = 1, cross_attention_dim: int | None = None,
                  upcast_attention: bool = False, use_flash_attention: bool = False,
-                 dropout_cattn: float = 0.0) -> None:
+                 dropout_cattn: float = 0.0, label_nc: int | None = None,
+                 spade_intermediate_channels: int = 128) -> None:
         super().__init__()
         self.resblock_updown = resblock_updown
         self.resnets = nn.ModuleList(_up_resnets(spatial_dims, in_channels, prev_output_channel, out_channels,
-                                                 temb_channels, num_res_blocks, norm_num_groups, norm_eps))
+                                                 temb_channels, num_res_blocks, norm_num_groups, norm_eps, label_nc,
+                                                 spade_intermediate_channels))
         self.attentions = nn.ModuleList([
             SpatialTransformer(spatial_dims, out_channels, out_channels // num_head_channels, num_head_channels,
                                num_layers=transformer_num_layers, norm_num_groups=norm_num_groups, norm_eps=norm_eps,
@@ -521,12 +545,14 @@ def get_mid_block(spatial_dims, in_channels, temb_channels, norm_num_groups, nor
 def get_up_block(spatial_dims, in_channels, prev_output_channel, out_channels, temb_channels, num_res_blocks,
                  norm_num_groups, norm_eps, add_upsample, resblock_updown, with_attn, with_cross_attn,
                  num_head_channels, transformer_num_layers, cross_attention_dim, upcast_attention=False,
-                 use_flash_attention=False, dropout_cattn=0.0) -> nn.Module:
-    """diffusion_model_unet.py:1577-1643."""
+                 use_flash_attention=False, dropout_cattn=0.0, label_nc=None,
+                 spade_intermediate_channels=128) -> nn.Module:
+    """diffusion_model_unet.py:1577-1643; with ``label_nc`` the SPADE variants (spade_diffusion_model_unet.py:540-609)."""
     common = dict(spatial_dims=spatial_dims, in_channels=in_channels, prev_output_channel=prev_output_channel,
                   out_channels=out_channels, temb_channels=temb_channels, num_res_blocks=num_res_blocks,
                   norm_num_groups=norm_num_groups, norm_eps=norm_eps, add_upsample=add_upsample,
-                  resblock_updown=resblock_updown)
+                  resblock_updown=resblock_updown, label_nc=label_nc,
+                  spade_intermediate_channels=spade_intermediate_channels)
     if with_attn:
         return AttnUpBlock(**common, num_head_channels=num_head_channels, use_flash_attention=use_flash_attention)
     if with_cross_attn:
@@ -569,7 +595,8 @@ class DiffusionModelUNet(nn.Module):
                  with_conditioning: bool = False, transformer_num_layers: int = 1,
                  cross_attention_dim: int | None = None, num_class_embeds: int | None = None,
                  upcast_attention: bool = False, use_flash_attention: bool = False,
-                 dropout_cattn: float = 0.0) -> None:
+                 dropout_cattn: float = 0.0, _label_nc: int | None = None,
+                 _spade_intermediate_channels: int = 128) -> None:
         super().__init__()
         if with_conditioning is True and cross_attention_dim is None:
             raise ValueError("DiffusionModelUNet expects dimension of the cross-attention conditioning "
@@ -644,7 +671,8 @@ class DiffusionModelUNet(nn.Module):
                 spatial_dims, input_channel, prev_output_channel, output_channel, time_embed_dim, rev_res[i] + 1,
                 norm_num_groups, norm_eps, not is_final_block, resblock_updown,
                 rev_attn[i] and not with_conditioning, rev_attn[i] and with_conditioning, rev_heads[i],
-                transformer_num_layers, cross_attention_dim, upcast_attention, use_flash_attention, dropout_cattn))
+                transformer_num_layers, cross_attention_dim, upcast_attention, use_flash_attention, dropout_cattn,
+                _label_nc, _spade_intermediate_channels))
 
         self.out = nn.Sequential(
             nn.GroupNorm(num_groups=norm_num_groups, num_channels=num_channels[0], eps=norm_eps, affine=True),
@@ -657,6 +685,11 @@ class DiffusionModelUNet(nn.Module):
                 class_labels: torch.Tensor | None = None,
                 down_block_additional_residuals: tuple[torch.Tensor] | None = None,
                 mid_block_additional_residual: torch.Tensor | None = None) -> torch.Tensor:
+        return self._forward(x, timesteps, context, class_labels, down_block_additional_residuals,
+                             mid_block_additional_residual, None)
+
+    def _forward(self, x, timesteps, context, class_labels, down_block_additional_residuals,
+                 mid_block_additional_residual, seg):
         require_cuda(x, self)
         emb = time_embedding(self, x, timesteps, class_labels)
         if context is not None and self.with_conditioning is False:
@@ -679,7 +712,7 @@ class DiffusionModelUNet(nn.Module):
             n = len(upsample_block.resnets)
             res_samples = down_block_res_samples[-n:]
             down_block_res_samples = down_block_res_samples[:-n]
-            h = upsample_block(hidden_states=h, res_hidden_states_list=res_samples, temb=emb, context=ctx)
+            h = upsample_block(hidden_states=h, res_hidden_states_list=res_samples, temb=emb, context=ctx, seg=seg)
         norm = self.out[0]
         h = ops.groupnorm(h, norm.num_groups, norm.eps, norm.weight, norm.bias, act=ACT_SILU)
         y = self.out[2](h, out_f32=True)

@@ -14,12 +14,12 @@ from typing import Sequence
 import torch
 
 from . import _lib
-from ._lib import (ACT_NONE, ACT_RELU, ACT_SILU, DT_BF16, DT_F32, DdimCoef, DdpmCoef, GnApplyParams, GnStatsParams,
+from ._lib import (ACT_LEAKYRELU, ACT_NONE, ACT_RELU, ACT_SILU, DT_BF16, DT_F32, DdimCoef, DdpmCoef, GnApplyParams, GnStatsParams,
                    IgemmParams, PndmCoef, check)
 
 __all__ = ["CL", "to_cl", "from_cl", "PackedConv", "PackedConvTranspose", "PackedLinear", "conv", "conv_transpose",
            "linear", "groupnorm", "layernorm", "upsample_nearest2x", "avgpool2", "axpy", "geglu", "attention",
-           "timestep_embedding", "small_linear", "ACT_NONE", "ACT_RELU", "ACT_SILU"]
+           "timestep_embedding", "small_linear", "ACT_NONE", "ACT_RELU", "ACT_SILU", "ACT_LEAKYRELU"]
 
 
 def _stream() -> int:
@@ -482,9 +482,34 @@ def linear(x: CL, pl: PackedLinear, *, residual: CL | None = None, act1: int = A
 # --------------------------------------------------------------------------------------------------
 # normalisation
 # --------------------------------------------------------------------------------------------------
-def groupnorm(srcs: CL | Sequence[CL], groups: int, eps: float, gamma: torch.Tensor, beta: torch.Tensor,
-              act: int = ACT_NONE) -> CL:
-    """GroupNorm (+SiLU) over the virtual channel-concat of ``srcs``; returns one dense CL."""
+def _gn_params(srcs: Sequence[CL]):
+    sp, ap = GnStatsParams(), GnApplyParams()
+    a0 = srcs[0]
+    for i, a in enumerate(srcs):
+        if (a.N, a.D, a.H, a.W) != (a0.N, a0.D, a0.H, a0.W):
+            raise ValueError("normalised inputs must share batch and spatial extent")
+        sp.x_ptr[i] = ap.x_ptr[i] = a.t.data_ptr()
+        sp.x_C[i] = ap.x_C[i] = a.C
+        sp.x_pitch[i] = ap.x_pitch[i] = a.pitch
+    sp.N = ap.N = a0.N
+    sp.spatial = ap.spatial = a0.spatial
+    return sp, ap
+
+
+_ONES: dict = {}
+
+
+def _const_vec(n: int, value: float, device) -> torch.Tensor:
+    key = (n, value, str(device))
+    if key not in _ONES:
+        _ONES[key] = torch.full((n,), value, dtype=torch.float32, device=device)
+    return _ONES[key]
+
+
+def groupnorm_affine(srcs: CL | Sequence[CL], groups: int, eps: float, gamma: torch.Tensor | None,
+                     beta: torch.Tensor | None) -> torch.Tensor:
+    """Per-(sample, channel) affine table [N, C, 2] = (rstd * gamma, beta - mean * rstd * gamma) of GroupNorm over the
+    virtual channel-concat of ``srcs`` (gamma / beta None = no affine, e.g. InstanceNorm with groups = C)."""
     lib = _lib.require_device()
     if isinstance(srcs, CL):
         srcs = [srcs]
@@ -494,17 +519,10 @@ def groupnorm(srcs: CL | Sequence[CL], groups: int, eps: float, gamma: torch.Ten
         raise ValueError(f"GroupNorm: {Ct} channels not divisible by {groups} groups")
     dev = a0.t.device
     affine = torch.empty((a0.N, Ct, 2), dtype=torch.float32, device=dev)
-    sp = GnStatsParams()
-    ap = GnApplyParams()
-    for i, a in enumerate(srcs):
-        sp.x_ptr[i] = ap.x_ptr[i] = a.t.data_ptr()
-        sp.x_C[i] = ap.x_C[i] = a.C
-        sp.x_pitch[i] = ap.x_pitch[i] = a.pitch
-    sp.N = ap.N = a0.N
-    sp.spatial = ap.spatial = a0.spatial
+    sp, _ = _gn_params(srcs)
     sp.groups, sp.eps = groups, eps
-    g32 = gamma if gamma.dtype == torch.float32 else gamma.float()
-    b32 = beta if beta.dtype == torch.float32 else beta.float()
+    g32 = _const_vec(Ct, 1.0, dev) if gamma is None else (gamma if gamma.dtype == torch.float32 else gamma.float())
+    b32 = _const_vec(Ct, 0.0, dev) if beta is None else (beta if beta.dtype == torch.float32 else beta.float())
     sp.gamma, sp.beta = g32.data_ptr(), b32.data_ptr()
     sp.affine = affine.data_ptr()
     cpg = Ct // groups
@@ -517,10 +535,56 @@ def groupnorm(srcs: CL | Sequence[CL], groups: int, eps: float, gamma: torch.Ten
         ws = torch.empty(lib.b200_groupnorm_workspace_bytes(a0.N, a0.spatial, Ct) // 4, dtype=torch.float32, device=dev)
         sp.partial = ws.data_ptr()
         check(lib.b200_groupnorm_stats(C.byref(sp), _stream()), "b200_groupnorm_stats")
-    out = a0.like(Ct)
+    return affine
+
+
+def groupnorm(srcs: CL | Sequence[CL], groups: int, eps: float, gamma: torch.Tensor, beta: torch.Tensor,
+              act: int = ACT_NONE) -> CL:
+    """GroupNorm (+SiLU) over the virtual channel-concat of ``srcs``; returns one dense CL."""
+    lib = _lib.require_device()
+    if isinstance(srcs, CL):
+        srcs = [srcs]
+    affine = groupnorm_affine(srcs, groups, eps, gamma, beta)
+    a0 = srcs[0]
+    _, ap = _gn_params(srcs)
+    out = a0.like(sum(a.C for a in srcs))
     ap.affine, ap.act = affine.data_ptr(), act
     ap.y_ptr, ap.y_pitch = out.t.data_ptr(), out.pitch
     check(lib.b200_groupnorm_apply(C.byref(ap), _stream()), "b200_groupnorm_apply")
+    return out
+
+
+def spade_modulate(srcs: CL | Sequence[CL], affine: torch.Tensor, gb: CL, gb_affine: torch.Tensor,
+                   act: int = ACT_NONE) -> CL:
+    """act(norm(x) * (1 + inorm(gamma)) + inorm(beta)) in one pass (blocks/spade_norm.py:95): ``affine`` is the
+    GroupNorm table of x, ``gb`` holds gamma | beta as channel halves, ``gb_affine`` their InstanceNorm table."""
+    lib = _lib.require_device()
+    if isinstance(srcs, CL):
+        srcs = [srcs]
+    a0 = srcs[0]
+    Ct = sum(a.C for a in srcs)
+    if gb.C != 2 * Ct or (gb.N, gb.D, gb.H, gb.W) != (a0.N, a0.D, a0.H, a0.W):
+        raise ValueError("SPADE modulation tensor does not match the normalised input")
+    _, ap = _gn_params(srcs)
+    out = a0.like(Ct)
+    ap.affine, ap.act = affine.data_ptr(), act
+    ap.y_ptr, ap.y_pitch = out.t.data_ptr(), out.pitch
+    check(lib.b200_spade_apply(C.byref(ap), gb.t.data_ptr(), gb.pitch, gb_affine.data_ptr(), _stream()),
+          "b200_spade_apply")
+    return out
+
+
+def resize_nearest(x: CL, dims: Sequence[int]) -> CL:
+    """F.interpolate(x, size=dims, mode="nearest") on a channels-last tensor."""
+    lib = _lib.require_device()
+    d = tuple(int(v) for v in dims)
+    if len(d) == 2:
+        d = (1, *d)
+    if d == (x.D, x.H, x.W):
+        return x
+    out = x.like(dims=d)
+    check(lib.b200_resize_nearest(x.t.data_ptr(), x.N, x.D, x.H, x.W, x.pitch, out.t.data_ptr(), *d, _stream()),
+          "b200_resize_nearest")
     return out
 
 
@@ -643,6 +707,7 @@ def geglu(x: CL) -> CL:
 _TC_ATTN_MIN_S = 64
 _FLASH_HEAD_DIMS = (64, 128, 256, 512)
 _FORCE_UNFUSED_ATTENTION = False      # tests flip this to cover the GEMM + softmax + GEMM path
+_LAST_FLASH_WS = None
 _FLASH_REPLAY = True                  # tests flip this to compare the replay and recompute variants of head_dim 512
 _ATTN_CHUNK_BYTES = 6 << 30   # fp32 score slab per query chunk
 
@@ -689,6 +754,8 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, dh:
             if need:        # head_dim 512: probability tiles are written once and replayed for the second output half
                 ws = torch.empty(need, dtype=torch.uint8, device=q.device)
                 fp.workspace, fp.workspace_bytes = ws.data_ptr(), need
+                global _LAST_FLASH_WS
+                _LAST_FLASH_WS = ws           # dev probes read the kernel's debug counters from here
         check(lib.b200_attention_flash(C.byref(fp), _stream()), "b200_attention_flash")
         return out
     Sp = round_up(S, 8)

@@ -33,6 +33,7 @@ extern "C" {
 #define B200_ACT_NONE 0
 #define B200_ACT_RELU 1
 #define B200_ACT_SILU 2
+#define B200_ACT_LEAKYRELU 3   /* nn.LeakyReLU() default slope 0.01 (monai act="LEAKYRELU" in blocks/spade_norm.py:52-60) */
 
 #define B200_IGEMM_MAX_SEG 128
 
@@ -157,6 +158,17 @@ typedef struct {
   int32_t y_pitch;
 } b200_gn_apply_params;
 int b200_groupnorm_apply(const b200_gn_apply_params* p, void* stream);
+
+/* SPADE modulation (generative/networks/blocks/spade_norm.py:78-96), one pass:
+ *   y = act( (x * ax + bx) * (1 + (g * ag + bg)) + (t * at + bt) )
+ * x = virtual concat of the sources in p (GroupNorm affine table p->affine from b200_groupnorm_stats), g / t = the
+ * gamma / beta halves of gb ([rows][gb_pitch] bf16, channels [0,C) and [C,2C)) whose own per-(sample, channel)
+ * InstanceNorm table gb_affine is [N][2C][2] (monai's Convolution default norm on mlp_gamma / mlp_beta). */
+int b200_spade_apply(const b200_gn_apply_params* p, const void* gb, int32_t gb_pitch, const float* gb_affine,
+                     void* stream);
+/* F.interpolate(mode="nearest", size=...) on NDHWC bf16: src index = min(floor(dst * in / out), in - 1) per axis. */
+int b200_resize_nearest(const void* x, int32_t N, int32_t D, int32_t H, int32_t W, int32_t pitch, void* y, int32_t OD,
+                        int32_t OH, int32_t OW, void* stream);
 
 /* nn.LayerNorm over the last dim of a bf16 [M, C] matrix (diffusion_model_unet.py:221-223). */
 int b200_layernorm(const void* x, int64_t M, int32_t C, int32_t x_pitch, const float* gamma,

@@ -4,7 +4,7 @@ conv_only, an `adn` child adds only the letters present in `ordering` (A = activ
 import numpy as np
 import torch.nn as nn
 
-from ..layers.factories import Conv, get_act_layer
+from ..layers.factories import Conv, get_act_layer, get_norm_layer
 
 
 def same_padding(kernel_size, dilation=1):
@@ -28,7 +28,9 @@ class ADN(nn.Sequential):
         super().__init__()
         ops = {"A": None, "D": None, "N": None}
         if norm is not None:
-            raise NotImplementedError("shim: ADN norm is not needed by the hot path")
+            if norm_dim is None:
+                raise ValueError("norm_dim needs to be specified.")
+            ops["N"] = get_norm_layer(name=norm, spatial_dims=norm_dim, channels=in_channels)
         if act is not None:
             ops["A"] = get_act_layer(act)
         if dropout is not None:

@@ -39,3 +39,23 @@ def get_pool_layer(name, spatial_dims=1):
         return Pool[name, spatial_dims]()
     n, kwargs = name
     return Pool[n, spatial_dims](**kwargs)
+
+
+def get_norm_layer(name, spatial_dims=1, channels=1):
+    """monai.networks.layers.utils.get_norm_layer for the norms the SPADE blocks use: "INSTANCE" -> nn.InstanceNorm{d}d
+    (PyTorch defaults: no affine, no running stats), ("GROUP", {...}) -> nn.GroupNorm(num_channels=channels, ...),
+    "BATCH" -> nn.BatchNorm{d}d."""
+    if name == "" or name is None:
+        return nn.Identity()
+    if isinstance(name, str):
+        n, kwargs = name, {}
+    else:
+        n, kwargs = name
+    n = str(n).upper()
+    if n == "INSTANCE":
+        return {1: nn.InstanceNorm1d, 2: nn.InstanceNorm2d, 3: nn.InstanceNorm3d}[spatial_dims](channels, **kwargs)
+    if n == "GROUP":
+        return nn.GroupNorm(num_channels=channels, **kwargs)
+    if n == "BATCH":
+        return {1: nn.BatchNorm1d, 2: nn.BatchNorm2d, 3: nn.BatchNorm3d}[spatial_dims](channels, **kwargs)
+    raise NotImplementedError(f"shim: norm {n}")

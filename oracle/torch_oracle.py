@@ -149,10 +149,33 @@ def _upsample_nearest(x):
     return F.interpolate(x, scale_factor=2.0, mode="nearest")
 
 
-def resnet_block(sd, p, x, emb, groups, eps, up=False, down=False):
-    """ResnetBlock.forward (diffusion_model_unet.py:669-696)."""
+def spade_norm(sd, p, x, seg, groups, eps):
+    """SPADE.forward (blocks/spade_norm.py:78-96) with the GROUP base norm the diffusion / autoencoder blocks select.
+    ``mlp_gamma`` / ``mlp_beta`` are monai Convolutions built with act=None but the DEFAULT norm="INSTANCE", so each
+    is conv -> InstanceNorm (no affine); ``mlp_shared`` is conv -> LeakyReLU(0.01)."""
+    normalized = F.group_norm(x, groups, sd.get(p + ".param_free_norm.N.weight"), sd.get(p + ".param_free_norm.N.bias"),
+                              eps)
+    seg = F.interpolate(seg, size=x.shape[2:], mode="nearest")
+    k = sd[p + ".mlp_shared.conv.weight"].shape[-1]
+    actv = F.leaky_relu(_conv(sd, p + ".mlp_shared.conv", seg, padding=k // 2), 0.01)
+    gamma = F.instance_norm(_conv(sd, p + ".mlp_gamma.conv", actv, padding=k // 2))
+    beta = F.instance_norm(_conv(sd, p + ".mlp_beta.conv", actv, padding=k // 2))
+    return normalized * (1 + gamma) + beta
+
+
+def _norm_any(sd, p, x, groups, eps, seg):
+    if _has(sd, p + ".mlp_shared."):
+        if seg is None:
+            raise ValueError("a SPADE block needs the segmentation map")
+        return spade_norm(sd, p, x, seg, groups, eps)
+    return _gn(sd, p, x, groups, eps)
+
+
+def resnet_block(sd, p, x, emb, groups, eps, up=False, down=False, seg=None):
+    """ResnetBlock.forward (diffusion_model_unet.py:669-696); with SPADE norms (keys ``norm1.mlp_shared...``) it is
+    SPADEResnetBlock.forward (spade_diffusion_model_unet.py:173-200)."""
     sdims = x.dim() - 2
-    h = F.silu(_gn(sd, p + ".norm1", x, groups, eps))
+    h = F.silu(_norm_any(sd, p + ".norm1", x, groups, eps, seg))
     if up:
         x, h = _upsample_nearest(x), _upsample_nearest(h)
     elif down:
@@ -161,7 +184,7 @@ def resnet_block(sd, p, x, emb, groups, eps, up=False, down=False):
     h = _conv(sd, p + ".conv1.conv", h, padding=1)
     temb = _linear(sd, p + ".time_emb_proj", F.silu(emb))
     h = h + temb[(...,) + (None,) * sdims]
-    h = F.silu(_gn(sd, p + ".norm2", h, groups, eps))
+    h = F.silu(_norm_any(sd, p + ".norm2", h, groups, eps, seg))
     h = _conv(sd, p + ".conv2.conv", h, padding=1)
     if _has(sd, p + ".skip_connection."):
         x = _conv(sd, p + ".skip_connection.conv", x)
@@ -212,8 +235,9 @@ def _time_embedding(sd, cfg, x, timesteps, class_labels, prefix=""):
 
 
 def unet_forward(sd, cfg, x, timesteps, context=None, class_labels=None, down_block_additional_residuals=None,
-                 mid_block_additional_residual=None):
-    """DiffusionModelUNet.forward (diffusion_model_unet.py:1869-1943).
+                 mid_block_additional_residual=None, seg=None):
+    """DiffusionModelUNet.forward (diffusion_model_unet.py:1869-1943); with ``seg`` and a state_dict whose up-path
+    ResnetBlocks carry SPADE norms, SPADEDiffusionModelUNet.forward (spade_diffusion_model_unet.py:836-912).
 
     cfg: {"num_head_channels": per-level tuple, "norm_num_groups", "norm_eps", "with_conditioning"}.
     """
@@ -252,7 +276,7 @@ def unet_forward(sd, cfg, x, timesteps, context=None, class_labels=None, down_bl
         bp = f"up_blocks.{i}"
         for j in range(_count(sd, bp + ".resnets.")):
             h = torch.cat([h, skips.pop()], dim=1)
-            h = resnet_block(sd, f"{bp}.resnets.{j}", h, emb, groups, eps)
+            h = resnet_block(sd, f"{bp}.resnets.{j}", h, emb, groups, eps, seg=seg)
             if _has(sd, f"{bp}.attentions.{j}."):
                 h = _attn_any(sd, f"{bp}.attentions.{j}", h, context, groups, eps, rev_nhc[i])
         if _has(sd, bp + ".upsampler.conv."):
@@ -296,23 +320,31 @@ def controlnet_forward(sd, cfg, x, timesteps, controlnet_cond, conditioning_scal
 # ======================================================================================================
 
 
-def _ae_resblock(sd, p, x, groups, eps):
-    """ResBlock.forward (autoencoderkl.py:179-193)."""
-    h = _conv(sd, p + ".conv1.conv", F.silu(_gn(sd, p + ".norm1", x, groups, eps)), padding=1)
-    h = _conv(sd, p + ".conv2.conv", F.silu(_gn(sd, p + ".norm2", h, groups, eps)), padding=1)
+def _ae_resblock(sd, p, x, groups, eps, seg=None):
+    """ResBlock.forward (autoencoderkl.py:179-193); SPADEResBlock.forward (spade_autoencoderkl.py:122-134) when the
+    norms are SPADE blocks — those build their GroupNorm from {"num_groups", "affine": False} only, so it runs with
+    PyTorch's default eps = 1e-5 rather than the network's norm_eps."""
+    if _has(sd, p + ".norm1.mlp_shared."):
+        if seg is None:
+            raise ValueError("a SPADE block needs the segmentation map")
+        h = _conv(sd, p + ".conv1.conv", F.silu(spade_norm(sd, p + ".norm1", x, seg, groups, 1e-5)), padding=1)
+        h = _conv(sd, p + ".conv2.conv", F.silu(spade_norm(sd, p + ".norm2", h, seg, groups, 1e-5)), padding=1)
+    else:
+        h = _conv(sd, p + ".conv1.conv", F.silu(_gn(sd, p + ".norm1", x, groups, eps)), padding=1)
+        h = _conv(sd, p + ".conv2.conv", F.silu(_gn(sd, p + ".norm2", h, groups, eps)), padding=1)
     if _has(sd, p + ".nin_shortcut."):
         x = _conv(sd, p + ".nin_shortcut.conv", x)
     return x + h
 
 
-def _ae_blocks(sd, prefix, x, groups, eps, decoder: bool):
+def _ae_blocks(sd, prefix, x, groups, eps, decoder: bool, seg=None):
     """Encoder.forward / Decoder.forward: walk `blocks` by the kind of parameters each holds (315-452, 455-597)."""
     sdims = x.dim() - 2
     n = _count(sd, prefix + "blocks.")
     for i in range(n):
         p = f"{prefix}blocks.{i}"
-        if _has(sd, p + ".norm1."):
-            x = _ae_resblock(sd, p, x, groups, eps)
+        if _has(sd, p + ".norm1.") or _has(sd, p + ".conv1."):
+            x = _ae_resblock(sd, p, x, groups, eps, seg)
         elif _has(sd, p + ".to_q."):
             x = attention_block(sd, p, x, groups, eps, None)
         elif (p + ".weight") in sd and sd[p + ".weight"].dim() == 1:
@@ -345,12 +377,13 @@ def autoencoderkl_encode(sd, cfg, x):
     return z_mu, torch.exp(z_log_var / 2)
 
 
-def autoencoderkl_decode(sd, cfg, z):
-    """AutoencoderKL.decode (autoencoderkl.py:769-784)."""
+def autoencoderkl_decode(sd, cfg, z, seg=None):
+    """AutoencoderKL.decode (autoencoderkl.py:769-784); with ``seg``, SPADEAutoencoderKL.decode
+    (spade_autoencoderkl.py:457-469)."""
     groups, eps = cfg.get("norm_num_groups", 32), cfg.get("norm_eps", 1e-6)
     sd = dict(sd)
     sd["__use_convtranspose__"] = cfg.get("use_convtranspose", False)
-    return _ae_blocks(sd, "decoder.", _conv(sd, "post_quant_conv.conv", z), groups, eps, decoder=True)
+    return _ae_blocks(sd, "decoder.", _conv(sd, "post_quant_conv.conv", z), groups, eps, decoder=True, seg=seg)
 
 
 # ======================================================================================================

@@ -40,6 +40,8 @@ def i64(ptr, count):
 
 
 def _act(x, a):
+    if a == _lib.ACT_LEAKYRELU:
+        return F.leaky_relu(x, 0.01)
     return F.relu(x) if a == _lib.ACT_RELU else F.silu(x) if a == _lib.ACT_SILU else x
 
 
@@ -107,6 +109,26 @@ class FakeLib:
         a = rstd.float().repeat_interleave(cpg, 1) * gamma
         b = beta - mean.float().repeat_interleave(cpg, 1) * a
         f32(p.affine, N * Cc * 2).view(N, Cc, 2).copy_(torch.stack([a, b], -1))
+        return 0
+
+    def b200_spade_apply(self, p, gb, gb_pitch, gb_affine, stream):
+        p = _obj(p)
+        x = self._gather_src(p)                        # [N, S, C]
+        N, S, Cc = x.shape
+        ab = f32(p.affine, N * Cc * 2).view(N, 1, Cc, 2)
+        g = bf16(gb, N * S * gb_pitch).view(N, S, gb_pitch)[:, :, :2 * Cc].float()
+        gab = f32(gb_affine, N * 2 * Cc * 2).view(N, 1, 2 * Cc, 2)
+        g = g * gab[..., 0] + gab[..., 1]
+        y = _act((x * ab[..., 0] + ab[..., 1]) * (1 + g[..., :Cc]) + g[..., Cc:], p.act)
+        dst = bf16(p.y_ptr, N * S * p.y_pitch).view(N, S, p.y_pitch)
+        dst.zero_()
+        dst[:, :, :Cc] = y.to(torch.bfloat16)
+        return 0
+
+    def b200_resize_nearest(self, x, N, D, H, W, pitch, y, OD, OH, OW, stream):
+        src = bf16(x, N * D * H * W * pitch).view(N, D, H, W, pitch).float().permute(0, 4, 1, 2, 3)
+        out = F.interpolate(src, size=(OD, OH, OW), mode="nearest").permute(0, 2, 3, 4, 1)
+        bf16(y, N * OD * OH * OW * pitch).view(N, OD, OH, OW, pitch).copy_(out.to(torch.bfloat16))
         return 0
 
     def b200_groupnorm_apply(self, p, stream):

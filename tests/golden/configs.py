@@ -56,6 +56,41 @@ VQVAE_CASES = {
 VQVAE_INPUTS = {"vqvae3d": (1, 1, 16, 16, 16), "vqvae2d": (2, 1, 32, 32)}
 
 
+SPADE_UNET_CASES = {
+    "spade_unet2d": dict(spatial_dims=2, in_channels=1, out_channels=1, label_nc=3, num_res_blocks=1,
+                         num_channels=(32, 64), attention_levels=(False, True), norm_num_groups=8,
+                         num_head_channels=(0, 32), spade_intermediate_channels=16),
+    "spade_unet3d_updown": dict(spatial_dims=3, in_channels=2, out_channels=2, label_nc=4, num_res_blocks=(1, 2),
+                                num_channels=(16, 16), attention_levels=(False, False), norm_num_groups=8,
+                                resblock_updown=True, spade_intermediate_channels=8),
+    "spade_unet2d_cross": dict(spatial_dims=2, in_channels=1, out_channels=1, label_nc=3, num_res_blocks=1,
+                               num_channels=(16, 32), attention_levels=(False, True), norm_num_groups=8,
+                               num_head_channels=(0, 16), with_conditioning=True, cross_attention_dim=8,
+                               transformer_num_layers=1),
+}
+SPADE_UNET_INPUTS = {"spade_unet2d": dict(shape=(2, 1, 16, 16), seg=(2, 3, 32, 32)),
+                     "spade_unet3d_updown": dict(shape=(1, 2, 8, 8, 8), seg=(1, 4, 8, 8, 8)),
+                     "spade_unet2d_cross": dict(shape=(2, 1, 16, 16), seg=(2, 3, 16, 16), context=(2, 3, 8))}
+SPADE_AEKL_CASES = {
+    "spade_aekl2d": dict(spatial_dims=2, label_nc=3, in_channels=1, out_channels=1, num_channels=(16, 16, 32),
+                         latent_channels=4, attention_levels=(False, False, True), num_res_blocks=1, norm_num_groups=8,
+                         spade_intermediate_channels=8),
+    "spade_aekl3d": dict(spatial_dims=3, label_nc=2, in_channels=1, out_channels=1, num_channels=(16, 16),
+                         latent_channels=3, attention_levels=(False, False), num_res_blocks=(1, 2), norm_num_groups=8,
+                         with_encoder_nonlocal_attn=False, with_decoder_nonlocal_attn=False,
+                         spade_intermediate_channels=8),
+}
+SPADE_AEKL_INPUTS = {"spade_aekl2d": (2, 1, 16, 16), "spade_aekl3d": (1, 1, 8, 8, 8)}
+
+
+def seg_onehot(shape, seed=0):
+    """Deterministic one-hot segmentation map [N, label_nc, *spatial]."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    idx = torch.randint(0, shape[1], (shape[0], *shape[2:]), generator=g)
+    return torch.nn.functional.one_hot(idx, shape[1]).movedim(-1, 1).float()
+
+
 def head_channels_tuple(kw):
     n = len(kw["num_channels"])
     nhc = kw.get("num_head_channels", 8)

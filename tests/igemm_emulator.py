@@ -6,7 +6,7 @@ import ctypes as C
 
 import numpy as np
 
-from generativemodels_b200._lib import ACT_RELU, ACT_SILU, DT_BF16, IgemmParams
+from generativemodels_b200._lib import ACT_LEAKYRELU, ACT_RELU, ACT_SILU, DT_BF16, IgemmParams
 
 
 def _bf16_view(ptr, count):
@@ -33,6 +33,8 @@ def _act(x, a):
         return np.maximum(x, 0)
     if a == ACT_SILU:
         return x / (1 + np.exp(-x))
+    if a == ACT_LEAKYRELU:
+        return np.where(x > 0, x, np.float32(0.01) * x)
     return x
 
 

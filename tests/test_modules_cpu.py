@@ -229,3 +229,29 @@ def test_likelihood_variants_host_logic_cpu():
     lat = torch.randn(1, 3, 4, 4)
     lik = ControlNetDiffusionInferer(s).get_likelihood(lat, un, cn, torch.randn(1, 1, 4, 4), s, verbose=False)
     assert lik.shape == (1,) and torch.isfinite(lik).all()
+
+
+def test_spade_golden_cpu():
+    """SPADEDiffusionModelUNet / SPADEAutoencoderKL host logic (strict state_dict load, fused gamma|beta conv,
+    InstanceNorm table, segmentation pyramid) against the reference's golden outputs."""
+    fx = load("g_spade_unet2d")
+    m = nets().SPADEDiffusionModelUNet(**fx["kwargs"]).eval()
+    m.load_state_dict(fx["state_dict"])              # strict: same keys as the reference
+    assert rel(m(fx["x"], fx["t"], fx["seg"]), fx["y"]) < 2e-2
+    with pytest.raises(ValueError):
+        m.up_blocks[0].resnets[0]([ops_cl(fx["x"], 16), ops_cl(fx["x"], 16)], torch.zeros(2, 32), None)
+    fx = load("g_spade_aekl2d")
+    ae = nets().SPADEAutoencoderKL(**fx["kwargs"]).eval()
+    ae.load_state_dict(fx["state_dict"])
+    mu, sigma = ae.encode(fx["x"])
+    assert rel(mu, fx["mu"]) < 2e-2 and rel(sigma, fx["sigma"]) < 2e-2
+    assert rel(ae.decode(fx["mu"], fx["seg"]), fx["rec"]) < 2e-2
+    assert rel(ae.reconstruct(fx["x"], fx["seg"]), fx["rec"]) < 3e-2
+    with pytest.raises(ValueError):
+        nets().SPADEDiffusionModelUNet(spatial_dims=2, in_channels=1, out_channels=1, label_nc=3,
+                                       num_channels=(8, 16), attention_levels=(False,), norm_num_groups=4)
+
+
+def ops_cl(x, C_):
+    from generativemodels_b200 import ops
+    return ops.CL(torch.zeros(x.shape[0], 1, x.shape[2], x.shape[3], C_, dtype=torch.bfloat16), C_, 2)

@@ -188,3 +188,42 @@ def test_get_likelihood(ref, monkeypatch, ptype, clip):
         want = DiffusionInferer(R).get_likelihood(inputs=x, diffusion_model=m, scheduler=R, verbose=False)
         got = O.get_likelihood(lambda xx, t, c: O.unet_forward(sd, cfg, xx, t, context=c), M, x, noise)
     _close(got, want, 1e-4)
+
+
+@pytest.mark.parametrize("name", list(G.SPADE_UNET_CASES))
+def test_spade_unet(ref, name):
+    """SPADEDiffusionModelUNet (spade_diffusion_model_unet.py:612-912): SPADE norms in the up path, incl. the
+    InstanceNorm that monai's Convolution puts on mlp_gamma / mlp_beta."""
+    nets, _ = ref
+    kw, inp = G.SPADE_UNET_CASES[name], G.SPADE_UNET_INPUTS[name]
+    torch.manual_seed(0)
+    m = G.randomize_zero_params(nets.SPADEDiffusionModelUNet(**kw)).eval()
+    torch.manual_seed(1)
+    x = torch.randn(*inp["shape"])
+    t = torch.randint(0, 1000, (inp["shape"][0],)).long()
+    seg = G.seg_onehot(inp["seg"])
+    ctx = torch.randn(*inp["context"]) if "context" in inp else None
+    with torch.no_grad():
+        want = m(x, t, seg, context=ctx)
+        got = O.unet_forward(m.state_dict(), G.unet_oracle_cfg(kw), x, t, context=ctx, seg=seg)
+    _close(got, want)
+
+
+@pytest.mark.parametrize("name", list(G.SPADE_AEKL_CASES))
+def test_spade_autoencoderkl(ref, name):
+    """SPADEAutoencoderKL.encode / decode(z, seg) (spade_autoencoderkl.py:425-469)."""
+    nets, _ = ref
+    kw = G.SPADE_AEKL_CASES[name]
+    torch.manual_seed(0)
+    m = nets.SPADEAutoencoderKL(**kw).eval()
+    torch.manual_seed(1)
+    x = torch.randn(*G.SPADE_AEKL_INPUTS[name])
+    seg = G.seg_onehot((x.shape[0], kw["label_nc"], *x.shape[2:]))
+    with torch.no_grad():
+        mu, sigma = m.encode(x)
+        rec = m.decode(mu, seg)
+        gmu, gsigma = O.autoencoderkl_encode(m.state_dict(), G.aekl_oracle_cfg(kw), x)
+        grec = O.autoencoderkl_decode(m.state_dict(), G.aekl_oracle_cfg(kw), gmu, seg=seg)
+    _close(gmu, mu)
+    _close(gsigma, sigma)
+    _close(grec, rec)

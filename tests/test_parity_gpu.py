@@ -424,6 +424,90 @@ def test_ddpm_kl_kernel_exact(cuda_device):
             assert torch.allclose(ss.cpu(), want.double().sum(1), rtol=1e-4), (name, t0)
 
 
+# ------------------------------------------------------------------------------------------------ SPADE (§8f rank 2)
+def test_spade_golden(cuda_device):
+    """SPADEDiffusionModelUNet / SPADEAutoencoderKL against the UNMODIFIED reference's outputs (fixtures from
+    tests/golden/make_golden_spade.py): state_dict loads strictly, forward(x, t, seg) and decode(z, seg) match."""
+    fx = load("g_spade_unet2d")
+    m = nets().SPADEDiffusionModelUNet(**fx["kwargs"]).eval()
+    m.load_state_dict(fx["state_dict"])
+    check(m.cuda()(fx["x"].cuda(), fx["t"].cuda(), fx["seg"].cuda()), fx["y"], FWD_TOL, "SPADE UNet golden")
+    fx = load("g_spade_aekl2d")
+    ae = nets().SPADEAutoencoderKL(**fx["kwargs"]).eval()
+    ae.load_state_dict(fx["state_dict"])
+    ae.cuda()
+    mu, sigma = ae.encode(fx["x"].cuda())
+    check(mu, fx["mu"], FWD_TOL, "SPADE AE mu")
+    check(sigma, fx["sigma"], FWD_TOL, "SPADE AE sigma")
+    check(ae.decode(fx["mu"].cuda(), fx["seg"].cuda()), fx["rec"], FWD_TOL, "SPADE AE decode golden")
+
+
+@pytest.mark.parametrize("name", list(G.SPADE_UNET_CASES))
+def test_spade_unet_vs_oracle(cuda_device, name):
+    kw, inp = G.SPADE_UNET_CASES[name], G.SPADE_UNET_INPUTS[name]
+    torch.manual_seed(0)
+    m = G.randomize_zero_params(nets().SPADEDiffusionModelUNet(**kw)).eval()
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    torch.manual_seed(1)
+    x = torch.randn(*inp["shape"])
+    t = torch.randint(0, 1000, (inp["shape"][0],)).long()
+    seg = G.seg_onehot(inp["seg"])
+    ctx = torch.randn(*inp["context"]) if "context" in inp else None
+    want = O.unet_forward(sd, G.unet_oracle_cfg(kw), x, t, context=ctx, seg=seg)
+    got = m.cuda()(x.cuda(), t.cuda(), seg.cuda(), context=None if ctx is None else ctx.cuda())
+    check(got, want, FWD_TOL, f"SPADE UNet {name}")
+
+
+@pytest.mark.parametrize("name", list(G.SPADE_AEKL_CASES))
+def test_spade_autoencoderkl_vs_oracle(cuda_device, name):
+    kw = G.SPADE_AEKL_CASES[name]
+    torch.manual_seed(0)
+    m = nets().SPADEAutoencoderKL(**kw).eval()
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    torch.manual_seed(1)
+    x = torch.randn(*G.SPADE_AEKL_INPUTS[name])
+    seg = G.seg_onehot((x.shape[0], kw["label_nc"], *x.shape[2:]))
+    cfg = G.aekl_oracle_cfg(kw)
+    mu_w, sig_w = O.autoencoderkl_encode(sd, cfg, x)
+    rec_w = O.autoencoderkl_decode(sd, cfg, mu_w, seg=seg)
+    m.cuda()
+    mu, sig = m.encode(x.cuda())
+    check(mu, mu_w, FWD_TOL, "SPADE AE mu")
+    check(m.decode(mu_w.cuda(), seg.cuda()), rec_w, FWD_TOL, f"SPADE AE decode {name}")
+
+
+def test_spade_latent_sampling_vs_oracle(cuda_device):
+    """LatentDiffusionInferer.sample with SPADE networks on both stages and ``seg=`` (inferer.py:431-474): 3 DDIM steps
+    of the SPADE UNet in latent space, then SPADEAutoencoderKL.decode(z / scale, seg)."""
+    from generativemodels_b200.inferers import LatentDiffusionInferer
+    from generativemodels_b200.networks.schedulers import DDIMScheduler
+    akw = G.SPADE_AEKL_CASES["spade_aekl2d"]
+    ukw = dict(G.SPADE_UNET_CASES["spade_unet2d"], in_channels=akw["latent_channels"],
+               out_channels=akw["latent_channels"])
+    torch.manual_seed(0)
+    ae = nets().SPADEAutoencoderKL(**akw).eval()
+    un = G.randomize_zero_params(nets().SPADEDiffusionModelUNet(**ukw)).eval()
+    asd = {k: v.clone() for k, v in ae.state_dict().items()}
+    usd = {k: v.clone() for k, v in un.state_dict().items()}
+    skw = dict(num_train_timesteps=1000, schedule="scaled_linear_beta", beta_start=0.0015, beta_end=0.0205,
+               clip_sample=False)
+    so, sp = O.DDIMOracle(**skw), DDIMScheduler(**skw)
+    so.set_timesteps(3)
+    sp.set_timesteps(3)
+    torch.manual_seed(4)
+    noise = torch.randn(2, akw["latent_channels"], 8, 8)
+    seg = G.seg_onehot((2, 3, 32, 32))
+    ucfg = G.unet_oracle_cfg(ukw)
+    lat = O.diffusion_sample(lambda x, t, c: O.unet_forward(usd, ucfg, x, t, context=c, seg=seg), so, noise)
+    want = O.autoencoderkl_decode(asd, G.aekl_oracle_cfg(akw), lat / 0.7, seg=seg)
+    got = LatentDiffusionInferer(sp, scale_factor=0.7).sample(noise.cuda(), ae.cuda(), un.cuda(), sp, seg=seg.cuda(),
+                                                             verbose=False)
+    check(got, want, TRAJ_TOL, "SPADE latent sampling")
+    other = nets().SPADEDiffusionModelUNet(**dict(ukw, label_nc=5)).cuda().eval()
+    with pytest.raises(ValueError):
+        LatentDiffusionInferer(sp, scale_factor=0.7).sample(noise.cuda(), ae, other, sp, seg=seg.cuda(), verbose=False)
+
+
 def test_no_cpu_path(cuda_device):
     m = nets().DiffusionModelUNet(2, 1, 1, num_res_blocks=1, num_channels=(8, 8), attention_levels=(False, False),
                                   norm_num_groups=4).cuda()
