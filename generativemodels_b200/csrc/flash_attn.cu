@@ -503,10 +503,8 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
         const float m_new = need ? mx : m_used;
         const float factor = (need && m_used > -INFINITY) ? exp2f(m_used - m_new) : 1.0f;
         const unsigned any = __ballot_sync(0xffffffffu, need && m_used > -INFINITY);
-        // P buffer pb must have been consumed by the PV MMA two hand-offs ago
         const int pb = pcount & 1;
         FA_T(3);
-        if (pcount >= 2) mbar_wait(p_empty(pb), ((pcount >> 1) & 1) ^ 1u);
         FA_T(4);
         if (any) {
           // O holds blocks < j; PV of block j - 1 must have completed before it is rewritten
@@ -551,6 +549,9 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
           pw[w] = *reinterpret_cast<uint32_t*>(&h);
         }
         FA_T(5);
+        // P buffer pb must have been consumed by the PV MMA two hand-offs ago; with QK^T running two blocks ahead that
+        // MMA sits behind QK_j in the pipe, so the wait comes as late as possible — after the exponentials
+        if (pcount >= 2) mbar_wait(p_empty(pb), ((pcount >> 1) & 1) ^ 1u);
         tmem_st32(tP + lane_addr + pb * 32, pw);
         if constexpr (REPLAY) {
           // the same 64 probabilities to this row of the slab (128 contiguous bytes), for pass 2

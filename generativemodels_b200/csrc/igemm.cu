@@ -553,7 +553,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
     const int rd = r >> (p.bw_log2 + p.bh_log2);
     float* addv = add_tiles + (warp - 2) * BN;
     int add_key = -1;
-    const bool fast_ok = p.out_vec && !p.out_staged && !p.stat_ptr && !p.row_bias &&
+    const bool fast_ok = p.out_vec && !p.out_staged && !p.stat_ptr &&
                          (!p.res_ptr || (p.res_vec && p.res_dtype == B200_DT_BF16));
     // GroupNorm partial sums for the consumer of this tensor: per warp [BN/8 groups][sum, sumsq] in shared memory
     // (aliases the staged-store tiles, which this mode excludes), flushed to this warp's private global slot
@@ -623,7 +623,14 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
           else tmem_ld16(taddr + c0, raw);
           tmem_ld_wait();
           float gs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          if (row_ok) epilogue_fast<CH>(p, raw, addv + c0, rv, out_off, n0 + c0, gn_on ? gs : nullptr);
+          if (row_ok) {
+            if (p.row_bias) {                       // operand-swapped GEMMs (V^T = W X^T): the bias runs along the rows
+              const float rb = __ldg(p.row_bias + ow);
+#pragma unroll
+              for (int j = 0; j < CH; ++j) raw[j] = __float_as_uint(__uint_as_float(raw[j]) + rb);
+            }
+            epilogue_fast<CH>(p, raw, addv + c0, rv, out_off, n0 + c0, gn_on ? gs : nullptr);
+          }
           if constexpr (CH == 32) {
             if (gn_on) {
               // 8 values x 32 lanes -> one total per lane: transpose-reduce over lane bits 4,3,2, butterfly over 1,0;
@@ -909,13 +916,13 @@ extern "C" int b200_igemm(const b200_igemm_params* p, void* stream_v) {
   {
     // rows far apart in memory (wide row-major GEMM outputs): stage the tile through smem for coalesced row stores
     const long long esz = (p->out_dtype == B200_DT_BF16) ? 2 : 4;
-    d.out_staged = (p->out_sW * esz > 2048) ? 1 : 0;
+    // (bf16 rows of 32 columns are already whole 64-byte segments per lane: those take the vectorised direct path)
+    d.out_staged = (p->out_sW * esz > 2048 && p->out_dtype == B200_DT_F32) ? 1 : 0;
   }
   d.gn_partial = p->gn_partial; d.gn_slots = p->gn_slots; d.gn_slot0 = p->gn_slot0;
   if (p->gn_partial) {
     // the partials ride on the vectorised epilogue: every column chunk must be a full 32-wide bf16 vector chunk
-    B200_CHECK_ARG(p->out_dtype == B200_DT_BF16 && p->cout % 32 == 0 && d.out_vec && !d.out_staged && !p->stat_ptr &&
-                   !p->row_bias && p->gn_slot0 >= 0 && p->gn_slot0 + 4 * sm_count() <= p->gn_slots,
+    B200_CHECK_ARG(p->out_dtype == B200_DT_BF16 && p->cout % 32 == 0 && d.out_vec && !d.out_staged && !p->stat_ptr && p->gn_slot0 >= 0 && p->gn_slot0 + 4 * sm_count() <= p->gn_slots,
                    "igemm: gn_partial needs a bf16 vector-aligned output with cout %% 32 == 0 and 4 x SM-count slots");
   }
   d.stat_ptr = p->stat_ptr;
