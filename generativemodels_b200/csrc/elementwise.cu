@@ -466,24 +466,35 @@ struct TapGeom {
 
 __global__ void tap_gather_kernel(const __nv_bfloat16* __restrict__ x, int C, int x_pitch, TapGeom g,
                                   __nv_bfloat16* __restrict__ out, int out_pitch) {
+  // one thread per (output voxel, 8-column vector): the voxel coordinates are decoded once, the row is written with
+  // 16-byte stores (out_pitch is a multiple of 8: it is the K pitch of the GEMM that follows)
   const int taps = g.kd * g.kh * g.kw;
-  const long long total = (long long)g.N * g.OD * g.OH * g.OW * out_pitch;
+  const int vecs = out_pitch >> 3;
+  const long long total = (long long)g.N * g.OD * g.OH * g.OW * vecs;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int col = (int)(i % out_pitch);
-    long long v = i / out_pitch;
-    __nv_bfloat16 val = __float2bfloat16_rn(0.f);
-    if (col < taps * C) {
-      const int tap = col / C, c = col - tap * C;
-      const int cw = tap % g.kw, bh = (tap / g.kw) % g.kh, ad = tap / (g.kw * g.kh);
-      const int ow = (int)(v % g.OW); long long t = v / g.OW;
-      const int oh = (int)(t % g.OH); t /= g.OH;
-      const int od = (int)(t % g.OD); const int n = (int)(t / g.OD);
-      const int iw = ow * g.sw + cw - g.pw, ih = oh * g.sh + bh - g.ph, id = od * g.sd + ad - g.pd;
-      if (iw >= 0 && iw < g.W && ih >= 0 && ih < g.H && id >= 0 && id < g.D)
-        val = x[((((long long)n * g.D + id) * g.H + ih) * g.W + iw) * x_pitch + c];
+    const int v8 = (int)(i % vecs);
+    long long v = i / vecs;
+    const int ow = (int)(v % g.OW); long long t = v / g.OW;
+    const int oh = (int)(t % g.OH); t /= g.OH;
+    const int od = (int)(t % g.OD); const int n = (int)(t / g.OD);
+    const __nv_bfloat16* xn = x + (long long)n * g.D * g.H * g.W * x_pitch;
+    __align__(16) __nv_bfloat16 vals[8];
+    int col = v8 * 8;
+    int tap = col / C, c = col - tap * C;
+#pragma unroll
+    for (int e = 0; e < 8; ++e, ++col) {
+      __nv_bfloat16 val = __float2bfloat16_rn(0.f);
+      if (tap < taps) {
+        const int cw = tap % g.kw, bh = (tap / g.kw) % g.kh, ad = tap / (g.kw * g.kh);
+        const int iw = ow * g.sw + cw - g.pw, ih = oh * g.sh + bh - g.ph, id = od * g.sd + ad - g.pd;
+        if (iw >= 0 && iw < g.W && ih >= 0 && ih < g.H && id >= 0 && id < g.D)
+          val = xn[(((long long)id * g.H + ih) * g.W + iw) * x_pitch + c];
+      }
+      vals[e] = val;
+      if (++c == C) { c = 0; ++tap; }
     }
-    out[i] = val;
+    *reinterpret_cast<uint4*>(out + v * out_pitch + v8 * 8) = *reinterpret_cast<const uint4*>(vals);
   }
 }
 
@@ -602,8 +613,9 @@ extern "C" int b200_tap_gather(const void* x, int32_t C, int32_t x_pitch, const 
   B200_CHECK_ARG(x && out && geom && C >= 1 && x_pitch >= C, "tap_gather: bad arguments");
   b200::TapGeom g;
   memcpy(&g, geom, sizeof(g));
-  B200_CHECK_ARG(tap_geom_ok(g) && out_pitch >= g.kd * g.kh * g.kw * C, "tap_gather: bad geometry");
-  const long long total = (long long)g.N * g.OD * g.OH * g.OW * out_pitch;
+  B200_CHECK_ARG(tap_geom_ok(g) && out_pitch >= g.kd * g.kh * g.kw * C && out_pitch % 8 == 0 &&
+                 ((uintptr_t)out % 16) == 0, "tap_gather: bad geometry (out_pitch must be a multiple of 8)");
+  const long long total = (long long)g.N * g.OD * g.OH * g.OW * (out_pitch / 8);
   tap_gather_kernel<<<grid_for(total), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), C, x_pitch, g,
                                                         reinterpret_cast<__nv_bfloat16*>(out), out_pitch);
   B200_LAUNCH_CHECK("tap_gather_kernel");
