@@ -661,349 +661,6 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
   }
 }
 
-
-// ------------------------------------------------------------------------------------------------
-// head_dim 512 with a workspace: two-phase kernel.
-//
-// A 128 x 512 fp32 output tile needs all 512 tensor-memory columns, so scores and output cannot be resident together.
-// Instead of slicing the output (and recomputing, or half-replaying, the scores) the item is split by OPERATION:
-//   phase 1   S_j = Q K_j^T for every 64-key block (6 score buffers in TMEM, the tensor pipe never waits for the
-//             softmax), online softmax statistics, P_j = 2^(S_j c - m) written as bf16 to this CTA's slab in global
-//             memory.  No P V here, hence no O, no S -> softmax -> P -> PV latency chain and no V traffic.
-//   phase 2   O (all 512 columns) += P_j V_j as a plain GEMM stream: P tiles (16 KB) and V^T halves (32 KB) arrive by
-//             TMA through a 7 x 32 KB ring that overlays the Q / K regions; L2 prefetch of the slab 24 blocks ahead.
-// The lazy-rescale decisions of phase 1 (reference maximum raised by more than 2^8) only touch the running row sum
-// there; they are logged per warp and replayed on O at the same block positions in phase 2 (gated mode, rare).
-// Tensor work is exactly the algorithmic 4 T S d; the price is 2 x T x S bf16 of slab traffic that overlaps it.
-// ------------------------------------------------------------------------------------------------
-static constexpr int kP1Slots = 6;       // phase-1 K ring: 16 KB slots (two 64-channel chunks of one key block)
-static constexpr int kP2Slots = 7;       // phase-2 ring: 32 KB slots over Q + K regions
-static constexpr int kNS = 6;            // score buffers (64 TMEM columns each)
-
-__global__ void __launch_bounds__(kThreads, 1) flash512_two_phase_kernel(const __grid_constant__ FlashDev p) {
-  constexpr int DCH = 8;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = base;
-  const uint32_t sK = sQ + DCH * kQChunkBytes;                        // 6 x 16 KB
-  const uint32_t bars = sK + kP1Slots * 16384;                       // = base + 224 KB
-  const uint32_t q_full = bars, q_empty = bars + 8;
-  auto kf = [&](int s) { return bars + 16 + 8u * s; };                // 8 ring slots (full / empty)
-  auto ke = [&](int s) { return bars + 80 + 8u * s; };
-  auto sf = [&](int b) { return bars + 144 + 8u * b; };               // kNS score buffers
-  auto se = [&](int b) { return bars + 192 + 8u * b; };
-  auto pf = [&](int b) { return bars + 240 + 8u * b; };               // gated phase 2: rescale hand-offs
-  auto pe = [&](int b) { return bars + 256 + 8u * b; };
-  const uint32_t o_full = bars + 272, o_empty = bars + 280, p1_done = bars + 288, r_done = bars + 296;
-  const uint32_t tmem_slot = bars + 304;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-  volatile int* ev_flags = reinterpret_cast<volatile int*>(tmem_slot_ptr + 2);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0 && lane == 0) {
-    mbar_init(q_full, 1); mbar_init(q_empty, 1);
-    for (int s = 0; s < 8; ++s) { mbar_init(kf(s), 1); mbar_init(ke(s), 1); }
-    for (int b = 0; b < kNS; ++b) { mbar_init(sf(b), 1); mbar_init(se(b), 4); }
-    for (int b = 0; b < 2; ++b) { mbar_init(pf(b), 4); mbar_init(pe(b), 1); }
-    mbar_init(o_full, 1); mbar_init(o_empty, 4); mbar_init(p1_done, 4); mbar_init(r_done, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  fence_before();
-  __syncthreads();
-  fence_after();
-  const uint32_t tmem = *tmem_slot_ptr;      // phase 1: score buffers at columns [0, 384); phase 2: O at [0, 512)
-  const int n_kv = p.n_kv;
-
-  if (warp == 0) {
-    // =========================== TMA producer ===========================
-    uint32_t ebits = 0, icount = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++icount) {
-      const Item it = decode<true>(p, item);
-      const int ch0 = it.h * p.dh;
-      mbar_wait_warp(r_done, (icount & 1) ^ 1u);                 // previous item's phase-2 ring drained
-      if (elect_one()) {
-        mbar_expect_tx(q_full, DCH * kQChunkBytes);
-#pragma unroll
-        for (int c = 0; c < DCH; ++c) tma_load_3d(&p.tmQ, q_full, sQ + c * kQChunkBytes, ch0 + c * 64, it.qt * kBM, it.b);
-      }
-      __syncwarp();
-      int slot = 0;
-      for (int j = 0; j < n_kv; ++j) {
-#pragma unroll
-        for (int step = 0; step < 4; ++step) {
-          mbar_wait_warp(ke(slot), ((ebits >> slot) & 1u) ^ 1u);
-          if (elect_one()) {
-            mbar_expect_tx(kf(slot), 16384);
-            tma_load_3d(&p.tmK, kf(slot), sK + slot * 16384, ch0 + step * 128, j * kBKV, it.b);
-            tma_load_3d(&p.tmK, kf(slot), sK + slot * 16384 + kKChunkBytes, ch0 + step * 128 + 64, j * kBKV, it.b);
-          }
-          __syncwarp();
-          ebits ^= 1u << slot;
-          if (++slot == kP1Slots) slot = 0;
-        }
-      }
-      // ---- phase 2 ----
-      mbar_wait_warp(q_empty, icount & 1);                       // every QK^T MMA has completed: Q and K ring are free
-      mbar_wait_warp(p1_done, icount & 1);                       // every P tile is written and visible to the async proxy
-      constexpr int kPrefetch = 24;
-      if (elect_one()) {
-        for (int j = 0; j < kPrefetch && j < n_kv; ++j) tma_prefetch_3d(&p.tmP, j * kBKV, 0, blockIdx.x);
-      }
-      __syncwarp();
-      slot = 0;
-      for (int j = 0; j < n_kv; ++j) {
-#pragma unroll
-        for (int part = 0; part < 3; ++part) {                   // P_j, V^T_j rows [0,256), V^T_j rows [256,512)
-          mbar_wait_warp(ke(slot), ((ebits >> slot) & 1u) ^ 1u);
-          if (elect_one()) {
-            const uint32_t dst = sQ + slot * 32768;
-            if (part == 0) {
-              if (j + kPrefetch < n_kv) tma_prefetch_3d(&p.tmP, (j + kPrefetch) * kBKV, 0, blockIdx.x);
-              mbar_expect_tx(kf(slot), 16384);
-              tma_load_3d(&p.tmP, kf(slot), dst, j * kBKV, 0, blockIdx.x);
-            } else {
-              mbar_expect_tx(kf(slot), 32768);
-              tma_load_3d(&p.tmVt, kf(slot), dst, j * kBKV, ch0 + (part - 1) * 256, it.b);
-            }
-          }
-          __syncwarp();
-          ebits ^= 1u << slot;
-          if (++slot == kP2Slots) slot = 0;
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // =========================== MMA issuer ===========================
-    const uint32_t idesc_s = idesc_bf16(kBM, kBKV);
-    const uint32_t idesc_o = idesc_bf16(kBM, 256);
-    const uint32_t q_lo = desc_lo(sQ), k_lo = desc_lo(sK);
-    uint32_t fbits = 0, scount = 0, gcount = 0, icount = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++icount) {
-      mbar_wait_warp(q_full, icount & 1);
-      mbar_wait_warp(o_empty, (icount & 1) ^ 1u);                // the score buffers alias O: previous epilogue done
-      fence_after();
-      int slot = 0;
-      for (int j = 0; j < n_kv; ++j) {
-        const int sb = scount % kNS;
-        mbar_wait_warp(se(sb), ((scount / kNS) & 1) ^ 1u);
-        fence_after();
-        const uint32_t d_s = tmem + sb * kBKV;
-#pragma unroll
-        for (int step = 0; step < 4; ++step) {
-          mbar_wait_warp(kf(slot), (fbits >> slot) & 1u);
-          fence_after();
-          if (elect_one()) {
-            const uint32_t b_lo = k_lo + slot * (16384 >> 4);
-#pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk)
-                umma_bf16(d_s, desc64(q_lo + (step * 2 + cc) * (kQChunkBytes >> 4) + 2 * kk),
-                          desc64(b_lo + cc * (kKChunkBytes >> 4) + 2 * kk), idesc_s, (step | cc | kk) != 0 ? 1u : 0u);
-            }
-            umma_commit(ke(slot));
-            if (step == 3) {
-              umma_commit(sf(sb));
-              if (j == n_kv - 1) umma_commit(q_empty);
-            }
-          }
-          __syncwarp();
-          fbits ^= 1u << slot;
-          if (++slot == kP1Slots) slot = 0;
-        }
-        ++scount;
-      }
-      // ---- phase 2: O += P_j V_j, both operands from shared memory ----
-      mbar_wait_warp(p1_done, icount & 1);       // softmax warps are done with every score buffer; rescale flags visible
-      const bool gated = (ev_flags[0] | ev_flags[1] | ev_flags[2] | ev_flags[3]) != 0;
-      fence_after();
-      slot = 0;
-      for (int j = 0; j < n_kv; ++j) {
-        const int pslot = slot;
-        mbar_wait_warp(kf(pslot), (fbits >> pslot) & 1u);
-        fbits ^= 1u << pslot;
-        if (++slot == kP2Slots) slot = 0;
-        const int gb = gcount & 1;
-        if (gated) mbar_wait_warp(pf(gb), (gcount >> 1) & 1);
-        const uint32_t a_lo = q_lo + pslot * (32768 >> 4);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          mbar_wait_warp(kf(slot), (fbits >> slot) & 1u);
-          fence_after();
-          if (elect_one()) {
-            const uint32_t b_lo = q_lo + slot * (32768 >> 4);
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              umma_bf16(tmem + h * 256, desc64(a_lo + 2 * kk), desc64(b_lo + 2 * kk), idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
-            umma_commit(ke(slot));
-            if (h == 1) {
-              umma_commit(ke(pslot));
-              if (gated) umma_commit(pe(gb));
-              if (j == n_kv - 1) { umma_commit(o_full); umma_commit(r_done); }
-            }
-          }
-          __syncwarp();
-          fbits ^= 1u << slot;
-          if (++slot == kP2Slots) slot = 0;
-        }
-        if (gated) ++gcount;
-      }
-    }
-  } else {
-    // =========================== softmax (phase 1), rescale replay + epilogue (phase 2) ===========================
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    uint32_t scount = 0, gcount = 0, icount = 0;
-    __nv_bfloat16* slab_row = p.pslab + ((long long)blockIdx.x * kBM + row) * p.p_pitch;
-    float* ev_fac = p.ev_fac + ((long long)blockIdx.x * 4 + q) * (long long)n_kv * 32;
-    int* ev_blk = p.ev_blk + ((long long)blockIdx.x * 4 + q) * (long long)n_kv;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++icount) {
-      const Item it = decode<true>(p, item);
-      float m_used = -INFINITY, l_run = 0.f;
-      int n_ev = 0;
-      for (int j = 0; j < n_kv; ++j, ++scount) {
-        const int sb = scount % kNS;
-        mbar_wait(sf(sb), (scount / kNS) & 1);
-        fence_after();
-        uint32_t raw[64];
-        tmem_ld32(tmem + lane_addr + sb * kBKV, raw);
-        tmem_ld32(tmem + lane_addr + sb * kBKV + 32, raw + 32);
-        tmem_ld_wait();
-        fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(se(sb));
-        const int kv_valid = p.S - j * kBKV;
-        float mx8[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) mx8[e] = -INFINITY;
-        if (kv_valid >= kBKV) {
-#pragma unroll
-          for (int c = 0; c < 64; ++c) mx8[c & 7] = fmaxf(mx8[c & 7], __uint_as_float(raw[c]));
-        } else {
-#pragma unroll
-          for (int c = 0; c < 64; ++c) {
-            const float sv = c < kv_valid ? __uint_as_float(raw[c]) : -INFINITY;
-            raw[c] = __float_as_uint(sv);
-            mx8[c & 7] = fmaxf(mx8[c & 7], sv);
-          }
-        }
-        const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
-                               fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7]))) * p.scale_log2;
-        const bool need = (mx > m_used + kRescaleThreshold);
-        const float m_new = need ? mx : m_used;
-        const float factor = (need && m_used > -INFINITY) ? exp2f(m_used - m_new) : 1.0f;
-        const unsigned any = __ballot_sync(0xffffffffu, need && m_used > -INFINITY);
-        if (any) {                    // O does not exist yet: only the running sum is rescaled now, O in phase 2
-          ev_fac[(long long)n_ev * 32 + lane] = factor;
-          if (lane == 0) ev_blk[n_ev] = j;
-          ++n_ev;
-        }
-        l_run *= factor;
-        m_used = m_new;
-        const float neg_m = -m_used;
-        float sum8[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) sum8[e] = 0.f;
-        uint32_t pw[32];
-#pragma unroll
-        for (int w = 0; w < 32; ++w) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(raw[2 * w]), p.scale_log2, neg_m));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(raw[2 * w + 1]), p.scale_log2, neg_m));
-          __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
-          pw[w] = *reinterpret_cast<uint32_t*>(&h);
-          // the normaliser sums the probabilities as the MMA will see them (bf16-rounded)
-          const float2 r = __bfloat1622float2(h);
-          sum8[(2 * w) & 7] += r.x;
-          sum8[(2 * w + 1) & 7] += r.y;
-        }
-        __nv_bfloat16* dst = slab_row + (long long)j * kBKV;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) stg256(dst + g * 16, pw + g * 8);
-        l_run += ((sum8[0] + sum8[1]) + (sum8[2] + sum8[3])) + ((sum8[4] + sum8[5]) + (sum8[6] + sum8[7]));
-      }
-      if (lane == 0) ev_flags[q] = n_ev > 0 ? 1 : 0;
-      __threadfence();
-      asm volatile("fence.proxy.async.global;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p1_done);
-      mbar_wait(p1_done, icount & 1);
-      const bool gated = (ev_flags[0] | ev_flags[1] | ev_flags[2] | ev_flags[3]) != 0;
-      if (gated) {
-        int e_next = 0;
-        int next_blk = (n_ev > 0) ? ev_blk[0] : 0x7fffffff;
-        for (int j = 0; j < n_kv; ++j, ++gcount) {
-          const int gb = gcount & 1;
-          if (gcount >= 2) mbar_wait(pe(gb), ((gcount >> 1) & 1) ^ 1u);
-          if (j == next_blk) {                    // warp-uniform; j >= 1 by construction
-            const uint32_t prev = gcount - 1;
-            mbar_wait(pe(prev & 1), (prev >> 1) & 1);          // O holds blocks < j
-            fence_after();
-            const float factor = ev_fac[(long long)e_next * 32 + lane];
-            for (int c0 = 0; c0 < 512; c0 += 32) {
-              uint32_t o[32];
-              tmem_ld32(tmem + lane_addr + c0, o);
-              tmem_ld_wait();
-#pragma unroll
-              for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * factor);
-              tmem_st32(tmem + lane_addr + c0, o);
-            }
-            tmem_st_wait();
-            fence_before();
-            ++e_next;
-            next_blk = (e_next < n_ev) ? ev_blk[e_next] : 0x7fffffff;
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(pf(gb));
-        }
-      }
-      // ---- epilogue: O / l (+ residual) -> bf16, all 512 columns ----
-      mbar_wait(o_full, icount & 1);
-      fence_after();
-      const float inv = 1.0f / l_run;
-      const int t = it.qt * kBM + row;
-      const bool ok = t < p.T;
-      const long long col0 = (long long)it.h * p.dh;
-      __nv_bfloat16* orow = p.out + it.b * p.out_bstride + (long long)t * p.out_pitch + col0;
-      const __nv_bfloat16* rrow = p.res ? p.res + it.b * p.res_bstride + (long long)t * p.res_pitch + col0 : nullptr;
-      for (int c0 = 0; c0 < 512; c0 += 32) {
-        uint32_t o[32];
-        tmem_ld32(tmem + lane_addr + c0, o);
-        tmem_ld_wait();
-        if (ok) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float f[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(o[g * 8 + e]) * inv;
-            if (rrow) {
-              float rf[8];
-              unpack8(__ldg(reinterpret_cast<const uint4*>(rrow + c0 + g * 8)), rf);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] += rf[e];
-            }
-            *reinterpret_cast<uint4*>(orow + c0 + g * 8) = pack8(f);
-          }
-        }
-      }
-      fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(o_empty);
-    }
-  }
-  fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
-  }
-}
-
 static PFN_cuTensorMapEncodeTiled g_encode = nullptr;
 static std::once_flag g_once;
 static void load_encode() {
@@ -1129,16 +786,8 @@ extern "C" int b200_attention_flash(const b200_flash_params* a, void* stream_v) 
     case 2: B200_FLASH_LAUNCH(2, false); break;
     case 4: B200_FLASH_LAUNCH(4, false); break;
     default:
-      if (replay) {
-        static bool attr2_done = false;
-        if (!attr2_done) {
-          B200_CUDA(cudaFuncSetAttribute(fa::flash512_two_phase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-          attr2_done = true;
-        }
-        fa::flash512_two_phase_kernel<<<grid, fa::kThreads, smem, stream>>>(d);
-      } else {
-        B200_FLASH_LAUNCH(8, false);
-      }
+      if (replay) B200_FLASH_LAUNCH(8, true);
+      else B200_FLASH_LAUNCH(8, false);
       break;
   }
 #undef B200_FLASH_LAUNCH

@@ -398,9 +398,9 @@ def test_attention_flash_rescale(cuda_device, monkeypatch, dh, replay):
 
 
 def test_attention_flash_replay_matches_recompute(cuda_device, monkeypatch):
-    """head_dim 512: the two-phase kernel (phase 1 scores + softmax with P tiles written to the slab, phase 2
-    O += P V over all 512 output columns) against the recompute variant on a multi-item, multi-batch, ragged problem
-    (T, S not multiples of the tiles; more work items than SMs so slabs and rescale logs are reused across items)."""
+    """head_dim 512: the probability-replay variant (P tiles written once, streamed back for output channels
+    256..511) against the recompute variant on a multi-item, multi-batch, ragged problem (T, S not multiples of the
+    tiles; more work items than SMs so slabs and rescale logs are reused across items)."""
     ops = _ops()
     torch.manual_seed(12)
     B, T, S, dh = 2, 128 * 90 + 37, 1000 + 21, 512
@@ -413,7 +413,8 @@ def test_attention_flash_replay_matches_recompute(cuda_device, monkeypatch):
     a = ops.attention(*args, vt=vt, residual=res).float().cpu()
     monkeypatch.setattr(ops, "_FLASH_REPLAY", False)
     b = ops.attention(*args, vt=vt, residual=res).float().cpu()
-    assert_close(a, b, 1e-2, "two-phase (stored probabilities) vs recompute variant")
+    assert torch.equal(a[..., :256], b[..., :256])          # pass 1 is the same code
+    assert_close(a[..., 256:], b[..., 256:], 1e-2, "replayed half vs recomputed half")
     ref = _attn_ref(bf(q[:1, :256]), bf(k[:1]), bf(v[:1]), 1, dh, 1 / math.sqrt(dh)) + res[:1, :256].float().cpu()
     assert_close(a[:1, :256], ref, 2e-2, "replay vs fp32 reference")
 
