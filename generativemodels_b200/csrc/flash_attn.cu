@@ -29,7 +29,8 @@ struct FlashDev {
   alignas(64) CUtensorMap tmQ;    // [B][T][C]      box (64 ch, 128 rows)
   alignas(64) CUtensorMap tmK;    // [B][S][C]      box (64 ch, 64 rows)
   alignas(64) CUtensorMap tmVt;   // [B][C][S]      box (64 keys, DV rows)
-  alignas(64) CUtensorMap tmP;    // [grid][128][S_pad] probability slabs (replay variant), box (64 keys, 128 rows)
+  alignas(64) CUtensorMap tmP;    // [grid][n_kv * 128][64] probability slabs (replay variant): one contiguous 16 KB tile
+                                  // per key block, box (64 keys, 128 rows)
   int B, T, S, heads, dh, d_chunks, dv, n_dv;
   int q_tiles, n_items, n_kv;
   float scale_log2;
@@ -37,8 +38,10 @@ struct FlashDev {
   long long out_bstride, out_pitch;
   const __nv_bfloat16* res;
   long long res_bstride, res_pitch;
-  __nv_bfloat16* pslab;           // replay workspace: [grid][128][p_pitch]
-  long long p_pitch;
+  __nv_bfloat16* pslab;           // replay workspace: [grid][n_kv][128 rows][64 keys] — tile-contiguous, so that the
+                                  // warps' row stores coalesce to 4 KB runs and every TMA tile is one 16 KB burst
+                                  // (row-major [128][S] slabs made every tile 128 scattered 128-byte DRAM accesses)
+  long long p_pitch;              // elements per CTA slab = n_kv * 128 * 64
   float* ev_fac;                  // [grid][4 warps][n_kv][32] logged rescale factors
   int* ev_blk;                    // [grid][4 warps][n_kv]     block index of each logged rescale
 };
@@ -327,16 +330,16 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
           // kPrefetch blocks ahead of the 4-stage shared-memory pipeline so that its loads see L2 latency only
           constexpr int kPrefetch = 24;
           if (elect_one()) {
-            for (int j = 0; j < kPrefetch && j < n_kv; ++j) tma_prefetch_3d(&p.tmP, j * kBKV, 0, blockIdx.x);
+            for (int j = 0; j < kPrefetch && j < n_kv; ++j) tma_prefetch_3d(&p.tmP, 0, j * kBM, blockIdx.x);
           }
           __syncwarp();
           for (int j = 0; j < n_kv; ++j) {
             mbar_wait_warp(k_empty(kst), kph ^ 1u);
             if (elect_one()) {
-              if (j + kPrefetch < n_kv) tma_prefetch_3d(&p.tmP, (j + kPrefetch) * kBKV, 0, blockIdx.x);
+              if (j + kPrefetch < n_kv) tma_prefetch_3d(&p.tmP, 0, (j + kPrefetch) * kBM, blockIdx.x);
               const uint32_t st = sQ + kst * kRStageBytes;
               mbar_expect_tx(k_full(kst), kRStageBytes);
-              tma_load_3d(&p.tmP, k_full(kst), st, j * kBKV, 0, blockIdx.x);
+              tma_load_3d(&p.tmP, k_full(kst), st, 0, j * kBM, blockIdx.x);
               tma_load_3d(&p.tmVt, k_full(kst), st + kQChunkBytes, j * kBKV, ch0 + 256, it.b);
             }
             __syncwarp();
@@ -458,7 +461,7 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
     uint32_t ocount = 0;       // epilogues done
     uint32_t icount = 0;
     // REPLAY: this CTA's probability slab and this warp's rescale log
-    __nv_bfloat16* slab_row = REPLAY ? p.pslab + ((long long)blockIdx.x * kBM + row) * p.p_pitch : nullptr;
+    __nv_bfloat16* slab_row = REPLAY ? p.pslab + (long long)blockIdx.x * p.p_pitch + row * kBKV : nullptr;
     float* ev_fac = REPLAY ? p.ev_fac + ((long long)blockIdx.x * 4 + q) * (long long)n_kv * 32 : nullptr;
     int* ev_blk = REPLAY ? p.ev_blk + ((long long)blockIdx.x * 4 + q) * (long long)n_kv : nullptr;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++icount) {
@@ -555,7 +558,7 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
         tmem_st32(tP + lane_addr + pb * 32, pw);
         if constexpr (REPLAY) {
           // the same 64 probabilities to this row of the slab (128 contiguous bytes), for pass 2
-          __nv_bfloat16* dst = slab_row + (long long)j * kBKV;
+          __nv_bfloat16* dst = slab_row + (long long)j * (kBM * kBKV);
 #pragma unroll
           for (int g = 0; g < 4; ++g) stg256(dst + g * 16, pw + g * 8);
         }
@@ -765,11 +768,11 @@ extern "C" int b200_attention_flash(const b200_flash_params* a, void* stream_v) 
     B200_CHECK_ARG(grid == rp.grid && d.n_kv == rp.n_kv, "attention_flash: internal replay plan mismatch");
     uint8_t* ws = static_cast<uint8_t*>(a->workspace);
     d.pslab = reinterpret_cast<__nv_bfloat16*>(ws);
-    d.p_pitch = (long long)d.n_kv * fa::kBKV;
+    d.p_pitch = (long long)d.n_kv * fa::kBM * fa::kBKV;
     d.ev_fac = reinterpret_cast<float*>(ws + rp.slab_bytes);
     d.ev_blk = reinterpret_cast<int*>(ws + rp.slab_bytes + rp.fac_bytes);
-    if ((rc = fa::encode3(&d.tmP, d.pslab, (cuuint64_t)d.p_pitch, fa::kBM, grid, (cuuint64_t)d.p_pitch * 2,
-                          (cuuint64_t)fa::kBM * d.p_pitch * 2, fa::kBKV, fa::kBM, "P slab"))) return rc;
+    if ((rc = fa::encode3(&d.tmP, d.pslab, fa::kBKV, (cuuint64_t)d.n_kv * fa::kBM, grid, (cuuint64_t)fa::kBKV * 2,
+                          (cuuint64_t)d.p_pitch * 2, fa::kBKV, fa::kBM, "P slab"))) return rc;
   }
 #define B200_FLASH_LAUNCH(DCH, RP)                                                                                    \
   do {                                                                                                                \

@@ -17,7 +17,7 @@ vt = torch.randn(1, dh, S, device="cuda").to(torch.bfloat16)
 modes = [("replay", True), ("recompute", False)] if len(sys.argv) < 2 else [(sys.argv[1], sys.argv[1] == "replay")]
 for name, flag in modes:
     ops._FLASH_REPLAY = flag
-    for i in range(3):
+    for i in range(6):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         o = ops.attention(q, k, None, 1, dh, 1 / math.sqrt(dh), vt=vt)
