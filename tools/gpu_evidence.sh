@@ -9,7 +9,7 @@ timeout -k 10 1500 ncu --metrics gpu__time_duration.sum --clock-control none --c
   python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
 tail -2 gpurun_out/ncu_bench.log
 timeout -k 10 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
-  -k regex:"igemm_tc_kernel<\(int\)256" -s 6 -c 1 -f -o gpurun_out/prof_igemm \
+  -k regex:"igemm_tc_kernel<\(int\)256" -s 1 -c 1 -f -o gpurun_out/prof_igemm \
   python tools/perf_c3.py --shape 160,224,160 --iters 0 --breakdown 0 > gpurun_out/ncu_igemm.log 2>&1
 tail -2 gpurun_out/ncu_igemm.log
 timeout -k 10 900 ncu --set full --clock-control none --import-source on -k regex:flash_attn -c 1 -f -o gpurun_out/prof_flash \
