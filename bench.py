@@ -314,8 +314,9 @@ def run_b200(args):
                          "frac": achieved / peak_tf if peak_tf else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel (the 256->256
                          # 3x3x3 conv at 160x224x160; algorithmic 5.88e9 B) from the ncu --set full capture in
-                         # profiles/r1_ncu_igemm_conv256_fullres_details.txt
-                         "traffic": 8.11e9,
+                         # profiles/r1_ncu_igemm_conv256_fullres_v6_details.txt (4.24 GB read + 2.91 GB written,
+                         # L2 hit rate 96.5 %, tensor pipe 97.6 % active in that capture)
+                         "traffic": 7.14e9,
                          "kernel": "igemm_tc_kernel<256,4> (3x3x3 convolutions)", "peak_source": which + " sustained bf16",
                          "share_of_step": conv_ms / ms_total if ms_total else None,
                          "launches_timed": len(conv_events)},
