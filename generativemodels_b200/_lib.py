@@ -14,7 +14,7 @@ LIB_PATH = _HERE / "lib" / "libb200gen.so"
 
 B200_OK, B200_EINVAL, B200_ENOTSUP, B200_ECUDA, B200_ENODEV = 0, -1, -2, -3, -4
 DT_BF16, DT_F32 = 0, 1
-ACT_NONE, ACT_RELU, ACT_SILU, ACT_LEAKYRELU = 0, 1, 2, 3
+ACT_NONE, ACT_RELU, ACT_SILU, ACT_LEAKYRELU, ACT_GELU = 0, 1, 2, 3, 4
 PRED_EPSILON, PRED_SAMPLE, PRED_V = 0, 1, 2
 IGEMM_MAX_SEG = 128
 
@@ -120,6 +120,9 @@ SIGNATURES = {
     "b200_geglu": [_P, _I64, _I32, _I32, _P, _I32, _P],
     "b200_softmax_rows": [_P, _I64, _I32, _I64, _P, _I64, _P],
     "b200_softmax_rows_partials": [_P, _I64, _I32, _I64, _P, _I32, _P, _I64, _P],
+    "b200_attention_small_ex": [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, C.c_float, _I32,
+                                _I32, _I32, _P],
+    "b200_embed_tokens": [_P, _I64, _I32, _I32, _P, _P, _I32, _P, _I32, _P],
     "b200_tap_gather": [_P, _I32, _I32, _P, _P, _I32, _P],
     "b200_tap_sum": [_P, _I32, _P, _I32, _P, _P, _I32, _I32, _P],
     "b200_attention_flash": [C.POINTER(FlashParams), _P],

@@ -14,7 +14,7 @@ template <int R>   // R = ceil(dh / 32) registers per lane
 __global__ void attention_small_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
                                        const __nv_bfloat16* __restrict__ v, __nv_bfloat16* __restrict__ out, int B,
                                        int T, int S, int heads, int dh, int q_pitch, int k_pitch, int v_pitch,
-                                       int o_pitch, float scale) {
+                                       int o_pitch, float scale, int kv_rows, int causal, int q_pos0) {
   const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long total = (long long)B * heads * T;
   if (wid >= total) return;
@@ -31,9 +31,13 @@ __global__ void attention_small_kernel(const __nv_bfloat16* __restrict__ q, cons
     acc[r] = 0.f;
   }
   float mx = -INFINITY, denom = 0.f;
-  const __nv_bfloat16* kb = k + (long long)b * S * k_pitch + h * dh;
-  const __nv_bfloat16* vb = v + (long long)b * S * v_pitch + h * dh;
-  for (int s = 0; s < S; ++s) {
+  // kv_rows = rows per batch item in the k / v buffers (a key/value cache holds max_seq rows, S of them valid);
+  // causal: query t (absolute position q_pos0 + t) only sees keys s <= q_pos0 + t (SABlock causal_mask,
+  // blocks/selfattention.py:93-97, 131-132)
+  const __nv_bfloat16* kb = k + (long long)b * kv_rows * k_pitch + h * dh;
+  const __nv_bfloat16* vb = v + (long long)b * kv_rows * v_pitch + h * dh;
+  const int s_end = causal ? min(S, q_pos0 + t + 1) : S;
+  for (int s = 0; s < s_end; ++s) {
     const __nv_bfloat16* kr = kb + (long long)s * k_pitch;
     float dot = 0.f;
 #pragma unroll
@@ -70,8 +74,17 @@ using namespace b200;
 extern "C" int b200_attention_small(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t T,
                                     int32_t S, int32_t heads, int32_t dh, int32_t q_pitch, int32_t k_pitch,
                                     int32_t v_pitch, int32_t o_pitch, float scale, void* stream_v) {
+  return b200_attention_small_ex(q, k, v, out, B, T, S, heads, dh, q_pitch, k_pitch, v_pitch, o_pitch, scale, S, 0, 0,
+                                 stream_v);
+}
+
+extern "C" int b200_attention_small_ex(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t T,
+                                       int32_t S, int32_t heads, int32_t dh, int32_t q_pitch, int32_t k_pitch,
+                                       int32_t v_pitch, int32_t o_pitch, float scale, int32_t kv_rows, int32_t causal,
+                                       int32_t q_pos0, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   B200_CHECK_ARG(q && k && v && out && B >= 1 && T >= 1 && S >= 1 && heads >= 1 && dh >= 1, "attention_small: bad arguments");
+  B200_CHECK_ARG(kv_rows >= S && q_pos0 >= 0, "attention_small: kv_rows %d < S %d or negative query offset", kv_rows, S);
   B200_CHECK_ARG(dh <= 1024, "attention_small: head_dim %d > 1024", dh);
   const long long total = (long long)B * heads * T;
   const int wpb = 8;
@@ -82,7 +95,7 @@ extern "C" int b200_attention_small(const void* q, const void* k, const void* v,
   const __nv_bfloat16* vv = reinterpret_cast<const __nv_bfloat16*>(v);
   __nv_bfloat16* oo = reinterpret_cast<__nv_bfloat16*>(out);
 #define LAUNCH(R) attention_small_kernel<R><<<(unsigned)blocks, wpb * 32, 0, stream>>>( \
-      qq, kk, vv, oo, B, T, S, heads, dh, q_pitch, k_pitch, v_pitch, o_pitch, scale)
+      qq, kk, vv, oo, B, T, S, heads, dh, q_pitch, k_pitch, v_pitch, o_pitch, scale, kv_rows, causal, q_pos0)
   if (dh <= 32) LAUNCH(1);
   else if (dh <= 64) LAUNCH(2);
   else if (dh <= 128) LAUNCH(4);

@@ -537,6 +537,22 @@ __global__ void tap_sum_kernel(const float* __restrict__ y, int y_pitch, TapGeom
   }
 }
 
+
+// token + absolute position embedding rows -> bf16 (nets/transformer.py:97-99)
+__global__ void embed_tokens_kernel(const long long* __restrict__ tokens, long long M, int seq_len, int pos0,
+                                    const float* __restrict__ tok_emb, const float* __restrict__ pos_emb, int C,
+                                    __nv_bfloat16* __restrict__ out, int pitch) {
+  const long long total = M * pitch;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % pitch);
+    const long long m = i / pitch;
+    float v = 0.f;
+    if (c < C) v = tok_emb[tokens[m] * C + c] + pos_emb[(long long)(pos0 + (int)(m % seq_len)) * C + c];
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -639,6 +655,19 @@ extern "C" int b200_tap_sum(const float* y, int32_t y_pitch, const int32_t* geom
     default: tap_sum_kernel<4><<<grid, 256, 0, stream>>>(y, y_pitch, g, bias, out, out_pitch, out_dtype); break;
   }
   B200_LAUNCH_CHECK("tap_sum_kernel");
+  return B200_OK;
+}
+
+
+extern "C" int b200_embed_tokens(const int64_t* tokens, int64_t M, int32_t seq_len, int32_t pos0, const float* tok_emb,
+                                 const float* pos_emb, int32_t C, void* out, int32_t pitch, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(tokens && tok_emb && pos_emb && out && M >= 1 && seq_len >= 1 && pos0 >= 0 && C >= 1 && pitch >= C,
+                 "embed_tokens: bad arguments");
+  embed_tokens_kernel<<<grid_for(M * pitch), 256, 0, stream>>>(reinterpret_cast<const long long*>(tokens), M, seq_len,
+                                                              pos0, tok_emb, pos_emb, C,
+                                                              reinterpret_cast<__nv_bfloat16*>(out), pitch);
+  B200_LAUNCH_CHECK("embed_tokens_kernel");
   return B200_OK;
 }
 

@@ -319,6 +319,9 @@ __device__ __forceinline__ void act_inplace(float* v, int act) {
   } else if (act == B200_ACT_LEAKYRELU) {
 #pragma unroll
     for (int j = 0; j < CH; ++j) v[j] = v[j] > 0.0f ? v[j] : 0.01f * v[j];
+  } else if (act == B200_ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < CH; ++j) v[j] = 0.5f * v[j] * (1.0f + erff(v[j] * 0.70710678118654752f));
   } else {
 #pragma unroll
     for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.0f);

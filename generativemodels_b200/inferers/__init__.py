@@ -1,2 +1,2 @@
 from .inferer import (ControlNetDiffusionInferer, ControlNetLatentDiffusionInferer, DiffusionInferer,  # noqa: F401
-                      LatentDiffusionInferer)
+                      LatentDiffusionInferer, VQVAETransformerInferer)

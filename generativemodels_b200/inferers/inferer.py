@@ -432,3 +432,101 @@ class ControlNetLatentDiffusionInferer(ControlNetDiffusionInferer, _LatentMixin)
                                          conditioning=conditioning, mode=mode, verbose=verbose, seg=seg)
         return self._resample_maps(outputs, inputs.shape[2:], save_intermediates, resample_latent_likelihoods,
                                    resample_interpolation_mode)
+
+
+class VQVAETransformerInferer(Inferer):
+    """inferer.py:1126-1330 — VQ-VAE indices + autoregressive transformer."""
+
+    def __init__(self) -> None:
+        Inferer.__init__(self)
+
+    @staticmethod
+    def _ordered_latent(inputs, vqvae_model, ordering):
+        with torch.no_grad():
+            latent = vqvae_model.index_quantize(inputs)
+        latent_spatial_dim = tuple(latent.shape[1:])
+        latent = latent.reshape(latent.shape[0], -1)
+        return latent[:, ordering.get_sequence_ordering()], latent_spatial_dim
+
+    def __call__(self, inputs: torch.Tensor, vqvae_model, transformer_model, ordering,
+                 condition: torch.Tensor | None = None, return_latent: bool = False):
+        """Teacher-forced forward of a training iteration (inferer.py:1134-1181): BOS-prefixed ordered indices in,
+        next-token logits out (a random max_seq_len window if the sequence is longer)."""
+        latent, latent_spatial_dim = self._ordered_latent(inputs, vqvae_model, ordering)
+        target = latent.clone()
+        latent = torch.nn.functional.pad(latent, (1, 0), "constant", vqvae_model.num_embeddings)
+        latent = latent[:, :-1].long()
+        seq_len = latent.shape[1]
+        max_seq_len = transformer_model.max_seq_len
+        start = torch.randint(low=0, high=seq_len + 1 - max_seq_len, size=(1,)).item() if max_seq_len < seq_len else 0
+        prediction = transformer_model(x=latent[:, start:start + max_seq_len], context=condition)
+        if return_latent:
+            return prediction, target[:, start:start + max_seq_len], latent_spatial_dim
+        return prediction
+
+    @torch.no_grad()
+    def sample(self, latent_spatial_dim, starting_tokens: torch.Tensor, vqvae_model, transformer_model, ordering,
+               conditioning: torch.Tensor | None = None, temperature: float = 1.0, top_k: int | None = None,
+               verbose: bool = True) -> torch.Tensor:
+        """inferer.py:1183-1245.  Token by token: logits of the last position / temperature -> optional top-k ->
+        softmax -> BOS probability zeroed -> torch.multinomial (the draw stays with PyTorch's generator).  While the
+        sequence fits ``max_seq_len`` the logits come from the transformer's key/value cache (one row per step);
+        once the window slides the whole window is recomputed per token, as the reference always does."""
+        import math
+        seq_len = math.prod(latent_spatial_dim)
+        steps = tqdm(range(seq_len)) if (verbose and has_tqdm) else iter(range(seq_len))
+        latent_seq = starting_tokens.long()
+        incremental = hasattr(transformer_model, "new_cache") and latent_seq.size(1) <= transformer_model.max_seq_len
+        cache = transformer_model.new_cache(latent_seq.shape[0], latent_seq.device, conditioning) if incremental else None
+        pending = latent_seq                      # tokens the cache has not seen yet
+        for _ in steps:
+            if cache is not None and cache.length + pending.size(1) <= transformer_model.max_seq_len:
+                logits = transformer_model.step(pending, cache)
+            else:
+                cache = None
+                idx_cond = latent_seq[:, -transformer_model.max_seq_len:]      # the whole sequence while it fits
+                logits = transformer_model(x=idx_cond, context=conditioning)
+            logits = logits[:, -1, :] / temperature
+            if top_k is not None:
+                v, _ = torch.topk(logits, min(top_k, logits.size(-1)))
+                logits[logits < v[:, [-1]]] = -float("Inf")
+            probs = torch.nn.functional.softmax(logits, dim=-1)
+            probs[:, vqvae_model.num_embeddings] = 0          # never sample the BOS token
+            idx_next = torch.multinomial(probs, num_samples=1)
+            latent_seq = torch.cat((latent_seq, idx_next), dim=1)
+            pending = idx_next
+        latent_seq = latent_seq[:, 1:]
+        latent_seq = latent_seq[:, ordering.get_revert_sequence_ordering()]
+        latent = latent_seq.reshape((starting_tokens.shape[0],) + tuple(latent_spatial_dim))
+        return vqvae_model.decode_samples(latent)
+
+    @torch.no_grad()
+    def get_likelihood(self, inputs: torch.Tensor, vqvae_model, transformer_model, ordering,
+                       condition: torch.Tensor | None = None, resample_latent_likelihoods: bool = False,
+                       resample_interpolation_mode: str = "nearest", verbose: bool = False) -> torch.Tensor:
+        """Log-likelihood of every latent token given its predecessors (inferer.py:1247-1330)."""
+        import math
+        if resample_latent_likelihoods and resample_interpolation_mode not in ("nearest", "bilinear", "trilinear"):
+            raise ValueError(f"resample_interpolation mode should be either nearest, bilinear, or trilinear,"
+                             f" got {resample_interpolation_mode}")
+        latent, latent_spatial_dim = self._ordered_latent(inputs, vqvae_model, ordering)
+        seq_len = math.prod(latent_spatial_dim)
+        latent = torch.nn.functional.pad(latent, (1, 0), "constant", vqvae_model.num_embeddings).long()
+        L = transformer_model.max_seq_len
+        logits = transformer_model(x=latent[:, :L], context=condition)
+        probs = torch.nn.functional.softmax(logits, dim=-1)
+        target = latent[:, 1:]
+        probs = torch.gather(probs, 2, target[:, :L].unsqueeze(2)).squeeze(2)
+        if probs.shape[1] < target.shape[1]:
+            steps = tqdm(range(L, seq_len)) if (verbose and has_tqdm) else iter(range(L, seq_len))
+            for i in steps:
+                lg = transformer_model(x=latent[:, i + 1 - L:i + 1], context=condition)[:, -1, :]
+                p = torch.gather(torch.nn.functional.softmax(lg, dim=-1), 1, target[:, i].unsqueeze(1))
+                probs = torch.cat((probs, p), dim=1)
+        probs = torch.log(probs)
+        probs = probs[:, ordering.get_revert_sequence_ordering()]
+        probs_reshaped = probs.reshape((inputs.shape[0],) + latent_spatial_dim)
+        if resample_latent_likelihoods:
+            probs_reshaped = nn.Upsample(size=inputs.shape[2:], mode=resample_interpolation_mode)(
+                probs_reshaped[:, None, ...])
+        return probs_reshaped

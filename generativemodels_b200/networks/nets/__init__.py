@@ -4,3 +4,4 @@ from .diffusion_model_unet import DiffusionModelUNet  # noqa: F401
 from .vqvae import VQVAE  # noqa: F401
 from .spade_diffusion_model_unet import SPADEDiffusionModelUNet  # noqa: F401
 from .spade_autoencoderkl import SPADEAutoencoderKL  # noqa: F401
+from .transformer import DecoderOnlyTransformer  # noqa: F401

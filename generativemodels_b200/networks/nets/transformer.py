@@ -1,0 +1,129 @@
+"""DecoderOnlyTransformer — ``generative/networks/nets/transformer.py:20-106`` on the B200 kernels.
+
+Same constructor, ``forward(x, context)`` -> logits [B, T, num_tokens] (fp32) and state_dict keys as the reference.
+Beyond that interface the class offers the incremental form the sampler wants: ``new_cache`` / ``step`` keep every
+layer's keys and values of the tokens seen so far (the reference recomputes the whole prefix for every new token,
+inferer.py:1219-1225 — O(n^3) over a sequence; with the cache each step is one row through the GEMMs plus attention of
+one query over the cached keys).  Absolute position embeddings make the cache valid only while the sequence still
+fits ``max_seq_len`` (after that the window slides and every position changes); ``step`` refuses beyond that and the
+inferer falls back to the full forward, exactly the reference's behaviour.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from ... import ops
+from ...ops import CL
+from .._holders import f32, packed_linear, require_cuda
+from ..blocks.transformerblock import TransformerBlock
+
+__all__ = ["DecoderOnlyTransformer", "AbsolutePositionalEmbedding"]
+
+
+class AbsolutePositionalEmbedding(nn.Module):
+    """nets/transformer.py:20-37 (a learnt table indexed by position; used through the fused embedding kernel)."""
+
+    def __init__(self, max_seq_len: int, embedding_dim: int) -> None:
+        super().__init__()
+        self.max_seq_len = max_seq_len
+        self.embedding_dim = embedding_dim
+        self.embedding = nn.Embedding(max_seq_len, embedding_dim)
+
+
+class _Cache:
+    """Keys / values of the tokens processed so far, per layer: bf16 [B, max_seq_len, pitch]; cross-attention keys
+    and values of the conditioning are projected once."""
+
+    def __init__(self, model: "DecoderOnlyTransformer", batch: int, device, context: torch.Tensor | None):
+        P = ops.round_up(model.attn_layers_dim, 8)
+        mk = lambda: torch.zeros((batch, model.max_seq_len, P), dtype=torch.bfloat16, device=device)
+        self.k = [mk() for _ in model.blocks]
+        self.v = [mk() for _ in model.blocks]
+        self.length = 0
+        self.batch = batch
+        self.cross = None
+        self.context_len = 0
+        if model.with_cross_attention:
+            if context is None:
+                raise ValueError("this transformer was built with cross attention: a context is required")
+            ctx = ops.as_rows(ops.to_cl(context.permute(0, 2, 1).unsqueeze(2).contiguous()).t, context.shape[2])
+            self.context_len = context.shape[1]
+            self.cross = []
+            for blk in model.blocks:
+                k, v = blk.cross_attn.project_kv(ctx)
+                self.cross.append((k.t.reshape(batch, self.context_len, -1), v.t.reshape(batch, self.context_len, -1)))
+
+
+class DecoderOnlyTransformer(nn.Module):
+    def __init__(self, num_tokens: int, max_seq_len: int, attn_layers_dim: int, attn_layers_depth: int,
+                 attn_layers_heads: int, with_cross_attention: bool = False, embedding_dropout_rate: float = 0.0,
+                 use_flash_attention: bool = False) -> None:
+        super().__init__()
+        self.num_tokens = num_tokens
+        self.max_seq_len = max_seq_len
+        self.attn_layers_dim = attn_layers_dim
+        self.attn_layers_depth = attn_layers_depth
+        self.attn_layers_heads = attn_layers_heads
+        self.with_cross_attention = with_cross_attention
+        self.token_embeddings = nn.Embedding(num_tokens, attn_layers_dim)
+        self.position_embeddings = AbsolutePositionalEmbedding(max_seq_len=max_seq_len, embedding_dim=attn_layers_dim)
+        self.embedding_dropout = nn.Dropout(embedding_dropout_rate)
+        self.blocks = nn.ModuleList([
+            TransformerBlock(hidden_size=attn_layers_dim, mlp_dim=attn_layers_dim * 4, num_heads=attn_layers_heads,
+                             dropout_rate=0.0, qkv_bias=False, causal=True, sequence_length=max_seq_len,
+                             with_cross_attention=with_cross_attention, use_flash_attention=use_flash_attention)
+            for _ in range(attn_layers_depth)])
+        self.to_logits = nn.Linear(attn_layers_dim, num_tokens)
+
+    # ------------------------------------------------------------------------------------------
+    def _embed(self, x: torch.Tensor, pos0: int) -> CL:
+        return ops.embed_tokens(x, f32(self.token_embeddings.weight), f32(self.position_embeddings.embedding.weight),
+                                pos0)
+
+    def _logits(self, h: CL, B: int, T: int) -> torch.Tensor:
+        y = ops.linear(h, packed_linear(self, "to_logits"), out_f32=True)
+        return y.reshape(B, T, -1)[:, :, : self.num_tokens]
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, context: torch.Tensor | None = None) -> torch.Tensor:
+        require_cuda(x, self)
+        B, T = x.shape
+        if T > self.max_seq_len:
+            raise IndexError(f"sequence of {T} tokens exceeds max_seq_len {self.max_seq_len}")
+        ctx, ctx_len = None, 0
+        if self.with_cross_attention:
+            if context is None:
+                raise ValueError("this transformer was built with cross attention: a context is required")
+            ctx = ops.as_rows(ops.to_cl(context.permute(0, 2, 1).unsqueeze(2).contiguous()).t, context.shape[2])
+            ctx_len = context.shape[1]
+        h = self._embed(x, 0)
+        for blk in self.blocks:
+            h = blk(h, B, T, context=ctx, context_len=ctx_len)
+        return self._logits(h, B, T)
+
+    # ---- incremental decoding -------------------------------------------------------------------
+    def new_cache(self, batch: int, device, context: torch.Tensor | None = None) -> _Cache:
+        return _Cache(self, batch, device, context)
+
+    @torch.no_grad()
+    def step(self, x: torch.Tensor, cache: _Cache) -> torch.Tensor:
+        """Logits [B, T_new, num_tokens] of ``x`` ([B, T_new] tokens that extend the cached prefix), identical to the
+        last T_new rows of ``forward`` on the whole sequence."""
+        require_cuda(x, self)
+        B, T = x.shape
+        L = cache.length
+        if B != cache.batch or L + T > self.max_seq_len:
+            raise IndexError("key/value cache exhausted: the sequence no longer fits max_seq_len")
+        h = self._embed(x, L)
+        for i, blk in enumerate(self.blocks):
+            n1 = blk._ln(blk.norm1, h)
+            ops.linear_into_cache(n1, B, T, packed_linear(blk.attn, "to_k"), cache.k[i], L)
+            ops.linear_into_cache(n1, B, T, packed_linear(blk.attn, "to_v"), cache.v[i], L)
+            h = blk.attn.attend(n1, B, T, cache.k[i], cache.v[i], L + T, L, residual=h)
+            if self.with_cross_attention:
+                ck, cv = cache.cross[i]
+                h = blk.cross_attn.attend(blk._ln(blk.norm2, h), B, T, ck, cv, cache.context_len, 0, residual=h)
+            h = blk.mlp(blk._ln(blk.norm3, h), residual=h)
+        cache.length = L + T
+        return self._logits(h, B, T)

@@ -14,12 +14,12 @@ from typing import Sequence
 import torch
 
 from . import _lib
-from ._lib import (ACT_LEAKYRELU, ACT_NONE, ACT_RELU, ACT_SILU, DT_BF16, DT_F32, DdimCoef, DdpmCoef, GnApplyParams, GnStatsParams,
+from ._lib import (ACT_GELU, ACT_LEAKYRELU, ACT_NONE, ACT_RELU, ACT_SILU, DT_BF16, DT_F32, DdimCoef, DdpmCoef, GnApplyParams, GnStatsParams,
                    IgemmParams, PndmCoef, check)
 
 __all__ = ["CL", "to_cl", "from_cl", "PackedConv", "PackedConvTranspose", "PackedLinear", "conv", "conv_transpose",
            "linear", "groupnorm", "layernorm", "upsample_nearest2x", "avgpool2", "axpy", "geglu", "attention",
-           "timestep_embedding", "small_linear", "ACT_NONE", "ACT_RELU", "ACT_SILU", "ACT_LEAKYRELU"]
+           "timestep_embedding", "small_linear", "ACT_NONE", "ACT_RELU", "ACT_SILU", "ACT_LEAKYRELU", "ACT_GELU"]
 
 
 def _stream() -> int:
@@ -847,6 +847,48 @@ def linear_transposed(x: torch.Tensor, C_in: int, pl: PackedLinear) -> torch.Ten
 # --------------------------------------------------------------------------------------------------
 # time embedding
 # --------------------------------------------------------------------------------------------------
+def linear_into_cache(x: CL, B: int, T: int, pl: PackedLinear, cache: torch.Tensor, pos0: int) -> None:
+    """cache[b, pos0 + t, :] = x[b * T + t, :] @ W^T (+ b): the K / V projection of T new tokens per sequence written
+    straight into a [B, max_seq, pitch] key/value cache by the GEMM epilogue (strided output rows), no copy."""
+    if x.C != pl.K:
+        raise ValueError(f"linear expects {pl.K} input features, got {x.C}")
+    Bc, L, P = cache.shape
+    if Bc != B or pos0 + T > L or P != round_up(pl.cout, 8):
+        raise ValueError("key/value cache does not match the projection")
+    xin = CL(x.t.reshape(B, 1, 1, T, x.pitch), x.C, 2)
+    p = _conv_params([xin], pl.w, pl.segs, (1, 1, 1), cache, (1, 1, T), pl.cout, DT_BF16, pl.bias, None, ACT_NONE, 1.0,
+                     None, DT_BF16, ACT_NONE, out_elem_off=pos0 * P, out_strides=(L * P, 0, 0, P))
+    igemm_raw(p)
+
+
+def attention_causal(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, dh: int, scale: float, S: int,
+                     causal: bool = True, q_pos0: int = 0) -> torch.Tensor:
+    """softmax(scale * Q K^T [+ causal mask]) V for the autoregressive transformer: q [B, T, pitch]; k, v
+    [B, rows >= S, pitch] — typically a key/value cache of which the first S rows are valid; query row t sits at
+    absolute position q_pos0 + t and, if causal, sees keys <= its position (blocks/selfattention.py:121-140)."""
+    lib = _lib.require_device()
+    B, T, qp = q.shape
+    out = torch.empty((B, T, round_up(heads * dh, 8)), dtype=torch.bfloat16, device=q.device)
+    if out.shape[2] > heads * dh:
+        out.zero_()
+    check(lib.b200_attention_small_ex(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, T, S, heads, dh, qp,
+                                      k.shape[2], v.shape[2], out.shape[2], scale, k.shape[1], int(causal), q_pos0,
+                                      _stream()), "b200_attention_small_ex")
+    return out
+
+
+def embed_tokens(tokens: torch.Tensor, tok_emb: torch.Tensor, pos_emb: torch.Tensor, pos0: int = 0) -> CL:
+    """Token + absolute-position embedding rows of an int64 [B, T] index tensor -> CL rows [1, 1, 1, B*T, pitch]."""
+    lib = _lib.require_device()
+    B, T = tokens.shape
+    C_ = tok_emb.shape[1]
+    tk = tokens if (tokens.dtype == torch.int64 and tokens.is_contiguous()) else tokens.long().contiguous()
+    out = torch.empty((1, 1, 1, B * T, round_up(C_, 8)), dtype=torch.bfloat16, device=tokens.device)
+    check(lib.b200_embed_tokens(tk.data_ptr(), B * T, T, pos0, tok_emb.data_ptr(), pos_emb.data_ptr(), C_,
+                                out.data_ptr(), out.shape[-1], _stream()), "b200_embed_tokens")
+    return CL(out, C_, 2)
+
+
 def timestep_embedding(t: torch.Tensor, dim: int, max_period: float = 10000.0) -> torch.Tensor:
     lib = _lib.require_device()
     t = t.contiguous().float()

@@ -33,6 +33,7 @@ extern "C" {
 #define B200_ACT_NONE 0
 #define B200_ACT_RELU 1
 #define B200_ACT_SILU 2
+#define B200_ACT_GELU 4        /* exact erf GELU (nn.GELU default; monai MLPBlock act="GELU") */
 #define B200_ACT_LEAKYRELU 3   /* nn.LeakyReLU() default slope 0.01 (monai act="LEAKYRELU" in blocks/spade_norm.py:52-60) */
 
 #define B200_IGEMM_MAX_SEG 128
@@ -244,6 +245,17 @@ int64_t b200_attention_flash_workspace_bytes(const b200_flash_params* p);
 int b200_attention_small(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t T,
                          int32_t S, int32_t heads, int32_t dh, int32_t q_pitch, int32_t k_pitch,
                          int32_t v_pitch, int32_t o_pitch, float scale, void* stream);
+/* The same with the two things the autoregressive transformer needs (blocks/selfattention.py:93-140,
+ * inferer.py:1183-1245): k / v may live in a cache of kv_rows >= S rows per batch item, and with causal != 0 query
+ * row t (absolute position q_pos0 + t) attends to keys s <= q_pos0 + t only. */
+int b200_attention_small_ex(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t T,
+                            int32_t S, int32_t heads, int32_t dh, int32_t q_pitch, int32_t k_pitch,
+                            int32_t v_pitch, int32_t o_pitch, float scale, int32_t kv_rows, int32_t causal,
+                            int32_t q_pos0, void* stream);
+/* Token + absolute position embedding rows (nets/transformer.py:20-37, 97-99):
+ * out[m, :] = tok_emb[tokens[m], :] + pos_emb[pos0 + m % seq_len, :], bf16 rows of pitch `pitch`. */
+int b200_embed_tokens(const int64_t* tokens, int64_t M, int32_t seq_len, int32_t pos0, const float* tok_emb,
+                      const float* pos_emb, int32_t C, void* out, int32_t pitch, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Time embedding path (diffusion_model_unet.py:461-485, 1759-1767, 1888-1902; ResnetBlock 641,686).

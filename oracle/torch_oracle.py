@@ -808,3 +808,85 @@ def get_likelihood(model_fn, scheduler: DDPMOracle, inputs, noise, conditioning=
                         + ((posterior_mean - predicted_mean) ** 2) * torch.exp(-log_pred))
         total_kl += kl.view(kl.shape[0], -1).mean(axis=1)
     return total_kl
+
+
+# ======================================================================================================
+# DecoderOnlyTransformer + VQVAETransformerInferer  (nets/transformer.py, blocks/{selfattention,transformerblock}.py,
+# utils/ordering.py, inferers/inferer.py:1126-1330) — SURVEY.md §8f rank 3
+# ======================================================================================================
+def _sa_block(sd, p, x, heads, causal, context=None):
+    """SABlock.forward (blocks/selfattention.py:101-148), non-xformers branch."""
+    b, t, c = x.shape
+    kv = context if context is not None else x
+    q = F.linear(x, sd[p + ".to_q.weight"], sd.get(p + ".to_q.bias"))
+    k = F.linear(kv, sd[p + ".to_k.weight"], sd.get(p + ".to_k.bias"))
+    v = F.linear(kv, sd[p + ".to_v.weight"], sd.get(p + ".to_v.bias"))
+    kv_t = kv.shape[1]
+    hs = c // heads
+    q = q.view(b, t, heads, hs).transpose(1, 2) * (1.0 / math.sqrt(hs))
+    k = k.view(b, kv_t, heads, hs).transpose(1, 2)
+    v = v.view(b, kv_t, heads, hs).transpose(1, 2)
+    s = q @ k.transpose(-2, -1)
+    if causal:
+        mask = torch.tril(torch.ones(t, kv_t)).view(1, 1, t, kv_t)
+        s = s.masked_fill(mask == 0, float("-inf"))
+    y = (F.softmax(s, dim=-1) @ v).transpose(1, 2).contiguous().view(b, t, c)
+    return F.linear(y, sd[p + ".out_proj.weight"], sd[p + ".out_proj.bias"])
+
+
+def transformer_forward(sd, heads, x, context=None):
+    """DecoderOnlyTransformer.forward (nets/transformer.py:96-106) over TransformerBlocks
+    (blocks/transformerblock.py:87-92): pre-LN causal self-attention, optional cross-attention, GELU MLP."""
+    b, t = x.shape
+    h = F.embedding(x, sd["token_embeddings.weight"]) + F.embedding(torch.arange(t).repeat(b, 1),
+                                                                  sd["position_embeddings.embedding.weight"])
+    for i in range(_count(sd, "blocks.")):
+        p = f"blocks.{i}"
+        h = h + _sa_block(sd, p + ".attn", _ln(sd, p + ".norm1", h), heads, True)
+        if _has(sd, p + ".cross_attn."):
+            h = h + _sa_block(sd, p + ".cross_attn", _ln(sd, p + ".norm2", h), heads, False, context=context)
+        m = _ln(sd, p + ".norm3", h)
+        m = _linear(sd, p + ".mlp.linear2", F.gelu(_linear(sd, p + ".mlp.linear1", m)))
+        h = h + m
+    return _linear(sd, "to_logits", h)
+
+
+def sequence_ordering(ordering_type, spatial_dims, dimensions, reflected_spatial_dims=(), transpositions_axes=(),
+                      rot90_axes=(), transformation_order=("transpose", "rotate_90", "reflect")):
+    """utils/ordering.py: index template -> transformations in the requested order -> raster / s-curve scan
+    (``random`` draws from numpy's global generator and is not restated)."""
+    import numpy as np
+    template = np.arange(int(np.prod(dimensions[1:]))).reshape(*dimensions[1:])
+    for tr in transformation_order:
+        if tr == "transpose":
+            for axes in transpositions_axes:
+                template = np.transpose(template, axes=axes)
+        elif tr == "rotate_90":
+            for axes in rot90_axes:
+                template = np.rot90(template, axes=axes)
+        elif tr == "reflect":
+            for axis, flag in enumerate(reflected_spatial_dims):
+                template = np.flip(template, axis=axis) if flag else template
+    shp = template.shape
+    out = []
+    for r in range(shp[0]):
+        cols = range(shp[1]) if (ordering_type == "raster_scan" or r % 2 == 0) else range(shp[1] - 1, -1, -1)
+        for c in cols:
+            if spatial_dims == 3:
+                deps = range(shp[2]) if (ordering_type == "raster_scan" or c % 2 == 0) else range(shp[2] - 1, -1, -1)
+                out.extend(template[r, c, d] for d in deps)
+            else:
+                out.append(template[r, c])
+    return np.array(out)
+
+
+def transformer_sample_greedy(sd, heads, max_seq_len, bos, seq_len, batch, context=None):
+    """VQVAETransformerInferer.sample (inferer.py:1183-1245) with top_k = 1 (the multinomial draw over a one-hot
+    distribution is deterministic): returns the token sequence without the BOS, before the ordering is reverted."""
+    seq = torch.full((batch, 1), bos, dtype=torch.long)
+    for _ in range(seq_len):
+        cond = seq if seq.shape[1] <= max_seq_len else seq[:, -max_seq_len:]
+        logits = transformer_forward(sd, heads, cond, context)[:, -1, :]
+        logits[:, bos] = -float("inf")            # probs[:, num_embeddings] = 0 in the reference
+        seq = torch.cat([seq, logits.argmax(-1, keepdim=True)], dim=1)
+    return seq[:, 1:]

@@ -42,6 +42,8 @@ def i64(ptr, count):
 def _act(x, a):
     if a == _lib.ACT_LEAKYRELU:
         return F.leaky_relu(x, 0.01)
+    if a == _lib.ACT_GELU:
+        return F.gelu(x)
     return F.relu(x) if a == _lib.ACT_RELU else F.silu(x) if a == _lib.ACT_SILU else x
 
 
@@ -257,6 +259,31 @@ class FakeLib:
         if a.res:
             out = out + bf16(a.res, B * T * a.res_pitch).view(B, T, a.res_pitch)[:, :, :Cc].float()
         bf16(a.out, B * T * a.out_pitch).view(B, T, a.out_pitch)[:, :, :Cc] = out.to(torch.bfloat16)
+        return 0
+
+    def b200_attention_small_ex(self, q, k, v, o, B, T, S, heads, dh, qp, kp, vp, op, scale, kv_rows, causal, q_pos0,
+                                stream):
+        Cc = heads * dh
+        qq = bf16(q, B * T * qp).view(B, T, qp)[:, :, :Cc].float().view(B, T, heads, dh).transpose(1, 2)
+        kk = bf16(k, B * kv_rows * kp).view(B, kv_rows, kp)[:, :S, :Cc].float().view(B, S, heads, dh).transpose(1, 2)
+        vv = bf16(v, B * kv_rows * vp).view(B, kv_rows, vp)[:, :S, :Cc].float().view(B, S, heads, dh).transpose(1, 2)
+        sc = scale * qq @ kk.transpose(-1, -2)
+        if causal:
+            allowed = torch.arange(S)[None, :] <= (q_pos0 + torch.arange(T))[:, None]
+            sc = sc.masked_fill(~allowed, float("-inf"))
+        out = (torch.softmax(sc, -1) @ vv).transpose(1, 2).reshape(B, T, Cc)
+        bf16(o, B * T * op).view(B, T, op)[:, :, :Cc] = out.to(torch.bfloat16)
+        return 0
+
+    def b200_embed_tokens(self, tokens, M, seq_len, pos0, tok_emb, pos_emb, C_, out, pitch, stream):
+        tk = i64(tokens, M)
+        V, Lmax = int(tk.max()) + 1, pos0 + seq_len
+        te = f32(tok_emb, V * C_).view(V, C_)
+        pe = f32(pos_emb, Lmax * C_).view(Lmax, C_)
+        pos = pos0 + torch.arange(M) % seq_len
+        dst = bf16(out, M * pitch).view(M, pitch)
+        dst.zero_()
+        dst[:, :C_] = (te[tk] + pe[pos]).to(torch.bfloat16)
         return 0
 
     def b200_attention_small(self, q, k, v, o, B, T, S, heads, dh, qp, kp, vp, op, scale, stream):

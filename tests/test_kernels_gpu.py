@@ -419,6 +419,52 @@ def test_attention_flash_replay_matches_recompute(cuda_device, monkeypatch):
     assert_close(a[:1, :256], ref, 2e-2, "replay vs fp32 reference")
 
 
+@pytest.mark.parametrize("B,T,S,heads,dh,q_pos0,causal", [(2, 9, 9, 4, 8, 0, True), (3, 1, 37, 2, 64, 36, True),
+                                                          (1, 5, 20, 1, 32, 15, True), (2, 6, 11, 2, 16, 0, False)])
+def test_attention_causal_and_cache(cuda_device, B, T, S, heads, dh, q_pos0, causal):
+    """b200_attention_small_ex: causal mask by absolute position and keys / values living in a longer cache
+    (SABlock, blocks/selfattention.py:121-140; the decode step of the transformer sampler)."""
+    ops = _ops()
+    torch.manual_seed(21)
+    Cc = heads * dh
+    rows = S + 5                                             # cache longer than the valid prefix
+    q, k, v = torch.randn(B, T, Cc), torch.randn(B, rows, Cc), torch.randn(B, rows, Cc)
+    qh = bf(q).view(B, T, heads, dh).transpose(1, 2)
+    kh = bf(k)[:, :S].reshape(B, S, heads, dh).transpose(1, 2)
+    vh = bf(v)[:, :S].reshape(B, S, heads, dh).transpose(1, 2)
+    sc = (qh @ kh.transpose(-1, -2)) / math.sqrt(dh)
+    if causal:
+        allowed = torch.arange(S)[None, :] <= (q_pos0 + torch.arange(T))[:, None]
+        sc = sc.masked_fill(~allowed, float("-inf"))
+    ref = (torch.softmax(sc, -1) @ vh).transpose(1, 2).reshape(B, T, Cc)
+    g = lambda t: t.to(torch.bfloat16).cuda().contiguous()
+    out = ops.attention_causal(g(q), g(k), g(v), heads, dh, 1 / math.sqrt(dh), S, causal=causal, q_pos0=q_pos0)
+    assert_close(out[..., :Cc], ref, 1e-2, "causal attention over a cache")
+
+
+def test_embed_tokens_gelu_and_cache_projection(cuda_device):
+    """Token + position embedding rows, exact-erf GELU in the GEMM epilogue, and the K / V projection that writes
+    its rows straight into a [B, max_seq, C] cache at an offset (nets/transformer.py:97-99; MLPBlock)."""
+    ops = _ops()
+    torch.manual_seed(22)
+    B, T, C_, V, L = 3, 5, 40, 17, 12
+    tok, pos = torch.randn(V, C_), torch.randn(L, C_)
+    x = torch.randint(0, V, (B, T))
+    e = ops.embed_tokens(x.cuda(), tok.cuda(), pos.cuda(), pos0=4)
+    want = tok[x] + pos[4 + torch.arange(T)][None]
+    assert_close(e.t.reshape(B, T, -1)[..., :C_], want, 1e-2, "embed_tokens")
+    assert e.t.reshape(B * T, -1)[:, C_:].abs().sum().item() == 0
+    w, b = torch.randn(64, C_) / math.sqrt(C_), torch.randn(64)
+    pl = ops.PackedLinear(w.cuda(), b.cuda())
+    y = ops.linear(e, pl, act1=ops.ACT_GELU)
+    assert_close(y.t.reshape(B * T, -1)[:, :64], F.gelu(F.linear(bf(want).reshape(B * T, C_), bf(w), b)), 1e-2, "GELU epilogue")
+    cache = torch.zeros(B, L, 64, dtype=torch.bfloat16, device="cuda")
+    ops.linear_into_cache(e, B, T, pl, cache, 6)
+    lin = F.linear(bf(want), bf(w), b)
+    assert_close(cache[:, 6:6 + T], lin, 1e-2, "projection into the cache")
+    assert cache[:, :6].abs().sum().item() == 0 and cache[:, 6 + T:].abs().sum().item() == 0
+
+
 # ------------------------------------------------------------------------------------------------ time embedding
 def test_timestep_embedding_and_small_linear(cuda_device):
     ops = _ops()

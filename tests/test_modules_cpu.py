@@ -255,3 +255,69 @@ def test_spade_golden_cpu():
 def ops_cl(x, C_):
     from generativemodels_b200 import ops
     return ops.CL(torch.zeros(x.shape[0], 1, x.shape[2], x.shape[3], C_, dtype=torch.bfloat16), C_, 2)
+
+
+def _transformer_pair(cross=False, max_seq_len=16, tokens=11):
+    torch.manual_seed(0)
+    m = nets().DecoderOnlyTransformer(num_tokens=tokens, max_seq_len=max_seq_len, attn_layers_dim=32,
+                                      attn_layers_depth=2, attn_layers_heads=4, with_cross_attention=cross).eval()
+    return m, {k: v.clone() for k, v in m.state_dict().items()}
+
+
+@pytest.mark.parametrize("cross", [False, True])
+def test_transformer_forward_and_cache_cpu(monkeypatch, cross):
+    """DecoderOnlyTransformer host logic (embedding kernel call, fused-GELU MLP, causal attention parameters, logits
+    slicing) against the oracle, and the key/value-cache ``step`` against the full forward — same rows, any chunking."""
+    import generativemodels_b200.networks.nets.transformer as T
+    monkeypatch.setattr(T, "require_cuda", lambda x, m: None)
+    m, sd = _transformer_pair(cross)
+    assert set(sd) == set(m.state_dict()) and "blocks.0.attn.causal_mask" in sd
+    x = torch.randint(0, 11, (2, 9))
+    ctx = torch.randn(2, 3, 32) if cross else None
+    want = O.transformer_forward(sd, 4, x, ctx)
+    got = m(x, context=ctx)
+    assert got.shape == (2, 9, 11) and rel(got, want) < 2e-2
+    cache = m.new_cache(2, x.device, ctx)
+    inc = torch.cat([m.step(x[:, :4], cache)] + [m.step(x[:, i:i + 1], cache) for i in range(4, 9)], 1)
+    assert torch.equal(inc, got)
+    with pytest.raises(IndexError):
+        m.step(torch.randint(0, 11, (2, 8)), cache)
+    if cross:
+        with pytest.raises(ValueError):
+            m(x)
+
+
+def test_vqvae_transformer_inferer_cpu(monkeypatch):
+    """VQVAETransformerInferer: greedy sampling (top_k = 1; key/value cache, then the sliding window once the sequence
+    outgrows max_seq_len) against the oracle's loop, teacher-forced __call__, get_likelihood and the Ordering class."""
+    import numpy as np
+    import generativemodels_b200.networks.nets.transformer as T
+    from generativemodels_b200.inferers import VQVAETransformerInferer
+    from generativemodels_b200.utils.ordering import Ordering
+    monkeypatch.setattr(T, "require_cuda", lambda x, m: None)
+    kw = G.VQVAE_CASES["vqvae2d"]
+    K = kw["num_embeddings"]
+    torch.manual_seed(0)
+    vq = nets().VQVAE(**kw).eval()
+    vsd = {k: v.clone() for k, v in vq.state_dict().items()}
+    tr, tsd = _transformer_pair(max_seq_len=10, tokens=K + 1)
+    ordering = Ordering("s_curve", 2, (1, 4, 4), reflected_spatial_dims=(True, False))
+    assert np.array_equal(ordering.get_sequence_ordering(),
+                          O.sequence_ordering("s_curve", 2, (1, 4, 4), reflected_spatial_dims=(True, False)))
+    inf = VQVAETransformerInferer()
+    start = torch.full((2, 1), K)
+    got = inf.sample((4, 4), start, vq, tr, ordering, top_k=1, verbose=False)
+    seq = O.transformer_sample_greedy(tsd, 4, 10, K, 16, 2)
+    seq = seq[:, ordering.get_revert_sequence_ordering()].reshape(2, 4, 4)
+    want = O.vqvae_decode(vsd, G.vqvae_oracle_cfg(kw), O.vq_embed(vsd["quantizer.quantizer.embedding.weight"], seq))
+    assert got.shape == want.shape and rel(got, want) < 3e-2
+    # teacher forcing and likelihood: shapes and agreement with the oracle's logits
+    x = torch.randn(2, 1, 16, 16)
+    pred, target, sdim = inf(x, vq, tr, ordering, return_latent=True)
+    assert sdim == (4, 4) and pred.shape == (2, 10, K + 1) and target.shape == (2, 10)
+    ll = inf.get_likelihood(x, vq, tr, ordering)
+    assert ll.shape == (2, 4, 4) and torch.isfinite(ll).all() and (ll <= 0).all()
+    ll_up = inf.get_likelihood(x, vq, tr, ordering, resample_latent_likelihoods=True)
+    assert ll_up.shape == (2, 1, 16, 16)
+    with pytest.raises(ValueError):
+        Ordering("hilbert", 2, (1, 4, 4))

@@ -227,3 +227,52 @@ def test_spade_autoencoderkl(ref, name):
     _close(gmu, mu)
     _close(gsigma, sigma)
     _close(grec, rec)
+
+
+def test_ordering(ref):
+    """utils/ordering.py: raster / s-curve scans of transposed, rotated and reflected index grids."""
+    import numpy as np
+    from generative.utils.ordering import Ordering
+    for kw in (dict(ordering_type="s_curve", spatial_dims=2, dimensions=(1, 3, 4), reflected_spatial_dims=(True, False)),
+               dict(ordering_type="raster_scan", spatial_dims=3, dimensions=(1, 2, 3, 4), transpositions_axes=((2, 0, 1),),
+                    rot90_axes=((0, 1),), reflected_spatial_dims=(False, True, True)),
+               dict(ordering_type="s_curve", spatial_dims=3, dimensions=(1, 3, 2, 4),
+                    transformation_order=("reflect", "transpose", "rotate_90"),
+                    reflected_spatial_dims=(True, True, False), transpositions_axes=((1, 0, 2),))):
+        assert np.array_equal(Ordering(**kw).get_sequence_ordering(), O.sequence_ordering(**kw))
+
+
+@pytest.mark.parametrize("cross", [False, True])
+def test_transformer(ref, cross):
+    """DecoderOnlyTransformer.forward (nets/transformer.py:96-106)."""
+    nets, _ = ref
+    torch.manual_seed(0)
+    m = nets.DecoderOnlyTransformer(num_tokens=11, max_seq_len=16, attn_layers_dim=32, attn_layers_depth=2,
+                                    attn_layers_heads=4, with_cross_attention=cross).eval()
+    x = torch.randint(0, 11, (2, 9))
+    ctx = torch.randn(2, 3, 32) if cross else None
+    with torch.no_grad():
+        _close(O.transformer_forward(m.state_dict(), 4, x, ctx), m(x, context=ctx))
+
+
+def test_transformer_greedy_sampling(ref):
+    """VQVAETransformerInferer.sample with top_k = 1 (inferer.py:1183-1245) against the oracle's greedy loop, incl.
+    the sliding window once the sequence outgrows max_seq_len."""
+    nets, _ = ref
+    from generative.inferers import VQVAETransformerInferer
+    from generative.utils.ordering import Ordering
+    torch.manual_seed(0)
+    vq = nets.VQVAE(**G.VQVAE_CASES["vqvae2d"]).eval()
+    K = G.VQVAE_CASES["vqvae2d"]["num_embeddings"]
+    tr = nets.DecoderOnlyTransformer(num_tokens=K + 1, max_seq_len=10, attn_layers_dim=32, attn_layers_depth=2,
+                                     attn_layers_heads=4).eval()
+    ordering = Ordering("raster_scan", 2, (1, 4, 4))
+    start = torch.full((2, 1), K)
+    with torch.no_grad():
+        want = VQVAETransformerInferer().sample((4, 4), start, vq, tr, ordering, top_k=1, verbose=False)
+        seq = O.transformer_sample_greedy(tr.state_dict(), 4, 10, K, 16, 2)
+        seq = seq[:, ordering.get_revert_sequence_ordering()].reshape(2, 4, 4)
+        sd = vq.state_dict()
+        emb = O.vq_embed(sd["quantizer.quantizer.embedding.weight"], seq)
+        got = O.vqvae_decode(sd, G.vqvae_oracle_cfg(G.VQVAE_CASES["vqvae2d"]), emb)
+    _close(got, want)

