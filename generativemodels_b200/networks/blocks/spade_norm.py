@@ -63,6 +63,10 @@ class SPADE(nn.Module, _Cached):
     def forward(self, x: CL | Sequence[CL], seg: SegPyramid, act: int = ACT_NONE) -> CL:
         srcs = [x] if isinstance(x, CL) else list(x)
         a0 = srcs[0]
+        if seg.base.C != self.mlp_shared.in_channels:
+            # the reference fails inside F.conv with a RuntimeError (tests/test_spade_diffusion_model_unet.py:293-306)
+            raise RuntimeError(f"segmentation map has {seg.base.C} channels but this SPADE block was built for "
+                               f"label_nc = {self.mlp_shared.in_channels}")
         gn = self.param_free_norm.N
         affine = ops.groupnorm_affine(srcs, gn.num_groups, gn.eps, gn.weight, gn.bias)
         dims = (a0.H, a0.W) if a0.spatial_dims == 2 else (a0.D, a0.H, a0.W)

@@ -360,3 +360,84 @@ def test_controlnet_latent_inferer_cases(cuda_device):
                                         cn_cond=mask, scheduler=s, save_intermediates=True,
                                         resample_latent_likelihoods=True, verbose=False)
         assert inter[0].shape[2:] == img.shape[2:]
+
+
+def test_spade_cases(cuda_device):
+    """tests/test_spade_diffusion_model_unet.py (shapes, wrong timestep / label shapes, channel validation, class and
+    cross-attention conditioning) and tests/test_spade_autoencoderkl.py (shape, encode / sampling / decode)."""
+    base = dict(spatial_dims=2, label_nc=3, in_channels=1, out_channels=1, num_res_blocks=1, num_channels=(8, 8, 8),
+                attention_levels=(False, False, False), norm_num_groups=8)
+    net = G.randomize_zero_params(nets().SPADEDiffusionModelUNet(**base)).cuda().eval()
+    x, t, seg = torch.rand(1, 1, 16, 16).cuda(), torch.randint(0, 1000, (1,)).long().cuda(), torch.rand(1, 3, 16, 16).cuda()
+    assert net(x, t, seg).shape == (1, 1, 16, 16)
+    with pytest.raises(ValueError):
+        net(x, torch.randint(0, 1000, (1, 1)).long().cuda(), seg)
+    with pytest.raises(RuntimeError):
+        net(x, t, torch.rand(1, 6, 16, 16).cuda())
+    io = G.randomize_zero_params(nets().SPADEDiffusionModelUNet(**dict(base, in_channels=6, out_channels=3))).cuda().eval()
+    assert io(torch.rand(1, 6, 16, 16).cuda(), t, seg).shape == (1, 3, 16, 16)
+    for bad in (dict(num_channels=(8, 8, 12)), dict(num_channels=(8, 8), attention_levels=(False, False, False)),
+                dict(num_res_blocks=(1, 1)), dict(attention_levels=(False, True, True), num_head_channels=(0, 2))):
+        with pytest.raises(ValueError):
+            nets().SPADEDiffusionModelUNet(**dict(base, **bad))
+    with pytest.raises(ValueError):
+        nets().SPADEDiffusionModelUNet(**dict(base, with_conditioning=True, cross_attention_dim=None))
+    cond = G.randomize_zero_params(nets().SPADEDiffusionModelUNet(**dict(
+        base, attention_levels=(False, False, True), num_head_channels=8, with_conditioning=True,
+        transformer_num_layers=1, cross_attention_dim=3, num_class_embeds=2))).cuda().eval()
+    out = cond(torch.rand(1, 1, 16, 32).cuda(), t, torch.rand(1, 3, 16, 32).cuda(), context=torch.rand(1, 1, 3).cuda(),
+               class_labels=torch.randint(0, 2, (1,)).long().cuda())
+    assert out.shape == (1, 1, 16, 32)
+    with pytest.raises(ValueError):
+        cond(torch.rand(1, 1, 16, 32).cuda(), t, torch.rand(1, 3, 16, 32).cuda(), context=torch.rand(1, 1, 3).cuda())
+    net3 = G.randomize_zero_params(nets().SPADEDiffusionModelUNet(**dict(base, spatial_dims=3))).cuda().eval()
+    assert net3(torch.rand(1, 1, 16, 16, 16).cuda(), t, torch.rand(1, 3, 16, 16, 16).cuda()).shape == (1, 1, 16, 16, 16)
+    # autoencoder
+    akw = dict(spatial_dims=2, label_nc=3, in_channels=1, out_channels=1, num_channels=(4, 4, 4), latent_channels=4,
+               attention_levels=(False, False, False), num_res_blocks=1, norm_num_groups=4)
+    ae = nets().SPADEAutoencoderKL(**akw).cuda().eval()
+    img, sg = torch.randn(1, 1, 16, 16).cuda(), torch.randn(1, 3, 16, 16).cuda()
+    rec, mu, sigma = ae(img, sg)
+    assert rec.shape == (1, 1, 16, 16) and mu.shape == (1, 4, 4, 4) and sigma.shape == (1, 4, 4, 4)
+    assert ae.sampling(mu, sigma).shape == (1, 4, 4, 4)
+    assert ae.decode(torch.randn(1, 4, 4, 4).cuda(), sg).shape == (1, 1, 16, 16)
+    for bad in (dict(num_channels=(24, 24, 24), norm_num_groups=16), dict(attention_levels=(False, False)),
+                dict(num_res_blocks=(8, 8))):
+        with pytest.raises(ValueError):
+            nets().SPADEAutoencoderKL(**dict(akw, **bad))
+
+
+@pytest.mark.parametrize("sd_", [2, 3])
+def test_transformer_inferer_cases(cuda_device, sd_):
+    """tests/test_transformer.py:20-45 and tests/test_vqvaetransformer_inferer.py:24-275: prediction shapes (also with
+    max_seq_len shorter than the sequence), sampling, likelihood and resampled likelihood maps."""
+    from generativemodels_b200.inferers import VQVAETransformerInferer
+    from generativemodels_b200.utils.ordering import Ordering
+    net = nets().DecoderOnlyTransformer(num_tokens=10, max_seq_len=16, attn_layers_dim=8, attn_layers_depth=2,
+                                        attn_layers_heads=2).cuda().eval()
+    assert net(torch.randint(0, 10, (1, 16)).cuda()).shape == (1, 16, 10)
+    netc = nets().DecoderOnlyTransformer(num_tokens=10, max_seq_len=16, attn_layers_dim=8, attn_layers_depth=2,
+                                         attn_layers_heads=2, with_cross_attention=True,
+                                         embedding_dropout_rate=0).cuda().eval()
+    assert netc(torch.randint(0, 10, (1, 16)).cuda(), context=torch.randn(1, 4, 8).cuda()).shape == (1, 16, 10)
+    vq = nets().VQVAE(spatial_dims=sd_, in_channels=1, out_channels=1, num_channels=(8, 8), num_res_channels=(8, 8),
+                      downsample_parameters=((2, 4, 1, 1),) * 2, upsample_parameters=((2, 4, 1, 1, 0),) * 2,
+                      num_res_layers=1, num_embeddings=16, embedding_dim=8).cuda().eval()
+    n_lat = 2 ** sd_
+    shape = (2, 1) + (8,) * sd_
+    lat_dims = (2,) * sd_
+    ordering = Ordering(ordering_type="raster_scan", spatial_dims=sd_, dimensions=(2,) + lat_dims)
+    inf = VQVAETransformerInferer()
+    x = torch.randn(shape).cuda()
+    for max_len in (n_lat, 2):                   # full-length and shorter-than-sequence windows
+        tr = nets().DecoderOnlyTransformer(num_tokens=17, max_seq_len=max_len, attn_layers_dim=4, attn_layers_depth=2,
+                                           attn_layers_heads=1).cuda().eval()
+        assert inf(inputs=x, vqvae_model=vq, transformer_model=tr, ordering=ordering).shape == (2, max_len, 17)
+        sample = inf.sample(latent_spatial_dim=lat_dims, starting_tokens=16 * torch.ones((2, 1)).cuda(),
+                            vqvae_model=vq, transformer_model=tr, ordering=ordering, verbose=False)
+        assert sample.shape == shape and torch.isfinite(sample).all()
+        ll = inf.get_likelihood(inputs=x, vqvae_model=vq, transformer_model=tr, ordering=ordering)
+        assert ll.shape == (2,) + lat_dims
+        up = inf.get_likelihood(inputs=x, vqvae_model=vq, transformer_model=tr, ordering=ordering,
+                                resample_latent_likelihoods=True, resample_interpolation_mode="nearest")
+        assert up.shape == shape
