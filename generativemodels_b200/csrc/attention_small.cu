@@ -14,7 +14,12 @@ template <int R>   // R = ceil(dh / 32) registers per lane
 __global__ void attention_small_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
                                        const __nv_bfloat16* __restrict__ v, __nv_bfloat16* __restrict__ out, int B,
                                        int T, int S, int heads, int dh, int q_pitch, int k_pitch, int v_pitch,
-                                       int o_pitch, float scale, int kv_rows, int causal, int q_pos0) {
+                                       int o_pitch, float scale, int kv_rows, int causal, int q_pos0,
+                                       const int* __restrict__ pos_dev) {
+  if (pos_dev) {                 // decode step captured in a CUDA graph: the prefix length lives in device memory
+    q_pos0 = *pos_dev;
+    S = q_pos0 + T;
+  }
   const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long total = (long long)B * heads * T;
   if (wid >= total) return;
@@ -75,16 +80,17 @@ extern "C" int b200_attention_small(const void* q, const void* k, const void* v,
                                     int32_t S, int32_t heads, int32_t dh, int32_t q_pitch, int32_t k_pitch,
                                     int32_t v_pitch, int32_t o_pitch, float scale, void* stream_v) {
   return b200_attention_small_ex(q, k, v, out, B, T, S, heads, dh, q_pitch, k_pitch, v_pitch, o_pitch, scale, S, 0, 0,
-                                 stream_v);
+                                 nullptr, stream_v);
 }
 
 extern "C" int b200_attention_small_ex(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t T,
                                        int32_t S, int32_t heads, int32_t dh, int32_t q_pitch, int32_t k_pitch,
                                        int32_t v_pitch, int32_t o_pitch, float scale, int32_t kv_rows, int32_t causal,
-                                       int32_t q_pos0, void* stream_v) {
+                                       int32_t q_pos0, const int32_t* pos_dev, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   B200_CHECK_ARG(q && k && v && out && B >= 1 && T >= 1 && S >= 1 && heads >= 1 && dh >= 1, "attention_small: bad arguments");
-  B200_CHECK_ARG(kv_rows >= S && q_pos0 >= 0, "attention_small: kv_rows %d < S %d or negative query offset", kv_rows, S);
+  B200_CHECK_ARG((pos_dev || kv_rows >= S) && q_pos0 >= 0, "attention_small: kv_rows %d < S %d or negative query offset",
+                 kv_rows, S);
   B200_CHECK_ARG(dh <= 1024, "attention_small: head_dim %d > 1024", dh);
   const long long total = (long long)B * heads * T;
   const int wpb = 8;
@@ -95,7 +101,7 @@ extern "C" int b200_attention_small_ex(const void* q, const void* k, const void*
   const __nv_bfloat16* vv = reinterpret_cast<const __nv_bfloat16*>(v);
   __nv_bfloat16* oo = reinterpret_cast<__nv_bfloat16*>(out);
 #define LAUNCH(R) attention_small_kernel<R><<<(unsigned)blocks, wpb * 32, 0, stream>>>( \
-      qq, kk, vv, oo, B, T, S, heads, dh, q_pitch, k_pitch, v_pitch, o_pitch, scale, kv_rows, causal, q_pos0)
+      qq, kk, vv, oo, B, T, S, heads, dh, q_pitch, k_pitch, v_pitch, o_pitch, scale, kv_rows, causal, q_pos0, pos_dev)
   if (dh <= 32) LAUNCH(1);
   else if (dh <= 64) LAUNCH(2);
   else if (dh <= 128) LAUNCH(4);

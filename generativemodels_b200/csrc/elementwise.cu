@@ -541,7 +541,8 @@ __global__ void tap_sum_kernel(const float* __restrict__ y, int y_pitch, TapGeom
 // token + absolute position embedding rows -> bf16 (nets/transformer.py:97-99)
 __global__ void embed_tokens_kernel(const long long* __restrict__ tokens, long long M, int seq_len, int pos0,
                                     const float* __restrict__ tok_emb, const float* __restrict__ pos_emb, int C,
-                                    __nv_bfloat16* __restrict__ out, int pitch) {
+                                    __nv_bfloat16* __restrict__ out, int pitch, const int* __restrict__ pos_dev) {
+  if (pos_dev) pos0 = *pos_dev;
   const long long total = M * pitch;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -659,14 +660,48 @@ extern "C" int b200_tap_sum(const float* y, int32_t y_pitch, const int32_t* geom
 }
 
 
+// rows of T new tokens per sequence appended to a [B, L, pitch] key/value cache at the device-side position
+__global__ void cache_append_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ cache, int B,
+                                    int T, int L, int pitch, const int* __restrict__ pos_dev) {
+  const int pos = *pos_dev;
+  const long long total = (long long)B * T * pitch;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % pitch);
+    const long long r = i / pitch;
+    const int t = (int)(r % T), b = (int)(r / T);
+    if (pos + t < L) cache[((long long)b * L + pos + t) * pitch + c] = src[i];
+  }
+}
+__global__ void advance_i32_kernel(int* p, int delta) { *p += delta; }
+
+extern "C" int b200_cache_append(const void* src, void* cache, int32_t B, int32_t T, int32_t L, int32_t pitch,
+                                 const int32_t* pos_dev, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(src && cache && pos_dev && B >= 1 && T >= 1 && L >= T && pitch >= 1, "cache_append: bad arguments");
+  cache_append_kernel<<<grid_for((long long)B * T * pitch), 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src), reinterpret_cast<__nv_bfloat16*>(cache), B, T, L, pitch, pos_dev);
+  B200_LAUNCH_CHECK("cache_append_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_advance_i32(int32_t* p, int32_t delta, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(p != nullptr, "advance_i32: null pointer");
+  advance_i32_kernel<<<1, 1, 0, stream>>>(p, delta);
+  B200_LAUNCH_CHECK("advance_i32_kernel");
+  return B200_OK;
+}
+
 extern "C" int b200_embed_tokens(const int64_t* tokens, int64_t M, int32_t seq_len, int32_t pos0, const float* tok_emb,
-                                 const float* pos_emb, int32_t C, void* out, int32_t pitch, void* stream_v) {
+                                 const float* pos_emb, int32_t C, void* out, int32_t pitch, const int32_t* pos_dev,
+                                 void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   B200_CHECK_ARG(tokens && tok_emb && pos_emb && out && M >= 1 && seq_len >= 1 && pos0 >= 0 && C >= 1 && pitch >= C,
                  "embed_tokens: bad arguments");
   embed_tokens_kernel<<<grid_for(M * pitch), 256, 0, stream>>>(reinterpret_cast<const long long*>(tokens), M, seq_len,
                                                               pos0, tok_emb, pos_emb, C,
-                                                              reinterpret_cast<__nv_bfloat16*>(out), pitch);
+                                                              reinterpret_cast<__nv_bfloat16*>(out), pitch, pos_dev);
   B200_LAUNCH_CHECK("embed_tokens_kernel");
   return B200_OK;
 }

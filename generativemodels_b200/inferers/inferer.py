@@ -477,7 +477,8 @@ class VQVAETransformerInferer(Inferer):
         steps = tqdm(range(seq_len)) if (verbose and has_tqdm) else iter(range(seq_len))
         latent_seq = starting_tokens.long()
         incremental = hasattr(transformer_model, "new_cache") and latent_seq.size(1) <= transformer_model.max_seq_len
-        cache = transformer_model.new_cache(latent_seq.shape[0], latent_seq.device, conditioning) if incremental else None
+        cache = transformer_model.new_cache(latent_seq.shape[0], latent_seq.device, conditioning,
+                                            graph=latent_seq.is_cuda) if incremental else None
         pending = latent_seq                      # tokens the cache has not seen yet
         for _ in steps:
             if cache is not None and cache.length + pending.size(1) <= transformer_model.max_seq_len:
@@ -486,7 +487,7 @@ class VQVAETransformerInferer(Inferer):
                 cache = None
                 idx_cond = latent_seq[:, -transformer_model.max_seq_len:]      # the whole sequence while it fits
                 logits = transformer_model(x=idx_cond, context=conditioning)
-            logits = logits[:, -1, :] / temperature
+            logits = logits[:, -1, :] / temperature          # (a fresh tensor: graph steps return a static buffer)
             if top_k is not None:
                 v, _ = torch.topk(logits, min(top_k, logits.size(-1)))
                 logits[logits < v[:, [-1]]] = -float("Inf")

@@ -47,11 +47,12 @@ class SABlock(nn.Module):
         return ops.linear(rows, packed_linear(self, "to_k")), ops.linear(rows, packed_linear(self, "to_v"))
 
     def attend(self, x: CL, B: int, T: int, k: torch.Tensor, v: torch.Tensor, S: int, q_pos0: int,
-               residual: CL | None) -> CL:
-        """x: rows [B*T, hidden]; k, v: [B, rows >= S, pitch] (a cache or fresh projections)."""
+               residual: CL | None, pos_dev: torch.Tensor | None = None) -> CL:
+        """x: rows [B*T, hidden]; k, v: [B, rows >= S, pitch] (a cache or fresh projections); with ``pos_dev`` the
+        prefix length is read on the device instead of (S, q_pos0)."""
         q = ops.linear(x, packed_linear(self, "to_q")).t.reshape(B, T, -1)
         o = ops.attention_causal(q, k, v, self.num_heads, self.head_dim, self.scale, S, causal=self.causal,
-                                 q_pos0=q_pos0)
+                                 q_pos0=q_pos0, pos_dev=pos_dev)
         return ops.linear(ops.as_rows(o, self.hidden_size), packed_linear(self, "out_proj"), residual=residual)
 
     def forward(self, x: CL, B: int, T: int, context: CL | None = None, context_len: int = 0,

@@ -35,7 +35,16 @@ class _Cache:
     """Keys / values of the tokens processed so far, per layer: bf16 [B, max_seq_len, pitch]; cross-attention keys
     and values of the conditioning are projected once."""
 
-    def __init__(self, model: "DecoderOnlyTransformer", batch: int, device, context: torch.Tensor | None):
+    def __init__(self, model: "DecoderOnlyTransformer", batch: int, device, context: torch.Tensor | None,
+                 graph: bool = False):
+        # ``graph``: single-token steps are captured once in a CUDA graph and replayed (the prefix length then lives
+        # in device memory, ``pos_dev``); the first two single-token steps run eagerly as the capture's warm-up
+        self.use_graph = graph
+        self.pos_dev = torch.zeros(1, dtype=torch.int32, device=device)
+        self.graph = None
+        self.static_tokens = None
+        self.static_logits = None
+        self.dyn_steps = 0
         P = ops.round_up(model.attn_layers_dim, 8)
         mk = lambda: torch.zeros((batch, model.max_seq_len, P), dtype=torch.bfloat16, device=device)
         self.k = [mk() for _ in model.blocks]
@@ -103,18 +112,57 @@ class DecoderOnlyTransformer(nn.Module):
         return self._logits(h, B, T)
 
     # ---- incremental decoding -------------------------------------------------------------------
-    def new_cache(self, batch: int, device, context: torch.Tensor | None = None) -> _Cache:
-        return _Cache(self, batch, device, context)
+    def new_cache(self, batch: int, device, context: torch.Tensor | None = None, graph: bool = False) -> _Cache:
+        return _Cache(self, batch, device, context, graph)
+
+    def _step_dyn(self, x: torch.Tensor, cache: _Cache) -> torch.Tensor:
+        """One single-token step whose only notion of "where" is ``cache.pos_dev`` in device memory: the same kernel
+        sequence serves every position, which is what lets it be captured in a CUDA graph."""
+        B = x.shape[0]
+        pos = cache.pos_dev
+        h = ops.embed_tokens(x, f32(self.token_embeddings.weight), f32(self.position_embeddings.embedding.weight),
+                             pos_dev=pos)
+        for i, blk in enumerate(self.blocks):
+            n1 = blk._ln(blk.norm1, h)
+            k, v = blk.attn.project_kv(n1)
+            ops.cache_append(k.t, cache.k[i], 1, pos)
+            ops.cache_append(v.t, cache.v[i], 1, pos)
+            h = blk.attn.attend(n1, B, 1, cache.k[i], cache.v[i], 1, 0, residual=h, pos_dev=pos)
+            if self.with_cross_attention:
+                ck, cv = cache.cross[i]
+                h = blk.cross_attn.attend(blk._ln(blk.norm2, h), B, 1, ck, cv, cache.context_len, 0, residual=h)
+            h = blk.mlp(blk._ln(blk.norm3, h), residual=h)
+        logits = self._logits(h, B, 1)
+        ops.advance_i32(pos, 1)
+        return logits
+
+    def _step_graph(self, x: torch.Tensor, cache: _Cache) -> torch.Tensor:
+        if cache.graph is None:
+            if cache.dyn_steps < 2:                         # real steps that double as the capture's warm-up
+                cache.dyn_steps += 1
+                return self._step_dyn(x.long().contiguous(), cache)
+            cache.static_tokens = x.long().contiguous().clone()
+            torch.cuda.synchronize()
+            cache.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(cache.graph):
+                cache.static_logits = self._step_dyn(cache.static_tokens, cache)
+        cache.static_tokens.copy_(x, non_blocking=True)
+        cache.graph.replay()
+        return cache.static_logits
 
     @torch.no_grad()
     def step(self, x: torch.Tensor, cache: _Cache) -> torch.Tensor:
         """Logits [B, T_new, num_tokens] of ``x`` ([B, T_new] tokens that extend the cached prefix), identical to the
-        last T_new rows of ``forward`` on the whole sequence."""
+        last T_new rows of ``forward`` on the whole sequence.  (With a graph cache the returned tensor of a
+        single-token step is a static buffer, valid until the next step.)"""
         require_cuda(x, self)
         B, T = x.shape
         L = cache.length
         if B != cache.batch or L + T > self.max_seq_len:
             raise IndexError("key/value cache exhausted: the sequence no longer fits max_seq_len")
+        if cache.use_graph and T == 1:
+            cache.length = L + 1
+            return self._step_graph(x, cache)
         h = self._embed(x, L)
         for i, blk in enumerate(self.blocks):
             n1 = blk._ln(blk.norm1, h)
@@ -126,4 +174,6 @@ class DecoderOnlyTransformer(nn.Module):
                 h = blk.cross_attn.attend(blk._ln(blk.norm2, h), B, T, ck, cv, cache.context_len, 0, residual=h)
             h = blk.mlp(blk._ln(blk.norm3, h), residual=h)
         cache.length = L + T
+        if cache.use_graph:
+            cache.pos_dev.fill_(L + T)                       # keep the device-side position in step with eager steps
         return self._logits(h, B, T)

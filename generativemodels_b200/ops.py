@@ -862,7 +862,7 @@ def linear_into_cache(x: CL, B: int, T: int, pl: PackedLinear, cache: torch.Tens
 
 
 def attention_causal(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, dh: int, scale: float, S: int,
-                     causal: bool = True, q_pos0: int = 0) -> torch.Tensor:
+                     causal: bool = True, q_pos0: int = 0, pos_dev: torch.Tensor | None = None) -> torch.Tensor:
     """softmax(scale * Q K^T [+ causal mask]) V for the autoregressive transformer: q [B, T, pitch]; k, v
     [B, rows >= S, pitch] — typically a key/value cache of which the first S rows are valid; query row t sits at
     absolute position q_pos0 + t and, if causal, sees keys <= its position (blocks/selfattention.py:121-140)."""
@@ -873,11 +873,24 @@ def attention_causal(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: i
         out.zero_()
     check(lib.b200_attention_small_ex(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, T, S, heads, dh, qp,
                                       k.shape[2], v.shape[2], out.shape[2], scale, k.shape[1], int(causal), q_pos0,
-                                      _stream()), "b200_attention_small_ex")
+                                      _ptr(pos_dev), _stream()), "b200_attention_small_ex")
     return out
 
 
-def embed_tokens(tokens: torch.Tensor, tok_emb: torch.Tensor, pos_emb: torch.Tensor, pos0: int = 0) -> CL:
+def cache_append(src: torch.Tensor, cache: torch.Tensor, T: int, pos_dev: torch.Tensor) -> None:
+    """cache[b, *pos_dev + t, :] = src[b * T + t, :] with the position read on the device (graph-captured decoding)."""
+    lib = _lib.require_device()
+    B, L, P = cache.shape
+    check(lib.b200_cache_append(src.data_ptr(), cache.data_ptr(), B, T, L, P, pos_dev.data_ptr(), _stream()),
+          "b200_cache_append")
+
+
+def advance_i32(p: torch.Tensor, delta: int) -> None:
+    check(_lib.require_device().b200_advance_i32(p.data_ptr(), delta, _stream()), "b200_advance_i32")
+
+
+def embed_tokens(tokens: torch.Tensor, tok_emb: torch.Tensor, pos_emb: torch.Tensor, pos0: int = 0,
+                 pos_dev: torch.Tensor | None = None) -> CL:
     """Token + absolute-position embedding rows of an int64 [B, T] index tensor -> CL rows [1, 1, 1, B*T, pitch]."""
     lib = _lib.require_device()
     B, T = tokens.shape
@@ -885,7 +898,7 @@ def embed_tokens(tokens: torch.Tensor, tok_emb: torch.Tensor, pos_emb: torch.Ten
     tk = tokens if (tokens.dtype == torch.int64 and tokens.is_contiguous()) else tokens.long().contiguous()
     out = torch.empty((1, 1, 1, B * T, round_up(C_, 8)), dtype=torch.bfloat16, device=tokens.device)
     check(lib.b200_embed_tokens(tk.data_ptr(), B * T, T, pos0, tok_emb.data_ptr(), pos_emb.data_ptr(), C_,
-                                out.data_ptr(), out.shape[-1], _stream()), "b200_embed_tokens")
+                                out.data_ptr(), out.shape[-1], _ptr(pos_dev), _stream()), "b200_embed_tokens")
     return CL(out, C_, 2)
 
 

@@ -247,15 +247,23 @@ int b200_attention_small(const void* q, const void* k, const void* v, void* out,
                          int32_t v_pitch, int32_t o_pitch, float scale, void* stream);
 /* The same with the two things the autoregressive transformer needs (blocks/selfattention.py:93-140,
  * inferer.py:1183-1245): k / v may live in a cache of kv_rows >= S rows per batch item, and with causal != 0 query
- * row t (absolute position q_pos0 + t) attends to keys s <= q_pos0 + t only. */
+ * row t (absolute position q_pos0 + t) attends to keys s <= q_pos0 + t only.  With pos_dev != NULL the prefix length
+ * is read on the device (q_pos0 = *pos_dev, S = *pos_dev + T): the decode step can then be captured ONCE in a CUDA
+ * graph and replayed for every token. */
 int b200_attention_small_ex(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t T,
                             int32_t S, int32_t heads, int32_t dh, int32_t q_pitch, int32_t k_pitch,
                             int32_t v_pitch, int32_t o_pitch, float scale, int32_t kv_rows, int32_t causal,
-                            int32_t q_pos0, void* stream);
+                            int32_t q_pos0, const int32_t* pos_dev, void* stream);
 /* Token + absolute position embedding rows (nets/transformer.py:20-37, 97-99):
- * out[m, :] = tok_emb[tokens[m], :] + pos_emb[pos0 + m % seq_len, :], bf16 rows of pitch `pitch`. */
+ * out[m, :] = tok_emb[tokens[m], :] + pos_emb[pos0 + m % seq_len, :], bf16 rows of pitch `pitch`
+ * (pos0 = *pos_dev when pos_dev != NULL). */
 int b200_embed_tokens(const int64_t* tokens, int64_t M, int32_t seq_len, int32_t pos0, const float* tok_emb,
-                      const float* pos_emb, int32_t C, void* out, int32_t pitch, void* stream);
+                      const float* pos_emb, int32_t C, void* out, int32_t pitch, const int32_t* pos_dev, void* stream);
+/* Graph-captured decoding: append T rows per sequence to a [B, L, pitch] bf16 cache at the device-side position,
+ * and advance that position. */
+int b200_cache_append(const void* src, void* cache, int32_t B, int32_t T, int32_t L, int32_t pitch,
+                      const int32_t* pos_dev, void* stream);
+int b200_advance_i32(int32_t* p, int32_t delta, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Time embedding path (diffusion_model_unet.py:461-485, 1759-1767, 1888-1902; ResnetBlock 641,686).

@@ -262,7 +262,10 @@ class FakeLib:
         return 0
 
     def b200_attention_small_ex(self, q, k, v, o, B, T, S, heads, dh, qp, kp, vp, op, scale, kv_rows, causal, q_pos0,
-                                stream):
+                                pos_dev, stream):
+        if pos_dev:
+            q_pos0 = int(_np(pos_dev, 1, C.c_int32)[0])
+            S = q_pos0 + T
         Cc = heads * dh
         qq = bf16(q, B * T * qp).view(B, T, qp)[:, :, :Cc].float().view(B, T, heads, dh).transpose(1, 2)
         kk = bf16(k, B * kv_rows * kp).view(B, kv_rows, kp)[:, :S, :Cc].float().view(B, S, heads, dh).transpose(1, 2)
@@ -275,7 +278,18 @@ class FakeLib:
         bf16(o, B * T * op).view(B, T, op)[:, :, :Cc] = out.to(torch.bfloat16)
         return 0
 
-    def b200_embed_tokens(self, tokens, M, seq_len, pos0, tok_emb, pos_emb, C_, out, pitch, stream):
+    def b200_cache_append(self, src, cache, B, T, L, pitch, pos_dev, stream):
+        pos = int(_np(pos_dev, 1, C.c_int32)[0])
+        bf16(cache, B * L * pitch).view(B, L, pitch)[:, pos:pos + T] = bf16(src, B * T * pitch).view(B, T, pitch)
+        return 0
+
+    def b200_advance_i32(self, p, delta, stream):
+        _np(p, 1, C.c_int32)[0] += delta
+        return 0
+
+    def b200_embed_tokens(self, tokens, M, seq_len, pos0, tok_emb, pos_emb, C_, out, pitch, pos_dev, stream):
+        if pos_dev:
+            pos0 = int(_np(pos_dev, 1, C.c_int32)[0])
         tk = i64(tokens, M)
         V, Lmax = int(tk.max()) + 1, pos0 + seq_len
         te = f32(tok_emb, V * C_).view(V, C_)

@@ -282,6 +282,10 @@ def test_transformer_forward_and_cache_cpu(monkeypatch, cross):
     assert torch.equal(inc, got)
     with pytest.raises(IndexError):
         m.step(torch.randint(0, 11, (2, 8)), cache)
+    # the position-in-device-memory form of the single-token step (what the CUDA graph captures)
+    dyn = m.new_cache(2, x.device, ctx)
+    rows = [m._step_dyn(x[:, i:i + 1].contiguous(), dyn) for i in range(9)]
+    assert int(dyn.pos_dev) == 9 and torch.equal(torch.cat(rows, 1), got)
     if cross:
         with pytest.raises(ValueError):
             m(x)

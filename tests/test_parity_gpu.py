@@ -525,6 +525,11 @@ def test_transformer_vs_oracle(cuda_device, cross):
     cache = m.new_cache(2, torch.device("cuda"), None if ctx is None else ctx.cuda())
     inc = torch.cat([m.step(x[:, :7].cuda(), cache)] + [m.step(x[:, i:i + 1].cuda(), cache) for i in range(7, 33)], 1)
     check(inc, got.float().cpu(), 5e-3, "incremental decoding vs full forward")
+    # single-token steps replayed from ONE captured CUDA graph (prefix length in device memory), after a 7-token prompt
+    gc = m.new_cache(2, torch.device("cuda"), None if ctx is None else ctx.cuda(), graph=True)
+    rows = [m.step(x[:, :7].cuda(), gc)] + [m.step(x[:, i:i + 1].cuda(), gc).clone() for i in range(7, 33)]
+    assert gc.graph is not None and int(gc.pos_dev) == 33
+    check(torch.cat(rows, 1), got.float().cpu(), 5e-3, "graph-replayed decoding vs full forward")
 
 
 def test_vqvae_transformer_inferer_vs_oracle(cuda_device):

@@ -85,3 +85,31 @@ def cfg_sample(N, guidance=7.0):
 for N in (1,):
     t = timed(lambda: cfg_sample(N), 1)
     print(f"C5 ControlNet+CFG DDIM-50 N={N}: {t*1e3:.0f} ms/guided sample, {N*3*256*256/t/1e6:.3f} Mvalues/s")
+
+# ---- transformer sampler: 32x32 latent grid = 1024 tokens, 12 layers x 512, 8 heads ----
+from generativemodels_b200.inferers import VQVAETransformerInferer
+from generativemodels_b200.networks.nets import DecoderOnlyTransformer
+from generativemodels_b200.utils.ordering import Ordering
+
+vq2 = VQVAE(2, 1, 1, num_channels=(128, 128), num_res_channels=128, num_res_layers=2,
+            downsample_parameters=((2, 4, 1, 1),) * 2, upsample_parameters=((2, 4, 1, 1, 0),) * 2, num_embeddings=256,
+            embedding_dim=32).cuda().eval()
+tr = DecoderOnlyTransformer(num_tokens=257, max_seq_len=1025, attn_layers_dim=512, attn_layers_depth=12,
+                            attn_layers_heads=8).cuda().eval()
+order = Ordering("raster_scan", 2, (1, 32, 32))
+vinf = VQVAETransformerInferer()
+for N in (1, 8):
+    start = torch.full((N, 1), 256).cuda()
+    t = timed(lambda: vinf.sample((32, 32), start, vq2, tr, order, verbose=False), 1)
+    print(f"transformer sampler 1024 tokens N={N} (key/value cache): {t:.2f} s/call, {N*1024/t:.0f} tokens/s")
+
+
+class _NoCache:          # the reference's loop: full forward over the prefix for every token
+    def __init__(self, m): self.m = m; self.max_seq_len = m.max_seq_len
+    def __call__(self, x, context=None): return self.m(x, context=context)
+
+
+start = torch.full((1, 1), 256).cuda()
+t = timed(lambda: vinf.sample((16, 16), start, vq2, _NoCache(tr), Ordering("raster_scan", 2, (1, 16, 16)), verbose=False), 1)
+t2 = timed(lambda: vinf.sample((16, 16), start, vq2, tr, Ordering("raster_scan", 2, (1, 16, 16)), verbose=False), 1)
+print(f"transformer sampler 256 tokens N=1: prefix recompute per token {t:.2f} s, key/value cache {t2:.2f} s")
