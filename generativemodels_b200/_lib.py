@@ -123,6 +123,8 @@ SIGNATURES = {
     "b200_attention_small_ex": [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, C.c_float, _I32,
                                 _I32, _I32, _P, _P],
     "b200_embed_tokens": [_P, _I64, _I32, _I32, _P, _P, _I32, _P, _I32, _P, _P],
+    "b200_rows_linear": [_P, _I32, _I32, _I32, _P, _P, C.c_float, _P, _I32, _I32, _P, _I32, _P, _I32, _P, _I32, _I32, _P],
+    "b200_attention_decode": [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, C.c_float, _I32, _P, _P],
     "b200_cache_append": [_P, _P, _I32, _I32, _I32, _I32, _P, _P],
     "b200_advance_i32": [_P, _I32, _P],
     "b200_tap_gather": [_P, _I32, _I32, _P, _P, _I32, _P],

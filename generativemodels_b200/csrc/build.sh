@@ -7,7 +7,7 @@ mkdir -p "$out" "$here/.obj"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC"
 pids=()
-for f in core igemm norm elementwise vq attention_small flash_attn; do
+for f in core igemm norm elementwise vq attention_small flash_attn decode; do
   if [ ! -f "$here/.obj/$f.o" ] || [ "$here/$f.cu" -nt "$here/.obj/$f.o" ] || [ "$here/common.cuh" -nt "$here/.obj/$f.o" ] || [ "$here/../../include/b200gen.h" -nt "$here/.obj/$f.o" ]; then
     $NVCC $FLAGS -c "$here/$f.cu" -o "$here/.obj/$f.o" &
     pids+=($!)

@@ -122,6 +122,8 @@ class DecoderOnlyTransformer(nn.Module):
         pos = cache.pos_dev
         h = ops.embed_tokens(x, f32(self.token_embeddings.weight), f32(self.position_embeddings.embedding.weight),
                              pos_dev=pos)
+        if B <= 8:
+            return self._step_rows(h.t.reshape(B, -1), cache)
         for i, blk in enumerate(self.blocks):
             n1 = blk._ln(blk.norm1, h)
             k, v = blk.attn.project_kv(n1)
@@ -135,6 +137,36 @@ class DecoderOnlyTransformer(nn.Module):
         logits = self._logits(h, B, 1)
         ops.advance_i32(pos, 1)
         return logits
+
+    def _step_rows(self, h: torch.Tensor, cache: _Cache) -> torch.Tensor:
+        """The same step for at most 8 sequences: every linear layer is a GEMV (b200_rows_linear, LayerNorm fused into
+        its prologue, GELU / residual into its epilogue) and attention is one query per (sequence, head) over the
+        cache (b200_attention_decode) — ~9 small launches per layer instead of 128-row tensor-core tiles."""
+        B, C_ = h.shape[0], self.attn_layers_dim
+        pos = cache.pos_dev
+        for i, blk in enumerate(self.blocks):
+            a = blk.attn
+            ln1 = (f32(blk.norm1.weight), f32(blk.norm1.bias), blk.norm1.eps)
+            q = ops.rows_linear(h, C_, packed_linear(a, "to_q"), ln=ln1)
+            k = ops.rows_linear(h, C_, packed_linear(a, "to_k"), ln=ln1)
+            v = ops.rows_linear(h, C_, packed_linear(a, "to_v"), ln=ln1)
+            ops.cache_append(k, cache.k[i], 1, pos)
+            ops.cache_append(v, cache.v[i], 1, pos)
+            o = ops.attention_decode(q, cache.k[i], cache.v[i], a.num_heads, a.head_dim, a.scale, 1, pos_dev=pos)
+            h = ops.rows_linear(o, C_, packed_linear(a, "out_proj"), residual=h)
+            if self.with_cross_attention:
+                c = blk.cross_attn
+                ck, cv = cache.cross[i]
+                ln2 = (f32(blk.norm2.weight), f32(blk.norm2.bias), blk.norm2.eps)
+                q = ops.rows_linear(h, C_, packed_linear(c, "to_q"), ln=ln2)
+                o = ops.attention_decode(q, ck, cv, c.num_heads, c.head_dim, c.scale, cache.context_len)
+                h = ops.rows_linear(o, C_, packed_linear(c, "out_proj"), residual=h)
+            ln3 = (f32(blk.norm3.weight), f32(blk.norm3.bias), blk.norm3.eps)
+            m = ops.rows_linear(h, C_, packed_linear(blk.mlp, "linear1"), ln=ln3, act=ops.ACT_GELU)
+            h = ops.rows_linear(m, blk.mlp.linear1.out_features, packed_linear(blk.mlp, "linear2"), residual=h)
+        logits = ops.rows_linear(h, C_, packed_linear(self, "to_logits"), out_f32=True)
+        ops.advance_i32(pos, 1)
+        return logits[:, : self.num_tokens].reshape(B, 1, self.num_tokens)
 
     def _step_graph(self, x: torch.Tensor, cache: _Cache) -> torch.Tensor:
         if cache.graph is None:

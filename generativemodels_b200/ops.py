@@ -877,6 +877,41 @@ def attention_causal(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: i
     return out
 
 
+def rows_linear(x: torch.Tensor, K: int, pl: PackedLinear, *, ln=None, act: int = ACT_NONE,
+                residual: torch.Tensor | None = None, out_f32: bool = False) -> torch.Tensor:
+    """Decode-time linear layer on M <= 8 bf16 rows ``x`` [M, pitch]: act(LN?(x) @ W^T + b) + residual, one GEMV
+    kernel (b200_rows_linear).  ``ln`` = (gamma, beta, eps) fuses the preceding LayerNorm."""
+    lib = _lib.require_device()
+    M = x.shape[0]
+    if K != pl.K:
+        raise ValueError(f"linear expects {pl.K} input features, got {K}")
+    out = torch.empty((M, round_up(pl.cout, 4 if out_f32 else 8)), dtype=torch.float32 if out_f32 else torch.bfloat16,
+                      device=x.device)
+    if out.shape[1] > pl.cout:
+        out.zero_()
+    g, b, eps = (ln[0].data_ptr(), ln[1].data_ptr(), float(ln[2])) if ln is not None else (None, None, 0.0)
+    check(lib.b200_rows_linear(x.data_ptr(), x.shape[1], M, K, g, b, eps, pl.w.data_ptr(), pl.w.shape[1], pl.cout,
+                               _ptr(pl.bias), act, _ptr(residual), 0 if residual is None else residual.shape[1],
+                               out.data_ptr(), out.shape[1], DT_F32 if out_f32 else DT_BF16, _stream()),
+          "b200_rows_linear")
+    return out
+
+
+def attention_decode(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, dh: int, scale: float, S: int,
+                     pos_dev: torch.Tensor | None = None) -> torch.Tensor:
+    """One query row per sequence ([B, pitch]) over the first S rows of the key / value caches [B, rows, pitch]
+    (S = *pos_dev + 1 when ``pos_dev`` is given)."""
+    lib = _lib.require_device()
+    B = q.shape[0]
+    out = torch.empty((B, round_up(heads * dh, 8)), dtype=torch.bfloat16, device=q.device)
+    if out.shape[1] > heads * dh:
+        out.zero_()
+    check(lib.b200_attention_decode(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, S, heads, dh,
+                                    q.shape[1], k.shape[2], v.shape[2], out.shape[1], scale, k.shape[1], _ptr(pos_dev),
+                                    _stream()), "b200_attention_decode")
+    return out
+
+
 def cache_append(src: torch.Tensor, cache: torch.Tensor, T: int, pos_dev: torch.Tensor) -> None:
     """cache[b, *pos_dev + t, :] = src[b * T + t, :] with the position read on the device (graph-captured decoding)."""
     lib = _lib.require_device()

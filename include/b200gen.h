@@ -264,6 +264,20 @@ int b200_embed_tokens(const int64_t* tokens, int64_t M, int32_t seq_len, int32_t
 int b200_cache_append(const void* src, void* cache, int32_t B, int32_t T, int32_t L, int32_t pitch,
                       const int32_t* pos_dev, void* stream);
 int b200_advance_i32(int32_t* p, int32_t delta, void* stream);
+/* Decode-time linear layers (one new token per sequence: M <= 8 rows, HBM/L2-bound GEMVs):
+ *   out[m, o] = act( LN?(x[m, :]) . w[o, :] + bias[o] ) + res[m, o]
+ * x bf16 rows; ln_gamma / ln_beta (NULL = no LayerNorm; nn.LayerNorm semantics, output rounded to bf16 as the
+ * stand-alone kernel does); w = the K-major bf16 matrix b200_igemm consumes (row pitch w_pitch, multiple of 8);
+ * out bf16 or fp32 (out_dtype).  (blocks/transformerblock.py:87-92, blocks/selfattention.py:103-110, 145.) */
+int b200_rows_linear(const void* x, int32_t x_pitch, int32_t M, int32_t K, const float* ln_gamma,
+                     const float* ln_beta, float ln_eps, const void* w, int32_t w_pitch, int32_t O, const float* bias,
+                     int32_t act, const void* res, int32_t r_pitch, void* out, int32_t o_pitch, int32_t out_dtype,
+                     void* stream);
+/* One query row per (batch, head) against S cached keys / values ([B, kv_rows, pitch] bf16; S = *pos_dev + 1 when
+ * pos_dev != NULL): the keys are split over the warps of a block and the online-softmax states merged. */
+int b200_attention_decode(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t S,
+                          int32_t heads, int32_t dh, int32_t q_pitch, int32_t k_pitch, int32_t v_pitch,
+                          int32_t o_pitch, float scale, int32_t kv_rows, const int32_t* pos_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Time embedding path (diffusion_model_unet.py:461-485, 1759-1767, 1888-1902; ResnetBlock 641,686).

@@ -278,6 +278,29 @@ class FakeLib:
         bf16(o, B * T * op).view(B, T, op)[:, :, :Cc] = out.to(torch.bfloat16)
         return 0
 
+    def b200_rows_linear(self, x, xp, M, K, g, b, eps, w, wp, O, bias, act, res, rp, out, op, odt, stream):
+        xs = bf16(x, M * xp).view(M, xp)[:, :K].float()
+        if g:
+            xs = F.layer_norm(xs, (K,), f32(g, K), f32(b, K), eps).to(torch.bfloat16).float()
+        W = bf16(w, O * wp).view(O, wp)[:, :K].float()
+        y = xs @ W.t()
+        if bias:
+            y = y + f32(bias, O)
+        y = _act(y, act)
+        if res:
+            y = y + bf16(res, M * rp).view(M, rp)[:, :O].float()
+        if odt == _lib.DT_F32:
+            f32(out, M * op).view(M, op)[:, :O] = y
+        else:
+            bf16(out, M * op).view(M, op)[:, :O] = y.to(torch.bfloat16)
+        return 0
+
+    def b200_attention_decode(self, q, k, v, o, B, S, heads, dh, qp, kp, vp, op, scale, kv_rows, pos_dev, stream):
+        if pos_dev:
+            S = int(_np(pos_dev, 1, C.c_int32)[0]) + 1
+        return self.b200_attention_small_ex(q, k, v, o, B, 1, S, heads, dh, qp, kp, vp, op, scale, kv_rows, 0, 0, None,
+                                            stream)
+
     def b200_cache_append(self, src, cache, B, T, L, pitch, pos_dev, stream):
         pos = int(_np(pos_dev, 1, C.c_int32)[0])
         bf16(cache, B * L * pitch).view(B, L, pitch)[:, pos:pos + T] = bf16(src, B * T * pitch).view(B, T, pitch)

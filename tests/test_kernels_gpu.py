@@ -465,6 +465,49 @@ def test_embed_tokens_gelu_and_cache_projection(cuda_device):
     assert cache[:, :6].abs().sum().item() == 0 and cache[:, 6 + T:].abs().sum().item() == 0
 
 
+@pytest.mark.parametrize("M,K,O,ln,act,res,f32out", [(1, 512, 512, True, 0, False, False), (8, 512, 2048, True, 4, False, False),
+                                                     (3, 2048, 512, False, 0, True, False), (2, 40, 257, False, 0, False, True),
+                                                     (5, 64, 17, True, 2, True, False)])
+def test_rows_linear(cuda_device, M, K, O, ln, act, res, f32out):
+    """b200_rows_linear: decode-time GEMV with LayerNorm prologue and bias / activation / residual epilogue."""
+    ops = _ops()
+    torch.manual_seed(23)
+    x, w, b = torch.randn(M, K), torch.randn(O, K) / math.sqrt(K), torch.randn(O)
+    g, be = torch.randn(K), torch.randn(K)
+    r = torch.randn(M, O)
+    xin = bf(x)
+    if ln:
+        xin = bf(F.layer_norm(xin, (K,), g, be, 1e-5))
+    ref = F.linear(xin, bf(w), b)
+    ref = {0: ref, 2: F.silu(ref), 4: F.gelu(ref)}[act]
+    if res:
+        ref = ref + bf(r)
+    P = (K + 7) // 8 * 8
+    xg = F.pad(x, (0, P - K)).to(torch.bfloat16).cuda()
+    pl = ops.PackedLinear(w.cuda(), b.cuda())
+    rg = F.pad(r, (0, (-O) % 8)).to(torch.bfloat16).cuda() if res else None
+    out = ops.rows_linear(xg, K, pl, ln=(g.cuda(), be.cuda(), 1e-5) if ln else None, act=act, residual=rg, out_f32=f32out)
+    assert out.dtype == (torch.float32 if f32out else torch.bfloat16)
+    assert_close(out[:, :O], ref, 1e-2, "rows_linear")
+
+
+@pytest.mark.parametrize("B,S,heads,dh", [(1, 1, 8, 64), (3, 1000, 8, 64), (8, 37, 2, 32), (2, 300, 1, 256)])
+def test_attention_decode(cuda_device, B, S, heads, dh):
+    """b200_attention_decode (keys split over 8 warps, merged online-softmax states) incl. the device-side length."""
+    ops = _ops()
+    torch.manual_seed(24)
+    Cc = heads * dh
+    rows = S + 3
+    q, k, v = torch.randn(B, Cc), torch.randn(B, rows, Cc), torch.randn(B, rows, Cc)
+    ref = _attn_ref(bf(q)[:, None], bf(k)[:, :S], bf(v)[:, :S], heads, dh, 1 / math.sqrt(dh))[:, 0]
+    g = lambda t: t.to(torch.bfloat16).cuda().contiguous()
+    out = ops.attention_decode(g(q), g(k), g(v), heads, dh, 1 / math.sqrt(dh), S)
+    assert_close(out[:, :Cc], ref, 1e-2, "attention_decode")
+    pos = torch.tensor([S - 1], dtype=torch.int32).cuda()
+    out2 = ops.attention_decode(g(q), g(k), g(v), heads, dh, 1 / math.sqrt(dh), 1, pos_dev=pos)
+    assert torch.equal(out, out2)
+
+
 # ------------------------------------------------------------------------------------------------ time embedding
 def test_timestep_embedding_and_small_linear(cuda_device):
     ops = _ops()

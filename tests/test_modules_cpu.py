@@ -285,7 +285,7 @@ def test_transformer_forward_and_cache_cpu(monkeypatch, cross):
     # the position-in-device-memory form of the single-token step (what the CUDA graph captures)
     dyn = m.new_cache(2, x.device, ctx)
     rows = [m._step_dyn(x[:, i:i + 1].contiguous(), dyn) for i in range(9)]
-    assert int(dyn.pos_dev) == 9 and torch.equal(torch.cat(rows, 1), got)
+    assert int(dyn.pos_dev) == 9 and rel(torch.cat(rows, 1), got) < 1e-2      # GEMV path: other rounding points
     if cross:
         with pytest.raises(ValueError):
             m(x)
