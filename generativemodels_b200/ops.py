@@ -708,6 +708,7 @@ _TC_ATTN_MIN_S = 64
 _FLASH_HEAD_DIMS = (64, 128, 256, 512)
 _FORCE_UNFUSED_ATTENTION = False      # tests flip this to cover the GEMM + softmax + GEMM path
 _LAST_FLASH_WS = None
+_KEEP_FLASH_WS = False
 _FLASH_REPLAY = True                  # tests flip this to compare the replay and recompute variants of head_dim 512
 _ATTN_CHUNK_BYTES = 6 << 30   # fp32 score slab per query chunk
 
@@ -754,8 +755,9 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, dh:
             if need:        # head_dim 512: probability tiles are written once and replayed for the second output half
                 ws = torch.empty(need, dtype=torch.uint8, device=q.device)
                 fp.workspace, fp.workspace_bytes = ws.data_ptr(), need
-                global _LAST_FLASH_WS
-                _LAST_FLASH_WS = ws           # dev probes read the kernel's debug counters from here
+                if _KEEP_FLASH_WS:            # dev probes (tools/attn_timing.py) read the kernel's counters from here
+                    global _LAST_FLASH_WS
+                    _LAST_FLASH_WS = ws
         check(lib.b200_attention_flash(C.byref(fp), _stream()), "b200_attention_flash")
         return out
     Sp = round_up(S, 8)

@@ -7,6 +7,7 @@ from generativemodels_b200 import _lib
 if os.environ.get("B200_DEV_LIB"):
     _lib.LIB_PATH = Path(os.environ["B200_DEV_LIB"]).resolve()
 from generativemodels_b200 import ops
+ops._KEEP_FLASH_WS = True
 T = S = 89600
 dh = 512
 torch.manual_seed(0)
