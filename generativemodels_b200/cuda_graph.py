@@ -6,7 +6,9 @@ few microseconds each per step, where the reference runs at 60-160 it/s regardle
 
 The wrapped module is captured with ``torch.cuda.graph`` on its first call for a given (shapes, dtypes, optional-args)
 signature: inputs are copied into static buffers, the graph is replayed, and the static output tensor is returned
-(valid until the next call with the same signature — exactly how a sampler consumes it).  Everything the forward does
+(valid until the next call with the same signature — exactly how a sampler consumes it).  A captured graph bakes in the
+addresses of the packed weights, so the cache is dropped whenever a parameter or buffer of the module is replaced or
+modified in place (``load_state_dict``, ``.to()``, an optimiser step): the next call re-captures.  Everything the forward does
 is capture-safe by construction: allocations come from the graph's private pool, kernels are enqueued on the current
 (capturing) stream through the C-ABI, tensor maps are encoded on the host with fixed addresses.
 """
@@ -22,6 +24,10 @@ class GraphedModule(nn.Module):
         self.module = module
         self._warmup = warmup
         self._entries: dict = {}
+        self._weights_sig = None
+
+    def _current_weights_sig(self):
+        return tuple((t.data_ptr(), t._version) for t in list(self.module.parameters()) + list(self.module.buffers()))
 
     def __getattr__(self, name):
         try:
@@ -45,6 +51,10 @@ class GraphedModule(nn.Module):
             key = self._sig(args, kwargs)
         except TypeError:
             return self.module(*args, **kwargs)          # e.g. channels-last residual handles: run eagerly
+        sig = self._current_weights_sig()
+        if sig != self._weights_sig:            # weights changed since the graphs were captured: they are stale
+            self._entries.clear()
+            self._weights_sig = sig
         entry = self._entries.get(key)
         if entry is None:
             static_args = [a.clone() if torch.is_tensor(a) else a for a in args]

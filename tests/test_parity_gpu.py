@@ -606,3 +606,8 @@ def test_cuda_graph_replay_matches_eager(cuda_device):
     a = DiffusionInferer(s).sample(x, m, s, verbose=False)
     b = DiffusionInferer(s).sample(x, g, s, verbose=False)
     assert torch.equal(a, b)
+    # new weights invalidate the captured graphs (they bake in the packed weights' addresses)
+    with torch.no_grad():
+        m.conv_in.conv.weight.mul_(1.5)
+    ts = torch.Tensor((500.0,)).cuda()
+    assert torch.equal(g(x, timesteps=ts).clone(), m(x, timesteps=ts))
