@@ -213,6 +213,13 @@ __device__ __forceinline__ void stg256(void* ptr, const uint32_t* w) {
 // O2 += P V2 — a pure GEMM stream with no QK^T and no exponentials (2/3 of the recompute variant's tensor work).
 // The rare lazy-rescale events of pass 1 are logged per warp (block index + per-row factor) and replayed on O2 at
 // the same block positions, so both slices see bit-identical P and the same normaliser l.
+// dev ablation (-DFA_ABLATE=6): every K / V^T load re-reads key block 0, i.e. always hits L2
+#if defined(FA_ABLATE) && FA_ABLATE == 6
+#define FA_KVROW(j) 0
+#else
+#define FA_KVROW(j) (j)
+#endif
+
 #ifdef FA_TIMING
 #define FA_T(i) do { long long fa_now = clock64(); fa_acc[i] += fa_now - fa_last; fa_last = fa_now; } while (0)
 #else
@@ -305,7 +312,7 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
 #pragma unroll
                 for (int cc = 0; cc < CPS; ++cc)
                   tma_load_3d(&p.tmK, k_full(kst), sK + kst * kKStageBytes + cc * kKChunkBytes,
-                              ch0 + (step * CPS + cc) * 64, j * kBKV, it.b);
+                              ch0 + (step * CPS + cc) * 64, FA_KVROW(j) * kBKV, it.b);
               }
               __syncwarp();
               if (++kst == kKStages) { kst = 0; kph ^= 1u; }
@@ -315,7 +322,7 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
             mbar_wait_warp(v_empty, (vcount & 1) ^ 1u);
             if (elect_one()) {
               mbar_expect_tx(v_full, p.dv * kBKV * 2);
-              tma_load_3d(&p.tmVt, v_full, sV, (j - kLookahead) * kBKV, ch0 + it.dvi * p.dv, it.b);
+              tma_load_3d(&p.tmVt, v_full, sV, FA_KVROW(j - kLookahead) * kBKV, ch0 + it.dvi * p.dv, it.b);
             }
             __syncwarp();
             ++vcount;
