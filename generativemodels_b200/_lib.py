@@ -6,7 +6,6 @@ raises — there is no CPU or PyTorch fallback anywhere in this package.
 from __future__ import annotations
 
 import ctypes as C
-import os
 from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent

@@ -18,7 +18,7 @@ import torch
 import torch.nn as nn
 
 from ... import ops
-from ...ops import ACT_NONE, ACT_SILU, CL
+from ...ops import ACT_SILU, CL
 from ..blocks.spade_norm import SPADE
 from .._holders import Convolution, f32, packed_linear, require_cuda
 

@@ -7,7 +7,6 @@ arithmetic is what moves to the GPU: each ``step`` reduces its coefficients to s
 """
 from __future__ import annotations
 
-import ctypes as C
 from enum import Enum
 
 import torch

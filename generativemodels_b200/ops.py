@@ -7,7 +7,6 @@ Internal activation format: :class:`CL` — channels-last bf16 ``[N, D, H, W, pi
 from __future__ import annotations
 
 import ctypes as C
-import math
 from dataclasses import dataclass
 from typing import Sequence
 
