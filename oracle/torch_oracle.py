@@ -890,3 +890,28 @@ def transformer_sample_greedy(sd, heads, max_seq_len, bos, seq_len, batch, conte
         logits[:, bos] = -float("inf")            # probs[:, num_embeddings] = 0 in the reference
         seq = torch.cat([seq, logits.argmax(-1, keepdim=True)], dim=1)
     return seq[:, 1:]
+
+
+# ======================================================================================================
+# brain-LDM bundle scripts  (model-zoo/models/brain_image_synthesis_latent_diffusion_model/scripts)
+# ======================================================================================================
+
+
+def bundle_sampling_fn(model_fn, decode_fn, scheduler, input_noise, conditioning):
+    """Sampler.sampling_fn (scripts/sampler.py:17-52): the conditioning vector is both broadcast to planes that are
+    concatenated to the latent and passed as cross-attention context; long timesteps; decode_stage_2_outputs at the
+    end (the CUDA autocast around it is a no-op on the CPU)."""
+    image = input_noise
+    cond_concat = conditioning.squeeze(1).unsqueeze(-1).unsqueeze(-1).unsqueeze(-1)
+    cond_concat = cond_concat.expand(list(cond_concat.shape[0:2]) + list(input_noise.shape[2:]))
+    for t in scheduler.timesteps:
+        out = model_fn(torch.cat((image, cond_concat), dim=1), torch.Tensor((t,)).long(), conditioning)
+        image, _ = scheduler.step(out, int(t), image)
+    return decode_fn(image)
+
+
+def bundle_nifti_quantise(image_data: np.ndarray) -> np.ndarray:
+    """NiftiSaver.save up to the nibabel call (scripts/saver.py:22-25)."""
+    image_data = image_data[0, 0, 5:-5, 5:-5, :-15]
+    image_data = (image_data - image_data.min()) / (image_data.max() - image_data.min())
+    return (image_data * 255).astype(np.uint8)

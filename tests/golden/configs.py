@@ -122,3 +122,17 @@ def randomize_zero_params(module, std=0.02, seed=1):
             if p.numel() > 0 and float(p.abs().max()) == 0.0:
                 p.copy_(torch.randn(p.shape, generator=g) * std)
     return module
+
+
+# brain-LDM bundle (model-zoo/.../configs/inference.json) at reduced widths: same topology and flags
+BUNDLE_AEKL = dict(spatial_dims=3, in_channels=1, out_channels=1, latent_channels=3, num_channels=(8, 8, 16, 16),
+                   num_res_blocks=2, norm_num_groups=4, norm_eps=1e-06, attention_levels=(False,) * 4,
+                   with_encoder_nonlocal_attn=False, with_decoder_nonlocal_attn=False)
+BUNDLE_UNET = dict(spatial_dims=3, in_channels=7, out_channels=3, num_channels=(8, 16, 16), num_res_blocks=2,
+                   attention_levels=(False, True, True), norm_num_groups=8, norm_eps=1e-06, resblock_updown=True,
+                   num_head_channels=(0, 16, 16), with_conditioning=True, transformer_num_layers=1,
+                   cross_attention_dim=4, upcast_attention=True, use_flash_attention=False)
+BUNDLE_SCHEDULER = dict(beta_start=0.0015, beta_end=0.0205, num_train_timesteps=1000, schedule="scaled_linear_beta",
+                        clip_sample=False)
+BUNDLE_STEPS = 5
+BUNDLE_NOISE = (1, 3, 4, 8, 4)
