@@ -208,7 +208,8 @@ def run_b200(args):
     launches = {"n": 0, "on": False}
     for name in _lib.SIGNATURES:
         if name in ("b200_last_error_string", "b200_version", "b200_device_check", "b200_sm_count", "b200_abi_sizeof",
-                    "b200_groupnorm_workspace_bytes", "b200_attention_flash_workspace_bytes"):
+                    "b200_groupnorm_workspace_bytes", "b200_attention_flash_workspace_bytes",
+                    "b200_igemm_split_workspace_bytes"):
             continue
         fn = getattr(lib, name)
 

@@ -45,6 +45,7 @@ class IgemmParams(C.Structure):
         ("res_sN", C.c_int64), ("res_sD", C.c_int64), ("res_sH", C.c_int64), ("res_sW", C.c_int64),
         ("act2", C.c_int32), ("stat_ptr", C.c_void_p), ("impl", C.c_int32),
         ("gn_partial", C.c_void_p), ("gn_slots", C.c_int32), ("gn_slot0", C.c_int32),
+        ("split_ws", C.c_void_p), ("split_ws_bytes", C.c_int64),
     ]
 
 
@@ -130,6 +131,7 @@ SIGNATURES = {
     "b200_tap_sum": [_P, _I32, _P, _I32, _P, _P, _I32, _I32, _P],
     "b200_attention_flash": [C.POINTER(FlashParams), _P],
     "b200_attention_flash_workspace_bytes": [C.POINTER(FlashParams)],
+    "b200_igemm_split_workspace_bytes": [C.POINTER(IgemmParams)],
     "b200_attention_small": [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _F, _P],
     "b200_timestep_embedding": [_P, _I32, _I32, _F, _P, _P],
     "b200_small_linear": [_P, _I32, _I32, _P, _P, _I32, _I32, _I32, _P, _P],
@@ -145,7 +147,7 @@ SIGNATURES = {
     "b200_vq_gather": [_P, _I64, _P, _I32, _I32, _P, _I32, _P],
 }
 _RESTYPES = {"b200_last_error_string": C.c_char_p, "b200_groupnorm_workspace_bytes": C.c_int64,
-             "b200_attention_flash_workspace_bytes": C.c_int64}
+             "b200_attention_flash_workspace_bytes": C.c_int64, "b200_igemm_split_workspace_bytes": C.c_int64}
 
 _lib = None
 _device_ok = False

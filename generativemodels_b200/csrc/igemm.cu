@@ -55,6 +55,8 @@ struct IgemmDev {
   int N, OD, OH, OW;
   int BW, BH, BD, bw_log2, bh_log2;
   int tiles_w, tiles_h, tiles_d, tiles_n, num_tiles;
+  int k_splits;             // >= 1: the reduction of every tile is cut into this many chunk ranges (fastest tile index)
+  long long split_stride;   // output elements between the partial results of consecutive ranges
   // epilogue
   void* out_ptr;
   int out_dtype, cout, out_cols, out_vec, out_staged, out_v256;
@@ -195,6 +197,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// first reduction chunk of range `ks` when `num_k` chunks are cut into `splits` near-equal ranges
+__host__ __device__ __forceinline__ int split_begin(int num_k, int splits, int ks) {
+  return (int)(((long long)num_k * ks) / splits);
+}
 
 // ------------------------------------------------------------------------------------------------
 // Fused epilogue for CH consecutive columns of one output row (shared by both kernels).
@@ -493,6 +500,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         int t = tile;
+        const int ks = t % p.k_splits; t /= p.k_splits;
         const int nt = t % p.tiles_n; t /= p.tiles_n;
         const int wt = t % p.tiles_w; t /= p.tiles_w;
         const int ht = t % p.tiles_h; t /= p.tiles_h;
@@ -501,12 +509,15 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
         const int iw0 = wt * p.BW * p.sw, ih0 = ht * p.BH * p.sh, id0 = dt * p.BD * p.sd;
         const int n0 = nt * BN;
         const int wb = p.w_batched ? nb : 0;
+        const int k_begin = split_begin(num_k, p.k_splits, ks), k_end = split_begin(num_k, p.k_splits, ks + 1);
         int kglob = 0;
         for (int s = 0; s < p.n_seg; ++s) {
           const SegDev sg = p.seg[s];
+          if (kglob + sg.nchunks <= k_begin || kglob >= k_end) { kglob += sg.nchunks; continue; }
           const CUtensorMap* tm = &p.tmA[sg.src];
           const int cw = iw0 + sg.dw, ch = ih0 + sg.dh, cd = id0 + sg.dd;
           for (int c = 0; c < sg.nchunks; ++c, ++kglob) {
+            if (kglob < k_begin || kglob >= k_end) continue;
             mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t a_dst = smem_base + stage * kStageBytes;
             mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
@@ -530,7 +541,9 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
         mbar_wait(tempty_bar(buf), acc_phase ^ 1u);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + buf * BN;
-        for (int k = 0; k < num_k; ++k) {
+        const int ks = tile % p.k_splits;
+        const int nk = split_begin(num_k, p.k_splits, ks + 1) - split_begin(num_k, p.k_splits, ks);
+        for (int k = 0; k < nk; ++k) {
           mbar_wait(full_bar(stage), phase);
           tcgen05_fence_after();
           const uint32_t a_addr = smem_base + stage * kStageBytes;
@@ -580,6 +593,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       int t = tile;
+      const int ks = t % p.k_splits; t /= p.k_splits;
       const int nt = t % p.tiles_n; t /= p.tiles_n;
       const int wt = t % p.tiles_w; t /= p.tiles_w;
       const int ht = t % p.tiles_h; t /= p.tiles_h;
@@ -587,7 +601,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
       const int nb = t;
       const int ow = wt * p.BW + rw, oh = ht * p.BH + rh, od = dt * p.BD + rd;
       const bool row_ok = (ow < p.OW) && (oh < p.OH) && (od < p.OD);
-      const long long out_off = nb * p.out_sN + od * p.out_sD + oh * p.out_sH + ow * p.out_sW;
+      const long long out_off = nb * p.out_sN + od * p.out_sD + oh * p.out_sH + ow * p.out_sW + ks * p.split_stride;
       const long long res_off = nb * p.res_sN + od * p.res_sD + oh * p.res_sH + ow * p.res_sW;
       const int n0 = nt * BN;
 
@@ -824,6 +838,77 @@ __global__ void gn8_partial_check_kernel(const __grid_constant__ IgemmDev p) {
   atomicAdd(dst + 1, q);
 }
 
+// Split-K second pass: one thread per (output row, 8-column group) sums the fp32 partials of the S reduction ranges
+// in range order (deterministic) and applies the call's real epilogue — the same epilogue_math / store_direct the
+// one-pass kernels use.
+__global__ void __launch_bounds__(256) igemm_split_reduce_kernel(const IgemmDev p, const float* __restrict__ ws,
+                                                                 int splits, int ws_cols, long long ws_stride) {
+  const int groups = (p.out_cols + 7) >> 3;
+  const long long rows = (long long)p.N * p.OD * p.OH * p.OW;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= rows * groups) return;
+  const int col0 = (int)(idx % groups) * 8;
+  const long long row = idx / groups;
+  long long t = row;
+  const int ow = (int)(t % p.OW); t /= p.OW;
+  const int oh = (int)(t % p.OH); t /= p.OH;
+  const int od = (int)(t % p.OD); t /= p.OD;
+  const int nb = (int)t;
+  float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const float* src = ws + row * ws_cols + col0;
+  for (int s = 0; s < splits; ++s, src += ws_stride) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(src + 4));
+    v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+    v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+  }
+  const long long out_off = nb * p.out_sN + od * p.out_sD + oh * p.out_sH + ow * p.out_sW;
+  const long long res_off = nb * p.res_sN + od * p.res_sD + oh * p.res_sH + ow * p.res_sW;
+  epilogue_math<8>(p, v, nb, ow, res_off, col0);
+  store_direct<8>(p, v, out_off, col0);
+}
+
+// Launch geometry shared by b200_igemm and b200_igemm_split_workspace_bytes (host only, no CUDA calls but sm_count()).
+struct Plan {
+  TileShape ts;
+  long long m_tiles, ntiles, rows;
+  int kchunks, BN, tiles_n;
+  int splits, ws_cols;
+  long long ws_bytes;
+};
+static Plan make_plan(const b200_igemm_params* p) {
+  Plan pl;
+  pl.kchunks = 0;
+  for (int s = 0; s < p->n_seg; ++s) pl.kchunks += p->seg[s].nchunks;
+  pl.ts = choose_tile(p->out_W, p->out_H, p->out_D, p->stride_w, p->stride_h, p->stride_d);
+  const long long tw = (p->out_W + pl.ts.bw - 1) / pl.ts.bw, th = (p->out_H + pl.ts.bh - 1) / pl.ts.bh,
+                  td = (p->out_D + pl.ts.bd - 1) / pl.ts.bd;
+  pl.m_tiles = tw * th * td * p->out_N;
+  pl.rows = (long long)p->out_N * p->out_D * p->out_H * p->out_W;
+  // N tile: as wide as the output needs, but narrower when the grid would not fill the SMs
+  const int cols16 = ((p->out_cols + 15) / 16) * 16;
+  int BN = cols16 <= 16 ? 16 : cols16 <= 32 ? 32 : cols16 <= 64 ? 64 : cols16 <= 128 ? 128 : 256;
+  if (p->stat_ptr) BN = 256;      // the caller sizes the partials buffer for 256-column tiles
+  while (!p->stat_ptr && BN > 64 && pl.m_tiles * ((cols16 + BN - 1) / BN) < sm_count() && pl.kchunks >= 8) BN >>= 1;
+  pl.BN = BN;
+  pl.tiles_n = (cols16 + BN - 1) / BN;
+  pl.ntiles = pl.m_tiles * pl.tiles_n;
+  // Split the reduction when at least three ranges of four or more 64-element chunks fit the idle SMs.
+  pl.splits = 1;
+  pl.ws_cols = ((p->out_cols + 7) / 8) * 8;
+  pl.ws_bytes = 0;
+  if (!p->stat_ptr && !p->gn_partial && p->impl != 1 && pl.kchunks >= 16 && pl.ntiles * 3 <= sm_count()) {
+    long long s = sm_count() / pl.ntiles;
+    if (s > pl.kchunks / 4) s = pl.kchunks / 4;
+    if (s > 32) s = 32;
+    if (s >= 3) {
+      pl.splits = (int)s;
+      pl.ws_bytes = s * pl.rows * pl.ws_cols * 4;
+    }
+  }
+  return pl;
+}
+
 template <int BN, int STAGES>
 static int launch_tc(const IgemmDev& d, cudaStream_t stream) {
   constexpr int kStageBytes = kABytes + BN * kBK * 2;
@@ -852,6 +937,14 @@ static int env_impl() {
 }  // namespace b200
 
 using namespace b200;
+
+extern "C" int64_t b200_igemm_split_workspace_bytes(const b200_igemm_params* p) {
+  if (!p || p->n_seg < 1 || p->n_seg > B200_IGEMM_MAX_SEG || p->out_N < 1 || p->out_D < 1 || p->out_H < 1 ||
+      p->out_W < 1 || p->out_cols < 1 || p->stride_d < 1 || p->stride_h < 1 || p->stride_w < 1)
+    return 0;
+  if ((p->impl ? p->impl : env_impl()) == 1) return 0;
+  return make_plan(p).ws_bytes;
+}
 
 extern "C" int b200_igemm(const b200_igemm_params* p, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
@@ -960,23 +1053,25 @@ extern "C" int b200_igemm(const b200_igemm_params* p, void* stream_v) {
   }
 
   // ---- tile geometry ----
-  const TileShape ts = choose_tile(d.OW, d.OH, d.OD, d.sw, d.sh, d.sd);
+  const Plan pl = make_plan(p);
+  const TileShape ts = pl.ts;
   d.BW = ts.bw; d.BH = ts.bh; d.BD = ts.bd;
   d.bw_log2 = ilog2(ts.bw); d.bh_log2 = ilog2(ts.bh);
   d.tiles_w = (d.OW + ts.bw - 1) / ts.bw;
   d.tiles_h = (d.OH + ts.bh - 1) / ts.bh;
   d.tiles_d = (d.OD + ts.bd - 1) / ts.bd;
-  const long long m_tiles = (long long)d.tiles_w * d.tiles_h * d.tiles_d * d.N;
-
-  // N tile: as wide as the output needs, but narrower when the grid would not fill the SMs
-  const int cols16 = ((p->out_cols + 15) / 16) * 16;
-  int BN = cols16 <= 16 ? 16 : cols16 <= 32 ? 32 : cols16 <= 64 ? 64 : cols16 <= 128 ? 128 : 256;
-  if (p->stat_ptr) BN = 256;      // the caller sizes the partials buffer for 256-column tiles
-  while (!p->stat_ptr && BN > 64 && m_tiles * ((cols16 + BN - 1) / BN) < sm_count() && kchunks >= 8) BN >>= 1;
-  d.tiles_n = (cols16 + BN - 1) / BN;
-  const long long ntiles = m_tiles * d.tiles_n;
-  B200_CHECK_ARG(ntiles < (1ll << 31), "igemm: too many tiles");
-  d.num_tiles = (int)ntiles;
+  const int BN = pl.BN;
+  d.tiles_n = pl.tiles_n;
+  d.k_splits = 1;
+  d.split_stride = 0;
+  const int splits = (p->split_ws && pl.splits > 1) ? pl.splits : 1;
+  if (splits > 1) {
+    B200_CHECK_ARG(p->split_ws_bytes >= pl.ws_bytes && ((uintptr_t)p->split_ws & 15) == 0,
+                   "igemm: split_ws needs %lld bytes, 16-byte aligned (got %lld)", pl.ws_bytes,
+                   (long long)p->split_ws_bytes);
+  }
+  B200_CHECK_ARG(pl.ntiles * splits < (1ll << 31), "igemm: too many tiles");
+  d.num_tiles = (int)pl.ntiles;
 
   // ---- tensor maps ----
   for (int s = 0; s < 2; ++s) {
@@ -1018,11 +1113,36 @@ extern "C" int b200_igemm(const b200_igemm_params* p, void* stream_v) {
     }
   }
 
-  switch (BN) {
-    case 16:  return launch_tc<16, 8>(d, stream);
-    case 32:  return launch_tc<32, 8>(d, stream);
-    case 64:  return launch_tc<64, 8>(d, stream);
-    case 128: return launch_tc<128, 6>(d, stream);
-    default:  return launch_tc<256, 4>(d, stream);
-  }
+  auto launch = [&](const IgemmDev& dev) {
+    switch (BN) {
+      case 16:  return launch_tc<16, 8>(dev, stream);
+      case 32:  return launch_tc<32, 8>(dev, stream);
+      case 64:  return launch_tc<64, 8>(dev, stream);
+      case 128: return launch_tc<128, 6>(dev, stream);
+      default:  return launch_tc<256, 4>(dev, stream);
+    }
+  };
+  if (splits == 1) return launch(d);
+
+  // ---- split-K: S partial GEMMs into the fp32 workspace, then the reduction applies this call's epilogue ----
+  IgemmDev ds = d;
+  ds.k_splits = splits;
+  ds.num_tiles = (int)(pl.ntiles * splits);
+  ds.out_ptr = p->split_ws; ds.out_dtype = B200_DT_F32; ds.out_cols = pl.ws_cols;
+  ds.out_sW = pl.ws_cols; ds.out_sH = ds.out_sW * d.OW; ds.out_sD = ds.out_sH * d.OH; ds.out_sN = ds.out_sD * d.OD;
+  ds.split_stride = pl.rows * pl.ws_cols;
+  ds.out_vec = 1; ds.out_v256 = 0;
+  ds.out_staged = (ds.out_sW * 4 > 2048) ? 1 : 0;
+  ds.bias = nullptr; ds.rowvec = nullptr; ds.row_bias = nullptr;
+  ds.act1 = B200_ACT_NONE; ds.act2 = B200_ACT_NONE; ds.scale = 1.0f;
+  ds.res_ptr = nullptr; ds.res_vec = 0; ds.res_v256 = 0;
+  ds.stat_ptr = nullptr; ds.gn_partial = nullptr;
+  const int rc = launch(ds);
+  if (rc != B200_OK) return rc;
+  const long long total = pl.rows * ((d.out_cols + 7) / 8);
+  B200_CHECK_ARG((total + 255) / 256 < (1ll << 31), "igemm: split reduction too large");
+  igemm_split_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+      d, static_cast<const float*>(p->split_ws), splits, pl.ws_cols, ds.split_stride);
+  B200_LAUNCH_CHECK("igemm_split_reduce_kernel");
+  return B200_OK;
 }

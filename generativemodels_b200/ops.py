@@ -7,6 +7,7 @@ Internal activation format: :class:`CL` — channels-last bf16 ``[N, D, H, W, pi
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Sequence
 
@@ -334,9 +335,27 @@ def _fill_segs(p: IgemmParams, segs) -> None:
         s.src, s.dw, s.dh, s.dd, s.c0, s.nchunks = src, dw, dh, dd, c0, nch
 
 
+_SPLIT_K = os.environ.get("B200_SPLIT_K", "1") != "0"    # dev switch (tests compare split and one-pass reductions)
+_SPLIT_LAUNCHES = 0      # calls that went through the split-K pair of kernels (tests / probes read it)
+
+
 def igemm_raw(p: IgemmParams) -> None:
+    """One b200_igemm launch.  Calls whose grid cannot fill the SMs (deep levels of a latent UNet, single-sample
+    linears) get the split-K workspace the library asks for; everything else is a single kernel."""
     lib = _lib.require_device()
-    check(lib.b200_igemm(C.byref(p), _stream()), "b200_igemm")
+    ws = None
+    if _SPLIT_K and not p.split_ws:
+        need = int(lib.b200_igemm_split_workspace_bytes(C.byref(p)))
+        if need:
+            global _SPLIT_LAUNCHES
+            _SPLIT_LAUNCHES += 1
+            ws = torch.empty(need, dtype=torch.uint8, device=torch.device("cuda", torch.cuda.current_device()))
+            p.split_ws, p.split_ws_bytes = ws.data_ptr(), need
+    try:
+        check(lib.b200_igemm(C.byref(p), _stream()), "b200_igemm")
+    finally:
+        if ws is not None:
+            p.split_ws, p.split_ws_bytes = None, 0       # the struct may be a cached template: never keep the pointer
 
 
 def _conv_params(srcs: Sequence[CL], w: torch.Tensor, segs, stride, out_t: torch.Tensor, out_dims, cout: int,

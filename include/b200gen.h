@@ -115,9 +115,20 @@ typedef struct {
    * Needs a bf16, 16-byte-aligned output with cout % 32 == 0.  NULL to skip. */
   float*  gn_partial;
   int32_t gn_slots, gn_slot0;
+  /* Optional split-K workspace.  A convolution on a small grid (the deep levels of a latent UNet: a few hundred
+   * voxels x 20 000 reduction elements) has fewer output tiles than the GPU has SMs, and each tile walks its whole
+   * reduction serially.  With a workspace of b200_igemm_split_workspace_bytes(p) bytes the reduction is cut into S
+   * ranges computed by S CTAs per tile into fp32 partials [S][rows][round_up(out_cols, 8)], and a second kernel sums
+   * them in a fixed order and applies the epilogue above (deterministic; fp32 summation order differs from the
+   * unsplit kernel).  NULL / 0 = never split. */
+  void*   split_ws;
+  int64_t split_ws_bytes;
 } b200_igemm_params;
 
 int b200_igemm(const b200_igemm_params* p, void* stream);
+/* Bytes of split_ws with which b200_igemm would split the reduction of this call; 0 when it would not (enough tiles
+ * to fill the SMs, short reduction, stat_ptr / gn_partial requested, impl = 1).  Host-only, no launch. */
+int64_t b200_igemm_split_workspace_bytes(const b200_igemm_params* p);
 
 /* ------------------------------------------------------------------------------------------------
  * GroupNorm (+SiLU) on NDHWC bf16, optionally over the virtual concat of two tensors.

@@ -247,6 +247,9 @@ class FakeLib:
     def b200_attention_flash_workspace_bytes(self, a):
         return 0
 
+    def b200_igemm_split_workspace_bytes(self, a):
+        return 0            # splitting the reduction is a scheduling decision of the CUDA library; results are the same
+
     def b200_attention_flash(self, a, stream):
         a = _obj(a)
         B, T, S, heads, dh = a.B, a.T, a.S, a.heads, a.dh

@@ -222,6 +222,69 @@ def test_conv_concat_epilogue(cuda_device, impl):
     assert_close(got32, ref32, 2e-3, "concat conv fp32 out")
 
 
+def test_split_k_conv_matches_one_pass_and_check_kernel(cuda_device, monkeypatch):
+    """Deep-level shape of a latent UNet (a few hundred voxels, K = 27 x 256): the grid has 2-6 tiles, so the
+    reduction is split across the idle SMs and a second kernel applies the epilogue.  Same result as the one-pass
+    kernel (fp32 summation order aside) and as the CUDA-core cross-check kernel, for every epilogue option."""
+    ops = _ops()
+    monkeypatch.setattr(ops, "_SPLIT_K", True)
+    torch.manual_seed(11)
+    N, Cin, Cout, sp = 2, 256, 200, (5, 7, 5)                     # cout not a multiple of the 64/128 column tile
+    x = torch.randn(N, Cin, *sp)
+    w = torch.randn(Cout, Cin, 3, 3, 3) / math.sqrt(Cin * 27)
+    b, temb, res = torch.randn(Cout), torch.randn(N, Cout), torch.randn(N, Cout, *sp)
+    ref = F.conv3d(bf(x), bf(w), b, padding=1) + temb[:, :, None, None, None]
+    ref = F.relu(bf(res) + 0.5 * F.silu(ref))
+    pc = ops.PackedConv(w.cuda(), b.cuda(), 1, 1)
+    xc, rc = ops.to_cl(x.cuda()), ops.to_cl(res.cuda())
+    kw = dict(rowvec=temb.cuda(), act1=ops.ACT_SILU, scale=0.5, residual=rc, act2=ops.ACT_RELU)
+    n0 = ops._SPLIT_LAUNCHES
+    split = ops.from_cl(ops.conv(xc, pc, **kw))
+    assert ops._SPLIT_LAUNCHES == n0 + 1, "this shape must take the split-K path"
+    monkeypatch.setattr(ops, "_SPLIT_K", False)
+    one_pass = ops.from_cl(ops.conv(xc, pc, **kw))
+    check = ops.from_cl(ops.conv(xc, pc, impl=1, **kw))
+    assert ops._SPLIT_LAUNCHES == n0 + 1
+    monkeypatch.setattr(ops, "_SPLIT_K", True)
+    assert_close(split, ref, 1e-2, "split-K conv vs torch")
+    assert rel_err(split, one_pass)[0] < 2e-3 and rel_err(split, check)[0] < 2e-3, (rel_err(split, one_pass),
+                                                                                    rel_err(split, check))
+    # strided conv, fp32 output, no epilogue; and determinism of the fixed-order reduction
+    pc2 = ops.PackedConv(w.cuda(), None, 2, 1)
+    o1 = ops.conv(xc, pc2, out_f32=True)
+    o2 = ops.conv(xc, pc2, out_f32=True)
+    assert ops._SPLIT_LAUNCHES == n0 + 3 and torch.equal(o1, o2)
+    assert_close(ops.from_cl_f32(o1, Cout, 3), F.conv3d(bf(x), bf(w), None, stride=2, padding=1), 2e-3, "split fp32")
+
+
+def test_split_k_linear_shapes(cuda_device, monkeypatch):
+    """GEMM-shaped calls on few rows (transformer blocks of the deepest UNet level): K = 3072 feed-forward with a
+    residual, and the operand-swapped V^T projection whose bias runs along the rows."""
+    ops = _ops()
+    monkeypatch.setattr(ops, "_SPLIT_K", True)
+    torch.manual_seed(12)
+    M, K, O = 175, 3072, 768
+    x, w, b, r = torch.randn(1, M, K), torch.randn(O, K) / math.sqrt(K), torch.randn(O), torch.randn(1, M, O)
+    pl = ops.PackedLinear(w.cuda(), b.cuda())
+    xc = ops.as_rows(bf(x).cuda().to(torch.bfloat16), K)
+    rc = ops.as_rows(bf(r).cuda().to(torch.bfloat16), O)
+    n0 = ops._SPLIT_LAUNCHES
+    got = ops.linear(xc, pl, residual=rc)
+    assert ops._SPLIT_LAUNCHES == n0 + 1
+    ref = F.linear(bf(x), bf(w), b) + bf(r)
+    assert_close(got.t.float().cpu().reshape(1, M, -1)[..., :O], ref, 1e-2, "split-K linear + residual")
+    xr = bf(torch.randn(2, 200, 1024)).cuda().to(torch.bfloat16)
+    w2, b2 = torch.randn(512, 1024) / math.sqrt(1024), torch.randn(512)
+    pl2 = ops.PackedLinear(w2.cuda(), b2.cuda())
+    vt = ops.linear_transposed(xr, 1024, pl2)                         # [B, O, S_pad]
+    assert ops._SPLIT_LAUNCHES == n0 + 3                              # one launch per batch entry
+    monkeypatch.setattr(ops, "_SPLIT_K", False)
+    vt1 = ops.linear_transposed(xr, 1024, pl2)
+    ref_vt = (F.linear(xr.float().cpu(), bf(w2), b2)).transpose(1, 2)
+    assert_close(vt[..., :200].float().cpu(), ref_vt, 1e-2, "V^T projection")
+    assert rel_err(vt.float(), vt1.float())[0] < 2e-3
+
+
 @pytest.mark.parametrize("sd,sp", [(2, (8, 12)), (3, (4, 6, 8))])
 def test_conv_transpose(cuda_device, sd, sp):
     """VQVAE decoder upsampling: ConvTranspose k4 s2 p1 (+ReLU) as per-phase implicit GEMMs (vqvae.py:220-260)."""
