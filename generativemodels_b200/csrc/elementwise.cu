@@ -274,7 +274,10 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, int N, in
   emb[idx] = v;
 }
 
-// one warp per output feature; loops over the (few) rows
+// one warp per output feature; loops over the (few) rows.  VEC: K % 128 == 0 and 16-byte aligned rows — every lane
+// issues all its float4 weight loads before the first FMA (a time-embedding projection is one 4 KB row per warp: the
+// scalar form spent ~15 us per call waiting on 32 dependent-latency loads).
+template <bool VEC>
 __global__ void small_linear_kernel(const float* __restrict__ x, int M, int K, const float* __restrict__ W,
                                     const float* __restrict__ b, int O, int act_in, int act_out,
                                     float* __restrict__ y) {
@@ -285,7 +288,30 @@ __global__ void small_linear_kernel(const float* __restrict__ x, int M, int K, c
   for (int m = 0; m < M; ++m) {
     const float* xr = x + (long long)m * K;
     float acc = 0.f;
-    for (int k = lane; k < K; k += 32) acc = fmaf(apply_act(xr[k], act_in), __ldg(w + k), acc);
+    if constexpr (VEC) {
+      for (int k0 = 0; k0 < K; k0 += 1024) {
+        float4 wv[8], xv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int k = k0 + i * 128 + lane * 4;
+          if (k < K) {
+            wv[i] = __ldg(reinterpret_cast<const float4*>(w + k));
+            xv[i] = *reinterpret_cast<const float4*>(xr + k);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (k0 + i * 128 + lane * 4 < K) {
+            acc = fmaf(apply_act(xv[i].x, act_in), wv[i].x, acc);
+            acc = fmaf(apply_act(xv[i].y, act_in), wv[i].y, acc);
+            acc = fmaf(apply_act(xv[i].z, act_in), wv[i].z, acc);
+            acc = fmaf(apply_act(xv[i].w, act_in), wv[i].w, acc);
+          }
+        }
+      }
+    } else {
+      for (int k = lane; k < K; k += 32) acc = fmaf(apply_act(xr[k], act_in), __ldg(w + k), acc);
+    }
     acc = warp_sum(acc);
     if (lane == 0) y[(long long)m * O + o] = apply_act(acc + (b ? b[o] : 0.f), act_out);
   }
@@ -770,7 +796,9 @@ extern "C" int b200_small_linear(const float* x, int32_t M, int32_t K, const flo
                                  int32_t act_in, int32_t act_out, float* y, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   B200_CHECK_ARG(x && W && y && M >= 1 && M <= 4096 && K >= 1 && O >= 1, "small_linear: bad arguments");
-  small_linear_kernel<<<(O + 7) / 8, 256, 0, stream>>>(x, M, K, W, b, O, act_in, act_out, y);
+  const bool vec = (K % 128 == 0) && (((uintptr_t)x | (uintptr_t)W) & 15) == 0;
+  if (vec) small_linear_kernel<true><<<(O + 7) / 8, 256, 0, stream>>>(x, M, K, W, b, O, act_in, act_out, y);
+  else small_linear_kernel<false><<<(O + 7) / 8, 256, 0, stream>>>(x, M, K, W, b, O, act_in, act_out, y);
   B200_LAUNCH_CHECK("small_linear_kernel");
   return B200_OK;
 }

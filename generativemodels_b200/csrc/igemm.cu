@@ -876,7 +876,7 @@ struct Plan {
   int splits, ws_cols;
   long long ws_bytes;
 };
-static Plan make_plan(const b200_igemm_params* p) {
+static Plan make_plan(const b200_igemm_params* p, bool allow_split) {
   Plan pl;
   pl.kchunks = 0;
   for (int s = 0; s < p->n_seg; ++s) pl.kchunks += p->seg[s].nchunks;
@@ -885,27 +885,34 @@ static Plan make_plan(const b200_igemm_params* p) {
                   td = (p->out_D + pl.ts.bd - 1) / pl.ts.bd;
   pl.m_tiles = tw * th * td * p->out_N;
   pl.rows = (long long)p->out_N * p->out_D * p->out_H * p->out_W;
-  // N tile: as wide as the output needs, but narrower when the grid would not fill the SMs
-  const int cols16 = ((p->out_cols + 15) / 16) * 16;
-  int BN = cols16 <= 16 ? 16 : cols16 <= 32 ? 32 : cols16 <= 64 ? 64 : cols16 <= 128 ? 128 : 256;
-  if (p->stat_ptr) BN = 256;      // the caller sizes the partials buffer for 256-column tiles
-  while (!p->stat_ptr && BN > 64 && pl.m_tiles * ((cols16 + BN - 1) / BN) < sm_count() && pl.kchunks >= 8) BN >>= 1;
-  pl.BN = BN;
-  pl.tiles_n = (cols16 + BN - 1) / BN;
-  pl.ntiles = pl.m_tiles * pl.tiles_n;
-  // Split the reduction when at least three ranges of four or more 64-element chunks fit the idle SMs.
   pl.splits = 1;
   pl.ws_cols = ((p->out_cols + 7) / 8) * 8;
   pl.ws_bytes = 0;
-  if (!p->stat_ptr && !p->gn_partial && p->impl != 1 && pl.kchunks >= 16 && pl.ntiles * 3 <= sm_count()) {
-    long long s = sm_count() / pl.ntiles;
+  // N tile: as wide as the output needs
+  const int cols16 = ((p->out_cols + 15) / 16) * 16;
+  int BN = cols16 <= 16 ? 16 : cols16 <= 32 ? 32 : cols16 <= 64 ? 64 : cols16 <= 128 ? 128 : 256;
+  if (p->stat_ptr) BN = 256;      // the caller sizes the partials buffer for 256-column tiles
+  // A grid that cannot fill the SMs: keep the wide tile (operand traffic from L2 per FLOP falls with the tile width —
+  // measured: 64-wide tiles of a 1400-row x 13824-deep convolution stream 456 MB at the L2's ~6.4 TB/s) and cut the
+  // reduction into ranges instead, when the caller brought a workspace and the reduction is long enough for at least
+  // two ranges of four 64-element chunks.
+  const long long wide_tiles = pl.m_tiles * ((cols16 + BN - 1) / BN);
+  if (allow_split && !p->stat_ptr && !p->gn_partial && p->impl != 1 && pl.kchunks >= 16 &&
+      wide_tiles * 2 <= sm_count()) {
+    long long s = sm_count() / wide_tiles;
     if (s > pl.kchunks / 4) s = pl.kchunks / 4;
     if (s > 32) s = 32;
-    if (s >= 3) {
+    if (s >= 2) {
       pl.splits = (int)s;
       pl.ws_bytes = s * pl.rows * pl.ws_cols * 4;
     }
   }
+  // otherwise narrower tiles, down to 64 columns, to put more CTAs on the problem
+  if (pl.splits == 1)
+    while (!p->stat_ptr && BN > 64 && pl.m_tiles * ((cols16 + BN - 1) / BN) < sm_count() && pl.kchunks >= 8) BN >>= 1;
+  pl.BN = BN;
+  pl.tiles_n = (cols16 + BN - 1) / BN;
+  pl.ntiles = pl.m_tiles * pl.tiles_n;
   return pl;
 }
 
@@ -943,7 +950,7 @@ extern "C" int64_t b200_igemm_split_workspace_bytes(const b200_igemm_params* p) 
       p->out_W < 1 || p->out_cols < 1 || p->stride_d < 1 || p->stride_h < 1 || p->stride_w < 1)
     return 0;
   if ((p->impl ? p->impl : env_impl()) == 1) return 0;
-  return make_plan(p).ws_bytes;
+  return make_plan(p, true).ws_bytes;
 }
 
 extern "C" int b200_igemm(const b200_igemm_params* p, void* stream_v) {
@@ -1053,7 +1060,7 @@ extern "C" int b200_igemm(const b200_igemm_params* p, void* stream_v) {
   }
 
   // ---- tile geometry ----
-  const Plan pl = make_plan(p);
+  const Plan pl = make_plan(p, p->split_ws != nullptr);
   const TileShape ts = pl.ts;
   d.BW = ts.bw; d.BH = ts.bh; d.BD = ts.bd;
   d.bw_log2 = ilog2(ts.bw); d.bh_log2 = ilog2(ts.bh);

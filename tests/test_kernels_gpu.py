@@ -590,6 +590,12 @@ def test_timestep_embedding_and_small_linear(cuda_device):
     ref = F.silu(F.linear(F.silu(x), w, b))
     got = ops.small_linear(x.cuda(), w.cuda(), b.cuda(), ops.ACT_SILU, ops.ACT_SILU).cpu()
     assert (got - ref).abs().max().item() < 1e-4
+    for K in (1024, 384, 2176):                    # K % 128 == 0: the float4 path (one / partial / three 1024-blocks)
+        x = torch.randn(2, K)
+        w, b = torch.randn(300, K) / math.sqrt(K), torch.randn(300)
+        ref = F.linear(F.silu(x), w, b)
+        got = ops.small_linear(x.cuda(), w.cuda(), b.cuda(), ops.ACT_SILU, ops.ACT_NONE).cpu()
+        assert (got - ref).abs().max().item() < 1e-4, K
 
 
 # ------------------------------------------------------------------------------------------------ perf smoke (prints)
