@@ -1,0 +1,38 @@
+"""Dev probe for ncu: warm the network, then ONE eager forward between cudaProfilerStart/Stop.
+
+    ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
+        --log-file gpurun_out/launches_brain.csv python tools/one_forward.py brain
+"""
+import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import torch
+
+from generativemodels_b200.networks.nets import DiffusionModelUNet
+
+which = sys.argv[1] if len(sys.argv) > 1 else "brain"
+torch.manual_seed(0)
+if which == "brain":
+    net = DiffusionModelUNet(spatial_dims=3, in_channels=7, out_channels=3, num_channels=(256, 512, 768),
+                             num_res_blocks=2, attention_levels=(False, True, True), norm_num_groups=32, norm_eps=1e-6,
+                             resblock_updown=True, num_head_channels=(0, 512, 768), with_conditioning=True,
+                             transformer_num_layers=1, cross_attention_dim=4).cuda().eval()
+    x, ctx = torch.randn(1, 7, 20, 28, 20).cuda(), torch.randn(1, 1, 4).cuda()
+else:
+    net = DiffusionModelUNet(2, 3, 3, num_res_blocks=2, num_channels=(128, 256, 512),
+                             attention_levels=(False, True, True), num_head_channels=(0, 256, 512)).cuda().eval()
+    x, ctx = torch.randn(1, 3, 64, 64).cuda(), None
+with torch.no_grad():
+    for p in net.parameters():
+        if float(p.abs().max()) == 0:
+            p.normal_(0, 0.02)
+t = torch.tensor([500]).cuda()
+for _ in range(3):
+    net(x, timesteps=t, context=ctx)
+torch.cuda.synchronize()
+torch.cuda.profiler.start()
+net(x, timesteps=t, context=ctx)
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
+print("done")
