@@ -10,7 +10,8 @@ import torch.nn as nn
 from ... import ops
 from ...ops import ACT_SILU, CL
 from .._holders import Convolution, require_cuda
-from .diffusion_model_unet import (_context_cl, ensure_tuple_rep, get_down_block, get_mid_block, time_embedding,
+from .diffusion_model_unet import (_context_cl, ensure_tuple_rep, get_down_block, get_mid_block, project_time_embedding,
+                                   time_embedding,
                                    zero_module)
 
 __all__ = ["ControlNet"]
@@ -137,7 +138,7 @@ class ControlNet(nn.Module):
         """-> (down residuals, mid residual) as NC[D]HW tensors (controlnet.py:367-436); with ``_internal`` the
         inferers get the channels-last handles and skip two layout passes per residual."""
         require_cuda(x, self)
-        emb = time_embedding(self, x, timesteps, class_labels)
+        emb = project_time_embedding(self, time_embedding(self, x, timesteps, class_labels))
         if context is not None and self.with_conditioning is False:
             raise ValueError("model should have with_conditioning = True if context is provided")
         ctx = _context_cl(context) if context is not None else None

@@ -224,6 +224,44 @@ class Upsample(nn.Module):
         return ops.upsample_nearest2x(x)
 
 
+class TimeEmb:
+    """The time embedding of one forward together with every ResnetBlock's ``time_emb_proj(silu(emb))`` row
+    (diffusion_model_unet.py:686-689), which depend on the timestep only: all of them come out of ONE GEMV launch over
+    the row-concatenated projection weights instead of one launch per block (a latent UNet step is ~300-500 dependent
+    launches of a few microseconds each — see DESIGN.md, latency-bound configurations).  ``proj[id(block)]`` is a
+    column slice ``[rows, out_channels]`` of that result; the conv epilogue reads it through its row stride."""
+
+    __slots__ = ("emb", "proj")
+
+    def __init__(self, emb: torch.Tensor, proj: dict) -> None:
+        self.emb, self.proj = emb, proj
+
+
+def project_time_embedding(root: nn.Module, emb: torch.Tensor) -> TimeEmb:
+    """Batch the time-embedding projections of all ResnetBlocks under ``root``.  The concatenated fp32 weights are
+    cached on ``root`` against the (data_ptr, version) of every projection parameter."""
+    blocks = root.__dict__.get("_temb_blocks")
+    if blocks is None:
+        blocks = root.__dict__["_temb_blocks"] = [m for m in root.modules() if isinstance(m, ResnetBlock)]
+    if len(blocks) < 2:
+        return TimeEmb(emb, {})
+    params = []
+    for b in blocks:
+        params += [b.time_emb_proj.weight, b.time_emb_proj.bias]
+    key = tuple((p.data_ptr(), p._version) for p in params)
+    cache = root.__dict__.get("_temb_cat")
+    if cache is None or cache[0] != key:
+        w = torch.cat([b.time_emb_proj.weight.detach().float() for b in blocks], 0).contiguous()
+        bias = torch.cat([b.time_emb_proj.bias.detach().float() for b in blocks], 0).contiguous()
+        cache = root.__dict__["_temb_cat"] = (key, w, bias)
+    rows = ops.small_linear(emb, cache[1], cache[2], act_in=ACT_SILU)
+    proj, off = {}, 0
+    for b in blocks:
+        proj[id(b)] = rows[:, off:off + b.out_channels]
+        off += b.out_channels
+    return TimeEmb(emb, proj)
+
+
 class ResnetBlock(nn.Module):
     """diffusion_model_unet.py:589-696; with ``label_nc`` the two norms are SPADE blocks and this is
     SPADEResnetBlock (spade_diffusion_model_unet.py:72-200; same keys, ``forward(x, emb, seg)``)."""
@@ -280,7 +318,10 @@ class ResnetBlock(nn.Module):
             resample = ops.upsample_nearest2x if self.up else ops.avgpool2
             srcs = [resample(srcs[0])]
             h = resample(h)
-        temb = ops.small_linear(emb, self.time_emb_proj.weight, self.time_emb_proj.bias, act_in=ACT_SILU)
+        temb = emb.proj.get(id(self)) if isinstance(emb, TimeEmb) else None
+        if temb is None:
+            e = emb.emb if isinstance(emb, TimeEmb) else emb
+            temb = ops.small_linear(e, self.time_emb_proj.weight, self.time_emb_proj.bias, act_in=ACT_SILU)
         h = self.conv1(h, rowvec=temb)
         h = self._norm(self.norm2, [h], seg)
         if isinstance(self.skip_connection, nn.Identity):
@@ -691,7 +732,7 @@ class DiffusionModelUNet(nn.Module):
     def _forward(self, x, timesteps, context, class_labels, down_block_additional_residuals,
                  mid_block_additional_residual, seg):
         require_cuda(x, self)
-        emb = time_embedding(self, x, timesteps, class_labels)
+        emb = project_time_embedding(self, time_embedding(self, x, timesteps, class_labels))
         if context is not None and self.with_conditioning is False:
             raise ValueError("model should have with_conditioning = True if context is provided")
         ctx = _context_cl(context) if context is not None else None

@@ -58,6 +58,37 @@ def test_unet_vs_oracle_cpu(name):
     assert rel(got, want) < 2e-2, rel(got, want)
 
 
+def test_time_embedding_projections_are_one_launch_cpu(monkeypatch):
+    """All ResnetBlocks' time_emb_proj(silu(emb)) come out of one GEMV over the concatenated weights and reach the
+    conv epilogues as strided column slices: same result as one launch per block, and the cache follows the weights."""
+    from generativemodels_b200 import _lib
+    import generativemodels_b200.networks.nets.diffusion_model_unet as U
+    kw = G.UNET_CASES["unet2d_updown_class"]
+    torch.manual_seed(0)
+    m = G.randomize_zero_params(nets().DiffusionModelUNet(**kw)).eval()
+    x, t, cls = torch.randn(2, 2, 16, 16), torch.tensor([10, 700]), torch.tensor([1, 4])
+    lib = _lib.require_device()
+    calls = []
+    orig = lib.b200_small_linear
+    monkeypatch.setattr(lib, "b200_small_linear", lambda *a: (calls.append(a[5]), orig(*a))[1])
+    batched = m(x, t, class_labels=cls)
+    n_res = sum(isinstance(b, U.ResnetBlock) for b in m.modules())
+    assert n_res >= 5 and len(calls) == 3 and calls[-1] == sum(
+        b.out_channels for b in m.modules() if isinstance(b, U.ResnetBlock))
+    calls.clear()
+    real = U.project_time_embedding
+    monkeypatch.setattr(U, "project_time_embedding", lambda root, emb: U.TimeEmb(emb, {}))
+    per_block = m(x, t, class_labels=cls)
+    assert len(calls) == 2 + n_res
+    assert rel(batched, per_block) < 1e-6
+    monkeypatch.setattr(U, "project_time_embedding", real)
+    with torch.no_grad():                                   # in-place weight update: the concatenation is rebuilt
+        blk = next(b for b in m.modules() if isinstance(b, U.ResnetBlock))
+        blk.time_emb_proj.bias.add_(1.0)
+    want = O.unet_forward(m.state_dict(), G.unet_oracle_cfg(kw), x, t, class_labels=cls)
+    assert rel(m(x, t, class_labels=cls), want) < 2e-2
+
+
 def test_samplers_golden_cpu():
     from generativemodels_b200.inferers import DiffusionInferer
     from generativemodels_b200.networks.schedulers import DDIMScheduler, DDPMScheduler, PNDMScheduler
