@@ -83,7 +83,8 @@ def save_packed(model: nn.Module, path: str) -> int:
 
 def load_packed(model: nn.Module, path: str) -> bool:
     """Install the packed weights of ``path`` into ``model``.  False (and nothing installed) if the file was written
-    for different weights or by another format version."""
+    for different weights or by another format version.  The file is a pickle of this package's packed-weight objects
+    (``torch.load(weights_only=False)``): load only files you wrote yourself, like any ``torch.load`` checkpoint."""
     blob = torch.load(path, map_location="cpu", weights_only=False)
     if blob.get("format") != _FORMAT or blob.get("fingerprint") != fingerprint(model):
         return False
