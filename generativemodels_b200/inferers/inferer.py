@@ -8,15 +8,16 @@ layout round trip.  ``get_likelihood`` runs the same net
 """
 from __future__ import annotations
 
+import os
 from abc import ABC, abstractmethod
 from collections.abc import Callable
+from functools import partial
 
 import torch
 import torch.nn as nn
 
-from functools import partial
-
 from .. import ops
+from ..cuda_graph import GraphedModule, graphed
 from ..networks.nets import VQVAE, ControlNet, SPADEAutoencoderKL, SPADEDiffusionModelUNet
 
 try:  # tqdm is optional, like in the reference
@@ -42,6 +43,30 @@ def _check_mode(mode: str) -> None:
 def _with_seg(diffusion_model, seg):
     """SPADE networks take the segmentation map as an extra argument (inferer.py:121-125, 210-214, 445-446)."""
     return partial(diffusion_model, seg=seg) if isinstance(diffusion_model, SPADEDiffusionModelUNet) else diffusion_model
+
+
+# Replay the network from a CUDA graph inside ``sample`` when one step is launch-latency-bound (a latent UNet step is
+# 300-500 dependent launches of a few microseconds: C2 at batch 1 goes from 3.4 to 8.4 samples/s).  Off by default
+# this round — the wrapper (generativemodels_b200.cuda_graph.graphed) is verified on the GPU when passed explicitly
+# (tests/test_parity_gpu.py::test_cuda_graph_replay_matches_eager, tools/run_configs.py, the bundle Sampler); doing it
+# implicitly for every caller has not had its own GPU run yet.  ``B200_AUTO_GRAPH=1`` or setting this flag turns it on.
+AUTO_CUDA_GRAPH = os.environ.get("B200_AUTO_GRAPH", "0") == "1"
+_AUTO_GRAPH_MAX_NUMEL = 1 << 18          # per-sample elements of the network input (64^3, 512^2): above, work dominates
+_AUTO_GRAPH_MIN_STEPS = 8                # capture costs ~3 forwards
+
+
+def _maybe_graphed(diffusion_model, input_noise: torch.Tensor, scheduler, seg):
+    """The network itself, or its CUDA-graph wrapper (cached on the module) when AUTO_CUDA_GRAPH applies."""
+    if not AUTO_CUDA_GRAPH or seg is not None or not isinstance(diffusion_model, nn.Module) or \
+            isinstance(diffusion_model, GraphedModule) or not input_noise.is_cuda:
+        return diffusion_model
+    if input_noise[0].numel() > _AUTO_GRAPH_MAX_NUMEL or len(scheduler.timesteps) < _AUTO_GRAPH_MIN_STEPS:
+        return diffusion_model
+    wrapper = diffusion_model.__dict__.get("_b200_auto_graph")
+    if wrapper is None:
+        wrapper = graphed(diffusion_model)
+        diffusion_model.__dict__["_b200_auto_graph"] = wrapper      # not a registered submodule: no state_dict change
+    return wrapper
 
 
 def _progress(scheduler, verbose: bool):
@@ -95,7 +120,7 @@ class DiffusionInferer(Inferer):
         _check_mode(mode)
         if not scheduler:
             scheduler = self.scheduler
-        diffusion_model = _with_seg(diffusion_model, seg)
+        diffusion_model = _with_seg(_maybe_graphed(diffusion_model, input_noise, scheduler, seg), seg)
         image = input_noise
         intermediates = []
         for t in _progress(scheduler, verbose):

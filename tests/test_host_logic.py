@@ -246,3 +246,38 @@ def test_attention_tc_host_logic(monkeypatch):
     qh, kh, vh = (bf(t).view(B, T, heads, dh).transpose(1, 2) for t in (q, k, v))
     ref = (torch.softmax(qh @ kh.transpose(-1, -2) / math.sqrt(dh), -1) @ vh).transpose(1, 2).reshape(B, T, Cc)
     close(out[..., :Cc].float(), ref, 2e-2)
+
+
+def test_auto_cuda_graph_policy(monkeypatch):
+    """inferers.AUTO_CUDA_GRAPH (off by default): which sample() calls would replay the network from a CUDA graph."""
+    import torch.nn as nn
+
+    import generativemodels_b200.inferers.inferer as I
+
+    class FakeNoise:
+        def __init__(self, per_sample, cuda=True):
+            self.is_cuda, self._n = cuda, per_sample
+
+        def __getitem__(self, i):
+            return torch.empty(self._n, device="meta")
+
+    class Sched:
+        def __init__(self, n):
+            self.timesteps = list(range(n))
+
+    made = []
+    monkeypatch.setattr(I, "graphed", lambda m: (made.append(m), ("graph-of", m))[1])
+    net = nn.Linear(2, 2)
+    assert I.AUTO_CUDA_GRAPH is False and I._maybe_graphed(net, FakeNoise(100), Sched(50), None) is net
+    monkeypatch.setattr(I, "AUTO_CUDA_GRAPH", True)
+    w = I._maybe_graphed(net, FakeNoise(3 * 64 * 64), Sched(50), None)
+    assert w == ("graph-of", net) and I._maybe_graphed(net, FakeNoise(3 * 64 * 64), Sched(50), None) is w
+    assert len(made) == 1 and "_b200_auto_graph" not in dict(net.named_modules()) and not net.state_dict().keys() - {
+        "weight", "bias"}
+    other = nn.Linear(2, 2)
+    assert I._maybe_graphed(other, FakeNoise(160 * 224 * 160), Sched(50), None) is other      # work-bound volume
+    assert I._maybe_graphed(other, FakeNoise(4096), Sched(4), None) is other                 # too few steps to amortise
+    assert I._maybe_graphed(other, FakeNoise(4096, cuda=False), Sched(50), None) is other
+    assert I._maybe_graphed(other, FakeNoise(4096), Sched(50), object()) is other             # SPADE: seg is bound late
+    fn = lambda *a, **k: None                                                                 # noqa: E731
+    assert I._maybe_graphed(fn, FakeNoise(4096), Sched(50), None) is fn and len(made) == 1
