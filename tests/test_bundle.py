@@ -189,6 +189,21 @@ def test_reference_inference_json_parses_when_present():
     assert isinstance(cfg.get("diffusion"), DiffusionModelUNet) and cfg.get("diffusion").in_channels == 7
 
 
+def test_bundle_cli_cpu(tmp_path, capsys):
+    """``python -m generativemodels_b200.bundle run <ids> --config_file f --key value`` (monai.bundle's call shape)."""
+    from generativemodels_b200.bundle.__main__ import main
+    cfg = tmp_path / "c.json"
+    cfg.write_text(json.dumps({"imports": ["$from pathlib import Path"], "root": ".", "age": 0.1, "name": "a",
+                               "touch": "$Path(@root, @name + str(@age)).write_text('x')"}))
+    assert main(["run", "touch", "--config_file", str(cfg), "--root", str(tmp_path), "--age", "0.7"]) == 0
+    assert (tmp_path / "a0.7").read_text() == "x"
+    assert main(["run", "touch", "--config_file", str(cfg), "--root", str(tmp_path), "--name", "b"]) == 0
+    assert (tmp_path / "b0.1").exists()
+    assert main([]) == 2 and main(["run", "--config_file", str(cfg)]) == 2 and main(["run", "touch"]) == 2
+    assert main(["run", "touch", "--config_file"]) == 2
+    capsys.readouterr()
+
+
 def test_packed_cache_roundtrip_cpu(monkeypatch, tmp_path):
     cpu_backend.install(monkeypatch)
     from generativemodels_b200 import ops
