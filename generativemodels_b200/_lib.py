@@ -110,6 +110,7 @@ SIGNATURES = {
     "b200_spade_apply": [C.POINTER(GnApplyParams), _P, _I32, _P, _P],
     "b200_resize_nearest": [_P, _I32, _I32, _I32, _I32, _I32, _P, _I32, _I32, _I32, _P],
     "b200_groupnorm_apply": [C.POINTER(GnApplyParams), _P],
+    "b200_groupnorm_fused": [C.POINTER(GnStatsParams), C.POINTER(GnApplyParams), _P],
     "b200_layernorm": [_P, _I64, _I32, _I32, _P, _P, _F, _P, _I32, _P],
     "b200_nchw_to_nhwc": [_P, _I32, _I32, _I64, _P, _I32, _P],
     "b200_nhwc_to_nchw": [_P, _I32, _I32, _I32, _I64, _I32, _P, _P],

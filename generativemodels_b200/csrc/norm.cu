@@ -257,6 +257,135 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, const __nv
   }
 }
 
+// ---- single-launch GroupNorm for small tensors ---------------------------------------------------------
+// The deep levels of a latent UNet normalise tensors of 10^4..10^6 elements ~50 times per step; the three-kernel form
+// above (partials, finalize, apply) then costs three launch latencies for microseconds of work.  Here one CTA per
+// (sample, group) owns the group's slab [spatial][cpg]: pass 1 sums it, a block reduction in fp64 gives mean / rstd,
+// pass 2 re-reads it (L1 / L2 hits), normalises, applies the activation and stores.  Thread t keeps one channel
+// vector (VEC channels, fixed) and strides over rows, so its affine pairs live in registers.
+template <int VEC>
+__device__ __forceinline__ void gn_load_vec(const __nv_bfloat16* p, float* f) {
+  if constexpr (VEC == 8) {
+    unpack8(__ldg(reinterpret_cast<const uint4*>(p)), f);
+  } else if constexpr (VEC == 4) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+    const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&v.x);
+    const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&v.y);
+    f[0] = __low2float(lo); f[1] = __high2float(lo); f[2] = __low2float(hi); f[3] = __high2float(hi);
+  } else if constexpr (VEC == 2) {
+    const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(p));
+    const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&v);
+    f[0] = __low2float(h); f[1] = __high2float(h);
+  } else {
+    f[0] = __bfloat162float(p[0]);
+  }
+}
+template <int VEC>
+__device__ __forceinline__ void gn_store_vec(__nv_bfloat16* p, const float* f) {
+  if constexpr (VEC == 8) {
+    *reinterpret_cast<uint4*>(p) = pack8(f);
+  } else if constexpr (VEC == 4) {
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(f[0], f[1]), hi = __floats2bfloat162_rn(f[2], f[3]);
+    uint2 v;
+    v.x = *reinterpret_cast<const uint32_t*>(&lo);
+    v.y = *reinterpret_cast<const uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(p) = v;
+  } else if constexpr (VEC == 2) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(f[0], f[1]);
+    *reinterpret_cast<uint32_t*>(p) = *reinterpret_cast<const uint32_t*>(&h);
+  } else {
+    p[0] = __float2bfloat16_rn(f[0]);
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(512) gn_fused_small_kernel(const __nv_bfloat16* __restrict__ x0,
+                                                             const __nv_bfloat16* __restrict__ x1, int C0, int C1,
+                                                             int pitch0, int pitch1, int spatial, int groups, float eps,
+                                                             const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, int act,
+                                                             __nv_bfloat16* __restrict__ y, int y_pitch) {
+  const int g = blockIdx.x, n = blockIdx.y;
+  const int C = C0 + C1, cpg = C / groups;
+  const int c_first = g * cpg;                       // the host guarantees a group never straddles the two sources
+  const __nv_bfloat16* src;
+  int pitch;
+  if (c_first < C0) { src = x0 + (long long)n * spatial * pitch0 + c_first; pitch = pitch0; }
+  else              { src = x1 + (long long)n * spatial * pitch1 + (c_first - C0); pitch = pitch1; }
+  __nv_bfloat16* dst = y + (long long)n * spatial * y_pitch + c_first;
+  const int vpr = cpg / VEC;                         // channel vectors per row (<= blockDim.x)
+  const int rows_per_iter = blockDim.x / vpr;
+  const int v = threadIdx.x % vpr, row0 = threadIdx.x / vpr;
+  const bool active = row0 < rows_per_iter;
+  const int c_off = v * VEC;
+
+  float s = 0.f, q = 0.f;
+  if (active) {
+#pragma unroll 4
+    for (int r = row0; r < spatial; r += rows_per_iter) {
+      float f[VEC];
+      gn_load_vec<VEC>(src + (long long)r * pitch + c_off, f);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) { s += f[j]; q = fmaf(f[j], f[j], q); }
+    }
+  }
+  double ds = (double)s, dq = (double)q;
+  for (int o = 16; o > 0; o >>= 1) {
+    ds += __shfl_xor_sync(0xffffffffu, ds, o);
+    dq += __shfl_xor_sync(0xffffffffu, dq, o);
+  }
+  __shared__ double red_s[16], red_q[16];
+  __shared__ float stat[2];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { red_s[w] = ds; red_q[w] = dq; }
+  __syncthreads();
+  if (w == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    ds = l < nw ? red_s[l] : 0.0;
+    dq = l < nw ? red_q[l] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) {
+      ds += __shfl_xor_sync(0xffffffffu, ds, o);
+      dq += __shfl_xor_sync(0xffffffffu, dq, o);
+    }
+    if (l == 0) {
+      const double cnt = (double)spatial * cpg;
+      const double mean = ds / cnt;
+      double var = dq / cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      stat[0] = (float)mean;
+      stat[1] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+  }
+  __syncthreads();
+  if (active) {
+    const float mean = stat[0], rstd = stat[1];
+    float a[VEC], b[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      a[j] = rstd * gamma[c_first + c_off + j];
+      b[j] = beta[c_first + c_off + j] - mean * a[j];
+    }
+#pragma unroll 4
+    for (int r = row0; r < spatial; r += rows_per_iter) {
+      float f[VEC];
+      gn_load_vec<VEC>(src + (long long)r * pitch + c_off, f);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        const float t = fmaf(f[j], a[j], b[j]);
+        f[j] = (act == B200_ACT_SILU) ? silu_fast(t) : t;
+      }
+      gn_store_vec<VEC>(dst + (long long)r * y_pitch + c_off, f);
+    }
+  }
+  // pad channels [C, y_pitch) stay exact zeros for the consumers' vector loads: the last group's CTA writes them
+  if (y_pitch > C && g == groups - 1) {
+    const int padw = y_pitch - C;
+    __nv_bfloat16* pad = y + (long long)n * spatial * y_pitch + C;
+    for (int i = threadIdx.x; i < spatial * padw; i += blockDim.x)
+      pad[(long long)(i / padw) * y_pitch + (i % padw)] = __float2bfloat16_rn(0.f);
+  }
+}
+
 // zero the pad channels [C, pitch) of a channels-last tensor (only when pitch > C)
 __global__ void zero_pad_channels_kernel(__nv_bfloat16* y, long long rows, int C, int pitch) {
   const int padw = pitch - C;
@@ -463,6 +592,46 @@ extern "C" int b200_groupnorm_apply(const b200_gn_apply_params* p, void* stream_
     zero_pad_channels_kernel<<<(unsigned)zb, 256, 0, stream>>>(y, rows, C, p->y_pitch);
     B200_LAUNCH_CHECK("zero_pad_channels_kernel");
   }
+  return B200_OK;
+}
+
+extern "C" int b200_groupnorm_fused(const b200_gn_stats_params* sp, const b200_gn_apply_params* ap, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(sp && ap && sp->x_ptr[0] && sp->gamma && sp->beta && ap->y_ptr, "groupnorm_fused: null pointer");
+  const int C0 = sp->x_C[0], C1 = sp->x_ptr[1] ? sp->x_C[1] : 0;
+  const int C = C0 + C1;
+  B200_CHECK_ARG(sp->groups >= 1 && C % sp->groups == 0, "groupnorm_fused: %d channels not divisible by %d groups", C,
+                 sp->groups);
+  B200_CHECK_ARG(sp->N >= 1 && sp->N <= 65535 && sp->spatial >= 1 && sp->spatial < (1ll << 24),
+                 "groupnorm_fused: batch / spatial extent out of range");
+  B200_CHECK_ARG(ap->y_pitch >= C, "groupnorm_fused: y_pitch %d < C %d", ap->y_pitch, C);
+  B200_CHECK_ARG(ap->act == B200_ACT_NONE || ap->act == B200_ACT_SILU, "groupnorm_fused: unsupported activation %d", ap->act);
+  const int cpg = C / sp->groups;
+  B200_CHECK_ARG(C1 == 0 || C0 % cpg == 0, "groupnorm_fused: a group of %d channels straddles the two sources", cpg);
+  // widest vector every access of every group can use: channel offsets, row pitches and base addresses
+  auto ok = [&](int vec) {
+    if (cpg % vec) return false;
+    const uintptr_t bytes = (uintptr_t)vec * 2;
+    if (sp->x_pitch[0] % vec || ap->y_pitch % vec || (C1 && sp->x_pitch[1] % vec)) return false;
+    if ((uintptr_t)sp->x_ptr[0] % bytes || (uintptr_t)ap->y_ptr % bytes) return false;
+    if (C1 && (uintptr_t)sp->x_ptr[1] % bytes) return false;
+    return true;
+  };
+  const int vec = ok(8) ? 8 : ok(4) ? 4 : ok(2) ? 2 : 1;
+  B200_CHECK_ARG(cpg / vec <= 512, "groupnorm_fused: %d channels per group is too many for one CTA", cpg);
+  const __nv_bfloat16* x0 = reinterpret_cast<const __nv_bfloat16*>(sp->x_ptr[0]);
+  const __nv_bfloat16* x1 = reinterpret_cast<const __nv_bfloat16*>(sp->x_ptr[1]);
+  __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(ap->y_ptr);
+  dim3 grid(sp->groups, sp->N);
+#define B200_GN_FUSED(V)                                                                                           \
+  gn_fused_small_kernel<V><<<grid, 512, 0, stream>>>(x0, x1, C0, C1, sp->x_pitch[0], sp->x_pitch[1], (int)sp->spatial, \
+                                                     sp->groups, sp->eps, sp->gamma, sp->beta, ap->act, y, ap->y_pitch)
+  if (vec == 8) B200_GN_FUSED(8);
+  else if (vec == 4) B200_GN_FUSED(4);
+  else if (vec == 2) B200_GN_FUSED(2);
+  else B200_GN_FUSED(1);
+#undef B200_GN_FUSED
+  B200_LAUNCH_CHECK("gn_fused_small_kernel");
   return B200_OK;
 }
 

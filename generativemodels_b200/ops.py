@@ -568,16 +568,37 @@ def groupnorm_affine(srcs: CL | Sequence[CL], groups: int, eps: float, gamma: to
     return affine
 
 
+# Single-launch GroupNorm for small tensors (b200_groupnorm_fused).  STAGED: written after round 1's GPU budget was
+# spent — compiled and exercised through the CPU stand-in only, so it is off until `B200_STAGED=1 pytest -m gpu` has
+# run its tests on a B200 (tests/test_kernels_gpu.py::test_groupnorm_fused_small).
+_GN_SMALL = os.environ.get("B200_GN_SMALL", "0") == "1"
+_GN_SMALL_MAX_ELEMS = 1 << 17           # spatial * channels-per-group handled by one CTA
+
+
 def groupnorm(srcs: CL | Sequence[CL], groups: int, eps: float, gamma: torch.Tensor, beta: torch.Tensor,
               act: int = ACT_NONE) -> CL:
     """GroupNorm (+SiLU) over the virtual channel-concat of ``srcs``; returns one dense CL."""
     lib = _lib.require_device()
     if isinstance(srcs, CL):
         srcs = [srcs]
-    affine = groupnorm_affine(srcs, groups, eps, gamma, beta)
     a0 = srcs[0]
+    Ct = sum(a.C for a in srcs)
+    if _GN_SMALL and Ct % groups == 0 and act in (ACT_NONE, ACT_SILU):
+        cpg = Ct // groups
+        if a0.spatial * cpg <= _GN_SMALL_MAX_ELEMS and cpg <= 4096 and (len(srcs) == 1 or a0.C % cpg == 0) \
+                and not (_GN_FUSE and all(a.gn is not None for a in srcs)):
+            sp, ap = _gn_params(srcs)
+            out = a0.like(Ct)
+            sp.groups, sp.eps = groups, eps
+            g32 = gamma if gamma.dtype == torch.float32 else gamma.float()
+            b32 = beta if beta.dtype == torch.float32 else beta.float()
+            sp.gamma, sp.beta = g32.data_ptr(), b32.data_ptr()
+            ap.act, ap.y_ptr, ap.y_pitch = act, out.t.data_ptr(), out.pitch
+            check(lib.b200_groupnorm_fused(C.byref(sp), C.byref(ap), _stream()), "b200_groupnorm_fused")
+            return out
+    affine = groupnorm_affine(srcs, groups, eps, gamma, beta)
     _, ap = _gn_params(srcs)
-    out = a0.like(sum(a.C for a in srcs))
+    out = a0.like(Ct)
     ap.affine, ap.act = affine.data_ptr(), act
     ap.y_ptr, ap.y_pitch = out.t.data_ptr(), out.pitch
     check(lib.b200_groupnorm_apply(C.byref(ap), _stream()), "b200_groupnorm_apply")

@@ -171,6 +171,14 @@ typedef struct {
 } b200_gn_apply_params;
 int b200_groupnorm_apply(const b200_gn_apply_params* p, void* stream);
 
+/* nn.GroupNorm (+ nn.SiLU) in ONE launch for small tensors (the deep levels of a latent UNet normalise 10^4..10^6
+ * elements ~50 times per step: three launch latencies per GroupNorm for microseconds of work otherwise).  One CTA per
+ * (sample, group) sums its slab, folds in fp64 and rewrites it; same arithmetic as stats + apply.  Reads x_ptr / x_C /
+ * x_pitch / N / spatial / groups / eps / gamma / beta of `s` (partial and affine are not used) and act / y_ptr /
+ * y_pitch of `a`.  With two sources no group may straddle them (C0 % (C / groups) == 0); at most 4096 channels per
+ * group.  Meant for spatial * C / groups up to ~10^5 elements per group — larger tensors want the two-phase form. */
+int b200_groupnorm_fused(const b200_gn_stats_params* s, const b200_gn_apply_params* a, void* stream);
+
 /* SPADE modulation (generative/networks/blocks/spade_norm.py:78-96), one pass:
  *   y = act( (x * ax + bx) * (1 + (g * ag + bg)) + (t * at + bt) )
  * x = virtual concat of the sources in p (GroupNorm affine table p->affine from b200_groupnorm_stats), g / t = the

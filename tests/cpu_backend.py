@@ -89,6 +89,18 @@ class FakeLib:
         f32(p.affine, N * Cc * 2).view(N, Cc, 2).copy_(torch.stack([a, b], -1))
         return 0
 
+    def b200_groupnorm_fused(self, sp, ap, stream):
+        sp, ap = _obj(sp), _obj(ap)
+        Cc = sp.x_C[0] + (sp.x_C[1] if sp.x_ptr[1] else 0)
+        assert Cc % sp.groups == 0 and (not sp.x_ptr[1] or sp.x_C[0] % (Cc // sp.groups) == 0)
+        table = torch.empty(sp.N * Cc * 2, dtype=torch.float32)          # the fused kernel keeps this in registers
+        sp.affine, ap.affine = table.data_ptr(), table.data_ptr()
+        try:
+            self.b200_groupnorm_stats(C.byref(sp), stream)
+            return self.b200_groupnorm_apply(C.byref(ap), stream)
+        finally:
+            sp.affine, ap.affine = None, None
+
     def b200_groupnorm_from_partials(self, p, partial, slots, stream):
         p = _obj(p)
         ptrs = [int(v) if v else 0 for v in partial]

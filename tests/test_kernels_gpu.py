@@ -356,6 +356,41 @@ def test_groupnorm_concat(cuda_device):
     assert_close(ops.from_cl(out), ref, 1e-2, "groupnorm concat")
 
 
+@pytest.mark.skipif(__import__("os").environ.get("B200_STAGED") != "1",
+                    reason="staged: b200_groupnorm_fused was written after round 1's GPU budget was spent; "
+                           "run with B200_STAGED=1 on a B200 before enabling ops._GN_SMALL")
+@pytest.mark.parametrize("shape,groups", [((2, 64, 16, 16), 32), ((1, 128, 64, 64), 32), ((2, 32, 5, 7, 5), 8),
+                                          ((1, 768, 5, 7, 5), 32), ((2, 24, 9, 11), 8), ((3, 20, 6, 6), 4),
+                                          ((1, 12, 33), 12)])
+def test_groupnorm_fused_small(cuda_device, monkeypatch, shape, groups):
+    """Single-launch GroupNorm (+SiLU) against torch and against the three-kernel path: channel vectors of 8 / 4 / 2 / 1,
+    3-D, pad channels, two sources."""
+    ops = _ops()
+    torch.manual_seed(21)
+    if len(shape) == 3:
+        shape = (shape[0], shape[1], 1, shape[2])
+    x = torch.randn(*shape) * 2 + 0.5
+    C_ = shape[1]
+    g, b = torch.randn(C_), torch.randn(C_)
+    ref = F.silu(F.group_norm(bf(x), groups, g, b, 1e-6))
+    xc = ops.to_cl(x.cuda())
+    monkeypatch.setattr(ops, "_GN_SMALL", False)
+    plain = ops.from_cl(ops.groupnorm(xc, groups, 1e-6, g.cuda(), b.cuda(), act=ops.ACT_SILU))
+    monkeypatch.setattr(ops, "_GN_SMALL", True)
+    out = ops.groupnorm(xc, groups, 1e-6, g.cuda(), b.cuda(), act=ops.ACT_SILU)
+    fused = ops.from_cl(out)
+    assert_close(fused, ref, 1e-2, "fused GroupNorm vs torch")
+    assert rel_err(fused, plain)[0] < 2e-3
+    if out.pitch > C_:
+        assert float(out.t[..., C_:].float().abs().max()) == 0.0           # pad channels are exact zeros
+    # no activation, and the virtual concat of two sources (groups must not straddle them)
+    if C_ % (2 * (C_ // groups)) == 0 and groups % 2 == 0:
+        h = C_ // 2
+        x0, x1 = ops.to_cl(x[:, :h].contiguous().cuda()), ops.to_cl(x[:, h:].contiguous().cuda())
+        cat = ops.from_cl(ops.groupnorm([x0, x1], groups, 1e-6, g.cuda(), b.cuda()))
+        assert_close(cat, F.group_norm(bf(x), groups, g, b, 1e-6), 1e-2, "fused GroupNorm over two sources")
+
+
 def test_layernorm_geglu(cuda_device):
     ops = _ops()
     torch.manual_seed(4)

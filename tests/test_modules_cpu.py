@@ -89,6 +89,29 @@ def test_time_embedding_projections_are_one_launch_cpu(monkeypatch):
     assert rel(m(x, t, class_labels=cls), want) < 2e-2
 
 
+def test_small_groupnorm_routing_cpu(monkeypatch):
+    """ops._GN_SMALL (staged, default off): small GroupNorms go through ONE b200_groupnorm_fused call — also over the
+    virtual concat of the up path — and the network output is unchanged."""
+    from generativemodels_b200 import _lib, ops
+    assert ops._GN_SMALL is False
+    kw = G.UNET_CASES["unet3d_attn"]
+    torch.manual_seed(0)
+    m = G.randomize_zero_params(nets().DiffusionModelUNet(**kw)).eval()
+    x, t = torch.randn(1, 1, 8, 12, 8), torch.Tensor((300,))
+    want = m(x, t)
+    lib = _lib.require_device()
+    calls = {"fused": 0, "stats": 0}
+    fused, stats = lib.b200_groupnorm_fused, lib.b200_groupnorm_stats
+    monkeypatch.setattr(lib, "b200_groupnorm_fused", lambda *a: (calls.__setitem__("fused", calls["fused"] + 1), fused(*a))[1])
+    monkeypatch.setattr(ops, "_GN_SMALL", True)
+    monkeypatch.setattr(ops, "_GN_SMALL_MAX_ELEMS", 8 * 12 * 8 * 4)       # level 0 of the up path (8 ch / group) stays two-phase
+    got = m(x, t)
+    monkeypatch.setattr(lib, "b200_groupnorm_stats", lambda *a: (calls.__setitem__("stats", calls["stats"] + 1), stats(*a))[1])
+    m(x, t)
+    assert calls["fused"] >= 2 * 10 and calls["stats"] >= 1
+    assert rel(got, want) < 1e-6
+
+
 def test_samplers_golden_cpu():
     from generativemodels_b200.inferers import DiffusionInferer
     from generativemodels_b200.networks.schedulers import DDIMScheduler, DDPMScheduler, PNDMScheduler
