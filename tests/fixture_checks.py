@@ -1,0 +1,63 @@
+"""Checks of the product against the reference-generated fixtures of SURVEY.md §8f ranks 1 and 3
+(tests/golden/g_likelihood.pt, g_transformer.pt; tests/golden/make_golden_next.py).  One body per check, run on the CPU
+stand-in by tests/test_modules_cpu.py and on the CUDA path by tests/test_parity_gpu.py."""
+from pathlib import Path
+
+import torch
+
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+def rel(a, b):
+    return ((a.float().cpu() - b.float().cpu()).norm() / (b.float().cpu().norm() + 1e-12)).item()
+
+
+def check_likelihood_fixture(device, monkeypatch):
+    from generativemodels_b200.inferers import DiffusionInferer
+    from generativemodels_b200.networks.nets import DiffusionModelUNet
+    from generativemodels_b200.networks.schedulers import DDPMScheduler
+    fx = torch.load(GOLD / "g_likelihood.pt", weights_only=False)
+    net_fx = torch.load(GOLD / fx["unet_fixture"], weights_only=False)
+    m = DiffusionModelUNet(**net_fx["kwargs"]).eval()
+    m.load_state_dict(net_fx["state_dict"])
+    m = m.to(device)
+    x, noise = fx["x"].to(device), fx["noise"].to(device)
+    monkeypatch.setattr(torch, "randn_like", lambda t: noise.clone())
+    for ptype, case in fx["cases"].items():
+        s = DDPMScheduler(**case["scheduler_kwargs"])
+        s.set_timesteps(case["scheduler_kwargs"]["num_train_timesteps"])
+        lik, inter = DiffusionInferer(s).get_likelihood(inputs=x, diffusion_model=m, scheduler=s,
+                                                        save_intermediates=True, verbose=False)
+        want = case["likelihood"]
+        assert lik.shape == want.shape and len(inter) == len(case["intermediates"]), ptype
+        # bf16 network, fp32 KL: the per-sample bound agrees to a few percent, every per-step map in relative L2
+        assert torch.allclose(lik.cpu(), want, rtol=5e-2, atol=1e-3), (ptype, lik.cpu(), want)
+        worst = max(rel(a, b) for a, b in zip(inter, case["intermediates"]))
+        assert worst < 8e-2, (ptype, worst)
+
+
+def check_transformer_fixture(device):
+    from generativemodels_b200.inferers import VQVAETransformerInferer
+    from generativemodels_b200.networks.nets import VQVAE, DecoderOnlyTransformer
+    from generativemodels_b200.utils.ordering import Ordering
+    fx = torch.load(GOLD / "g_transformer.pt", weights_only=False)
+    for name in ("plain", "cross"):
+        c = fx[name]
+        tr = DecoderOnlyTransformer(**c["kwargs"]).eval()
+        assert set(tr.state_dict()) == set(c["state_dict"])
+        tr.load_state_dict(c["state_dict"])
+        tr = tr.to(device)
+        ctx = None if c["context"] is None else c["context"].to(device)
+        got = tr(c["tokens"].to(device), context=ctx)
+        assert got.shape == c["logits"].shape and rel(got, c["logits"]) < 2e-2, (name, rel(got, c["logits"]))
+    s = fx["sampler"]
+    vq = VQVAE(**s["vqvae_kwargs"]).eval()
+    vq.load_state_dict(s["vqvae_state"])
+    tr = DecoderOnlyTransformer(**s["transformer_kwargs"]).eval()
+    tr.load_state_dict(s["transformer_state"])
+    vq, tr = vq.to(device), tr.to(device)
+    ordering = Ordering(**s["ordering_kwargs"])
+    got = VQVAETransformerInferer().sample((4, 4), s["start"].to(device), vq, tr, ordering, top_k=1, verbose=False)
+    # greedy decoding is discrete: a token flipped by bf16 logits would change whole codebook vectors, so the decoded
+    # image either matches to bf16 round-off or is grossly off
+    assert got.shape == s["sample"].shape and rel(got, s["sample"]) < 3e-2, rel(got, s["sample"])

@@ -379,3 +379,12 @@ def test_vqvae_transformer_inferer_cpu(monkeypatch):
     assert ll_up.shape == (2, 1, 16, 16)
     with pytest.raises(ValueError):
         Ordering("hilbert", 2, (1, 4, 4))
+
+
+def test_rank1_rank3_reference_fixtures_cpu(monkeypatch):
+    """get_likelihood and the transformer sampler against fixtures written by the unmodified reference."""
+    import generativemodels_b200.networks.nets.transformer as T
+    from tests import fixture_checks
+    monkeypatch.setattr(T, "require_cuda", lambda x, m: None)
+    fixture_checks.check_likelihood_fixture("cpu", monkeypatch)
+    fixture_checks.check_transformer_fixture("cpu")

@@ -611,3 +611,12 @@ def test_cuda_graph_replay_matches_eager(cuda_device):
         m.conv_in.conv.weight.mul_(1.5)
     ts = torch.Tensor((500.0,)).cuda()
     assert torch.equal(g(x, timesteps=ts).clone(), m(x, timesteps=ts))
+
+
+def test_rank1_rank3_reference_fixtures(cuda_device, monkeypatch):
+    """get_likelihood (12 DDPM steps, two prediction types, KL maps) and the transformer forward / greedy
+    VQVAETransformerInferer.sample against fixtures written by the unmodified reference (make_golden_next.py); the same
+    bodies run on the CPU stand-in in tests/test_modules_cpu.py."""
+    from tests import fixture_checks
+    fixture_checks.check_likelihood_fixture("cuda", monkeypatch)
+    fixture_checks.check_transformer_fixture("cuda")
