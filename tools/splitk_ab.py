@@ -1,6 +1,9 @@
-"""Dev probe: graph-replayed sampling with and without split-K in ONE process on ONE box (box-to-box variance is a few
-percent, the same order as the effect): brain-LDM latent UNet (3-D, 20x28x20) and the C2 latent UNet (2-D 64x64),
-batch 1, DDIM-50 loops without the decoder."""
+"""Dev probe: graph-replayed sampling with one switch of generativemodels_b200.ops off / on in ONE process on ONE box
+(box-to-box variance is a few percent, the same order as the effects): brain-LDM latent UNet (3-D, 20x28x20) and the C2
+latent UNet (2-D 64x64), batch 1, DDIM-50 loops without the decoder.
+
+    python tools/splitk_ab.py [_SPLIT_K | _GN_SMALL]      (default _SPLIT_K)
+"""
 import sys
 import time
 from pathlib import Path
@@ -13,6 +16,8 @@ from generativemodels_b200.cuda_graph import graphed
 from generativemodels_b200.networks.nets import DiffusionModelUNet
 from generativemodels_b200.networks.schedulers import DDIMScheduler
 
+FLAG = sys.argv[1] if len(sys.argv) > 1 else "_SPLIT_K"
+assert hasattr(ops, FLAG), FLAG
 torch.manual_seed(0)
 
 
@@ -50,7 +55,7 @@ for name, (net, x, ctx, keep) in cases.items():
     res = {}
     for rep in range(2):
         for split in (False, True):
-            ops._SPLIT_K = split
+            setattr(ops, FLAG, split)
             g = graphed(net)
             loop(g, x.clone(), ctx, keep)
             torch.cuda.synchronize()
@@ -59,5 +64,5 @@ for name, (net, x, ctx, keep) in cases.items():
                 loop(g, x.clone(), ctx, keep)
             torch.cuda.synchronize()
             res.setdefault(split, []).append((time.perf_counter() - t0) / 3 / 50 * 1e3)
-    print(f"{name}: ms/step one-pass {min(res[False]):.3f} (runs {res[False]}), split-K {min(res[True]):.3f} "
+    print(f"{name}: ms/step {FLAG}=False {min(res[False]):.3f} (runs {res[False]}), {FLAG}=True {min(res[True]):.3f} "
           f"(runs {res[True]})")
