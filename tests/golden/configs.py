@@ -136,3 +136,36 @@ BUNDLE_SCHEDULER = dict(beta_start=0.0015, beta_end=0.0205, num_train_timesteps=
                         clip_sample=False)
 BUNDLE_STEPS = 5
 BUNDLE_NOISE = (1, 3, 4, 8, 4)
+
+
+# BASELINE.json configs[0] (C1): the reference's own CPU-runnable case — 2d_ddpm_tutorial.py:166-174 network,
+# DDPMScheduler(1000) with set_timesteps(4), batch 2 of 1x64x64.  The 30 M weights are not committed: both sides
+# regenerate them from this recipe (same state_dict keys and shapes on both sides).
+C1_UNET = dict(spatial_dims=2, in_channels=1, out_channels=1, num_channels=(128, 256, 256),
+               attention_levels=(False, True, True), num_res_blocks=1, num_head_channels=256)
+C1_SHAPE = (2, 1, 64, 64)
+C1_STEPS = 4
+
+
+def recipe_state_dict(module, seed=2024):
+    """Deterministic, implementation-independent weights: every floating tensor of ``module.state_dict()`` (keys in
+    sorted order) is drawn from one seeded CPU generator — matrices / filters ~ N(0, 1/fan_in), norm scales ~ 1 +
+    0.1 N(0,1), biases ~ 0.1 N(0,1).  Loads the result into ``module`` and returns it."""
+    import math
+
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    sd = module.state_dict()
+    out = {}
+    for k in sorted(sd):
+        t = sd[k]
+        if not t.is_floating_point():
+            out[k] = t.clone()
+        elif t.dim() > 1:
+            out[k] = torch.randn(t.shape, generator=g) / math.sqrt(t[0].numel())
+        elif k.endswith("weight"):
+            out[k] = 1.0 + 0.1 * torch.randn(t.shape, generator=g)
+        else:
+            out[k] = 0.1 * torch.randn(t.shape, generator=g)
+    module.load_state_dict(out)
+    return out

@@ -388,3 +388,9 @@ def test_rank1_rank3_reference_fixtures_cpu(monkeypatch):
     monkeypatch.setattr(T, "require_cuda", lambda x, m: None)
     fixture_checks.check_likelihood_fixture("cpu", monkeypatch)
     fixture_checks.check_transformer_fixture("cpu")
+
+
+def test_c1_reference_fixture_cpu():
+    """BASELINE.json configs[0] at its real size through the modules on the CPU stand-in (~25 s of numpy GEMMs)."""
+    from tests import fixture_checks
+    fixture_checks.check_c1_fixture("cpu")

@@ -620,3 +620,10 @@ def test_rank1_rank3_reference_fixtures(cuda_device, monkeypatch):
     from tests import fixture_checks
     fixture_checks.check_likelihood_fixture("cuda", monkeypatch)
     fixture_checks.check_transformer_fixture("cuda")
+
+
+def test_c1_reference_fixture(cuda_device):
+    """BASELINE.json configs[0]: tutorial 2-D UNet (128, 256, 256), DDPM with 4 inference steps, batch 2 of 1x64x64 —
+    the CUDA path against the unmodified reference's CPU run (tests/golden/g_c1.pt)."""
+    from tests import fixture_checks
+    fixture_checks.check_c1_fixture("cuda")
