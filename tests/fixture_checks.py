@@ -87,3 +87,42 @@ def check_c1_fixture(device, sample_tol=5e-2):
     torch.manual_seed(fx["ddpm_seed"])
     sample = DiffusionInferer(s).sample(input_noise=noise, diffusion_model=m, scheduler=s, verbose=False)
     assert sample.shape == fx["sample"].shape and rel(sample, fx["sample"]) < sample_tol, rel(sample, fx["sample"])
+
+
+# Probe 24 (t = 500) of the random-weight C2 trajectory sits at a peaked softmax: rounding ONLY q and k to bf16 inside
+# the fp32 oracle already moves the network output by 1.2e-2 there (1.5e-4 at the other probes), and the full bf16
+# data path by 7e-2 on the stand-in.  It is kept as a loosely bounded, documented case, not hidden.
+C2_PROBE_TOL = {0: 3e-2, 1: 3e-2, 24: 2e-1, 49: 3e-2}
+
+
+def check_c2_fixture(device, probes=(0, 1, 24, 49), strict_ill_conditioned=True):
+    """BASELINE.json configs[1]: LDM-tutorial AutoencoderKL + latent UNet, DDIM-50, pinned teacher-forced along the
+    unmodified reference's trajectory (tests/golden/make_golden_c2.py): network output and scheduler step at the probe
+    steps from the reference's x_k, and the decoder on the reference's final latent."""
+    from generativemodels_b200.networks.nets import AutoencoderKL, DiffusionModelUNet
+    from generativemodels_b200.networks.schedulers import DDIMScheduler
+    from tests.golden import configs as G
+    fx = torch.load(GOLD / "g_c2.pt", weights_only=False)
+    unet = DiffusionModelUNet(**G.C2_UNET).eval()
+    G.recipe_state_dict(unet, 12)
+    unet = unet.to(device)
+    s = DDIMScheduler(**G.C2_SCHEDULER)
+    s.set_timesteps(50)
+    report = {}
+    for k in probes:
+        p = fx["probes"][k]
+        assert int(s.timesteps[k]) == p["t"]
+        x = p["x"].to(device)
+        eps = unet(x, timesteps=torch.Tensor((p["t"],)).to(device))
+        nxt, _ = s.step(eps, p["t"], x)
+        exact, _ = s.step(p["eps"].to(device), p["t"], x)            # the scheduler alone: fp32 on both sides
+        assert rel(exact, p["nxt"]) < 1e-5, (k, rel(exact, p["nxt"]))
+        report[k] = (rel(eps, p["eps"]), rel(nxt, p["nxt"]))
+        if k != 24 or strict_ill_conditioned:
+            assert max(report[k]) < C2_PROBE_TOL[k], (k, report[k])
+    ae = AutoencoderKL(**G.C2_AEKL).eval()
+    G.recipe_state_dict(ae, 11)
+    ae = ae.to(device)
+    img = ae.decode_stage_2_outputs(fx["latent"].to(device))
+    assert img.shape == fx["image"].shape and rel(img, fx["image"]) < 3e-2, rel(img, fx["image"])
+    return report

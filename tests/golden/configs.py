@@ -169,3 +169,14 @@ def recipe_state_dict(module, seed=2024):
             out[k] = 0.1 * torch.randn(t.shape, generator=g)
     module.load_state_dict(out)
     return out
+
+
+# BASELINE.json configs[1] (C2): 2d_ldm_tutorial.py:143-153 autoencoder + 303-311 latent UNet, DDIM-50 on a 3x64x64 latent
+C2_AEKL = dict(spatial_dims=2, in_channels=1, out_channels=1, num_channels=(128, 128, 256), latent_channels=3,
+               num_res_blocks=2, attention_levels=(False, False, False), with_encoder_nonlocal_attn=False,
+               with_decoder_nonlocal_attn=False)
+C2_UNET = dict(spatial_dims=2, in_channels=3, out_channels=3, num_res_blocks=2, num_channels=(128, 256, 512),
+               attention_levels=(False, True, True), num_head_channels=(0, 256, 512))
+C2_SCHEDULER = dict(num_train_timesteps=1000, schedule="linear_beta", beta_start=0.0015, beta_end=0.0195)
+C2_LATENT = (1, 3, 64, 64)
+C2_PROBES = (0, 1, 24, 49)             # DDIM step indices at which the reference trajectory is pinned teacher-forced

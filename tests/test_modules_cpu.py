@@ -394,3 +394,11 @@ def test_c1_reference_fixture_cpu():
     """BASELINE.json configs[0] at its real size through the modules on the CPU stand-in (~25 s of numpy GEMMs)."""
     from tests import fixture_checks
     fixture_checks.check_c1_fixture("cpu")
+
+
+def test_c2_reference_fixture_cpu():
+    """BASELINE.json configs[1] at its real size on the CPU stand-in: two probe steps of the reference trajectory (the
+    benign first step and the ill-conditioned t = 500 one) and the 256 x 256 decoder."""
+    from tests import fixture_checks
+    report = fixture_checks.check_c2_fixture("cpu", probes=(0, 24))
+    assert report[24][0] > report[0][0]          # the peaked-softmax probe is the harder one, as documented
