@@ -6,13 +6,25 @@ raises — there is no CPU or PyTorch fallback anywhere in this package.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "lib" / "libb200gen.so"
+# 16-bit storage type ("h16") of activations and packed weights: IEEE fp16 by default, bfloat16 with
+# B200_ACT_DTYPE=bf16 (the same sources built with -DB200_H16_IS_BF16; for models whose activations exceed fp16's
+# range — fp16 stores saturate at +-65504).  Read once at import; the loaded library must agree (b200_act_dtype()).
+ACT_DTYPE = os.environ.get("B200_ACT_DTYPE", "fp16").lower()
+if ACT_DTYPE in ("float16", "half", "f16"):
+    ACT_DTYPE = "fp16"
+if ACT_DTYPE in ("bfloat16",):
+    ACT_DTYPE = "bf16"
+if ACT_DTYPE not in ("fp16", "bf16"):
+    raise ValueError(f"B200_ACT_DTYPE must be fp16 or bf16, got {ACT_DTYPE!r}")
+LIB_PATH = _HERE / "lib" / ("libb200gen.so" if ACT_DTYPE == "fp16" else "libb200gen_bf16.so")
 
 B200_OK, B200_EINVAL, B200_ENOTSUP, B200_ECUDA, B200_ENODEV = 0, -1, -2, -3, -4
-DT_BF16, DT_F32 = 0, 1
+DT_H16, DT_F32 = 0, 1
+H16_FP16, H16_BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_SILU, ACT_LEAKYRELU, ACT_GELU = 0, 1, 2, 3, 4
 PRED_EPSILON, PRED_SAMPLE, PRED_V = 0, 1, 2
 IGEMM_MAX_SEG = 128
@@ -100,6 +112,7 @@ _P, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 SIGNATURES = {
     "b200_last_error_string": [],
     "b200_version": [],
+    "b200_act_dtype": [],
     "b200_device_check": [],
     "b200_sm_count": [],
     "b200_abi_sizeof": [C.c_int],
@@ -116,7 +129,7 @@ SIGNATURES = {
     "b200_nhwc_to_nchw": [_P, _I32, _I32, _I32, _I64, _I32, _P, _P],
     "b200_upsample_nearest2x": [_P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P],
     "b200_avgpool2": [_P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P],
-    "b200_axpy_bf16": [_P, _P, _F, _P, _I64, _P],
+    "b200_axpy_h16": [_P, _P, _F, _P, _I64, _P],
     "b200_copy_channels": [_P, _I32, _I32, _P, _I32, _I32, _I64, _P],
     "b200_geglu": [_P, _I64, _I32, _I32, _P, _I32, _P],
     "b200_softmax_rows": [_P, _I64, _I32, _I64, _P, _I64, _P],
@@ -174,6 +187,10 @@ def load():
         if c_size != C.sizeof(struct):
             raise B200Error(f"ABI mismatch: {struct.__name__} is {C.sizeof(struct)} bytes in Python but {c_size} in "
                             f"{LIB_PATH.name}; rebuild the library (generativemodels_b200/csrc/build.sh)")
+    want = H16_FP16 if ACT_DTYPE == "fp16" else H16_BF16
+    if lib.b200_act_dtype() != want:
+        raise B200Error(f"{LIB_PATH.name} stores 16-bit data as format {lib.b200_act_dtype()} but B200_ACT_DTYPE="
+                        f"{ACT_DTYPE} was requested; rebuild the library (generativemodels_b200/csrc/build.sh)")
     _lib = lib
     return lib
 

@@ -6,7 +6,7 @@ unchanged through :mod:`generativemodels_b200.bundle.config`.
 B200 specifics: the latent is 3x20x28x20 (11 200 voxels), so one UNet step is ~250 launches of a few microseconds —
 the network is wrapped in a CUDA graph (one capture, 50 replays); the conditioning planes are broadcast once, not per
 step; the decoder (15 TFLOP of 64..128-channel 3-D convolutions at up to 160x224x160) runs once on the implicit-GEMM
-kernel.  The reference decodes under ``autocast`` (fp16 convolutions); here the decoder is bf16 with fp32 accumulation
+kernel.  The reference decodes under ``autocast`` (fp16 convolutions); here the decoder is 16-bit (fp16 by default) with fp32 accumulation
 like every other network, so no autocast context is needed or used.
 """
 from __future__ import annotations

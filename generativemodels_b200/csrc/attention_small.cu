@@ -11,8 +11,8 @@
 namespace b200 {
 
 template <int R>   // R = ceil(dh / 32) registers per lane
-__global__ void attention_small_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
-                                       const __nv_bfloat16* __restrict__ v, __nv_bfloat16* __restrict__ out, int B,
+__global__ void attention_small_kernel(const h16* __restrict__ q, const h16* __restrict__ k,
+                                       const h16* __restrict__ v, h16* __restrict__ out, int B,
                                        int T, int S, int heads, int dh, int q_pitch, int k_pitch, int v_pitch,
                                        int o_pitch, float scale, int kv_rows, int causal, int q_pos0,
                                        const int* __restrict__ pos_dev) {
@@ -27,48 +27,48 @@ __global__ void attention_small_kernel(const __nv_bfloat16* __restrict__ q, cons
   const int t = (int)(wid % T);
   const int h = (int)((wid / T) % heads);
   const int b = (int)(wid / ((long long)T * heads));
-  const __nv_bfloat16* qr = q + ((long long)b * T + t) * q_pitch + h * dh;
+  const h16* qr = q + ((long long)b * T + t) * q_pitch + h * dh;
   float qreg[R], acc[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int d = lane + 32 * r;
-    qreg[r] = d < dh ? __bfloat162float(qr[d]) * scale : 0.f;
+    qreg[r] = d < dh ? h2f(qr[d]) * scale : 0.f;
     acc[r] = 0.f;
   }
   float mx = -INFINITY, denom = 0.f;
   // kv_rows = rows per batch item in the k / v buffers (a key/value cache holds max_seq rows, S of them valid);
   // causal: query t (absolute position q_pos0 + t) only sees keys s <= q_pos0 + t (SABlock causal_mask,
   // blocks/selfattention.py:93-97, 131-132)
-  const __nv_bfloat16* kb = k + (long long)b * kv_rows * k_pitch + h * dh;
-  const __nv_bfloat16* vb = v + (long long)b * kv_rows * v_pitch + h * dh;
+  const h16* kb = k + (long long)b * kv_rows * k_pitch + h * dh;
+  const h16* vb = v + (long long)b * kv_rows * v_pitch + h * dh;
   const int s_end = causal ? min(S, q_pos0 + t + 1) : S;
   for (int s = 0; s < s_end; ++s) {
-    const __nv_bfloat16* kr = kb + (long long)s * k_pitch;
+    const h16* kr = kb + (long long)s * k_pitch;
     float dot = 0.f;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const int d = lane + 32 * r;
-      if (d < dh) dot = fmaf(qreg[r], __bfloat162float(kr[d]), dot);
+      if (d < dh) dot = fmaf(qreg[r], h2f(kr[d]), dot);
     }
     dot = warp_sum(dot);
     const float nmx = fmaxf(mx, dot);
     const float corr = __expf(mx - nmx);      // exp(-inf) = 0 on the first key
     const float p = __expf(dot - nmx);
     denom = denom * corr + p;
-    const __nv_bfloat16* vr = vb + (long long)s * v_pitch;
+    const h16* vr = vb + (long long)s * v_pitch;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const int d = lane + 32 * r;
-      if (d < dh) acc[r] = acc[r] * corr + p * __bfloat162float(vr[d]);
+      if (d < dh) acc[r] = acc[r] * corr + p * h2f(vr[d]);
     }
     mx = nmx;
   }
   const float inv = 1.0f / denom;
-  __nv_bfloat16* orow = out + ((long long)b * T + t) * o_pitch + h * dh;
+  h16* orow = out + ((long long)b * T + t) * o_pitch + h * dh;
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int d = lane + 32 * r;
-    if (d < dh) orow[d] = __float2bfloat16_rn(acc[r] * inv);
+    if (d < dh) orow[d] = f2h(acc[r] * inv);
   }
 }
 
@@ -96,10 +96,10 @@ extern "C" int b200_attention_small_ex(const void* q, const void* k, const void*
   const int wpb = 8;
   const long long blocks = (total + wpb - 1) / wpb;
   B200_CHECK_ARG(blocks < (1ll << 31), "attention_small: too many rows");
-  const __nv_bfloat16* qq = reinterpret_cast<const __nv_bfloat16*>(q);
-  const __nv_bfloat16* kk = reinterpret_cast<const __nv_bfloat16*>(k);
-  const __nv_bfloat16* vv = reinterpret_cast<const __nv_bfloat16*>(v);
-  __nv_bfloat16* oo = reinterpret_cast<__nv_bfloat16*>(out);
+  const h16* qq = reinterpret_cast<const h16*>(q);
+  const h16* kk = reinterpret_cast<const h16*>(k);
+  const h16* vv = reinterpret_cast<const h16*>(v);
+  h16* oo = reinterpret_cast<h16*>(out);
 #define LAUNCH(R) attention_small_kernel<R><<<(unsigned)blocks, wpb * 32, 0, stream>>>( \
       qq, kk, vv, oo, B, T, S, heads, dh, q_pitch, k_pitch, v_pitch, o_pitch, scale, kv_rows, causal, q_pos0, pos_dev)
   if (dh <= 32) LAUNCH(1);

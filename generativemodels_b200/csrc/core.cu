@@ -32,7 +32,13 @@ int sm_count() {
 
 extern "C" const char* b200_last_error_string(void) { return b200::g_err; }
 
-extern "C" int b200_version(void) { return 100; }
+extern "C" int b200_version(void) { return 200; }
+
+#ifdef B200_H16_IS_BF16
+extern "C" int b200_act_dtype(void) { return B200_H16_BF16; }
+#else
+extern "C" int b200_act_dtype(void) { return B200_H16_FP16; }
+#endif
 
 extern "C" int b200_sm_count(void) { return b200::sm_count(); }
 

@@ -12,36 +12,36 @@ namespace b200 {
 static constexpr int kRowsMax = 8;
 
 // y[m, o] = act( LN?(x[m, :]) . W[o, :] + bias[o] ) + res[m, o]      (m < M <= 8; W bf16 K-major, row pitch w_pitch)
-__global__ void __launch_bounds__(256) rows_linear_kernel(const __nv_bfloat16* __restrict__ x, int x_pitch, int M, int K,
+__global__ void __launch_bounds__(256) rows_linear_kernel(const h16* __restrict__ x, int x_pitch, int M, int K,
                                                           const float* __restrict__ ln_g, const float* __restrict__ ln_b,
-                                                          float ln_eps, const __nv_bfloat16* __restrict__ W, int w_pitch,
+                                                          float ln_eps, const h16* __restrict__ W, int w_pitch,
                                                           int O, const float* __restrict__ bias, int act,
-                                                          const __nv_bfloat16* __restrict__ res, int r_pitch, void* out,
+                                                          const h16* __restrict__ res, int r_pitch, void* out,
                                                           int o_pitch, int out_f32) {
   extern __shared__ __align__(16) uint8_t dsm[];
-  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(dsm);        // [M][Kp], Kp = K rounded up to 8
+  h16* xs = reinterpret_cast<h16*>(dsm);        // [M][Kp], Kp = K rounded up to 8
   const int Kp = (K + 7) & ~7;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // ---- stage the rows (LayerNorm applied on the way in, rounded to bf16 like the stand-alone kernel's output) ----
   for (int m = warp; m < M; m += 8) {
-    const __nv_bfloat16* xr = x + (long long)m * x_pitch;
+    const h16* xr = x + (long long)m * x_pitch;
     if (ln_g) {
       float s = 0.f, q = 0.f;
-      for (int k = lane; k < K; k += 32) { const float v = __bfloat162float(xr[k]); s += v; q = fmaf(v, v, q); }
+      for (int k = lane; k < K; k += 32) { const float v = h2f(xr[k]); s += v; q = fmaf(v, v, q); }
       s = warp_sum(s); q = warp_sum(q);
       const float mean = s / K;
       const float rstd = rsqrtf(fmaxf(q / K - mean * mean, 0.f) + ln_eps);
       for (int k = lane; k < Kp; k += 32)
-        xs[m * Kp + k] = k < K ? __float2bfloat16_rn((__bfloat162float(xr[k]) - mean) * rstd * ln_g[k] + ln_b[k])
-                               : __float2bfloat16_rn(0.f);
+        xs[m * Kp + k] = k < K ? f2h((h2f(xr[k]) - mean) * rstd * ln_g[k] + ln_b[k])
+                               : f2h(0.f);
     } else {
-      for (int k = lane; k < Kp; k += 32) xs[m * Kp + k] = k < K ? xr[k] : __float2bfloat16_rn(0.f);
+      for (int k = lane; k < Kp; k += 32) xs[m * Kp + k] = k < K ? xr[k] : f2h(0.f);
     }
   }
   __syncthreads();
   // ---- one output column per warp per pass ----
   for (int o = blockIdx.x * 8 + warp; o < O; o += gridDim.x * 8) {
-    const __nv_bfloat16* wr = W + (long long)o * w_pitch;
+    const h16* wr = W + (long long)o * w_pitch;
     float acc[kRowsMax];
 #pragma unroll
     for (int m = 0; m < kRowsMax; ++m) acc[m] = 0.f;
@@ -68,9 +68,9 @@ __global__ void __launch_bounds__(256) rows_linear_kernel(const __nv_bfloat16* _
         if (m == lane) v = acc[m];
       if (bias) v += bias[o];
       v = apply_act(v, act);
-      if (res) v += __bfloat162float(res[(long long)lane * r_pitch + o]);
+      if (res) v += h2f(res[(long long)lane * r_pitch + o]);
       if (out_f32) reinterpret_cast<float*>(out)[(long long)lane * o_pitch + o] = v;
-      else reinterpret_cast<__nv_bfloat16*>(out)[(long long)lane * o_pitch + o] = __float2bfloat16_rn(v);
+      else reinterpret_cast<h16*>(out)[(long long)lane * o_pitch + o] = f2h(v);
     }
   }
 }
@@ -78,44 +78,44 @@ __global__ void __launch_bounds__(256) rows_linear_kernel(const __nv_bfloat16* _
 // One query row per (batch, head) over S cached keys: 8 warps split the keys, each keeps an online-softmax state,
 // the states are merged through shared memory.  S (and the causal horizon) may come from device memory.
 template <int R>
-__global__ void __launch_bounds__(256) attention_decode_kernel(const __nv_bfloat16* __restrict__ q,
-                                                               const __nv_bfloat16* __restrict__ k,
-                                                               const __nv_bfloat16* __restrict__ v,
-                                                               __nv_bfloat16* __restrict__ out, int S, int heads, int dh,
+__global__ void __launch_bounds__(256) attention_decode_kernel(const h16* __restrict__ q,
+                                                               const h16* __restrict__ k,
+                                                               const h16* __restrict__ v,
+                                                               h16* __restrict__ out, int S, int heads, int dh,
                                                                int q_pitch, int k_pitch, int v_pitch, int o_pitch,
                                                                float scale, int kv_rows, const int* __restrict__ pos_dev) {
   if (pos_dev) S = *pos_dev + 1;
   const int h = blockIdx.x % heads, b = blockIdx.x / heads;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const __nv_bfloat16* qr = q + (long long)b * q_pitch + h * dh;
+  const h16* qr = q + (long long)b * q_pitch + h * dh;
   float qreg[R], acc[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int d = lane + 32 * r;
-    qreg[r] = d < dh ? __bfloat162float(qr[d]) * scale : 0.f;
+    qreg[r] = d < dh ? h2f(qr[d]) * scale : 0.f;
     acc[r] = 0.f;
   }
   float mx = -INFINITY, denom = 0.f;
-  const __nv_bfloat16* kb = k + (long long)b * kv_rows * k_pitch + h * dh;
-  const __nv_bfloat16* vb = v + (long long)b * kv_rows * v_pitch + h * dh;
+  const h16* kb = k + (long long)b * kv_rows * k_pitch + h * dh;
+  const h16* vb = v + (long long)b * kv_rows * v_pitch + h * dh;
   for (int s = warp; s < S; s += 8) {
-    const __nv_bfloat16* kr = kb + (long long)s * k_pitch;
+    const h16* kr = kb + (long long)s * k_pitch;
     float dot = 0.f;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const int d = lane + 32 * r;
-      if (d < dh) dot = fmaf(qreg[r], __bfloat162float(kr[d]), dot);
+      if (d < dh) dot = fmaf(qreg[r], h2f(kr[d]), dot);
     }
     dot = warp_sum(dot);
     const float nmx = fmaxf(mx, dot);
     const float corr = __expf(mx - nmx);
     const float p = __expf(dot - nmx);
     denom = denom * corr + p;
-    const __nv_bfloat16* vr = vb + (long long)s * v_pitch;
+    const h16* vr = vb + (long long)s * v_pitch;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const int d = lane + 32 * r;
-      if (d < dh) acc[r] = acc[r] * corr + p * __bfloat162float(vr[d]);
+      if (d < dh) acc[r] = acc[r] * corr + p * h2f(vr[d]);
     }
     mx = nmx;
   }
@@ -141,11 +141,11 @@ __global__ void __launch_bounds__(256) attention_decode_kernel(const __nv_bfloat
       for (int r = 0; r < R; ++r) o[r] += s_acc[w][lane + 32 * r] * c;
     }
     const float inv = 1.0f / den;
-    __nv_bfloat16* orow = out + (long long)b * o_pitch + h * dh;
+    h16* orow = out + (long long)b * o_pitch + h * dh;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const int d = lane + 32 * r;
-      if (d < dh) orow[d] = __float2bfloat16_rn(o[r] * inv);
+      if (d < dh) orow[d] = f2h(o[r] * inv);
     }
   }
 }
@@ -168,8 +168,8 @@ extern "C" int b200_rows_linear(const void* x, int32_t x_pitch, int32_t M, int32
   int blocks = (O + 7) / 8;
   if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
   rows_linear_kernel<<<blocks, 256, smem, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), x_pitch, M, K, ln_gamma, ln_beta, ln_eps,
-      reinterpret_cast<const __nv_bfloat16*>(w), w_pitch, O, bias, act, reinterpret_cast<const __nv_bfloat16*>(res),
+      reinterpret_cast<const h16*>(x), x_pitch, M, K, ln_gamma, ln_beta, ln_eps,
+      reinterpret_cast<const h16*>(w), w_pitch, O, bias, act, reinterpret_cast<const h16*>(res),
       r_pitch, out, o_pitch, out_dtype == B200_DT_F32 ? 1 : 0);
   B200_LAUNCH_CHECK("rows_linear_kernel");
   return B200_OK;
@@ -182,10 +182,10 @@ extern "C" int b200_attention_decode(const void* q, const void* k, const void* v
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   B200_CHECK_ARG(q && k && v && out && B >= 1 && heads >= 1 && dh >= 1 && dh <= 256 && (pos_dev || (S >= 1 && S <= kv_rows)),
                  "attention_decode: bad arguments (head_dim <= 256)");
-  const __nv_bfloat16* qq = reinterpret_cast<const __nv_bfloat16*>(q);
-  const __nv_bfloat16* kk = reinterpret_cast<const __nv_bfloat16*>(k);
-  const __nv_bfloat16* vv = reinterpret_cast<const __nv_bfloat16*>(v);
-  __nv_bfloat16* oo = reinterpret_cast<__nv_bfloat16*>(out);
+  const h16* qq = reinterpret_cast<const h16*>(q);
+  const h16* kk = reinterpret_cast<const h16*>(k);
+  const h16* vv = reinterpret_cast<const h16*>(v);
+  h16* oo = reinterpret_cast<h16*>(out);
 #define LAUNCH(R) attention_decode_kernel<R><<<B * heads, 256, 0, stream>>>(qq, kk, vv, oo, S, heads, dh, q_pitch, k_pitch, \
                                                                           v_pitch, o_pitch, scale, kv_rows, pos_dev)
   if (dh <= 32) LAUNCH(1);

@@ -10,13 +10,13 @@ namespace b200 {
 // NC[D]HW fp32 <-> NDHWC bf16: 32x32 shared-memory tile transpose (coalesced on both sides).
 // ------------------------------------------------------------------------------------------------
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int C, long long spatial,
-                                    __nv_bfloat16* __restrict__ y, int pitch) {
+                                    h16* __restrict__ y, int pitch) {
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const long long s0 = (long long)blockIdx.x * 32;
   const int c0 = blockIdx.y * 32;
   const float* xb = x + (long long)n * C * spatial;
-  __nv_bfloat16* yb = y + (long long)n * spatial * pitch;
+  h16* yb = y + (long long)n * spatial * pitch;
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     const int c = c0 + j;
     const long long s = s0 + threadIdx.x;
@@ -26,7 +26,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int C, long lon
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     const long long s = s0 + j;
     const int c = c0 + threadIdx.x;
-    if (s < spatial && c < pitch) yb[s * pitch + c] = __float2bfloat16_rn(tile[threadIdx.x][j]);
+    if (s < spatial && c < pitch) yb[s * pitch + c] = f2h(tile[threadIdx.x][j]);
   }
 }
 
@@ -44,7 +44,7 @@ __global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, int C, long long sp
     const int c = c0 + threadIdx.x;
     float v = 0.f;
     if (s < spatial && c < C) {
-      if constexpr (sizeof(T) == 2) v = __bfloat162float(xb[s * pitch + c]);
+      if constexpr (sizeof(T) == 2) v = h2f(xb[s * pitch + c]);
       else v = xb[s * pitch + c];
     }
     tile[j][threadIdx.x] = v;
@@ -110,7 +110,7 @@ __global__ void avgpool2_kernel(const uint4* __restrict__ x, int N, int D, int H
   }
 }
 
-__global__ void axpy_bf16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, float alpha,
+__global__ void axpy_h16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, float alpha,
                                  uint4* __restrict__ y, long long nvec) {
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < nvec;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -123,8 +123,8 @@ __global__ void axpy_bf16_kernel(const uint4* __restrict__ a, const uint4* __res
   }
 }
 
-__global__ void copy_channels_kernel(const __nv_bfloat16* __restrict__ src, int C, int src_pitch,
-                                     __nv_bfloat16* __restrict__ dst, int dst_pitch, int dst_off, long long rows, int vec) {
+__global__ void copy_channels_kernel(const h16* __restrict__ src, int C, int src_pitch,
+                                     h16* __restrict__ dst, int dst_pitch, int dst_off, long long rows, int vec) {
   const int per_row = C / vec;
   const long long total = rows * per_row;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -143,8 +143,8 @@ __global__ void copy_channels_kernel(const __nv_bfloat16* __restrict__ src, int 
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
-__global__ void geglu_kernel(const __nv_bfloat16* __restrict__ x, long long M, int H, int x_pitch,
-                             __nv_bfloat16* __restrict__ y, int y_pitch) {
+__global__ void geglu_kernel(const h16* __restrict__ x, long long M, int H, int x_pitch,
+                             h16* __restrict__ y, int y_pitch) {
   const int HV = H / 8;
   const long long total = M * HV;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -165,7 +165,7 @@ __global__ void geglu_kernel(const __nv_bfloat16* __restrict__ x, long long M, i
 // ------------------------------------------------------------------------------------------------
 template <int TPR>
 __global__ void softmax_rows_kernel(const float* __restrict__ s, long long M, int S, long long s_pitch,
-                                    __nv_bfloat16* __restrict__ p, long long p_pitch) {
+                                    h16* __restrict__ p, long long p_pitch) {
   constexpr int RPB = 256 / TPR;
   const long long row = (long long)blockIdx.x * RPB + threadIdx.x / TPR;
   const int t = threadIdx.x % TPR;
@@ -197,16 +197,16 @@ __global__ void softmax_rows_kernel(const float* __restrict__ s, long long M, in
   }
   if (!live) return;
   const float inv = 1.0f / sum;
-  __nv_bfloat16* pr = p + row * p_pitch;
-  for (int c = t; c < S; c += TPR) pr[c] = __float2bfloat16_rn(__expf(sr[c] - mx) * inv);
-  for (long long c = S + t; c < p_pitch; c += TPR) pr[c] = __float2bfloat16_rn(0.f);
+  h16* pr = p + row * p_pitch;
+  for (int c = t; c < S; c += TPR) pr[c] = f2h(__expf(sr[c] - mx) * inv);
+  for (long long c = S + t; c < p_pitch; c += TPR) pr[c] = f2h(0.f);
 }
 
 // One-pass variant: the score GEMM's epilogue already left (max, sum exp) per 256-column tile of every row, so the
 // row maximum and denominator come from a few hundred partials and the scores are read exactly once.
 __global__ void softmax_rows_partials_kernel(const float* __restrict__ s, int S, long long s_pitch,
                                              const float2* __restrict__ part, int n_tiles,
-                                             __nv_bfloat16* __restrict__ p, long long p_pitch) {
+                                             h16* __restrict__ p, long long p_pitch) {
   const long long row = blockIdx.x;
   const int t = threadIdx.x;
   __shared__ float red[8];
@@ -233,25 +233,25 @@ __global__ void softmax_rows_partials_kernel(const float* __restrict__ s, int S,
   for (int i = 0; i < 8; ++i) sum += red[i];
   const float inv = 1.0f / sum;
   const float* sr = s + row * s_pitch;
-  __nv_bfloat16* po = p + row * p_pitch;
+  h16* po = p + row * p_pitch;
   const bool vec = (s_pitch % 4 == 0) && (p_pitch % 4 == 0) && ((reinterpret_cast<uintptr_t>(s) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(p) & 7) == 0);
   if (vec) {
     const int S4 = S / 4;
     for (int c = t; c < S4; c += 256) {
       const float4 v = __ldg(reinterpret_cast<const float4*>(sr) + c);
-      __nv_bfloat162 lo = __floats2bfloat162_rn(__expf(v.x - mx) * inv, __expf(v.y - mx) * inv);
-      __nv_bfloat162 hi = __floats2bfloat162_rn(__expf(v.z - mx) * inv, __expf(v.w - mx) * inv);
+      h162 lo = f2h2(__expf(v.x - mx) * inv, __expf(v.y - mx) * inv);
+      h162 hi = f2h2(__expf(v.z - mx) * inv, __expf(v.w - mx) * inv);
       uint2 o;
       o.x = *reinterpret_cast<uint32_t*>(&lo);
       o.y = *reinterpret_cast<uint32_t*>(&hi);
       *reinterpret_cast<uint2*>(po + 4 * (long long)c) = o;
     }
-    for (int c = S4 * 4 + t; c < S; c += 256) po[c] = __float2bfloat16_rn(__expf(sr[c] - mx) * inv);
+    for (int c = S4 * 4 + t; c < S; c += 256) po[c] = f2h(__expf(sr[c] - mx) * inv);
   } else {
-    for (int c = t; c < S; c += 256) po[c] = __float2bfloat16_rn(__expf(sr[c] - mx) * inv);
+    for (int c = t; c < S; c += 256) po[c] = f2h(__expf(sr[c] - mx) * inv);
   }
-  for (long long c = S + t; c < p_pitch; c += 256) po[c] = __float2bfloat16_rn(0.f);
+  for (long long c = S + t; c < p_pitch; c += 256) po[c] = f2h(0.f);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -490,8 +490,8 @@ struct TapGeom {
   int N, D, H, W, OD, OH, OW, kd, kh, kw, sd, sh, sw, pd, ph, pw;
 };
 
-__global__ void tap_gather_kernel(const __nv_bfloat16* __restrict__ x, int C, int x_pitch, TapGeom g,
-                                  __nv_bfloat16* __restrict__ out, int out_pitch) {
+__global__ void tap_gather_kernel(const h16* __restrict__ x, int C, int x_pitch, TapGeom g,
+                                  h16* __restrict__ out, int out_pitch) {
   // one thread per (output voxel, 8-column vector): the voxel coordinates are decoded once, the row is written with
   // 16-byte stores (out_pitch is a multiple of 8: it is the K pitch of the GEMM that follows)
   const int taps = g.kd * g.kh * g.kw;
@@ -504,13 +504,13 @@ __global__ void tap_gather_kernel(const __nv_bfloat16* __restrict__ x, int C, in
     const int ow = (int)(v % g.OW); long long t = v / g.OW;
     const int oh = (int)(t % g.OH); t /= g.OH;
     const int od = (int)(t % g.OD); const int n = (int)(t / g.OD);
-    const __nv_bfloat16* xn = x + (long long)n * g.D * g.H * g.W * x_pitch;
-    __align__(16) __nv_bfloat16 vals[8];
+    const h16* xn = x + (long long)n * g.D * g.H * g.W * x_pitch;
+    __align__(16) h16 vals[8];
     int col = v8 * 8;
     int tap = col / C, c = col - tap * C;
 #pragma unroll
     for (int e = 0; e < 8; ++e, ++col) {
-      __nv_bfloat16 val = __float2bfloat16_rn(0.f);
+      h16 val = f2h(0.f);
       if (tap < taps) {
         const int cw = tap % g.kw, bh = (tap / g.kw) % g.kh, ad = tap / (g.kw * g.kh);
         const int iw = ow * g.sw + cw - g.pw, ih = oh * g.sh + bh - g.ph, id = od * g.sd + ad - g.pd;
@@ -553,9 +553,9 @@ __global__ void tap_sum_kernel(const float* __restrict__ y, int y_pitch, TapGeom
         }
       }
     }
-    if (out_dtype == B200_DT_BF16) {
-      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + v * out_pitch;
-      for (int co = 0; co < out_pitch; ++co) o[co] = __float2bfloat16_rn(co < COUT ? acc[co < COUT ? co : 0] : 0.f);
+    if (out_dtype == B200_DT_H16) {
+      h16* o = reinterpret_cast<h16*>(out) + v * out_pitch;
+      for (int co = 0; co < out_pitch; ++co) o[co] = f2h(co < COUT ? acc[co < COUT ? co : 0] : 0.f);
     } else {
       float* o = reinterpret_cast<float*>(out) + v * out_pitch;
       for (int co = 0; co < out_pitch; ++co) o[co] = co < COUT ? acc[co < COUT ? co : 0] : 0.f;
@@ -567,7 +567,7 @@ __global__ void tap_sum_kernel(const float* __restrict__ y, int y_pitch, TapGeom
 // token + absolute position embedding rows -> bf16 (nets/transformer.py:97-99)
 __global__ void embed_tokens_kernel(const long long* __restrict__ tokens, long long M, int seq_len, int pos0,
                                     const float* __restrict__ tok_emb, const float* __restrict__ pos_emb, int C,
-                                    __nv_bfloat16* __restrict__ out, int pitch, const int* __restrict__ pos_dev) {
+                                    h16* __restrict__ out, int pitch, const int* __restrict__ pos_dev) {
   if (pos_dev) pos0 = *pos_dev;
   const long long total = M * pitch;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -576,7 +576,7 @@ __global__ void embed_tokens_kernel(const long long* __restrict__ tokens, long l
     const long long m = i / pitch;
     float v = 0.f;
     if (c < C) v = tok_emb[tokens[m] * C + c] + pos_emb[(long long)(pos0 + (int)(m % seq_len)) * C + c];
-    out[i] = __float2bfloat16_rn(v);
+    out[i] = f2h(v);
   }
 }
 
@@ -591,7 +591,7 @@ extern "C" int b200_nchw_to_nhwc(const float* x, int32_t N, int32_t C, int64_t s
   const long long bx = (spatial + 31) / 32;
   B200_CHECK_ARG(bx < (1ll << 31) && N <= 65535, "nchw_to_nhwc: extent too large");
   dim3 grid((unsigned)bx, (pitch + 31) / 32, N);
-  nchw_to_nhwc_kernel<<<grid, dim3(32, 8), 0, stream>>>(x, C, spatial, reinterpret_cast<__nv_bfloat16*>(y), pitch);
+  nchw_to_nhwc_kernel<<<grid, dim3(32, 8), 0, stream>>>(x, C, spatial, reinterpret_cast<h16*>(y), pitch);
   B200_LAUNCH_CHECK("nchw_to_nhwc_kernel");
   return B200_OK;
 }
@@ -603,8 +603,8 @@ extern "C" int b200_nhwc_to_nchw(const void* x, int32_t x_dtype, int32_t N, int3
   const long long bx = (spatial + 31) / 32;
   B200_CHECK_ARG(bx < (1ll << 31) && N <= 65535, "nhwc_to_nchw: extent too large");
   dim3 grid((unsigned)bx, (C + 31) / 32, N);
-  if (x_dtype == B200_DT_BF16)
-    nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, dim3(32, 8), 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), C, spatial, pitch, y);
+  if (x_dtype == B200_DT_H16)
+    nhwc_to_nchw_kernel<h16><<<grid, dim3(32, 8), 0, stream>>>(reinterpret_cast<const h16*>(x), C, spatial, pitch, y);
   else
     nhwc_to_nchw_kernel<float><<<grid, dim3(32, 8), 0, stream>>>(reinterpret_cast<const float*>(x), C, spatial, pitch, y);
   B200_LAUNCH_CHECK("nhwc_to_nchw_kernel");
@@ -634,13 +634,13 @@ extern "C" int b200_avgpool2(const void* x, int32_t N, int32_t D, int32_t H, int
   return B200_OK;
 }
 
-extern "C" int b200_axpy_bf16(const void* a, const void* b, float alpha, void* y, int64_t n, void* stream_v) {
+extern "C" int b200_axpy_h16(const void* a, const void* b, float alpha, void* y, int64_t n, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  B200_CHECK_ARG(a && b && y && n % 8 == 0, "axpy_bf16: element count must be a multiple of 8");
+  B200_CHECK_ARG(a && b && y && n % 8 == 0, "axpy_h16: element count must be a multiple of 8");
   if (n == 0) return B200_OK;
-  axpy_bf16_kernel<<<grid_for(n / 8), 256, 0, stream>>>(reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b),
+  axpy_h16_kernel<<<grid_for(n / 8), 256, 0, stream>>>(reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b),
                                                        alpha, reinterpret_cast<uint4*>(y), n / 8);
-  B200_LAUNCH_CHECK("axpy_bf16_kernel");
+  B200_LAUNCH_CHECK("axpy_h16_kernel");
   return B200_OK;
 }
 
@@ -659,8 +659,8 @@ extern "C" int b200_tap_gather(const void* x, int32_t C, int32_t x_pitch, const 
   B200_CHECK_ARG(tap_geom_ok(g) && out_pitch >= g.kd * g.kh * g.kw * C && out_pitch % 8 == 0 &&
                  ((uintptr_t)out % 16) == 0, "tap_gather: bad geometry (out_pitch must be a multiple of 8)");
   const long long total = (long long)g.N * g.OD * g.OH * g.OW * (out_pitch / 8);
-  tap_gather_kernel<<<grid_for(total), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), C, x_pitch, g,
-                                                        reinterpret_cast<__nv_bfloat16*>(out), out_pitch);
+  tap_gather_kernel<<<grid_for(total), 256, 0, stream>>>(reinterpret_cast<const h16*>(x), C, x_pitch, g,
+                                                        reinterpret_cast<h16*>(out), out_pitch);
   B200_LAUNCH_CHECK("tap_gather_kernel");
   return B200_OK;
 }
@@ -687,7 +687,7 @@ extern "C" int b200_tap_sum(const float* y, int32_t y_pitch, const int32_t* geom
 
 
 // rows of T new tokens per sequence appended to a [B, L, pitch] key/value cache at the device-side position
-__global__ void cache_append_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ cache, int B,
+__global__ void cache_append_kernel(const h16* __restrict__ src, h16* __restrict__ cache, int B,
                                     int T, int L, int pitch, const int* __restrict__ pos_dev) {
   const int pos = *pos_dev;
   const long long total = (long long)B * T * pitch;
@@ -706,7 +706,7 @@ extern "C" int b200_cache_append(const void* src, void* cache, int32_t B, int32_
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   B200_CHECK_ARG(src && cache && pos_dev && B >= 1 && T >= 1 && L >= T && pitch >= 1, "cache_append: bad arguments");
   cache_append_kernel<<<grid_for((long long)B * T * pitch), 256, 0, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(src), reinterpret_cast<__nv_bfloat16*>(cache), B, T, L, pitch, pos_dev);
+      reinterpret_cast<const h16*>(src), reinterpret_cast<h16*>(cache), B, T, L, pitch, pos_dev);
   B200_LAUNCH_CHECK("cache_append_kernel");
   return B200_OK;
 }
@@ -727,7 +727,7 @@ extern "C" int b200_embed_tokens(const int64_t* tokens, int64_t M, int32_t seq_l
                  "embed_tokens: bad arguments");
   embed_tokens_kernel<<<grid_for(M * pitch), 256, 0, stream>>>(reinterpret_cast<const long long*>(tokens), M, seq_len,
                                                               pos0, tok_emb, pos_emb, C,
-                                                              reinterpret_cast<__nv_bfloat16*>(out), pitch, pos_dev);
+                                                              reinterpret_cast<h16*>(out), pitch, pos_dev);
   B200_LAUNCH_CHECK("embed_tokens_kernel");
   return B200_OK;
 }
@@ -738,8 +738,8 @@ extern "C" int b200_copy_channels(const void* src, int32_t C, int32_t src_pitch,
   B200_CHECK_ARG(src && dst && C >= 1 && src_pitch >= C && dst_pitch >= dst_off + C && rows >= 1, "copy_channels: bad arguments");
   const int vec = (C % 8 == 0 && src_pitch % 8 == 0 && dst_pitch % 8 == 0 && dst_off % 8 == 0 &&
                    ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0)) ? 8 : 1;
-  copy_channels_kernel<<<grid_for(rows * (C / vec)), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(src), C, src_pitch,
-                                                                     reinterpret_cast<__nv_bfloat16*>(dst), dst_pitch, dst_off, rows, vec);
+  copy_channels_kernel<<<grid_for(rows * (C / vec)), 256, 0, stream>>>(reinterpret_cast<const h16*>(src), C, src_pitch,
+                                                                     reinterpret_cast<h16*>(dst), dst_pitch, dst_off, rows, vec);
   B200_LAUNCH_CHECK("copy_channels_kernel");
   return B200_OK;
 }
@@ -749,8 +749,8 @@ extern "C" int b200_geglu(const void* x, int64_t M, int32_t H, int32_t x_pitch, 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   B200_CHECK_ARG(x && y && H % 8 == 0 && x_pitch % 8 == 0 && y_pitch % 8 == 0 && x_pitch >= 2 * H && y_pitch >= H,
                  "geglu: bad arguments");
-  geglu_kernel<<<grid_for(M * (H / 8)), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), M, H, x_pitch,
-                                                         reinterpret_cast<__nv_bfloat16*>(y), y_pitch);
+  geglu_kernel<<<grid_for(M * (H / 8)), 256, 0, stream>>>(reinterpret_cast<const h16*>(x), M, H, x_pitch,
+                                                         reinterpret_cast<h16*>(y), y_pitch);
   B200_LAUNCH_CHECK("geglu_kernel");
   return B200_OK;
 }
@@ -759,7 +759,7 @@ extern "C" int b200_softmax_rows(const float* s, int64_t M, int32_t S, int64_t s
                                  void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   B200_CHECK_ARG(s && p && M >= 1 && S >= 1 && s_pitch >= S && p_pitch >= S, "softmax_rows: bad arguments");
-  __nv_bfloat16* pp = reinterpret_cast<__nv_bfloat16*>(p);
+  h16* pp = reinterpret_cast<h16*>(p);
   if (S <= 1024) {
     const long long blocks = (M + 7) / 8;
     B200_CHECK_ARG(blocks < (1ll << 31), "softmax_rows: too many rows");
@@ -778,7 +778,7 @@ extern "C" int b200_softmax_rows_partials(const float* s, int64_t M, int32_t S, 
   B200_CHECK_ARG(s && p && partials && M >= 1 && M < (1ll << 31) && S >= 1 && s_pitch >= S && p_pitch >= S && n_tiles >= 1,
                  "softmax_rows_partials: bad arguments");
   softmax_rows_partials_kernel<<<(unsigned)M, 256, 0, stream>>>(s, S, s_pitch, reinterpret_cast<const float2*>(partials),
-                                                               n_tiles, reinterpret_cast<__nv_bfloat16*>(p), p_pitch);
+                                                               n_tiles, reinterpret_cast<h16*>(p), p_pitch);
   B200_LAUNCH_CHECK("softmax_rows_partials_kernel");
   return B200_OK;
 }

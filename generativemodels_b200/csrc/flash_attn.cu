@@ -34,11 +34,11 @@ struct FlashDev {
   int B, T, S, heads, dh, d_chunks, dv, n_dv;
   int q_tiles, n_items, n_kv;
   float scale_log2;
-  __nv_bfloat16* out;
+  h16* out;
   long long out_bstride, out_pitch;
-  const __nv_bfloat16* res;
+  const h16* res;
   long long res_bstride, res_pitch;
-  __nv_bfloat16* pslab;           // replay workspace: [grid][n_kv][128 rows][64 keys] — tile-contiguous, so that the
+  h16* pslab;           // replay workspace: [grid][n_kv][128 rows][64 keys] — tile-contiguous, so that the
                                   // warps' row stores coalesce to 4 KB runs and every TMA tile is one 16 KB burst
                                   // (row-major [128][S] slabs made every tile 128 scattered 128-byte DRAM accesses)
   long long p_pitch;              // elements per CTA slab = n_kv * 128 * 64
@@ -107,7 +107,7 @@ __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::aft
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+__device__ __forceinline__ void umma_h16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
@@ -116,7 +116,7 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
       : "memory");
 }
 // A operand from tensor memory (row = lane, two bf16 per 32-bit column), B from shared memory
-__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+__device__ __forceinline__ void umma_h16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
@@ -138,8 +138,8 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {      // K-major, 
 static constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
 __device__ __forceinline__ uint32_t desc_lo(uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); }
 __device__ __forceinline__ uint64_t desc64(uint32_t lo) { return (static_cast<uint64_t>(kDescHi) << 32) | lo; }
-__device__ __forceinline__ uint32_t idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+__device__ __forceinline__ uint32_t idesc_h16(int M, int N) {
+  return (1u << 4) | (B200_H16_FMT << 7) | (B200_H16_FMT << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
@@ -358,8 +358,8 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
   } else if (warp == 1) {
     // =========================== MMA issuer (whole warp runs the loop; one elected lane issues) ========
     {
-      const uint32_t idesc_s = idesc_bf16(kBM, kBKV);
-      const uint32_t idesc_o = idesc_bf16(kBM, p.dv);
+      const uint32_t idesc_s = idesc_h16(kBM, kBKV);
+      const uint32_t idesc_o = idesc_h16(kBM, p.dv);
       const uint32_t q_lo = desc_lo(sQ), k_lo = desc_lo(sK), v_lo = desc_lo(sV);
       int kst = 0; uint32_t kph = 0;
       uint32_t scount = 0;      // number of S blocks issued so far (global across items)
@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
                 for (int cc = 0; cc < CPS; ++cc) {
 #pragma unroll
                   for (int kk = 0; kk < 4; ++kk)
-                    umma_bf16(d_s, desc64(q_lo + (step * CPS + cc) * (kQChunkBytes >> 4) + 2 * kk),
+                    umma_h16(d_s, desc64(q_lo + (step * CPS + cc) * (kQChunkBytes >> 4) + 2 * kk),
                               desc64(b_lo + cc * (kKChunkBytes >> 4) + 2 * kk), idesc_s,
                               (step | cc | kk) != 0 ? 1u : 0u);
                 }
@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
               const uint32_t a_tmem = tP + pb * 32;          // 16 bf16 = 8 columns per K step
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk)
-                umma_bf16_ts(tO, a_tmem + 8u * kk, desc64(v_lo + 2 * kk), idesc_o,
+                umma_h16_ts(tO, a_tmem + 8u * kk, desc64(v_lo + 2 * kk), idesc_o,
                              (j > kLookahead || kk > 0) ? 1u : 0u);
               umma_commit(v_empty);
               umma_commit(p_empty(pb));
@@ -440,7 +440,7 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
               const uint32_t b_lo = a_lo + (kQChunkBytes >> 4);
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk)
-                umma_bf16(tO, desc64(a_lo + 2 * kk), desc64(b_lo + 2 * kk), idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+                umma_h16(tO, desc64(a_lo + 2 * kk), desc64(b_lo + 2 * kk), idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
               umma_commit(k_empty(kst));
               if (gated) umma_commit(p_empty(pb));
               if (j == n_kv - 1) {
@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
     uint32_t ocount = 0;       // epilogues done
     uint32_t icount = 0;
     // REPLAY: this CTA's probability slab and this warp's rescale log
-    __nv_bfloat16* slab_row = REPLAY ? p.pslab + (long long)blockIdx.x * p.p_pitch + row * kBKV : nullptr;
+    h16* slab_row = REPLAY ? p.pslab + (long long)blockIdx.x * p.p_pitch + row * kBKV : nullptr;
     float* ev_fac = REPLAY ? p.ev_fac + ((long long)blockIdx.x * 4 + q) * (long long)n_kv * 32 : nullptr;
     int* ev_blk = REPLAY ? p.ev_blk + ((long long)blockIdx.x * 4 + q) * (long long)n_kv : nullptr;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++icount) {
@@ -555,7 +555,7 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
           const float p1 = ex2_approx(fmaf(__uint_as_float(raw[2 * w + 1]), p.scale_log2, neg_m));
           sum8[(2 * w) & 7] += p0;
           sum8[(2 * w + 1) & 7] += p1;
-          __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
+          h162 h = f2h2(p0, p1);
           pw[w] = *reinterpret_cast<uint32_t*>(&h);
         }
         FA_T(5);
@@ -565,7 +565,7 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
         tmem_st32(tP + lane_addr + pb * 32, pw);
         if constexpr (REPLAY) {
           // the same 64 probabilities to this row of the slab (128 contiguous bytes), for pass 2
-          __nv_bfloat16* dst = slab_row + (long long)j * (kBM * kBKV);
+          h16* dst = slab_row + (long long)j * (kBM * kBKV);
 #pragma unroll
           for (int g = 0; g < 4; ++g) stg256(dst + g * 16, pw + g * 8);
         }
@@ -635,8 +635,8 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
         ++ocount;
         fence_after();
         const long long col0 = (long long)it.h * p.dh + (long long)(REPLAY ? pass : it.dvi) * p.dv;
-        __nv_bfloat16* orow = p.out + it.b * p.out_bstride + (long long)t * p.out_pitch + col0;
-        const __nv_bfloat16* rrow = p.res ? p.res + it.b * p.res_bstride + (long long)t * p.res_pitch + col0 : nullptr;
+        h16* orow = p.out + it.b * p.out_bstride + (long long)t * p.out_pitch + col0;
+        const h16* rrow = p.res ? p.res + it.b * p.res_bstride + (long long)t * p.res_pitch + col0 : nullptr;
         for (int c0 = 0; c0 < p.dv; c0 += 32) {
           uint32_t o[32];
           tmem_ld32(tO + lane_addr + c0, o);
@@ -687,7 +687,7 @@ static int encode3(CUtensorMap* tm, const void* ptr, cuuint64_t d0, cuuint64_t d
   cuuint64_t strides[2] = {s1_bytes, s2_bytes};
   cuuint32_t box[3] = {b0, b1, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = g_encode(tm, B200_H16_TMAP, 3, const_cast<void*>(ptr), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -757,9 +757,9 @@ extern "C" int b200_attention_flash(const b200_flash_params* a, void* stream_v) 
   B200_CHECK_ARG(items < (1ll << 31), "attention_flash: too many work items");
   d.n_items = (int)items;
   d.scale_log2 = a->scale * 1.4426950408889634f;
-  d.out = reinterpret_cast<__nv_bfloat16*>(a->out);
+  d.out = reinterpret_cast<h16*>(a->out);
   d.out_pitch = a->out_pitch; d.out_bstride = (long long)a->T * a->out_pitch;
-  d.res = reinterpret_cast<const __nv_bfloat16*>(a->res);
+  d.res = reinterpret_cast<const h16*>(a->res);
   d.res_pitch = a->res_pitch; d.res_bstride = (long long)a->T * a->res_pitch;
   int rc;
   if ((rc = fa::encode3(&d.tmQ, a->q, C, a->T, a->B, (cuuint64_t)a->q_pitch * 2, (cuuint64_t)a->T * a->q_pitch * 2, 64,
@@ -774,7 +774,7 @@ extern "C" int b200_attention_flash(const b200_flash_params* a, void* stream_v) 
   if (replay) {
     B200_CHECK_ARG(grid == rp.grid && d.n_kv == rp.n_kv, "attention_flash: internal replay plan mismatch");
     uint8_t* ws = static_cast<uint8_t*>(a->workspace);
-    d.pslab = reinterpret_cast<__nv_bfloat16*>(ws);
+    d.pslab = reinterpret_cast<h16*>(ws);
     d.p_pitch = (long long)d.n_kv * fa::kBM * fa::kBKV;
     d.ev_fac = reinterpret_cast<float*>(ws + rp.slab_bytes);
     d.ev_blk = reinterpret_cast<int*>(ws + rp.slab_bytes + rp.fac_bytes);

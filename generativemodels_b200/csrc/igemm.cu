@@ -42,10 +42,10 @@ struct IgemmDev {
   alignas(64) CUtensorMap tmA[2];
   alignas(64) CUtensorMap tmB;
   // raw views for the cross-check kernel
-  const __nv_bfloat16* a_ptr[2];
+  const h16* a_ptr[2];
   int a_C[2], a_pitch[2];
   int in_N, in_D, in_H, in_W;
-  const __nv_bfloat16* w_ptr;
+  const h16* w_ptr;
   int w_rows, w_K, w_pitch;
   long long w_bstride;
   int w_batched;
@@ -147,7 +147,7 @@ __device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
                : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+__device__ __forceinline__ void umma_h16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -171,7 +171,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 // kind::f16 instruction descriptor: c=f32 (bit4), a=bf16 (bit7), b=bf16 (bit10), K-major both,
 // N>>3 at [17,23), M>>4 at [24,29).
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
+  return (1u << 4) | (B200_H16_FMT << 7) | (B200_H16_FMT << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 
@@ -224,8 +224,8 @@ __device__ __forceinline__ void epilogue_math(const IgemmDev& p, float* v, int n
     v[j] = x * p.scale;
   }
   if (p.res_ptr) {
-    if (p.res_dtype == B200_DT_BF16) {
-      const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(p.res_ptr) + res_off + col0;
+    if (p.res_dtype == B200_DT_H16) {
+      const h16* r = reinterpret_cast<const h16*>(p.res_ptr) + res_off + col0;
       if (p.res_vec) {
 #pragma unroll
         for (int g = 0; g < CH / 8; ++g) {
@@ -240,7 +240,7 @@ __device__ __forceinline__ void epilogue_math(const IgemmDev& p, float* v, int n
       } else {
 #pragma unroll
         for (int j = 0; j < CH; ++j)
-          if (col0 + j < p.out_cols) v[j] += __bfloat162float(r[j]);
+          if (col0 + j < p.out_cols) v[j] += h2f(r[j]);
       }
     } else {
       const float* r = reinterpret_cast<const float*>(p.res_ptr) + res_off + col0;
@@ -272,8 +272,8 @@ __device__ __forceinline__ void epilogue_math(const IgemmDev& p, float* v, int n
 // each thread stores its own row segment (good when consecutive rows are adjacent in memory: conv outputs)
 template <int CH>
 __device__ __forceinline__ void store_direct(const IgemmDev& p, const float* v, long long out_off, int col0) {
-  if (p.out_dtype == B200_DT_BF16) {
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out_ptr) + out_off + col0;
+  if (p.out_dtype == B200_DT_H16) {
+    h16* o = reinterpret_cast<h16*>(p.out_ptr) + out_off + col0;
     if (p.out_vec) {
 #pragma unroll
       for (int g = 0; g < CH / 8; ++g)
@@ -281,7 +281,7 @@ __device__ __forceinline__ void store_direct(const IgemmDev& p, const float* v, 
     } else {
 #pragma unroll
       for (int j = 0; j < CH; ++j)
-        if (col0 + j < p.out_cols) o[j] = __float2bfloat16_rn(v[j]);
+        if (col0 + j < p.out_cols) o[j] = f2h(v[j]);
     }
   } else {
     float* o = reinterpret_cast<float*>(p.out_ptr) + out_off + col0;
@@ -337,7 +337,7 @@ __device__ __forceinline__ void act_inplace(float* v, int act) {
 // residual prefetch for one row chunk (bf16, 16-byte aligned): CH/8 uint4
 template <int CH>
 __device__ __forceinline__ void load_res_fast(const IgemmDev& p, uint4* rv, long long res_off, int col0) {
-  const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(p.res_ptr) + res_off + col0;
+  const h16* r = reinterpret_cast<const h16*>(p.res_ptr) + res_off + col0;
   if (p.res_v256) {
 #pragma unroll
     for (int g = 0; g < CH / 16; ++g) ldg256(r + g * 16, rv[2 * g], rv[2 * g + 1]);
@@ -373,8 +373,8 @@ __device__ __forceinline__ void epilogue_fast(const IgemmDev& p, const uint32_t*
     }
   }
   act_inplace<CH>(v, p.act2);
-  if (p.out_dtype == B200_DT_BF16) {
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out_ptr) + out_off + col0;
+  if (p.out_dtype == B200_DT_H16) {
+    h16* o = reinterpret_cast<h16*>(p.out_ptr) + out_off + col0;
     uint4 pk[CH / 8];
 #pragma unroll
     for (int g = 0; g < CH / 8; ++g) pk[g] = pack8(v + g * 8);
@@ -431,8 +431,8 @@ __device__ __forceinline__ void store_staged(const IgemmDev& p, const float* v, 
     const long long off = __shfl_sync(0xffffffffu, out_off, r);
     if (((okmask >> r) & 1u) && col_ok) {
       const float x = tile[r * LD + (lane % CH)];
-      if (p.out_dtype == B200_DT_BF16)
-        reinterpret_cast<__nv_bfloat16*>(p.out_ptr)[off + col] = __float2bfloat16_rn(x);
+      if (p.out_dtype == B200_DT_H16)
+        reinterpret_cast<h16*>(p.out_ptr)[off + col] = f2h(x);
       else
         reinterpret_cast<float*>(p.out_ptr)[off + col] = x;
     }
@@ -552,7 +552,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
 #pragma unroll
           for (int kk = 0; kk < kBK / 16; ++kk) {
             // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in >>4 units
-            umma_bf16(d_tmem, adesc + 2u * kk, bdesc + 2u * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+            umma_h16(d_tmem, adesc + 2u * kk, bdesc + 2u * kk, idesc, (k | kk) != 0 ? 1u : 0u);
           }
           tcgen05_commit(empty_bar(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -570,7 +570,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
     float* addv = add_tiles + (warp - 2) * BN;
     int add_key = -1;
     const bool fast_ok = p.out_vec && !p.out_staged && !p.stat_ptr &&
-                         (!p.res_ptr || (p.res_vec && p.res_dtype == B200_DT_BF16));
+                         (!p.res_ptr || (p.res_vec && p.res_dtype == B200_DT_H16));
     // GroupNorm partial sums for the consumer of this tensor: per warp [BN/8 groups][sum, sumsq] in shared memory
     // (aliases the staged-store tiles, which this mode excludes), flushed to this warp's private global slot
     // whenever the (sample, column tile) changes and at the end — deterministic, no atomics.
@@ -744,13 +744,13 @@ __global__ void igemm_check_kernel(const __grid_constant__ IgemmDev p) {
 #pragma unroll
   for (int j = 0; j < 16; ++j) acc[j] = 0.f;
   const int wb = p.w_batched ? nb : 0;
-  const __nv_bfloat16* wbase = p.w_ptr + (long long)wb * p.w_bstride;
+  const h16* wbase = p.w_ptr + (long long)wb * p.w_bstride;
   int kglob = 0;
   for (int s = 0; s < p.n_seg; ++s) {
     const SegDev sg = p.seg[s];
     const int iw = ow * p.sw + sg.dw, ih = oh * p.sh + sg.dh, id = od * p.sd + sg.dd;
     const bool inb = iw >= 0 && iw < p.in_W && ih >= 0 && ih < p.in_H && id >= 0 && id < p.in_D;
-    const __nv_bfloat16* a = p.a_ptr[sg.src] +
+    const h16* a = p.a_ptr[sg.src] +
         ((((long long)nb * p.in_D + id) * p.in_H + ih) * p.in_W + iw) * p.a_pitch[sg.src];
     for (int c = 0; c < sg.nchunks; ++c, ++kglob) {
       if (!inb) continue;
@@ -758,11 +758,11 @@ __global__ void igemm_check_kernel(const __grid_constant__ IgemmDev p) {
         const int ch = (sg.c0 + c) * kBK + e;
         const int kk = kglob * kBK + e;
         if (ch >= p.a_C[sg.src] || kk >= p.w_K) break;
-        const float av = __bfloat162float(a[ch]);
+        const float av = h2f(a[ch]);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int col = cg * 16 + j;
-          if (col < p.w_rows) acc[j] += av * __bfloat162float(wbase[(long long)col * p.w_pitch + kk]);
+          if (col < p.w_rows) acc[j] += av * h2f(wbase[(long long)col * p.w_pitch + kk]);
         }
       }
     }
@@ -829,10 +829,10 @@ __global__ void gn8_partial_check_kernel(const __grid_constant__ IgemmDev p) {
   const int oh = (int)(m % p.OH); m /= p.OH;
   const int od = (int)(m % p.OD); m /= p.OD;
   const int nb = (int)m;
-  const __nv_bfloat16* o = reinterpret_cast<const __nv_bfloat16*>(p.out_ptr) + nb * p.out_sN + od * p.out_sD +
+  const h16* o = reinterpret_cast<const h16*>(p.out_ptr) + nb * p.out_sN + od * p.out_sD +
                            oh * p.out_sH + ow * p.out_sW + g * 8;
   float s = 0.f, q = 0.f;
-  for (int j = 0; j < 8; ++j) { const float f = __bfloat162float(o[j]); s += f; q = fmaf(f, f, q); }
+  for (int j = 0; j < 8; ++j) { const float f = h2f(o[j]); s += f; q = fmaf(f, f, q); }
   float* dst = p.gn_partial + (((long long)nb * p.gn_slots + p.gn_slot0) * groups + g) * 2;
   atomicAdd(dst, s);
   atomicAdd(dst + 1, q);
@@ -990,12 +990,12 @@ extern "C" int b200_igemm(const b200_igemm_params* p, void* stream_v) {
   d.n_seg = p->n_seg;
   d.num_k_chunks = kchunks;
   for (int s = 0; s < 2; ++s) {
-    d.a_ptr[s] = reinterpret_cast<const __nv_bfloat16*>(p->a_ptr[s]);
+    d.a_ptr[s] = reinterpret_cast<const h16*>(p->a_ptr[s]);
     d.a_C[s] = p->a_C[s];
     d.a_pitch[s] = p->a_pitch[s];
   }
   d.in_N = p->in_N; d.in_D = p->in_D; d.in_H = p->in_H; d.in_W = p->in_W;
-  d.w_ptr = reinterpret_cast<const __nv_bfloat16*>(p->w_ptr);
+  d.w_ptr = reinterpret_cast<const h16*>(p->w_ptr);
   d.w_rows = p->w_rows; d.w_K = w_K; d.w_pitch = p->w_pitch;
   d.w_bstride = p->w_bstride; d.w_batched = p->w_batched;
   d.sd = p->stride_d; d.sh = p->stride_h; d.sw = p->stride_w;
@@ -1007,39 +1007,39 @@ extern "C" int b200_igemm(const b200_igemm_params* p, void* stream_v) {
   d.res_ptr = p->res_ptr; d.res_dtype = p->res_dtype;
   d.res_sN = p->res_sN; d.res_sD = p->res_sD; d.res_sH = p->res_sH; d.res_sW = p->res_sW;
   {
-    const int g = (p->out_dtype == B200_DT_BF16) ? 8 : 4;
-    const int esz = (p->out_dtype == B200_DT_BF16) ? 2 : 4;
+    const int g = (p->out_dtype == B200_DT_H16) ? 8 : 4;
+    const int esz = (p->out_dtype == B200_DT_H16) ? 2 : 4;
     d.out_vec = (p->out_cols % g == 0) && (p->out_sN % g == 0) && (p->out_sD % g == 0) &&
                 (p->out_sH % g == 0) && (p->out_sW % g == 0) && (((uintptr_t)p->out_ptr) % 16 == 0);
     (void)esz;
-    d.out_v256 = d.out_vec && p->out_dtype == B200_DT_BF16 && (p->out_cols % 16 == 0) && (p->out_sN % 16 == 0) &&
+    d.out_v256 = d.out_vec && p->out_dtype == B200_DT_H16 && (p->out_cols % 16 == 0) && (p->out_sN % 16 == 0) &&
                  (p->out_sD % 16 == 0) && (p->out_sH % 16 == 0) && (p->out_sW % 16 == 0) &&
                  (((uintptr_t)p->out_ptr) % 32 == 0);
   }
   {
     // rows far apart in memory (wide row-major GEMM outputs): stage the tile through smem for coalesced row stores
-    const long long esz = (p->out_dtype == B200_DT_BF16) ? 2 : 4;
+    const long long esz = (p->out_dtype == B200_DT_H16) ? 2 : 4;
     // (bf16 rows of 32 columns are already whole 64-byte segments per lane: those take the vectorised direct path)
     d.out_staged = (p->out_sW * esz > 2048 && p->out_dtype == B200_DT_F32) ? 1 : 0;
   }
   d.gn_partial = p->gn_partial; d.gn_slots = p->gn_slots; d.gn_slot0 = p->gn_slot0;
   if (p->gn_partial) {
     // the partials ride on the vectorised epilogue: every column chunk must be a full 32-wide bf16 vector chunk
-    B200_CHECK_ARG(p->out_dtype == B200_DT_BF16 && p->cout % 32 == 0 && d.out_vec && !d.out_staged && !p->stat_ptr && p->gn_slot0 >= 0 && p->gn_slot0 + 4 * sm_count() <= p->gn_slots,
-                   "igemm: gn_partial needs a bf16 vector-aligned output with cout %% 32 == 0 and 4 x SM-count slots");
+    B200_CHECK_ARG(p->out_dtype == B200_DT_H16 && p->cout % 32 == 0 && d.out_vec && !d.out_staged && !p->stat_ptr && p->gn_slot0 >= 0 && p->gn_slot0 + 4 * sm_count() <= p->gn_slots,
+                   "igemm: gn_partial needs an h16 vector-aligned output with cout %% 32 == 0 and 4 x SM-count slots");
   }
   d.stat_ptr = p->stat_ptr;
   if (p->stat_ptr)
     B200_CHECK_ARG(p->out_N == 1 && p->out_D == 1 && p->out_H == 1, "igemm: stat_ptr needs a GEMM-shaped call");
   if (p->res_ptr) {
-    const int g = (p->res_dtype == B200_DT_BF16) ? 8 : 4;
+    const int g = (p->res_dtype == B200_DT_H16) ? 8 : 4;
     d.res_vec = (p->out_cols % g == 0) && (p->res_sN % g == 0) && (p->res_sD % g == 0) &&
                 (p->res_sH % g == 0) && (p->res_sW % g == 0) && (((uintptr_t)p->res_ptr) % 16 == 0);
-    d.res_v256 = d.res_vec && p->res_dtype == B200_DT_BF16 && (p->out_cols % 16 == 0) && (p->res_sN % 16 == 0) &&
+    d.res_v256 = d.res_vec && p->res_dtype == B200_DT_H16 && (p->out_cols % 16 == 0) && (p->res_sN % 16 == 0) &&
                  (p->res_sD % 16 == 0) && (p->res_sH % 16 == 0) && (p->res_sW % 16 == 0) &&
                  (((uintptr_t)p->res_ptr) % 32 == 0);
-    B200_CHECK_ARG(!p->gn_partial || (d.res_vec && p->res_dtype == B200_DT_BF16),
-                   "igemm: gn_partial needs a vector-aligned bf16 residual");
+    B200_CHECK_ARG(!p->gn_partial || (d.res_vec && p->res_dtype == B200_DT_H16),
+                   "igemm: gn_partial needs a vector-aligned h16 residual");
   }
 
   const int impl = p->impl ? p->impl : env_impl();
@@ -1091,7 +1091,7 @@ extern "C" int b200_igemm(const b200_igemm_params* p, void* stream_v) {
     cuuint32_t box[5] = {(cuuint32_t)kBK, (cuuint32_t)(ts.bw * d.sw), (cuuint32_t)(ts.bh * d.sh),
                          (cuuint32_t)(ts.bd * d.sd), 1};
     cuuint32_t estr[5] = {1, (cuuint32_t)d.sw, (cuuint32_t)d.sh, (cuuint32_t)d.sd, 1};
-    CUresult r = g_encode(&d.tmA[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(p->a_ptr[s]),
+    CUresult r = g_encode(&d.tmA[s], B200_H16_TMAP, 5, const_cast<void*>(p->a_ptr[s]),
                           dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1110,7 +1110,7 @@ extern "C" int b200_igemm(const b200_igemm_params* p, void* stream_v) {
     B200_CHECK_ARG(bs % 16 == 0, "igemm: weight batch stride not 16-byte aligned");
     cuuint32_t box[3] = {(cuuint32_t)kBK, (cuuint32_t)BN, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = g_encode(&d.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(p->w_ptr), dims,
+    CUresult r = g_encode(&d.tmB, B200_H16_TMAP, 3, const_cast<void*>(p->w_ptr), dims,
                           strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {

@@ -20,7 +20,7 @@ static constexpr int kGnMaxChunks = 512;
 // ---- stats --------------------------------------------------------------------------------------
 // grid = (chunks, N); block = CV * rows threads, CV = C_total / VEC channel vectors.
 template <int VEC>
-__global__ void gn_partial_kernel(const __nv_bfloat16* __restrict__ x0, const __nv_bfloat16* __restrict__ x1,
+__global__ void gn_partial_kernel(const h16* __restrict__ x0, const h16* __restrict__ x1,
                                   int C0, int C1, int pitch0, int pitch1, long long spatial,
                                   long long vox_per_chunk, float* __restrict__ partial) {
   const int C = C0 + C1;
@@ -35,7 +35,7 @@ __global__ void gn_partial_kernel(const __nv_bfloat16* __restrict__ x0, const __
   if (s1 > spatial) s1 = spatial;
 
   const int c = cv * VEC;
-  const __nv_bfloat16* src;
+  const h16* src;
   int pitch;
   int cc;
   if (c < C0) { src = x0; pitch = pitch0; cc = c; }
@@ -54,7 +54,7 @@ __global__ void gn_partial_kernel(const __nv_bfloat16* __restrict__ x0, const __
         unpack8(v, f);
       } else {
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) f[j] = __bfloat162float(src[s * pitch + j]);
+        for (int j = 0; j < VEC; ++j) f[j] = h2f(src[s * pitch + j]);
       }
 #pragma unroll
       for (int j = 0; j < VEC; ++j) { sum[j] += f[j]; sq[j] = fmaf(f[j], f[j], sq[j]); }
@@ -189,9 +189,9 @@ __device__ __forceinline__ float silu_fast(float x) {
 }
 
 template <int VEC>
-__global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, const __nv_bfloat16* __restrict__ x1,
+__global__ void gn_apply_kernel(const h16* __restrict__ x0, const h16* __restrict__ x1,
                                 int C0, int C1, int pitch0, int pitch1, long long spatial, long long vox_per_chunk,
-                                const float* __restrict__ affine, int act, __nv_bfloat16* __restrict__ y,
+                                const float* __restrict__ affine, int act, h16* __restrict__ y,
                                 int y_pitch) {
   const int C = C0 + C1;
   const int CV = C / VEC;
@@ -204,11 +204,11 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, const __nv
   long long s1 = s0 + vox_per_chunk;
   if (s1 > spatial) s1 = spatial;
   const int c = cv * VEC;
-  const __nv_bfloat16* src;
+  const h16* src;
   int pitch;
   if (c < C0) { src = x0 + (long long)n * spatial * pitch0 + c; pitch = pitch0; }
   else        { src = x1 + (long long)n * spatial * pitch1 + (c - C0); pitch = pitch1; }
-  __nv_bfloat16* dst = y + (long long)n * spatial * y_pitch + c;
+  h16* dst = y + (long long)n * spatial * y_pitch + c;
   float a[VEC], b[VEC];
 #pragma unroll
   for (int j = 0; j < VEC; ++j) {
@@ -241,7 +241,7 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, const __nv
       unpack8(__ldg(reinterpret_cast<const uint4*>(src + s * pitch)), f);
     } else {
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) f[j] = __bfloat162float(src[s * pitch + j]);
+      for (int j = 0; j < VEC; ++j) f[j] = h2f(src[s * pitch + j]);
     }
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
@@ -252,7 +252,7 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, const __nv
       *reinterpret_cast<uint4*>(dst + s * y_pitch) = pack8(f);
     } else {
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) dst[s * y_pitch + j] = __float2bfloat16_rn(f[j]);
+      for (int j = 0; j < VEC; ++j) dst[s * y_pitch + j] = f2h(f[j]);
     }
   }
 }
@@ -264,55 +264,55 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, const __nv
 // pass 2 re-reads it (L1 / L2 hits), normalises, applies the activation and stores.  Thread t keeps one channel
 // vector (VEC channels, fixed) and strides over rows, so its affine pairs live in registers.
 template <int VEC>
-__device__ __forceinline__ void gn_load_vec(const __nv_bfloat16* p, float* f) {
+__device__ __forceinline__ void gn_load_vec(const h16* p, float* f) {
   if constexpr (VEC == 8) {
     unpack8(__ldg(reinterpret_cast<const uint4*>(p)), f);
   } else if constexpr (VEC == 4) {
     const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
-    const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&v.x);
-    const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&v.y);
+    const h162 lo = *reinterpret_cast<const h162*>(&v.x);
+    const h162 hi = *reinterpret_cast<const h162*>(&v.y);
     f[0] = __low2float(lo); f[1] = __high2float(lo); f[2] = __low2float(hi); f[3] = __high2float(hi);
   } else if constexpr (VEC == 2) {
     const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(p));
-    const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&v);
+    const h162 h = *reinterpret_cast<const h162*>(&v);
     f[0] = __low2float(h); f[1] = __high2float(h);
   } else {
-    f[0] = __bfloat162float(p[0]);
+    f[0] = h2f(p[0]);
   }
 }
 template <int VEC>
-__device__ __forceinline__ void gn_store_vec(__nv_bfloat16* p, const float* f) {
+__device__ __forceinline__ void gn_store_vec(h16* p, const float* f) {
   if constexpr (VEC == 8) {
     *reinterpret_cast<uint4*>(p) = pack8(f);
   } else if constexpr (VEC == 4) {
-    const __nv_bfloat162 lo = __floats2bfloat162_rn(f[0], f[1]), hi = __floats2bfloat162_rn(f[2], f[3]);
+    const h162 lo = f2h2(f[0], f[1]), hi = f2h2(f[2], f[3]);
     uint2 v;
     v.x = *reinterpret_cast<const uint32_t*>(&lo);
     v.y = *reinterpret_cast<const uint32_t*>(&hi);
     *reinterpret_cast<uint2*>(p) = v;
   } else if constexpr (VEC == 2) {
-    const __nv_bfloat162 h = __floats2bfloat162_rn(f[0], f[1]);
+    const h162 h = f2h2(f[0], f[1]);
     *reinterpret_cast<uint32_t*>(p) = *reinterpret_cast<const uint32_t*>(&h);
   } else {
-    p[0] = __float2bfloat16_rn(f[0]);
+    p[0] = f2h(f[0]);
   }
 }
 
 template <int VEC>
-__global__ void __launch_bounds__(512) gn_fused_small_kernel(const __nv_bfloat16* __restrict__ x0,
-                                                             const __nv_bfloat16* __restrict__ x1, int C0, int C1,
+__global__ void __launch_bounds__(512) gn_fused_small_kernel(const h16* __restrict__ x0,
+                                                             const h16* __restrict__ x1, int C0, int C1,
                                                              int pitch0, int pitch1, int spatial, int groups, float eps,
                                                              const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, int act,
-                                                             __nv_bfloat16* __restrict__ y, int y_pitch) {
+                                                             h16* __restrict__ y, int y_pitch) {
   const int g = blockIdx.x, n = blockIdx.y;
   const int C = C0 + C1, cpg = C / groups;
   const int c_first = g * cpg;                       // the host guarantees a group never straddles the two sources
-  const __nv_bfloat16* src;
+  const h16* src;
   int pitch;
   if (c_first < C0) { src = x0 + (long long)n * spatial * pitch0 + c_first; pitch = pitch0; }
   else              { src = x1 + (long long)n * spatial * pitch1 + (c_first - C0); pitch = pitch1; }
-  __nv_bfloat16* dst = y + (long long)n * spatial * y_pitch + c_first;
+  h16* dst = y + (long long)n * spatial * y_pitch + c_first;
   const int vpr = cpg / VEC;                         // channel vectors per row (<= blockDim.x)
   const int rows_per_iter = blockDim.x / vpr;
   const int v = threadIdx.x % vpr, row0 = threadIdx.x / vpr;
@@ -380,19 +380,19 @@ __global__ void __launch_bounds__(512) gn_fused_small_kernel(const __nv_bfloat16
   // pad channels [C, y_pitch) stay exact zeros for the consumers' vector loads: the last group's CTA writes them
   if (y_pitch > C && g == groups - 1) {
     const int padw = y_pitch - C;
-    __nv_bfloat16* pad = y + (long long)n * spatial * y_pitch + C;
+    h16* pad = y + (long long)n * spatial * y_pitch + C;
     for (int i = threadIdx.x; i < spatial * padw; i += blockDim.x)
-      pad[(long long)(i / padw) * y_pitch + (i % padw)] = __float2bfloat16_rn(0.f);
+      pad[(long long)(i / padw) * y_pitch + (i % padw)] = f2h(0.f);
   }
 }
 
 // zero the pad channels [C, pitch) of a channels-last tensor (only when pitch > C)
-__global__ void zero_pad_channels_kernel(__nv_bfloat16* y, long long rows, int C, int pitch) {
+__global__ void zero_pad_channels_kernel(h16* y, long long rows, int C, int pitch) {
   const int padw = pitch - C;
   const long long total = rows * padw;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    y[(idx / padw) * pitch + C + idx % padw] = __float2bfloat16_rn(0.f);
+    y[(idx / padw) * pitch + C + idx % padw] = f2h(0.f);
   }
 }
 
@@ -400,10 +400,10 @@ __global__ void zero_pad_channels_kernel(__nv_bfloat16* y, long long rows, int C
 // ---- SPADE modulation -----------------------------------------------------------------------------
 // one thread per (voxel, 8-channel vector) when everything is 16-byte aligned, else per (voxel, channel)
 template <int VEC>
-__global__ void spade_apply_kernel(const __nv_bfloat16* __restrict__ x0, const __nv_bfloat16* __restrict__ x1, int C0,
+__global__ void spade_apply_kernel(const h16* __restrict__ x0, const h16* __restrict__ x1, int C0,
                                    int C1, int pitch0, int pitch1, long long spatial, int N,
-                                   const float* __restrict__ affine, const __nv_bfloat16* __restrict__ gb, int gb_pitch,
-                                   const float* __restrict__ gb_affine, int act, __nv_bfloat16* __restrict__ y,
+                                   const float* __restrict__ affine, const h16* __restrict__ gb, int gb_pitch,
+                                   const float* __restrict__ gb_affine, int act, h16* __restrict__ y,
                                    int y_pitch) {
   const int C = C0 + C1;
   const int CV = C / VEC;
@@ -413,15 +413,15 @@ __global__ void spade_apply_kernel(const __nv_bfloat16* __restrict__ x0, const _
     const int c = (int)(i % CV) * VEC;
     const long long row = i / CV;
     const int n = (int)(row / spatial);
-    const __nv_bfloat16* src = c < C0 ? x0 + row * pitch0 + c : x1 + row * pitch1 + (c - C0);
-    const __nv_bfloat16* g = gb + row * gb_pitch + c;
+    const h16* src = c < C0 ? x0 + row * pitch0 + c : x1 + row * pitch1 + (c - C0);
+    const h16* g = gb + row * gb_pitch + c;
     float xv[VEC], gv[VEC], tv[VEC];
     if constexpr (VEC == 8) {
       unpack8(__ldg(reinterpret_cast<const uint4*>(src)), xv);
       unpack8(__ldg(reinterpret_cast<const uint4*>(g)), gv);
       unpack8(__ldg(reinterpret_cast<const uint4*>(g + C)), tv);
     } else {
-      xv[0] = __bfloat162float(src[0]); gv[0] = __bfloat162float(g[0]); tv[0] = __bfloat162float(g[C]);
+      xv[0] = h2f(src[0]); gv[0] = h2f(g[0]); tv[0] = h2f(g[C]);
     }
     const float* ax = affine + ((long long)n * C + c) * 2;
     const float* ag = gb_affine + ((long long)n * 2 * C + c) * 2;
@@ -434,14 +434,14 @@ __global__ void spade_apply_kernel(const __nv_bfloat16* __restrict__ x0, const _
       const float tt = fmaf(tv[j], at[2 * j], at[2 * j + 1]);
       out[j] = apply_act(fmaf(nx, 1.0f + gg, tt), act);
     }
-    __nv_bfloat16* dst = y + row * y_pitch + c;
+    h16* dst = y + row * y_pitch + c;
     if constexpr (VEC == 8) *reinterpret_cast<uint4*>(dst) = pack8(out);
-    else dst[0] = __float2bfloat16_rn(out[0]);
+    else dst[0] = f2h(out[0]);
   }
 }
 
-__global__ void resize_nearest_kernel(const __nv_bfloat16* __restrict__ x, int N, int D, int H, int W, int pitch,
-                                      __nv_bfloat16* __restrict__ y, int OD, int OH, int OW) {
+__global__ void resize_nearest_kernel(const h16* __restrict__ x, int N, int D, int H, int W, int pitch,
+                                      h16* __restrict__ y, int OD, int OH, int OW) {
   const long long total = (long long)N * OD * OH * OW * pitch;
   const float sd = (float)D / OD, sh = (float)H / OH, sw = (float)W / OW;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -459,28 +459,28 @@ __global__ void resize_nearest_kernel(const __nv_bfloat16* __restrict__ x, int N
 }
 
 // ---- LayerNorm: one warp per row ----------------------------------------------------------------
-__global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long M, int C, int x_pitch,
+__global__ void layernorm_kernel(const h16* __restrict__ x, long long M, int C, int x_pitch,
                                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                 __nv_bfloat16* __restrict__ y, int y_pitch) {
+                                 h16* __restrict__ y, int y_pitch) {
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
-  const __nv_bfloat16* xr = x + row * x_pitch;
+  const h16* xr = x + row * x_pitch;
   float s = 0.f;
-  for (int c = lane; c < C; c += 32) s += __bfloat162float(xr[c]);
+  for (int c = lane; c < C; c += 32) s += h2f(xr[c]);
   const float mean = warp_sum(s) / C;
   float q = 0.f;
   for (int c = lane; c < C; c += 32) {
-    const float d = __bfloat162float(xr[c]) - mean;
+    const float d = h2f(xr[c]) - mean;
     q = fmaf(d, d, q);
   }
   const float rstd = rsqrtf(warp_sum(q) / C + eps);
-  __nv_bfloat16* yr = y + row * y_pitch;
+  h16* yr = y + row * y_pitch;
   for (int c = lane; c < C; c += 32) {
-    const float v = (__bfloat162float(xr[c]) - mean) * rstd * gamma[c] + beta[c];
-    yr[c] = __float2bfloat16_rn(v);
+    const float v = (h2f(xr[c]) - mean) * rstd * gamma[c] + beta[c];
+    yr[c] = f2h(v);
   }
-  for (int c = C + lane; c < y_pitch; c += 32) yr[c] = __float2bfloat16_rn(0.f);
+  for (int c = C + lane; c < y_pitch; c += 32) yr[c] = f2h(0.f);
 }
 
 static int gn_chunks(int N, long long spatial, int rows) {
@@ -526,8 +526,8 @@ extern "C" int b200_groupnorm_stats(const b200_gn_stats_params* p, void* stream_
   const int threads = cv * rows;
   const size_t smem = (size_t)rows * C * 2 * sizeof(float);
   dim3 grid(chunks, p->N);
-  const __nv_bfloat16* x0 = reinterpret_cast<const __nv_bfloat16*>(p->x_ptr[0]);
-  const __nv_bfloat16* x1 = reinterpret_cast<const __nv_bfloat16*>(p->x_ptr[1]);
+  const h16* x0 = reinterpret_cast<const h16*>(p->x_ptr[0]);
+  const h16* x1 = reinterpret_cast<const h16*>(p->x_ptr[1]);
   if (vec == 8)
     gn_partial_kernel<8><<<grid, threads, smem, stream>>>(x0, x1, C0, C1, p->x_pitch[0], p->x_pitch[1], p->spatial, vpc, p->partial);
   else
@@ -577,9 +577,9 @@ extern "C" int b200_groupnorm_apply(const b200_gn_apply_params* p, void* stream_
   const long long vpc = (p->spatial + chunks - 1) / chunks;
   dim3 grid((unsigned)chunks, p->N);
   const int threads = cv * rows;
-  const __nv_bfloat16* x0 = reinterpret_cast<const __nv_bfloat16*>(p->x_ptr[0]);
-  const __nv_bfloat16* x1 = reinterpret_cast<const __nv_bfloat16*>(p->x_ptr[1]);
-  __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(p->y_ptr);
+  const h16* x0 = reinterpret_cast<const h16*>(p->x_ptr[0]);
+  const h16* x1 = reinterpret_cast<const h16*>(p->x_ptr[1]);
+  h16* y = reinterpret_cast<h16*>(p->y_ptr);
   if (vec == 8)
     gn_apply_kernel<8><<<grid, threads, 0, stream>>>(x0, x1, C0, C1, p->x_pitch[0], p->x_pitch[1], p->spatial, vpc, p->affine, p->act, y, p->y_pitch);
   else
@@ -619,9 +619,9 @@ extern "C" int b200_groupnorm_fused(const b200_gn_stats_params* sp, const b200_g
   };
   const int vec = ok(8) ? 8 : ok(4) ? 4 : ok(2) ? 2 : 1;
   B200_CHECK_ARG(cpg / vec <= 512, "groupnorm_fused: %d channels per group is too many for one CTA", cpg);
-  const __nv_bfloat16* x0 = reinterpret_cast<const __nv_bfloat16*>(sp->x_ptr[0]);
-  const __nv_bfloat16* x1 = reinterpret_cast<const __nv_bfloat16*>(sp->x_ptr[1]);
-  __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(ap->y_ptr);
+  const h16* x0 = reinterpret_cast<const h16*>(sp->x_ptr[0]);
+  const h16* x1 = reinterpret_cast<const h16*>(sp->x_ptr[1]);
+  h16* y = reinterpret_cast<h16*>(ap->y_ptr);
   dim3 grid(sp->groups, sp->N);
 #define B200_GN_FUSED(V)                                                                                           \
   gn_fused_small_kernel<V><<<grid, 512, 0, stream>>>(x0, x1, C0, C1, sp->x_pitch[0], sp->x_pitch[1], (int)sp->spatial, \
@@ -649,10 +649,10 @@ extern "C" int b200_spade_apply(const b200_gn_apply_params* p, const void* gb, i
   const long long total = (long long)p->N * p->spatial * (C / (vec ? 8 : 1));
   long long blocks = (total + 255) / 256;
   if (blocks > 16ll * sm_count()) blocks = 16ll * sm_count();
-  const __nv_bfloat16* x0 = reinterpret_cast<const __nv_bfloat16*>(p->x_ptr[0]);
-  const __nv_bfloat16* x1 = reinterpret_cast<const __nv_bfloat16*>(p->x_ptr[1]);
-  const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(gb);
-  __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(p->y_ptr);
+  const h16* x0 = reinterpret_cast<const h16*>(p->x_ptr[0]);
+  const h16* x1 = reinterpret_cast<const h16*>(p->x_ptr[1]);
+  const h16* g = reinterpret_cast<const h16*>(gb);
+  h16* y = reinterpret_cast<h16*>(p->y_ptr);
   if (vec)
     spade_apply_kernel<8><<<(unsigned)blocks, 256, 0, stream>>>(x0, x1, C0, C1, p->x_pitch[0], p->x_pitch[1], p->spatial,
                                                                 p->N, p->affine, g, gb_pitch, gb_affine, p->act, y, p->y_pitch);
@@ -678,8 +678,8 @@ extern "C" int b200_resize_nearest(const void* x, int32_t N, int32_t D, int32_t 
   const long long total = (long long)N * OD * OH * OW * pitch;
   long long blocks = (total + 255) / 256;
   if (blocks > 16ll * sm_count()) blocks = 16ll * sm_count();
-  resize_nearest_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), N, D, H, W, pitch,
-                                                             reinterpret_cast<__nv_bfloat16*>(y), OD, OH, OW);
+  resize_nearest_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const h16*>(x), N, D, H, W, pitch,
+                                                             reinterpret_cast<h16*>(y), OD, OH, OW);
   B200_LAUNCH_CHECK("resize_nearest_kernel");
   return B200_OK;
 }
@@ -691,8 +691,8 @@ extern "C" int b200_layernorm(const void* x, int64_t M, int32_t C, int32_t x_pit
   const int wpb = 8;
   const long long blocks = (M + wpb - 1) / wpb;
   B200_CHECK_ARG(blocks < (1ll << 31), "layernorm: too many rows");
-  layernorm_kernel<<<(unsigned)blocks, wpb * 32, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), M, C, x_pitch,
-                                                             gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(y), y_pitch);
+  layernorm_kernel<<<(unsigned)blocks, wpb * 32, 0, stream>>>(reinterpret_cast<const h16*>(x), M, C, x_pitch,
+                                                             gamma, beta, eps, reinterpret_cast<h16*>(y), y_pitch);
   B200_LAUNCH_CHECK("layernorm_kernel");
   return B200_OK;
 }

@@ -14,7 +14,7 @@ static constexpr int kVqWarps = 8;
 
 __global__ void vq_argmin_kernel(const float* __restrict__ x, long long M, int D, int x_pitch,
                                  const float* __restrict__ cb, int K, long long* __restrict__ idx_out,
-                                 __nv_bfloat16* __restrict__ q16, int q_pitch, float* __restrict__ q32, int ste,
+                                 h16* __restrict__ q16, int q_pitch, float* __restrict__ q32, int ste,
                                  double* __restrict__ sqerr, int* __restrict__ hist) {
   extern __shared__ float sm[];
   const int DP = D + 1;                       // padded pitch: lanes hit distinct banks
@@ -65,12 +65,12 @@ __global__ void vq_argmin_kernel(const float* __restrict__ x, long long M, int D
     const float* e = s_cb + bi * DP;
     for (int d = lane; d < D; d += 32) {
       const float qv = e[d], xv = xs[d];
-      if (q16) q16[m * q_pitch + d] = __float2bfloat16_rn(qv);
+      if (q16) q16[m * q_pitch + d] = f2h(qv);
       if (q32) q32[m * D + d] = ste ? xv + (qv - xv) : qv;
       if (sqerr) { const float df = qv - xv; err_acc += (double)df * (double)df; }
     }
     if (q16)
-      for (int d = D + lane; d < q_pitch; d += 32) q16[m * q_pitch + d] = __float2bfloat16_rn(0.f);
+      for (int d = D + lane; d < q_pitch; d += 32) q16[m * q_pitch + d] = f2h(0.f);
     __syncwarp();
   }
   if (sqerr) {
@@ -80,7 +80,7 @@ __global__ void vq_argmin_kernel(const float* __restrict__ x, long long M, int D
 }
 
 __global__ void vq_gather_kernel(const long long* __restrict__ idx, long long M, const float* __restrict__ cb, int K,
-                                 int D, __nv_bfloat16* __restrict__ q16, int q_pitch) {
+                                 int D, h16* __restrict__ q16, int q_pitch) {
   const long long total = M * q_pitch;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -89,7 +89,7 @@ __global__ void vq_gather_kernel(const long long* __restrict__ idx, long long M,
     long long k = idx[m];
     if (k < 0) k = 0;
     if (k >= K) k = K - 1;
-    q16[i] = __float2bfloat16_rn(d < D ? cb[k * D + d] : 0.f);
+    q16[i] = f2h(d < D ? cb[k * D + d] : 0.f);
   }
 }
 
@@ -98,11 +98,11 @@ __global__ void vq_gather_kernel(const long long* __restrict__ idx, long long M,
 using namespace b200;
 
 extern "C" int b200_vq_argmin_gather(const float* x, int64_t M, int32_t D, int32_t x_pitch, const float* codebook,
-                                     int32_t K, int64_t* indices, void* q_bf16, int32_t q_pitch, float* q_f32,
+                                     int32_t K, int64_t* indices, void* q_h16, int32_t q_pitch, float* q_f32,
                                      int32_t ste, double* sqerr_sum, int32_t* hist, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   B200_CHECK_ARG(x && codebook && indices && M >= 1 && D >= 1 && K >= 1 && x_pitch >= D, "vq_argmin: bad arguments");
-  B200_CHECK_ARG(!q_bf16 || q_pitch >= D, "vq_argmin: q_pitch %d < D %d", q_pitch, D);
+  B200_CHECK_ARG(!q_h16 || q_pitch >= D, "vq_argmin: q_pitch %d < D %d", q_pitch, D);
   const size_t smem = ((size_t)K * (D + 1) + K + (size_t)kVqWarps * D) * sizeof(float);
   if (smem > 200 * 1024) {
     set_error("vq_argmin: codebook %d x %d does not fit in shared memory", K, D);
@@ -117,21 +117,21 @@ extern "C" int b200_vq_argmin_gather(const float* x, int64_t M, int32_t D, int32
   const long long cap = 2ll * sm_count();
   if (blocks > cap) blocks = cap;
   vq_argmin_kernel<<<(unsigned)blocks, kVqWarps * 32, smem, stream>>>(
-      x, M, D, x_pitch, codebook, K, reinterpret_cast<long long*>(indices), reinterpret_cast<__nv_bfloat16*>(q_bf16),
+      x, M, D, x_pitch, codebook, K, reinterpret_cast<long long*>(indices), reinterpret_cast<h16*>(q_h16),
       q_pitch, q_f32, ste, sqerr_sum, hist);
   B200_LAUNCH_CHECK("vq_argmin_kernel");
   return B200_OK;
 }
 
 extern "C" int b200_vq_gather(const int64_t* indices, int64_t M, const float* codebook, int32_t K, int32_t D,
-                              void* q_bf16, int32_t q_pitch, void* stream_v) {
+                              void* q_h16, int32_t q_pitch, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  B200_CHECK_ARG(indices && codebook && q_bf16 && M >= 1 && q_pitch >= D, "vq_gather: bad arguments");
+  B200_CHECK_ARG(indices && codebook && q_h16 && M >= 1 && q_pitch >= D, "vq_gather: bad arguments");
   long long blocks = (M * q_pitch + 255) / 256;
   const long long cap = 8ll * sm_count();
   if (blocks > cap) blocks = cap;
   vq_gather_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const long long*>(indices), M, codebook, K, D,
-                                                         reinterpret_cast<__nv_bfloat16*>(q_bf16), q_pitch);
+                                                         reinterpret_cast<h16*>(q_h16), q_pitch);
   B200_LAUNCH_CHECK("vq_gather_kernel");
   return B200_OK;
 }

@@ -2,7 +2,7 @@
 
 The modules keep the reference's module tree and ``state_dict`` keys by holding their parameters in
 ordinary ``torch.nn`` layers that are never *called*: ``forward`` hands the weights — repacked once into the K-major
-bf16 layout the tcgen05 kernel wants and cached against the parameter's version — to the C-ABI operators.
+h16 layout the tcgen05 kernel wants and cached against the parameter's version — to the C-ABI operators.
 """
 from __future__ import annotations
 

@@ -45,7 +45,7 @@ class EMAQuantizer(nn.Module):
     # ---------------------------------------------------------------- CUDA path (eval)
     def quantize_cl(self, z: torch.Tensor, want_f32: bool = True, ste: bool = True) -> dict:
         """``z``: fp32 channels-last ``[N, D, H, W, pitch]`` encoder output.  Returns indices ``[N, D, H, W]``,
-        the gathered rows as a bf16 :class:`CL` (decoder input) and fp32 channels-last, the commitment loss and the
+        the gathered rows as a h16 :class:`CL` (decoder input) and fp32 channels-last, the commitment loss and the
         code histogram."""
         lib = _lib.require_device()
         N, D, H, W, P = z.shape
@@ -158,7 +158,7 @@ class VectorQuantizer(torch.nn.Module):
         return loss, quantized
 
     def forward_cl(self, z: torch.Tensor, want_f32: bool) -> dict:
-        """Channels-last fast path used by VQVAE (fp32 encoder output in, bf16 decoder input out)."""
+        """Channels-last fast path used by VQVAE (fp32 encoder output in, h16 decoder input out)."""
         r = self.quantizer.quantize_cl(z, want_f32=want_f32)
         self.perplexity = self._perplexity_from_hist(r["hist"], r["count"])
         return r

@@ -1,7 +1,7 @@
 """DiffusionModelUNet on the B200 kernels — same classes, constructor arguments, attribute names and ``state_dict``
 keys as generative/networks/nets/diffusion_model_unet.py (reference lines cited per class), different insides:
 
-* activations stay channels-last bf16 (:class:`~generativemodels_b200.ops.CL`) from ``conv_in`` to the output head;
+* activations stay channels-last h16 (:class:`~generativemodels_b200.ops.CL`) from ``conv_in`` to the output head;
 * every ResnetBlock is  GN-stats -> GN-apply+SiLU -> tcgen05 conv (+bias +time-embedding row vector in the epilogue)
   -> GN -> tcgen05 conv (+bias +skip/residual in the epilogue);
 * the up path never materialises ``torch.cat([h, skip])`` raw: GroupNorm and the 1x1 skip conv read both tensors;

@@ -32,7 +32,7 @@ class AbsolutePositionalEmbedding(nn.Module):
 
 
 class _Cache:
-    """Keys / values of the tokens processed so far, per layer: bf16 [B, max_seq_len, pitch]; cross-attention keys
+    """Keys / values of the tokens processed so far, per layer: h16 [B, max_seq_len, pitch]; cross-attention keys
     and values of the conditioning are projected once."""
 
     def __init__(self, model: "DecoderOnlyTransformer", batch: int, device, context: torch.Tensor | None,
@@ -46,7 +46,7 @@ class _Cache:
         self.static_logits = None
         self.dyn_steps = 0
         P = ops.round_up(model.attn_layers_dim, 8)
-        mk = lambda: torch.zeros((batch, model.max_seq_len, P), dtype=torch.bfloat16, device=device)
+        mk = lambda: torch.zeros((batch, model.max_seq_len, P), dtype=ops.H16, device=device)
         self.k = [mk() for _ in model.blocks]
         self.v = [mk() for _ in model.blocks]
         self.length = 0

@@ -1,7 +1,7 @@
 """Host-side operators: thin, allocation-only wrappers that turn torch tensors into C-ABI calls.
 
 PyTorch here is plumbing (device memory, streams, RNG); every FLOP of the sampling path runs in libb200gen.so.
-Internal activation format: :class:`CL` — channels-last bf16 ``[N, D, H, W, pitch]`` (2-D images have D == 1),
+Internal activation format: :class:`CL` — channels-last h16 ``[N, D, H, W, pitch]`` (2-D images have D == 1),
 ``pitch`` = channels rounded up to 8 (the 16-byte TMA stride granule).
 """
 from __future__ import annotations
@@ -14,8 +14,11 @@ from typing import Sequence
 import torch
 
 from . import _lib
-from ._lib import (ACT_GELU, ACT_LEAKYRELU, ACT_NONE, ACT_RELU, ACT_SILU, DT_BF16, DT_F32, DdimCoef, DdpmCoef, GnApplyParams, GnStatsParams,
+from ._lib import (ACT_GELU, ACT_LEAKYRELU, ACT_NONE, ACT_RELU, ACT_SILU, DT_H16, DT_F32, DdimCoef, DdpmCoef, GnApplyParams, GnStatsParams,
                    IgemmParams, PndmCoef, check)
+
+# torch dtype of the library's 16-bit storage type (fp16 unless B200_ACT_DTYPE=h16; see _lib.ACT_DTYPE)
+H16 = torch.float16 if _lib.ACT_DTYPE == "fp16" else torch.bfloat16
 
 __all__ = ["CL", "to_cl", "from_cl", "PackedConv", "PackedConvTranspose", "PackedLinear", "conv", "conv_transpose",
            "linear", "groupnorm", "layernorm", "upsample_nearest2x", "avgpool2", "axpy", "geglu", "attention",
@@ -36,7 +39,7 @@ def round_up(x: int, m: int) -> int:
 
 @dataclass
 class CL:
-    """Channels-last bf16 activation: ``t`` is ``[N, D, H, W, pitch]`` contiguous, ``C`` valid channels."""
+    """Channels-last h16 activation: ``t`` is ``[N, D, H, W, pitch]`` contiguous, ``C`` valid channels."""
     t: torch.Tensor
     C: int
     spatial_dims: int = 2
@@ -59,12 +62,12 @@ class CL:
     def like(self, C_: int | None = None, dims: Sequence[int] | None = None) -> "CL":
         C_ = self.C if C_ is None else C_
         d = (self.D, self.H, self.W) if dims is None else tuple(dims)
-        t = torch.empty((self.N, *d, round_up(C_, 8)), dtype=torch.bfloat16, device=self.t.device)
+        t = torch.empty((self.N, *d, round_up(C_, 8)), dtype=H16, device=self.t.device)
         return CL(t, C_, self.spatial_dims)
 
 
 def new_cl(N: int, dims: Sequence[int], C_: int, device, spatial_dims: int) -> CL:
-    t = torch.empty((N, *dims, round_up(C_, 8)), dtype=torch.bfloat16, device=device)
+    t = torch.empty((N, *dims, round_up(C_, 8)), dtype=H16, device=device)
     return CL(t, C_, spatial_dims)
 
 
@@ -72,7 +75,7 @@ def new_cl(N: int, dims: Sequence[int], C_: int, device, spatial_dims: int) -> C
 # API-edge layout conversion
 # --------------------------------------------------------------------------------------------------
 def to_cl(x: torch.Tensor) -> CL:
-    """NC[D]HW float tensor -> channels-last bf16 (pad channels zero)."""
+    """NC[D]HW float tensor -> channels-last h16 (pad channels zero)."""
     lib = _lib.require_device()
     if x.dim() not in (4, 5):
         raise ValueError(f"expected a 4-D or 5-D NC[D]HW tensor, got shape {tuple(x.shape)}")
@@ -90,7 +93,7 @@ def from_cl(a: CL, dtype=torch.float32) -> torch.Tensor:
     lib = _lib.require_device()
     shape = (a.N, a.C, a.H, a.W) if a.spatial_dims == 2 else (a.N, a.C, a.D, a.H, a.W)
     y = torch.empty(shape, dtype=torch.float32, device=a.t.device)
-    check(lib.b200_nhwc_to_nchw(a.t.data_ptr(), DT_BF16, a.N, a.C, a.spatial, a.pitch, y.data_ptr(), _stream()),
+    check(lib.b200_nhwc_to_nchw(a.t.data_ptr(), DT_H16, a.N, a.C, a.spatial, a.pitch, y.data_ptr(), _stream()),
           "b200_nhwc_to_nchw")
     return y if dtype == torch.float32 else y.to(dtype)
 
@@ -109,7 +112,7 @@ def from_cl_f32(t: torch.Tensor, C_: int, spatial_dims: int) -> torch.Tensor:
 # weight packing (one-time, cached by the modules; not on the per-step path)
 # --------------------------------------------------------------------------------------------------
 def _pack_taps(blocks: list[torch.Tensor], rows: int) -> torch.Tensor:
-    """blocks: list of [Cout, Cs] fp32 matrices -> bf16 [rows_pad, sum ceil64(Cs)] K-major."""
+    """blocks: list of [Cout, Cs] fp32 matrices -> h16 [rows_pad, sum ceil64(Cs)] K-major."""
     cols = []
     for b in blocks:
         cs = b.shape[1]
@@ -119,11 +122,11 @@ def _pack_taps(blocks: list[torch.Tensor], rows: int) -> torch.Tensor:
     rpad = round_up(rows, 16) - rows
     if rpad:
         w = torch.nn.functional.pad(w, (0, 0, 0, rpad))
-    return w.to(torch.bfloat16).contiguous()
+    return w.to(H16).contiguous()
 
 
 class PackedConv:
-    """K-major bf16 weight matrix + tap table for one nn.Conv{2,3}d.
+    """K-major h16 weight matrix + tap table for one nn.Conv{2,3}d.
 
     ``splits`` are the channel counts of the (up to two) input tensors the conv reads — the virtual concat of
     the UNet up path.  ``padding`` is ``(lo, hi)`` per spatial dim (asymmetric for the AutoencoderKL downsampler,
@@ -187,7 +190,7 @@ class PackedConv:
 
 
 class PackedLinear:
-    """nn.Linear weight [O, K] -> K-major bf16 (already K-major; only padded and cast)."""
+    """nn.Linear weight [O, K] -> K-major h16 (already K-major; only padded and cast)."""
 
     def __init__(self, weight: torch.Tensor, bias: torch.Tensor | None):
         w = weight.detach().float()
@@ -292,8 +295,8 @@ def conv_upsample2x(src: CL, pu: PackedUpsampleConv, impl: int = 0) -> CL:
     for i, (r, w, segs) in enumerate(pu.phases):
         off = r[0] * full[1] + r[1] * full[2] + r[2] * full[3]
         strides = (full[0], full[1] * sdd, full[2] * 2, full[3] * 2)
-        p = _conv_params([src], w, segs, (1, 1, 1), out.t, (src.D, src.H, src.W), pu.cout, DT_BF16, pu.bias, None,
-                         ACT_NONE, 1.0, None, DT_BF16, ACT_NONE, out_elem_off=off, out_strides=strides, impl=impl)
+        p = _conv_params([src], w, segs, (1, 1, 1), out.t, (src.D, src.H, src.W), pu.cout, DT_H16, pu.bias, None,
+                         ACT_NONE, 1.0, None, DT_H16, ACT_NONE, out_elem_off=off, out_strides=strides, impl=impl)
         if part is not None:          # every phase launch owns its own range of slots
             p.gn_partial, p.gn_slots, p.gn_slot0 = part.data_ptr(), part.shape[1], i * _gn_slots()
         igemm_raw(p)
@@ -315,7 +318,7 @@ def _gn_slots(launches: int = 1) -> int:
 
 def _gn_partial_for(out: CL, rows: int, n_seg: int, launches: int = 1) -> torch.Tensor | None:
     """Zero-filled partial-sum buffer if this output is worth instrumenting: a heavy (>= 8 tap) convolution writing a
-    large bf16 tensor whose channel count tiles the 32-column epilogue chunks."""
+    large h16 tensor whose channel count tiles the 32-column epilogue chunks."""
     if not _GN_FUSE or rows < _GN_FUSE_MIN_ROWS or n_seg < 8 or out.C % 32 != 0 or out.pitch != out.C:
         return None
     out.gn = torch.zeros((out.N, _gn_slots(launches), out.C // 8, 2), dtype=torch.float32, device=out.t.device)
@@ -384,7 +387,7 @@ def _conv_params(srcs: Sequence[CL], w: torch.Tensor, segs, stride, out_t: torch
         p.a_pitch[i] = a.pitch
     p.in_N, p.in_D, p.in_H, p.in_W = a0.N, a0.D, a0.H, a0.W
     p.stride_d, p.stride_h, p.stride_w = stride
-    esz = 2 if out_dtype == DT_BF16 else 4
+    esz = 2 if out_dtype == DT_H16 else 4
     p.out_ptr = out_t.data_ptr() + out_elem_off * esz
     p.out_dtype = out_dtype
     p.out_N = a0.N
@@ -401,7 +404,7 @@ def _conv_params(srcs: Sequence[CL], w: torch.Tensor, segs, stride, out_t: torch
         p.rowvec_bstride = rowvec.stride(0) if rowvec.shape[0] > 1 else 0
     p.act1, p.scale, p.act2 = act1, scale, act2
     if res is not None:
-        p.res_ptr = res.data_ptr() + (out_elem_off * (2 if res_dtype == DT_BF16 else 4))
+        p.res_ptr = res.data_ptr() + (out_elem_off * (2 if res_dtype == DT_H16 else 4))
         p.res_dtype = res_dtype
         if res_strides is None:
             RP = res.shape[-1]
@@ -417,7 +420,7 @@ def conv(srcs: CL | Sequence[CL], pc: PackedConv, *, rowvec: torch.Tensor | None
          impl: int = 0) -> CL | torch.Tensor:
     """Fused convolution: act2(residual + scale * act1(conv(cat(srcs)) + bias + rowvec[n])).
 
-    Returns a :class:`CL` (bf16) or, with ``out_f32``, an fp32 channels-last tensor ``[N, D, H, W, round_up(C, 4)]``.
+    Returns a :class:`CL` (h16) or, with ``out_f32``, an fp32 channels-last tensor ``[N, D, H, W, round_up(C, 4)]``.
     """
     if isinstance(srcs, CL):
         srcs = [srcs]
@@ -437,17 +440,17 @@ def conv(srcs: CL | Sequence[CL], pc: PackedConv, *, rowvec: torch.Tensor | None
         raise ValueError("residual shape mismatch")
     rows = a0.N * od[0] * od[1] * od[2]
     if impl == 0 and rows >= _TAP_MIN_ROWS and pc.tap_in is not None:
-        # conv_in-like: im2col of the few input channels (one bf16 row of <= 64 values per output voxel), then the
+        # conv_in-like: im2col of the few input channels (one h16 row of <= 64 values per output voxel), then the
         # ordinary fused GEMM epilogue
         lib = _lib.require_device()
         Kp = round_up(pc.tap_in.K, 8)
-        x2 = torch.empty((a0.N, *od, Kp), dtype=torch.bfloat16, device=a0.t.device)
+        x2 = torch.empty((a0.N, *od, Kp), dtype=H16, device=a0.t.device)
         check(lib.b200_tap_gather(a0.t.data_ptr(), a0.C, a0.pitch, pc.geom(a0.N, a0.D, a0.H, a0.W), x2.data_ptr(), Kp,
                                   _stream()), "b200_tap_gather")
         pl = pc.tap_in
         p = _conv_params([CL(x2, pl.K, a0.spatial_dims)], pl.w, pl.segs, (1, 1, 1), out_t, od, pc.cout,
-                         DT_F32 if out_f32 else DT_BF16, pl.bias, rowvec, act1, scale,
-                         None if residual is None else residual.t, DT_BF16, act2)
+                         DT_F32 if out_f32 else DT_H16, pl.bias, rowvec, act1, scale,
+                         None if residual is None else residual.t, DT_H16, act2)
         igemm_raw(p)
         return out
     if (impl == 0 and rows >= _TAP_MIN_ROWS and pc.tap_out is not None and rowvec is None and residual is None
@@ -456,11 +459,11 @@ def conv(srcs: CL | Sequence[CL], pc: PackedConv, *, rowvec: torch.Tensor | None
         lib = _lib.require_device()
         y = linear(a0, pc.tap_out, out_f32=True)
         check(lib.b200_tap_sum(y.data_ptr(), y.shape[-1], pc.geom(a0.N, a0.D, a0.H, a0.W), pc.cout, _ptr(pc.bias),
-                               out_t.data_ptr(), out_t.shape[-1], DT_F32 if out_f32 else DT_BF16, _stream()),
+                               out_t.data_ptr(), out_t.shape[-1], DT_F32 if out_f32 else DT_H16, _stream()),
               "b200_tap_sum")
         return out
-    p = _conv_params(srcs, pc.w, pc.segs, pc.stride, out_t, od, pc.cout, DT_F32 if out_f32 else DT_BF16, pc.bias,
-                     rowvec, act1, scale, None if residual is None else residual.t, DT_BF16, act2, impl=impl)
+    p = _conv_params(srcs, pc.w, pc.segs, pc.stride, out_t, od, pc.cout, DT_F32 if out_f32 else DT_H16, pc.bias,
+                     rowvec, act1, scale, None if residual is None else residual.t, DT_H16, act2, impl=impl)
     if not out_f32:
         part = _gn_partial_for(out, rows, len(pc.segs))
         if part is not None:
@@ -480,14 +483,14 @@ def conv_transpose(src: CL, pt: PackedConvTranspose, *, act1: int = ACT_NONE, im
             continue
         off = r[0] * full[1] + r[1] * full[2] + r[2] * full[3]
         strides = (full[0], full[1] * pt.s[0], full[2] * pt.s[1], full[3] * pt.s[2])
-        p = _conv_params([src], w, segs, (1, 1, 1), out.t, cnt, pt.cout, DT_BF16, pt.bias, None, act1, 1.0, None,
-                         DT_BF16, ACT_NONE, out_elem_off=off, out_strides=strides, impl=impl)
+        p = _conv_params([src], w, segs, (1, 1, 1), out.t, cnt, pt.cout, DT_H16, pt.bias, None, act1, 1.0, None,
+                         DT_H16, ACT_NONE, out_elem_off=off, out_strides=strides, impl=impl)
         igemm_raw(p)
     return out
 
 
 def as_rows(t: torch.Tensor, C_: int) -> CL:
-    """View a bf16 [..., pitch] tensor as a token matrix CL [1, 1, 1, M, pitch]."""
+    """View a h16 [..., pitch] tensor as a token matrix CL [1, 1, 1, M, pitch]."""
     P = t.shape[-1]
     return CL(t.reshape(1, 1, 1, -1, P), C_, 2)
 
@@ -503,8 +506,8 @@ def linear(x: CL, pl: PackedLinear, *, residual: CL | None = None, act1: int = A
     else:
         out = x.like(pl.cout)
         out_t = out.t
-    p = _conv_params([x], pl.w, pl.segs, (1, 1, 1), out_t, (x.D, x.H, x.W), pl.cout, DT_F32 if out_f32 else DT_BF16,
-                     pl.bias, None, act1, 1.0, None if residual is None else residual.t, DT_BF16, ACT_NONE, impl=impl)
+    p = _conv_params([x], pl.w, pl.segs, (1, 1, 1), out_t, (x.D, x.H, x.W), pl.cout, DT_F32 if out_f32 else DT_H16,
+                     pl.bias, None, act1, 1.0, None if residual is None else residual.t, DT_H16, ACT_NONE, impl=impl)
     igemm_raw(p)
     return out
 
@@ -678,8 +681,8 @@ def axpy(a: CL, b: CL, alpha: float = 1.0, inplace: bool = False) -> CL:
         raise ValueError(f"axpy shape mismatch {tuple(a.t.shape)} vs {tuple(b.t.shape)}")
     out = a if inplace else a.like()
     out.gn = None
-    check(lib.b200_axpy_bf16(a.t.data_ptr(), b.t.data_ptr(), alpha, out.t.data_ptr(), a.t.numel(), _stream()),
-          "b200_axpy_bf16")
+    check(lib.b200_axpy_h16(a.t.data_ptr(), b.t.data_ptr(), alpha, out.t.data_ptr(), a.t.numel(), _stream()),
+          "b200_axpy_h16")
     return out
 
 
@@ -766,20 +769,20 @@ _ATTN_CHUNK_BYTES = 6 << 30   # fp32 score slab per query chunk
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, dh: int, scale: float,
               vt: torch.Tensor | None = None, residual: torch.Tensor | None = None) -> torch.Tensor:
-    """softmax(scale * Q K^T) V on packed [B, T, pitch] bf16 rows (heads are channel slices).
+    """softmax(scale * Q K^T) V on packed [B, T, pitch] h16 rows (heads are channel slices).
 
     Tensor-core paths (head_dim % 64 == 0, S >= 64; ``vt`` must hold V^T ``[B, H*dh, S_pitch]``, produced for free
     by swapping the operands of the V projection):
       * head_dim in {64, 128, 256, 512}: the flash-style tcgen05 kernel — scores stay in TMEM, online softmax;
       * other multiples of 64 (e.g. 768): per (batch, head) QK^T -> fp32 scores (+ softmax partials from the GEMM
-        epilogue), one-pass row softmax -> bf16, PV, in query slabs so the score matrix never exceeds a few GB.
-    Everything else runs on the CUDA-core online-softmax kernel.  ``residual`` ([B, T, pitch] bf16) is added in
+        epilogue), one-pass row softmax -> h16, PV, in query slabs so the score matrix never exceeds a few GB.
+    Everything else runs on the CUDA-core online-softmax kernel.  ``residual`` ([B, T, pitch] h16) is added in
     the PV epilogue on the tensor-core path only (callers add it themselves otherwise).
     """
     lib = _lib.require_device()
     B, T, qp = q.shape
     S = k.shape[1]
-    out = torch.empty((B, T, round_up(heads * dh, 8)), dtype=torch.bfloat16, device=q.device)
+    out = torch.empty((B, T, round_up(heads * dh, 8)), dtype=H16, device=q.device)
     use_tc = (dh % 64 == 0) and S >= _TC_ATTN_MIN_S and vt is not None
     if not use_tc:
         if residual is not None:
@@ -814,7 +817,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, dh:
     Sp = round_up(S, 8)
     chunk = max(128, min(T, (_ATTN_CHUNK_BYTES // (4 * Sp)) // 128 * 128))
     scores = torch.empty((min(chunk, T), Sp), dtype=torch.float32, device=q.device)
-    probs = torch.empty((min(chunk, T), Sp), dtype=torch.bfloat16, device=q.device)
+    probs = torch.empty((min(chunk, T), Sp), dtype=H16, device=q.device)
     n_tiles = (Sp + 255) // 256
     partials = torch.empty((min(chunk, T), n_tiles, 2), dtype=torch.float32, device=q.device)
     nk = round_up(dh, 64) // 64
@@ -852,21 +855,21 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, dh:
                 p2.w_rows, p2.w_pitch, p2.w_K = dh, vtp, S
                 _fill_segs(p2, [(0, 0, 0, 0, 0, ns)])
                 op = out.shape[2]
-                p2.out_ptr, p2.out_dtype = out.data_ptr() + ((b * T + t0) * op + h * dh) * 2, DT_BF16
+                p2.out_ptr, p2.out_dtype = out.data_ptr() + ((b * T + t0) * op + h * dh) * 2, DT_H16
                 p2.out_N, p2.out_D, p2.out_H, p2.out_W = 1, 1, 1, tc
                 p2.cout, p2.out_cols = dh, dh
                 p2.out_sN, p2.out_sD, p2.out_sH, p2.out_sW = tc * op, tc * op, tc * op, op
                 p2.act1, p2.scale, p2.act2 = ACT_NONE, 1.0, ACT_NONE
                 if residual is not None:
                     rp = residual.shape[2]
-                    p2.res_ptr, p2.res_dtype = residual.data_ptr() + ((b * T + t0) * rp + h * dh) * 2, DT_BF16
+                    p2.res_ptr, p2.res_dtype = residual.data_ptr() + ((b * T + t0) * rp + h * dh) * 2, DT_H16
                     p2.res_sN, p2.res_sD, p2.res_sH, p2.res_sW = tc * rp, tc * rp, tc * rp, rp
                 igemm_raw(p2)
     return out
 
 
 def linear_transposed(x: torch.Tensor, C_in: int, pl: PackedLinear) -> torch.Tensor:
-    """V^T = W x^T + b:  x is [B, S, pitch] bf16 rows; returns [B, O, round_up(S, 8)] bf16.
+    """V^T = W x^T + b:  x is [B, S, pitch] h16 rows; returns [B, O, round_up(S, 8)] h16.
 
     The projection weight plays the A operand (rows = output features) and the activations play the K-major
     "weight" operand, so the transposed value matrix costs no extra pass.
@@ -874,7 +877,7 @@ def linear_transposed(x: torch.Tensor, C_in: int, pl: PackedLinear) -> torch.Ten
     B, S, xp = x.shape
     O = pl.cout
     Sp = round_up(S, 8)
-    out = torch.empty((B, O, Sp), dtype=torch.bfloat16, device=x.device)
+    out = torch.empty((B, O, Sp), dtype=H16, device=x.device)
     if Sp > S:
         out.zero_()
     nk = round_up(C_in, 64) // 64
@@ -887,7 +890,7 @@ def linear_transposed(x: torch.Tensor, C_in: int, pl: PackedLinear) -> torch.Ten
         p.w_ptr = x.data_ptr() + b * S * xp * 2
         p.w_rows, p.w_pitch, p.w_K = S, xp, C_in
         _fill_segs(p, [(0, 0, 0, 0, 0, nk)])
-        p.out_ptr, p.out_dtype = out.data_ptr() + b * O * Sp * 2, DT_BF16
+        p.out_ptr, p.out_dtype = out.data_ptr() + b * O * Sp * 2, DT_H16
         p.out_N, p.out_D, p.out_H, p.out_W = 1, 1, 1, O
         p.cout, p.out_cols = S, Sp
         p.out_sN, p.out_sD, p.out_sH, p.out_sW = O * Sp, O * Sp, O * Sp, Sp
@@ -909,8 +912,8 @@ def linear_into_cache(x: CL, B: int, T: int, pl: PackedLinear, cache: torch.Tens
     if Bc != B or pos0 + T > L or P != round_up(pl.cout, 8):
         raise ValueError("key/value cache does not match the projection")
     xin = CL(x.t.reshape(B, 1, 1, T, x.pitch), x.C, 2)
-    p = _conv_params([xin], pl.w, pl.segs, (1, 1, 1), cache, (1, 1, T), pl.cout, DT_BF16, pl.bias, None, ACT_NONE, 1.0,
-                     None, DT_BF16, ACT_NONE, out_elem_off=pos0 * P, out_strides=(L * P, 0, 0, P))
+    p = _conv_params([xin], pl.w, pl.segs, (1, 1, 1), cache, (1, 1, T), pl.cout, DT_H16, pl.bias, None, ACT_NONE, 1.0,
+                     None, DT_H16, ACT_NONE, out_elem_off=pos0 * P, out_strides=(L * P, 0, 0, P))
     igemm_raw(p)
 
 
@@ -921,7 +924,7 @@ def attention_causal(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: i
     absolute position q_pos0 + t and, if causal, sees keys <= its position (blocks/selfattention.py:121-140)."""
     lib = _lib.require_device()
     B, T, qp = q.shape
-    out = torch.empty((B, T, round_up(heads * dh, 8)), dtype=torch.bfloat16, device=q.device)
+    out = torch.empty((B, T, round_up(heads * dh, 8)), dtype=H16, device=q.device)
     if out.shape[2] > heads * dh:
         out.zero_()
     check(lib.b200_attention_small_ex(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, T, S, heads, dh, qp,
@@ -932,20 +935,20 @@ def attention_causal(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: i
 
 def rows_linear(x: torch.Tensor, K: int, pl: PackedLinear, *, ln=None, act: int = ACT_NONE,
                 residual: torch.Tensor | None = None, out_f32: bool = False) -> torch.Tensor:
-    """Decode-time linear layer on M <= 8 bf16 rows ``x`` [M, pitch]: act(LN?(x) @ W^T + b) + residual, one GEMV
+    """Decode-time linear layer on M <= 8 h16 rows ``x`` [M, pitch]: act(LN?(x) @ W^T + b) + residual, one GEMV
     kernel (b200_rows_linear).  ``ln`` = (gamma, beta, eps) fuses the preceding LayerNorm."""
     lib = _lib.require_device()
     M = x.shape[0]
     if K != pl.K:
         raise ValueError(f"linear expects {pl.K} input features, got {K}")
-    out = torch.empty((M, round_up(pl.cout, 4 if out_f32 else 8)), dtype=torch.float32 if out_f32 else torch.bfloat16,
+    out = torch.empty((M, round_up(pl.cout, 4 if out_f32 else 8)), dtype=torch.float32 if out_f32 else H16,
                       device=x.device)
     if out.shape[1] > pl.cout:
         out.zero_()
     g, b, eps = (ln[0].data_ptr(), ln[1].data_ptr(), float(ln[2])) if ln is not None else (None, None, 0.0)
     check(lib.b200_rows_linear(x.data_ptr(), x.shape[1], M, K, g, b, eps, pl.w.data_ptr(), pl.w.shape[1], pl.cout,
                                _ptr(pl.bias), act, _ptr(residual), 0 if residual is None else residual.shape[1],
-                               out.data_ptr(), out.shape[1], DT_F32 if out_f32 else DT_BF16, _stream()),
+                               out.data_ptr(), out.shape[1], DT_F32 if out_f32 else DT_H16, _stream()),
           "b200_rows_linear")
     return out
 
@@ -956,7 +959,7 @@ def attention_decode(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: i
     (S = *pos_dev + 1 when ``pos_dev`` is given)."""
     lib = _lib.require_device()
     B = q.shape[0]
-    out = torch.empty((B, round_up(heads * dh, 8)), dtype=torch.bfloat16, device=q.device)
+    out = torch.empty((B, round_up(heads * dh, 8)), dtype=H16, device=q.device)
     if out.shape[1] > heads * dh:
         out.zero_()
     check(lib.b200_attention_decode(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, S, heads, dh,
@@ -984,7 +987,7 @@ def embed_tokens(tokens: torch.Tensor, tok_emb: torch.Tensor, pos_emb: torch.Ten
     B, T = tokens.shape
     C_ = tok_emb.shape[1]
     tk = tokens if (tokens.dtype == torch.int64 and tokens.is_contiguous()) else tokens.long().contiguous()
-    out = torch.empty((1, 1, 1, B * T, round_up(C_, 8)), dtype=torch.bfloat16, device=tokens.device)
+    out = torch.empty((1, 1, 1, B * T, round_up(C_, 8)), dtype=H16, device=tokens.device)
     check(lib.b200_embed_tokens(tk.data_ptr(), B * T, T, pos0, tok_emb.data_ptr(), pos_emb.data_ptr(), C_,
                                 out.data_ptr(), out.shape[-1], _ptr(pos_dev), _stream()), "b200_embed_tokens")
     return CL(out, C_, 2)

@@ -6,8 +6,8 @@
  *   - every entry point returns 0 on success or a negative B200_E* code; b200_last_error_string()
  *     gives the detail for the calling thread.  Nothing throws, exits, allocates device memory or
  *     synchronises the stream: all work is enqueued on `stream` (a cudaStream_t passed as void*).
- *   - activations are channels-last ("NDHWC") bf16 unless a dtype field says otherwise; a 2-D image
- *     is D == 1; a token matrix [M, C] is D == H == 1, W == M.  The channel pitch of every bf16
+ *   - activations are channels-last ("NDHWC") h16 unless a dtype field says otherwise; a 2-D image
+ *     is D == 1; a token matrix [M, C] is D == H == 1, W == M.  The channel pitch of every h16
  *     activation is a multiple of 8 elements (16 bytes, the TMA global-stride granule).
  *   - each function cites the reference code (file:line under /root/reference) whose arithmetic it
  *     replaces.  The Python host (generativemodels_b200/) binds these with ctypes.
@@ -27,8 +27,13 @@ extern "C" {
 #define B200_ECUDA    -3   /* CUDA runtime / driver error, see b200_last_error_string */
 #define B200_ENODEV   -4   /* device is not compute capability 10.x                   */
 
-#define B200_DT_BF16 0
+/* "h16" = the library's 16-bit storage type for activations and packed weights: IEEE fp16 in libb200gen.so (the
+ * default: 11 significand bits, fp32 -> fp16 conversions saturate at +-65504), bfloat16 in the libb200gen_bf16.so
+ * flavour built with -DB200_H16_IS_BF16.  b200_act_dtype() reports which one a loaded library computes in. */
+#define B200_DT_H16  0
 #define B200_DT_F32  1
+#define B200_H16_FP16 0
+#define B200_H16_BF16 1
 
 #define B200_ACT_NONE 0
 #define B200_ACT_RELU 1
@@ -40,6 +45,8 @@ extern "C" {
 
 const char* b200_last_error_string(void);
 int b200_version(void);
+/* B200_H16_FP16 or B200_H16_BF16: the 16-bit format this build stores activations / weights in. */
+int b200_act_dtype(void);
 /* 0 iff the current CUDA device is sm_100-class (fails loudly elsewhere: there is no fallback). */
 int b200_device_check(void);
 int b200_sm_count(void);
@@ -72,13 +79,13 @@ typedef struct {
 } b200_igemm_seg;
 
 typedef struct {
-  /* A: up to two bf16 NDHWC sources sharing N and the spatial extent */
+  /* A: up to two h16 NDHWC sources sharing N and the spatial extent */
   const void* a_ptr[2];
   int32_t a_C[2];      /* valid channels of each source                          */
   int32_t a_pitch[2];  /* elements between consecutive voxels (>= a_C, % 8 == 0) */
   int32_t in_N, in_D, in_H, in_W;
   int32_t stride_d, stride_h, stride_w;   /* conv stride (1 or 2)               */
-  /* W: bf16 [w_batch][w_rows][w_pitch], K-major, w_pitch % 64 == 0             */
+  /* W: h16 [w_batch][w_rows][w_pitch], K-major, w_pitch % 64 == 0             */
   const void* w_ptr;
   int32_t w_rows;       /* valid rows (>= cout)                                  */
   int32_t w_pitch;      /* elements per row                                      */
@@ -89,7 +96,7 @@ typedef struct {
   b200_igemm_seg seg[B200_IGEMM_MAX_SEG];
   /* output */
   void*   out_ptr;
-  int32_t out_dtype;    /* B200_DT_BF16 / B200_DT_F32                            */
+  int32_t out_dtype;    /* B200_DT_H16 / B200_DT_F32                            */
   int32_t out_N, out_D, out_H, out_W;
   int32_t cout;         /* valid output channels                                 */
   int32_t out_cols;     /* channels stored per voxel (>= cout; extras get 0)     */
@@ -110,9 +117,9 @@ typedef struct {
   int32_t impl;         /* 0 = tcgen05 kernel, 1 = CUDA-core cross-check kernel  */
   /* Optional GroupNorm partial sums for whoever normalises this output next (nn.GroupNorm after every conv of the
    * ResnetBlock, diffusion_model_unet.py:623-684): gn_partial[n][slot][cout/8][2] += (sum, sum of squares) of the
-   * stored bf16 values per 8-channel group; the kernel uses slots [gn_slot0, gn_slot0 + 4 * SM count) of the
+   * stored h16 values per 8-channel group; the kernel uses slots [gn_slot0, gn_slot0 + 4 * SM count) of the
    * gn_slots per sample, the caller zero-fills the buffer and b200_groupnorm_from_partials reduces it.
-   * Needs a bf16, 16-byte-aligned output with cout % 32 == 0.  NULL to skip. */
+   * Needs a h16, 16-byte-aligned output with cout % 32 == 0.  NULL to skip. */
   float*  gn_partial;
   int32_t gn_slots, gn_slot0;
   /* Optional split-K workspace.  A convolution on a small grid (the deep levels of a latent UNet: a few hundred
@@ -131,13 +138,13 @@ int b200_igemm(const b200_igemm_params* p, void* stream);
 int64_t b200_igemm_split_workspace_bytes(const b200_igemm_params* p);
 
 /* ------------------------------------------------------------------------------------------------
- * GroupNorm (+SiLU) on NDHWC bf16, optionally over the virtual concat of two tensors.
+ * GroupNorm (+SiLU) on NDHWC h16, optionally over the virtual concat of two tensors.
  * Replaces nn.GroupNorm + nn.SiLU in ResnetBlock / AttentionBlock / out head
  * (diffusion_model_unet.py:623-624,643,671,684, 372, 1853-1855; autoencoderkl.py:139-146,229).
  * Two phases: per-block partial sums -> per-(n,c) affine (a = rstd*gamma, b = beta - mean*a).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
-  const void* x_ptr[2];   /* bf16 NDHWC sources (second may be NULL)      */
+  const void* x_ptr[2];   /* h16 NDHWC sources (second may be NULL)      */
   int32_t x_C[2];         /* valid channels                               */
   int32_t x_pitch[2];     /* channel pitch                                */
   int32_t N;
@@ -166,7 +173,7 @@ typedef struct {
   int64_t spatial;
   const float* affine;    /* [N][C][2] from b200_groupnorm_stats          */
   int32_t act;            /* B200_ACT_NONE / B200_ACT_SILU                */
-  void*   y_ptr;          /* bf16 NDHWC, channel pitch y_pitch            */
+  void*   y_ptr;          /* h16 NDHWC, channel pitch y_pitch            */
   int32_t y_pitch;
 } b200_gn_apply_params;
 int b200_groupnorm_apply(const b200_gn_apply_params* p, void* stream);
@@ -182,22 +189,22 @@ int b200_groupnorm_fused(const b200_gn_stats_params* s, const b200_gn_apply_para
 /* SPADE modulation (generative/networks/blocks/spade_norm.py:78-96), one pass:
  *   y = act( (x * ax + bx) * (1 + (g * ag + bg)) + (t * at + bt) )
  * x = virtual concat of the sources in p (GroupNorm affine table p->affine from b200_groupnorm_stats), g / t = the
- * gamma / beta halves of gb ([rows][gb_pitch] bf16, channels [0,C) and [C,2C)) whose own per-(sample, channel)
+ * gamma / beta halves of gb ([rows][gb_pitch] h16, channels [0,C) and [C,2C)) whose own per-(sample, channel)
  * InstanceNorm table gb_affine is [N][2C][2] (monai's Convolution default norm on mlp_gamma / mlp_beta). */
 int b200_spade_apply(const b200_gn_apply_params* p, const void* gb, int32_t gb_pitch, const float* gb_affine,
                      void* stream);
-/* F.interpolate(mode="nearest", size=...) on NDHWC bf16: src index = min(floor(dst * in / out), in - 1) per axis. */
+/* F.interpolate(mode="nearest", size=...) on NDHWC h16: src index = min(floor(dst * in / out), in - 1) per axis. */
 int b200_resize_nearest(const void* x, int32_t N, int32_t D, int32_t H, int32_t W, int32_t pitch, void* y, int32_t OD,
                         int32_t OH, int32_t OW, void* stream);
 
-/* nn.LayerNorm over the last dim of a bf16 [M, C] matrix (diffusion_model_unet.py:221-223). */
+/* nn.LayerNorm over the last dim of a h16 [M, C] matrix (diffusion_model_unet.py:221-223). */
 int b200_layernorm(const void* x, int64_t M, int32_t C, int32_t x_pitch, const float* gamma,
                    const float* beta, float eps, void* y, int32_t y_pitch, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Layout / resampling / elementwise helpers on the API edge and between fused ops.
  * ---------------------------------------------------------------------------------------------- */
-/* NC[D]HW fp32 -> NDHWC bf16 (channel pitch `pitch`, pad channels zeroed) and back. */
+/* NC[D]HW fp32 -> NDHWC h16 (channel pitch `pitch`, pad channels zeroed) and back. */
 int b200_nchw_to_nhwc(const float* x, int32_t N, int32_t C, int64_t spatial, void* y, int32_t pitch,
                       void* stream);
 int b200_nhwc_to_nchw(const void* x, int32_t x_dtype, int32_t N, int32_t C, int64_t spatial,
@@ -208,10 +215,10 @@ int b200_upsample_nearest2x(const void* x, int32_t N, int32_t D, int32_t H, int3
 /* nn.AvgPool{2,3}d(kernel=2, stride=2) (diffusion_model_unet.py:522). */
 int b200_avgpool2(const void* x, int32_t N, int32_t D, int32_t H, int32_t W, int32_t pitch,
                   int32_t dims, void* y, void* stream);
-/* y = a + alpha * b on bf16 buffers of n elements (ControlNet residual adds,
+/* y = a + alpha * b on h16 buffers of n elements (ControlNet residual adds,
  * diffusion_model_unet.py:1917-1925,1931-1932; controlnet.py:405-407,433-434). */
-int b200_axpy_bf16(const void* a, const void* b, float alpha, void* y, int64_t n, void* stream);
-/* Copy C channels of every row of a channels-last bf16 tensor into columns [dst_off, dst_off + C) of another
+int b200_axpy_h16(const void* a, const void* b, float alpha, void* y, int64_t n, void* stream);
+/* Copy C channels of every row of a channels-last h16 tensor into columns [dst_off, dst_off + C) of another
  * (materialises torch.cat([a, b], dim=1) only where a raw concatenated tensor is really needed). */
 int b200_copy_channels(const void* src, int32_t C, int32_t src_pitch, void* dst, int32_t dst_pitch, int32_t dst_off,
                        int64_t rows, void* stream);
@@ -219,9 +226,9 @@ int b200_copy_channels(const void* src, int32_t C, int32_t src_pitch, void* dst,
  * input channel, .out[2] with one output channel; diffusion_model_unet.py:1744-1752, 1856-1867).
  * geom = {N, D, H, W, OD, OH, OW, kd, kh, kw, sd, sh, sw, pd, ph, pw} (input extent, output extent, kernel, stride,
  * low-side zero padding).
- * tap_gather: out[v][tap*C + c] = x[in_voxel(v, tap)][c] (zero outside the input), v over N*OD*OH*OW, bf16 rows.
+ * tap_gather: out[v][tap*C + c] = x[in_voxel(v, tap)][c] (zero outside the input), v over N*OD*OH*OW, h16 rows.
  * tap_sum:    out[v][co] = bias[co] + sum_tap y[v + off(tap)][tap*cout + co], y fp32 rows over the INPUT grid
- *             (stride 1, cout <= 4); out bf16 or fp32, columns [cout, out_pitch) zeroed. */
+ *             (stride 1, cout <= 4); out h16 or fp32, columns [cout, out_pitch) zeroed. */
 int b200_tap_gather(const void* x, int32_t C, int32_t x_pitch, const int32_t* geom, void* out, int32_t out_pitch,
                     void* stream);
 int b200_tap_sum(const float* y, int32_t y_pitch, const int32_t* geom, int32_t cout, const float* bias, void* out,
@@ -230,7 +237,7 @@ int b200_tap_sum(const float* y, int32_t y_pitch, const int32_t* geom, int32_t c
  * diffusion_model_unet.py:211). x: [M, 2H] pitch x_pitch; y: [M, H] pitch y_pitch. */
 int b200_geglu(const void* x, int64_t M, int32_t H, int32_t x_pitch, void* y, int32_t y_pitch,
                void* stream);
-/* softmax over rows of an fp32 [M, S] score matrix -> bf16 probabilities [M, p_pitch]
+/* softmax over rows of an fp32 [M, S] score matrix -> h16 probabilities [M, p_pitch]
  * (attention_scores.softmax(dim=-1), diffusion_model_unet.py:150,412). Pad columns are zeroed. */
 int b200_softmax_rows(const float* s, int64_t M, int32_t S, int64_t s_pitch, void* p, int64_t p_pitch,
                       void* stream);
@@ -239,8 +246,8 @@ int b200_softmax_rows_partials(const float* s, int64_t M, int32_t S, int64_t s_p
                                int32_t n_tiles, void* p, int64_t p_pitch, void* stream);
 
 /* Flash-style attention on tcgen05 (scores stay in TMEM; online softmax; head_dim in {64,128,256,512}, any T, S).
- * q: [B][T][q_pitch], k: [B][S][k_pitch] bf16 rows with heads as channel slices [h*dh, (h+1)*dh);
- * vt: V transposed, [B][heads*dh][vt_pitch] (key index contiguous); out / res: [B][T][pitch] bf16; res may be NULL.
+ * q: [B][T][q_pitch], k: [B][S][k_pitch] h16 rows with heads as channel slices [h*dh, (h+1)*dh);
+ * vt: V transposed, [B][heads*dh][vt_pitch] (key index contiguous); out / res: [B][T][pitch] h16; res may be NULL.
  * out[b,t,h*dh+c] = sum_s softmax_s(scale * q.k)[s] * v[s,c] (+ res).   (diffusion_model_unet.py:143-153, 406-416) */
 typedef struct {
   const void* q; const void* k; const void* vt; void* out; const void* res;
@@ -250,7 +257,7 @@ typedef struct {
   /* Optional device scratch for head_dim 512 (whose 128 x 512 fp32 output tile does not fit tensor memory beside the
    * scores): with at least b200_attention_flash_workspace_bytes() bytes the kernel computes every probability tile
    * once and replays it for the second half of the output channels; with NULL it recomputes the scores instead
-   * (same result up to bf16 rounding of identical P values, 1.5x the tensor work).  Other head dims ignore it. */
+   * (same result up to h16 rounding of identical P values, 1.5x the tensor work).  Other head dims ignore it. */
   void* workspace; int64_t workspace_bytes;
 } b200_flash_params;
 int b200_attention_flash(const b200_flash_params* p, void* stream);
@@ -259,7 +266,7 @@ int64_t b200_attention_flash_workspace_bytes(const b200_flash_params* p);
 
 /* Small-shape attention on CUDA cores (any head_dim <= 256, any S); used for the test-suite
  * head dims (2..8) and for cross-attention with a handful of context tokens.
- * q: [B, T, H*dh] bf16 pitch q_pitch; k, v: [B, S, H*dh]; out: [B, T, H*dh].
+ * q: [B, T, H*dh] h16 pitch q_pitch; k, v: [B, S, H*dh]; out: [B, T, H*dh].
  * (CrossAttention._attention, diffusion_model_unet.py:136-153; AttentionBlock 406-416.) */
 int b200_attention_small(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t T,
                          int32_t S, int32_t heads, int32_t dh, int32_t q_pitch, int32_t k_pitch,
@@ -274,25 +281,25 @@ int b200_attention_small_ex(const void* q, const void* k, const void* v, void* o
                             int32_t v_pitch, int32_t o_pitch, float scale, int32_t kv_rows, int32_t causal,
                             int32_t q_pos0, const int32_t* pos_dev, void* stream);
 /* Token + absolute position embedding rows (nets/transformer.py:20-37, 97-99):
- * out[m, :] = tok_emb[tokens[m], :] + pos_emb[pos0 + m % seq_len, :], bf16 rows of pitch `pitch`
+ * out[m, :] = tok_emb[tokens[m], :] + pos_emb[pos0 + m % seq_len, :], h16 rows of pitch `pitch`
  * (pos0 = *pos_dev when pos_dev != NULL). */
 int b200_embed_tokens(const int64_t* tokens, int64_t M, int32_t seq_len, int32_t pos0, const float* tok_emb,
                       const float* pos_emb, int32_t C, void* out, int32_t pitch, const int32_t* pos_dev, void* stream);
-/* Graph-captured decoding: append T rows per sequence to a [B, L, pitch] bf16 cache at the device-side position,
+/* Graph-captured decoding: append T rows per sequence to a [B, L, pitch] h16 cache at the device-side position,
  * and advance that position. */
 int b200_cache_append(const void* src, void* cache, int32_t B, int32_t T, int32_t L, int32_t pitch,
                       const int32_t* pos_dev, void* stream);
 int b200_advance_i32(int32_t* p, int32_t delta, void* stream);
 /* Decode-time linear layers (one new token per sequence: M <= 8 rows, HBM/L2-bound GEMVs):
  *   out[m, o] = act( LN?(x[m, :]) . w[o, :] + bias[o] ) + res[m, o]
- * x bf16 rows; ln_gamma / ln_beta (NULL = no LayerNorm; nn.LayerNorm semantics, output rounded to bf16 as the
- * stand-alone kernel does); w = the K-major bf16 matrix b200_igemm consumes (row pitch w_pitch, multiple of 8);
- * out bf16 or fp32 (out_dtype).  (blocks/transformerblock.py:87-92, blocks/selfattention.py:103-110, 145.) */
+ * x h16 rows; ln_gamma / ln_beta (NULL = no LayerNorm; nn.LayerNorm semantics, output rounded to h16 as the
+ * stand-alone kernel does); w = the K-major h16 matrix b200_igemm consumes (row pitch w_pitch, multiple of 8);
+ * out h16 or fp32 (out_dtype).  (blocks/transformerblock.py:87-92, blocks/selfattention.py:103-110, 145.) */
 int b200_rows_linear(const void* x, int32_t x_pitch, int32_t M, int32_t K, const float* ln_gamma,
                      const float* ln_beta, float ln_eps, const void* w, int32_t w_pitch, int32_t O, const float* bias,
                      int32_t act, const void* res, int32_t r_pitch, void* out, int32_t o_pitch, int32_t out_dtype,
                      void* stream);
-/* One query row per (batch, head) against S cached keys / values ([B, kv_rows, pitch] bf16; S = *pos_dev + 1 when
+/* One query row per (batch, head) against S cached keys / values ([B, kv_rows, pitch] h16; S = *pos_dev + 1 when
  * pos_dev != NULL): the keys are split over the warps of a block and the online-softmax states merged. */
 int b200_attention_decode(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t S,
                           int32_t heads, int32_t dh, int32_t q_pitch, int32_t k_pitch, int32_t v_pitch,
@@ -379,15 +386,15 @@ int b200_add_noise(const float* x0, const float* noise, const float* ca, const f
  * d = |x|^2 + |e|^2 - 2 x.e (fp32), first index wins ties; writes int64 indices and optionally the
  * gathered rows.  x: fp32 [M, D] (channels-last); codebook fp32 [K, D].
  * ---------------------------------------------------------------------------------------------- */
-/* Optional outputs (NULL to skip): q_bf16 rows (pitch q_pitch, pad zeroed) for the decoder; q_f32 [M, D] with the
+/* Optional outputs (NULL to skip): q_h16 rows (pitch q_pitch, pad zeroed) for the decoder; q_f32 [M, D] with the
  * straight-through rounding x + (q - x) when ste != 0 (vector_quantizer.py:186) else q; sqerr_sum += sum (q-x)^2
  * (commitment loss numerator, 183); hist[k] += count (perplexity, 212-218). */
 int b200_vq_argmin_gather(const float* x, int64_t M, int32_t D, int32_t x_pitch, const float* codebook,
-                          int32_t K, int64_t* indices, void* q_bf16, int32_t q_pitch, float* q_f32,
+                          int32_t K, int64_t* indices, void* q_h16, int32_t q_pitch, float* q_f32,
                           int32_t ste, double* sqerr_sum, int32_t* hist, void* stream);
-/* nn.Embedding gather for decode_samples (vqvae.py:445-450): idx int64 [M] -> bf16 rows. */
+/* nn.Embedding gather for decode_samples (vqvae.py:445-450): idx int64 [M] -> h16 rows. */
 int b200_vq_gather(const int64_t* indices, int64_t M, const float* codebook, int32_t K, int32_t D,
-                   void* q_bf16, int32_t q_pitch, void* stream);
+                   void* q_h16, int32_t q_pitch, void* stream);
 
 #ifdef __cplusplus
 }

@@ -31,7 +31,7 @@ def f32(ptr, count):
 
 def bf16(ptr, count):
     a = _np(ptr, count, C.c_uint16)
-    return None if a is None else torch.from_numpy(a.view(np.int16)).view(torch.bfloat16)
+    return None if a is None else torch.from_numpy(a.view(np.int16)).view(ops.H16)
 
 
 def i64(ptr, count):
@@ -59,11 +59,11 @@ class FakeLib:
         src = f32(x, N * C_ * sp).view(N, C_, sp)
         dst = bf16(y, N * sp * pitch).view(N, sp, pitch)
         dst.zero_()
-        dst[:, :, :C_] = src.transpose(1, 2).to(torch.bfloat16)
+        dst[:, :, :C_] = src.transpose(1, 2).to(ops.H16)
         return 0
 
     def b200_nhwc_to_nchw(self, x, dt, N, C_, sp, pitch, y, stream):
-        src = (bf16 if dt == _lib.DT_BF16 else f32)(x, N * sp * pitch).view(N, sp, pitch)
+        src = (bf16 if dt == _lib.DT_H16 else f32)(x, N * sp * pitch).view(N, sp, pitch)
         f32(y, N * C_ * sp).view(N, C_, sp).copy_(src[:, :, :C_].float().transpose(1, 2))
         return 0
 
@@ -136,13 +136,13 @@ class FakeLib:
         y = _act((x * ab[..., 0] + ab[..., 1]) * (1 + g[..., :Cc]) + g[..., Cc:], p.act)
         dst = bf16(p.y_ptr, N * S * p.y_pitch).view(N, S, p.y_pitch)
         dst.zero_()
-        dst[:, :, :Cc] = y.to(torch.bfloat16)
+        dst[:, :, :Cc] = y.to(ops.H16)
         return 0
 
     def b200_resize_nearest(self, x, N, D, H, W, pitch, y, OD, OH, OW, stream):
         src = bf16(x, N * D * H * W * pitch).view(N, D, H, W, pitch).float().permute(0, 4, 1, 2, 3)
         out = F.interpolate(src, size=(OD, OH, OW), mode="nearest").permute(0, 2, 3, 4, 1)
-        bf16(y, N * OD * OH * OW * pitch).view(N, OD, OH, OW, pitch).copy_(out.to(torch.bfloat16))
+        bf16(y, N * OD * OH * OW * pitch).view(N, OD, OH, OW, pitch).copy_(out.to(ops.H16))
         return 0
 
     def b200_groupnorm_apply(self, p, stream):
@@ -153,7 +153,7 @@ class FakeLib:
         y = _act(x * ab[..., 0] + ab[..., 1], p.act)
         dst = bf16(p.y_ptr, N * S * p.y_pitch).view(N, S, p.y_pitch)
         dst.zero_()
-        dst[:, :, :Cc] = y.to(torch.bfloat16)
+        dst[:, :, :Cc] = y.to(ops.H16)
         return 0
 
     def b200_layernorm(self, x, M, C_, xp, g, b, eps, y, yp, stream):
@@ -161,7 +161,7 @@ class FakeLib:
         out = F.layer_norm(src, (C_,), f32(g, C_), f32(b, C_), eps)
         dst = bf16(y, M * yp).view(M, yp)
         dst.zero_()
-        dst[:, :C_] = out.to(torch.bfloat16)
+        dst[:, :C_] = out.to(ops.H16)
         return 0
 
     def b200_upsample_nearest2x(self, x, N, D, H, W, pitch, dims, y, stream):
@@ -175,11 +175,11 @@ class FakeLib:
     def b200_avgpool2(self, x, N, D, H, W, pitch, dims, y, stream):
         src = bf16(x, N * D * H * W * pitch).view(N, D, H, W, pitch).float().permute(0, 4, 1, 2, 3)
         o = F.avg_pool3d(src, (2, 2, 2) if dims == 3 else (1, 2, 2)).permute(0, 2, 3, 4, 1).contiguous()
-        bf16(y, o.numel()).view(o.shape).copy_(o.to(torch.bfloat16))
+        bf16(y, o.numel()).view(o.shape).copy_(o.to(ops.H16))
         return 0
 
-    def b200_axpy_bf16(self, a, b, alpha, y, n, stream):
-        out = (bf16(a, n).float() + alpha * bf16(b, n).float()).to(torch.bfloat16)
+    def b200_axpy_h16(self, a, b, alpha, y, n, stream):
+        out = (bf16(a, n).float() + alpha * bf16(b, n).float()).to(ops.H16)
         bf16(y, n).copy_(out)
         return 0
 
@@ -198,7 +198,7 @@ class FakeLib:
             for b in range(kh):
                 for c in range(kw):
                     win = big[:, a:a + sd * OD:sd, b:b + sh * OH:sh, c:c + sw * OW:sw, :]
-                    dst[..., tap * C_:(tap + 1) * C_] = win.to(torch.bfloat16)
+                    dst[..., tap * C_:(tap + 1) * C_] = win.to(ops.H16)
                     tap += 1
         return 0
 
@@ -215,10 +215,10 @@ class FakeLib:
                 for c in range(kw):
                     acc += big[:, a:a + OD, b:b + OH, c:c + OW, tap * cout:(tap + 1) * cout]
                     tap += 1
-        if odt == _lib.DT_BF16:
+        if odt == _lib.DT_H16:
             dst = bf16(out, N * OD * OH * OW * op).view(N, OD, OH, OW, op)
             dst.zero_()
-            dst[..., :cout] = acc.to(torch.bfloat16)
+            dst[..., :cout] = acc.to(ops.H16)
         else:
             dst = f32(out, N * OD * OH * OW * op).view(N, OD, OH, OW, op)
             dst.zero_()
@@ -233,14 +233,14 @@ class FakeLib:
         src = bf16(x, M * xp).view(M, xp).float()
         out = src[:, :H] * F.gelu(src[:, H:2 * H])
         dst = bf16(y, M * yp).view(M, yp)
-        dst[:, :H] = out.to(torch.bfloat16)
+        dst[:, :H] = out.to(ops.H16)
         return 0
 
     def b200_softmax_rows(self, s, M, S, sp, p, pp, stream):
         sc = f32(s, M * sp).view(M, sp)[:, :S]
         dst = bf16(p, M * pp).view(M, pp)
         dst.zero_()
-        dst[:, :S] = torch.softmax(sc, -1).to(torch.bfloat16)
+        dst[:, :S] = torch.softmax(sc, -1).to(ops.H16)
         return 0
 
     def b200_softmax_rows_partials(self, s, M, S, sp, part, n_tiles, p, pp, stream):
@@ -250,7 +250,7 @@ class FakeLib:
         den = (pt[:, :, 1] * torch.exp(pt[:, :, 0] - mx[:, None])).nan_to_num(0.0).sum(1)
         dst = bf16(p, M * pp).view(M, pp)
         dst.zero_()
-        dst[:, :S] = (torch.exp(sc - mx[:, None]) / den[:, None]).to(torch.bfloat16)
+        dst[:, :S] = (torch.exp(sc - mx[:, None]) / den[:, None]).to(ops.H16)
         return 0
 
     def b200_sm_count(self):
@@ -273,7 +273,7 @@ class FakeLib:
         out = (torch.softmax(a.scale * qq @ kk.transpose(-1, -2), -1) @ vv).transpose(1, 2).reshape(B, T, Cc)
         if a.res:
             out = out + bf16(a.res, B * T * a.res_pitch).view(B, T, a.res_pitch)[:, :, :Cc].float()
-        bf16(a.out, B * T * a.out_pitch).view(B, T, a.out_pitch)[:, :, :Cc] = out.to(torch.bfloat16)
+        bf16(a.out, B * T * a.out_pitch).view(B, T, a.out_pitch)[:, :, :Cc] = out.to(ops.H16)
         return 0
 
     def b200_attention_small_ex(self, q, k, v, o, B, T, S, heads, dh, qp, kp, vp, op, scale, kv_rows, causal, q_pos0,
@@ -290,13 +290,13 @@ class FakeLib:
             allowed = torch.arange(S)[None, :] <= (q_pos0 + torch.arange(T))[:, None]
             sc = sc.masked_fill(~allowed, float("-inf"))
         out = (torch.softmax(sc, -1) @ vv).transpose(1, 2).reshape(B, T, Cc)
-        bf16(o, B * T * op).view(B, T, op)[:, :, :Cc] = out.to(torch.bfloat16)
+        bf16(o, B * T * op).view(B, T, op)[:, :, :Cc] = out.to(ops.H16)
         return 0
 
     def b200_rows_linear(self, x, xp, M, K, g, b, eps, w, wp, O, bias, act, res, rp, out, op, odt, stream):
         xs = bf16(x, M * xp).view(M, xp)[:, :K].float()
         if g:
-            xs = F.layer_norm(xs, (K,), f32(g, K), f32(b, K), eps).to(torch.bfloat16).float()
+            xs = F.layer_norm(xs, (K,), f32(g, K), f32(b, K), eps).to(ops.H16).float()
         W = bf16(w, O * wp).view(O, wp)[:, :K].float()
         y = xs @ W.t()
         if bias:
@@ -307,7 +307,7 @@ class FakeLib:
         if odt == _lib.DT_F32:
             f32(out, M * op).view(M, op)[:, :O] = y
         else:
-            bf16(out, M * op).view(M, op)[:, :O] = y.to(torch.bfloat16)
+            bf16(out, M * op).view(M, op)[:, :O] = y.to(ops.H16)
         return 0
 
     def b200_attention_decode(self, q, k, v, o, B, S, heads, dh, qp, kp, vp, op, scale, kv_rows, pos_dev, stream):
@@ -335,7 +335,7 @@ class FakeLib:
         pos = pos0 + torch.arange(M) % seq_len
         dst = bf16(out, M * pitch).view(M, pitch)
         dst.zero_()
-        dst[:, :C_] = (te[tk] + pe[pos]).to(torch.bfloat16)
+        dst[:, :C_] = (te[tk] + pe[pos]).to(ops.H16)
         return 0
 
     def b200_attention_small(self, q, k, v, o, B, T, S, heads, dh, qp, kp, vp, op, scale, stream):
@@ -344,7 +344,7 @@ class FakeLib:
         kk = bf16(k, B * S * kp).view(B, S, kp)[:, :, :Cc].float().view(B, S, heads, dh).transpose(1, 2)
         vv = bf16(v, B * S * vp).view(B, S, vp)[:, :, :Cc].float().view(B, S, heads, dh).transpose(1, 2)
         out = (torch.softmax(scale * qq @ kk.transpose(-1, -2), -1) @ vv).transpose(1, 2).reshape(B, T, Cc)
-        bf16(o, B * T * op).view(B, T, op)[:, :, :Cc] = out.to(torch.bfloat16)
+        bf16(o, B * T * op).view(B, T, op)[:, :, :Cc] = out.to(ops.H16)
         return 0
 
     def b200_timestep_embedding(self, t, N, dim, max_period, emb, stream):
@@ -475,7 +475,7 @@ class FakeLib:
         if q16:
             dst = bf16(q16, M * qp).view(M, qp)
             dst.zero_()
-            dst[:, :D] = qv.to(torch.bfloat16)
+            dst[:, :D] = qv.to(ops.H16)
         if q32:
             f32(q32, M * D).view(M, D).copy_(xx + (qv - xx) if ste else qv)
         if sq:
@@ -488,7 +488,7 @@ class FakeLib:
     def b200_vq_gather(self, idx, M, cb, K, D, q16, qp, stream):
         dst = bf16(q16, M * qp).view(M, qp)
         dst.zero_()
-        dst[:, :D] = f32(cb, K * D).view(K, D)[i64(idx, M)].to(torch.bfloat16)
+        dst[:, :D] = f32(cb, K * D).view(K, D)[i64(idx, M)].to(ops.H16)
         return 0
 
 

@@ -6,7 +6,7 @@ import ctypes as C
 
 import numpy as np
 
-from generativemodels_b200._lib import ACT_GELU, ACT_LEAKYRELU, ACT_RELU, ACT_SILU, DT_BF16, IgemmParams
+from generativemodels_b200._lib import ACT_DTYPE, ACT_GELU, ACT_LEAKYRELU, ACT_RELU, ACT_SILU, DT_H16, IgemmParams
 
 
 def _bf16_view(ptr, count):
@@ -14,14 +14,22 @@ def _bf16_view(ptr, count):
     return raw
 
 
-def _bf16_to_f32(u16):
-    return (u16.astype(np.uint32) << 16).view(np.float32)
+# the library's 16-bit storage type ("h16"): IEEE fp16 (saturating stores) unless B200_ACT_DTYPE=bf16
+if ACT_DTYPE == "fp16":
+    def _bf16_to_f32(u16):
+        return np.ascontiguousarray(u16).view(np.float16).astype(np.float32)
 
+    def _f32_to_bf16(x):
+        x = np.clip(np.ascontiguousarray(x, dtype=np.float32), -65504.0, 65504.0)
+        return x.astype(np.float16).view(np.uint16)
+else:
+    def _bf16_to_f32(u16):
+        return (u16.astype(np.uint32) << 16).view(np.float32)
 
-def _f32_to_bf16(x):
-    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
-    rounded = (u + 0x7FFF + ((u >> 16) & 1)) >> 16          # round to nearest even
-    return rounded.astype(np.uint16)
+    def _f32_to_bf16(x):
+        u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+        rounded = (u + 0x7FFF + ((u >> 16) & 1)) >> 16          # round to nearest even
+        return rounded.astype(np.uint16)
 
 
 def _f32_view(ptr, count):
@@ -120,7 +128,7 @@ def emulate(p: IgemmParams) -> None:
 
     if p.res_ptr:
         idx = strided_index(p.res_sN, p.res_sD, p.res_sH, p.res_sW)
-        if p.res_dtype == DT_BF16:
+        if p.res_dtype == DT_H16:
             r = _bf16_to_f32(_bf16_view(p.res_ptr, int(idx.max()) + 1)[idx])
         else:
             r = _f32_view(p.res_ptr, int(idx.max()) + 1)[idx]
@@ -128,7 +136,7 @@ def emulate(p: IgemmParams) -> None:
     v = _act(v, p.act2)
     v[..., ~valid] = 0
     idx = strided_index(p.out_sN, p.out_sD, p.out_sH, p.out_sW)
-    if p.out_dtype == DT_BF16:
+    if p.out_dtype == DT_H16:
         dst = _bf16_view(p.out_ptr, int(idx.max()) + 1)
         dst[idx] = _f32_to_bf16(v)
         if p.gn_partial:

@@ -29,7 +29,7 @@ def test_conv_fullres_tc_vs_crosscheck(cuda_device):
     torch.manual_seed(0)
     D, H, W = FULL
     C = 256
-    a = ops.CL((torch.randn(1, D, H, W, C, device="cuda") * 0.5).to(torch.bfloat16), C, 3)
+    a = ops.CL((torch.randn(1, D, H, W, C, device="cuda") * 0.5).to(ops.H16), C, 3)
     w = torch.randn(C, C, 3, 3, 3, device="cuda") / math.sqrt(C * 27)
     b = torch.randn(C, device="cuda")
     pc = ops.PackedConv(w, b, 1, 1)
@@ -56,9 +56,9 @@ def test_attention_full_length(cuda_device):
     T = S = FULL[0] // 4 * FULL[1] // 4 * FULL[2] // 4       # 89 600 tokens at the attention level
     assert T == 89600
     dh = 512
-    q = (torch.randn(1, T, dh, device="cuda") * 0.5).to(torch.bfloat16)
-    k = (torch.randn(1, S, dh, device="cuda") * 0.5).to(torch.bfloat16)
-    v = torch.randn(1, S, dh, device="cuda").to(torch.bfloat16)
+    q = (torch.randn(1, T, dh, device="cuda") * 0.5).to(ops.H16)
+    k = (torch.randn(1, S, dh, device="cuda") * 0.5).to(ops.H16)
+    v = torch.randn(1, S, dh, device="cuda").to(ops.H16)
     vt = v.transpose(1, 2).contiguous()
     scale = 1 / math.sqrt(dh)
     out = ops.attention(q, k, None, 1, dh, scale, vt=vt)
@@ -76,7 +76,7 @@ def test_attention_full_length(cuda_device):
     rel = ((got.float() - ref.float()).norm() / ref.float().norm()).item()
     assert rel < 2e-2, f"flash vs unfused at T = 89600: rel L2 {rel:.3e}"
     # (b) softmax rows sum to one: a constant value matrix must come back unchanged (up to bf16 rounding)
-    vc = torch.full((1, dh, S), 0.75, device="cuda", dtype=torch.bfloat16)
+    vc = torch.full((1, dh, S), 0.75, device="cuda", dtype=ops.H16)
     outc = ops.attention(q[:, :1024].contiguous(), k, None, 1, dh, scale, vt=vc)
     assert (outc.float() - 0.75).abs().max().item() < 1e-2
 
@@ -86,7 +86,7 @@ def test_groupnorm_full_resolution_statistics(cuda_device):
     torch.manual_seed(2)
     D, H, W = FULL
     C, G = 256, 32
-    x = ops.CL((torch.randn(1, D // 2, H, W, C, device="cuda") * 3 + 1.5).to(torch.bfloat16), C, 3)
+    x = ops.CL((torch.randn(1, D // 2, H, W, C, device="cuda") * 3 + 1.5).to(ops.H16), C, 3)
     y = ops.groupnorm(x, G, 1e-6, torch.ones(C, device="cuda"), torch.zeros(C, device="cuda")).t.float()
     g = y.view(-1, G, C // G)
     mean = g.mean(dim=(0, 2))

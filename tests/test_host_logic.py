@@ -18,7 +18,7 @@ def _emulated(monkeypatch):
 
 
 def bf(x):
-    return x.to(torch.bfloat16).float()
+    return x.to(ops.H16).float()
 
 
 def cl_cpu(x):
@@ -29,7 +29,7 @@ def cl_cpu(x):
         t = t.unsqueeze(1)
     C_ = x.shape[1]
     P = ops.round_up(C_, 8)
-    t = F.pad(t, (0, P - C_)).to(torch.bfloat16).contiguous()
+    t = F.pad(t, (0, P - C_)).to(ops.H16).contiguous()
     return ops.CL(t, C_, sd)
 
 
@@ -240,7 +240,7 @@ def test_attention_tc_host_logic(monkeypatch):
     monkeypatch.setattr(ops._lib, "require_device", lambda: FakeLib())
     monkeypatch.setattr(ops, "_stream", lambda: 0)
     monkeypatch.setattr(ops, "_FORCE_UNFUSED_ATTENTION", True)     # this test covers the GEMM + softmax + GEMM blocks
-    qb, kb, vb = (t.to(torch.bfloat16).contiguous() for t in (q, k, v))
+    qb, kb, vb = (t.to(ops.H16).contiguous() for t in (q, k, v))
     vt = F.pad(vb.transpose(1, 2), (0, ops.round_up(T, 8) - T)).contiguous()
     out = ops.attention(qb, kb, None, heads, dh, 1 / math.sqrt(dh), vt=vt)
     qh, kh, vh = (bf(t).view(B, T, heads, dh).transpose(1, 2) for t in (q, k, v))

@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 
 
 def bf(x):
-    return x.to(torch.bfloat16).float()
+    return x.to(ops.H16).float()
 
 
 def rel_err(a, b):
@@ -266,14 +266,14 @@ def test_split_k_linear_shapes(cuda_device, monkeypatch):
     M, K, O = 175, 3072, 768
     x, w, b, r = torch.randn(1, M, K), torch.randn(O, K) / math.sqrt(K), torch.randn(O), torch.randn(1, M, O)
     pl = ops.PackedLinear(w.cuda(), b.cuda())
-    xc = ops.as_rows(bf(x).cuda().to(torch.bfloat16), K)
-    rc = ops.as_rows(bf(r).cuda().to(torch.bfloat16), O)
+    xc = ops.as_rows(bf(x).cuda().to(ops.H16), K)
+    rc = ops.as_rows(bf(r).cuda().to(ops.H16), O)
     n0 = ops._SPLIT_LAUNCHES
     got = ops.linear(xc, pl, residual=rc)
     assert ops._SPLIT_LAUNCHES == n0 + 1
     ref = F.linear(bf(x), bf(w), b) + bf(r)
     assert_close(got.t.float().cpu().reshape(1, M, -1)[..., :O], ref, 1e-2, "split-K linear + residual")
-    xr = bf(torch.randn(2, 200, 1024)).cuda().to(torch.bfloat16)
+    xr = bf(torch.randn(2, 200, 1024)).cuda().to(ops.H16)
     w2, b2 = torch.randn(512, 1024) / math.sqrt(1024), torch.randn(512)
     pl2 = ops.PackedLinear(w2.cuda(), b2.cuda())
     vt = ops.linear_transposed(xr, 1024, pl2)                         # [B, O, S_pad]
@@ -443,7 +443,7 @@ def test_attention_small(cuda_device, B, T, S, heads, dh):
     P = (Cc + 7) // 8 * 8
     q, k, v = torch.randn(B, T, Cc), torch.randn(B, S, Cc), torch.randn(B, S, Cc)
     ref = _attn_ref(bf(q), bf(k), bf(v), heads, dh, 1 / math.sqrt(dh))
-    pad = lambda t: F.pad(t, (0, P - Cc)).to(torch.bfloat16).cuda().contiguous()
+    pad = lambda t: F.pad(t, (0, P - Cc)).to(ops.H16).cuda().contiguous()
     out = ops.attention(pad(q), pad(k), pad(v), heads, dh, 1 / math.sqrt(dh))
     assert_close(out[..., :Cc], ref, 1e-2, "attention_small")
 
@@ -464,7 +464,7 @@ def test_attention_tensorcore(cuda_device, B, T, heads, dh, unfused, monkeypatch
     xb = bf(x)
     q, k, v = F.linear(xb, bf(wq)), F.linear(xb, bf(wk)), F.linear(xb, bf(wv), bv)
     ref = _attn_ref(bf(q), bf(k), bf(v), heads, dh, 1 / math.sqrt(dh))
-    xc = ops.CL(x.to(torch.bfloat16).cuda().reshape(B, 1, 1, T, Cc), Cc, 2)
+    xc = ops.CL(x.to(ops.H16).cuda().reshape(B, 1, 1, T, Cc), Cc, 2)
     plq, plk = ops.PackedLinear(wq.cuda(), None), ops.PackedLinear(wk.cuda(), None)
     plv = ops.PackedLinear(wv.cuda(), bv.cuda())
     qg = ops.linear(xc, plq).t.reshape(B, T, -1)
@@ -472,7 +472,7 @@ def test_attention_tensorcore(cuda_device, B, T, heads, dh, unfused, monkeypatch
     vt = ops.linear_transposed(xc.t.reshape(B, T, Cc), Cc, plv)
     assert_close(vt[:, :, :T].transpose(1, 2), bf(v), 1e-2, "V^T projection")
     res = torch.randn(B, T, Cc)
-    out = ops.attention(qg, kg, None, heads, dh, 1 / math.sqrt(dh), vt=vt, residual=res.to(torch.bfloat16).cuda())
+    out = ops.attention(qg, kg, None, heads, dh, 1 / math.sqrt(dh), vt=vt, residual=res.to(ops.H16).cuda())
     assert_close(out[..., :Cc], ref + bf(res), 2e-2, "attention tensor-core")
 
 
@@ -490,8 +490,8 @@ def test_attention_flash_rescale(cuda_device, monkeypatch, dh, replay):
     v = torch.randn(B, S, dh)
     scale = 1 / math.sqrt(dh)
     ref = _attn_ref(bf(q), bf(k), bf(v), 1, dh, scale)
-    vt = v.to(torch.bfloat16).transpose(1, 2).contiguous().cuda()
-    out = ops.attention(q.to(torch.bfloat16).cuda(), k.to(torch.bfloat16).cuda(), None, 1, dh, scale, vt=vt)
+    vt = v.to(ops.H16).transpose(1, 2).contiguous().cuda()
+    out = ops.attention(q.to(ops.H16).cuda(), k.to(ops.H16).cuda(), None, 1, dh, scale, vt=vt)
     assert_close(out[..., :dh], ref, 2e-2, "flash attention with rescale")
 
 
@@ -504,9 +504,9 @@ def test_attention_flash_replay_matches_recompute(cuda_device, monkeypatch):
     B, T, S, dh = 2, 128 * 90 + 37, 1000 + 21, 512
     q, k, v = torch.randn(B, T, dh), torch.randn(B, S, dh), torch.randn(B, S, dh)
     k[:, 500:] *= 3.0                                     # a few late rescales in some rows
-    res = torch.randn(B, T, dh).to(torch.bfloat16).cuda()
-    args = (q.to(torch.bfloat16).cuda(), k.to(torch.bfloat16).cuda(), None, 1, dh, 1 / math.sqrt(dh))
-    vt = F.pad(v.to(torch.bfloat16).transpose(1, 2), (0, (-S) % 8)).contiguous().cuda()
+    res = torch.randn(B, T, dh).to(ops.H16).cuda()
+    args = (q.to(ops.H16).cuda(), k.to(ops.H16).cuda(), None, 1, dh, 1 / math.sqrt(dh))
+    vt = F.pad(v.to(ops.H16).transpose(1, 2), (0, (-S) % 8)).contiguous().cuda()
     monkeypatch.setattr(ops, "_FLASH_REPLAY", True)
     a = ops.attention(*args, vt=vt, residual=res).float().cpu()
     monkeypatch.setattr(ops, "_FLASH_REPLAY", False)
@@ -535,7 +535,7 @@ def test_attention_causal_and_cache(cuda_device, B, T, S, heads, dh, q_pos0, cau
         allowed = torch.arange(S)[None, :] <= (q_pos0 + torch.arange(T))[:, None]
         sc = sc.masked_fill(~allowed, float("-inf"))
     ref = (torch.softmax(sc, -1) @ vh).transpose(1, 2).reshape(B, T, Cc)
-    g = lambda t: t.to(torch.bfloat16).cuda().contiguous()
+    g = lambda t: t.to(ops.H16).cuda().contiguous()
     out = ops.attention_causal(g(q), g(k), g(v), heads, dh, 1 / math.sqrt(dh), S, causal=causal, q_pos0=q_pos0)
     assert_close(out[..., :Cc], ref, 1e-2, "causal attention over a cache")
 
@@ -556,7 +556,7 @@ def test_embed_tokens_gelu_and_cache_projection(cuda_device):
     pl = ops.PackedLinear(w.cuda(), b.cuda())
     y = ops.linear(e, pl, act1=ops.ACT_GELU)
     assert_close(y.t.reshape(B * T, -1)[:, :64], F.gelu(F.linear(bf(want).reshape(B * T, C_), bf(w), b)), 1e-2, "GELU epilogue")
-    cache = torch.zeros(B, L, 64, dtype=torch.bfloat16, device="cuda")
+    cache = torch.zeros(B, L, 64, dtype=ops.H16, device="cuda")
     ops.linear_into_cache(e, B, T, pl, cache, 6)
     lin = F.linear(bf(want), bf(w), b)
     assert_close(cache[:, 6:6 + T], lin, 1e-2, "projection into the cache")
@@ -581,11 +581,11 @@ def test_rows_linear(cuda_device, M, K, O, ln, act, res, f32out):
     if res:
         ref = ref + bf(r)
     P = (K + 7) // 8 * 8
-    xg = F.pad(x, (0, P - K)).to(torch.bfloat16).cuda()
+    xg = F.pad(x, (0, P - K)).to(ops.H16).cuda()
     pl = ops.PackedLinear(w.cuda(), b.cuda())
-    rg = F.pad(r, (0, (-O) % 8)).to(torch.bfloat16).cuda() if res else None
+    rg = F.pad(r, (0, (-O) % 8)).to(ops.H16).cuda() if res else None
     out = ops.rows_linear(xg, K, pl, ln=(g.cuda(), be.cuda(), 1e-5) if ln else None, act=act, residual=rg, out_f32=f32out)
-    assert out.dtype == (torch.float32 if f32out else torch.bfloat16)
+    assert out.dtype == (torch.float32 if f32out else ops.H16)
     assert_close(out[:, :O], ref, 1e-2, "rows_linear")
 
 
@@ -598,7 +598,7 @@ def test_attention_decode(cuda_device, B, S, heads, dh):
     rows = S + 3
     q, k, v = torch.randn(B, Cc), torch.randn(B, rows, Cc), torch.randn(B, rows, Cc)
     ref = _attn_ref(bf(q)[:, None], bf(k)[:, :S], bf(v)[:, :S], heads, dh, 1 / math.sqrt(dh))[:, 0]
-    g = lambda t: t.to(torch.bfloat16).cuda().contiguous()
+    g = lambda t: t.to(ops.H16).cuda().contiguous()
     out = ops.attention_decode(g(q), g(k), g(v), heads, dh, 1 / math.sqrt(dh), S)
     assert_close(out[:, :Cc], ref, 1e-2, "attention_decode")
     pos = torch.tensor([S - 1], dtype=torch.int32).cuda()

@@ -308,7 +308,7 @@ def test_spade_golden_cpu():
 
 def ops_cl(x, C_):
     from generativemodels_b200 import ops
-    return ops.CL(torch.zeros(x.shape[0], 1, x.shape[2], x.shape[3], C_, dtype=torch.bfloat16), C_, 2)
+    return ops.CL(torch.zeros(x.shape[0], 1, x.shape[2], x.shape[3], C_, dtype=ops.H16), C_, 2)
 
 
 def _transformer_pair(cross=False, max_seq_len=16, tokens=11):

@@ -11,9 +11,9 @@ from generativemodels_b200 import ops
 T = S = 89600
 dh = 512
 torch.manual_seed(0)
-q = (torch.randn(1, T, dh, device="cuda") * 0.5).to(torch.bfloat16)
-k = (torch.randn(1, S, dh, device="cuda") * 0.5).to(torch.bfloat16)
-vt = torch.randn(1, dh, S, device="cuda").to(torch.bfloat16)
+q = (torch.randn(1, T, dh, device="cuda") * 0.5).to(ops.H16)
+k = (torch.randn(1, S, dh, device="cuda") * 0.5).to(ops.H16)
+vt = torch.randn(1, dh, S, device="cuda").to(ops.H16)
 modes = [("replay", True), ("recompute", False)] if len(sys.argv) < 2 else [(sys.argv[1], sys.argv[1] == "replay")]
 for name, flag in modes:
     ops._FLASH_REPLAY = flag

@@ -11,9 +11,9 @@ ops._KEEP_FLASH_WS = True
 T = S = 89600
 dh = 512
 torch.manual_seed(0)
-q = (torch.randn(1, T, dh, device="cuda") * 0.5).to(torch.bfloat16)
-k = (torch.randn(1, S, dh, device="cuda") * 0.5).to(torch.bfloat16)
-vt = torch.randn(1, dh, S, device="cuda").to(torch.bfloat16)
+q = (torch.randn(1, T, dh, device="cuda") * 0.5).to(ops.H16)
+k = (torch.randn(1, S, dh, device="cuda") * 0.5).to(ops.H16)
+vt = torch.randn(1, dh, S, device="cuda").to(ops.H16)
 for i in range(2):
     o = ops.attention(q, k, None, 1, dh, 1 / math.sqrt(dh), vt=vt)
     torch.cuda.synchronize()
