@@ -180,3 +180,39 @@ C2_UNET = dict(spatial_dims=2, in_channels=3, out_channels=3, num_res_blocks=2, 
 C2_SCHEDULER = dict(num_train_timesteps=1000, schedule="linear_beta", beta_start=0.0015, beta_end=0.0195)
 C2_LATENT = (1, 3, 64, 64)
 C2_PROBES = (0, 1, 24, 49)             # DDIM step indices at which the reference trajectory is pinned teacher-forced
+
+
+# BASELINE.json configs[2] (C3): 3d_ddpm_tutorial.py:159-167 network — the bench's headline model — at the tutorial's
+# volume 32x40x32 (the oracle finishes a forward in seconds there): one forward + a DDIM-5 sample.  190 M weights from
+# the recipe (seed 13), not committed.
+C3_UNET = dict(spatial_dims=3, in_channels=1, out_channels=1, num_channels=(256, 256, 512),
+               attention_levels=(False, False, True), num_head_channels=(0, 0, 512), num_res_blocks=2)
+C3_SCHEDULER = dict(num_train_timesteps=1000, schedule="scaled_linear_beta", beta_start=0.0005, beta_end=0.0195,
+                    clip_sample=False)
+C3_SHAPE = (1, 1, 32, 40, 32)
+C3_STEPS = 5
+
+# BASELINE.json configs[3] (C4): 3d_vqvae_tutorial.py:128-139 network at 1x64^3 (encode -> quantise -> decode)
+C4_VQVAE = dict(spatial_dims=3, in_channels=1, out_channels=1, num_channels=(256, 256), num_res_channels=256,
+                num_res_layers=2, downsample_parameters=((2, 4, 1, 1),) * 2,
+                upsample_parameters=((2, 4, 1, 1, 0),) * 2, num_embeddings=256, embedding_dim=32)
+C4_SHAPE = (1, 1, 64, 64, 64)
+
+# BASELINE.json configs[4] (C5): 2d_controlnet.py:196-204 UNet widened to 3 channels with the CFG tutorial's
+# cross-attention conditioning (classifier_free_guidance tutorial 193-203) + ControlNet (2d_controlnet.py:300-308),
+# one classifier-free-guidance DDIM step at 3x256x256 (batch doubled to 2 inside the step; T = 16 384 at 128^2)
+C5_COMMON = dict(spatial_dims=2, in_channels=3, num_res_blocks=1, num_channels=(128, 256, 256),
+                 attention_levels=(False, True, True), num_head_channels=256, with_conditioning=True,
+                 cross_attention_dim=1)
+C5_UNET = dict(out_channels=3, **C5_COMMON)
+C5_CONTROLNET = dict(conditioning_embedding_in_channels=1, conditioning_embedding_num_channels=(16,), **C5_COMMON)
+C5_SHAPE = (1, 3, 256, 256)
+C5_GUIDANCE = 7.0
+C5_T_INDEX = 25           # DDIM-50 step index of the pinned step (t = 480)
+
+
+def c5_mask():
+    """Binary disc ((x-128)^2 + (y-128)^2 < 100^2), the synthetic control image of SURVEY.md section 8(d)."""
+    import torch
+    yy, xx = torch.meshgrid(torch.arange(256), torch.arange(256), indexing="ij")
+    return (((xx - 128) ** 2 + (yy - 128) ** 2) < 100 ** 2).float()[None, None]
