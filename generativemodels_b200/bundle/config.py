@@ -95,7 +95,9 @@ class BundleConfig:
             refs[m.group(1)] = self.get(m.group(1))
             return f"__refs__[{m.group(1)!r}]"
         code = _REF.sub(sub, expr)
-        return eval(code, self._expr_globals(), {"__refs__": refs})   # noqa: S307
+        # the references go into a copy of the GLOBALS: names used inside comprehensions / lambdas of the expression are
+        # looked up there, not in the eval locals (NameError on Python < 3.12 otherwise)
+        return eval(code, {**self._expr_globals(), "__refs__": refs})   # noqa: S307
 
     def _resolve(self, node: Any) -> Any:
         if isinstance(node, str):

@@ -5,8 +5,7 @@ few microseconds each per step, where the reference runs at 60-160 it/s regardle
     inferer.sample(input_noise=z, diffusion_model=unet, scheduler=scheduler)
 
 The wrapped module is captured with ``torch.cuda.graph`` on its first call for a given (shapes, dtypes, optional-args)
-signature: inputs are copied into static buffers, the graph is replayed, and the static output tensor is returned
-(valid until the next call with the same signature — exactly how a sampler consumes it).  A captured graph bakes in the
+signature: inputs are copied into static buffers, the graph is replayed, and a copy of the static output tensor is returned.  A captured graph bakes in the
 addresses of the packed weights, so the cache is dropped whenever a parameter or buffer of the module is replaced or
 modified in place (``load_state_dict``, ``.to()``, an optimiser step): the next call re-captures.  Everything the forward does
 is capture-safe by construction: allocations come from the graph's private pool, kernels are enqueued on the current
@@ -88,7 +87,9 @@ class GraphedModule(nn.Module):
             if torch.is_tensor(dst):
                 dst.copy_(kwargs[k], non_blocking=True)
         graph.replay()
-        return out
+        # a fresh tensor per call (one small stream-ordered copy): callers such as PNDMScheduler keep references to
+        # past outputs, which a shared static buffer would silently overwrite on the next replay
+        return out.clone() if torch.is_tensor(out) else out
 
 
 def graphed(module: nn.Module, warmup: int = 2) -> GraphedModule:

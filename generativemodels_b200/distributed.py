@@ -27,12 +27,22 @@ def shard_batch(x: torch.Tensor, rank: int | None = None, world: int | None = No
     return x[lo:hi]
 
 
-def gather_samples(local: torch.Tensor, total: int) -> torch.Tensor:
-    """All ranks receive the full batch ``[total, ...]`` in rank order (handles ragged shards by padding)."""
+def gather_samples(local: torch.Tensor | None, total: int, device=None) -> torch.Tensor:
+    """All ranks receive the full batch ``[total, ...]`` in rank order (ragged shards are padded).  A rank whose shard
+    is empty (more ranks than samples) passes ``None``: it learns the per-sample shape from the others and still takes
+    part in the collective, so nobody is left blocked in ``all_gather``."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return local
     world = dist.get_world_size()
     per = max(shard_bounds(total, r, world)[1] - shard_bounds(total, r, world)[0] for r in range(world))
+    if total < world:                      # only then can a shard be empty: agree on the per-sample shape first
+        metas = [None] * world
+        dist.all_gather_object(metas, None if local is None else (tuple(local.shape[1:]), local.dtype))
+        tail, dtype = next(m for m in metas if m is not None)
+        if local is None:
+            dev = device if device is not None else torch.device("cuda", torch.cuda.current_device()) \
+                if dist.get_backend() == "nccl" else torch.device("cpu")
+            local = torch.zeros((0, *tail), dtype=dtype, device=dev)
     pad = local
     if local.shape[0] < per:
         pad = torch.cat([local, local.new_zeros((per - local.shape[0], *local.shape[1:]))], 0)
@@ -51,5 +61,6 @@ def sample_sharded(sample_fn, input_noise: torch.Tensor, **kwargs) -> torch.Tens
     total = input_noise.shape[0]
     local_kwargs = {k: (shard_batch(v) if torch.is_tensor(v) and v.dim() > 0 and v.shape[0] == total else v)
                     for k, v in kwargs.items()}
-    out = sample_fn(input_noise=shard_batch(input_noise), **local_kwargs)
-    return gather_samples(out, total)
+    shard = shard_batch(input_noise)
+    out = sample_fn(input_noise=shard, **local_kwargs) if shard.shape[0] > 0 else None
+    return gather_samples(out, total, device=input_noise.device)

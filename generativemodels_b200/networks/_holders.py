@@ -6,6 +6,7 @@ h16 layout the tcgen05 kernel wants and cached against the parameter's version â
 """
 from __future__ import annotations
 
+import functools
 from typing import Sequence
 
 import torch
@@ -119,3 +120,34 @@ def require_cuda(x: torch.Tensor, module: nn.Module):
     if not x.is_cuda:
         raise RuntimeError(f"{type(module).__name__}: generativemodels_b200 runs on sm_100a CUDA devices only "
                            "(input tensor is on the CPU and there is no CPU path)")
+
+
+def on_input_device(fn):
+    """Run a module / scheduler entry point with the CUDA device of its first tensor argument current: the C-ABI
+    launches on the current device and allocates workspaces there, so a model living on cuda:1 while cuda:0 is current
+    would otherwise read its tensors across the peer link or fault (PyTorch modules do not require set_device)."""
+    @functools.wraps(fn)
+    def wrapped(self, x, *args, **kwargs):
+        if torch.is_tensor(x) and x.is_cuda and x.device.index != torch.cuda.current_device():
+            with torch.cuda.device(x.device):
+                return fn(self, x, *args, **kwargs)
+        return fn(self, x, *args, **kwargs)
+    return wrapped
+
+
+def invalidate_packed(module: nn.Module) -> None:
+    """Drop every packed-weight / concatenated-projection / captured-graph cache under ``module``.
+
+    The caches are keyed by ``(data_ptr, _version, device)`` of the parameters, which catches ``load_state_dict``,
+    optimiser steps, ``.to()`` and any in-place op on the parameter itself â€” but NOT writes through ``param.data``
+    (``p.data.copy_(ema)``, ``p.data.mul_()``: PyTorch does not bump ``p._version`` for those).  Call this after such
+    weight surgery (EMA swaps) and the next forward repacks from the live parameters."""
+    for m in module.modules():
+        for key in ("_pack_cache", "_lin_holders", "_temb_cat", "_temb_blocks", "_bare_cache"):
+            m.__dict__.pop(key, None)
+        g = m.__dict__.get("_b200_auto_graph")
+        if g is not None:
+            g._entries.clear()
+        if hasattr(m, "_entries") and hasattr(m, "_weights_sig"):      # a GraphedModule
+            m._entries.clear()
+            m._weights_sig = None

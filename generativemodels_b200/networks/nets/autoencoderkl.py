@@ -11,7 +11,7 @@ import torch.nn as nn
 from ... import ops
 from ...ops import ACT_NONE, ACT_SILU, CL
 from ..blocks.spade_norm import SPADE
-from .._holders import Convolution, require_cuda
+from .._holders import Convolution, on_input_device, require_cuda
 from .diffusion_model_unet import _sdp, ensure_tuple_rep
 
 __all__ = ["AutoencoderKL"]
@@ -250,6 +250,7 @@ class AutoencoderKL(nn.Module):
         self.out_channels = out_channels
         self.use_checkpointing = use_checkpointing     # activation checkpointing is a training feature: ignored
 
+    @on_input_device
     @torch.no_grad()
     def encode(self, x: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
         require_cuda(x, self)
@@ -263,10 +264,12 @@ class AutoencoderKL(nn.Module):
         eps = torch.randn_like(z_sigma)       # RNG stays with PyTorch so seeds behave like the reference's
         return ops.fma_f32(z_mu, eps, z_sigma)
 
+    @on_input_device
     def reconstruct(self, x: torch.Tensor) -> torch.Tensor:
         z_mu, _ = self.encode(x)
         return self.decode(z_mu)
 
+    @on_input_device
     @torch.no_grad()
     def decode(self, z: torch.Tensor) -> torch.Tensor:
         return self._decode(z, None)
@@ -277,14 +280,17 @@ class AutoencoderKL(nn.Module):
         out = ops.from_cl_f32(y, self.out_channels, self.spatial_dims)
         return out if z.dtype == torch.float32 else out.to(z.dtype)
 
+    @on_input_device
     def forward(self, x: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         z_mu, z_sigma = self.encode(x)
         z = self.sampling(z_mu, z_sigma)
         return self.decode(z), z_mu, z_sigma
 
+    @on_input_device
     def encode_stage_2_inputs(self, x: torch.Tensor) -> torch.Tensor:
         z_mu, z_sigma = self.encode(x)
         return self.sampling(z_mu, z_sigma)
 
+    @on_input_device
     def decode_stage_2_outputs(self, z: torch.Tensor) -> torch.Tensor:
         return self.decode(z)

@@ -9,7 +9,7 @@ import torch.nn as nn
 
 from ... import ops
 from ...ops import ACT_SILU, CL
-from .._holders import Convolution, require_cuda
+from .._holders import Convolution, on_input_device, require_cuda
 from .diffusion_model_unet import (_context_cl, ensure_tuple_rep, get_down_block, get_mid_block, project_time_embedding,
                                    time_embedding,
                                    zero_module)
@@ -131,6 +131,7 @@ class ControlNet(nn.Module):
             cache["key"], cache["pc"] = key, ops.PackedConv(block.weight, block.bias, 1, 0)
         return ops.conv(x, cache["pc"], scale=scale)
 
+    @on_input_device
     @torch.no_grad()
     def forward(self, x: torch.Tensor, timesteps: torch.Tensor, controlnet_cond: torch.Tensor,
                 conditioning_scale: float = 1.0, context: torch.Tensor | None = None,

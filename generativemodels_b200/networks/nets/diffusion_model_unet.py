@@ -20,7 +20,7 @@ import torch.nn as nn
 from ... import ops
 from ...ops import ACT_SILU, CL
 from ..blocks.spade_norm import SPADE
-from .._holders import Convolution, f32, packed_linear, require_cuda
+from .._holders import Convolution, f32, on_input_device, packed_linear, require_cuda
 
 __all__ = ["DiffusionModelUNet"]
 
@@ -729,6 +729,7 @@ class DiffusionModelUNet(nn.Module):
         return self._forward(x, timesteps, context, class_labels, down_block_additional_residuals,
                              mid_block_additional_residual, None)
 
+    @on_input_device
     def _forward(self, x, timesteps, context, class_labels, down_block_additional_residuals,
                  mid_block_additional_residual, seg):
         require_cuda(x, self)

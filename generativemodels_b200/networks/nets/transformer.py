@@ -15,7 +15,7 @@ import torch.nn as nn
 
 from ... import ops
 from ...ops import CL
-from .._holders import f32, packed_linear, require_cuda
+from .._holders import f32, packed_linear, on_input_device, require_cuda
 from ..blocks.transformerblock import TransformerBlock
 
 __all__ = ["DecoderOnlyTransformer", "AbsolutePositionalEmbedding"]
@@ -94,6 +94,7 @@ class DecoderOnlyTransformer(nn.Module):
         y = ops.linear(h, packed_linear(self, "to_logits"), out_f32=True)
         return y.reshape(B, T, -1)[:, :, : self.num_tokens]
 
+    @on_input_device
     @torch.no_grad()
     def forward(self, x: torch.Tensor, context: torch.Tensor | None = None) -> torch.Tensor:
         require_cuda(x, self)
@@ -182,6 +183,7 @@ class DecoderOnlyTransformer(nn.Module):
         cache.graph.replay()
         return cache.static_logits
 
+    @on_input_device
     @torch.no_grad()
     def step(self, x: torch.Tensor, cache: _Cache) -> torch.Tensor:
         """Logits [B, T_new, num_tokens] of ``x`` ([B, T_new] tokens that extend the cached prefix), identical to the

@@ -8,7 +8,7 @@ import torch.nn as nn
 
 from ... import _lib, ops
 from ...ops import ACT_RELU, CL
-from .._holders import Convolution, require_cuda
+from .._holders import Convolution, on_input_device, require_cuda
 from ..layers.vector_quantizer import EMAQuantizer, VectorQuantizer
 from .diffusion_model_unet import ensure_tuple_rep
 
@@ -147,6 +147,7 @@ class VQVAE(nn.Module):
         return ops.from_cl(self.decoder(q))
 
     # ---- reference interface (vqvae.py:417-455) --------------------------------------------------
+    @on_input_device
     @torch.no_grad()
     def encode(self, images: torch.Tensor) -> torch.Tensor:
         return self._z_to_nchw(self._encode_cl(images))
@@ -155,16 +156,19 @@ class VQVAE(nn.Module):
         x_loss, x = self.quantizer(encodings)
         return x, x_loss
 
+    @on_input_device
     @torch.no_grad()
     def decode(self, quantizations: torch.Tensor) -> torch.Tensor:
         require_cuda(quantizations, self)
         return self._decode_cl(ops.to_cl(quantizations))
 
+    @on_input_device
     @torch.no_grad()
     def index_quantize(self, images: torch.Tensor) -> torch.Tensor:
         r = self.quantizer.forward_cl(self._encode_cl(images), want_f32=False)
         return self.quantizer.quantizer._indices_view(r["indices"])
 
+    @on_input_device
     @torch.no_grad()
     def decode_samples(self, embedding_indices: torch.Tensor) -> torch.Tensor:
         require_cuda(embedding_indices, self)
@@ -179,6 +183,7 @@ class VQVAE(nn.Module):
                    "b200_vq_gather")
         return self._decode_cl(out)
 
+    @on_input_device
     @torch.no_grad()
     def forward(self, images: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
         if self.training:
@@ -186,6 +191,7 @@ class VQVAE(nn.Module):
         r = self.quantizer.forward_cl(self._encode_cl(images), want_f32=False)
         return self._decode_cl(r["q"]), r["loss"]
 
+    @on_input_device
     @torch.no_grad()
     def encode_stage_2_inputs(self, x: torch.Tensor, quantized: bool = True) -> torch.Tensor:
         z = self._encode_cl(x)
@@ -194,6 +200,7 @@ class VQVAE(nn.Module):
         r = self.quantizer.forward_cl(z, want_f32=True)
         return ops.from_cl_f32(r["q_f32"].contiguous(), self.embedding_dim, self.spatial_dims)
 
+    @on_input_device
     @torch.no_grad()
     def decode_stage_2_outputs(self, z: torch.Tensor) -> torch.Tensor:
         """Re-quantises the latent before decoding (vqvae.py:452-455)."""

@@ -8,6 +8,7 @@ import torch
 
 from ... import _lib
 from .scheduler import PRED_CODES, Scheduler, StrEnum, _f, _prep, _stream
+from .._holders import on_input_device
 
 
 class DDIMPredictionType(StrEnum):
@@ -65,6 +66,7 @@ class DDIMScheduler(Scheduler):
             prev, x0 = prev.to(sample.dtype), x0.to(sample.dtype)
         return prev, x0
 
+    @on_input_device
     def step(self, model_output: torch.Tensor, timestep: int, sample: torch.Tensor, eta: float = 0.0,
              generator: torch.Generator | None = None) -> tuple[torch.Tensor, torch.Tensor]:
         """ddim.py:156-237 -> (pred_prev_sample, pred_original_sample)."""
@@ -82,6 +84,7 @@ class DDIMScheduler(Scheduler):
             sigma = variance ** 0.5 * eta
         return self._launch(model_output, sample, a_t, a_prev, 1 - a_prev - std_dev_t ** 2, sigma, noise)
 
+    @on_input_device
     def reversed_step(self, model_output: torch.Tensor, timestep: int,
                       sample: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
         """ddim.py:239-301 -> (pred_next_sample, pred_original_sample)."""

@@ -8,6 +8,7 @@ import torch
 
 from ... import _lib
 from .scheduler import PRED_CODES, Scheduler, StrEnum, _f, _prep, _stream
+from .._holders import on_input_device
 
 
 class DDPMPredictionType(StrEnum):
@@ -74,6 +75,7 @@ class DDPMScheduler(Scheduler):
             variance = frac * self.betas[timestep] + (1 - frac) * variance
         return variance
 
+    @on_input_device
     def step(self, model_output: torch.Tensor, timestep: int, sample: torch.Tensor,
              generator: torch.Generator | None = None) -> tuple[torch.Tensor, torch.Tensor]:
         """ddpm.py:191-252 -> (pred_prev_sample, pred_original_sample)."""

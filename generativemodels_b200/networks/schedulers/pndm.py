@@ -15,6 +15,7 @@ import torch
 
 from ... import _lib
 from .scheduler import PRED_CODES, Scheduler, StrEnum, _f, _prep, _stream
+from .._holders import on_input_device
 
 
 class PNDMPredictionType(StrEnum):
@@ -95,11 +96,18 @@ class PNDMScheduler(Scheduler):
             prev = prev.to(sample.dtype)
         return prev, eps
 
+    @on_input_device
     def step(self, model_output: torch.Tensor, timestep: int, sample: torch.Tensor) -> tuple[torch.Tensor, Any]:
         """pndm.py:164-183."""
         if self.counter < len(self.prk_timesteps) and not self.skip_prk_steps:
             return self.step_prk(model_output=model_output, timestep=timestep, sample=sample), None
         return self.step_plms(model_output=model_output, timestep=timestep, sample=sample), None
+
+    @staticmethod
+    def _keep(model_output: torch.Tensor) -> torch.Tensor:
+        """History entries must own their storage: a CUDA-graph-replayed network returns the same output buffer
+        every step, which the next replay overwrites (the four PLMS weights would then all multiply the current eps)."""
+        return model_output.clone()
 
     def step_prk(self, model_output: torch.Tensor, timestep: int, sample: torch.Tensor) -> torch.Tensor:
         """pndm.py:185-228 (Runge-Kutta warm-up, four network evaluations per step)."""
@@ -111,10 +119,14 @@ class PNDMScheduler(Scheduler):
         prev_timestep = timestep - diff_to_prev
         timestep = int(self.prk_timesteps[self.counter // 4 * 4])
         phase = self.counter % 4
+        # like the reference, phase 0 ACCUMULATES (``self.cur_model_output += 1/6 * model_output``, pndm.py:208-209) into
+        # whatever the last cycle left — 0 after a completed cycle, a stale partial sum after a loop aborted mid-cycle
+        # (set_timesteps resets ``ets`` / ``counter`` only, pndm.py:160-161).  Kept bug-for-bug: results must be the
+        # reference's on the same call sequence (tests/test_modules_cpu.py::test_pndm_restart_mid_runge_kutta_cpu).
         acc = self.cur_model_output
         has_acc = torch.is_tensor(acc)
         if phase == 0:
-            self.ets.append(model_output)
+            self.ets.append(self._keep(model_output))
             self.cur_sample = sample
         if phase in (0, 1, 2):
             w = 1 / 6 if phase == 0 else 1 / 3
@@ -141,7 +153,7 @@ class PNDMScheduler(Scheduler):
         prev_timestep = timestep - self.num_train_timesteps // self.num_inference_steps
         if self.counter != 1:
             self.ets = self.ets[-3:]
-            self.ets.append(model_output)
+            self.ets.append(self._keep(model_output))
         else:
             prev_timestep = timestep
             timestep = timestep + self.num_train_timesteps // self.num_inference_steps

@@ -66,7 +66,7 @@ def _launch(total):
     return got if all(p.exitcode == 0 for p in procs) else None
 
 
-@pytest.mark.parametrize("total", [2, 5])
+@pytest.mark.parametrize("total", [1, 2, 5])       # 1: the second rank's shard is empty
 def test_sharded_sampling_matches_single_process(total):
     got = None
     for _ in range(3):

@@ -402,3 +402,44 @@ def test_c2_reference_fixture_cpu():
     from tests import fixture_checks
     report = fixture_checks.check_c2_fixture("cpu", probes=(0, 24))
     assert report[24][0] > report[0][0]          # the peaked-softmax probe is the harder one, as documented
+
+
+def test_pndm_restart_mid_runge_kutta_cpu():
+    """A sampling loop aborted inside a Runge-Kutta cycle and restarted on the same scheduler: the reference keeps the
+    stale accumulator (``+=`` at phase 0, pndm.py:208; set_timesteps resets ets / counter only, 160-161) — the
+    round-1 advisor read it as an assignment; the reference's code is the contract, so the call sequence must give the
+    oracle's (= the reference's) numbers, stale sum included."""
+    from generativemodels_b200.networks.schedulers import PNDMScheduler
+    torch.manual_seed(0)
+    x = torch.randn(1, 1, 8, 8)
+    outs = [torch.randn(1, 1, 8, 8) for _ in range(8)]
+
+    def drive(s):
+        s.set_timesteps(4)
+        y = x
+        for t, e in zip(s.timesteps[:2], outs):      # abort after phases 0 and 1 of the first cycle
+            y, _ = s.step(e, int(t), y)
+        s.set_timesteps(4)
+        y = x
+        for t, e in zip(s.timesteps[:8], outs):
+            y, _ = s.step(e, int(t), y)
+        return y
+    got = drive(PNDMScheduler(num_train_timesteps=1000, skip_prk_steps=False))
+    want = drive(O.PNDMOracle(num_train_timesteps=1000, skip_prk_steps=False))
+    assert rel(got, want) < 1e-5, rel(got, want)
+
+
+def test_invalidate_packed_cpu():
+    import generativemodels_b200 as B
+    kw = G.UNET_CASES["unet2d_attn"]
+    torch.manual_seed(0)
+    m = G.randomize_zero_params(nets().DiffusionModelUNet(**kw)).eval()
+    x, t = torch.randn(1, 1, 16, 16), torch.Tensor((500,))
+    y0 = m(x, t)
+    with torch.no_grad():
+        m.conv_in.conv.weight.data.mul_(2.0)          # invisible to the version-keyed cache ...
+    assert torch.equal(m(x, t), y0)
+    B.invalidate_packed(m)                               # ... until the caches are dropped
+    y1 = m(x, t)
+    want = O.unet_forward(m.state_dict(), G.unet_oracle_cfg(kw), x, t)
+    assert rel(y1, want) < 2e-2 and not torch.equal(y0, y1)

@@ -276,3 +276,32 @@ def test_transformer_greedy_sampling(ref):
         emb = O.vq_embed(sd["quantizer.quantizer.embedding.weight"], seq)
         got = O.vqvae_decode(sd, G.vqvae_oracle_cfg(G.VQVAE_CASES["vqvae2d"]), emb)
     _close(got, want)
+
+
+def test_pndm_restart_mid_runge_kutta(ref):
+    """The reference keeps a stale Runge-Kutta accumulator when a loop is aborted mid-cycle and restarted on the same
+    scheduler (``+=`` at phase 0, pndm.py:208; set_timesteps resets ets / counter only): the oracle follows it."""
+    _, sch = ref
+    torch.manual_seed(0)
+    x = torch.randn(1, 1, 8, 8)
+    outs = [torch.randn(1, 1, 8, 8) for _ in range(8)]
+
+    def drive(s):
+        s.set_timesteps(4)
+        y = x
+        for t, e in zip(s.timesteps[:2], outs):
+            y, _ = s.step(e.clone(), int(t), y)
+        s.set_timesteps(4)
+        y = x
+        for t, e in zip(s.timesteps[:8], outs):
+            y, _ = s.step(e.clone(), int(t), y)
+        return y
+    want = drive(sch.PNDMScheduler(num_train_timesteps=1000, skip_prk_steps=False))
+    got = drive(O.PNDMOracle(num_train_timesteps=1000, skip_prk_steps=False))
+    fresh = sch.PNDMScheduler(num_train_timesteps=1000, skip_prk_steps=False)
+    fresh.set_timesteps(4)
+    y = x
+    for t, e in zip(fresh.timesteps[:8], outs):
+        y, _ = fresh.step(e.clone(), int(t), y)
+    assert not torch.allclose(want, y)          # the stale sum really is inherited by the reference
+    _close(got, want, 1e-6)

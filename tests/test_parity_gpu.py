@@ -611,3 +611,52 @@ def test_cuda_graph_replay_matches_eager(cuda_device):
         m.conv_in.conv.weight.mul_(1.5)
     ts = torch.Tensor((500.0,)).cuda()
     assert torch.equal(g(x, timesteps=ts).clone(), m(x, timesteps=ts))
+
+
+def test_cuda_graph_with_pndm_history(cuda_device):
+    """A graph-replayed network hands out a fresh tensor per call: PNDMScheduler keeps up to four past model outputs
+    (pndm.py:230-291), which a shared static output buffer would silently alias (all PLMS weights on the current eps).
+    Graphed and eager sampling must agree bit for bit, with and without the Runge-Kutta warm-up."""
+    from generativemodels_b200.cuda_graph import graphed
+    from generativemodels_b200.inferers import DiffusionInferer
+    from generativemodels_b200.networks.schedulers import PNDMScheduler
+    kw = G.UNET_CASES["unet2d_attn"]
+    torch.manual_seed(0)
+    m = G.randomize_zero_params(nets().DiffusionModelUNet(**kw)).cuda().eval()
+    g = graphed(m)
+    torch.manual_seed(1)
+    x = torch.randn(2, 1, 16, 16).cuda()
+    for skip in (True, False):
+        outs = []
+        for net in (m, g):
+            s = PNDMScheduler(num_train_timesteps=1000, skip_prk_steps=skip)
+            s.set_timesteps(8)
+            outs.append(DiffusionInferer(s).sample(x, net, s, verbose=False))
+        assert torch.equal(outs[0], outs[1]), f"graphed PNDM sampling differs from eager (skip_prk_steps={skip})"
+    ts = torch.Tensor((500.0,)).cuda()
+    a, b = g(x, timesteps=ts), g(x + 1, timesteps=ts)
+    assert a.data_ptr() != b.data_ptr() and not torch.equal(a, b)
+
+
+def test_param_data_surgery_needs_invalidate(cuda_device):
+    """Writes through ``param.data`` (EMA swaps) do not bump the version counter the packed-weight caches key on;
+    ``generativemodels_b200.invalidate_packed`` is the documented way to make the next forward see them."""
+    import generativemodels_b200 as B
+    kw = G.UNET_CASES["unet2d_attn"]
+    torch.manual_seed(0)
+    m = G.randomize_zero_params(nets().DiffusionModelUNet(**kw)).cuda().eval()
+    torch.manual_seed(1)
+    x, ts = torch.randn(2, 1, 16, 16).cuda(), torch.Tensor((300.0,)).cuda()
+    y0 = m(x, timesteps=ts)
+    new = {k: v.clone() for k, v in m.state_dict().items()}
+    for k in new:
+        if k.endswith("conv1.conv.weight"):
+            new[k] = new[k] * 1.25
+    with torch.no_grad():
+        for k, p_ in m.named_parameters():
+            p_.data.copy_(new[k])
+    B.invalidate_packed(m)
+    y1 = m(x, timesteps=ts)
+    want = O.unet_forward({k: v.cpu() for k, v in new.items()}, G.unet_oracle_cfg(kw), x.cpu(), ts.cpu())
+    check(y1, want)
+    assert not torch.equal(y0, y1)
