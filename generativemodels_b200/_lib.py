@@ -106,6 +106,13 @@ class PndmCoef(C.Structure):
                 ("v_alpha", C.c_float), ("v_beta", C.c_float), ("prediction_type", C.c_int32)]
 
 
+class RepackBlock(C.Structure):
+    _fields_ = [("col0", C.c_int32), ("cin0", C.c_int32), ("cs", C.c_int32), ("ntaps", C.c_int32),
+                ("tap", C.c_int16 * 8)]
+
+
+REPACK_BLOCKS, REPACK_TAP_IN, REPACK_TAP_OUT = 0, 1, 2
+
 _P, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
 # name -> argtypes (restype is int unless listed in _RESTYPES); mirrors include/b200gen.h exactly
@@ -159,6 +166,7 @@ SIGNATURES = {
     "b200_add_noise": [_P, _P, _P, _P, _F, _I32, _I64, _P, _P],
     "b200_vq_argmin_gather": [_P, _I64, _I32, _I32, _P, _I32, _P, _P, _I32, _P, _I32, _P, _P, _P],
     "b200_vq_gather": [_P, _I64, _P, _I32, _I32, _P, _I32, _P],
+    "b200_repack_weight": [_P, _I32, _I32, _I32, _I32, _I32, C.POINTER(RepackBlock), _I32, _P, _I32, _I32, _P],
 }
 _RESTYPES = {"b200_last_error_string": C.c_char_p, "b200_groupnorm_workspace_bytes": C.c_int64,
              "b200_attention_flash_workspace_bytes": C.c_int64, "b200_igemm_split_workspace_bytes": C.c_int64}
@@ -182,7 +190,7 @@ def load():
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, C.c_int)
     for which, struct in enumerate((IgemmParams, GnStatsParams, GnApplyParams, DdimCoef, DdpmCoef, PndmCoef, IgemmSeg,
-                                    FlashParams, KlCoef)):
+                                    FlashParams, KlCoef, RepackBlock)):
         c_size = lib.b200_abi_sizeof(which)
         if c_size != C.sizeof(struct):
             raise B200Error(f"ABI mismatch: {struct.__name__} is {C.sizeof(struct)} bytes in Python but {c_size} in "

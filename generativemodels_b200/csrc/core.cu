@@ -68,6 +68,7 @@ extern "C" int b200_abi_sizeof(int which) {
     case 6: return (int)sizeof(b200_igemm_seg);
     case 7: return (int)sizeof(b200_flash_params);
     case 8: return (int)sizeof(b200_kl_coef);
+    case 9: return (int)sizeof(b200_repack_block);
     default: return -1;
   }
 }

@@ -127,11 +127,12 @@ def on_input_device(fn):
     launches on the current device and allocates workspaces there, so a model living on cuda:1 while cuda:0 is current
     would otherwise read its tensors across the peer link or fault (PyTorch modules do not require set_device)."""
     @functools.wraps(fn)
-    def wrapped(self, x, *args, **kwargs):
+    def wrapped(self, *args, **kwargs):
+        x = args[0] if args else next((v for v in kwargs.values() if torch.is_tensor(v)), None)
         if torch.is_tensor(x) and x.is_cuda and x.device.index != torch.cuda.current_device():
             with torch.cuda.device(x.device):
-                return fn(self, x, *args, **kwargs)
-        return fn(self, x, *args, **kwargs)
+                return fn(self, *args, **kwargs)
+        return fn(self, *args, **kwargs)
     return wrapped
 
 

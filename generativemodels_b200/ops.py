@@ -111,18 +111,30 @@ def from_cl_f32(t: torch.Tensor, C_: int, spatial_dims: int) -> torch.Tensor:
 # --------------------------------------------------------------------------------------------------
 # weight packing (one-time, cached by the modules; not on the per-step path)
 # --------------------------------------------------------------------------------------------------
-def _pack_taps(blocks: list[torch.Tensor], rows: int) -> torch.Tensor:
-    """blocks: list of [Cout, Cs] fp32 matrices -> h16 [rows_pad, sum ceil64(Cs)] K-major."""
-    cols = []
-    for b in blocks:
-        cs = b.shape[1]
-        pad = round_up(cs, 64) - cs
-        cols.append(torch.nn.functional.pad(b, (0, pad)) if pad else b)
-    w = torch.cat(cols, dim=1)
-    rpad = round_up(rows, 16) - rows
-    if rpad:
-        w = torch.nn.functional.pad(w, (0, 0, 0, rpad))
-    return w.to(H16).contiguous()
+def _src_f32(weight: torch.Tensor) -> torch.Tensor:
+    w = weight.detach()
+    return w if (w.dtype == torch.float32 and w.is_contiguous()) else w.float().contiguous()
+
+
+def repack(w: torch.Tensor, cout: int, cin: int, taps: int, blocks, rows: int, *, transposed: bool = False,
+           mode: int = _lib.REPACK_BLOCKS, pitch: int | None = None) -> torch.Tensor:
+    """One b200_repack_weight launch: fp32 parameter ``w`` -> K-major h16 ``[round_up(rows, 16), pitch]``.
+    ``blocks`` = [(cin0, cs, (tap, ...)), ...] in segment order; every block is ceil64(cs) columns wide."""
+    lib = _lib.require_device()
+    arr, col = None, 0
+    if mode == _lib.REPACK_BLOCKS:
+        arr = (_lib.RepackBlock * len(blocks))()
+        for i, (cin0, cs, taps_i) in enumerate(blocks):
+            b = arr[i]
+            b.col0, b.cin0, b.cs, b.ntaps = col, cin0, cs, len(taps_i)
+            for j, t in enumerate(taps_i):
+                b.tap[j] = t
+            col += round_up(cs, 64)
+        pitch = col
+    out = torch.empty((round_up(rows, 16), pitch), dtype=H16, device=w.device)
+    check(lib.b200_repack_weight(w.data_ptr(), cout, cin, taps, int(transposed), mode, arr, len(blocks) if blocks else 0,
+                                 out.data_ptr(), out.shape[0], pitch, _stream()), "b200_repack_weight")
+    return out
 
 
 class PackedConv:
@@ -135,13 +147,12 @@ class PackedConv:
 
     def __init__(self, weight: torch.Tensor, bias: torch.Tensor | None, stride: int | Sequence[int],
                  padding, splits: Sequence[int] | None = None):
-        w = weight.detach().float()
+        w = _src_f32(weight)
         sd = w.dim() - 2
         self.spatial_dims = sd
         self.cout, cin = w.shape[0], w.shape[1]
         k = tuple(w.shape[2:])
         if sd == 2:
-            w = w.unsqueeze(2)
             k = (1, *k)
         self.k = k
         st = (stride,) * sd if isinstance(stride, int) else tuple(stride)
@@ -159,26 +170,30 @@ class PackedConv:
                 for c in range(k[2]):
                     off = 0
                     for s, cs in enumerate(self.splits):
-                        blocks.append(w[:, off:off + cs, a, b, c])
+                        blocks.append((off, cs, ((a * k[1] + b) * k[2] + c,)))
                         segs.append((s, c - self.pad[2][0], b - self.pad[1][0], a - self.pad[0][0], 0,
                                      round_up(cs, 64) // 64))
                         off += cs
         if len(segs) > _lib.IGEMM_MAX_SEG:
             raise ValueError(f"convolution needs {len(segs)} taps; the kernel supports {_lib.IGEMM_MAX_SEG}")
-        self.w = _pack_taps(blocks, self.cout)
+        taps = k[0] * k[1] * k[2]
+        self.w = repack(w, self.cout, cin, taps, blocks, self.cout)
         self.segs = segs
-        self.bias = None if bias is None else bias.detach().float().contiguous()
+        self.bias = None if bias is None else _src_f32(bias)
         # Degenerate ends of the UNet (see b200_tap_gather / b200_tap_sum): with very few input channels the taps
         # are folded into ONE 64-wide K chunk; with very few output channels the taps become GEMM columns.
-        taps = k[0] * k[1] * k[2]
         self.tap_in = self.tap_out = None
         if taps > 1 and len(self.splits) == 1 and taps * cin <= 64:
-            w2 = w.permute(0, 2, 3, 4, 1).reshape(self.cout, taps * cin)              # [co][tap*cin + c]
-            self.tap_in = PackedLinear(w2, bias)
+            # [co][tap*cin + c]
+            self.tap_in = PackedLinear.from_packed(repack(w, self.cout, cin, taps, None, self.cout,
+                                                          mode=_lib.REPACK_TAP_IN, pitch=64),
+                                                   self.cout, taps * cin, self.bias)
         elif (taps > 1 and len(self.splits) == 1 and self.cout <= 4 and taps * self.cout <= 128 and cin >= 64
               and self.stride == (1, 1, 1)):
-            w2 = w.permute(2, 3, 4, 0, 1).reshape(taps * self.cout, cin)               # [tap*cout + co][c]
-            self.tap_out = PackedLinear(w2, None)
+            # [tap*cout + co][c]
+            self.tap_out = PackedLinear.from_packed(repack(w, self.cout, cin, taps, None, taps * self.cout,
+                                                           mode=_lib.REPACK_TAP_OUT, pitch=round_up(cin, 64)),
+                                                    taps * self.cout, cin, None)
 
     def geom(self, N: int, D: int, H: int, W: int):
         od = self.out_dims(D, H, W)
@@ -193,12 +208,20 @@ class PackedLinear:
     """nn.Linear weight [O, K] -> K-major h16 (already K-major; only padded and cast)."""
 
     def __init__(self, weight: torch.Tensor, bias: torch.Tensor | None):
-        w = weight.detach().float()
+        w = _src_f32(weight)
         self.cout, self.K = w.shape
-        self.w = _pack_taps([w], self.cout)
+        self.w = repack(w, self.cout, self.K, 1, [(0, self.K, (0,))], self.cout)
         self.segs = [(0, 0, 0, 0, 0, round_up(self.K, 64) // 64)]
-        self.bias = None if bias is None else bias.detach().float().contiguous()
+        self.bias = None if bias is None else _src_f32(bias)
         self.stride = (1, 1, 1)
+
+    @classmethod
+    def from_packed(cls, w16: torch.Tensor, cout: int, K: int, bias: torch.Tensor | None) -> "PackedLinear":
+        self = cls.__new__(cls)
+        self.cout, self.K, self.w = cout, K, w16
+        self.segs = [(0, 0, 0, 0, 0, round_up(K, 64) // 64)]
+        self.bias, self.stride = bias, (1, 1, 1)
+        return self
 
 
 class PackedConvTranspose:
@@ -206,20 +229,20 @@ class PackedConvTranspose:
 
     def __init__(self, weight: torch.Tensor, bias: torch.Tensor | None, stride: int, padding: int,
                  output_padding: int):
-        w = weight.detach().float()           # [Cin, Cout, k...]
+        w = _src_f32(weight)                  # [Cin, Cout, k...]
         sd = w.dim() - 2
         self.spatial_dims = sd
         self.cin, self.cout = w.shape[0], w.shape[1]
         k = tuple(w.shape[2:])
         if sd == 2:
-            w = w.unsqueeze(2)
             k = (1, *k)
         self.k = k
         self.s = (1, stride, stride) if sd == 2 else (stride,) * 3
         self.p = (0, padding, padding) if sd == 2 else (padding,) * 3
         self.op = (0, output_padding, output_padding) if sd == 2 else (output_padding,) * 3
-        self.bias = None if bias is None else bias.detach().float().contiguous()
+        self.bias = None if bias is None else _src_f32(bias)
         nch = round_up(self.cin, 64) // 64
+        ntaps = k[0] * k[1] * k[2]
         self.phases = []
         for rd in range(self.s[0]):
             for rh in range(self.s[1]):
@@ -231,11 +254,12 @@ class PackedConvTranspose:
                     for (a, oa) in taps[0]:
                         for (b, ob) in taps[1]:
                             for (c, oc) in taps[2]:
-                                blocks.append(w[:, :, a, b, c].t())      # [Cout, Cin]
+                                blocks.append((0, self.cin, ((a * k[1] + b) * k[2] + c,)))
                                 segs.append((0, oc, ob, oa, 0, nch))
                     if not segs:
                         continue
-                    self.phases.append((r, _pack_taps(blocks, self.cout), segs))
+                    self.phases.append((r, repack(w, self.cout, self.cin, ntaps, blocks, self.cout, transposed=True),
+                                        segs))
 
     def out_dims(self, D: int, H: int, W: int) -> tuple[int, int, int]:
         i = (D, H, W)
@@ -254,15 +278,14 @@ class PackedUpsampleConv:
     _TAPS = {0: ((-1, (0,)), (0, (1, 2))), 1: ((0, (0, 1)), (1, (2,)))}
 
     def __init__(self, weight: torch.Tensor, bias: torch.Tensor | None):
-        w = weight.detach().float()
+        w = _src_f32(weight)
         sd = w.dim() - 2
         if tuple(w.shape[2:]) != (3,) * sd:
             raise ValueError("PackedUpsampleConv expects a 3^d kernel")
         self.spatial_dims = sd
         self.cout, self.cin = w.shape[0], w.shape[1]
-        if sd == 2:
-            w = w.unsqueeze(2)
-        self.bias = None if bias is None else bias.detach().float().contiguous()
+        kk = (1, 3, 3) if sd == 2 else (3, 3, 3)
+        self.bias = None if bias is None else _src_f32(bias)
         nch = round_up(self.cin, 64) // 64
         self.phases = []
         d_phases = (0, 1) if sd == 3 else (None,)
@@ -274,14 +297,11 @@ class PackedUpsampleConv:
                     for (od, kds) in td:
                         for (oh, khs) in self._TAPS[ph]:
                             for (ow, kws) in self._TAPS[pw]:
-                                ws = 0
-                                for a in kds:
-                                    for b in khs:
-                                        for c in kws:
-                                            ws = ws + w[:, :, a, b, c]
-                                blocks.append(ws)
+                                src_taps = tuple((a * kk[1] + b) * kk[2] + c for a in kds for b in khs for c in kws)
+                                blocks.append((0, self.cin, src_taps))
                                 segs.append((0, ow, oh, od, 0, nch))
-                    self.phases.append(((pd or 0, ph, pw), _pack_taps(blocks, self.cout), segs))
+                    self.phases.append(((pd or 0, ph, pw), repack(w, self.cout, self.cin, kk[0] * kk[1] * kk[2],
+                                                                   blocks, self.cout), segs))
 
 
 def conv_upsample2x(src: CL, pu: PackedUpsampleConv, impl: int = 0) -> CL:

@@ -52,7 +52,7 @@ int b200_device_check(void);
 int b200_sm_count(void);
 /* sizeof() of the parameter structs below, for binding-layer ABI checks:
  * 0 igemm_params, 1 gn_stats_params, 2 gn_apply_params, 3 ddim_coef, 4 ddpm_coef, 5 pndm_coef, 6 igemm_seg,
- * 7 flash_params, 8 kl_coef. */
+ * 7 flash_params, 8 kl_coef, 9 repack_block. */
 int b200_abi_sizeof(int which);
 
 /* ------------------------------------------------------------------------------------------------
@@ -395,6 +395,33 @@ int b200_vq_argmin_gather(const float* x, int64_t M, int32_t D, int32_t x_pitch,
 /* nn.Embedding gather for decode_samples (vqvae.py:445-450): idx int64 [M] -> h16 rows. */
 int b200_vq_gather(const int64_t* indices, int64_t M, const float* codebook, int32_t K, int32_t D,
                    void* q_h16, int32_t q_pitch, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Weight repacking (b200_repack_conv_weight / b200_repack_linear_weight): one launch turns an fp32
+ * parameter into the K-major h16 matrix [rows_pad][dst_pitch] that b200_igemm's weight tensor map reads.  The matrix
+ * is a sequence of column BLOCKS, one per b200_igemm segment (filter tap x input-tensor split), each ceil64(cs) wide:
+ *   dst[co][blk.col0 + c] = sum_{t < blk.ntaps} src(co, blk.cin0 + c, blk.tap[t])      for c < blk.cs, co < cout
+ * and zero elsewhere (channel tails, pad rows).  Plain convolutions have one source tap per block; the nearest-x2
+ * upsample folded into a 3^d convolution (diffusion_model_unet.py:574-586) sums up to 8 original taps per phase tap
+ * (added in index order, fp32); a transposed convolution (vqvae.py:220-260) packs the taps of one output phase.
+ *   src layout: transposed == 0: [cout][cin][taps] (nn.ConvNd / nn.Linear with taps == 1);
+ *               transposed == 1: [cin][cout][taps] (nn.ConvTransposeNd).
+ * mode B200_REPACK_TAP_IN  : dst[co][tap * cin + c] = src[co][c][tap]   (few-input-channel convs as ONE K chunk)
+ * mode B200_REPACK_TAP_OUT : dst[tap * cout + co][c] = src[co][c][tap]   (few-output-channel convs: taps as GEMM rows)
+ * `blocks` is a HOST array (copied into the launch parameters; at most B200_IGEMM_MAX_SEG entries).
+ * ---------------------------------------------------------------------------------------------- */
+#define B200_REPACK_BLOCKS  0
+#define B200_REPACK_TAP_IN  1
+#define B200_REPACK_TAP_OUT 2
+typedef struct {
+  int32_t col0;       /* first destination column (multiple of 64)     */
+  int32_t cin0, cs;   /* source channel range [cin0, cin0 + cs)         */
+  int32_t ntaps;      /* 1..8 source taps summed into this block        */
+  int16_t tap[8];     /* flattened source tap indices                   */
+} b200_repack_block;
+int b200_repack_weight(const float* src, int32_t cout, int32_t cin, int32_t taps, int32_t transposed, int32_t mode,
+                       const b200_repack_block* blocks, int32_t n_blocks, void* dst, int32_t rows_pad,
+                       int32_t dst_pitch, void* stream);
 
 #ifdef __cplusplus
 }

@@ -485,6 +485,27 @@ class FakeLib:
             h += np.bincount(ii.numpy(), minlength=K).astype(np.int32)
         return 0
 
+    def b200_repack_weight(self, src, cout, cin, taps, transposed, mode, blocks, n_blocks, dst, rows_pad, pitch, stream):
+        """include/b200gen.h, b200_repack_weight — literal restatement (fp32 sums in tap order, then one rounding)."""
+        w = f32(src, cout * cin * taps)
+        w = w.view(cin, cout, taps).transpose(0, 1) if transposed else w.view(cout, cin, taps)      # [co][c][tap]
+        out = torch.zeros(rows_pad, pitch, dtype=torch.float32)
+        if mode == _lib.REPACK_TAP_IN:
+            out[:cout, :taps * cin] = w.permute(0, 2, 1).reshape(cout, taps * cin)
+        elif mode == _lib.REPACK_TAP_OUT:
+            out[:taps * cout, :cin] = w.permute(2, 0, 1).reshape(taps * cout, cin)
+        else:
+            for i in range(n_blocks):
+                b = blocks[i]
+                acc = torch.zeros(cout, b.cs)
+                for t in range(b.ntaps):
+                    acc = acc + w[:, b.cin0:b.cin0 + b.cs, b.tap[t]]
+                out[:cout, b.col0:b.col0 + b.cs] = acc
+        if ops.H16 == torch.float16:
+            out = out.clamp(-65504.0, 65504.0)
+        bf16(dst, rows_pad * pitch).view(rows_pad, pitch).copy_(out.to(ops.H16))
+        return 0
+
     def b200_vq_gather(self, idx, M, cb, K, D, q16, qp, stream):
         dst = bf16(q16, M * qp).view(M, qp)
         dst.zero_()

@@ -9,11 +9,12 @@ import torch
 import torch.nn.functional as F
 
 from generativemodels_b200 import ops
-from tests import igemm_emulator
+from tests import cpu_backend, igemm_emulator
 
 
 @pytest.fixture(autouse=True)
 def _emulated(monkeypatch):
+    cpu_backend.install(monkeypatch)          # weight repacking and the GEMM both go through the C-ABI stand-in
     monkeypatch.setattr(ops, "igemm_raw", igemm_emulator.emulate)
 
 

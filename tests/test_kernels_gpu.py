@@ -1,9 +1,9 @@
 """Op-level parity of every CUDA kernel (called through the C-ABI) against plain fp32 CPU arithmetic.
 
 The checker for one op is the reference's own arithmetic: torch CPU fp32 functional ops (what the reference
-executes on CPU) applied to the SAME bf16-rounded inputs the kernel sees.  Tolerances: the
-kernels take bf16 operands and accumulate in fp32, so a result differs from the fp32 checker only by the final
-bf16 rounding of the output (rel 2^-8) plus accumulation-order noise -> atol/rtol 2e-2 on O(1) data; fp32-out
+executes on CPU) applied to the SAME 16-bit-rounded inputs the kernel sees.  Tolerances: the
+kernels take 16-bit operands (fp16 by default, bf16 in the second flavour) and accumulate in fp32, so a result differs
+from the fp32 checker only by the final 16-bit rounding of the output (rel 2^-8 for bf16) plus accumulation-order noise -> atol/rtol 2e-2 on O(1) data; fp32-out
 paths are held to 2e-3; integer outputs (VQ indices) are exact outside fp32 near-ties.
 """
 import math
@@ -11,6 +11,8 @@ import math
 import pytest
 import torch
 import torch.nn.functional as F
+
+from generativemodels_b200 import ops
 
 pytestmark = pytest.mark.gpu
 
@@ -655,3 +657,42 @@ def test_conv_perf_probe(cuda_device, capsys):
     with capsys.disabled():
         print(f"\n[perf-probe] conv3d 256->256 k3 @16x112x80: {ms:.3f} ms, {flops / ms / 1e9:.1f} TFLOP/s")
     assert ms > 0
+
+
+def test_repack_weight_matches_host_restatement(cuda_device, monkeypatch):
+    """b200_repack_weight (one launch per weight) against the literal host restatement in tests/cpu_backend.py, bit for
+    bit: plain / split (virtual concat) / strided convolutions, linear, the folded-upsample phase sums (2-D and 3-D),
+    transposed-convolution phases and the two degenerate tap reformulations."""
+    from tests import cpu_backend
+    torch.manual_seed(0)
+    r = torch.randn
+    cases = [
+        ("conv3d", r(96, 72, 3, 3, 3), lambda w: ops.PackedConv(w, None, 1, 1)),
+        ("conv3d split", r(96, 72, 3, 3, 3), lambda w: ops.PackedConv(w, None, 1, 1, splits=[40, 32])),
+        ("conv2d stride 2", r(130, 200, 3, 3), lambda w: ops.PackedConv(w, None, 2, 1)),
+        ("conv k4", r(64, 32, 4, 4, 4), lambda w: ops.PackedConv(w, None, 2, 1)),
+        ("conv_in (tap_in)", r(256, 1, 3, 3, 3), lambda w: ops.PackedConv(w, None, 1, 1)),
+        ("out conv (tap_out)", r(1, 256, 3, 3, 3), lambda w: ops.PackedConv(w, None, 1, 1)),
+        ("linear", r(300, 520), lambda w: ops.PackedLinear(w, None)),
+        ("upsample 3d", r(64, 72, 3, 3, 3), lambda w: ops.PackedUpsampleConv(w, None)),
+        ("upsample 2d", r(48, 130, 3, 3), lambda w: ops.PackedUpsampleConv(w, None)),
+        ("convT 3d", r(72, 40, 4, 4, 4), lambda w: ops.PackedConvTranspose(w, None, 2, 1, 0)),
+        ("convT 2d", r(64, 24, 4, 4), lambda w: ops.PackedConvTranspose(w, None, 2, 1, 0)),
+    ]
+
+    def mats(p):
+        out = [ph[1] for ph in p.phases] if hasattr(p, "phases") else [p.w]
+        for extra in ("tap_in", "tap_out"):
+            if getattr(p, extra, None) is not None:
+                out.append(getattr(p, extra).w)
+        return out
+
+    for name, w, build in cases:
+        with monkeypatch.context() as mp:
+            cpu_backend.install(mp)
+            want = [m.clone() for m in mats(build(w))]
+        got = mats(build(w.cuda()))
+        assert len(got) == len(want), name
+        for g, x in zip(got, want):
+            assert g.is_cuda and g.shape == x.shape and g.dtype == x.dtype, name
+            assert torch.equal(g.cpu().view(torch.int16), x.view(torch.int16)), f"{name}: packed weights differ"

@@ -2,10 +2,12 @@
   (1) the committed golden vectors = outputs of the UNMODIFIED reference (tests/golden/*.pt), and
   (2) the CPU oracle (oracle/torch_oracle.py) on seeded models at sizes it finishes in seconds.
 
-Tolerances (stated per north_star): the kernels compute bf16 x bf16 -> fp32 with bf16 activations between ops, the
-checker is fp32 end to end, so a network forward is held to a relative L2 error of 2e-2 (observed ~3e-3) and a
-multi-step sampler trajectory to 5e-2; scheduler steps are fp32 elementwise and held to 1e-5; VQ indices are
-bit-exact except at fp32 near-ties (gap between best and second-best code below 1e-4 relative), which are counted.
+Tolerances (stated once, tests/fixture_checks.py and DESIGN.md section 3): the kernels multiply 16-bit operands (fp16 by
+default) into fp32 accumulators with 16-bit activations between ops, the checker is fp32 end to end, so a network
+forward is held to a relative L2 error of TOL_REL = 2e-2 AND a largest pointwise deviation of TOL_MAX = 4e-2 of the
+largest reference magnitude; a multi-step sampler trajectory to TOL_TRAJ = 5e-2 (max-abs 1e-1); scheduler steps are
+fp32 elementwise and held to 1e-5; VQ indices are bit-exact except at fp32 near-ties (gap between best and second-best
+code below 1e-4 relative), which are counted.
 """
 import math
 from pathlib import Path
@@ -14,11 +16,12 @@ import pytest
 import torch
 
 from oracle import torch_oracle as O
+from tests.fixture_checks import TOL_MAX, TOL_REL, TOL_TRAJ, relmax
 from tests.golden import configs as G
 
 pytestmark = pytest.mark.gpu
 GOLD = Path(__file__).resolve().parent / "golden"
-FWD_TOL, TRAJ_TOL = 2e-2, 5e-2
+FWD_TOL, TRAJ_TOL = TOL_REL, TOL_TRAJ
 
 
 def load(name):
@@ -30,10 +33,13 @@ def rel(a, b):
     return ((a - b).norm() / (b.norm() + 1e-12)).item()
 
 
-def check(a, b, tol, what):
+def check(a, b, tol=FWD_TOL, what="", tol_max=None):
+    """relative L2 < tol and normalised max-abs < tol_max (default 2 x tol: TOL_MAX for forwards)."""
     assert tuple(a.shape) == tuple(b.shape), f"{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
-    r = rel(a, b)
+    r, m = rel(a, b), relmax(a.detach(), b.detach())
+    tol_max = 2 * tol if tol_max is None else tol_max
     assert math.isfinite(r) and r < tol, f"{what}: relative L2 error {r:.3e} >= {tol}"
+    assert math.isfinite(m) and m < tol_max, f"{what}: max-abs error {m:.3e} of the reference's peak >= {tol_max}"
     return r
 
 
