@@ -126,11 +126,19 @@ def import_reference():
     return generative
 
 
+CPU_THREAD_CAP = 32
+
+
 def cpu_threads():
-    """One policy for every CPU leg: PyTorch's default intra-op pool (the physical cores it detects), never re-tuned
-    per call — round 1 auto-picked per leg and the two legs of one record disagreed by 1.7x."""
+    """One fixed policy for every CPU leg of every arm: min(host cores, 32) intra-op threads.  oneDNN's direct
+    convolutions of these shapes run SLOWER on 64 threads across sockets than on 32 (round 1 measured 247 vs 411-460
+    voxel/s on the same box when one leg auto-picked and the other took the default; round 2's default-64 run gave
+    225) — a fixed cap keeps the legs comparable and the baseline at its better operating point."""
     import torch
-    return torch.get_num_threads()
+    n = max(1, min(os.cpu_count() or 1, CPU_THREAD_CAP))
+    if torch.get_num_threads() != n:
+        torch.set_num_threads(n)
+    return n
 
 
 def cpu_c3_steps(state_dict, steps: int, warmup: int):
@@ -138,6 +146,7 @@ def cpu_c3_steps(state_dict, steps: int, warmup: int):
     seconds per step, threads, kind)."""
     import torch
     ref = import_reference()
+    cpu_threads()
     torch.manual_seed(1234)
     x = torch.randn(1, 1, *CPU_VOLUME)
     sd = {k: v.detach().cpu() for k, v in state_dict.items()}
@@ -213,6 +222,7 @@ def cpu_other_configs(states):
     import torch
     if import_reference() is None:
         return {}
+    cpu_threads()
     from generative.networks.nets import VQVAE, AutoencoderKL, ControlNet, DiffusionModelUNet
     from generative.networks.schedulers import DDIMScheduler
     out = {}

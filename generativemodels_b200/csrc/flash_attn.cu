@@ -671,6 +671,527 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
   }
 }
 
+// ================================================================================================================
+// CTA-pair variant for head_dim 512 (the 3-D UNet's T = S = 89 600 self-attention): tcgen05.mma.cta_group::2 over 256
+// queries per pair.
+//
+// Why: the single-CTA kernel above moves ~160 GB per call through the L2 -> SM path at T = S = 89 600 (every K and
+// V^T tile is fetched once per 128 queries, plus the probability replay) — ~10 TB/s, the fabric's limit, which is why
+// no tensor-side or latency-side change moved it (profiles/r1_attention_experiments.txt).  With a pair, each CTA keeps
+// its own 128 query rows (Q tile, scores, probabilities and output in its own shared / tensor memory) but the B
+// operands of every MMA are SPLIT across the pair: for QK^T each CTA stages 32 of the block's 64 keys, for PV the V^T
+// rows of 128 of the 256 output channels.  K / V^T traffic per query halves (160 -> 96 GB per call), the same 96 KB of
+// rings holds two key blocks in flight instead of one, and one issuing thread drives both SMs' tensor pipes.
+// Protocol: every barrier the issuing thread waits on lives in the leader CTA (rank 0) — TMA of both CTAs completes on
+// the leader's barrier (cp.async.bulk.tensor.cta_group::2), the peer's softmax warps arrive remotely — and every
+// barrier the softmax / producer warps wait on is signalled in BOTH CTAs by tcgen05.commit ... multicast::cluster.
+// The two-pass structure (pass 1: flash loop for output channels 0..255 + P tiles to a per-CTA slab; pass 2: replay
+// P x V^T[256..511]) and the rescale-event log are those of flash_attn_kernel<8, true>.
+// ================================================================================================================
+static constexpr uint32_t kPeerMask = 0xFEFFFFFFu;      // clears the CTA-rank bit of a shared::cluster address -> leader
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive (release at cluster scope) on a barrier given by its shared::cluster address
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void mbar_wait_cluster_warp(uint32_t bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) mbar_wait_cluster(bar, parity);
+  __syncwarp();
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+// TMA load of this CTA's half of a pair operand: data into OWN shared memory, bytes counted on the LEADER's barrier
+__device__ __forceinline__ void tma_load_3d_pair(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar & kPeerMask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit(uint32_t bar) {      // arrives on the same barrier offset in both CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void umma2_h16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_h16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
+static constexpr int kPDCH = 8;                               // head_dim 512
+static constexpr int kPKeysCta = kBKV / 2;                    // keys of a block staged by each CTA
+static constexpr int kPKChunkBytes = kPKeysCta * 64 * 2;      // 4 KB: 32 keys x 64 channels
+static constexpr int kPKStageBytes = 4 * kPKChunkBytes;       // 16 KB: four channel chunks
+static constexpr int kPKStages = kKRingBytes / kPKStageBytes; // 4 stages = two key blocks in flight
+static constexpr int kPKSteps = kPDCH / 4;                    // ring stages per key block
+static constexpr int kPVRows = 128;                           // V^T rows (output channels) staged by each CTA
+static constexpr int kPVBytes = kPVRows * kBKV * 2;           // 16 KB
+static constexpr int kPVStages = 2;
+static constexpr int kPRStageBytes = kQChunkBytes + kPVBytes; // pass-2 stage: own P tile 16 KB + V^T half 16 KB
+static constexpr int kPRStages = 7;                           // 224 KB overlaying Q | K ring | V^T
+static_assert(kPRStages * kPRStageBytes <= kPDCH * kQChunkBytes + kKRingBytes + kPVStages * kPVBytes, "pass-2 overlay");
+static constexpr int kPairSmem = kPDCH * kQChunkBytes + kKRingBytes + kPVStages * kPVBytes + 1024 + 1024;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+flash_pair_kernel(const __grid_constant__ FlashDev p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = base;
+  const uint32_t sK = sQ + kPDCH * kQChunkBytes;
+  const uint32_t sV = sK + kKRingBytes;
+  const uint32_t bars = sV + kPVStages * kPVBytes;
+  // barrier slots (8 bytes each, identical offsets in both CTAs).  "leader": only rank 0's copy is used.
+  int off = 0;
+  auto take = [&](int n) { const uint32_t a = bars + 8u * off; off += n; return a; };
+  const uint32_t q_full = take(1), q_empty = take(1);            // leader (TMA of both CTAs) / both (commit)
+  const uint32_t k_full0 = take(kPKStages), k_empty0 = take(kPKStages);
+  const uint32_t v_full0 = take(kPVStages), v_empty0 = take(kPVStages);
+  const uint32_t r_full0 = take(kPRStages), r_empty0 = take(kPRStages);
+  const uint32_t s_full0 = take(kSBuf), s_empty0 = take(kSBuf);   // both (commit) / leader (8 softmax warps)
+  const uint32_t p_full0 = take(2), p_empty0 = take(2);           // leader (8) / both (commit)
+  const uint32_t o_full = take(1), o_empty = take(1);             // both (commit) / leader (8)
+  const uint32_t p1_done = take(1);   // both, 8 arrivals each: every P tile of the pair is written, flags exchanged
+  const uint32_t r_done = take(1);    // both (commit): every pass-2 MMA has completed
+  const uint32_t tmem_slot = take(1);
+  const uint32_t ev_flags_addr = take(4);                          // int[8]: warps of rank 0, then rank 1
+  auto k_full = [&](int s) { return k_full0 + 8u * s; };
+  auto k_empty = [&](int s) { return k_empty0 + 8u * s; };
+  auto v_full = [&](int s) { return v_full0 + 8u * s; };
+  auto v_empty = [&](int s) { return v_empty0 + 8u * s; };
+  auto r_full = [&](int s) { return r_full0 + 8u * s; };
+  auto r_empty = [&](int s) { return r_empty0 + 8u * s; };
+  auto s_full = [&](int b) { return s_full0 + 8u * b; };
+  auto s_empty = [&](int b) { return s_empty0 + 8u * b; };
+  auto p_full = [&](int b) { return p_full0 + 8u * b; };
+  auto p_empty = [&](int b) { return p_empty0 + 8u * b; };
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  volatile int* ev_flags = reinterpret_cast<volatile int*>(smem_raw + (ev_flags_addr - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  if (warp == 0 && lane == 0) {
+    mbar_init(q_full, 1); mbar_init(q_empty, 1);
+    for (int s = 0; s < kPKStages; ++s) { mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); }
+    for (int s = 0; s < kPVStages; ++s) { mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1); }
+    for (int s = 0; s < kPRStages; ++s) { mbar_init(r_full(s), 1); mbar_init(r_empty(s), 1); }
+    for (int b = 0; b < kSBuf; ++b) { mbar_init(s_full(b), 1); mbar_init(s_empty(b), 8); }
+    for (int b = 0; b < 2; ++b) { mbar_init(p_full(b), 8); mbar_init(p_empty(b), 1); }
+    mbar_init(o_full, 1); mbar_init(o_empty, 8);
+    mbar_init(p1_done, 8); mbar_init(r_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {      // the same warp of both CTAs: one pair-wide allocation of all 512 columns
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  fence_before();
+  __syncthreads();
+  cluster_sync_all();                    // the peer's barriers exist before anything signals them remotely
+  fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  const uint32_t tO = tmem, tS = tmem + 256, tP = tmem + 448;
+  const int n_kv = p.n_kv;
+  const int pair_tiles = (p.q_tiles + 1) >> 1;               // pair items per (batch, head)
+
+  if (warp == 0) {
+    // =========================== TMA producer (both CTAs: own Q rows, own half of every B operand) ===========
+    int kst = 0; uint32_t kph = 0;
+    int rst = 0; uint32_t rph = 0;
+    uint32_t vcount = 0, icount = 0;
+    for (int item = pair_id; item < p.n_items; item += n_pairs, ++icount) {
+      const int pt = item % pair_tiles, bh = item / pair_tiles;
+      const int h = bh % p.heads, b = bh / p.heads;
+      const int qt = 2 * pt + (int)rank;
+      const int ch0 = h * p.dh;
+      mbar_wait_warp(r_done, (icount & 1) ^ 1u);            // previous item's pass-2 stages drained (both CTAs)
+      if (elect_one()) {
+        if (leader) mbar_expect_tx(q_full, 2 * kPDCH * kQChunkBytes);
+#pragma unroll
+        for (int c = 0; c < kPDCH; ++c)
+          tma_load_3d_pair(&p.tmQ, q_full, sQ + c * kQChunkBytes, ch0 + c * 64, qt * kBM, b);
+      }
+      __syncwarp();
+      for (int j = 0; j < n_kv + kLookahead; ++j) {
+        if (j < n_kv) {
+#pragma unroll
+          for (int step = 0; step < kPKSteps; ++step) {
+            mbar_wait_warp(k_empty(kst), kph ^ 1u);
+            if (elect_one()) {
+              if (leader) mbar_expect_tx(k_full(kst), 2 * kPKStageBytes);
+#pragma unroll
+              for (int cc = 0; cc < 4; ++cc)
+                tma_load_3d_pair(&p.tmK, k_full(kst), sK + kst * kPKStageBytes + cc * kPKChunkBytes,
+                                 ch0 + (step * 4 + cc) * 64, j * kBKV + (int)rank * kPKeysCta, b);
+            }
+            __syncwarp();
+            if (++kst == kPKStages) { kst = 0; kph ^= 1u; }
+          }
+        }
+        if (j >= kLookahead) {
+          const int vs = vcount & 1;
+          mbar_wait_warp(v_empty(vs), ((vcount >> 1) & 1) ^ 1u);
+          if (elect_one()) {
+            if (leader) mbar_expect_tx(v_full(vs), 2 * kPVBytes);
+            tma_load_3d_pair(&p.tmVt, v_full(vs), sV + vs * kPVBytes, (j - kLookahead) * kBKV,
+                             ch0 + (int)rank * kPVRows, b);
+          }
+          __syncwarp();
+          ++vcount;
+        }
+      }
+      // ---- pass 2: own P tiles + own half of V^T[256..511] through 32 KB stages overlaying Q | K ring | V^T ----
+      mbar_wait_warp(q_empty, icount & 1);                   // every pass-1 MMA of the pair has completed
+      mbar_wait_cluster_warp(p1_done, icount & 1);           // all P tiles written and fenced
+      constexpr int kPrefetch = 24;
+      if (elect_one()) {
+        for (int j = 0; j < kPrefetch && j < n_kv; ++j) tma_prefetch_3d(&p.tmP, 0, j * kBM, blockIdx.x);
+      }
+      __syncwarp();
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait_warp(r_empty(rst), rph ^ 1u);
+        if (elect_one()) {
+          if (j + kPrefetch < n_kv) tma_prefetch_3d(&p.tmP, 0, (j + kPrefetch) * kBM, blockIdx.x);
+          const uint32_t st = sQ + rst * kPRStageBytes;
+          if (leader) mbar_expect_tx(r_full(rst), 2 * kPRStageBytes);
+          tma_load_3d_pair(&p.tmP, r_full(rst), st, 0, j * kBM, blockIdx.x);
+          tma_load_3d_pair(&p.tmVt, r_full(rst), st + kQChunkBytes, j * kBKV, ch0 + 256 + (int)rank * kPVRows, b);
+        }
+        __syncwarp();
+        if (++rst == kPRStages) { rst = 0; rph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer: the leader's warp drives both SMs ===========================
+    if (leader) {
+      const uint32_t idesc_s = idesc_h16(2 * kBM, kBKV);          // S[256 x 64]: 128 rows and 32 keys per CTA
+      const uint32_t idesc_o = idesc_h16(2 * kBM, 256);           // O[256 x 256]: 128 rows and 128 channels per CTA
+      const uint32_t q_lo = desc_lo(sQ), k_lo = desc_lo(sK), v_lo = desc_lo(sV);
+      int kst = 0; uint32_t kph = 0;
+      int rst = 0; uint32_t rph = 0;
+      uint32_t scount = 0, pvcount = 0, vcount = 0, icount = 0, ocount = 0;
+      for (int item = pair_id; item < p.n_items; item += n_pairs, ++icount) {
+        mbar_wait_warp(q_full, icount & 1);
+        mbar_wait_cluster_warp(o_empty, (ocount & 1) ^ 1u);    // both CTAs' epilogues have drained O
+        ++ocount;
+        fence_after();
+        for (int j = 0; j < n_kv + kLookahead; ++j) {
+          if (j < n_kv) {
+            const int sb = scount % kSBuf;
+            mbar_wait_cluster_warp(s_empty(sb), ((scount / kSBuf) & 1) ^ 1u);
+            fence_after();
+            const uint32_t d_s = tS + sb * kBKV;
+#pragma unroll
+            for (int step = 0; step < kPKSteps; ++step) {
+              mbar_wait_warp(k_full(kst), kph);
+              fence_after();
+              if (elect_one()) {
+                const uint32_t b_lo = k_lo + kst * (kPKStageBytes >> 4);
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+#pragma unroll
+                  for (int kk = 0; kk < 4; ++kk)
+                    umma2_h16(d_s, desc64(q_lo + (step * 4 + cc) * (kQChunkBytes >> 4) + 2 * kk),
+                              desc64(b_lo + cc * (kPKChunkBytes >> 4) + 2 * kk), idesc_s,
+                              (step | cc | kk) != 0 ? 1u : 0u);
+                }
+                umma2_commit(k_empty(kst));
+                if (step == kPKSteps - 1) umma2_commit(s_full(sb));
+              }
+              __syncwarp();
+              if (++kst == kPKStages) { kst = 0; kph ^= 1u; }
+            }
+            ++scount;
+          }
+          if (j >= kLookahead) {
+            const int pb = pvcount & 1, vs = vcount & 1;
+            mbar_wait_cluster_warp(p_full(pb), (pvcount >> 1) & 1);
+            mbar_wait_warp(v_full(vs), (vcount >> 1) & 1);
+            fence_after();
+            if (elect_one()) {
+              const uint32_t a_tmem = tP + pb * 32;
+              const uint32_t b_lo = v_lo + vs * (kPVBytes >> 4);
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                umma2_h16_ts(tO, a_tmem + 8u * kk, desc64(b_lo + 2 * kk), idesc_o, (j > kLookahead || kk > 0) ? 1u : 0u);
+              umma2_commit(v_empty(vs));
+              umma2_commit(p_empty(pb));
+              if (j == n_kv + kLookahead - 1) {
+                umma2_commit(o_full);
+                umma2_commit(q_empty);
+              }
+            }
+            __syncwarp();
+            ++pvcount;
+            ++vcount;
+          }
+        }
+        // ---- pass 2 ----
+        mbar_wait_cluster_warp(p1_done, icount & 1);           // rescale flags of all eight softmax warps are visible
+        bool gated = false;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) gated |= ev_flags[e] != 0;
+        mbar_wait_cluster_warp(o_empty, (ocount & 1) ^ 1u);    // pass-1 epilogues have drained O
+        ++ocount;
+        fence_after();
+        for (int j = 0; j < n_kv; ++j) {
+          const int pb = pvcount & 1;
+          mbar_wait_warp(r_full(rst), rph);
+          if (gated) mbar_wait_cluster_warp(p_full(pb), (pvcount >> 1) & 1);
+          fence_after();
+          if (elect_one()) {
+            const uint32_t a_lo = q_lo + rst * (kPRStageBytes >> 4);
+            const uint32_t b_lo = a_lo + (kQChunkBytes >> 4);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma2_h16(tO, desc64(a_lo + 2 * kk), desc64(b_lo + 2 * kk), idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+            umma2_commit(r_empty(rst));
+            if (gated) umma2_commit(p_empty(pb));
+            if (j == n_kv - 1) {
+              umma2_commit(o_full);
+              umma2_commit(r_done);
+            }
+          }
+          __syncwarp();
+          if (++rst == kPRStages) { rst = 0; rph ^= 1u; }
+          if (gated) ++pvcount;
+        }
+      }
+    }
+  } else {
+    // =========================== softmax + epilogue warps (both CTAs, own 128 rows) ===========================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    // shared::cluster addresses of the LEADER's copies of the barriers these warps arrive on, and of both CTAs'
+    // p1_done / flag words
+    const uint32_t l_s_empty0 = s_empty0 & kPeerMask, l_p_full0 = p_full0 & kPeerMask, l_o_empty = o_empty & kPeerMask;
+    const uint32_t p1_done_a[2] = {mapa_u32(p1_done, 0), mapa_u32(p1_done, 1)};
+    const uint32_t flag_a[2] = {mapa_u32(ev_flags_addr + 4u * (rank * 4 + q), 0), mapa_u32(ev_flags_addr + 4u * (rank * 4 + q), 1)};
+    uint32_t scount = 0, pcount = 0, ocount = 0, icount = 0;
+    h16* slab_row = p.pslab + (long long)blockIdx.x * p.p_pitch + row * kBKV;
+    float* ev_fac = p.ev_fac + ((long long)blockIdx.x * 4 + q) * (long long)n_kv * 32;
+    int* ev_blk = p.ev_blk + ((long long)blockIdx.x * 4 + q) * (long long)n_kv;
+    for (int item = pair_id; item < p.n_items; item += n_pairs, ++icount) {
+      const int pt = item % pair_tiles, bh = item / pair_tiles;
+      const int h = bh % p.heads, b = bh / p.heads;
+      const int qt = 2 * pt + (int)rank;
+      float m_used = -INFINITY, l_run = 0.f;
+      int n_ev = 0;
+      for (int j = 0; j < n_kv; ++j, ++scount, ++pcount) {
+        const int sb = scount % kSBuf;
+        mbar_wait(s_full(sb), (scount / kSBuf) & 1);
+        fence_after();
+        uint32_t raw[64];
+        tmem_ld32(tS + lane_addr + sb * kBKV, raw);
+        tmem_ld32(tS + lane_addr + sb * kBKV + 32, raw + 32);
+        tmem_ld_wait();
+        fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(l_s_empty0 + 8u * sb);
+        const int kv_valid = p.S - j * kBKV;
+        float mx8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) mx8[e] = -INFINITY;
+        if (kv_valid >= kBKV) {
+#pragma unroll
+          for (int c = 0; c < 64; ++c) mx8[c & 7] = fmaxf(mx8[c & 7], __uint_as_float(raw[c]));
+        } else {
+#pragma unroll
+          for (int c = 0; c < 64; ++c) {
+            const float sv = c < kv_valid ? __uint_as_float(raw[c]) : -INFINITY;
+            raw[c] = __float_as_uint(sv);
+            mx8[c & 7] = fmaxf(mx8[c & 7], sv);
+          }
+        }
+        const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
+                               fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7]))) * p.scale_log2;
+        const bool need = (mx > m_used + kRescaleThreshold);
+        const float m_new = need ? mx : m_used;
+        const float factor = (need && m_used > -INFINITY) ? exp2f(m_used - m_new) : 1.0f;
+        const unsigned any = __ballot_sync(0xffffffffu, need && m_used > -INFINITY);
+        const int pb = pcount & 1;
+        if (any) {
+          if (j >= 1) {            // O holds blocks < j: the PV of block j - 1 must have completed before O is rewritten
+            const uint32_t prev = pcount - 1;
+            mbar_wait(p_empty(prev & 1), (prev >> 1) & 1);
+          }
+          fence_after();
+          for (int c0 = 0; c0 < 256; c0 += 32) {
+            uint32_t o[32];
+            tmem_ld32(tO + lane_addr + c0, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * factor);
+            tmem_st32(tO + lane_addr + c0, o);
+          }
+          tmem_st_wait();
+          fence_before();
+          ev_fac[(long long)n_ev * 32 + lane] = factor;
+          if (lane == 0) ev_blk[n_ev] = j;
+          ++n_ev;
+        }
+        l_run *= factor;
+        m_used = m_new;
+        const float neg_m = -m_used;
+        float sum8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sum8[e] = 0.f;
+        uint32_t pw[32];
+#pragma unroll
+        for (int w = 0; w < 32; ++w) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(raw[2 * w]), p.scale_log2, neg_m));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(raw[2 * w + 1]), p.scale_log2, neg_m));
+          sum8[(2 * w) & 7] += p0;
+          sum8[(2 * w + 1) & 7] += p1;
+          h162 hh = f2h2(p0, p1);
+          pw[w] = *reinterpret_cast<uint32_t*>(&hh);
+        }
+        if (pcount >= 2) mbar_wait(p_empty(pb), ((pcount >> 1) & 1) ^ 1u);
+        tmem_st32(tP + lane_addr + pb * 32, pw);
+        {
+          h16* dst = slab_row + (long long)j * (kBM * kBKV);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) stg256(dst + g * 16, pw + g * 8);
+        }
+        tmem_st_wait();
+        const float lsum = ((sum8[0] + sum8[1]) + (sum8[2] + sum8[3])) + ((sum8[4] + sum8[5]) + (sum8[6] + sum8[7]));
+        l_run += lsum;
+        fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(l_p_full0 + 8u * pb);
+      }
+      // publish this warp's "logged a rescale" flag to both CTAs, make the slab visible to the TMA reads of pass 2,
+      // then arrive on both CTAs' p1_done
+      __threadfence();
+      asm volatile("fence.proxy.async.global;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        st_cluster_u32(flag_a[0], n_ev > 0 ? 1u : 0u);
+        st_cluster_u32(flag_a[1], n_ev > 0 ? 1u : 0u);
+        mbar_arrive_cluster(p1_done_a[0]);
+        mbar_arrive_cluster(p1_done_a[1]);
+      }
+      mbar_wait_cluster(p1_done, icount & 1);
+      bool gated = false;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) gated |= ev_flags[e] != 0;
+      const float inv = 1.0f / l_run;
+      const int t = qt * kBM + row;
+      const bool ok = t < p.T;
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 1 && gated) {
+          int e_next = 0;
+          int next_blk = (n_ev > 0) ? ev_blk[0] : 0x7fffffff;
+          for (int j = 0; j < n_kv; ++j, ++pcount) {
+            const int pb = pcount & 1;
+            if (pcount >= 2) mbar_wait(p_empty(pb), ((pcount >> 1) & 1) ^ 1u);
+            if (j == next_blk) {
+              const uint32_t prev = pcount - 1;
+              mbar_wait(p_empty(prev & 1), (prev >> 1) & 1);
+              fence_after();
+              const float factor = ev_fac[(long long)e_next * 32 + lane];
+              for (int c0 = 0; c0 < 256; c0 += 32) {
+                uint32_t o[32];
+                tmem_ld32(tO + lane_addr + c0, o);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * factor);
+                tmem_st32(tO + lane_addr + c0, o);
+              }
+              tmem_st_wait();
+              fence_before();
+              ++e_next;
+              next_blk = (e_next < n_ev) ? ev_blk[e_next] : 0x7fffffff;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(l_p_full0 + 8u * pb);
+          }
+        }
+        // ---- epilogue: O / l (+ residual) -> h16 ----
+        mbar_wait(o_full, ocount & 1);
+        ++ocount;
+        fence_after();
+        const long long col0 = (long long)h * p.dh + (long long)pass * 256;
+        h16* orow = p.out + b * p.out_bstride + (long long)t * p.out_pitch + col0;
+        const h16* rrow = p.res ? p.res + b * p.res_bstride + (long long)t * p.res_pitch + col0 : nullptr;
+        for (int c0 = 0; c0 < 256; c0 += 32) {
+          uint32_t o[32];
+          tmem_ld32(tO + lane_addr + c0, o);
+          tmem_ld_wait();
+          if (ok) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(o[g * 8 + e]) * inv;
+              if (rrow) {
+                float rf[8];
+                unpack8(__ldg(reinterpret_cast<const uint4*>(rrow + c0 + g * 8)), rf);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] += rf[e];
+              }
+              *reinterpret_cast<uint4*>(orow + c0 + g * 8) = pack8(f);
+            }
+          }
+        }
+        fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(l_o_empty);
+      }
+    }
+  }
+  fence_before();
+  __syncthreads();
+  cluster_sync_all();            // neither CTA may leave (or free tensor memory) while the other still uses the pair
+  if (warp == 1) {
+    fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
 static PFN_cuTensorMapEncodeTiled g_encode = nullptr;
 static std::once_flag g_once;
 static void load_encode() {
@@ -702,9 +1223,11 @@ static ReplayPlan replay_plan(const b200_flash_params* a) {
   ReplayPlan r;
   memset(&r, 0, sizeof(r));
   if (a->dh != 512) return r;
+  // CTA pairs: one work item = 256 queries (two 128-row tiles), one CTA per tile
   const long long q_tiles = (a->T + kBM - 1) / kBM;
-  const long long items = (long long)a->B * a->heads * q_tiles;
-  r.grid = (int)(items < sm_count() ? items : sm_count());
+  const long long items = (long long)a->B * a->heads * ((q_tiles + 1) / 2);
+  const long long pairs = sm_count() / 2;
+  r.grid = 2 * (int)(items < pairs ? items : pairs);
   r.n_kv = (a->S + kBKV - 1) / kBKV;
   r.slab_bytes = (long long)r.grid * kBM * r.n_kv * kBKV * 2;
   r.fac_bytes = (long long)r.grid * 4 * r.n_kv * 32 * 4;
@@ -753,7 +1276,8 @@ extern "C" int b200_attention_flash(const b200_flash_params* a, void* stream_v) 
                    (long long)a->workspace_bytes, rp.total);
     B200_CHECK_ARG(((uintptr_t)a->workspace & 255) == 0, "attention_flash: workspace must be 256-byte aligned");
   }
-  const long long items = (long long)a->B * a->heads * d.q_tiles * (replay ? 1 : d.n_dv);
+  const long long items = replay ? (long long)a->B * a->heads * ((d.q_tiles + 1) / 2)
+                                 : (long long)a->B * a->heads * d.q_tiles * d.n_dv;
   B200_CHECK_ARG(items < (1ll << 31), "attention_flash: too many work items");
   d.n_items = (int)items;
   d.scale_log2 = a->scale * 1.4426950408889634f;
@@ -764,13 +1288,14 @@ extern "C" int b200_attention_flash(const b200_flash_params* a, void* stream_v) 
   int rc;
   if ((rc = fa::encode3(&d.tmQ, a->q, C, a->T, a->B, (cuuint64_t)a->q_pitch * 2, (cuuint64_t)a->T * a->q_pitch * 2, 64,
                         fa::kBM, "Q"))) return rc;
+  // pair kernel: each CTA stages half of every B operand (32 of a block's 64 keys; 128 of the 256 V^T rows)
   if ((rc = fa::encode3(&d.tmK, a->k, C, a->S, a->B, (cuuint64_t)a->k_pitch * 2, (cuuint64_t)a->S * a->k_pitch * 2, 64,
-                        fa::kBKV, "K"))) return rc;
+                        replay ? fa::kPKeysCta : fa::kBKV, "K"))) return rc;
   if ((rc = fa::encode3(&d.tmVt, a->vt, a->S, C, a->B, (cuuint64_t)a->vt_pitch * 2, (cuuint64_t)C * a->vt_pitch * 2,
-                        fa::kBKV, d.dv, "V^T"))) return rc;
+                        fa::kBKV, replay ? fa::kPVRows : d.dv, "V^T"))) return rc;
 
   const int smem = d.d_chunks * fa::kQChunkBytes + fa::kKRingBytes + d.dv * fa::kBKV * 2 + 1024 + 512;
-  const int grid = d.n_items < sm_count() ? d.n_items : sm_count();
+  const int grid = replay ? rp.grid : (d.n_items < sm_count() ? d.n_items : sm_count());
   if (replay) {
     B200_CHECK_ARG(grid == rp.grid && d.n_kv == rp.n_kv, "attention_flash: internal replay plan mismatch");
     uint8_t* ws = static_cast<uint8_t*>(a->workspace);
@@ -796,8 +1321,16 @@ extern "C" int b200_attention_flash(const b200_flash_params* a, void* stream_v) 
     case 2: B200_FLASH_LAUNCH(2, false); break;
     case 4: B200_FLASH_LAUNCH(4, false); break;
     default:
-      if (replay) B200_FLASH_LAUNCH(8, true);
-      else B200_FLASH_LAUNCH(8, false);
+      if (replay) {
+        static bool pair_attr_done = false;
+        if (!pair_attr_done) {
+          B200_CUDA(cudaFuncSetAttribute(fa::flash_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fa::kPairSmem));
+          pair_attr_done = true;
+        }
+        fa::flash_pair_kernel<<<grid, fa::kThreads, fa::kPairSmem, stream>>>(d);       // clusters of 2 (__cluster_dims__)
+      } else {
+        B200_FLASH_LAUNCH(8, false);
+      }
       break;
   }
 #undef B200_FLASH_LAUNCH

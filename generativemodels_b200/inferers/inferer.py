@@ -46,11 +46,10 @@ def _with_seg(diffusion_model, seg):
 
 
 # Replay the network from a CUDA graph inside ``sample`` when one step is launch-latency-bound (a latent UNet step is
-# 300-500 dependent launches of a few microseconds: C2 at batch 1 goes from 3.4 to 8.4 samples/s).  Off by default
-# this round — the wrapper (generativemodels_b200.cuda_graph.graphed) is verified on the GPU when passed explicitly
-# (tests/test_parity_gpu.py::test_cuda_graph_replay_matches_eager, tools/run_configs.py, the bundle Sampler); doing it
-# implicitly for every caller has not had its own GPU run yet.  ``B200_AUTO_GRAPH=1`` or setting this flag turns it on.
-AUTO_CUDA_GRAPH = os.environ.get("B200_AUTO_GRAPH", "0") == "1"
+# 150-500 dependent launches of a few microseconds: C2 at batch 1 goes from 3.4 to 8.7 samples/s).  On by default since
+# round 2 (the -m gpu suite runs with it; graph-replayed and eager sampling are bit-identical, incl. PNDM's history).
+# ``B200_AUTO_GRAPH=0`` or setting this flag to False turns it off.
+AUTO_CUDA_GRAPH = os.environ.get("B200_AUTO_GRAPH", "1") != "0"
 _AUTO_GRAPH_MAX_NUMEL = 1 << 18          # per-sample elements of the network input (64^3, 512^2): above, work dominates
 _AUTO_GRAPH_MIN_STEPS = 8                # capture costs ~3 forwards
 

@@ -112,6 +112,19 @@ def packed_linear(owner: nn.Module, name: str) -> ops.PackedLinear:
     return h.packed()
 
 
+def packed_linear_stack(owner: nn.Module, names: Sequence[str]) -> ops.PackedLinear:
+    """The linears ``names`` of ``owner`` (same input) as one stacked GEMM weight, cached like packed_linear."""
+    lins = [getattr(owner, n) for n in names]
+    cache = owner.__dict__.setdefault("_pack_cache", {})
+    key = ("stack", tuple(names))
+    k = (key, _key(*[t for lin in lins for t in (lin.weight, lin.bias)]))      # same entry layout as _Cached
+    hit = cache.get(key)
+    if hit is None or hit[0] != k:
+        hit = (k, ops.PackedLinear.stacked([lin.weight for lin in lins], [lin.bias for lin in lins]))
+        cache[key] = hit
+    return hit[1]
+
+
 def f32(p: torch.Tensor) -> torch.Tensor:
     return p if p.dtype == torch.float32 else p.float()
 

@@ -20,7 +20,7 @@ import torch.nn as nn
 from ... import ops
 from ...ops import ACT_SILU, CL
 from ..blocks.spade_norm import SPADE
-from .._holders import Convolution, f32, on_input_device, packed_linear, require_cuda
+from .._holders import Convolution, f32, on_input_device, packed_linear, packed_linear_stack, require_cuda
 
 __all__ = ["DiffusionModelUNet"]
 
@@ -53,16 +53,24 @@ def _sdp(owner: nn.Module, xq: CL, xkv: CL, heads: int, dh: int, scale: float, r
          bias_qkv: bool) -> CL:
     """scaled-dot-product attention of ``xq`` over ``xkv`` with this module's to_q/to_k/to_v."""
     S = xkv.spatial
-    q = ops.linear(xq, packed_linear(owner, "to_q"))
-    k = ops.linear(xkv, packed_linear(owner, "to_k"))
+    inner = heads * dh
+    if xq is xkv and inner % 16 == 0:
+        # self-attention: q and k from ONE GEMM over the stacked [to_q; to_k] weights; the attention kernels read
+        # them as column slices of the [N, T, 2C] result (row pitch from the stride)
+        qk = ops.linear(xq, packed_linear_stack(owner, ("to_q", "to_k")))
+        qk_rows = _rows(qk)
+        q_rows, k_rows = qk_rows[:, :, :inner], qk_rows[:, :, inner:2 * inner]
+    else:
+        q_rows = _rows(ops.linear(xq, packed_linear(owner, "to_q")))
+        k_rows = _rows(ops.linear(xkv, packed_linear(owner, "to_k")))
     use_tc = dh % 64 == 0 and S >= 64
     if use_tc:
         vt = ops.linear_transposed(_rows(xkv), xkv.C, packed_linear(owner, "to_v"))
-        o = ops.attention(_rows(q), _rows(k), None, heads, dh, scale, vt=vt,
+        o = ops.attention(q_rows, k_rows, None, heads, dh, scale, vt=vt,
                           residual=None if residual is None else _rows(residual))
         return CL(o.reshape(xq.t.shape[0], xq.D, xq.H, xq.W, o.shape[-1]), heads * dh, xq.spatial_dims)
     v = ops.linear(xkv, packed_linear(owner, "to_v"))
-    o = ops.attention(_rows(q), _rows(k), _rows(v), heads, dh, scale)
+    o = ops.attention(q_rows, k_rows, _rows(v), heads, dh, scale)
     out = CL(o.reshape(xq.t.shape[0], xq.D, xq.H, xq.W, o.shape[-1]), heads * dh, xq.spatial_dims)
     if residual is not None:
         out = ops.axpy(out, residual, 1.0, inplace=True)

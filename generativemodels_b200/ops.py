@@ -216,6 +216,34 @@ class PackedLinear:
         self.stride = (1, 1, 1)
 
     @classmethod
+    def stacked(cls, weights, biases) -> "PackedLinear":
+        """Several nn.Linear layers with the same input applied as ONE GEMM: their weight matrices stacked along the
+        output dimension (each repacked by its own launch into its row range of one matrix).  Every layer but the
+        last must have a multiple of 16 output features (the packed row granule)."""
+        ws = [_src_f32(w) for w in weights]
+        K = ws[0].shape[1]
+        outs = [w.shape[0] for w in ws]
+        if any(w.shape[1] != K for w in ws) or any(o % 16 for o in outs[:-1]):
+            raise ValueError("stacked linears need a common input width and 16-row-aligned blocks")
+        lib = _lib.require_device()
+        pitch = round_up(K, 64)
+        w16 = torch.empty((round_up(sum(outs), 16), pitch), dtype=H16, device=ws[0].device)
+        blk = (_lib.RepackBlock * 1)()
+        blk[0].col0, blk[0].cin0, blk[0].cs, blk[0].ntaps = 0, 0, K, 1
+        row = 0
+        for w, o in zip(ws, outs):
+            rows_pad = round_up(o, 16)
+            check(lib.b200_repack_weight(w.data_ptr(), o, K, 1, 0, _lib.REPACK_BLOCKS, blk, 1,
+                                         w16.data_ptr() + row * pitch * 2, rows_pad, pitch, _stream()),
+                  "b200_repack_weight")
+            row += o
+        bias = None
+        if any(b is not None for b in biases):
+            bias = torch.cat([(_src_f32(b) if b is not None else torch.zeros(o, device=ws[0].device))
+                              for b, o in zip(biases, outs)]).contiguous()
+        return cls.from_packed(w16, sum(outs), K, bias)
+
+    @classmethod
     def from_packed(cls, w16: torch.Tensor, cout: int, K: int, bias: torch.Tensor | None) -> "PackedLinear":
         self = cls.__new__(cls)
         self.cout, self.K, self.w = cout, K, w16
@@ -591,10 +619,11 @@ def groupnorm_affine(srcs: CL | Sequence[CL], groups: int, eps: float, gamma: to
     return affine
 
 
-# Single-launch GroupNorm for small tensors (b200_groupnorm_fused).  STAGED: written after round 1's GPU budget was
-# spent — compiled and exercised through the CPU stand-in only, so it is off until `B200_STAGED=1 pytest -m gpu` has
-# run its tests on a B200 (tests/test_kernels_gpu.py::test_groupnorm_fused_small).
-_GN_SMALL = os.environ.get("B200_GN_SMALL", "0") == "1"
+# Single-launch GroupNorm for small tensors (b200_groupnorm_fused): one CTA per (sample, group) computes the statistics
+# and applies them — GroupNorm is 138 of the 309 launches of a C2 latent-UNet step as three kernels.  Verified on a B200
+# in round 2 (the full -m gpu suite with it on; C2 UNet step 2.28 -> 1.88 ms, brain-LDM UNet 7.65 -> 7.39 ms, graph
+# replayed).  B200_GN_SMALL=0 turns it off.
+_GN_SMALL = os.environ.get("B200_GN_SMALL", "1") != "0"
 _GN_SMALL_MAX_ELEMS = 1 << 17           # spatial * channels-per-group handled by one CTA
 
 
@@ -800,8 +829,13 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, dh:
     the PV epilogue on the tensor-core path only (callers add it themselves otherwise).
     """
     lib = _lib.require_device()
-    B, T, qp = q.shape
+    B, T, _ = q.shape
     S = k.shape[1]
+    # row pitches come from the strides: q and k may be column slices of ONE fused [B, T, 2C] projection
+    qp, kp = q.stride(1), k.stride(1)
+    for name, t_ in (("q", q), ("k", k)):
+        if t_.stride(2) != 1 or t_.stride(0) != t_.shape[1] * t_.stride(1) or t_.stride(1) % 8 or t_.data_ptr() % 16:
+            raise ValueError(f"attention: {name} must be rows of a packed [B, T, pitch] tensor (pitch % 8 == 0)")
     out = torch.empty((B, T, round_up(heads * dh, 8)), dtype=H16, device=q.device)
     use_tc = (dh % 64 == 0) and S >= _TC_ATTN_MIN_S and vt is not None
     if not use_tc:
@@ -810,7 +844,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, dh:
         if out.shape[2] > heads * dh:
             out.zero_()
         check(lib.b200_attention_small(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, T, S, heads, dh,
-                                       qp, k.shape[2], v.shape[2], out.shape[2], scale, _stream()),
+                                       qp, kp, v.shape[2], out.shape[2], scale, _stream()),
               "b200_attention_small")
         return out
     if dh in _FLASH_HEAD_DIMS and not _FORCE_UNFUSED_ATTENTION:
@@ -818,7 +852,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, dh:
         fp.q, fp.k, fp.vt, fp.out = q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr()
         fp.res = _ptr(residual)
         fp.B, fp.T, fp.S, fp.heads, fp.dh = B, T, S, heads, dh
-        fp.q_pitch, fp.k_pitch, fp.vt_pitch, fp.out_pitch = qp, k.shape[2], vt.shape[2], out.shape[2]
+        fp.q_pitch, fp.k_pitch, fp.vt_pitch, fp.out_pitch = qp, kp, vt.shape[2], out.shape[2]
         fp.res_pitch = 0 if residual is None else residual.shape[2]
         fp.scale = scale
         if out.shape[2] > heads * dh:
@@ -852,8 +886,8 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, dh:
                 p.a_C[0], p.a_pitch[0] = dh, qp
                 p.in_N, p.in_D, p.in_H, p.in_W = 1, 1, 1, tc
                 p.stride_d = p.stride_h = p.stride_w = 1
-                p.w_ptr = k.data_ptr() + (b * S * k.shape[2] + h * dh) * 2
-                p.w_rows, p.w_pitch, p.w_K = S, k.shape[2], dh
+                p.w_ptr = k.data_ptr() + (b * S * kp + h * dh) * 2
+                p.w_rows, p.w_pitch, p.w_K = S, kp, dh
                 _fill_segs(p, [(0, 0, 0, 0, 0, nk)])
                 p.out_ptr, p.out_dtype = scores.data_ptr(), DT_F32
                 p.out_N, p.out_D, p.out_H, p.out_W = 1, 1, 1, tc

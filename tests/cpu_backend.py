@@ -34,6 +34,13 @@ def bf16(ptr, count):
     return None if a is None else torch.from_numpy(a.view(np.int16)).view(ops.H16)
 
 
+def rows16(ptr, n_rows, pitch, cols):
+    """[n_rows, cols] view of 16-bit rows `pitch` elements apart that may be a column slice of a wider buffer: only
+    (n_rows - 1) * pitch + cols elements are touched."""
+    flat = bf16(ptr, (n_rows - 1) * pitch + cols)
+    return torch.as_strided(flat, (n_rows, cols), (pitch, 1))
+
+
 def i64(ptr, count):
     a = _np(ptr, count, C.c_int64)
     return None if a is None else torch.from_numpy(a)
@@ -266,8 +273,8 @@ class FakeLib:
         a = _obj(a)
         B, T, S, heads, dh = a.B, a.T, a.S, a.heads, a.dh
         Cc = heads * dh
-        qq = bf16(a.q, B * T * a.q_pitch).view(B, T, a.q_pitch)[:, :, :Cc].float().view(B, T, heads, dh).transpose(1, 2)
-        kk = bf16(a.k, B * S * a.k_pitch).view(B, S, a.k_pitch)[:, :, :Cc].float().view(B, S, heads, dh).transpose(1, 2)
+        qq = rows16(a.q, B * T, a.q_pitch, Cc).float().view(B, T, heads, dh).transpose(1, 2)
+        kk = rows16(a.k, B * S, a.k_pitch, Cc).float().view(B, S, heads, dh).transpose(1, 2)
         vv = bf16(a.vt, B * Cc * a.vt_pitch).view(B, Cc, a.vt_pitch)[:, :, :S].float().transpose(1, 2)
         vv = vv.reshape(B, S, heads, dh).transpose(1, 2)
         out = (torch.softmax(a.scale * qq @ kk.transpose(-1, -2), -1) @ vv).transpose(1, 2).reshape(B, T, Cc)
@@ -282,8 +289,8 @@ class FakeLib:
             q_pos0 = int(_np(pos_dev, 1, C.c_int32)[0])
             S = q_pos0 + T
         Cc = heads * dh
-        qq = bf16(q, B * T * qp).view(B, T, qp)[:, :, :Cc].float().view(B, T, heads, dh).transpose(1, 2)
-        kk = bf16(k, B * kv_rows * kp).view(B, kv_rows, kp)[:, :S, :Cc].float().view(B, S, heads, dh).transpose(1, 2)
+        qq = rows16(q, B * T, qp, Cc).float().view(B, T, heads, dh).transpose(1, 2)
+        kk = rows16(k, B * kv_rows, kp, Cc).float().view(B, kv_rows, Cc)[:, :S].reshape(B, S, heads, dh).transpose(1, 2)
         vv = bf16(v, B * kv_rows * vp).view(B, kv_rows, vp)[:, :S, :Cc].float().view(B, S, heads, dh).transpose(1, 2)
         sc = scale * qq @ kk.transpose(-1, -2)
         if causal:

@@ -250,7 +250,7 @@ def test_attention_tc_host_logic(monkeypatch):
 
 
 def test_auto_cuda_graph_policy(monkeypatch):
-    """inferers.AUTO_CUDA_GRAPH (off by default): which sample() calls would replay the network from a CUDA graph."""
+    """inferers.AUTO_CUDA_GRAPH (on by default since round 2): which sample() calls replay the network from a CUDA graph."""
     import torch.nn as nn
 
     import generativemodels_b200.inferers.inferer as I
@@ -269,7 +269,9 @@ def test_auto_cuda_graph_policy(monkeypatch):
     made = []
     monkeypatch.setattr(I, "graphed", lambda m: (made.append(m), ("graph-of", m))[1])
     net = nn.Linear(2, 2)
-    assert I.AUTO_CUDA_GRAPH is False and I._maybe_graphed(net, FakeNoise(100), Sched(50), None) is net
+    assert I.AUTO_CUDA_GRAPH is True
+    monkeypatch.setattr(I, "AUTO_CUDA_GRAPH", False)
+    assert I._maybe_graphed(net, FakeNoise(100), Sched(50), None) is net
     monkeypatch.setattr(I, "AUTO_CUDA_GRAPH", True)
     w = I._maybe_graphed(net, FakeNoise(3 * 64 * 64), Sched(50), None)
     assert w == ("graph-of", net) and I._maybe_graphed(net, FakeNoise(3 * 64 * 64), Sched(50), None) is w

@@ -358,9 +358,6 @@ def test_groupnorm_concat(cuda_device):
     assert_close(ops.from_cl(out), ref, 1e-2, "groupnorm concat")
 
 
-@pytest.mark.skipif(__import__("os").environ.get("B200_STAGED") != "1",
-                    reason="staged: b200_groupnorm_fused was written after round 1's GPU budget was spent; "
-                           "run with B200_STAGED=1 on a B200 before enabling ops._GN_SMALL")
 @pytest.mark.parametrize("shape,groups", [((2, 64, 16, 16), 32), ((1, 128, 64, 64), 32), ((2, 32, 5, 7, 5), 8),
                                           ((1, 768, 5, 7, 5), 32), ((2, 24, 9, 11), 8), ((3, 20, 6, 6), 4),
                                           ((1, 12, 33), 12)])

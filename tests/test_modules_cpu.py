@@ -90,10 +90,11 @@ def test_time_embedding_projections_are_one_launch_cpu(monkeypatch):
 
 
 def test_small_groupnorm_routing_cpu(monkeypatch):
-    """ops._GN_SMALL (staged, default off): small GroupNorms go through ONE b200_groupnorm_fused call — also over the
+    """ops._GN_SMALL (on by default since round 2): small GroupNorms go through ONE b200_groupnorm_fused call — also over the
     virtual concat of the up path — and the network output is unchanged."""
     from generativemodels_b200 import _lib, ops
-    assert ops._GN_SMALL is False
+    assert ops._GN_SMALL is True
+    monkeypatch.setattr(ops, "_GN_SMALL", False)
     kw = G.UNET_CASES["unet3d_attn"]
     torch.manual_seed(0)
     m = G.randomize_zero_params(nets().DiffusionModelUNet(**kw)).eval()
