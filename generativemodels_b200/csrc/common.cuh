@@ -6,6 +6,8 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <stdlib.h>
+#include <utility>
 #include "../../include/b200gen.h"
 
 namespace b200 {
@@ -35,6 +37,45 @@ int cuda_fail(cudaError_t e, const char* what);
   } while (0)
 
 int sm_count();
+
+// ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  Every kernel of this library is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization and starts with pdl_launch_dependents() (the next kernel in the
+// stream may be scheduled as soon as every CTA of this one is resident) and pdl_wait() before its first global-memory
+// access (blocks until the preceding grid has COMPLETED and its writes are visible — so the data dependencies are
+// exactly those of plain stream order).  What overlaps is the next kernel's launch latency and prologue (barrier
+// initialisation, tensor-memory allocation, tensor-map fetch) with this kernel's execution: a latent-UNet step is
+// 150-300 dependent kernels of a few microseconds each (latency-bound configurations).
+// B200_PDL=0 in the environment launches without the attribute (the device-side instructions are then no-ops).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_entry() { pdl_launch_dependents(); pdl_wait(); }
+
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 

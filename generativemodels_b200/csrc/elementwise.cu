@@ -11,6 +11,7 @@ namespace b200 {
 // ------------------------------------------------------------------------------------------------
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int C, long long spatial,
                                     h16* __restrict__ y, int pitch) {
+  pdl_entry();
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const long long s0 = (long long)blockIdx.x * 32;
@@ -33,6 +34,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int C, long lon
 template <typename T>
 __global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, int C, long long spatial, int pitch,
                                     float* __restrict__ y) {
+  pdl_entry();
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const long long s0 = (long long)blockIdx.x * 32;
@@ -62,6 +64,7 @@ __global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, int C, long long sp
 // ------------------------------------------------------------------------------------------------
 __global__ void upsample2x_kernel(const uint4* __restrict__ x, int N, int D, int H, int W, int pv, int dims,
                                   uint4* __restrict__ y) {
+  pdl_entry();
   const int OD = dims == 3 ? 2 * D : D, OH = 2 * H, OW = 2 * W;
   const long long total = (long long)N * OD * OH * OW * pv;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -79,6 +82,7 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ x, int N, int D, int
 
 __global__ void avgpool2_kernel(const uint4* __restrict__ x, int N, int D, int H, int W, int pv, int dims,
                                 uint4* __restrict__ y) {
+  pdl_entry();
   const int OD = dims == 3 ? D / 2 : D, OH = H / 2, OW = W / 2;
   const int kd = dims == 3 ? 2 : 1;
   const float inv = 1.0f / (float)(kd * 4);
@@ -112,6 +116,7 @@ __global__ void avgpool2_kernel(const uint4* __restrict__ x, int N, int D, int H
 
 __global__ void axpy_h16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, float alpha,
                                  uint4* __restrict__ y, long long nvec) {
+  pdl_entry();
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < nvec;
        idx += (long long)gridDim.x * blockDim.x) {
     float fa[8], fb[8];
@@ -125,6 +130,7 @@ __global__ void axpy_h16_kernel(const uint4* __restrict__ a, const uint4* __rest
 
 __global__ void copy_channels_kernel(const h16* __restrict__ src, int C, int src_pitch,
                                      h16* __restrict__ dst, int dst_pitch, int dst_off, long long rows, int vec) {
+  pdl_entry();
   const int per_row = C / vec;
   const long long total = rows * per_row;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -145,6 +151,7 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 
 __global__ void geglu_kernel(const h16* __restrict__ x, long long M, int H, int x_pitch,
                              h16* __restrict__ y, int y_pitch) {
+  pdl_entry();
   const int HV = H / 8;
   const long long total = M * HV;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -166,6 +173,7 @@ __global__ void geglu_kernel(const h16* __restrict__ x, long long M, int H, int 
 template <int TPR>
 __global__ void softmax_rows_kernel(const float* __restrict__ s, long long M, int S, long long s_pitch,
                                     h16* __restrict__ p, long long p_pitch) {
+  pdl_entry();
   constexpr int RPB = 256 / TPR;
   const long long row = (long long)blockIdx.x * RPB + threadIdx.x / TPR;
   const int t = threadIdx.x % TPR;
@@ -207,6 +215,7 @@ __global__ void softmax_rows_kernel(const float* __restrict__ s, long long M, in
 __global__ void softmax_rows_partials_kernel(const float* __restrict__ s, int S, long long s_pitch,
                                              const float2* __restrict__ part, int n_tiles,
                                              h16* __restrict__ p, long long p_pitch) {
+  pdl_entry();
   const long long row = blockIdx.x;
   const int t = threadIdx.x;
   __shared__ float red[8];
@@ -259,6 +268,7 @@ __global__ void softmax_rows_partials_kernel(const float* __restrict__ s, int S,
 // ------------------------------------------------------------------------------------------------
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, int N, int dim, float max_period,
                                           float* __restrict__ emb) {
+  pdl_entry();
   const int half = dim / 2;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N * dim) return;
@@ -281,6 +291,7 @@ template <bool VEC>
 __global__ void small_linear_kernel(const float* __restrict__ x, int M, int K, const float* __restrict__ W,
                                     const float* __restrict__ b, int O, int act_in, int act_out,
                                     float* __restrict__ y) {
+  pdl_entry();
   const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (o >= O) return;
   const int lane = threadIdx.x & 31;
@@ -323,6 +334,7 @@ __global__ void small_linear_kernel(const float* __restrict__ x, int M, int K, c
 __global__ void ddim_step_kernel(const float* __restrict__ eps_in, const float* __restrict__ x,
                                  const float* __restrict__ noise, b200_ddim_coef c,
                                  float* __restrict__ prev, float* __restrict__ x0_out, long long n) {
+  pdl_entry();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     const float m = eps_in[i], s = x[i];
@@ -349,6 +361,7 @@ __global__ void ddpm_step_kernel(const float* __restrict__ eps_in, const float* 
                                  const float* __restrict__ noise, const float* __restrict__ pred_var,
                                  b200_ddpm_coef c, float* __restrict__ prev, float* __restrict__ x0_out,
                                  long long n) {
+  pdl_entry();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     const float m = eps_in[i], s = x[i];
@@ -380,6 +393,7 @@ __device__ __forceinline__ float approx_normal_cdf(float x) {
 __global__ void ddpm_kl_kernel(const float* __restrict__ x0, const float* __restrict__ xt,
                                const float* __restrict__ mo, b200_kl_coef c, float* __restrict__ kl_out,
                                double* __restrict__ sample_sum, long long per_sample) {
+  pdl_entry();
   const int n = blockIdx.y;
   const long long base = (long long)n * per_sample;
   float acc = 0.f;
@@ -429,6 +443,7 @@ struct PndmPtrs { const float* h[4]; };
 
 __global__ void pndm_step_kernel(PndmPtrs hp, const float* __restrict__ x, b200_pndm_coef c,
                                  float* __restrict__ prev, float* __restrict__ eps_out, long long n) {
+  pdl_entry();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     float e = 0.f;
@@ -447,6 +462,7 @@ __global__ void pndm_step_kernel(PndmPtrs hp, const float* __restrict__ x, b200_
 __global__ void add_noise_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
                                  const float* __restrict__ ca, const float* __restrict__ cb, float sign_b,
                                  long long per_sample, float* __restrict__ out) {
+  pdl_entry();
   const int n = blockIdx.y;
   const float a = ca[n], b = cb[n] * sign_b;
   const long long base = (long long)n * per_sample;
@@ -456,17 +472,20 @@ __global__ void add_noise_kernel(const float* __restrict__ x0, const float* __re
 }
 
 __global__ void exp_half_clamped_kernel(const float* __restrict__ x, float lo, float hi, float* __restrict__ y, long long n) {
+  pdl_entry();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     y[i] = expf(fminf(fmaxf(x[i], lo), hi) / 2.0f);
 }
 
 __global__ void fma_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
                                float* __restrict__ y, long long n) {
+  pdl_entry();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     y[i] = a[i] + b[i] * c[i];
 }
 
 __global__ void scale_f32_kernel(const float* __restrict__ x, float mul, float div, float* __restrict__ y, long long n) {
+  pdl_entry();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     y[i] = x[i] * mul / div;
 }
@@ -492,6 +511,7 @@ struct TapGeom {
 
 __global__ void tap_gather_kernel(const h16* __restrict__ x, int C, int x_pitch, TapGeom g,
                                   h16* __restrict__ out, int out_pitch) {
+  pdl_entry();
   // one thread per (output voxel, 8-column vector): the voxel coordinates are decoded once, the row is written with
   // 16-byte stores (out_pitch is a multiple of 8: it is the K pitch of the GEMM that follows)
   const int taps = g.kd * g.kh * g.kw;
@@ -527,6 +547,7 @@ __global__ void tap_gather_kernel(const h16* __restrict__ x, int C, int x_pitch,
 template <int COUT>
 __global__ void tap_sum_kernel(const float* __restrict__ y, int y_pitch, TapGeom g, const float* __restrict__ bias,
                                void* __restrict__ out, int out_pitch, int out_dtype) {
+  pdl_entry();
   const long long total = (long long)g.N * g.OD * g.OH * g.OW;
   for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < total;
        v += (long long)gridDim.x * blockDim.x) {
@@ -568,6 +589,7 @@ __global__ void tap_sum_kernel(const float* __restrict__ y, int y_pitch, TapGeom
 __global__ void embed_tokens_kernel(const long long* __restrict__ tokens, long long M, int seq_len, int pos0,
                                     const float* __restrict__ tok_emb, const float* __restrict__ pos_emb, int C,
                                     h16* __restrict__ out, int pitch, const int* __restrict__ pos_dev) {
+  pdl_entry();
   if (pos_dev) pos0 = *pos_dev;
   const long long total = M * pitch;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -591,7 +613,7 @@ extern "C" int b200_nchw_to_nhwc(const float* x, int32_t N, int32_t C, int64_t s
   const long long bx = (spatial + 31) / 32;
   B200_CHECK_ARG(bx < (1ll << 31) && N <= 65535, "nchw_to_nhwc: extent too large");
   dim3 grid((unsigned)bx, (pitch + 31) / 32, N);
-  nchw_to_nhwc_kernel<<<grid, dim3(32, 8), 0, stream>>>(x, C, spatial, reinterpret_cast<h16*>(y), pitch);
+  B200_CUDA(b200::launch_pdl(nchw_to_nhwc_kernel, grid, dim3(32, 8), 0, stream, x, C, spatial, reinterpret_cast<h16*>(y), pitch));
   B200_LAUNCH_CHECK("nchw_to_nhwc_kernel");
   return B200_OK;
 }
@@ -604,9 +626,9 @@ extern "C" int b200_nhwc_to_nchw(const void* x, int32_t x_dtype, int32_t N, int3
   B200_CHECK_ARG(bx < (1ll << 31) && N <= 65535, "nhwc_to_nchw: extent too large");
   dim3 grid((unsigned)bx, (C + 31) / 32, N);
   if (x_dtype == B200_DT_H16)
-    nhwc_to_nchw_kernel<h16><<<grid, dim3(32, 8), 0, stream>>>(reinterpret_cast<const h16*>(x), C, spatial, pitch, y);
+    B200_CUDA(b200::launch_pdl(nhwc_to_nchw_kernel<h16>, grid, dim3(32, 8), 0, stream, reinterpret_cast<const h16*>(x), C, spatial, pitch, y));
   else
-    nhwc_to_nchw_kernel<float><<<grid, dim3(32, 8), 0, stream>>>(reinterpret_cast<const float*>(x), C, spatial, pitch, y);
+    B200_CUDA(b200::launch_pdl(nhwc_to_nchw_kernel<float>, grid, dim3(32, 8), 0, stream, reinterpret_cast<const float*>(x), C, spatial, pitch, y));
   B200_LAUNCH_CHECK("nhwc_to_nchw_kernel");
   return B200_OK;
 }
@@ -616,8 +638,8 @@ extern "C" int b200_upsample_nearest2x(const void* x, int32_t N, int32_t D, int3
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   B200_CHECK_ARG(x && y && pitch % 8 == 0 && (dims == 2 || dims == 3), "upsample2x: bad arguments");
   const long long total = (long long)N * (dims == 3 ? 2 * D : D) * 2 * H * 2 * W * (pitch / 8);
-  upsample2x_kernel<<<grid_for(total), 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), N, D, H, W, pitch / 8, dims,
-                                                        reinterpret_cast<uint4*>(y));
+  B200_CUDA(b200::launch_pdl(upsample2x_kernel, grid_for(total), 256, 0, stream, reinterpret_cast<const uint4*>(x), N, D, H, W, pitch / 8, dims,
+                                                        reinterpret_cast<uint4*>(y)));
   B200_LAUNCH_CHECK("upsample2x_kernel");
   return B200_OK;
 }
@@ -628,8 +650,8 @@ extern "C" int b200_avgpool2(const void* x, int32_t N, int32_t D, int32_t H, int
   B200_CHECK_ARG(x && y && pitch % 8 == 0 && (dims == 2 || dims == 3), "avgpool2: bad arguments");
   const long long total = (long long)N * (dims == 3 ? D / 2 : D) * (H / 2) * (W / 2) * (pitch / 8);
   if (total == 0) return B200_OK;
-  avgpool2_kernel<<<grid_for(total), 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), N, D, H, W, pitch / 8, dims,
-                                                      reinterpret_cast<uint4*>(y));
+  B200_CUDA(b200::launch_pdl(avgpool2_kernel, grid_for(total), 256, 0, stream, reinterpret_cast<const uint4*>(x), N, D, H, W, pitch / 8, dims,
+                                                      reinterpret_cast<uint4*>(y)));
   B200_LAUNCH_CHECK("avgpool2_kernel");
   return B200_OK;
 }
@@ -638,8 +660,8 @@ extern "C" int b200_axpy_h16(const void* a, const void* b, float alpha, void* y,
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   B200_CHECK_ARG(a && b && y && n % 8 == 0, "axpy_h16: element count must be a multiple of 8");
   if (n == 0) return B200_OK;
-  axpy_h16_kernel<<<grid_for(n / 8), 256, 0, stream>>>(reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b),
-                                                       alpha, reinterpret_cast<uint4*>(y), n / 8);
+  B200_CUDA(b200::launch_pdl(axpy_h16_kernel, grid_for(n / 8), 256, 0, stream, reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b),
+                                                       alpha, reinterpret_cast<uint4*>(y), n / 8));
   B200_LAUNCH_CHECK("axpy_h16_kernel");
   return B200_OK;
 }
@@ -659,8 +681,8 @@ extern "C" int b200_tap_gather(const void* x, int32_t C, int32_t x_pitch, const 
   B200_CHECK_ARG(tap_geom_ok(g) && out_pitch >= g.kd * g.kh * g.kw * C && out_pitch % 8 == 0 &&
                  ((uintptr_t)out % 16) == 0, "tap_gather: bad geometry (out_pitch must be a multiple of 8)");
   const long long total = (long long)g.N * g.OD * g.OH * g.OW * (out_pitch / 8);
-  tap_gather_kernel<<<grid_for(total), 256, 0, stream>>>(reinterpret_cast<const h16*>(x), C, x_pitch, g,
-                                                        reinterpret_cast<h16*>(out), out_pitch);
+  B200_CUDA(b200::launch_pdl(tap_gather_kernel, grid_for(total), 256, 0, stream, reinterpret_cast<const h16*>(x), C, x_pitch, g,
+                                                        reinterpret_cast<h16*>(out), out_pitch));
   B200_LAUNCH_CHECK("tap_gather_kernel");
   return B200_OK;
 }
@@ -676,10 +698,10 @@ extern "C" int b200_tap_sum(const float* y, int32_t y_pitch, const int32_t* geom
   const long long total = (long long)g.N * g.OD * g.OH * g.OW;
   const unsigned grid = grid_for(total);
   switch (cout) {
-    case 1: tap_sum_kernel<1><<<grid, 256, 0, stream>>>(y, y_pitch, g, bias, out, out_pitch, out_dtype); break;
-    case 2: tap_sum_kernel<2><<<grid, 256, 0, stream>>>(y, y_pitch, g, bias, out, out_pitch, out_dtype); break;
-    case 3: tap_sum_kernel<3><<<grid, 256, 0, stream>>>(y, y_pitch, g, bias, out, out_pitch, out_dtype); break;
-    default: tap_sum_kernel<4><<<grid, 256, 0, stream>>>(y, y_pitch, g, bias, out, out_pitch, out_dtype); break;
+    case 1: B200_CUDA(b200::launch_pdl(tap_sum_kernel<1>, grid, 256, 0, stream, y, y_pitch, g, bias, out, out_pitch, out_dtype)); break;
+    case 2: B200_CUDA(b200::launch_pdl(tap_sum_kernel<2>, grid, 256, 0, stream, y, y_pitch, g, bias, out, out_pitch, out_dtype)); break;
+    case 3: B200_CUDA(b200::launch_pdl(tap_sum_kernel<3>, grid, 256, 0, stream, y, y_pitch, g, bias, out, out_pitch, out_dtype)); break;
+    default: B200_CUDA(b200::launch_pdl(tap_sum_kernel<4>, grid, 256, 0, stream, y, y_pitch, g, bias, out, out_pitch, out_dtype)); break;
   }
   B200_LAUNCH_CHECK("tap_sum_kernel");
   return B200_OK;
@@ -689,6 +711,7 @@ extern "C" int b200_tap_sum(const float* y, int32_t y_pitch, const int32_t* geom
 // rows of T new tokens per sequence appended to a [B, L, pitch] key/value cache at the device-side position
 __global__ void cache_append_kernel(const h16* __restrict__ src, h16* __restrict__ cache, int B,
                                     int T, int L, int pitch, const int* __restrict__ pos_dev) {
+  pdl_entry();
   const int pos = *pos_dev;
   const long long total = (long long)B * T * pitch;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -699,14 +722,15 @@ __global__ void cache_append_kernel(const h16* __restrict__ src, h16* __restrict
     if (pos + t < L) cache[((long long)b * L + pos + t) * pitch + c] = src[i];
   }
 }
-__global__ void advance_i32_kernel(int* p, int delta) { *p += delta; }
+__global__ void advance_i32_kernel(int* p, int delta) {
+  pdl_entry(); *p += delta; }
 
 extern "C" int b200_cache_append(const void* src, void* cache, int32_t B, int32_t T, int32_t L, int32_t pitch,
                                  const int32_t* pos_dev, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   B200_CHECK_ARG(src && cache && pos_dev && B >= 1 && T >= 1 && L >= T && pitch >= 1, "cache_append: bad arguments");
-  cache_append_kernel<<<grid_for((long long)B * T * pitch), 256, 0, stream>>>(
-      reinterpret_cast<const h16*>(src), reinterpret_cast<h16*>(cache), B, T, L, pitch, pos_dev);
+  B200_CUDA(b200::launch_pdl(cache_append_kernel, grid_for((long long)B * T * pitch), 256, 0, stream, 
+      reinterpret_cast<const h16*>(src), reinterpret_cast<h16*>(cache), B, T, L, pitch, pos_dev));
   B200_LAUNCH_CHECK("cache_append_kernel");
   return B200_OK;
 }
@@ -714,7 +738,7 @@ extern "C" int b200_cache_append(const void* src, void* cache, int32_t B, int32_
 extern "C" int b200_advance_i32(int32_t* p, int32_t delta, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   B200_CHECK_ARG(p != nullptr, "advance_i32: null pointer");
-  advance_i32_kernel<<<1, 1, 0, stream>>>(p, delta);
+  B200_CUDA(b200::launch_pdl(advance_i32_kernel, 1, 1, 0, stream, p, delta));
   B200_LAUNCH_CHECK("advance_i32_kernel");
   return B200_OK;
 }
@@ -725,9 +749,9 @@ extern "C" int b200_embed_tokens(const int64_t* tokens, int64_t M, int32_t seq_l
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   B200_CHECK_ARG(tokens && tok_emb && pos_emb && out && M >= 1 && seq_len >= 1 && pos0 >= 0 && C >= 1 && pitch >= C,
                  "embed_tokens: bad arguments");
-  embed_tokens_kernel<<<grid_for(M * pitch), 256, 0, stream>>>(reinterpret_cast<const long long*>(tokens), M, seq_len,
+  B200_CUDA(b200::launch_pdl(embed_tokens_kernel, grid_for(M * pitch), 256, 0, stream, reinterpret_cast<const long long*>(tokens), M, seq_len,
                                                               pos0, tok_emb, pos_emb, C,
-                                                              reinterpret_cast<h16*>(out), pitch, pos_dev);
+                                                              reinterpret_cast<h16*>(out), pitch, pos_dev));
   B200_LAUNCH_CHECK("embed_tokens_kernel");
   return B200_OK;
 }
@@ -738,8 +762,8 @@ extern "C" int b200_copy_channels(const void* src, int32_t C, int32_t src_pitch,
   B200_CHECK_ARG(src && dst && C >= 1 && src_pitch >= C && dst_pitch >= dst_off + C && rows >= 1, "copy_channels: bad arguments");
   const int vec = (C % 8 == 0 && src_pitch % 8 == 0 && dst_pitch % 8 == 0 && dst_off % 8 == 0 &&
                    ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0)) ? 8 : 1;
-  copy_channels_kernel<<<grid_for(rows * (C / vec)), 256, 0, stream>>>(reinterpret_cast<const h16*>(src), C, src_pitch,
-                                                                     reinterpret_cast<h16*>(dst), dst_pitch, dst_off, rows, vec);
+  B200_CUDA(b200::launch_pdl(copy_channels_kernel, grid_for(rows * (C / vec)), 256, 0, stream, reinterpret_cast<const h16*>(src), C, src_pitch,
+                                                                     reinterpret_cast<h16*>(dst), dst_pitch, dst_off, rows, vec));
   B200_LAUNCH_CHECK("copy_channels_kernel");
   return B200_OK;
 }
@@ -749,8 +773,8 @@ extern "C" int b200_geglu(const void* x, int64_t M, int32_t H, int32_t x_pitch, 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   B200_CHECK_ARG(x && y && H % 8 == 0 && x_pitch % 8 == 0 && y_pitch % 8 == 0 && x_pitch >= 2 * H && y_pitch >= H,
                  "geglu: bad arguments");
-  geglu_kernel<<<grid_for(M * (H / 8)), 256, 0, stream>>>(reinterpret_cast<const h16*>(x), M, H, x_pitch,
-                                                         reinterpret_cast<h16*>(y), y_pitch);
+  B200_CUDA(b200::launch_pdl(geglu_kernel, grid_for(M * (H / 8)), 256, 0, stream, reinterpret_cast<const h16*>(x), M, H, x_pitch,
+                                                         reinterpret_cast<h16*>(y), y_pitch));
   B200_LAUNCH_CHECK("geglu_kernel");
   return B200_OK;
 }
@@ -763,10 +787,10 @@ extern "C" int b200_softmax_rows(const float* s, int64_t M, int32_t S, int64_t s
   if (S <= 1024) {
     const long long blocks = (M + 7) / 8;
     B200_CHECK_ARG(blocks < (1ll << 31), "softmax_rows: too many rows");
-    softmax_rows_kernel<32><<<(unsigned)blocks, 256, 0, stream>>>(s, M, S, s_pitch, pp, p_pitch);
+    B200_CUDA(b200::launch_pdl(softmax_rows_kernel<32>, (unsigned)blocks, 256, 0, stream, s, M, S, s_pitch, pp, p_pitch));
   } else {
     B200_CHECK_ARG(M < (1ll << 31), "softmax_rows: too many rows");
-    softmax_rows_kernel<256><<<(unsigned)M, 256, 0, stream>>>(s, M, S, s_pitch, pp, p_pitch);
+    B200_CUDA(b200::launch_pdl(softmax_rows_kernel<256>, (unsigned)M, 256, 0, stream, s, M, S, s_pitch, pp, p_pitch));
   }
   B200_LAUNCH_CHECK("softmax_rows_kernel");
   return B200_OK;
@@ -777,8 +801,8 @@ extern "C" int b200_softmax_rows_partials(const float* s, int64_t M, int32_t S, 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   B200_CHECK_ARG(s && p && partials && M >= 1 && M < (1ll << 31) && S >= 1 && s_pitch >= S && p_pitch >= S && n_tiles >= 1,
                  "softmax_rows_partials: bad arguments");
-  softmax_rows_partials_kernel<<<(unsigned)M, 256, 0, stream>>>(s, S, s_pitch, reinterpret_cast<const float2*>(partials),
-                                                               n_tiles, reinterpret_cast<h16*>(p), p_pitch);
+  B200_CUDA(b200::launch_pdl(softmax_rows_partials_kernel, (unsigned)M, 256, 0, stream, s, S, s_pitch, reinterpret_cast<const float2*>(partials),
+                                                               n_tiles, reinterpret_cast<h16*>(p), p_pitch));
   B200_LAUNCH_CHECK("softmax_rows_partials_kernel");
   return B200_OK;
 }
@@ -787,7 +811,7 @@ extern "C" int b200_timestep_embedding(const float* t, int32_t N, int32_t dim, f
                                        void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   B200_CHECK_ARG(t && emb && N >= 1 && dim >= 1, "timestep_embedding: bad arguments");
-  timestep_embedding_kernel<<<(N * dim + 255) / 256, 256, 0, stream>>>(t, N, dim, max_period, emb);
+  B200_CUDA(b200::launch_pdl(timestep_embedding_kernel, (N * dim + 255) / 256, 256, 0, stream, t, N, dim, max_period, emb));
   B200_LAUNCH_CHECK("timestep_embedding_kernel");
   return B200_OK;
 }
@@ -797,8 +821,8 @@ extern "C" int b200_small_linear(const float* x, int32_t M, int32_t K, const flo
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   B200_CHECK_ARG(x && W && y && M >= 1 && M <= 4096 && K >= 1 && O >= 1, "small_linear: bad arguments");
   const bool vec = (K % 128 == 0) && (((uintptr_t)x | (uintptr_t)W) & 15) == 0;
-  if (vec) small_linear_kernel<true><<<(O + 7) / 8, 256, 0, stream>>>(x, M, K, W, b, O, act_in, act_out, y);
-  else small_linear_kernel<false><<<(O + 7) / 8, 256, 0, stream>>>(x, M, K, W, b, O, act_in, act_out, y);
+  if (vec) B200_CUDA(b200::launch_pdl(small_linear_kernel<true>, (O + 7) / 8, 256, 0, stream, x, M, K, W, b, O, act_in, act_out, y));
+  else B200_CUDA(b200::launch_pdl(small_linear_kernel<false>, (O + 7) / 8, 256, 0, stream, x, M, K, W, b, O, act_in, act_out, y));
   B200_LAUNCH_CHECK("small_linear_kernel");
   return B200_OK;
 }
@@ -807,7 +831,7 @@ extern "C" int b200_ddim_step(const float* model_out, const float* sample, const
                               float* prev_sample, float* pred_x0, int64_t n, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   B200_CHECK_ARG(model_out && sample && c && prev_sample && n >= 1, "ddim_step: bad arguments");
-  ddim_step_kernel<<<grid_for(n), 256, 0, stream>>>(model_out, sample, noise, *c, prev_sample, pred_x0, n);
+  B200_CUDA(b200::launch_pdl(ddim_step_kernel, grid_for(n), 256, 0, stream, model_out, sample, noise, *c, prev_sample, pred_x0, n));
   B200_LAUNCH_CHECK("ddim_step_kernel");
   return B200_OK;
 }
@@ -817,7 +841,7 @@ extern "C" int b200_ddpm_step(const float* model_out, const float* sample, const
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   B200_CHECK_ARG(model_out && sample && c && prev_sample && n >= 1, "ddpm_step: bad arguments");
   B200_CHECK_ARG(c->var_mode == 0 || pred_var, "ddpm_step: learned variance needs pred_var");
-  ddpm_step_kernel<<<grid_for(n), 256, 0, stream>>>(model_out, sample, noise, pred_var, *c, prev_sample, pred_x0, n);
+  B200_CUDA(b200::launch_pdl(ddpm_step_kernel, grid_for(n), 256, 0, stream, model_out, sample, noise, pred_var, *c, prev_sample, pred_x0, n));
   B200_LAUNCH_CHECK("ddpm_step_kernel");
   return B200_OK;
 }
@@ -830,7 +854,7 @@ extern "C" int b200_pndm_step(const float* const* hist, const float* sample, con
   PndmPtrs hp;
   for (int k = 0; k < 4; ++k) hp.h[k] = k < c->n_hist ? hist[k] : nullptr;
   for (int k = 0; k < c->n_hist; ++k) B200_CHECK_ARG(hp.h[k], "pndm_step: null history tensor %d", k);
-  pndm_step_kernel<<<grid_for(n), 256, 0, stream>>>(hp, sample, *c, prev_sample, eps_out, n);
+  B200_CUDA(b200::launch_pdl(pndm_step_kernel, grid_for(n), 256, 0, stream, hp, sample, *c, prev_sample, eps_out, n));
   B200_LAUNCH_CHECK("pndm_step_kernel");
   return B200_OK;
 }
@@ -840,7 +864,7 @@ extern "C" int b200_add_noise(const float* x0, const float* noise, const float* 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   B200_CHECK_ARG(x0 && noise && ca && cb && out && N >= 1 && N <= 65535 && per_sample >= 1, "add_noise: bad arguments");
   dim3 grid(grid_for(per_sample, 256, 4), N);
-  add_noise_kernel<<<grid, 256, 0, stream>>>(x0, noise, ca, cb, sign_b, per_sample, out);
+  B200_CUDA(b200::launch_pdl(add_noise_kernel, grid, 256, 0, stream, x0, noise, ca, cb, sign_b, per_sample, out));
   B200_LAUNCH_CHECK("add_noise_kernel");
   return B200_OK;
 }
@@ -848,7 +872,7 @@ extern "C" int b200_add_noise(const float* x0, const float* noise, const float* 
 extern "C" int b200_exp_half_clamped(const float* log_var, float lo, float hi, float* sigma, int64_t n, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   B200_CHECK_ARG(log_var && sigma && n >= 1, "exp_half_clamped: bad arguments");
-  exp_half_clamped_kernel<<<grid_for(n), 256, 0, stream>>>(log_var, lo, hi, sigma, n);
+  B200_CUDA(b200::launch_pdl(exp_half_clamped_kernel, grid_for(n), 256, 0, stream, log_var, lo, hi, sigma, n));
   B200_LAUNCH_CHECK("exp_half_clamped_kernel");
   return B200_OK;
 }
@@ -856,7 +880,7 @@ extern "C" int b200_exp_half_clamped(const float* log_var, float lo, float hi, f
 extern "C" int b200_fma_f32(const float* a, const float* b, const float* c, float* out, int64_t n, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   B200_CHECK_ARG(a && b && c && out && n >= 1, "fma_f32: bad arguments");
-  fma_f32_kernel<<<grid_for(n), 256, 0, stream>>>(a, b, c, out, n);
+  B200_CUDA(b200::launch_pdl(fma_f32_kernel, grid_for(n), 256, 0, stream, a, b, c, out, n));
   B200_LAUNCH_CHECK("fma_f32_kernel");
   return B200_OK;
 }
@@ -864,7 +888,7 @@ extern "C" int b200_fma_f32(const float* a, const float* b, const float* c, floa
 extern "C" int b200_scale_f32(const float* x, float mul, float div, float* out, int64_t n, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   B200_CHECK_ARG(x && out && n >= 1 && div != 0.f, "scale_f32: bad arguments");
-  scale_f32_kernel<<<grid_for(n), 256, 0, stream>>>(x, mul, div, out, n);
+  B200_CUDA(b200::launch_pdl(scale_f32_kernel, grid_for(n), 256, 0, stream, x, mul, div, out, n));
   B200_LAUNCH_CHECK("scale_f32_kernel");
   return B200_OK;
 }
@@ -874,7 +898,7 @@ extern "C" int b200_ddpm_kl(const float* x0, const float* xt, const float* model
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   B200_CHECK_ARG(x0 && xt && model_out && c && sample_sum && N >= 1 && N <= 65535 && per_sample >= 1, "ddpm_kl: bad arguments");
   dim3 grid(grid_for(per_sample, 256, 4), N);
-  ddpm_kl_kernel<<<grid, 256, 0, stream>>>(x0, xt, model_out, *c, kl_out, sample_sum, per_sample);
+  B200_CUDA(b200::launch_pdl(ddpm_kl_kernel, grid, 256, 0, stream, x0, xt, model_out, *c, kl_out, sample_sum, per_sample));
   B200_LAUNCH_CHECK("ddpm_kl_kernel");
   return B200_OK;
 }

@@ -235,6 +235,7 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
   constexpr int kRStageBytes = kQChunkBytes + 256 * kBKV * 2;     // replay stage: P tile (16 KB) + V^T slice (32 KB)
   static_assert(!REPLAY || (DCH == 8 && kKStages * kRStageBytes <= DCH * kQChunkBytes + kKRingBytes + 256 * kBKV * 2),
                 "replay stages overlay the Q / K / V regions");
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = base;
@@ -277,6 +278,7 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
   __syncthreads();
   fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
+  pdl_wait();
   const uint32_t tO = tmem;              // columns [0, 256)
   const uint32_t tS = tmem + 256;        // kSBuf = 3 score buffers of 64 columns
   const uint32_t tP = tmem + 448;        // two 32-column probability buffers (bf16 pairs): 512 columns in all
@@ -773,6 +775,7 @@ static constexpr int kPairSmem = kPDCH * kQChunkBytes + kKRingBytes + kPVStages 
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 flash_pair_kernel(const __grid_constant__ FlashDev p) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = base;
@@ -831,6 +834,7 @@ flash_pair_kernel(const __grid_constant__ FlashDev p) {
   cluster_sync_all();                    // the peer's barriers exist before anything signals them remotely
   fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
+  pdl_wait();
   const uint32_t tO = tmem, tS = tmem + 256, tP = tmem + 448;
   const int n_kv = p.n_kv;
   const int pair_tiles = (p.q_tiles + 1) >> 1;               // pair items per (batch, head)
@@ -1218,11 +1222,20 @@ static int encode3(CUtensorMap* tm, const void* ptr, cuuint64_t d0, cuuint64_t d
   return B200_OK;
 }
 
+// Few query tiles (latent UNets: T = 256 .. 1024 tokens): the call is a latency chain on a handful of SMs, not a
+// throughput problem.  Such calls skip the two-pass replay and cut the output dimension into 64-wide slices instead —
+// every slice is its own work item that recomputes the (tiny) score tiles — so 8x more SMs share the chain's PV half
+// and nothing round-trips through global memory.
+static bool small_problem(const b200_flash_params* a) {
+  const long long q_tiles = (a->T + kBM - 1) / kBM;
+  return (long long)a->B * a->heads * q_tiles * 4 <= sm_count();
+}
+
 struct ReplayPlan { int grid, n_kv; long long slab_bytes, fac_bytes, blk_bytes, total; };
 static ReplayPlan replay_plan(const b200_flash_params* a) {
   ReplayPlan r;
   memset(&r, 0, sizeof(r));
-  if (a->dh != 512) return r;
+  if (a->dh != 512 || small_problem(a)) return r;
   // CTA pairs: one work item = 256 queries (two 128-row tiles), one CTA per tile
   const long long q_tiles = (a->T + kBM - 1) / kBM;
   const long long items = (long long)a->B * a->heads * ((q_tiles + 1) / 2);
@@ -1266,11 +1279,12 @@ extern "C" int b200_attention_flash(const b200_flash_params* a, void* stream_v) 
   d.B = a->B; d.T = a->T; d.S = a->S; d.heads = a->heads; d.dh = a->dh;
   d.d_chunks = a->dh / 64;
   d.dv = a->dh < 256 ? a->dh : 256;
+  if (fa::small_problem(a) && a->dh >= 128) d.dv = 64;
   d.n_dv = a->dh / d.dv;
   d.q_tiles = (a->T + fa::kBM - 1) / fa::kBM;
   d.n_kv = (a->S + fa::kBKV - 1) / fa::kBKV;
   const fa::ReplayPlan rp = fa::replay_plan(a);
-  const bool replay = a->dh == 512 && a->workspace != nullptr;
+  const bool replay = a->dh == 512 && a->workspace != nullptr && !fa::small_problem(a);
   if (replay) {
     B200_CHECK_ARG(a->workspace_bytes >= rp.total, "attention_flash: workspace of %lld bytes, need %lld",
                    (long long)a->workspace_bytes, rp.total);
@@ -1295,6 +1309,7 @@ extern "C" int b200_attention_flash(const b200_flash_params* a, void* stream_v) 
                         fa::kBKV, replay ? fa::kPVRows : d.dv, "V^T"))) return rc;
 
   const int smem = d.d_chunks * fa::kQChunkBytes + fa::kKRingBytes + d.dv * fa::kBKV * 2 + 1024 + 512;
+  const int smem_max = d.d_chunks * fa::kQChunkBytes + fa::kKRingBytes + 256 * fa::kBKV * 2 + 1024 + 512;
   const int grid = replay ? rp.grid : (d.n_items < sm_count() ? d.n_items : sm_count());
   if (replay) {
     B200_CHECK_ARG(grid == rp.grid && d.n_kv == rp.n_kv, "attention_flash: internal replay plan mismatch");
@@ -1311,10 +1326,10 @@ extern "C" int b200_attention_flash(const b200_flash_params* a, void* stream_v) 
     static bool attr_done = false;                                                                                    \
     if (!attr_done) {                                                                                                 \
       B200_CUDA(cudaFuncSetAttribute(fa::flash_attn_kernel<DCH, RP>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
-                                     smem));                                                                          \
+                                     smem_max));   /* the widest output slice: later calls may need it */          \
       attr_done = true;                                                                                               \
     }                                                                                                                 \
-    fa::flash_attn_kernel<DCH, RP><<<grid, fa::kThreads, smem, stream>>>(d);                                          \
+    B200_CUDA(b200::launch_pdl(fa::flash_attn_kernel<DCH, RP>, grid, fa::kThreads, smem, stream, d));                                          \
   } while (0)
   switch (d.d_chunks) {
     case 1: B200_FLASH_LAUNCH(1, false); break;
@@ -1327,7 +1342,7 @@ extern "C" int b200_attention_flash(const b200_flash_params* a, void* stream_v) 
           B200_CUDA(cudaFuncSetAttribute(fa::flash_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fa::kPairSmem));
           pair_attr_done = true;
         }
-        fa::flash_pair_kernel<<<grid, fa::kThreads, fa::kPairSmem, stream>>>(d);       // clusters of 2 (__cluster_dims__)
+        B200_CUDA(b200::launch_pdl(fa::flash_pair_kernel, grid, fa::kThreads, fa::kPairSmem, stream, d));       // clusters of 2 (__cluster_dims__)
       } else {
         B200_FLASH_LAUNCH(8, false);
       }

@@ -450,6 +450,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
   constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;   // power of two for BN in {16..256}
   constexpr int CH = (BN >= 32) ? 32 : 16;
 
+  pdl_launch_dependents();          // the next kernel's prologue may overlap this kernel (it blocks in its own pdl_wait)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + STAGES * kStageBytes;
@@ -488,6 +489,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();                       // barriers and tensor memory are set up: now wait for the producer of our inputs
 
   const int num_k = p.num_k_chunks;
 
@@ -730,6 +732,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
 // One thread per (output voxel, 16-column group).  Used by tests and for debugging only.
 // ------------------------------------------------------------------------------------------------
 __global__ void igemm_check_kernel(const __grid_constant__ IgemmDev p) {
+  pdl_entry();
   const long long rows = (long long)p.N * p.OD * p.OH * p.OW;
   const int col_groups = (p.out_cols + 15) / 16;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -819,6 +822,7 @@ static TileShape choose_tile(int OW, int OH, int OD, int sw, int sh, int sd) {
 // GroupNorm partials for the cross-check implementation: (sum, sumsq) of the stored bf16 outputs per 8-channel
 // group, accumulated into slot gn_slot0 (fp32 atomics: test path only).
 __global__ void gn8_partial_check_kernel(const __grid_constant__ IgemmDev p) {
+  pdl_entry();
   const long long rows = (long long)p.N * p.OD * p.OH * p.OW;
   const int groups = p.cout >> 3;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -843,6 +847,7 @@ __global__ void gn8_partial_check_kernel(const __grid_constant__ IgemmDev p) {
 // one-pass kernels use.
 __global__ void __launch_bounds__(256) igemm_split_reduce_kernel(const IgemmDev p, const float* __restrict__ ws,
                                                                  int splits, int ws_cols, long long ws_stride) {
+  pdl_entry();
   const int groups = (p.out_cols + 7) >> 3;
   const long long rows = (long long)p.N * p.OD * p.OH * p.OW;
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -927,7 +932,7 @@ static int launch_tc(const IgemmDev& d, cudaStream_t stream) {
     attr_done = true;
   }
   int grid = d.num_tiles < sm_count() ? d.num_tiles : sm_count();
-  igemm_tc_kernel<BN, STAGES><<<grid, kThreads, smem, stream>>>(d);
+  B200_CUDA(b200::launch_pdl(igemm_tc_kernel<BN, STAGES>, grid, kThreads, smem, stream, d));
   B200_LAUNCH_CHECK("igemm_tc_kernel");
   return B200_OK;
 }
@@ -1049,11 +1054,11 @@ extern "C" int b200_igemm(const b200_igemm_params* p, void* stream_v) {
     const int threads = 128;
     const long long blocks = (total + threads - 1) / threads;
     B200_CHECK_ARG(blocks < (1ll << 31), "igemm(check): problem too large");
-    igemm_check_kernel<<<(unsigned)blocks, threads, 0, stream>>>(d);
+    B200_CUDA(b200::launch_pdl(igemm_check_kernel, (unsigned)blocks, threads, 0, stream, d));
     B200_LAUNCH_CHECK("igemm_check_kernel");
     if (d.gn_partial) {
       const long long tot = rows * (d.cout >> 3);
-      gn8_partial_check_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(d);
+      B200_CUDA(b200::launch_pdl(gn8_partial_check_kernel, (unsigned)((tot + 255) / 256), 256, 0, stream, d));
       B200_LAUNCH_CHECK("gn8_partial_check_kernel");
     }
     return B200_OK;
@@ -1148,8 +1153,8 @@ extern "C" int b200_igemm(const b200_igemm_params* p, void* stream_v) {
   if (rc != B200_OK) return rc;
   const long long total = pl.rows * ((d.out_cols + 7) / 8);
   B200_CHECK_ARG((total + 255) / 256 < (1ll << 31), "igemm: split reduction too large");
-  igemm_split_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
-      d, static_cast<const float*>(p->split_ws), splits, pl.ws_cols, ds.split_stride);
+  B200_CUDA(b200::launch_pdl(igemm_split_reduce_kernel, (unsigned)((total + 255) / 256), 256, 0, stream, 
+      d, static_cast<const float*>(p->split_ws), splits, pl.ws_cols, ds.split_stride));
   B200_LAUNCH_CHECK("igemm_split_reduce_kernel");
   return B200_OK;
 }

@@ -22,6 +22,7 @@ __device__ __forceinline__ float src_at(const RepackDev& p, int co, int c, int t
 }
 
 __global__ void __launch_bounds__(256) repack_kernel(const __grid_constant__ RepackDev p) {
+  pdl_entry();
   const int groups = p.pitch >> 3;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)p.rows_pad * groups) return;
@@ -106,7 +107,7 @@ extern "C" int b200_repack_weight(const float* src, int32_t cout, int32_t cin, i
   }
   const long long total = (long long)rows_pad * (dst_pitch / 8);
   B200_CHECK_ARG((total + 255) / 256 < (1ll << 31), "repack_weight: weight too large");
-  repack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(d);
+  B200_CUDA(b200::launch_pdl(repack_kernel, (unsigned)((total + 255) / 256), 256, 0, stream, d));
   B200_LAUNCH_CHECK("repack_kernel");
   return B200_OK;
 }

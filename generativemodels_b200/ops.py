@@ -834,7 +834,8 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, dh:
     # row pitches come from the strides: q and k may be column slices of ONE fused [B, T, 2C] projection
     qp, kp = q.stride(1), k.stride(1)
     for name, t_ in (("q", q), ("k", k)):
-        if t_.stride(2) != 1 or t_.stride(0) != t_.shape[1] * t_.stride(1) or t_.stride(1) % 8 or t_.data_ptr() % 16:
+        if (t_.stride(2) != 1 or (B > 1 and t_.stride(0) != t_.shape[1] * t_.stride(1)) or t_.stride(1) % 8
+                or t_.data_ptr() % 16):
             raise ValueError(f"attention: {name} must be rows of a packed [B, T, pitch] tensor (pitch % 8 == 0)")
     out = torch.empty((B, T, round_up(heads * dh, 8)), dtype=H16, device=q.device)
     use_tc = (dh % 64 == 0) and S >= _TC_ATTN_MIN_S and vt is not None
