@@ -46,7 +46,11 @@ int sm_count();
 // exactly those of plain stream order).  What overlaps is the next kernel's launch latency and prologue (barrier
 // initialisation, tensor-memory allocation, tensor-map fetch) with this kernel's execution: a latent-UNet step is
 // 150-300 dependent kernels of a few microseconds each (latency-bound configurations).
-// B200_PDL=0 in the environment launches without the attribute (the device-side instructions are then no-ops).
+// MEASURED (round 2, same box, graph-replayed samplers): it does not pay here — C2 at batch 1 85.2 -> 93.2 ms per
+// sample, C5 564 -> 605 ms per guided sample with the attribute on, the C3 step unchanged — the persistent tensor-core
+// kernels hold ~200 KB of shared memory per CTA, so a dependent grid can only start on SMs the running grid left idle
+// and its early-resident CTAs then spin in griddepcontrol.wait.  The launches therefore go out WITHOUT the attribute
+// by default (the device-side instructions are no-ops then); B200_PDL=1 turns it on for experiments.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -56,7 +60,7 @@ inline bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("B200_PDL");
-    v = (e && e[0] == '0') ? 0 : 1;
+    v = (e && e[0] == '1') ? 1 : 0;
   }
   return v != 0;
 }

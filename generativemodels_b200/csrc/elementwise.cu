@@ -331,27 +331,63 @@ __global__ void small_linear_kernel(const float* __restrict__ x, int M, int K, c
 // ------------------------------------------------------------------------------------------------
 // scheduler steps
 // ------------------------------------------------------------------------------------------------
-__global__ void ddim_step_kernel(const float* __restrict__ eps_in, const float* __restrict__ x,
-                                 const float* __restrict__ noise, b200_ddim_coef c,
-                                 float* __restrict__ prev, float* __restrict__ x0_out, long long n) {
+__device__ __forceinline__ void ddim_one(const b200_ddim_coef& c, float m, float s, float nz, bool has_noise, float& p,
+                                         float& x0) {
+  float eps;
+  if (c.prediction_type == B200_PRED_EPSILON) {
+    x0 = (s - c.sqrt_beta_prod_t * m) / c.sqrt_alpha_prod_t;
+    eps = m;
+  } else if (c.prediction_type == B200_PRED_SAMPLE) {
+    x0 = m;
+    eps = (s - c.sqrt_alpha_prod_t * x0) / c.sqrt_beta_prod_t;
+  } else {
+    x0 = c.sqrt_alpha_prod_t * s - c.sqrt_beta_prod_t * m;
+    eps = c.sqrt_alpha_prod_t * m + c.sqrt_beta_prod_t * s;
+  }
+  if (c.clip) x0 = fminf(fmaxf(x0, c.clip_min), c.clip_max);
+  p = c.sqrt_alpha_prod_prev * x0 + c.dir_coef * eps;
+  if (has_noise) p += c.sigma * nz;
+}
+
+// 128-bit loads / stores, two independent vectors per thread and iteration (the update is 2 reads + 2 writes of 4 B per
+// element: pure HBM streaming, so what matters is bytes in flight per SM); scalar tail for n % 4.
+// VEC = 0: pointers not 16-byte aligned -> scalar path.
+template <int VEC>
+__global__ void __launch_bounds__(256) ddim_step_kernel(const float* __restrict__ eps_in, const float* __restrict__ x,
+                                                        const float* __restrict__ noise, b200_ddim_coef c,
+                                                        float* __restrict__ prev, float* __restrict__ x0_out, long long n) {
   pdl_entry();
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
-    const float m = eps_in[i], s = x[i];
-    float x0, eps;
-    if (c.prediction_type == B200_PRED_EPSILON) {
-      x0 = (s - c.sqrt_beta_prod_t * m) / c.sqrt_alpha_prod_t;
-      eps = m;
-    } else if (c.prediction_type == B200_PRED_SAMPLE) {
-      x0 = m;
-      eps = (s - c.sqrt_alpha_prod_t * x0) / c.sqrt_beta_prod_t;
-    } else {
-      x0 = c.sqrt_alpha_prod_t * s - c.sqrt_beta_prod_t * m;
-      eps = c.sqrt_alpha_prod_t * m + c.sqrt_beta_prod_t * s;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long long)gridDim.x * blockDim.x;
+  const bool has_noise = noise != nullptr;
+  long long done = 0;
+  if (VEC) {
+    const long long nv = n >> 2;
+    const float4* e4 = reinterpret_cast<const float4*>(eps_in);
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    const float4* n4 = reinterpret_cast<const float4*>(noise);
+    float4* p4 = reinterpret_cast<float4*>(prev);
+    float4* o4 = reinterpret_cast<float4*>(x0_out);
+    for (long long i = tid; i < nv; i += 2 * nthr) {
+      const long long i2 = i + nthr;
+      const bool two = i2 < nv;
+      const float4 ma = __ldg(e4 + i), sa = __ldg(x4 + i);
+      const float4 mb = two ? __ldg(e4 + i2) : ma, sb = two ? __ldg(x4 + i2) : sa;
+      float4 za = make_float4(0.f, 0.f, 0.f, 0.f), zb = za;
+      if (has_noise) { za = __ldg(n4 + i); if (two) zb = __ldg(n4 + i2); }
+      float4 pa, oa, pb, ob;
+      ddim_one(c, ma.x, sa.x, za.x, has_noise, pa.x, oa.x); ddim_one(c, ma.y, sa.y, za.y, has_noise, pa.y, oa.y);
+      ddim_one(c, ma.z, sa.z, za.z, has_noise, pa.z, oa.z); ddim_one(c, ma.w, sa.w, za.w, has_noise, pa.w, oa.w);
+      ddim_one(c, mb.x, sb.x, zb.x, has_noise, pb.x, ob.x); ddim_one(c, mb.y, sb.y, zb.y, has_noise, pb.y, ob.y);
+      ddim_one(c, mb.z, sb.z, zb.z, has_noise, pb.z, ob.z); ddim_one(c, mb.w, sb.w, zb.w, has_noise, pb.w, ob.w);
+      p4[i] = pa;
+      if (x0_out) o4[i] = oa;
+      if (two) { p4[i2] = pb; if (x0_out) o4[i2] = ob; }
     }
-    if (c.clip) x0 = fminf(fmaxf(x0, c.clip_min), c.clip_max);
-    float p = c.sqrt_alpha_prod_prev * x0 + c.dir_coef * eps;
-    if (noise) p += c.sigma * noise[i];
+    done = nv << 2;
+  }
+  for (long long i = done + tid; i < n; i += nthr) {
+    float p, x0;
+    ddim_one(c, eps_in[i], x[i], has_noise ? noise[i] : 0.f, has_noise, p, x0);
     prev[i] = p;
     if (x0_out) x0_out[i] = x0;
   }
@@ -831,7 +867,9 @@ extern "C" int b200_ddim_step(const float* model_out, const float* sample, const
                               float* prev_sample, float* pred_x0, int64_t n, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   B200_CHECK_ARG(model_out && sample && c && prev_sample && n >= 1, "ddim_step: bad arguments");
-  B200_CUDA(b200::launch_pdl(ddim_step_kernel, grid_for(n), 256, 0, stream, model_out, sample, noise, *c, prev_sample, pred_x0, n));
+  const bool vec = (((uintptr_t)model_out | (uintptr_t)sample | (uintptr_t)noise | (uintptr_t)prev_sample | (uintptr_t)pred_x0) & 15) == 0;
+  if (vec) B200_CUDA(b200::launch_pdl(ddim_step_kernel<1>, grid_for((n + 7) / 8, 256, 16), 256, 0, stream, model_out, sample, noise, *c, prev_sample, pred_x0, (long long)n));
+  else B200_CUDA(b200::launch_pdl(ddim_step_kernel<0>, grid_for(n), 256, 0, stream, model_out, sample, noise, *c, prev_sample, pred_x0, (long long)n));
   B200_LAUNCH_CHECK("ddim_step_kernel");
   return B200_OK;
 }

@@ -220,6 +220,15 @@ __device__ __forceinline__ void stg256(void* ptr, const uint32_t* w) {
 #define FA_KVROW(j) (j)
 #endif
 
+// dev ablations (-DFA_ABLATE=n; results are wrong on purpose, only the timing means something):
+//   1 no K / V^T / P tile loads   2 no exp2   3 no slab stores   4 softmax warps only hand-shake
+//   5 no QK^T MMAs                6 all K / V^T loads hit key block 0 (L2)   7 no PV MMAs
+#ifdef FA_ABLATE
+#define FA_ABL(n) (FA_ABLATE == (n))
+#else
+#define FA_ABL(n) 0
+#endif
+
 #ifdef FA_TIMING
 #define FA_T(i) do { long long fa_now = clock64(); fa_acc[i] += fa_now - fa_last; fa_last = fa_now; } while (0)
 #else
@@ -310,11 +319,13 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
             for (int step = 0; step < NSTEP; ++step) {
               mbar_wait_warp(k_empty(kst), kph ^ 1u);
               if (elect_one()) {
+                if (FA_ABL(1)) { mbar_arrive(k_full(kst)); } else {
                 mbar_expect_tx(k_full(kst), kKStageBytes);
 #pragma unroll
                 for (int cc = 0; cc < CPS; ++cc)
                   tma_load_3d(&p.tmK, k_full(kst), sK + kst * kKStageBytes + cc * kKChunkBytes,
                               ch0 + (step * CPS + cc) * 64, FA_KVROW(j) * kBKV, it.b);
+                }
               }
               __syncwarp();
               if (++kst == kKStages) { kst = 0; kph ^= 1u; }
@@ -323,8 +334,10 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
           if (j >= kLookahead) {
             mbar_wait_warp(v_empty, (vcount & 1) ^ 1u);
             if (elect_one()) {
+              if (FA_ABL(1)) { mbar_arrive(v_full); } else {
               mbar_expect_tx(v_full, p.dv * kBKV * 2);
               tma_load_3d(&p.tmVt, v_full, sV, FA_KVROW(j - kLookahead) * kBKV, ch0 + it.dvi * p.dv, it.b);
+              }
             }
             __syncwarp();
             ++vcount;
@@ -347,9 +360,11 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
             if (elect_one()) {
               if (j + kPrefetch < n_kv) tma_prefetch_3d(&p.tmP, 0, (j + kPrefetch) * kBM, blockIdx.x);
               const uint32_t st = sQ + kst * kRStageBytes;
+              if (FA_ABL(1)) { mbar_arrive(k_full(kst)); } else {
               mbar_expect_tx(k_full(kst), kRStageBytes);
               tma_load_3d(&p.tmP, k_full(kst), st, 0, j * kBM, blockIdx.x);
               tma_load_3d(&p.tmVt, k_full(kst), st + kQChunkBytes, j * kBKV, ch0 + 256, it.b);
+              }
             }
             __syncwarp();
             if (++kst == kKStages) { kst = 0; kph ^= 1u; }
@@ -389,7 +404,7 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
                 for (int cc = 0; cc < CPS; ++cc) {
 #pragma unroll
                   for (int kk = 0; kk < 4; ++kk)
-                    umma_h16(d_s, desc64(q_lo + (step * CPS + cc) * (kQChunkBytes >> 4) + 2 * kk),
+                    if (!FA_ABL(5)) umma_h16(d_s, desc64(q_lo + (step * CPS + cc) * (kQChunkBytes >> 4) + 2 * kk),
                               desc64(b_lo + cc * (kKChunkBytes >> 4) + 2 * kk), idesc_s,
                               (step | cc | kk) != 0 ? 1u : 0u);
                 }
@@ -410,7 +425,7 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
               const uint32_t a_tmem = tP + pb * 32;          // 16 bf16 = 8 columns per K step
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk)
-                umma_h16_ts(tO, a_tmem + 8u * kk, desc64(v_lo + 2 * kk), idesc_o,
+                if (!FA_ABL(7)) umma_h16_ts(tO, a_tmem + 8u * kk, desc64(v_lo + 2 * kk), idesc_o,
                              (j > kLookahead || kk > 0) ? 1u : 0u);
               umma_commit(v_empty);
               umma_commit(p_empty(pb));
@@ -442,7 +457,7 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
               const uint32_t b_lo = a_lo + (kQChunkBytes >> 4);
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk)
-                umma_h16(tO, desc64(a_lo + 2 * kk), desc64(b_lo + 2 * kk), idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+                if (!FA_ABL(7)) umma_h16(tO, desc64(a_lo + 2 * kk), desc64(b_lo + 2 * kk), idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
               umma_commit(k_empty(kst));
               if (gated) umma_commit(p_empty(pb));
               if (j == n_kv - 1) {
@@ -484,9 +499,14 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
         fence_after();
         FA_T(1);
         uint32_t raw[64];
+#if FA_ABL(4)
+#pragma unroll
+        for (int c = 0; c < 64; ++c) raw[c] = 0u;
+#else
         tmem_ld32(tS + lane_addr + sb * kBKV, raw);
         tmem_ld32(tS + lane_addr + sb * kBKV + 32, raw + 32);
         tmem_ld_wait();
+#endif
         fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(s_empty(sb));     // S buffer may be overwritten by block j + 2
@@ -553,8 +573,16 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
         uint32_t pw[32];
 #pragma unroll
         for (int w = 0; w < 32; ++w) {
+#if FA_ABL(4)
+          pw[w] = 0x3c003c00u; sum8[w & 7] += 2.0f; continue;
+#endif
+#if FA_ABL(2)
+          const float p0 = fmaf(__uint_as_float(raw[2 * w]), p.scale_log2, neg_m);
+          const float p1 = fmaf(__uint_as_float(raw[2 * w + 1]), p.scale_log2, neg_m);
+#else
           const float p0 = ex2_approx(fmaf(__uint_as_float(raw[2 * w]), p.scale_log2, neg_m));
           const float p1 = ex2_approx(fmaf(__uint_as_float(raw[2 * w + 1]), p.scale_log2, neg_m));
+#endif
           sum8[(2 * w) & 7] += p0;
           sum8[(2 * w + 1) & 7] += p1;
           h162 h = f2h2(p0, p1);
@@ -564,12 +592,12 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
         // P buffer pb must have been consumed by the PV MMA two hand-offs ago; with QK^T running two blocks ahead that
         // MMA sits behind QK_j in the pipe, so the wait comes as late as possible — after the exponentials
         if (pcount >= 2) mbar_wait(p_empty(pb), ((pcount >> 1) & 1) ^ 1u);
-        tmem_st32(tP + lane_addr + pb * 32, pw);
+        if (!FA_ABL(4)) tmem_st32(tP + lane_addr + pb * 32, pw);
         if constexpr (REPLAY) {
           // the same 64 probabilities to this row of the slab (128 contiguous bytes), for pass 2
           h16* dst = slab_row + (long long)j * (kBM * kBKV);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) stg256(dst + g * 16, pw + g * 8);
+          for (int g = 0; g < 4; ++g) { if (!FA_ABL(3) && !FA_ABL(4)) stg256(dst + g * 16, pw + g * 8); }
         }
         tmem_st_wait();
         const float lsum = ((sum8[0] + sum8[1]) + (sum8[2] + sum8[3])) + ((sum8[4] + sum8[5]) + (sum8[6] + sum8[7]));
@@ -690,6 +718,9 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
 // The two-pass structure (pass 1: flash loop for output channels 0..255 + P tiles to a per-CTA slab; pass 2: replay
 // P x V^T[256..511]) and the rescale-event log are those of flash_attn_kernel<8, true>.
 // ================================================================================================================
+#ifndef B200_FLASH_PAIR_DEFAULT
+#define B200_FLASH_PAIR_DEFAULT 0
+#endif
 static constexpr uint32_t kPeerMask = 0xFEFFFFFFu;      // clears the CTA-rank bit of a shared::cluster address -> leader
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -863,11 +894,13 @@ flash_pair_kernel(const __grid_constant__ FlashDev p) {
           for (int step = 0; step < kPKSteps; ++step) {
             mbar_wait_warp(k_empty(kst), kph ^ 1u);
             if (elect_one()) {
+              if (FA_ABL(1)) { if (leader) mbar_arrive(k_full(kst)); } else {
               if (leader) mbar_expect_tx(k_full(kst), 2 * kPKStageBytes);
 #pragma unroll
               for (int cc = 0; cc < 4; ++cc)
                 tma_load_3d_pair(&p.tmK, k_full(kst), sK + kst * kPKStageBytes + cc * kPKChunkBytes,
-                                 ch0 + (step * 4 + cc) * 64, j * kBKV + (int)rank * kPKeysCta, b);
+                                 ch0 + (step * 4 + cc) * 64, FA_KVROW(j) * kBKV + (int)rank * kPKeysCta, b);
+              }
             }
             __syncwarp();
             if (++kst == kPKStages) { kst = 0; kph ^= 1u; }
@@ -877,9 +910,11 @@ flash_pair_kernel(const __grid_constant__ FlashDev p) {
           const int vs = vcount & 1;
           mbar_wait_warp(v_empty(vs), ((vcount >> 1) & 1) ^ 1u);
           if (elect_one()) {
+            if (FA_ABL(1)) { if (leader) mbar_arrive(v_full(vs)); } else {
             if (leader) mbar_expect_tx(v_full(vs), 2 * kPVBytes);
-            tma_load_3d_pair(&p.tmVt, v_full(vs), sV + vs * kPVBytes, (j - kLookahead) * kBKV,
+            tma_load_3d_pair(&p.tmVt, v_full(vs), sV + vs * kPVBytes, FA_KVROW(j - kLookahead) * kBKV,
                              ch0 + (int)rank * kPVRows, b);
+            }
           }
           __syncwarp();
           ++vcount;
@@ -898,9 +933,11 @@ flash_pair_kernel(const __grid_constant__ FlashDev p) {
         if (elect_one()) {
           if (j + kPrefetch < n_kv) tma_prefetch_3d(&p.tmP, 0, (j + kPrefetch) * kBM, blockIdx.x);
           const uint32_t st = sQ + rst * kPRStageBytes;
+          if (FA_ABL(1)) { if (leader) mbar_arrive(r_full(rst)); } else {
           if (leader) mbar_expect_tx(r_full(rst), 2 * kPRStageBytes);
           tma_load_3d_pair(&p.tmP, r_full(rst), st, 0, j * kBM, blockIdx.x);
-          tma_load_3d_pair(&p.tmVt, r_full(rst), st + kQChunkBytes, j * kBKV, ch0 + 256 + (int)rank * kPVRows, b);
+          tma_load_3d_pair(&p.tmVt, r_full(rst), st + kQChunkBytes, FA_KVROW(j) * kBKV, ch0 + 256 + (int)rank * kPVRows, b);
+          }
         }
         __syncwarp();
         if (++rst == kPRStages) { rst = 0; rph ^= 1u; }
@@ -936,7 +973,7 @@ flash_pair_kernel(const __grid_constant__ FlashDev p) {
                 for (int cc = 0; cc < 4; ++cc) {
 #pragma unroll
                   for (int kk = 0; kk < 4; ++kk)
-                    umma2_h16(d_s, desc64(q_lo + (step * 4 + cc) * (kQChunkBytes >> 4) + 2 * kk),
+                    if (!FA_ABL(5)) umma2_h16(d_s, desc64(q_lo + (step * 4 + cc) * (kQChunkBytes >> 4) + 2 * kk),
                               desc64(b_lo + cc * (kPKChunkBytes >> 4) + 2 * kk), idesc_s,
                               (step | cc | kk) != 0 ? 1u : 0u);
                 }
@@ -958,7 +995,7 @@ flash_pair_kernel(const __grid_constant__ FlashDev p) {
               const uint32_t b_lo = v_lo + vs * (kPVBytes >> 4);
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk)
-                umma2_h16_ts(tO, a_tmem + 8u * kk, desc64(b_lo + 2 * kk), idesc_o, (j > kLookahead || kk > 0) ? 1u : 0u);
+                if (!FA_ABL(7)) umma2_h16_ts(tO, a_tmem + 8u * kk, desc64(b_lo + 2 * kk), idesc_o, (j > kLookahead || kk > 0) ? 1u : 0u);
               umma2_commit(v_empty(vs));
               umma2_commit(p_empty(pb));
               if (j == n_kv + kLookahead - 1) {
@@ -989,7 +1026,7 @@ flash_pair_kernel(const __grid_constant__ FlashDev p) {
             const uint32_t b_lo = a_lo + (kQChunkBytes >> 4);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
-              umma2_h16(tO, desc64(a_lo + 2 * kk), desc64(b_lo + 2 * kk), idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+              if (!FA_ABL(7)) umma2_h16(tO, desc64(a_lo + 2 * kk), desc64(b_lo + 2 * kk), idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
             umma2_commit(r_empty(rst));
             if (gated) umma2_commit(p_empty(pb));
             if (j == n_kv - 1) {
@@ -1028,9 +1065,14 @@ flash_pair_kernel(const __grid_constant__ FlashDev p) {
         mbar_wait(s_full(sb), (scount / kSBuf) & 1);
         fence_after();
         uint32_t raw[64];
+#if FA_ABL(4)
+#pragma unroll
+        for (int c = 0; c < 64; ++c) raw[c] = 0u;
+#else
         tmem_ld32(tS + lane_addr + sb * kBKV, raw);
         tmem_ld32(tS + lane_addr + sb * kBKV + 32, raw + 32);
         tmem_ld_wait();
+#endif
         fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(l_s_empty0 + 8u * sb);
@@ -1085,19 +1127,27 @@ flash_pair_kernel(const __grid_constant__ FlashDev p) {
         uint32_t pw[32];
 #pragma unroll
         for (int w = 0; w < 32; ++w) {
+#if FA_ABL(4)
+          pw[w] = 0x3c003c00u; sum8[w & 7] += 2.0f; continue;
+#endif
+#if FA_ABL(2)
+          const float p0 = fmaf(__uint_as_float(raw[2 * w]), p.scale_log2, neg_m);
+          const float p1 = fmaf(__uint_as_float(raw[2 * w + 1]), p.scale_log2, neg_m);
+#else
           const float p0 = ex2_approx(fmaf(__uint_as_float(raw[2 * w]), p.scale_log2, neg_m));
           const float p1 = ex2_approx(fmaf(__uint_as_float(raw[2 * w + 1]), p.scale_log2, neg_m));
+#endif
           sum8[(2 * w) & 7] += p0;
           sum8[(2 * w + 1) & 7] += p1;
           h162 hh = f2h2(p0, p1);
           pw[w] = *reinterpret_cast<uint32_t*>(&hh);
         }
         if (pcount >= 2) mbar_wait(p_empty(pb), ((pcount >> 1) & 1) ^ 1u);
-        tmem_st32(tP + lane_addr + pb * 32, pw);
+        if (!FA_ABL(4)) tmem_st32(tP + lane_addr + pb * 32, pw);
         {
           h16* dst = slab_row + (long long)j * (kBM * kBKV);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) stg256(dst + g * 16, pw + g * 8);
+          for (int g = 0; g < 4; ++g) { if (!FA_ABL(3) && !FA_ABL(4)) stg256(dst + g * 16, pw + g * 8); }
         }
         tmem_st_wait();
         const float lsum = ((sum8[0] + sum8[1]) + (sum8[2] + sum8[3])) + ((sum8[4] + sum8[5]) + (sum8[6] + sum8[7]));
@@ -1231,16 +1281,30 @@ static bool small_problem(const b200_flash_params* a) {
   return (long long)a->B * a->heads * q_tiles * 4 <= sm_count();
 }
 
+// which head_dim-512 replay kernel runs: the CTA-pair kernel (1) or the single-CTA one (0).  B200_FLASH_PAIR overrides.
+static bool pair_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200_FLASH_PAIR");
+    v = e ? (e[0] != '0') : B200_FLASH_PAIR_DEFAULT;
+  }
+  return v != 0;
+}
+
 struct ReplayPlan { int grid, n_kv; long long slab_bytes, fac_bytes, blk_bytes, total; };
 static ReplayPlan replay_plan(const b200_flash_params* a) {
   ReplayPlan r;
   memset(&r, 0, sizeof(r));
   if (a->dh != 512 || small_problem(a)) return r;
-  // CTA pairs: one work item = 256 queries (two 128-row tiles), one CTA per tile
   const long long q_tiles = (a->T + kBM - 1) / kBM;
-  const long long items = (long long)a->B * a->heads * ((q_tiles + 1) / 2);
-  const long long pairs = sm_count() / 2;
-  r.grid = 2 * (int)(items < pairs ? items : pairs);
+  if (pair_mode()) {   // CTA pairs: one work item = 256 queries (two 128-row tiles), one CTA per tile
+    const long long items = (long long)a->B * a->heads * ((q_tiles + 1) / 2);
+    const long long pairs = sm_count() / 2;
+    r.grid = 2 * (int)(items < pairs ? items : pairs);
+  } else {
+    const long long items = (long long)a->B * a->heads * q_tiles;
+    r.grid = (int)(items < sm_count() ? items : sm_count());
+  }
   r.n_kv = (a->S + kBKV - 1) / kBKV;
   r.slab_bytes = (long long)r.grid * kBM * r.n_kv * kBKV * 2;
   r.fac_bytes = (long long)r.grid * 4 * r.n_kv * 32 * 4;
@@ -1290,8 +1354,9 @@ extern "C" int b200_attention_flash(const b200_flash_params* a, void* stream_v) 
                    (long long)a->workspace_bytes, rp.total);
     B200_CHECK_ARG(((uintptr_t)a->workspace & 255) == 0, "attention_flash: workspace must be 256-byte aligned");
   }
-  const long long items = replay ? (long long)a->B * a->heads * ((d.q_tiles + 1) / 2)
-                                 : (long long)a->B * a->heads * d.q_tiles * d.n_dv;
+  const bool pair = replay && fa::pair_mode();
+  const long long items = pair ? (long long)a->B * a->heads * ((d.q_tiles + 1) / 2)
+                               : (long long)a->B * a->heads * d.q_tiles * (replay ? 1 : d.n_dv);
   B200_CHECK_ARG(items < (1ll << 31), "attention_flash: too many work items");
   d.n_items = (int)items;
   d.scale_log2 = a->scale * 1.4426950408889634f;
@@ -1304,9 +1369,9 @@ extern "C" int b200_attention_flash(const b200_flash_params* a, void* stream_v) 
                         fa::kBM, "Q"))) return rc;
   // pair kernel: each CTA stages half of every B operand (32 of a block's 64 keys; 128 of the 256 V^T rows)
   if ((rc = fa::encode3(&d.tmK, a->k, C, a->S, a->B, (cuuint64_t)a->k_pitch * 2, (cuuint64_t)a->S * a->k_pitch * 2, 64,
-                        replay ? fa::kPKeysCta : fa::kBKV, "K"))) return rc;
+                        pair ? fa::kPKeysCta : fa::kBKV, "K"))) return rc;
   if ((rc = fa::encode3(&d.tmVt, a->vt, a->S, C, a->B, (cuuint64_t)a->vt_pitch * 2, (cuuint64_t)C * a->vt_pitch * 2,
-                        fa::kBKV, replay ? fa::kPVRows : d.dv, "V^T"))) return rc;
+                        fa::kBKV, pair ? fa::kPVRows : d.dv, "V^T"))) return rc;
 
   const int smem = d.d_chunks * fa::kQChunkBytes + fa::kKRingBytes + d.dv * fa::kBKV * 2 + 1024 + 512;
   const int smem_max = d.d_chunks * fa::kQChunkBytes + fa::kKRingBytes + 256 * fa::kBKV * 2 + 1024 + 512;
@@ -1323,12 +1388,14 @@ extern "C" int b200_attention_flash(const b200_flash_params* a, void* stream_v) 
   }
 #define B200_FLASH_LAUNCH(DCH, RP)                                                                                    \
   do {                                                                                                                \
-    static bool attr_done = false;                                                                                    \
-    if (!attr_done) {                                                                                                 \
-      B200_CUDA(cudaFuncSetAttribute(fa::flash_attn_kernel<DCH, RP>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
-                                     smem_max));   /* the widest output slice: later calls may need it */          \
-      attr_done = true;                                                                                               \
-    }                                                                                                                 \
+    static std::once_flag attr_once;                                                                                  \
+    static cudaError_t attr_rc = cudaSuccess;                                                                         \
+    const int smem_attr = smem_max;   /* the widest output slice: later calls may need it */                          \
+    std::call_once(attr_once, [smem_attr] {                                                                           \
+      attr_rc = cudaFuncSetAttribute(fa::flash_attn_kernel<DCH, RP>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                     smem_attr);                                                                      \
+    });                                                                                                               \
+    B200_CUDA(attr_rc);                                                                                               \
     B200_CUDA(b200::launch_pdl(fa::flash_attn_kernel<DCH, RP>, grid, fa::kThreads, smem, stream, d));                                          \
   } while (0)
   switch (d.d_chunks) {
@@ -1336,13 +1403,16 @@ extern "C" int b200_attention_flash(const b200_flash_params* a, void* stream_v) 
     case 2: B200_FLASH_LAUNCH(2, false); break;
     case 4: B200_FLASH_LAUNCH(4, false); break;
     default:
-      if (replay) {
-        static bool pair_attr_done = false;
-        if (!pair_attr_done) {
-          B200_CUDA(cudaFuncSetAttribute(fa::flash_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fa::kPairSmem));
-          pair_attr_done = true;
-        }
+      if (pair) {
+        static std::once_flag pair_once;
+        static cudaError_t pair_rc = cudaSuccess;
+        std::call_once(pair_once, [] {
+          pair_rc = cudaFuncSetAttribute(fa::flash_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fa::kPairSmem);
+        });
+        B200_CUDA(pair_rc);
         B200_CUDA(b200::launch_pdl(fa::flash_pair_kernel, grid, fa::kThreads, fa::kPairSmem, stream, d));       // clusters of 2 (__cluster_dims__)
+      } else if (replay) {
+        B200_FLASH_LAUNCH(8, true);
       } else {
         B200_FLASH_LAUNCH(8, false);
       }

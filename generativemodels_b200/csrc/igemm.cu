@@ -925,12 +925,12 @@ template <int BN, int STAGES>
 static int launch_tc(const IgemmDev& d, cudaStream_t stream) {
   constexpr int kStageBytes = kABytes + BN * kBK * 2;
   constexpr int smem = STAGES * kStageBytes + 1024 + 256 + 4 * 32 * 33 * 4 + 4 * BN * 4;
-  static bool attr_done = false;
-  if (!attr_done) {
-    B200_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   smem));
-    attr_done = true;
-  }
+  static std::once_flag attr_once;          // per instantiation; read-only afterwards (re-entrant entry point)
+  static cudaError_t attr_rc = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_rc = cudaFuncSetAttribute(igemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  });
+  B200_CUDA(attr_rc);
   int grid = d.num_tiles < sm_count() ? d.num_tiles : sm_count();
   B200_CUDA(b200::launch_pdl(igemm_tc_kernel<BN, STAGES>, grid, kThreads, smem, stream, d));
   B200_LAUNCH_CHECK("igemm_tc_kernel");

@@ -5,7 +5,7 @@ sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 import os
 import torch
 from generativemodels_b200 import _lib
-if os.environ.get("B200_DEV_LIB"):            # dev ablation builds of the library (tools only)
+if os.environ.get("B200_DEV_LIB", ""):            # dev ablation builds of the library (tools only)
     _lib.LIB_PATH = Path(os.environ["B200_DEV_LIB"]).resolve()
 from generativemodels_b200 import ops
 T = S = 89600

@@ -1,0 +1,11 @@
+#!/bin/bash
+# Attention ablation matrix at T = S = 89 600, d = 512: {single-CTA replay, CTA-pair} x {full, 7 ablations}.
+mkdir -p gpurun_out
+: > gpurun_out/attn_ablate.log
+for pair in 0 1; do
+  for ab in base 1 2 3 4 5 6 7; do
+    if [ $ab = base ]; then lib=""; else lib="tools/devlibs/libb200gen_ab$ab.so"; fi
+    res=$(timeout -k 10 120 env B200_FLASH_PAIR=$pair B200_DEV_LIB=$lib python tools/attn_probe.py replay 2>&1 | grep "ms," | awk '{print $6}' | tr '\n' ' ')
+    echo "pair=$pair ablate=$ab : $res" | tee -a gpurun_out/attn_ablate.log
+  done
+done
