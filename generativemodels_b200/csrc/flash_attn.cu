@@ -593,18 +593,19 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
         // MMA sits behind QK_j in the pipe, so the wait comes as late as possible — after the exponentials
         if (pcount >= 2) mbar_wait(p_empty(pb), ((pcount >> 1) & 1) ^ 1u);
         if (!FA_ABL(4)) tmem_st32(tP + lane_addr + pb * 32, pw);
-        if constexpr (REPLAY) {
-          // the same 64 probabilities to this row of the slab (128 contiguous bytes), for pass 2
-          h16* dst = slab_row + (long long)j * (kBM * kBKV);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) { if (!FA_ABL(3) && !FA_ABL(4)) stg256(dst + g * 16, pw + g * 8); }
-        }
         tmem_st_wait();
         const float lsum = ((sum8[0] + sum8[1]) + (sum8[2] + sum8[3])) + ((sum8[4] + sum8[5]) + (sum8[6] + sum8[7]));
         l_run += lsum;
         fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full(pb));
+        if constexpr (REPLAY) {
+          // the same 64 probabilities to this row of the slab (128 contiguous bytes), for pass 2 — after the hand-off,
+          // so that the releasing arrive above does not have to cover these stores
+          h16* dst = slab_row + (long long)j * (kBM * kBKV);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) { if (!FA_ABL(3) && !FA_ABL(4)) stg256(dst + g * 16, pw + g * 8); }
+        }
         FA_T(6);
       }
 #ifdef FA_TIMING
@@ -719,7 +720,7 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
 // P x V^T[256..511]) and the rescale-event log are those of flash_attn_kernel<8, true>.
 // ================================================================================================================
 #ifndef B200_FLASH_PAIR_DEFAULT
-#define B200_FLASH_PAIR_DEFAULT 0
+#define B200_FLASH_PAIR_DEFAULT 1
 #endif
 static constexpr uint32_t kPeerMask = 0xFEFFFFFFu;      // clears the CTA-rank bit of a shared::cluster address -> leader
 
@@ -732,8 +733,16 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// arrive (release at cluster scope) on a barrier given by its shared::cluster address
+// arrive on a barrier given by its shared::cluster address.  The per-block hand-offs (s_empty / p_full / o_empty) publish
+// nothing through memory — scores and probabilities travel through tensor memory, ordered by tcgen05.wait + fence — so
+// they use the default semantics (release at CTA scope).  A release at CLUSTER scope makes the arrive wait until the
+// thread's earlier global stores (the probability slab, 128 B per thread and block) are visible cluster-wide: measured
+// 4.6 ms of a 20.5 ms call (profiles/r2_attention_ablations.txt).  Only p1_done, which publishes the remote flag
+// words and the slab, uses the cluster-scope form.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t bar_cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
@@ -954,13 +963,13 @@ flash_pair_kernel(const __grid_constant__ FlashDev p) {
       uint32_t scount = 0, pvcount = 0, vcount = 0, icount = 0, ocount = 0;
       for (int item = pair_id; item < p.n_items; item += n_pairs, ++icount) {
         mbar_wait_warp(q_full, icount & 1);
-        mbar_wait_cluster_warp(o_empty, (ocount & 1) ^ 1u);    // both CTAs' epilogues have drained O
+        mbar_wait_warp(o_empty, (ocount & 1) ^ 1u);    // both CTAs' epilogues have drained O
         ++ocount;
         fence_after();
         for (int j = 0; j < n_kv + kLookahead; ++j) {
           if (j < n_kv) {
             const int sb = scount % kSBuf;
-            mbar_wait_cluster_warp(s_empty(sb), ((scount / kSBuf) & 1) ^ 1u);
+            mbar_wait_warp(s_empty(sb), ((scount / kSBuf) & 1) ^ 1u);
             fence_after();
             const uint32_t d_s = tS + sb * kBKV;
 #pragma unroll
@@ -987,7 +996,7 @@ flash_pair_kernel(const __grid_constant__ FlashDev p) {
           }
           if (j >= kLookahead) {
             const int pb = pvcount & 1, vs = vcount & 1;
-            mbar_wait_cluster_warp(p_full(pb), (pvcount >> 1) & 1);
+            mbar_wait_warp(p_full(pb), (pvcount >> 1) & 1);
             mbar_wait_warp(v_full(vs), (vcount >> 1) & 1);
             fence_after();
             if (elect_one()) {
@@ -1013,13 +1022,13 @@ flash_pair_kernel(const __grid_constant__ FlashDev p) {
         bool gated = false;
 #pragma unroll
         for (int e = 0; e < 8; ++e) gated |= ev_flags[e] != 0;
-        mbar_wait_cluster_warp(o_empty, (ocount & 1) ^ 1u);    // pass-1 epilogues have drained O
+        mbar_wait_warp(o_empty, (ocount & 1) ^ 1u);    // pass-1 epilogues have drained O
         ++ocount;
         fence_after();
         for (int j = 0; j < n_kv; ++j) {
           const int pb = pvcount & 1;
           mbar_wait_warp(r_full(rst), rph);
-          if (gated) mbar_wait_cluster_warp(p_full(pb), (pvcount >> 1) & 1);
+          if (gated) mbar_wait_warp(p_full(pb), (pvcount >> 1) & 1);
           fence_after();
           if (elect_one()) {
             const uint32_t a_lo = q_lo + rst * (kPRStageBytes >> 4);
@@ -1144,17 +1153,17 @@ flash_pair_kernel(const __grid_constant__ FlashDev p) {
         }
         if (pcount >= 2) mbar_wait(p_empty(pb), ((pcount >> 1) & 1) ^ 1u);
         if (!FA_ABL(4)) tmem_st32(tP + lane_addr + pb * 32, pw);
-        {
-          h16* dst = slab_row + (long long)j * (kBM * kBKV);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) { if (!FA_ABL(3) && !FA_ABL(4)) stg256(dst + g * 16, pw + g * 8); }
-        }
         tmem_st_wait();
         const float lsum = ((sum8[0] + sum8[1]) + (sum8[2] + sum8[3])) + ((sum8[4] + sum8[5]) + (sum8[6] + sum8[7]));
         l_run += lsum;
         fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(l_p_full0 + 8u * pb);
+        {   // the slab copy of the same probabilities (pass 2) goes out AFTER the hand-off: nothing waits on it
+          h16* dst = slab_row + (long long)j * (kBM * kBKV);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) { if (!FA_ABL(3) && !FA_ABL(4)) stg256(dst + g * 16, pw + g * 8); }
+        }
       }
       // publish this warp's "logged a rescale" flag to both CTAs, make the slab visible to the TMA reads of pass 2,
       // then arrive on both CTAs' p1_done
@@ -1164,8 +1173,8 @@ flash_pair_kernel(const __grid_constant__ FlashDev p) {
       if (lane == 0) {
         st_cluster_u32(flag_a[0], n_ev > 0 ? 1u : 0u);
         st_cluster_u32(flag_a[1], n_ev > 0 ? 1u : 0u);
-        mbar_arrive_cluster(p1_done_a[0]);
-        mbar_arrive_cluster(p1_done_a[1]);
+        mbar_arrive_cluster_release(p1_done_a[0]);
+        mbar_arrive_cluster_release(p1_done_a[1]);
       }
       mbar_wait_cluster(p1_done, icount & 1);
       bool gated = false;
