@@ -50,10 +50,28 @@ class GraphedModule(nn.Module):
         def one(v):
             if torch.is_tensor(v):
                 return ("T", tuple(v.shape), v.dtype, v.device)
-            if v is None:
-                return None
-            raise TypeError("graphed modules take tensors / None only")
+            if v is None or isinstance(v, (bool, int, float, str)):
+                return ("C", v)                       # baked into the captured graph: part of the signature
+            if isinstance(v, (list, tuple)):
+                return ("L", type(v).__name__, tuple(one(e) for e in v))
+            raise TypeError("graphed modules take tensors, None, scalars and (nested) lists / tuples of them")
         return tuple(one(a) for a in args), tuple((k, one(v)) for k, v in sorted(kwargs.items()))
+
+    @staticmethod
+    def _clone(v):
+        if torch.is_tensor(v):
+            return v.clone()
+        if isinstance(v, (list, tuple)):
+            return type(v)(GraphedModule._clone(e) for e in v)
+        return v
+
+    @staticmethod
+    def _copy_into(dst, src):
+        if torch.is_tensor(dst):
+            dst.copy_(src, non_blocking=True)
+        elif isinstance(dst, (list, tuple)):
+            for d, s_ in zip(dst, src):
+                GraphedModule._copy_into(d, s_)
 
     @torch.no_grad()
     def forward(self, *args, **kwargs):
@@ -67,8 +85,8 @@ class GraphedModule(nn.Module):
             self._weights_sig = sig
         entry = self._entries.get(key)
         if entry is None:
-            static_args = [a.clone() if torch.is_tensor(a) else a for a in args]
-            static_kwargs = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in kwargs.items()}
+            static_args = [self._clone(a) for a in args]
+            static_kwargs = {k: self._clone(v) for k, v in kwargs.items()}
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
@@ -81,15 +99,13 @@ class GraphedModule(nn.Module):
             entry = self._entries[key] = (graph, static_args, static_kwargs, out)
         graph, static_args, static_kwargs, out = entry
         for dst, src in zip(static_args, args):
-            if torch.is_tensor(dst):
-                dst.copy_(src, non_blocking=True)
+            self._copy_into(dst, src)
         for k, dst in static_kwargs.items():
-            if torch.is_tensor(dst):
-                dst.copy_(kwargs[k], non_blocking=True)
+            self._copy_into(dst, kwargs[k])
         graph.replay()
-        # a fresh tensor per call (one small stream-ordered copy): callers such as PNDMScheduler keep references to
-        # past outputs, which a shared static buffer would silently overwrite on the next replay
-        return out.clone() if torch.is_tensor(out) else out
+        # fresh tensors per call (small stream-ordered copies): callers such as PNDMScheduler keep references to past
+        # outputs, which shared static buffers would silently overwrite on the next replay
+        return self._clone(out)
 
 
 def graphed(module: nn.Module, warmup: int = 2) -> GraphedModule:

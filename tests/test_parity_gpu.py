@@ -666,3 +666,29 @@ def test_param_data_surgery_needs_invalidate(cuda_device):
     want = O.unet_forward({k: v.cpu() for k, v in new.items()}, G.unet_oracle_cfg(kw), x.cpu(), ts.cpu())
     check(y1, want)
     assert not torch.equal(y0, y1)
+
+
+def test_cuda_graph_nested_inputs_outputs(cuda_device):
+    """graphed() with a tuple of tensors as OUTPUT (ControlNet residuals) and a list of tensors + a scalar as INPUTS
+    (UNet with down_block_additional_residuals, ControlNet conditioning_scale): replay equals the eager call, outputs
+    are fresh tensors per call, a different scalar is a different graph."""
+    from generativemodels_b200.cuda_graph import graphed
+    torch.manual_seed(0)
+    cn = G.randomize_zero_params(nets().ControlNet(**G.CONTROLNET_CASE)).cuda().eval()
+    ukw = {k: v for k, v in G.CONTROLNET_CASE.items() if not k.startswith("conditioning_embedding")}
+    un = G.randomize_zero_params(nets().DiffusionModelUNet(out_channels=3, **ukw)).cuda().eval()
+    gcn, gun = graphed(cn), graphed(un)
+    torch.manual_seed(1)
+    x, cond, ctx = torch.randn(2, 3, 16, 16).cuda(), torch.rand(2, 1, 16, 16).cuda(), torch.randn(2, 3, 8).cuda()
+    for t, scale in ((700.0, 1.0), (100.0, 1.0), (100.0, 0.5)):
+        ts = torch.Tensor((t,)).cuda()
+        down, mid = cn(x, ts, cond, conditioning_scale=scale, context=ctx)
+        gdown, gmid = gcn(x, ts, cond, conditioning_scale=scale, context=ctx)
+        assert len(gdown) == len(down) and all(torch.equal(a, b) for a, b in zip(gdown, down)) and torch.equal(gmid, mid)
+        want = un(x, ts, context=ctx, down_block_additional_residuals=down, mid_block_additional_residual=mid)
+        got = gun(x, ts, context=ctx, down_block_additional_residuals=gdown, mid_block_additional_residual=gmid)
+        assert torch.equal(got, want)
+    assert len(gcn._entries) == 2            # two conditioning scales -> two captured graphs
+    a = gcn(x, ts, cond, conditioning_scale=0.5, context=ctx)[0][0]
+    b = gcn(x + 1, ts, cond, conditioning_scale=0.5, context=ctx)[0][0]
+    assert a.data_ptr() != b.data_ptr() and not torch.equal(a, b)
