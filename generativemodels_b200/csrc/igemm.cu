@@ -175,6 +175,53 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// ---- CTA-pair (cta_group::2) variants: see igemm_tc_kernel<BN, STAGES, true> ----
+static constexpr uint32_t kPeerMask = 0xFEFFFFFFu;      // clears the CTA-rank bit of a shared::cluster address -> leader
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// default semantics (release at CTA scope): the hand-off publishes nothing through memory (the accumulator lives in
+// tensor memory, ordered by tcgen05.wait + fence) — a cluster-scope release would wait for the epilogue's global stores
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerMask) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_pair(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c0, int c1,
+                                                 int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar & kPeerMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c0, int c1,
+                                                 int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar & kPeerMask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit2(uint32_t bar) {      // same barrier offset in both CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void umma2_h16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -443,9 +490,15 @@ __device__ __forceinline__ void store_staged(const IgemmDev& p, const float* v, 
 // ------------------------------------------------------------------------------------------------
 // The tcgen05 kernel
 // ------------------------------------------------------------------------------------------------
-template <int BN, int STAGES>
+// PAIR = true: the CTA-pair (tcgen05.mma.cta_group::2) variant for the big 256-column convolutions.  Two CTAs form one
+// 256-row x BN tile: each owns 128 output voxels (its A box, its accumulator in its own tensor memory, its epilogue) but
+// stages only HALF of the weight tile — the B operand of an M = 256 MMA is split across the pair — so the per-SM operand
+// bytes per tensor cycle drop from 48 KB to 32 KB per 64-channel chunk (less shared-memory and L2 -> SM traffic under
+// the power cap, six stages instead of four in the same 192 KB).  The leader CTA's issuing thread drives both tensor
+// pipes; TMA of both CTAs completes on the leader's barriers; commits are multicast to both CTAs.
+template <int BN, int STAGES, bool PAIR = false>
 __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_constant__ IgemmDev p) {
-  constexpr int kBBytes = BN * kBK * 2;
+  constexpr int kBBytes = (PAIR ? BN / 2 : BN) * kBK * 2;
   constexpr int kStageBytes = kABytes + kBBytes;
   constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;   // power of two for BN in {16..256}
   constexpr int CH = (BN >= 32) ? 32 : 16;
@@ -466,6 +519,11 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  // PAIR: one work unit per CTA pair; `tile` below is the pair-level tile index
+  const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int n_workers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -474,24 +532,53 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), 4);
+      mbar_init(tempty_bar(b), PAIR ? 8 : 4);       // PAIR: the four epilogue warps of both CTAs, on the leader's copy
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
-                 "r"((uint32_t)kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (PAIR) {      // the same warp of both CTAs: one pair-wide allocation
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                   "r"((uint32_t)kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                   "r"((uint32_t)kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tcgen05_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();       // the peer's barriers exist before anything signals them remotely
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   pdl_wait();                       // barriers and tensor memory are set up: now wait for the producer of our inputs
 
   const int num_k = p.num_k_chunks;
+  // work-unit index -> (k-split, column tile, spatial tile, sample).  PAIR: the unit is a pair of M tiles (2 * mp + rank)
+  // sharing one column tile; an odd tile count leaves the last pair's second CTA a dead tile (nb == N: its TMA boxes
+  // are zero-filled, its rows are never stored).
+  struct TileIdx { int ks, nt, wt, ht, dt, nb; };
+  auto decode_tile = [&](int tile) {
+    TileIdx t;
+    int x = tile;
+    if constexpr (PAIR) {
+      t.ks = 0;
+      t.nt = x % p.tiles_n; x /= p.tiles_n;
+      x = 2 * x + (int)rank;
+    } else {
+      t.ks = x % p.k_splits; x /= p.k_splits;
+      t.nt = x % p.tiles_n; x /= p.tiles_n;
+    }
+    t.wt = x % p.tiles_w; x /= p.tiles_w;
+    t.ht = x % p.tiles_h; x /= p.tiles_h;
+    t.dt = x % p.tiles_d; x /= p.tiles_d;
+    t.nb = x;
+    return t;
+  };
 
   if (warp == 0) {
     // ============================== TMA producer ==============================
@@ -500,14 +587,9 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        int t = tile;
-        const int ks = t % p.k_splits; t /= p.k_splits;
-        const int nt = t % p.tiles_n; t /= p.tiles_n;
-        const int wt = t % p.tiles_w; t /= p.tiles_w;
-        const int ht = t % p.tiles_h; t /= p.tiles_h;
-        const int dt = t % p.tiles_d; t /= p.tiles_d;
-        const int nb = t;
+      for (int tile = worker; tile < p.num_tiles; tile += n_workers) {
+        const TileIdx ti = decode_tile(tile);
+        const int ks = ti.ks, nt = ti.nt, wt = ti.wt, ht = ti.ht, dt = ti.dt, nb = ti.nb;
         const int iw0 = wt * p.BW * p.sw, ih0 = ht * p.BH * p.sh, id0 = dt * p.BD * p.sd;
         const int n0 = nt * BN;
         const int wb = p.w_batched ? nb : 0;
@@ -522,9 +604,16 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
             if (kglob < k_begin || kglob >= k_end) continue;
             mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t a_dst = smem_base + stage * kStageBytes;
-            mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
-            tma_load_5d(tm, full_bar(stage), a_dst, (sg.c0 + c) * kBK, cw, ch, cd, nb);
-            tma_load_3d(&p.tmB, full_bar(stage), a_dst + kABytes, kglob * kBK, n0, wb);
+            if constexpr (PAIR) {
+              // both CTAs load their own A box and their half of the weight tile; all bytes land on the LEADER's barrier
+              if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * kStageBytes);
+              tma_load_5d_pair(tm, full_bar(stage), a_dst, (sg.c0 + c) * kBK, cw, ch, cd, nb);
+              tma_load_3d_pair(&p.tmB, full_bar(stage), a_dst + kABytes, kglob * kBK, n0 + (int)rank * (BN / 2), wb);
+            } else {
+              mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
+              tma_load_5d(tm, full_bar(stage), a_dst, (sg.c0 + c) * kBK, cw, ch, cd, nb);
+              tma_load_3d(&p.tmB, full_bar(stage), a_dst + kABytes, kglob * kBK, n0, wb);
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
         }
@@ -532,18 +621,18 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
     }
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(kBM, BN);
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc(PAIR ? 2 * kBM : kBM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = worker; tile < p.num_tiles; tile += n_workers, ++it) {
         const int buf = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(tempty_bar(buf), acc_phase ^ 1u);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + buf * BN;
-        const int ks = tile % p.k_splits;
+        const int ks = PAIR ? 0 : tile % p.k_splits;
         const int nk = split_begin(num_k, p.k_splits, ks + 1) - split_begin(num_k, p.k_splits, ks);
         for (int k = 0; k < nk; ++k) {
           mbar_wait(full_bar(stage), phase);
@@ -554,12 +643,13 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
 #pragma unroll
           for (int kk = 0; kk < kBK / 16; ++kk) {
             // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in >>4 units
-            umma_h16(d_tmem, adesc + 2u * kk, bdesc + 2u * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+            if constexpr (PAIR) umma2_h16(d_tmem, adesc + 2u * kk, bdesc + 2u * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+            else umma_h16(d_tmem, adesc + 2u * kk, bdesc + 2u * kk, idesc, (k | kk) != 0 ? 1u : 0u);
           }
-          tcgen05_commit(empty_bar(stage));
+          if constexpr (PAIR) tcgen05_commit2(empty_bar(stage)); else tcgen05_commit(empty_bar(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        tcgen05_commit(tfull_bar(buf));
+        if constexpr (PAIR) tcgen05_commit2(tfull_bar(buf)); else tcgen05_commit(tfull_bar(buf));
       }
     }
   } else {
@@ -593,16 +683,13 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
     };
     if (gn_on) gn_flush();
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      int t = tile;
-      const int ks = t % p.k_splits; t /= p.k_splits;
-      const int nt = t % p.tiles_n; t /= p.tiles_n;
-      const int wt = t % p.tiles_w; t /= p.tiles_w;
-      const int ht = t % p.tiles_h; t /= p.tiles_h;
-      const int dt = t % p.tiles_d; t /= p.tiles_d;
-      const int nb = t;
+    for (int tile = worker; tile < p.num_tiles; tile += n_workers, ++it) {
+      const TileIdx ti = decode_tile(tile);
+      const int ks = ti.ks, nt = ti.nt, wt = ti.wt, ht = ti.ht, dt = ti.dt;
+      const bool live = ti.nb < p.N;               // PAIR: the second CTA of the last pair may hold a dead tile
+      const int nb = live ? ti.nb : p.N - 1;
       const int ow = wt * p.BW + rw, oh = ht * p.BH + rh, od = dt * p.BD + rd;
-      const bool row_ok = (ow < p.OW) && (oh < p.OH) && (od < p.OD);
+      const bool row_ok = live && (ow < p.OW) && (oh < p.OH) && (od < p.OD);
       const long long out_off = nb * p.out_sN + od * p.out_sD + oh * p.out_sH + ow * p.out_sW + ks * p.split_stride;
       const long long res_off = nb * p.res_sN + od * p.res_sD + oh * p.res_sH + ow * p.res_sW;
       const int n0 = nt * BN;
@@ -712,18 +799,24 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
       }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(buf));
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_leader(tempty_bar(buf)); else mbar_arrive(tempty_bar(buf));
+      }
     }
     if (gn_on) { __syncwarp(); gn_flush(); }
   }
 
   tcgen05_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();     // neither CTA may leave (or free tensor memory) while the pair is in use
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"((uint32_t)kTmemCols)
-                 : "memory");
+    if constexpr (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols)
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols)
+                   : "memory");
   }
 }
 
