@@ -1014,20 +1014,39 @@ static Plan make_plan(const b200_igemm_params* p, bool allow_split) {
   return pl;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool PAIR = false>
 static int launch_tc(const IgemmDev& d, cudaStream_t stream) {
-  constexpr int kStageBytes = kABytes + BN * kBK * 2;
+  constexpr int kStageBytes = kABytes + (PAIR ? BN / 2 : BN) * kBK * 2;
   constexpr int smem = STAGES * kStageBytes + 1024 + 256 + 4 * 32 * 33 * 4 + 4 * BN * 4;
   static std::once_flag attr_once;          // per instantiation; read-only afterwards (re-entrant entry point)
   static cudaError_t attr_rc = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_rc = cudaFuncSetAttribute(igemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr_rc = cudaFuncSetAttribute(igemm_tc_kernel<BN, STAGES, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   });
   B200_CUDA(attr_rc);
-  int grid = d.num_tiles < sm_count() ? d.num_tiles : sm_count();
-  B200_CUDA(b200::launch_pdl(igemm_tc_kernel<BN, STAGES>, grid, kThreads, smem, stream, d));
+  if constexpr (PAIR) {
+    const int pairs = sm_count() / 2;
+    const int grid = 2 * (d.num_tiles < pairs ? d.num_tiles : pairs);
+    B200_CUDA(b200::launch_cluster(igemm_tc_kernel<BN, STAGES, PAIR>, 2, grid, kThreads, smem, stream, d));
+  } else {
+    int grid = d.num_tiles < sm_count() ? d.num_tiles : sm_count();
+    B200_CUDA(b200::launch_pdl(igemm_tc_kernel<BN, STAGES, PAIR>, grid, kThreads, smem, stream, d));
+  }
   B200_LAUNCH_CHECK("igemm_tc_kernel");
   return B200_OK;
+}
+
+// the CTA-pair variant of the 256-column kernel (0 / 1; B200_IGEMM_PAIR overrides the build default)
+#ifndef B200_IGEMM_PAIR_DEFAULT
+#define B200_IGEMM_PAIR_DEFAULT 1
+#endif
+static bool igemm_pair_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200_IGEMM_PAIR");
+    v = e ? (e[0] != '0') : B200_IGEMM_PAIR_DEFAULT;
+  }
+  return v != 0;
 }
 
 static int env_impl() {
@@ -1177,6 +1196,10 @@ extern "C" int b200_igemm(const b200_igemm_params* p, void* stream_v) {
   }
   B200_CHECK_ARG(pl.ntiles * splits < (1ll << 31), "igemm: too many tiles");
   d.num_tiles = (int)pl.ntiles;
+  // CTA pairs for the big 256-column calls: at least one pair-tile per pair of SMs, no split-K / score statistics
+  const bool pair = igemm_pair_mode() && BN == 256 && splits == 1 && !p->stat_ptr && !d.out_staged &&
+                    pl.m_tiles >= 2ll * sm_count();
+  if (pair) d.num_tiles = (int)(((pl.m_tiles + 1) / 2) * pl.tiles_n);
 
   // ---- tensor maps ----
   for (int s = 0; s < 2; ++s) {
@@ -1206,7 +1229,7 @@ extern "C" int b200_igemm(const b200_igemm_params* p, void* stream_v) {
     cuuint64_t bs = p->w_bstride ? (cuuint64_t)p->w_bstride * 2 : (cuuint64_t)p->w_rows * p->w_pitch * 2;
     cuuint64_t strides[2] = {(cuuint64_t)p->w_pitch * 2, bs};
     B200_CHECK_ARG(bs % 16 == 0, "igemm: weight batch stride not 16-byte aligned");
-    cuuint32_t box[3] = {(cuuint32_t)kBK, (cuuint32_t)BN, 1};
+    cuuint32_t box[3] = {(cuuint32_t)kBK, (cuuint32_t)(pair ? BN / 2 : BN), 1};     // pair: each CTA stages half the rows
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = g_encode(&d.tmB, B200_H16_TMAP, 3, const_cast<void*>(p->w_ptr), dims,
                           strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -1224,7 +1247,7 @@ extern "C" int b200_igemm(const b200_igemm_params* p, void* stream_v) {
       case 32:  return launch_tc<32, 8>(dev, stream);
       case 64:  return launch_tc<64, 8>(dev, stream);
       case 128: return launch_tc<128, 6>(dev, stream);
-      default:  return launch_tc<256, 4>(dev, stream);
+      default:  return pair ? launch_tc<256, 6, true>(dev, stream) : launch_tc<256, 4>(dev, stream);
     }
   };
   if (splits == 1) return launch(d);
