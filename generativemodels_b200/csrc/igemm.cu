@@ -1196,9 +1196,10 @@ extern "C" int b200_igemm(const b200_igemm_params* p, void* stream_v) {
   }
   B200_CHECK_ARG(pl.ntiles * splits < (1ll << 31), "igemm: too many tiles");
   d.num_tiles = (int)pl.ntiles;
-  // CTA pairs for the big 256-column calls: at least one pair-tile per pair of SMs, no split-K / score statistics
+  // CTA pairs for the 256-column calls that fill the machine (at least one tile per SM — pairs of M tiles over pairs
+  // of SMs quantise like single tiles over single SMs), no split-K / score statistics / staged stores
   const bool pair = igemm_pair_mode() && BN == 256 && splits == 1 && !p->stat_ptr && !d.out_staged &&
-                    pl.m_tiles >= 2ll * sm_count();
+                    pl.m_tiles >= 2 && pl.ntiles >= sm_count();
   if (pair) d.num_tiles = (int)(((pl.m_tiles + 1) / 2) * pl.tiles_n);
 
   // ---- tensor maps ----
