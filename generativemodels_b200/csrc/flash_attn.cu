@@ -34,6 +34,7 @@ struct FlashDev {
   int B, T, S, heads, dh, d_chunks, dv, n_dv;
   int q_tiles, n_items, n_kv;
   float scale_log2;
+  float rescale_thr;               // lazy-rescale threshold in log2 units (see kRescaleThreshold)
   h16* out;
   long long out_bstride, out_pitch;
   const h16* res;
@@ -54,7 +55,11 @@ static constexpr int kKRingBytes = 64 * 1024;           // K ring: 4 stages x 2 
 static constexpr int kMaxKStages = 8;
 static constexpr int kQChunkBytes = kBM * 64 * 2;      // 16 KB
 static constexpr int kKChunkBytes = kBKV * 64 * 2;     // 8 KB: 64 keys x 64 channels
-static constexpr float kRescaleThreshold = 8.0f;       // log2 domain
+// Lazy rescale: the reference maximum of a row is only raised when a block's maximum exceeds it by more than 2^thr,
+// so probabilities reach at most 2^thr.  12 keeps them far inside fp16's range (65504) and its 11-bit precision holds
+// for every p >= 6e-5; rows whose maximum drifts slowly (the common case on real activations) then never rescale, and a
+// work item without rescales runs its pass 2 ungated.  B200_FLASH_RESCALE overrides (dev A/B).
+static constexpr float kRescaleThreshold = 12.0f;      // log2 domain
 // The chain S_j -> softmax -> P_j -> PV_j is a latency chain (TMEM read, barrier hand-offs, TMEM write); the tensor pipe
 // only stays busy if independent work is queued behind it: QK^T runs kLookahead blocks ahead of PV.
 static constexpr int kSBuf = 3, kLookahead = 2;
@@ -531,7 +536,7 @@ __global__ void __launch_bounds__(kThreads, 1) flash_attn_kernel(const __grid_co
         const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
                                fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7]))) * p.scale_log2;
         // lazy rescale: only raise the reference maximum when it would grow by more than 2^8
-        const bool need = (mx > m_used + kRescaleThreshold);
+        const bool need = (mx > m_used + p.rescale_thr);
         const float m_new = need ? mx : m_used;
         const float factor = (need && m_used > -INFINITY) ? exp2f(m_used - m_new) : 1.0f;
         const unsigned any = __ballot_sync(0xffffffffu, need && m_used > -INFINITY);
@@ -1102,7 +1107,7 @@ flash_pair_kernel(const __grid_constant__ FlashDev p) {
         }
         const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
                                fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7]))) * p.scale_log2;
-        const bool need = (mx > m_used + kRescaleThreshold);
+        const bool need = (mx > m_used + p.rescale_thr);
         const float m_new = need ? mx : m_used;
         const float factor = (need && m_used > -INFINITY) ? exp2f(m_used - m_new) : 1.0f;
         const unsigned any = __ballot_sync(0xffffffffu, need && m_used > -INFINITY);
@@ -1369,6 +1374,15 @@ extern "C" int b200_attention_flash(const b200_flash_params* a, void* stream_v) 
   B200_CHECK_ARG(items < (1ll << 31), "attention_flash: too many work items");
   d.n_items = (int)items;
   d.scale_log2 = a->scale * 1.4426950408889634f;
+  {
+    static float thr = -1.f;
+    if (thr < 0.f) {
+      const char* e = getenv("B200_FLASH_RESCALE");
+      thr = e ? (float)atof(e) : fa::kRescaleThreshold;
+      if (!(thr >= 1.f && thr <= 14.f)) thr = fa::kRescaleThreshold;
+    }
+    d.rescale_thr = thr;
+  }
   d.out = reinterpret_cast<h16*>(a->out);
   d.out_pitch = a->out_pitch; d.out_bstride = (long long)a->T * a->out_pitch;
   d.res = reinterpret_cast<const h16*>(a->res);

@@ -477,15 +477,16 @@ def test_attention_tensorcore(cuda_device, B, T, heads, dh, unfused, monkeypatch
 
 @pytest.mark.parametrize("dh,replay", [(256, True), (512, True), (512, False)], ids=["d256", "d512-replay", "d512-recompute"])
 def test_attention_flash_rescale(cuda_device, monkeypatch, dh, replay):
-    """Keys whose scores grow along the sequence force the running maximum up by far more than 2^8 several times,
-    exercising the lazy O-rescale path (tcgen05.ld / tcgen05.st on the accumulator) and, for head_dim 512 with a
-    workspace, the logged-rescale replay on the second output half (gated pass 2)."""
+    """Keys whose scores grow along the sequence force the running maximum up by far more than the lazy-rescale
+    threshold (2^12) several times, exercising the O-rescale path (tcgen05.ld / tcgen05.st on the accumulator) and, for
+    head_dim 512 with a workspace, the logged-rescale replay on the second output half (gated pass 2).  Enough query
+    tiles that the call is not routed to the small-problem path."""
     ops = _ops()
     monkeypatch.setattr(ops, "_FLASH_REPLAY", replay)
     torch.manual_seed(11)
-    B, T, S = 1, 300, 1000
+    B, T, S = 1, 128 * 40 + 9, 1000
     q = torch.randn(B, T, dh)
-    k = torch.randn(B, S, dh) * torch.linspace(0.2, 6.0, S)[None, :, None]
+    k = torch.randn(B, S, dh) * torch.linspace(0.2, 9.0, S)[None, :, None]
     v = torch.randn(B, S, dh)
     scale = 1 / math.sqrt(dh)
     ref = _attn_ref(bf(q), bf(k), bf(v), 1, dh, scale)
@@ -502,7 +503,7 @@ def test_attention_flash_replay_matches_recompute(cuda_device, monkeypatch):
     torch.manual_seed(12)
     B, T, S, dh = 2, 128 * 90 + 37, 1000 + 21, 512
     q, k, v = torch.randn(B, T, dh), torch.randn(B, S, dh), torch.randn(B, S, dh)
-    k[:, 500:] *= 3.0                                     # a few late rescales in some rows
+    k[:, 500:] *= 6.0                                     # late rescales (beyond the 2^12 threshold) in many rows
     res = torch.randn(B, T, dh).to(ops.H16).cuda()
     args = (q.to(ops.H16).cuda(), k.to(ops.H16).cuda(), None, 1, dh, 1 / math.sqrt(dh))
     vt = F.pad(v.to(ops.H16).transpose(1, 2), (0, (-S) % 8)).contiguous().cuda()
