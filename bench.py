@@ -14,7 +14,7 @@ Definitions:
   * value     = inputs resident in HBM; e2e = the same metric through DiffusionInferer.sample() starting from pinned
                 HOST noise (H2D), the per-step timestep H2D the reference API does, the final D2H of the sample and —
                 at N > 1 — the all_gather of the finished samples.
-  * roofline  = tensor-pipe: algorithmic FLOPs of the 3x3x3-conv launches of igemm_tc_kernel<256,4> in the timed
+  * roofline  = tensor-pipe: algorithmic FLOPs of the 3x3x3-conv launches of igemm_tc_kernel<256,6,pair> in the timed
                 region / their CUDA-event time, against MEASURED_PEAKS.json's sustained bf16/fp16 GEMM throughput;
                 roofline.secondary[] = the attention kernel (tensor) and the HBM-bound kernels (GroupNorm apply,
                 DDIM step) timed the same way against the measured copy bandwidth.
@@ -422,7 +422,7 @@ def other_configs_gpu(world, rank, peak_tf, states_out):
         host = torch.randn(nb, 3, 64, 64).pin_memory()
         dev = host.cuda()
         out_host = torch.empty(nb, 1, 256, 256).pin_memory()
-        t = maxrank(time_calls(lambda: inf.sample(dev, ae, un, s, verbose=False), 2, sync))
+        t = maxrank(time_calls(lambda: inf.sample(dev, ae, un, s, verbose=False), 3 if nb == 1 else 2, sync))
 
         def e2e():
             out_host.copy_(inf.sample(host.cuda(non_blocking=True), ae, un, s, verbose=False), non_blocking=True)
@@ -651,10 +651,12 @@ def run_b200(args):
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved / peak_tf if peak_tf else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel (the 256->256
-                         # 3x3x3 conv at 160x224x160; algorithmic 5.88e9 B) from the ncu --set full capture under
-                         # profiles/ (r1_ncu_igemm_conv256_fullres_v6_details.txt: 4.24 GB read + 2.91 GB written)
-                         "traffic": 7.14e9,
-                         "kernel": "igemm_tc_kernel<256,4> (3x3x3 convolutions)", "peak_source": which + " sustained 16-bit GEMM",
+                         # 3x3x3 conv at 160x224x160; algorithmic 5.88e9 B) from the ncu --set full capture
+                         # profiles/r2_ncu_igemm_pair_conv256_fullres_details.txt (3.47 GB read + 2.91 GB written,
+                         # L2 hit rate 94.8 %, tensor pipe 99.8 % of active cycles at 1.28 GHz in that capture)
+                         "traffic": 6.37e9,
+                         "kernel": "igemm_tc_kernel<256,6,pair> (3x3x3 convolutions, tcgen05 cta_group::2)",
+                         "peak_source": which + " sustained 16-bit GEMM",
                          "share_of_step": times["conv"] / ms_local if ms_local else None,
                          "launches_timed": counts["conv"], "secondary": secondary},
             "cpu_baseline": cpu_line,
