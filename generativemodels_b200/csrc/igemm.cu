@@ -376,6 +376,9 @@ __device__ __forceinline__ void act_inplace(float* v, int act) {
   } else if (act == B200_ACT_GELU) {
 #pragma unroll
     for (int j = 0; j < CH; ++j) v[j] = 0.5f * v[j] * (1.0f + erff(v[j] * 0.70710678118654752f));
+  } else if (act == B200_ACT_TANH || act == B200_ACT_SIGMOID) {
+#pragma unroll
+    for (int j = 0; j < CH; ++j) v[j] = apply_act(v[j], act);
   } else {
 #pragma unroll
     for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.0f);

@@ -33,6 +33,21 @@ class _Cached:
         return hit[1]
 
 
+_ACT_CODES = {"RELU": ops.ACT_RELU, "SILU": ops.ACT_SILU, "SWISH": ops.ACT_SILU, "LEAKYRELU": ops.ACT_LEAKYRELU,
+              "GELU": ops.ACT_GELU, "TANH": ops.ACT_TANH, "SIGMOID": ops.ACT_SIGMOID}
+
+
+def act_code(act) -> int:
+    """monai ``Act[...]`` name (or (name, kwargs) tuple with default kwargs) -> epilogue activation code."""
+    name = act[0] if isinstance(act, (tuple, list)) else act
+    if isinstance(act, (tuple, list)) and len(act) > 1 and act[1]:
+        raise NotImplementedError(f"activation {act!r} with non-default arguments is not supported")
+    code = _ACT_CODES.get(str(name).upper())
+    if code is None:
+        raise NotImplementedError(f"activation {name!r} is not supported on the B200 path ({sorted(_ACT_CODES)})")
+    return code
+
+
 def _same_padding(kernel_size: int, dilation: int = 1) -> int:
     return (kernel_size - 1) // 2 * dilation
 
@@ -60,9 +75,7 @@ class Convolution(nn.Module, _Cached):
         else:
             ctor = nn.Conv2d if spatial_dims == 2 else nn.Conv3d
             self.conv = ctor(in_channels, out_channels, kernel_size, stride=strides, padding=self.padding, bias=bias)
-        self.act = ops.ACT_NONE if (conv_only or act is None) else {"RELU": ops.ACT_RELU, "SILU": ops.ACT_SILU,
-                                                                            "LEAKYRELU": ops.ACT_LEAKYRELU}[
-            str(act).upper()]
+        self.act = ops.ACT_NONE if (conv_only or act is None) else act_code(act)
 
     def packed(self, splits: Sequence[int] | None = None, padding=None):
         pad = self.padding if padding is None else padding

@@ -8,7 +8,7 @@ import torch.nn as nn
 
 from ... import _lib, ops
 from ...ops import ACT_RELU, CL
-from .._holders import Convolution, on_input_device, require_cuda
+from .._holders import Convolution, act_code, on_input_device, require_cuda
 from ..layers.vector_quantizer import EMAQuantizer, VectorQuantizer
 from .diffusion_model_unet import ensure_tuple_rep
 
@@ -75,7 +75,9 @@ class Decoder(nn.Module):
                                       kernel_size=k, dilation=d, padding=p, output_padding=op, is_transposed=True,
                                       conv_only=last, act=act))
         if output_act:
-            raise NotImplementedError("VQVAE output_act is not on the sampling path of the reference tutorials")
+            # vqvae.py:263-264 appends Act[output_act]() after the last (conv_only) transposed convolution: here it
+            # rides in that convolution's epilogue
+            blocks[-1].act = act_code(output_act)
         self.blocks = nn.ModuleList(blocks)
 
     def forward(self, x: CL) -> CL:

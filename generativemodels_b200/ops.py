@@ -14,7 +14,7 @@ from typing import Sequence
 import torch
 
 from . import _lib
-from ._lib import (ACT_GELU, ACT_LEAKYRELU, ACT_NONE, ACT_RELU, ACT_SILU, DT_H16, DT_F32, DdimCoef, DdpmCoef, GnApplyParams, GnStatsParams,
+from ._lib import (ACT_GELU, ACT_LEAKYRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SILU, ACT_TANH, DT_H16, DT_F32, DdimCoef, DdpmCoef, GnApplyParams, GnStatsParams,
                    IgemmParams, PndmCoef, check)
 
 # torch dtype of the library's 16-bit storage type (fp16 unless B200_ACT_DTYPE=h16; see _lib.ACT_DTYPE)
@@ -22,7 +22,7 @@ H16 = torch.float16 if _lib.ACT_DTYPE == "fp16" else torch.bfloat16
 
 __all__ = ["CL", "to_cl", "from_cl", "PackedConv", "PackedConvTranspose", "PackedLinear", "conv", "conv_transpose",
            "linear", "groupnorm", "layernorm", "upsample_nearest2x", "avgpool2", "axpy", "geglu", "attention",
-           "timestep_embedding", "small_linear", "ACT_NONE", "ACT_RELU", "ACT_SILU", "ACT_LEAKYRELU", "ACT_GELU"]
+           "timestep_embedding", "small_linear", "ACT_NONE", "ACT_RELU", "ACT_SILU", "ACT_LEAKYRELU", "ACT_GELU", "ACT_TANH", "ACT_SIGMOID"]
 
 
 def _stream() -> int:

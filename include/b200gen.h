@@ -39,6 +39,8 @@ extern "C" {
 #define B200_ACT_RELU 1
 #define B200_ACT_SILU 2
 #define B200_ACT_GELU 4        /* exact erf GELU (nn.GELU default; monai MLPBlock act="GELU") */
+#define B200_ACT_TANH 5        /* VQVAE output_act (vqvae.py:263-264, monai Act["TANH"])       */
+#define B200_ACT_SIGMOID 6     /* VQVAE output_act (monai Act["SIGMOID"])                      */
 #define B200_ACT_LEAKYRELU 3   /* nn.LeakyReLU() default slope 0.01 (monai act="LEAKYRELU" in blocks/spade_norm.py:52-60) */
 
 #define B200_IGEMM_MAX_SEG 128

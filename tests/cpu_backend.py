@@ -51,6 +51,10 @@ def _act(x, a):
         return F.leaky_relu(x, 0.01)
     if a == _lib.ACT_GELU:
         return F.gelu(x)
+    if a == _lib.ACT_TANH:
+        return torch.tanh(x)
+    if a == _lib.ACT_SIGMOID:
+        return torch.sigmoid(x)
     return F.relu(x) if a == _lib.ACT_RELU else F.silu(x) if a == _lib.ACT_SILU else x
 
 

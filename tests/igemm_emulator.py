@@ -6,7 +6,8 @@ import ctypes as C
 
 import numpy as np
 
-from generativemodels_b200._lib import ACT_DTYPE, ACT_GELU, ACT_LEAKYRELU, ACT_RELU, ACT_SILU, DT_H16, IgemmParams
+from generativemodels_b200._lib import (ACT_DTYPE, ACT_GELU, ACT_LEAKYRELU, ACT_RELU, ACT_SIGMOID, ACT_SILU, ACT_TANH, DT_H16,
+                                         IgemmParams)
 
 
 def _bf16_view(ptr, count):
@@ -43,6 +44,10 @@ def _act(x, a):
         return x / (1 + np.exp(-x))
     if a == ACT_LEAKYRELU:
         return np.where(x > 0, x, np.float32(0.01) * x)
+    if a == ACT_TANH:
+        return np.tanh(x)
+    if a == ACT_SIGMOID:
+        return (1 / (1 + np.exp(-x))).astype(np.float32)
     if a == ACT_GELU:
         from math import erf
         return (0.5 * x * (1.0 + np.vectorize(erf)(x * 0.7071067811865476))).astype(np.float32)

@@ -444,3 +444,17 @@ def test_invalidate_packed_cpu():
     y1 = m(x, t)
     want = O.unet_forward(m.state_dict(), G.unet_oracle_cfg(kw), x, t)
     assert rel(y1, want) < 2e-2 and not torch.equal(y0, y1)
+
+
+@pytest.mark.parametrize("act", ["tanh", "sigmoid", "relu"])
+def test_vqvae_output_act_cpu(act):
+    """VQVAE(output_act=...) (vqvae.py:263-264): the activation rides in the last transposed convolution's epilogue."""
+    kw = dict(G.VQVAE_CASES["vqvae2d"], output_act=act)
+    torch.manual_seed(0)
+    m = nets().VQVAE(**kw).eval()
+    cfg = G.vqvae_oracle_cfg(kw)
+    torch.manual_seed(4)
+    z = torch.randn(2, kw["embedding_dim"], 8, 8)
+    assert rel(m.decode(z), O.vqvae_decode(m.state_dict(), cfg, z)) < 2e-2
+    with pytest.raises(NotImplementedError):
+        nets().VQVAE(**dict(kw, output_act="mish"))

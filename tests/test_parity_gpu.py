@@ -692,3 +692,17 @@ def test_cuda_graph_nested_inputs_outputs(cuda_device):
     a = gcn(x, ts, cond, conditioning_scale=0.5, context=ctx)[0][0]
     b = gcn(x + 1, ts, cond, conditioning_scale=0.5, context=ctx)[0][0]
     assert a.data_ptr() != b.data_ptr() and not torch.equal(a, b)
+
+
+@pytest.mark.parametrize("act", ["tanh", "sigmoid"])
+def test_vqvae_output_act(cuda_device, act):
+    """VQVAE(output_act=...) (vqvae.py:263-264) against the oracle: the activation is applied in the epilogue of the last
+    transposed convolution's phase launches."""
+    kw = dict(G.VQVAE_CASES["vqvae3d"], output_act=act)
+    torch.manual_seed(0)
+    m = nets().VQVAE(**kw).eval()
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    torch.manual_seed(4)
+    z = torch.randn(1, kw["embedding_dim"], 4, 4, 4)
+    want = O.vqvae_decode(sd, G.vqvae_oracle_cfg(kw), z)
+    check(m.cuda().decode(z.cuda()), want, FWD_TOL, f"vqvae decode with output_act={act}")
