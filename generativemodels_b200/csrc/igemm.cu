@@ -1199,9 +1199,9 @@ extern "C" int b200_igemm(const b200_igemm_params* p, void* stream_v) {
   }
   B200_CHECK_ARG(pl.ntiles * splits < (1ll << 31), "igemm: too many tiles");
   d.num_tiles = (int)pl.ntiles;
-  // CTA pairs for the 256-column calls that fill the machine (at least one tile per SM — pairs of M tiles over pairs
+  // CTA pairs for the 256- and 128-column calls that fill the machine (at least one tile per SM — pairs of M tiles over pairs
   // of SMs quantise like single tiles over single SMs), no split-K / score statistics / staged stores
-  const bool pair = igemm_pair_mode() && BN == 256 && splits == 1 && !p->stat_ptr && !d.out_staged &&
+  const bool pair = igemm_pair_mode() && (BN == 256 || BN == 128) && splits == 1 && !p->stat_ptr && !d.out_staged &&
                     pl.m_tiles >= 2 && pl.ntiles >= sm_count();
   if (pair) d.num_tiles = (int)(((pl.m_tiles + 1) / 2) * pl.tiles_n);
 
@@ -1250,7 +1250,7 @@ extern "C" int b200_igemm(const b200_igemm_params* p, void* stream_v) {
       case 16:  return launch_tc<16, 8>(dev, stream);
       case 32:  return launch_tc<32, 8>(dev, stream);
       case 64:  return launch_tc<64, 8>(dev, stream);
-      case 128: return launch_tc<128, 6>(dev, stream);
+      case 128: return pair ? launch_tc<128, 8, true>(dev, stream) : launch_tc<128, 6>(dev, stream);
       default:  return pair ? launch_tc<256, 6, true>(dev, stream) : launch_tc<256, 4>(dev, stream);
     }
   };

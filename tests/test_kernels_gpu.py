@@ -81,6 +81,14 @@ CONV_CASES = [
     (3, 1, 32, 64, (8, 8, 8), 4, 2, 1),
     (2, 1, 8, 8, (4, 4), 3, 1, 1),
     (3, 1, 8, 16, (4, 4, 4), 3, 1, 1),
+    # grids of at least one tile per SM: the CTA-pair (cta_group::2) kernels, 256- and 128-column tiles, even and odd
+    # tile counts (an odd count leaves the last pair's second CTA a dead tile), stride 2, two samples
+    (2, 1, 64, 256, (160, 128), 3, 1, 1),
+    (2, 1, 96, 256, (151, 129), 3, 1, 1),
+    (2, 2, 64, 128, (104, 128), 3, 1, 1),
+    (3, 1, 64, 512, (12, 40, 40), 3, 1, 1),
+    (2, 1, 64, 256, (300, 260), 3, 2, 1),
+    (2, 1, 64, 384, (100, 128), 1, 1, 0),
 ]
 
 
