@@ -804,22 +804,26 @@ __device__ __forceinline__ void umma2_h16_ts(uint32_t d_tmem, uint32_t a_tmem, u
       : "memory");
 }
 
-static constexpr int kPDCH = 8;                               // head_dim 512
 static constexpr int kPKeysCta = kBKV / 2;                    // keys of a block staged by each CTA
 static constexpr int kPKChunkBytes = kPKeysCta * 64 * 2;      // 4 KB: 32 keys x 64 channels
 static constexpr int kPKStageBytes = 4 * kPKChunkBytes;       // 16 KB: four channel chunks
 static constexpr int kPKStages = kKRingBytes / kPKStageBytes; // 4 stages = two key blocks in flight
-static constexpr int kPKSteps = kPDCH / 4;                    // ring stages per key block
 static constexpr int kPVRows = 128;                           // V^T rows (output channels) staged by each CTA
 static constexpr int kPVBytes = kPVRows * kBKV * 2;           // 16 KB
 static constexpr int kPVStages = 2;
 static constexpr int kPRStageBytes = kQChunkBytes + kPVBytes; // pass-2 stage: own P tile 16 KB + V^T half 16 KB
 static constexpr int kPRStages = 7;                           // 224 KB overlaying Q | K ring | V^T
-static_assert(kPRStages * kPRStageBytes <= kPDCH * kQChunkBytes + kKRingBytes + kPVStages * kPVBytes, "pass-2 overlay");
-static constexpr int kPairSmem = kPDCH * kQChunkBytes + kKRingBytes + kPVStages * kPVBytes + 1024 + 1024;
+static_assert(kPRStages * kPRStageBytes <= 8 * kQChunkBytes + kKRingBytes + kPVStages * kPVBytes, "pass-2 overlay");
+template <int DCH>
+constexpr int pair_smem() { return DCH * kQChunkBytes + kKRingBytes + kPVStages * kPVBytes + 1024 + 1024; }
 
+// DCH = head_dim / 64 (8: head_dim 512, two passes with the probability replay; 4: head_dim 256, one pass, no slab)
+template <int DCH, bool REPLAY>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 flash_pair_kernel(const __grid_constant__ FlashDev p) {
+  static_assert((DCH == 8 && REPLAY) || (DCH == 4 && !REPLAY), "pair kernel: head_dim 512 with replay or head_dim 256");
+  constexpr int kPDCH = DCH;
+  constexpr int kPKSteps = DCH / 4;                     // ring stages per key block
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -894,7 +898,8 @@ flash_pair_kernel(const __grid_constant__ FlashDev p) {
       const int h = bh % p.heads, b = bh / p.heads;
       const int qt = 2 * pt + (int)rank;
       const int ch0 = h * p.dh;
-      mbar_wait_warp(r_done, (icount & 1) ^ 1u);            // previous item's pass-2 stages drained (both CTAs)
+      // previous item's smem is free: all pass-2 MMAs (replay) / all pass-1 MMAs done — signalled in both CTAs
+      mbar_wait_warp(REPLAY ? r_done : q_empty, (icount & 1) ^ 1u);
       if (elect_one()) {
         if (leader) mbar_expect_tx(q_full, 2 * kPDCH * kQChunkBytes);
 #pragma unroll
@@ -934,6 +939,7 @@ flash_pair_kernel(const __grid_constant__ FlashDev p) {
           ++vcount;
         }
       }
+      if constexpr (REPLAY) {
       // ---- pass 2: own P tiles + own half of V^T[256..511] through 32 KB stages overlaying Q | K ring | V^T ----
       mbar_wait_warp(q_empty, icount & 1);                   // every pass-1 MMA of the pair has completed
       mbar_wait_cluster_warp(p1_done, icount & 1);           // all P tiles written and fenced
@@ -955,6 +961,7 @@ flash_pair_kernel(const __grid_constant__ FlashDev p) {
         }
         __syncwarp();
         if (++rst == kPRStages) { rst = 0; rph ^= 1u; }
+      }
       }
     }
   } else if (warp == 1) {
@@ -1022,6 +1029,7 @@ flash_pair_kernel(const __grid_constant__ FlashDev p) {
             ++vcount;
           }
         }
+        if constexpr (REPLAY) {
         // ---- pass 2 ----
         mbar_wait_cluster_warp(p1_done, icount & 1);           // rescale flags of all eight softmax warps are visible
         bool gated = false;
@@ -1052,6 +1060,7 @@ flash_pair_kernel(const __grid_constant__ FlashDev p) {
           if (++rst == kPRStages) { rst = 0; rph ^= 1u; }
           if (gated) ++pvcount;
         }
+        }
       }
     }
   } else {
@@ -1065,9 +1074,9 @@ flash_pair_kernel(const __grid_constant__ FlashDev p) {
     const uint32_t p1_done_a[2] = {mapa_u32(p1_done, 0), mapa_u32(p1_done, 1)};
     const uint32_t flag_a[2] = {mapa_u32(ev_flags_addr + 4u * (rank * 4 + q), 0), mapa_u32(ev_flags_addr + 4u * (rank * 4 + q), 1)};
     uint32_t scount = 0, pcount = 0, ocount = 0, icount = 0;
-    h16* slab_row = p.pslab + (long long)blockIdx.x * p.p_pitch + row * kBKV;
-    float* ev_fac = p.ev_fac + ((long long)blockIdx.x * 4 + q) * (long long)n_kv * 32;
-    int* ev_blk = p.ev_blk + ((long long)blockIdx.x * 4 + q) * (long long)n_kv;
+    h16* slab_row = REPLAY ? p.pslab + (long long)blockIdx.x * p.p_pitch + row * kBKV : nullptr;
+    float* ev_fac = REPLAY ? p.ev_fac + ((long long)blockIdx.x * 4 + q) * (long long)n_kv * 32 : nullptr;
+    int* ev_blk = REPLAY ? p.ev_blk + ((long long)blockIdx.x * 4 + q) * (long long)n_kv : nullptr;
     for (int item = pair_id; item < p.n_items; item += n_pairs, ++icount) {
       const int pt = item % pair_tiles, bh = item / pair_tiles;
       const int h = bh % p.heads, b = bh / p.heads;
@@ -1128,9 +1137,11 @@ flash_pair_kernel(const __grid_constant__ FlashDev p) {
           }
           tmem_st_wait();
           fence_before();
-          ev_fac[(long long)n_ev * 32 + lane] = factor;
-          if (lane == 0) ev_blk[n_ev] = j;
-          ++n_ev;
+          if constexpr (REPLAY) {
+            ev_fac[(long long)n_ev * 32 + lane] = factor;
+            if (lane == 0) ev_blk[n_ev] = j;
+            ++n_ev;
+          }
         }
         l_run *= factor;
         m_used = m_new;
@@ -1164,12 +1175,14 @@ flash_pair_kernel(const __grid_constant__ FlashDev p) {
         fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(l_p_full0 + 8u * pb);
-        {   // the slab copy of the same probabilities (pass 2) goes out AFTER the hand-off: nothing waits on it
+        if constexpr (REPLAY) {   // the slab copy of the same probabilities (pass 2) goes out AFTER the hand-off
           h16* dst = slab_row + (long long)j * (kBM * kBKV);
 #pragma unroll
           for (int g = 0; g < 4; ++g) { if (!FA_ABL(3) && !FA_ABL(4)) stg256(dst + g * 16, pw + g * 8); }
         }
       }
+      bool gated = false;
+      if constexpr (REPLAY) {
       // publish this warp's "logged a rescale" flag to both CTAs, make the slab visible to the TMA reads of pass 2,
       // then arrive on both CTAs' p1_done
       __threadfence();
@@ -1182,14 +1195,14 @@ flash_pair_kernel(const __grid_constant__ FlashDev p) {
         mbar_arrive_cluster_release(p1_done_a[1]);
       }
       mbar_wait_cluster(p1_done, icount & 1);
-      bool gated = false;
 #pragma unroll
       for (int e = 0; e < 8; ++e) gated |= ev_flags[e] != 0;
+      }
       const float inv = 1.0f / l_run;
       const int t = qt * kBM + row;
       const bool ok = t < p.T;
 #pragma unroll 1
-      for (int pass = 0; pass < 2; ++pass) {
+      for (int pass = 0; pass < (REPLAY ? 2 : 1); ++pass) {
         if (pass == 1 && gated) {
           int e_next = 0;
           int next_blk = (n_ev > 0) ? ev_blk[0] : 0x7fffffff;
@@ -1368,7 +1381,10 @@ extern "C" int b200_attention_flash(const b200_flash_params* a, void* stream_v) 
                    (long long)a->workspace_bytes, rp.total);
     B200_CHECK_ARG(((uintptr_t)a->workspace & 255) == 0, "attention_flash: workspace must be 256-byte aligned");
   }
-  const bool pair = replay && fa::pair_mode();
+  // CTA pairs: head_dim 512 with the replay workspace, and head_dim 256 (one pass, no workspace), unless the call is a
+  // small problem
+  const bool pair256 = a->dh == 256 && fa::pair_mode() && !fa::small_problem(a);
+  const bool pair = (replay && fa::pair_mode()) || pair256;
   const long long items = pair ? (long long)a->B * a->heads * ((d.q_tiles + 1) / 2)
                                : (long long)a->B * a->heads * d.q_tiles * (replay ? 1 : d.n_dv);
   B200_CHECK_ARG(items < (1ll << 31), "attention_flash: too many work items");
@@ -1398,7 +1414,9 @@ extern "C" int b200_attention_flash(const b200_flash_params* a, void* stream_v) 
 
   const int smem = d.d_chunks * fa::kQChunkBytes + fa::kKRingBytes + d.dv * fa::kBKV * 2 + 1024 + 512;
   const int smem_max = d.d_chunks * fa::kQChunkBytes + fa::kKRingBytes + 256 * fa::kBKV * 2 + 1024 + 512;
-  const int grid = replay ? rp.grid : (d.n_items < sm_count() ? d.n_items : sm_count());
+  const int grid = replay ? rp.grid
+                   : pair ? 2 * (d.n_items < sm_count() / 2 ? d.n_items : sm_count() / 2)
+                          : (d.n_items < sm_count() ? d.n_items : sm_count());
   if (replay) {
     B200_CHECK_ARG(grid == rp.grid && d.n_kv == rp.n_kv, "attention_flash: internal replay plan mismatch");
     uint8_t* ws = static_cast<uint8_t*>(a->workspace);
@@ -1424,16 +1442,30 @@ extern "C" int b200_attention_flash(const b200_flash_params* a, void* stream_v) 
   switch (d.d_chunks) {
     case 1: B200_FLASH_LAUNCH(1, false); break;
     case 2: B200_FLASH_LAUNCH(2, false); break;
-    case 4: B200_FLASH_LAUNCH(4, false); break;
+    case 4:
+      if (pair) {
+        static std::once_flag pair4_once;
+        static cudaError_t pair4_rc = cudaSuccess;
+        std::call_once(pair4_once, [] {
+          pair4_rc = cudaFuncSetAttribute(fa::flash_pair_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          fa::pair_smem<4>());
+        });
+        B200_CUDA(pair4_rc);
+        B200_CUDA(b200::launch_pdl(fa::flash_pair_kernel<4, false>, grid, fa::kThreads, fa::pair_smem<4>(), stream, d));
+      } else {
+        B200_FLASH_LAUNCH(4, false);
+      }
+      break;
     default:
       if (pair) {
         static std::once_flag pair_once;
         static cudaError_t pair_rc = cudaSuccess;
         std::call_once(pair_once, [] {
-          pair_rc = cudaFuncSetAttribute(fa::flash_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fa::kPairSmem);
+          pair_rc = cudaFuncSetAttribute(fa::flash_pair_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         fa::pair_smem<8>());
         });
         B200_CUDA(pair_rc);
-        B200_CUDA(b200::launch_pdl(fa::flash_pair_kernel, grid, fa::kThreads, fa::kPairSmem, stream, d));       // clusters of 2 (__cluster_dims__)
+        B200_CUDA(b200::launch_pdl(fa::flash_pair_kernel<8, true>, grid, fa::kThreads, fa::pair_smem<8>(), stream, d));   // clusters of 2 (__cluster_dims__)
       } else if (replay) {
         B200_FLASH_LAUNCH(8, true);
       } else {
