@@ -457,7 +457,9 @@ def test_attention_small(cuda_device, B, T, S, heads, dh):
 
 @pytest.mark.parametrize("unfused", [False, True], ids=["flash", "unfused"])
 @pytest.mark.parametrize("B,T,heads,dh", [(1, 256, 1, 256), (2, 200, 1, 512), (1, 1024, 2, 64), (1, 2300, 1, 128),
-                                          (1, 700, 1, 512), (1, 600, 2, 512)])
+                                          (1, 700, 1, 512), (1, 600, 2, 512),
+                                          # enough query tiles for the CTA-pair kernels (ragged last pair, odd tile count)
+                                          (1, 128 * 39 + 50, 1, 512), (2, 128 * 21 + 7, 1, 256)])
 def test_attention_tensorcore(cuda_device, B, T, heads, dh, unfused, monkeypatch):
     """Flash-style tcgen05 attention (scores in TMEM) and the GEMM + softmax + GEMM path, V^T produced by the
     operand-swapped projection, against fp32 softmax(QK^T)V on the same bf16-rounded q, k, v."""
