@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 from dataclasses import dataclass
 from typing import Sequence
 
@@ -376,7 +377,9 @@ def _gn_partial_for(out: CL, rows: int, n_seg: int, launches: int = 1) -> torch.
 # --------------------------------------------------------------------------------------------------
 # implicit GEMM launcher
 # --------------------------------------------------------------------------------------------------
-_PARAM_TEMPLATES: dict = {}      # id(packed weight tensor) -> (weight, segs, IgemmParams with weight + tap table filled)
+# id(packed weight tensor) -> (weakref to it, segs, IgemmParams with weight + tap table filled).  Weak: the cache must not
+# keep the packed weights of a deleted model alive (round-1 review); a dead or recycled id simply misses.
+_PARAM_TEMPLATES: dict = {}
 
 
 def _fill_segs(p: IgemmParams, segs) -> None:
@@ -415,7 +418,7 @@ def _conv_params(srcs: Sequence[CL], w: torch.Tensor, segs, stride, out_t: torch
     # the tap table (up to 128 segments), weight pointer and stride are fixed for a packed weight: filling them
     # field by field through ctypes costs ~30 us per 27-tap call, a struct copy of a per-weight template 0.5 us
     tmpl = _PARAM_TEMPLATES.get(id(w))
-    if tmpl is not None and tmpl[0] is w and tmpl[1] is segs:
+    if tmpl is not None and tmpl[0]() is w and tmpl[1] is segs:
         p = IgemmParams.from_buffer_copy(tmpl[2])
     else:
         p = IgemmParams()
@@ -425,7 +428,9 @@ def _conv_params(srcs: Sequence[CL], w: torch.Tensor, segs, stride, out_t: torch
         _fill_segs(p, segs)
         if len(_PARAM_TEMPLATES) > 4096:
             _PARAM_TEMPLATES.clear()
-        _PARAM_TEMPLATES[id(w)] = (w, segs, IgemmParams.from_buffer_copy(p))
+        key = id(w)
+        _PARAM_TEMPLATES[key] = (weakref.ref(w, lambda _r, _k=key: _PARAM_TEMPLATES.pop(_k, None)), segs,
+                                 IgemmParams.from_buffer_copy(p))
     a0 = srcs[0]
     for i, a in enumerate(srcs):
         if (a.N, a.D, a.H, a.W) != (a0.N, a0.D, a0.H, a0.W):
