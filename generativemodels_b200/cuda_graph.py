@@ -13,8 +13,32 @@ is capture-safe by construction: allocations come from the graph's private pool,
 """
 from __future__ import annotations
 
+import contextlib
+import gc
+
 import torch
 import torch.nn as nn
+
+
+@contextlib.contextmanager
+def capture(graph: "torch.cuda.CUDAGraph"):
+    """``torch.cuda.graph(graph)`` with the cyclic garbage collector held off for the duration of the capture.
+
+    A collection that happens to run in the middle of a capture can finalise an OLDER CUDAGraph (e.g. the decode-step
+    graph of a transformer cache that has just gone out of scope); destroying it releases its private memory pool
+    (cudaFree), which is not allowed while a stream is capturing and invalidates the capture in progress
+    ("operation failed due to a previous error during capture" — seen intermittently in the round-2 GPU suite).
+    ``torch.cuda.graph`` collects on entry; this additionally keeps the collector from starting on its own until the
+    capture has ended.  Reference-count frees of tensors are unaffected (they only return blocks to the allocator)."""
+    gc.collect()
+    was_enabled = gc.isenabled()
+    gc.disable()
+    try:
+        with torch.cuda.graph(graph):
+            yield
+    finally:
+        if was_enabled:
+            gc.enable()
 
 
 class GraphedModule(nn.Module):
@@ -94,7 +118,7 @@ class GraphedModule(nn.Module):
                     self.module(*static_args, **static_kwargs)
             torch.cuda.current_stream().wait_stream(side)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with capture(graph):
                 out = self.module(*static_args, **static_kwargs)
             entry = self._entries[key] = (graph, static_args, static_kwargs, out)
         graph, static_args, static_kwargs, out = entry

@@ -13,7 +13,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from ... import ops
+from ... import cuda_graph, ops
 from ...ops import CL
 from .._holders import f32, packed_linear, on_input_device, require_cuda
 from ..blocks.transformerblock import TransformerBlock
@@ -177,7 +177,7 @@ class DecoderOnlyTransformer(nn.Module):
             cache.static_tokens = x.long().contiguous().clone()
             torch.cuda.synchronize()
             cache.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(cache.graph):
+            with cuda_graph.capture(cache.graph):
                 cache.static_logits = self._step_dyn(cache.static_tokens, cache)
         cache.static_tokens.copy_(x, non_blocking=True)
         cache.graph.replay()
