@@ -57,6 +57,11 @@ struct IgemmDev {
   int tiles_w, tiles_h, tiles_d, tiles_n, num_tiles;
   int k_splits;             // >= 1: the reduction of every tile is cut into this many chunk ranges (fastest tile index)
   long long split_stride;   // output elements between the partial results of consecutive ranges
+  // one-launch split-K: fp32 partials [k_splits][split_rows][ws_cols] + per-output-tile tickets (see the epilogue)
+  float* split_ws;
+  int* split_counters;
+  long long split_rows;
+  int ws_cols;
   // epilogue
   void* out_ptr;
   int out_dtype, cout, out_cols, out_vec, out_staged, out_v256;
@@ -697,6 +702,66 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
       const long long res_off = nb * p.res_sN + od * p.res_sD + oh * p.res_sH + ow * p.res_sW;
       const int n0 = nt * BN;
 
+      if constexpr (!PAIR) {
+        if (p.split_counters) {
+          // ---- one-launch split-K: this range's raw accumulators go to the workspace; the CTA that draws the last
+          //      ticket of the output tile sums the ranges in order and applies the call's epilogue ----
+          const int buf = it & 1;
+          mbar_wait(tfull_bar(buf), (it >> 1) & 1);
+          tcgen05_fence_after();
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
+          const long long lin_row = (((long long)nb * p.OD + od) * p.OH + oh) * p.OW + ow;
+          float* wrow = p.split_ws + ((long long)ks * p.split_rows + lin_row) * p.ws_cols;
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN; c0 += CH) {
+            if (n0 + c0 >= p.ws_cols) break;             // warp-uniform
+            uint32_t raw[CH];
+            if constexpr (CH == 32) tmem_ld32(taddr + c0, raw);
+            else tmem_ld16(taddr + c0, raw);
+            tmem_ld_wait();
+            if (row_ok) {
+#pragma unroll
+              for (int g = 0; g < CH / 4; ++g)
+                if (n0 + c0 + g * 4 < p.ws_cols)
+                  *reinterpret_cast<float4*>(wrow + n0 + c0 + g * 4) =
+                      make_float4(__uint_as_float(raw[g * 4]), __uint_as_float(raw[g * 4 + 1]),
+                                  __uint_as_float(raw[g * 4 + 2]), __uint_as_float(raw[g * 4 + 3]));
+            }
+          }
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(buf));           // the accumulator buffer may be refilled
+          volatile int* flag = reinterpret_cast<volatile int*>(stage_tiles);
+          const int out_tile = tile / p.k_splits;
+          __threadfence();                                        // this thread's partial rows are visible device-wide
+          asm volatile("bar.sync 1, 128;" ::: "memory");          // ... and so are the other 127 epilogue threads'
+          if (warp == 2 && lane == 0) *flag = atomicAdd(p.split_counters + out_tile, 1);
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          const bool last = (*flag == p.k_splits - 1);
+          asm volatile("bar.sync 1, 128;" ::: "memory");          // everyone has read the flag before it is reused
+          if (last) {
+            __threadfence();
+            if (row_ok) {
+              const float* src0 = p.split_ws + lin_row * p.ws_cols;
+              for (int col0 = n0; col0 < n0 + BN && col0 < p.out_cols; col0 += 8) {
+                float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                const float* src = src0 + col0;
+                for (int s = 0; s < p.k_splits; ++s, src += p.split_rows * p.ws_cols) {
+                  const float4 a = __ldcg(reinterpret_cast<const float4*>(src));
+                  const float4 b = __ldcg(reinterpret_cast<const float4*>(src + 4));
+                  v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+                  v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+                }
+                epilogue_math<8>(p, v, nb, ow, res_off, col0);
+                store_direct<8>(p, v, out_off, col0);
+              }
+            }
+            if (warp == 2 && lane == 0) p.split_counters[out_tile] = 0;      // leave the tickets zero for the next call
+          }
+          continue;
+        }
+      }
+
       if (fast_ok && add_key != nb * p.tiles_n + nt) {
         if (gn_on) { gn_flush(); gn_nb = nb; gn_n0 = n0; }
         // bias + per-sample row vector of this (sample, column tile): shared by all rows, refreshed only on change
@@ -1256,6 +1321,20 @@ extern "C" int b200_igemm(const b200_igemm_params* p, void* stream_v) {
   };
   if (splits == 1) return launch(d);
 
+  if (p->split_counters) {
+    // ---- one-launch split-K: partials + per-tile tickets; the last CTA of a tile reduces and applies the epilogue ----
+    B200_CHECK_ARG(pl.ntiles <= B200_IGEMM_SPLIT_COUNTERS, "igemm: %lld output tiles exceed the %d split-K tickets",
+                   pl.ntiles, B200_IGEMM_SPLIT_COUNTERS);
+    IgemmDev df = d;
+    df.k_splits = splits;
+    df.num_tiles = (int)(pl.ntiles * splits);
+    df.split_ws = static_cast<float*>(p->split_ws);
+    df.split_counters = p->split_counters;
+    df.split_rows = pl.rows;
+    df.ws_cols = pl.ws_cols;
+    df.split_stride = 0;             // out_off addresses the REAL output in this mode
+    return launch(df);
+  }
   // ---- split-K: S partial GEMMs into the fp32 workspace, then the reduction applies this call's epilogue ----
   IgemmDev ds = d;
   ds.k_splits = splits;

@@ -390,6 +390,15 @@ def _fill_segs(p: IgemmParams, segs) -> None:
 
 
 _SPLIT_K = os.environ.get("B200_SPLIT_K", "1") != "0"    # dev switch (tests compare split and one-pass reductions)
+_SPLIT_FUSED = os.environ.get("B200_SPLIT_FUSED", "1") != "0"     # one launch (per-tile tickets) instead of GEMM + reduce
+_SPLIT_COUNTERS: dict = {}       # device index -> int32 [IGEMM_SPLIT_COUNTERS] zeros (self-resetting tickets)
+
+
+def _split_counters(device: torch.device) -> torch.Tensor:
+    t = _SPLIT_COUNTERS.get(device.index)
+    if t is None:
+        t = _SPLIT_COUNTERS[device.index] = torch.zeros(_lib.IGEMM_SPLIT_COUNTERS, dtype=torch.int32, device=device)
+    return t
 _SPLIT_LAUNCHES = 0      # calls that went through the split-K pair of kernels (tests / probes read it)
 
 
@@ -403,13 +412,15 @@ def igemm_raw(p: IgemmParams) -> None:
         if need:
             global _SPLIT_LAUNCHES
             _SPLIT_LAUNCHES += 1
-            ws = torch.empty(need, dtype=torch.uint8, device=torch.device("cuda", torch.cuda.current_device()))
+            dev = torch.device("cuda", torch.cuda.current_device())
+            ws = torch.empty(need, dtype=torch.uint8, device=dev)
             p.split_ws, p.split_ws_bytes = ws.data_ptr(), need
+            p.split_counters = _split_counters(dev).data_ptr() if _SPLIT_FUSED else None
     try:
         check(lib.b200_igemm(C.byref(p), _stream()), "b200_igemm")
     finally:
-        if ws is not None:
-            p.split_ws, p.split_ws_bytes = None, 0       # the struct may be a cached template: never keep the pointer
+        if ws is not None:       # the struct may be a cached template: never keep the pointers
+            p.split_ws, p.split_ws_bytes, p.split_counters = None, 0, None
 
 
 def _conv_params(srcs: Sequence[CL], w: torch.Tensor, segs, stride, out_t: torch.Tensor, out_dims, cout: int,

@@ -132,7 +132,13 @@ typedef struct {
    * unsplit kernel).  NULL / 0 = never split. */
   void*   split_ws;
   int64_t split_ws_bytes;
+  /* Optional: B200_IGEMM_SPLIT_COUNTERS int32 counters, zero before the FIRST call and left zero by every call, not
+   * shared by calls running concurrently on different streams.  With it the split happens in ONE launch: the CTA
+   * that finishes an output tile's last range (a per-tile ticket) sums the S partials in range order and applies the
+   * epilogue itself — same arithmetic and summation order as the two-kernel form.  NULL = two kernels. */
+  int32_t* split_counters;
 } b200_igemm_params;
+#define B200_IGEMM_SPLIT_COUNTERS 256
 
 int b200_igemm(const b200_igemm_params* p, void* stream);
 /* Bytes of split_ws with which b200_igemm would split the reduction of this call; 0 when it would not (enough tiles
