@@ -56,14 +56,19 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_entry() { pdl_launch_dependents(); pdl_wait(); }
 
-inline bool pdl_enabled() {
+// B200_PDL: 0 (default) = plain stream order; 1 = attribute on, every kernel triggers its dependents at entry (the whole
+// remainder of a captured graph piles onto the idle SMs and spins); 2 = attribute on, the tensor-core GEMM kernel
+// triggers only after its producer warp has issued the last operand load (the dependent's launch latency and prologue
+// overlap this kernel's last MMAs and epilogue, and the chain of early launches stops at the next GEMM).
+inline int pdl_mode() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("B200_PDL");
-    v = (e && e[0] == '1') ? 1 : 0;
+    v = (e && e[0] >= '1' && e[0] <= '2') ? e[0] - '0' : 0;
   }
-  return v != 0;
+  return v;
 }
+inline bool pdl_enabled() { return pdl_mode() != 0; }
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_cluster(void (*kernel)(KArgs...), int cluster_x, dim3 grid, dim3 block, size_t smem,

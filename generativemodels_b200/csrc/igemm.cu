@@ -55,6 +55,7 @@ struct IgemmDev {
   int N, OD, OH, OW;
   int BW, BH, BD, bw_log2, bh_log2;
   int tiles_w, tiles_h, tiles_d, tiles_n, num_tiles;
+  int pdl_late;             // programmatic dependent launch: trigger after the last operand load instead of at entry
   int k_splits;             // >= 1: the reduction of every tile is cut into this many chunk ranges (fastest tile index)
   long long split_stride;   // output elements between the partial results of consecutive ranges
   // one-launch split-K: fp32 partials [k_splits][split_rows][ws_cols] + per-output-tile tickets (see the epilogue)
@@ -511,7 +512,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
   constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;   // power of two for BN in {16..256}
   constexpr int CH = (BN >= 32) ? 32 : 16;
 
-  pdl_launch_dependents();          // the next kernel's prologue may overlap this kernel (it blocks in its own pdl_wait)
+  if (!p.pdl_late) pdl_launch_dependents();   // the next kernel's prologue may overlap this kernel (it blocks in its own pdl_wait)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + STAGES * kStageBytes;
@@ -626,6 +627,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
           }
         }
       }
+      if (p.pdl_late) pdl_launch_dependents();     // every operand load of this CTA is issued
     }
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
@@ -731,32 +733,89 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(buf));           // the accumulator buffer may be refilled
-          volatile int* flag = reinterpret_cast<volatile int*>(stage_tiles);
+          // ---- cooperative reduction: every CTA of the output tile draws a ticket once its partial rows are visible,
+          //      waits until all k_splits tickets are drawn (the k_splits CTAs of a tile are distinct CTAs of one wave:
+          //      the grid never exceeds one CTA per SM, and a CTA only ever waits for CTAs working on lower or equal
+          //      tile indices, so the wait cannot cycle), then sums ITS share of the tile's rows in range order —
+          //      threads run along the columns, so the fp32 partials are read as contiguous 32-byte pieces — and
+          //      applies the call's epilogue.  The CTA that draws ticket 2 * k_splits - 1 leaves the counter at zero.
           const int out_tile = tile / p.k_splits;
+          int* counter = p.split_counters + out_tile;
           __threadfence();                                        // this thread's partial rows are visible device-wide
           asm volatile("bar.sync 1, 128;" ::: "memory");          // ... and so are the other 127 epilogue threads'
-          if (warp == 2 && lane == 0) *flag = atomicAdd(p.split_counters + out_tile, 1);
+          if (warp == 2 && lane == 0) {
+            atomicAdd(counter, 1);
+            int seen;
+            do {
+              asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+            } while (seen < p.k_splits);
+          }
           asm volatile("bar.sync 1, 128;" ::: "memory");
-          const bool last = (*flag == p.k_splits - 1);
-          asm volatile("bar.sync 1, 128;" ::: "memory");          // everyone has read the flag before it is reused
-          if (last) {
-            __threadfence();
-            if (row_ok) {
-              const float* src0 = p.split_ws + lin_row * p.ws_cols;
-              for (int col0 = n0; col0 < n0 + BN && col0 < p.out_cols; col0 += 8) {
-                float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                const float* src = src0 + col0;
-                for (int s = 0; s < p.k_splits; ++s, src += p.split_rows * p.ws_cols) {
-                  const float4 a = __ldcg(reinterpret_cast<const float4*>(src));
-                  const float4 b = __ldcg(reinterpret_cast<const float4*>(src + 4));
-                  v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
-                  v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+          __threadfence();
+          {
+            const int et = (warp - 2) * 32 + lane;                // 0..127 (warps 2..5)
+            const int r_begin = split_begin(kBM, p.k_splits, ks), r_end = split_begin(kBM, p.k_splits, ks + 1);
+            int ncols = p.out_cols - n0;
+            if (ncols > BN) ncols = BN;
+            const int ncg = (ncols + 7) >> 3;
+            const int items = (r_end - r_begin) * ncg;
+            for (int item = et; item < items; item += 128) {
+              const int rr = r_begin + item / ncg;
+              const int col0 = n0 + (item % ncg) * 8;
+              const int ow2 = wt * p.BW + (rr & (p.BW - 1));
+              const int oh2 = ht * p.BH + ((rr >> p.bw_log2) & (p.BH - 1));
+              const int od2 = dt * p.BD + (rr >> (p.bw_log2 + p.bh_log2));
+              if (ow2 >= p.OW || oh2 >= p.OH || od2 >= p.OD) continue;
+              const long long lin2 = (((long long)nb * p.OD + od2) * p.OH + oh2) * p.OW + ow2;
+              const float* src = p.split_ws + lin2 * p.ws_cols + col0;
+              float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+              const long long sstride = p.split_rows * p.ws_cols;
+              int s = 0;
+              // eight ranges' loads in flight per thread (one SM reads the whole share: a serial load -> add chain of
+              // up to 32 L2 round trips per item was the 4-20 % this form first lost to the separate reduction kernel);
+              // the additions stay in range order
+              for (; s + 8 <= p.k_splits; s += 8, src += 8 * sstride) {
+                float4 a[8], b[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  a[j] = __ldcg(reinterpret_cast<const float4*>(src + j * sstride));
+                  b[j] = __ldcg(reinterpret_cast<const float4*>(src + j * sstride + 4));
                 }
-                epilogue_math<8>(p, v, nb, ow, res_off, col0);
-                store_direct<8>(p, v, out_off, col0);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  v[0] += a[j].x; v[1] += a[j].y; v[2] += a[j].z; v[3] += a[j].w;
+                  v[4] += b[j].x; v[5] += b[j].y; v[6] += b[j].z; v[7] += b[j].w;
+                }
               }
+              if (s + 4 <= p.k_splits) {
+                float4 a[4], b[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  a[j] = __ldcg(reinterpret_cast<const float4*>(src + j * sstride));
+                  b[j] = __ldcg(reinterpret_cast<const float4*>(src + j * sstride + 4));
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  v[0] += a[j].x; v[1] += a[j].y; v[2] += a[j].z; v[3] += a[j].w;
+                  v[4] += b[j].x; v[5] += b[j].y; v[6] += b[j].z; v[7] += b[j].w;
+                }
+                s += 4; src += 4 * sstride;
+              }
+              for (; s < p.k_splits; ++s, src += sstride) {
+                const float4 a = __ldcg(reinterpret_cast<const float4*>(src));
+                const float4 b = __ldcg(reinterpret_cast<const float4*>(src + 4));
+                v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+                v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+              }
+              const long long out2 = nb * p.out_sN + od2 * p.out_sD + oh2 * p.out_sH + ow2 * p.out_sW;
+              const long long res2 = nb * p.res_sN + od2 * p.res_sD + oh2 * p.res_sH + ow2 * p.res_sW;
+              epilogue_math<8>(p, v, nb, ow2, res2, col0);
+              store_direct<8>(p, v, out2, col0);
             }
-            if (warp == 2 && lane == 0) p.split_counters[out_tile] = 0;      // leave the tickets zero for the next call
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");          // every thread is done reading the partials
+          if (warp == 2 && lane == 0) {
+            if (atomicAdd(counter, 1) == 2 * p.k_splits - 1) *counter = 0;     // leave the tickets zero for the next call
           }
           continue;
         }
@@ -1255,6 +1314,7 @@ extern "C" int b200_igemm(const b200_igemm_params* p, void* stream_v) {
   const int BN = pl.BN;
   d.tiles_n = pl.tiles_n;
   d.k_splits = 1;
+  d.pdl_late = (b200::pdl_mode() == 2) ? 1 : 0;
   d.split_stride = 0;
   const int splits = (p->split_ws && pl.splits > 1) ? pl.splits : 1;
   if (splits > 1) {

@@ -390,7 +390,10 @@ def _fill_segs(p: IgemmParams, segs) -> None:
 
 
 _SPLIT_K = os.environ.get("B200_SPLIT_K", "1") != "0"    # dev switch (tests compare split and one-pass reductions)
-_SPLIT_FUSED = os.environ.get("B200_SPLIT_FUSED", "1") != "0"     # one launch (per-tile tickets) instead of GEMM + reduce
+# one launch (per-tile tickets, the CTAs of a tile reduce it cooperatively) instead of GEMM + reduce kernel.  Off by default:
+# the first form (the LAST CTA of a tile reduced all of it, one row per thread) measured 4x slower end to end (C2 UNet
+# step 1.79 -> 7.88 ms, brain-LDM 7.12 -> 11.29 ms); B200_SPLIT_FUSED=1 selects the cooperative form for A/B runs.
+_SPLIT_FUSED = os.environ.get("B200_SPLIT_FUSED", "0") != "0"
 _SPLIT_COUNTERS: dict = {}       # device index -> int32 [IGEMM_SPLIT_COUNTERS] zeros (self-resetting tickets)
 
 

@@ -133,9 +133,10 @@ typedef struct {
   void*   split_ws;
   int64_t split_ws_bytes;
   /* Optional: B200_IGEMM_SPLIT_COUNTERS int32 counters, zero before the FIRST call and left zero by every call, not
-   * shared by calls running concurrently on different streams.  With it the split happens in ONE launch: the CTA
-   * that finishes an output tile's last range (a per-tile ticket) sums the S partials in range order and applies the
-   * epilogue itself — same arithmetic and summation order as the two-kernel form.  NULL = two kernels. */
+   * shared by calls running concurrently on different streams.  With it the split happens in ONE launch: the S CTAs
+   * of an output tile (all resident: the grid never exceeds one CTA per SM) draw a per-tile ticket after storing
+   * their partials, wait for the S-th ticket, and each sums 1/S of the tile's rows in range order and applies the
+   * epilogue — same arithmetic and summation order as the two-kernel form.  NULL = two kernels. */
   int32_t* split_counters;
 } b200_igemm_params;
 #define B200_IGEMM_SPLIT_COUNTERS 256

@@ -268,14 +268,14 @@ def test_split_k_conv_matches_one_pass_and_check_kernel(cuda_device, monkeypatch
     # the one-launch form (per-tile tickets: the CTA that finishes a tile's last range reduces and applies the
     # epilogue) against the two-kernel form: same summation order, same epilogue code -> bit-identical; repeated calls
     # check that the tickets are left at zero
-    assert ops._SPLIT_FUSED
+    monkeypatch.setattr(ops, "_SPLIT_FUSED", True)
     fused = [ops.conv(xc, pc, **kw).t.clone() for _ in range(3)]
+    o1f = ops.conv(xc, pc2, out_f32=True)
     monkeypatch.setattr(ops, "_SPLIT_FUSED", False)
     two_kernel = ops.conv(xc, pc, **kw).t
     o3 = ops.conv(xc, pc2, out_f32=True)
-    monkeypatch.setattr(ops, "_SPLIT_FUSED", True)
     assert all(torch.equal(f, two_kernel) for f in fused), "one-launch split-K differs from GEMM + reduce"
-    assert torch.equal(o1, o3)
+    assert torch.equal(o1f, o3)
     assert int(ops._split_counters(xc.t.device).abs().sum()) == 0
 
 

@@ -36,10 +36,15 @@ brain = redraw(DiffusionModelUNet(spatial_dims=3, in_channels=7, out_channels=3,
                                   cross_attention_dim=4)).cuda().eval()
 c2 = redraw(DiffusionModelUNet(2, 3, 3, num_res_blocks=2, num_channels=(128, 256, 512),
                                attention_levels=(False, True, True), num_head_channels=(0, 256, 512))).cuda().eval()
+c5 = redraw(DiffusionModelUNet(2, 3, 3, num_res_blocks=1, num_channels=(128, 256, 256),
+                               attention_levels=(False, True, True), num_head_channels=256, with_conditioning=True,
+                               cross_attention_dim=1)).cuda().eval()
 sched = DDIMScheduler(1000, "linear_beta", beta_start=0.0015, beta_end=0.0195)
 sched.set_timesteps(50)
 cases = {"brain-LDM UNet 7x20x28x20": (brain, torch.randn(1, 7, 20, 28, 20).cuda(), torch.randn(1, 1, 4).cuda(), 3),
-         "C2 UNet 3x64x64": (c2, torch.randn(1, 3, 64, 64).cuda(), None, 3)}
+         "C2 UNet 3x64x64": (c2, torch.randn(1, 3, 64, 64).cuda(), None, 3),
+         "C5 UNet 2x3x256x256 (CFG batch, no ControlNet residuals)": (c5, torch.randn(2, 3, 256, 256).cuda(),
+                                                                     torch.tensor([[[-1.0]], [[1.0]]]).cuda(), 3)}
 
 
 def loop(net, x, ctx, keep):
