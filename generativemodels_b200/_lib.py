@@ -59,6 +59,7 @@ class IgemmParams(C.Structure):
         ("act2", C.c_int32), ("stat_ptr", C.c_void_p), ("impl", C.c_int32),
         ("gn_partial", C.c_void_p), ("gn_slots", C.c_int32), ("gn_slot0", C.c_int32),
         ("split_ws", C.c_void_p), ("split_ws_bytes", C.c_int64), ("split_counters", C.c_void_p),
+        ("a_broadcast", C.c_int32),
     ]
 
 

@@ -45,6 +45,7 @@ struct IgemmDev {
   const h16* a_ptr[2];
   int a_C[2], a_pitch[2];
   int in_N, in_D, in_H, in_W;
+  int a_bcast;              // 1: every sample reads A at batch index 0
   const h16* w_ptr;
   int w_rows, w_K, w_pitch;
   long long w_bstride;
@@ -467,6 +468,41 @@ __device__ __forceinline__ void epilogue_row(const IgemmDev& p, float* v, int nb
   store_direct<CH>(p, v, out_off, col0);
 }
 
+// The leanest epilogue: out = h16(acc + bias/row-vector [+ residual]) for a full CH-column chunk of a 32-byte-aligned h16
+// output — every nn.Linear of the transformer blocks, 1x1 projections.  Same arithmetic and order as epilogue_fast
+// with act1 = act2 = none and scale = 1 (bit-identical), but none of its run-time switches: with one epilogue warp per
+// scheduler the ~20 uniform branches per chunk of the general body (activation chains, scale, output type, statistics)
+// and its instruction footprint were what a K = 256 GEMM spent its time on (ncu source view: branch_resolving /
+// no_inst stalls spread over the whole body; 12.7k cycles per 128 x 256 tile against ~1k of issue work).
+template <int CH, bool HAS_RES>
+__device__ __forceinline__ void epilogue_lean(const IgemmDev& p, const uint32_t* raw, const float* addv,
+                                              const uint4* rv, long long out_off, int col0) {
+  float v[CH];
+#pragma unroll
+  for (int j = 0; j < CH; j += 4) {
+    const float4 a = *reinterpret_cast<const float4*>(addv + j);
+    v[j] = __uint_as_float(raw[j]) + a.x;
+    v[j + 1] = __uint_as_float(raw[j + 1]) + a.y;
+    v[j + 2] = __uint_as_float(raw[j + 2]) + a.z;
+    v[j + 3] = __uint_as_float(raw[j + 3]) + a.w;
+  }
+  if constexpr (HAS_RES) {
+#pragma unroll
+    for (int g = 0; g < CH / 8; ++g) {
+      float f[8];
+      unpack8(rv[g], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[g * 8 + j] += f[j];
+    }
+  }
+  h16* o = reinterpret_cast<h16*>(p.out_ptr) + out_off + col0;
+  uint4 pk[CH / 8];
+#pragma unroll
+  for (int g = 0; g < CH / 8; ++g) pk[g] = pack8(v + g * 8);
+#pragma unroll
+  for (int g = 0; g < CH / 16; ++g) stg256(o + g * 16, pk[2 * g], pk[2 * g + 1]);
+}
+
 // Row-coalesced store for wide row-major outputs (GEMM-shaped calls whose rows are far apart in memory, e.g. the
 // 89 600-column attention score matrix): the warp's 32 x CH tile goes through a padded shared-memory tile so that
 // every store instruction writes one contiguous CH-element row segment instead of 32 scattered 16-byte pieces.
@@ -602,6 +638,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
         const int iw0 = wt * p.BW * p.sw, ih0 = ht * p.BH * p.sh, id0 = dt * p.BD * p.sd;
         const int n0 = nt * BN;
         const int wb = p.w_batched ? nb : 0;
+        const int a_nb = p.a_bcast ? 0 : nb;
         const int k_begin = split_begin(num_k, p.k_splits, ks), k_end = split_begin(num_k, p.k_splits, ks + 1);
         int kglob = 0;
         for (int s = 0; s < p.n_seg; ++s) {
@@ -616,11 +653,11 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
             if constexpr (PAIR) {
               // both CTAs load their own A box and their half of the weight tile; all bytes land on the LEADER's barrier
               if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * kStageBytes);
-              tma_load_5d_pair(tm, full_bar(stage), a_dst, (sg.c0 + c) * kBK, cw, ch, cd, nb);
+              tma_load_5d_pair(tm, full_bar(stage), a_dst, (sg.c0 + c) * kBK, cw, ch, cd, a_nb);
               tma_load_3d_pair(&p.tmB, full_bar(stage), a_dst + kABytes, kglob * kBK, n0 + (int)rank * (BN / 2), wb);
             } else {
               mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
-              tma_load_5d(tm, full_bar(stage), a_dst, (sg.c0 + c) * kBK, cw, ch, cd, nb);
+              tma_load_5d(tm, full_bar(stage), a_dst, (sg.c0 + c) * kBK, cw, ch, cd, a_nb);
               tma_load_3d(&p.tmB, full_bar(stage), a_dst + kABytes, kglob * kBK, n0, wb);
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -673,6 +710,8 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
     int add_key = -1;
     const bool fast_ok = p.out_vec && !p.out_staged && !p.stat_ptr &&
                          (!p.res_ptr || (p.res_vec && p.res_dtype == B200_DT_H16));
+    const bool lean_ok = fast_ok && p.act1 == B200_ACT_NONE && p.act2 == B200_ACT_NONE && p.scale == 1.0f &&
+                         !p.row_bias && !p.gn_partial && p.out_dtype == B200_DT_H16 && p.out_v256;
     // GroupNorm partial sums for the consumer of this tensor: per warp [BN/8 groups][sum, sumsq] in shared memory
     // (aliases the staged-store tiles, which this mode excludes), flushed to this warp's private global slot
     // whenever the (sample, column tile) changes and at the end — deterministic, no atomics.
@@ -826,17 +865,32 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
         // bias + per-sample row vector of this (sample, column tile): shared by all rows, refreshed only on change
         add_key = nb * p.tiles_n + nt;
         __syncwarp();
-        for (int c = lane; c < BN; c += 32) {
-          const int col = n0 + c;
-          float a = 0.f;
-          if (col < p.cout) {
-            if (p.bias) a += __ldg(p.bias + col);
-            if (p.rowvec) a += __ldg(p.rowvec + (long long)nb * p.rowvec_bstride + col);
+        {
+          // all loads first: with the column tile as the fastest tile index a GEMM-shaped call refreshes this vector
+          // for EVERY tile, and a load -> add chain per element cost eight L2 round trips per tile (a third of the
+          // epilogue of the K = 256 linears of the transformer blocks, ncu source view of round 2)
+          constexpr int PER = (BN + 31) / 32;
+          float bv[PER], rw[PER];
+#pragma unroll
+          for (int i = 0; i < PER; ++i) {
+            const int col = n0 + lane + 32 * i;
+            const bool ok = (lane + 32 * i < BN) && col < p.cout;
+            bv[i] = (ok && p.bias) ? __ldg(p.bias + col) : 0.f;
+            rw[i] = (ok && p.rowvec) ? __ldg(p.rowvec + (long long)nb * p.rowvec_bstride + col) : 0.f;
           }
-          addv[c] = a;
+#pragma unroll
+          for (int i = 0; i < PER; ++i)
+            if (lane + 32 * i < BN) addv[lane + 32 * i] = bv[i] + rw[i];
         }
         __syncwarp();
       }
+
+      // residual of the first full chunk: in flight while this warp waits for the accumulator; every later chunk's
+      // residual is requested one chunk ahead (a load -> use chain per chunk exposed one HBM / L2 latency per 32
+      // columns: the epilogue warps are one per scheduler, nothing else hides it)
+      const bool res_fast = fast_ok && p.res_ptr && row_ok;
+      uint4 rv_next[CH / 8];
+      if (res_fast && n0 + CH <= p.cout) load_res_fast<CH>(p, rv_next, res_off, n0);
 
       const int buf = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -845,12 +899,37 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
       float run_max = -INFINITY, run_sum = 0.f;
       float* my_tile = stage_tiles + (warp - 2) * (32 * (CH + 1));
+      int c0 = 0;
+      if (lean_ok) {
+        // (A shared-memory transposed variant — two chunks staged per warp, eight lanes writing each row's whole
+        //  128-byte line — measured no faster: 65 -> 71 us on the 32768 x 2048 x 256 feed-forward GEMM; the
+        //  row-per-thread 256-bit stores stay.)
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += CH) {
+        for (; c0 < BN && n0 + c0 + CH <= p.cout; c0 += CH) {       // warp-uniform: full chunks of real columns
+          uint4 rv[CH / 8];
+#pragma unroll
+          for (int g = 0; g < CH / 8; ++g) rv[g] = rv_next[g];
+          if (res_fast && c0 + CH < BN && n0 + c0 + 2 * CH <= p.cout)
+            load_res_fast<CH>(p, rv_next, res_off, n0 + c0 + CH);
+          uint32_t raw[CH];
+          if constexpr (CH == 32) tmem_ld32(taddr + c0, raw);
+          else tmem_ld16(taddr + c0, raw);
+          tmem_ld_wait();
+          if (row_ok) {
+            if (p.res_ptr) epilogue_lean<CH, true>(p, raw, addv + c0, rv, out_off, n0 + c0);
+            else epilogue_lean<CH, false>(p, raw, addv + c0, rv, out_off, n0 + c0);
+          }
+        }
+      }
+#pragma unroll 1
+      for (; c0 < BN; c0 += CH) {
         if (n0 + c0 >= p.out_cols) break;             // warp-uniform
         if (fast_ok && n0 + c0 + CH <= p.cout) {      // warp-uniform: a full chunk of real columns
           uint4 rv[CH / 8];
-          if (p.res_ptr && row_ok) load_res_fast<CH>(p, rv, res_off, n0 + c0);   // in flight during the TMEM read
+#pragma unroll
+          for (int g = 0; g < CH / 8; ++g) rv[g] = rv_next[g];
+          if (res_fast && c0 + CH < BN && n0 + c0 + 2 * CH <= p.cout)
+            load_res_fast<CH>(p, rv_next, res_off, n0 + c0 + CH);      // next chunk's residual, one chunk ahead
           uint32_t raw[CH];
           if constexpr (CH == 32) tmem_ld32(taddr + c0, raw);
           else tmem_ld16(taddr + c0, raw);
@@ -974,7 +1053,7 @@ __global__ void igemm_check_kernel(const __grid_constant__ IgemmDev p) {
     const int iw = ow * p.sw + sg.dw, ih = oh * p.sh + sg.dh, id = od * p.sd + sg.dd;
     const bool inb = iw >= 0 && iw < p.in_W && ih >= 0 && ih < p.in_H && id >= 0 && id < p.in_D;
     const h16* a = p.a_ptr[sg.src] +
-        ((((long long)nb * p.in_D + id) * p.in_H + ih) * p.in_W + iw) * p.a_pitch[sg.src];
+        ((((long long)(p.a_bcast ? 0 : nb) * p.in_D + id) * p.in_H + ih) * p.in_W + iw) * p.a_pitch[sg.src];
     for (int c = 0; c < sg.nchunks; ++c, ++kglob) {
       if (!inb) continue;
       for (int e = 0; e < kBK; ++e) {
@@ -1081,7 +1160,45 @@ __global__ void __launch_bounds__(256) igemm_split_reduce_kernel(const IgemmDev 
   const int nb = (int)t;
   float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const float* src = ws + row * ws_cols + col0;
-  for (int s = 0; s < splits; ++s, src += ws_stride) {
+  int s = 0;
+  // eight (then four) ranges' loads in flight per thread, additions in range order: the plain load -> add loop was one
+  // L2 round trip per range (8-12 us per call in the ncu lists of the latent UNets, as long as the GEMM it completes)
+  for (; s + 8 <= splits; s += 8, src += 8 * ws_stride) {
+    float4 a[8], b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a[j] = __ldg(reinterpret_cast<const float4*>(src + j * ws_stride));
+      b[j] = __ldg(reinterpret_cast<const float4*>(src + j * ws_stride + 4));
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[0] += a[j].x; v[1] += a[j].y; v[2] += a[j].z; v[3] += a[j].w;
+      v[4] += b[j].x; v[5] += b[j].y; v[6] += b[j].z; v[7] += b[j].w;
+    }
+  }
+  if (s + 4 <= splits) {
+    float4 a[4], b[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      a[j] = __ldg(reinterpret_cast<const float4*>(src + j * ws_stride));
+      b[j] = __ldg(reinterpret_cast<const float4*>(src + j * ws_stride + 4));
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[0] += a[j].x; v[1] += a[j].y; v[2] += a[j].z; v[3] += a[j].w;
+      v[4] += b[j].x; v[5] += b[j].y; v[6] += b[j].z; v[7] += b[j].w;
+    }
+    s += 4; src += 4 * ws_stride;
+  }
+  if (s + 2 <= splits) {
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(src)), b0 = __ldg(reinterpret_cast<const float4*>(src + 4));
+    const float4 a1 = __ldg(reinterpret_cast<const float4*>(src + ws_stride));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(src + ws_stride + 4));
+    v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w; v[4] += b0.x; v[5] += b0.y; v[6] += b0.z; v[7] += b0.w;
+    v[0] += a1.x; v[1] += a1.y; v[2] += a1.z; v[3] += a1.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+    s += 2; src += 2 * ws_stride;
+  }
+  if (s < splits) {
     const float4 a = __ldg(reinterpret_cast<const float4*>(src));
     const float4 b = __ldg(reinterpret_cast<const float4*>(src + 4));
     v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
@@ -1101,6 +1218,19 @@ struct Plan {
   int splits, ws_cols;
   long long ws_bytes;
 };
+// dev knobs (read once): the shortest reduction, in 64-element chunks, for which an under-filled grid narrows its
+// column tile within one wave (B200_NARROW_MIN_CHUNKS, default 4), and the fewest ranges a split reduction must have to be worth its
+// fp32 partials + second kernel (B200_SPLIT_MIN, default 2), and the shortest range, in chunks, a split may leave each
+// CTA (B200_SPLIT_RANGE_MIN, default 32: measured per shape and on graph-replayed UNet steps with 4 / 12 / 24 — a
+// split only pays when every range still has ~2 000 elements of reduction to hide its partial stores and the second
+// kernel behind; C2 step 1.74 -> 1.59 ms, C5 5.18 -> 5.08 ms, brain-LDM 6.89 -> 6.65 ms from 4 to 24)
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && *e) ? atoi(e) : dflt;
+}
+static int narrow_min_chunks() { static int v = env_int("B200_NARROW_MIN_CHUNKS", 4); return v; }
+static int split_min() { static int v = env_int("B200_SPLIT_MIN", 2); return v; }
+static int split_range_min() { static int v = env_int("B200_SPLIT_RANGE_MIN", 32); return v < 1 ? 1 : v; }
 static Plan make_plan(const b200_igemm_params* p, bool allow_split) {
   Plan pl;
   pl.kchunks = 0;
@@ -1125,16 +1255,22 @@ static Plan make_plan(const b200_igemm_params* p, bool allow_split) {
   if (allow_split && !p->stat_ptr && !p->gn_partial && p->impl != 1 && pl.kchunks >= 16 &&
       wide_tiles * 2 <= sm_count()) {
     long long s = sm_count() / wide_tiles;
-    if (s > pl.kchunks / 4) s = pl.kchunks / 4;
+    if (s > pl.kchunks / split_range_min()) s = pl.kchunks / split_range_min();
     if (s > 32) s = 32;
-    if (s >= 2) {
+    if (s >= split_min()) {
       pl.splits = (int)s;
       pl.ws_bytes = s * pl.rows * pl.ws_cols * 4;
     }
   }
   // otherwise narrower tiles, down to 64 columns, to put more CTAs on the problem
-  if (pl.splits == 1)
+  if (pl.splits == 1) {
     while (!p->stat_ptr && BN > 64 && pl.m_tiles * ((cols16 + BN - 1) / BN) < sm_count() && pl.kchunks >= 8) BN >>= 1;
+    // short reductions (K = 256 / 384: the transformer linears) are epilogue-bound: halve the column tile while the
+    // narrower tiles still fit ONE wave (measured: 8192 x 256 x 256 + residual 8.9 -> 7.3 us, 1024 x 256 x 256
+    // 7.3 -> 5.2 us; going past one wave — 8192 x 512 — loses)
+    while (!p->stat_ptr && BN > 64 && pl.kchunks >= narrow_min_chunks() && pl.kchunks < 8 &&
+           pl.m_tiles * ((cols16 + BN / 2 - 1) / (BN / 2)) <= sm_count()) BN >>= 1;
+  }
   pl.BN = BN;
   pl.tiles_n = (cols16 + BN - 1) / BN;
   pl.ntiles = pl.m_tiles * pl.tiles_n;
@@ -1239,6 +1375,7 @@ extern "C" int b200_igemm(const b200_igemm_params* p, void* stream_v) {
     d.a_pitch[s] = p->a_pitch[s];
   }
   d.in_N = p->in_N; d.in_D = p->in_D; d.in_H = p->in_H; d.in_W = p->in_W;
+  d.a_bcast = p->a_broadcast ? 1 : 0;
   d.w_ptr = reinterpret_cast<const h16*>(p->w_ptr);
   d.w_rows = p->w_rows; d.w_K = w_K; d.w_pitch = p->w_pitch;
   d.w_bstride = p->w_bstride; d.w_batched = p->w_batched;
@@ -1327,14 +1464,17 @@ extern "C" int b200_igemm(const b200_igemm_params* p, void* stream_v) {
   // CTA pairs for the 256- and 128-column calls that fill the machine (at least one tile per SM — pairs of M tiles over pairs
   // of SMs quantise like single tiles over single SMs), no split-K / score statistics / staged stores
   const bool pair = igemm_pair_mode() && (BN == 256 || BN == 128) && splits == 1 && !p->stat_ptr && !d.out_staged &&
-                    pl.m_tiles >= 2 && pl.ntiles >= sm_count();
+                    pl.m_tiles >= 2 && pl.ntiles >= sm_count() &&
+                    // a pair shares ONE column tile of ONE weight batch: with per-sample weights the two M tiles of a
+                    // pair must belong to the same sample
+                    (!p->w_batched || ((pl.m_tiles / p->out_N) % 2 == 0));
   if (pair) d.num_tiles = (int)(((pl.m_tiles + 1) / 2) * pl.tiles_n);
 
   // ---- tensor maps ----
   for (int s = 0; s < 2; ++s) {
     if (!p->a_ptr[s]) continue;
     cuuint64_t dims[5] = {(cuuint64_t)p->a_C[s], (cuuint64_t)p->in_W, (cuuint64_t)p->in_H,
-                          (cuuint64_t)p->in_D, (cuuint64_t)p->in_N};
+                          (cuuint64_t)p->in_D, (cuuint64_t)(p->a_broadcast ? 1 : p->in_N)};
     const cuuint64_t pb = (cuuint64_t)p->a_pitch[s] * 2;
     cuuint64_t strides[4] = {pb, pb * p->in_W, pb * p->in_W * p->in_H,
                              pb * p->in_W * p->in_H * p->in_D};

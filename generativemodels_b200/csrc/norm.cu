@@ -509,6 +509,67 @@ __global__ void layernorm_kernel(const h16* __restrict__ x, long long M, int C, 
   for (int c = C + lane; c < y_pitch; c += 32) yr[c] = f2h(0.f);
 }
 
+// 128-bit variant (C % 8 == 0, 16-byte-aligned rows): the row lives in registers (VPL vectors of 8 channels per lane),
+// one global read and one write per element instead of three scalar reads; mean and variance as in the scalar kernel
+// (two passes, fp32), the per-lane summation order differs.
+template <int VPL>
+__global__ void layernorm_vec_kernel(const h16* __restrict__ x, long long M, int C, int x_pitch,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                     h16* __restrict__ y, int y_pitch) {
+  pdl_entry();
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  const int nv = C >> 3;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + row * x_pitch);
+  float f[VPL][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi < nv) {
+      const uint4 t = __ldg(xr + vi);
+      unpack8(t, f[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += f[i][j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[i][j] = 0.f;
+    }
+  }
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    if (lane + 32 * i < nv) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = f[i][j] - mean;
+        q = fmaf(d, d, q);
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / C + eps);
+  h16* yr = y + row * y_pitch;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi < nv) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * vi);
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * vi + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * vi);
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * vi + 1);
+      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (f[i][j] - mean) * rstd * g[j] + b[j];
+      *reinterpret_cast<uint4*>(yr + vi * 8) = pack8(v);
+    }
+  }
+  for (int c = C + lane; c < y_pitch; c += 32) yr[c] = f2h(0.f);
+}
+
 static int gn_chunks(int N, long long spatial, int rows) {
   long long want = (4ll * sm_count() + N - 1) / N;
   long long maxc = (spatial + rows * 8 - 1) / (rows * 8);   // at least 8 iterations per thread
@@ -717,8 +778,17 @@ extern "C" int b200_layernorm(const void* x, int64_t M, int32_t C, int32_t x_pit
   const int wpb = 8;
   const long long blocks = (M + wpb - 1) / wpb;
   B200_CHECK_ARG(blocks < (1ll << 31), "layernorm: too many rows");
-  B200_CUDA(b200::launch_pdl(layernorm_kernel, (unsigned)blocks, wpb * 32, 0, stream, reinterpret_cast<const h16*>(x), M, C, x_pitch,
-                                                             gamma, beta, eps, reinterpret_cast<h16*>(y), y_pitch));
+  const bool vec = C % 8 == 0 && C <= 2048 && x_pitch % 8 == 0 && y_pitch % 8 == 0 && ((uintptr_t)x % 16 == 0) &&
+                   ((uintptr_t)y % 16 == 0) && ((uintptr_t)gamma % 16 == 0) && ((uintptr_t)beta % 16 == 0);
+#define B200_LN_LAUNCH(K)                                                                                              \
+  B200_CUDA(b200::launch_pdl(K, (unsigned)blocks, wpb * 32, 0, stream, reinterpret_cast<const h16*>(x), M, C, x_pitch, \
+                             gamma, beta, eps, reinterpret_cast<h16*>(y), y_pitch))
+  if (!vec) B200_LN_LAUNCH(layernorm_kernel);
+  else if (C <= 256) B200_LN_LAUNCH(layernorm_vec_kernel<1>);
+  else if (C <= 512) B200_LN_LAUNCH(layernorm_vec_kernel<2>);
+  else if (C <= 1024) B200_LN_LAUNCH(layernorm_vec_kernel<4>);
+  else B200_LN_LAUNCH(layernorm_vec_kernel<8>);
+#undef B200_LN_LAUNCH
   B200_LAUNCH_CHECK("layernorm_kernel");
   return B200_OK;
 }

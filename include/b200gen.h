@@ -138,6 +138,10 @@ typedef struct {
    * their partials, wait for the S-th ticket, and each sums 1/S of the tile's rows in range order and applies the
    * epilogue — same arithmetic and summation order as the two-kernel form.  NULL = two kernels. */
   int32_t* split_counters;
+  /* 1: the A sources hold ONE sample that every one of the in_N samples reads (the operand-swapped projection
+   * V^T[n] = W x[n]^T of a whole batch in one launch: A = the shared weight matrix, the per-sample activations are the
+   * batched K-major operand, w_batched = 1).  0: sample n reads A at batch index n. */
+  int32_t a_broadcast;
 } b200_igemm_params;
 #define B200_IGEMM_SPLIT_COUNTERS 256
 

@@ -61,8 +61,9 @@ def emulate(p: IgemmParams) -> None:
         if not p.a_ptr[s]:
             srcs.append(None)
             continue
-        cnt = N * ID * IH * IW * p.a_pitch[s]
-        a = _bf16_to_f32(_bf16_view(p.a_ptr[s], cnt).copy()).reshape(N, ID, IH, IW, p.a_pitch[s])
+        NA = 1 if p.a_broadcast else N          # a_broadcast: one A sample shared by all N
+        cnt = NA * ID * IH * IW * p.a_pitch[s]
+        a = _bf16_to_f32(_bf16_view(p.a_ptr[s], cnt).copy()).reshape(NA, ID, IH, IW, p.a_pitch[s])
         srcs.append(a)
     wK = p.w_K if p.w_K > 0 else p.w_pitch
     nwb = N if p.w_batched else 1
@@ -86,7 +87,7 @@ def emulate(p: IgemmParams) -> None:
             ihh = oh * p.stride_h + sg.dh
             iww = ow * p.stride_w + sg.dw
             ok = (idd >= 0) & (idd < ID) & (ihh >= 0) & (ihh < IH) & (iww >= 0) & (iww < IW)
-            g = a[n][np.clip(idd, 0, ID - 1), np.clip(ihh, 0, IH - 1), np.clip(iww, 0, IW - 1)]   # [OD,OH,OW,pitch]
+            g = a[0 if p.a_broadcast else n][np.clip(idd, 0, ID - 1), np.clip(ihh, 0, IH - 1), np.clip(iww, 0, IW - 1)]   # [OD,OH,OW,pitch]
             g = g * ok[..., None]
             for c in range(sg.nchunks):
                 ch0 = (sg.c0 + c) * 64

@@ -213,6 +213,13 @@ def test_linear_and_transposed_host_logic():
     close(out.t[0, 0, 0, :, :O].float(), ref)
     vt = ops.linear_transposed(a.t.reshape(1, M, -1), K, pl)
     close(vt[0, :, :M].float(), ref.t())
+    # a batch goes through ONE launch: the projection matrix is the broadcast A operand, sample b's rows are weight
+    # batch b (b200gen.h a_broadcast / w_batched)
+    xb = torch.randn(3, K, 1, M)
+    ab = cl_cpu(xb)
+    vtb = ops.linear_transposed(ab.t.reshape(3, M, -1), K, pl)
+    for i in range(3):
+        close(vtb[i, :, :M].float(), F.linear(bf(xb)[i, :, 0].t(), bf(w), b).t())
 
 
 def test_attention_tc_host_logic(monkeypatch):

@@ -280,12 +280,13 @@ def test_split_k_conv_matches_one_pass_and_check_kernel(cuda_device, monkeypatch
 
 
 def test_split_k_linear_shapes(cuda_device, monkeypatch):
-    """GEMM-shaped calls on few rows (transformer blocks of the deepest UNet level): K = 3072 feed-forward with a
-    residual, and the operand-swapped V^T projection whose bias runs along the rows."""
+    """GEMM-shaped calls on few rows (transformer blocks of the deepest UNet level): a long feed-forward reduction with a
+    residual, and the operand-swapped V^T projection whose bias runs along the rows.  Reductions long enough for the
+    planner to split (every range keeps >= 32 chunks of 64: B200_SPLIT_RANGE_MIN)."""
     ops = _ops()
     monkeypatch.setattr(ops, "_SPLIT_K", True)
     torch.manual_seed(12)
-    M, K, O = 175, 3072, 768
+    M, K, O = 175, 6144, 768
     x, w, b, r = torch.randn(1, M, K), torch.randn(O, K) / math.sqrt(K), torch.randn(O), torch.randn(1, M, O)
     pl = ops.PackedLinear(w.cuda(), b.cuda())
     xc = ops.as_rows(bf(x).cuda().to(ops.H16), K)
@@ -295,13 +296,13 @@ def test_split_k_linear_shapes(cuda_device, monkeypatch):
     assert ops._SPLIT_LAUNCHES == n0 + 1
     ref = F.linear(bf(x), bf(w), b) + bf(r)
     assert_close(got.t.float().cpu().reshape(1, M, -1)[..., :O], ref, 1e-2, "split-K linear + residual")
-    xr = bf(torch.randn(2, 200, 1024)).cuda().to(ops.H16)
-    w2, b2 = torch.randn(512, 1024) / math.sqrt(1024), torch.randn(512)
+    xr = bf(torch.randn(2, 200, 4096)).cuda().to(ops.H16)
+    w2, b2 = torch.randn(512, 4096) / math.sqrt(4096), torch.randn(512)
     pl2 = ops.PackedLinear(w2.cuda(), b2.cuda())
-    vt = ops.linear_transposed(xr, 1024, pl2)                         # [B, O, S_pad]
-    assert ops._SPLIT_LAUNCHES == n0 + 3                              # one launch per batch entry
+    vt = ops.linear_transposed(xr, 4096, pl2)                         # [B, O, S_pad]
+    assert ops._SPLIT_LAUNCHES == n0 + 2                              # ONE launch for the whole batch (a_broadcast)
     monkeypatch.setattr(ops, "_SPLIT_K", False)
-    vt1 = ops.linear_transposed(xr, 1024, pl2)
+    vt1 = ops.linear_transposed(xr, 4096, pl2)
     ref_vt = (F.linear(xr.float().cpu(), bf(w2), b2)).transpose(1, 2)
     assert_close(vt[..., :200].float().cpu(), ref_vt, 1e-2, "V^T projection")
     assert rel_err(vt.float(), vt1.float())[0] < 2e-3
@@ -419,6 +420,14 @@ def test_layernorm_geglu(cuda_device):
     ref = F.layer_norm(bf(x)[0, :, 0].t(), (Cc,), g, b, 1e-5)
     out = ops.layernorm(ops.to_cl(x.cuda()), g.cuda(), b.cuda(), 1e-5)
     assert_close(out.t[0, 0, 0, :, :Cc], ref, 1e-2, "layernorm")
+    # every width of the 128-bit kernel (1 / 2 / 4 / 8 vectors per lane, ragged last vector) and the scalar fallback
+    for C2 in (8, 40, 264, 512, 768, 2048, 12, 2056):
+        x2 = torch.randn(1, C2, 1, 67) * 2 + 0.5
+        g2, b2 = torch.randn(C2), torch.randn(C2)
+        ref2 = F.layer_norm(bf(x2)[0, :, 0].t(), (C2,), g2, b2, 1e-5)
+        out2 = ops.layernorm(ops.to_cl(x2.cuda()), g2.cuda(), b2.cuda(), 1e-5)
+        assert_close(out2.t[0, 0, 0, :, :C2], ref2, 1e-2, f"layernorm C={C2}")
+        assert float(out2.t[0, 0, 0, :, C2:].abs().max() if out2.t.shape[-1] > C2 else 0.0) == 0.0
     xa = bf(x)[0, :, 0].t()
     a, gate = xa.chunk(2, -1)
     refg = a * F.gelu(gate)

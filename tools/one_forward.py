@@ -24,10 +24,10 @@ elif which == "c5":          # one guided step's UNet forward on the doubled bat
                              attention_levels=(False, True, True), num_head_channels=256, with_conditioning=True,
                              cross_attention_dim=1).cuda().eval()
     x, ctx = torch.randn(2, 3, 256, 256).cuda(), torch.tensor([[[-1.0]], [[1.0]]]).cuda()
-else:
+else:                        # c2 (batch 1) / c2n32 (batch 32)
     net = DiffusionModelUNet(2, 3, 3, num_res_blocks=2, num_channels=(128, 256, 512),
                              attention_levels=(False, True, True), num_head_channels=(0, 256, 512)).cuda().eval()
-    x, ctx = torch.randn(1, 3, 64, 64).cuda(), None
+    x, ctx = torch.randn(32 if which == "c2n32" else 1, 3, 64, 64).cuda(), None
 with torch.no_grad():
     for p in net.parameters():
         if float(p.abs().max()) == 0:
@@ -36,8 +36,27 @@ t = torch.tensor([500]).cuda()
 for _ in range(3):
     net(x, timesteps=t, context=ctx)
 torch.cuda.synchronize()
+# the implicit-GEMM problems of the profiled forward, in launch order (joined with the ncu list by tools/join_shapes.py)
+import json
+from generativemodels_b200 import _lib
+lib = _lib.require_device()
+shapes, raw = [], lib.b200_igemm
+
+
+def logged(pp, stream):
+    p = pp._obj
+    shapes.append(dict(rows=p.out_N * p.out_D * p.out_H * p.out_W, cout=p.cout,
+                       chunks=sum(p.seg[i].nchunks for i in range(p.n_seg)), n_seg=p.n_seg,
+                       split=bool(p.split_ws), stride=p.stride_w, out_f32=p.out_dtype != 0))
+    return raw(pp, stream)
+
+
+lib.b200_igemm = logged
 torch.cuda.profiler.start()
 net(x, timesteps=t, context=ctx)
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
-print("done")
+lib.b200_igemm = raw
+Path("gpurun_out").mkdir(exist_ok=True)
+Path(f"gpurun_out/shapes_{which}.json").write_text(json.dumps(shapes))
+print("done", len(shapes), "igemm calls")

@@ -43,6 +43,7 @@ sched = DDIMScheduler(1000, "linear_beta", beta_start=0.0015, beta_end=0.0195)
 sched.set_timesteps(50)
 cases = {"brain-LDM UNet 7x20x28x20": (brain, torch.randn(1, 7, 20, 28, 20).cuda(), torch.randn(1, 1, 4).cuda(), 3),
          "C2 UNet 3x64x64": (c2, torch.randn(1, 3, 64, 64).cuda(), None, 3),
+         "C2 UNet 32x3x64x64": (c2, torch.randn(32, 3, 64, 64).cuda(), None, 3),
          "C5 UNet 2x3x256x256 (CFG batch, no ControlNet residuals)": (c5, torch.randn(2, 3, 256, 256).cuda(),
                                                                      torch.tensor([[[-1.0]], [[1.0]]]).cuda(), 3)}
 
