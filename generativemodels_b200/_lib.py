@@ -26,6 +26,7 @@ B200_OK, B200_EINVAL, B200_ENOTSUP, B200_ECUDA, B200_ENODEV = 0, -1, -2, -3, -4
 DT_H16, DT_F32 = 0, 1
 H16_FP16, H16_BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_SILU, ACT_LEAKYRELU, ACT_GELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3, 4, 5, 6
+ACT_GEGLU = 7        # b200_igemm act1 only: [32 a | 32 gate] column groups -> a * gelu(gate), half as many output channels
 PRED_EPSILON, PRED_SAMPLE, PRED_V = 0, 1, 2
 IGEMM_MAX_SEG = 128
 IGEMM_SPLIT_COUNTERS = 256

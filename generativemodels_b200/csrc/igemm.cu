@@ -76,6 +76,7 @@ struct IgemmDev {
   long long rowvec_bstride;
   const float* row_bias;
   int act1, act2;
+  int geglu;                // act1 was B200_ACT_GEGLU: [32 a | 32 gate] column groups -> a * gelu(gate), cout / 2 output channels
   float scale;
   const void* res_ptr;
   int res_dtype, res_vec, res_v256;
@@ -711,7 +712,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
     const bool fast_ok = p.out_vec && !p.out_staged && !p.stat_ptr &&
                          (!p.res_ptr || (p.res_vec && p.res_dtype == B200_DT_H16));
     const bool lean_ok = fast_ok && p.act1 == B200_ACT_NONE && p.act2 == B200_ACT_NONE && p.scale == 1.0f &&
-                         !p.row_bias && !p.gn_partial && p.out_dtype == B200_DT_H16 && p.out_v256;
+                         !p.row_bias && !p.gn_partial && p.out_dtype == B200_DT_H16 && p.out_v256 && !p.geglu;
     // GroupNorm partial sums for the consumer of this tensor: per warp [BN/8 groups][sum, sumsq] in shared memory
     // (aliases the staged-store tiles, which this mode excludes), flushed to this warp's private global slot
     // whenever the (sample, column tile) changes and at the end — deterministic, no atomics.
@@ -900,6 +901,47 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
       float run_max = -INFINITY, run_sum = 0.f;
       float* my_tile = stage_tiles + (warp - 2) * (32 * (CH + 1));
       int c0 = 0;
+      if constexpr (CH == 32 && BN >= 64) {
+        if (p.geglu) {
+          // GEGLU feed-forward: this GEMM's columns are [32 a | 32 gate] groups; out = (a + b_a) * gelu(gate + b_g) on
+          // the fp32 accumulators (the unfused path rounded linear1's output to 16 bits first and spent a 200 MB pass
+          // per block on the gating), half as many channels stored
+#pragma unroll 1
+          for (; c0 + 64 <= BN && n0 + c0 + 64 <= p.cout; c0 += 64) {
+            uint32_t ra[32], rg[32];
+            tmem_ld32(taddr + c0, ra);
+            tmem_ld32(taddr + c0 + 32, rg);
+            tmem_ld_wait();
+            if (row_ok) {
+              float v[32];
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 ba = *reinterpret_cast<const float4*>(addv + c0 + j);
+                const float4 bg = *reinterpret_cast<const float4*>(addv + c0 + 32 + j);
+                const float a4[4] = {ba.x, ba.y, ba.z, ba.w}, g4[4] = {bg.x, bg.y, bg.z, bg.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float a = __uint_as_float(ra[j + e]) + a4[e];
+                  const float g = __uint_as_float(rg[j + e]) + g4[e];
+                  v[j + e] = a * (0.5f * g * (1.0f + erff(g * 0.70710678118654752f)));
+                }
+              }
+              h16* o = reinterpret_cast<h16*>(p.out_ptr) + out_off + ((n0 + c0) >> 1);
+              uint4 pk[4];
+#pragma unroll
+              for (int g = 0; g < 4; ++g) pk[g] = pack8(v + g * 8);
+              if (p.out_v256) {
+                stg256(o, pk[0], pk[1]);
+                stg256(o + 16, pk[2], pk[3]);
+              } else {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(o + g * 8) = pk[g];
+              }
+            }
+          }
+          c0 = BN;       // cout is a multiple of 64: every real column of this tile has been consumed
+        }
+      }
       if (lean_ok) {
         // (A shared-memory transposed variant — two chunks staged per warp, eight lanes writing each row's whole
         //  128-byte line — measured no faster: 65 -> 71 us on the 32768 x 2048 x 256 feed-forward GEMM; the
@@ -1244,7 +1286,7 @@ static Plan make_plan(const b200_igemm_params* p, bool allow_split) {
   pl.ws_cols = ((p->out_cols + 7) / 8) * 8;
   pl.ws_bytes = 0;
   // N tile: as wide as the output needs
-  const int cols16 = ((p->out_cols + 15) / 16) * 16;
+  const int cols16 = (((p->act1 == B200_ACT_GEGLU ? p->cout : p->out_cols) + 15) / 16) * 16;   // GEGLU: tile the GEMM's columns
   int BN = cols16 <= 16 ? 16 : cols16 <= 32 ? 32 : cols16 <= 64 ? 64 : cols16 <= 128 ? 128 : 256;
   if (p->stat_ptr) BN = 256;      // the caller sizes the partials buffer for 256-column tiles
   // A grid that cannot fill the SMs: keep the wide tile (operand traffic from L2 per FLOP falls with the tile width —
@@ -1252,7 +1294,7 @@ static Plan make_plan(const b200_igemm_params* p, bool allow_split) {
   // reduction into ranges instead, when the caller brought a workspace and the reduction is long enough for at least
   // two ranges of four 64-element chunks.
   const long long wide_tiles = pl.m_tiles * ((cols16 + BN - 1) / BN);
-  if (allow_split && !p->stat_ptr && !p->gn_partial && p->impl != 1 && pl.kchunks >= 16 &&
+  if (allow_split && !p->stat_ptr && !p->gn_partial && p->impl != 1 && p->act1 != B200_ACT_GEGLU && pl.kchunks >= 16 &&
       wide_tiles * 2 <= sm_count()) {
     long long s = sm_count() / wide_tiles;
     if (s > pl.kchunks / split_range_min()) s = pl.kchunks / split_range_min();
@@ -1340,7 +1382,15 @@ extern "C" int b200_igemm(const b200_igemm_params* p, void* stream_v) {
   B200_CHECK_ARG(p->n_seg >= 1 && p->n_seg <= B200_IGEMM_MAX_SEG, "igemm: n_seg=%d out of range", p->n_seg);
   B200_CHECK_ARG(p->in_N >= 1 && p->in_D >= 1 && p->in_H >= 1 && p->in_W >= 1, "igemm: bad input extent");
   B200_CHECK_ARG(p->out_N == p->in_N && p->out_D >= 1 && p->out_H >= 1 && p->out_W >= 1, "igemm: bad output extent");
-  B200_CHECK_ARG(p->cout >= 1 && p->out_cols >= p->cout, "igemm: bad cout/out_cols");
+  const bool geglu = p->act1 == B200_ACT_GEGLU;
+  B200_CHECK_ARG(p->cout >= 1 && p->out_cols >= (geglu ? p->cout / 2 : p->cout), "igemm: bad cout/out_cols");
+  if (geglu) {
+    B200_CHECK_ARG(p->cout % 64 == 0 && p->out_dtype == B200_DT_H16 && !p->res_ptr && p->scale == 1.0f &&
+                   p->act2 == B200_ACT_NONE && !p->stat_ptr && !p->gn_partial && !p->row_bias && p->impl != 1 &&
+                   env_impl() != 1,
+                   "igemm: B200_ACT_GEGLU needs cout %% 64 == 0, a h16 output and no residual / scale / act2 / "
+                   "statistics / row bias (and has no cross-check kernel)");
+  }
   B200_CHECK_ARG(p->w_pitch % 8 == 0 && p->w_rows >= 1, "igemm: weight pitch must be a multiple of 8");
   B200_CHECK_ARG(((uintptr_t)p->w_ptr & 15) == 0, "igemm: weight pointer not 16-byte aligned");
   B200_CHECK_ARG(p->stride_d >= 1 && p->stride_d <= 8 && p->stride_h >= 1 && p->stride_h <= 8 &&
@@ -1384,7 +1434,9 @@ extern "C" int b200_igemm(const b200_igemm_params* p, void* stream_v) {
   d.out_ptr = p->out_ptr; d.out_dtype = p->out_dtype; d.cout = p->cout; d.out_cols = p->out_cols;
   d.out_sN = p->out_sN; d.out_sD = p->out_sD; d.out_sH = p->out_sH; d.out_sW = p->out_sW;
   d.bias = p->bias; d.rowvec = p->rowvec; d.rowvec_bstride = p->rowvec_bstride; d.row_bias = p->row_bias;
-  d.act1 = p->act1; d.act2 = p->act2; d.scale = p->scale;
+  d.act1 = geglu ? B200_ACT_NONE : p->act1; d.act2 = p->act2; d.scale = p->scale;
+  d.geglu = geglu ? 1 : 0;
+  if (geglu) d.out_cols = p->cout;        // the kernel's column loops run over the GEMM's columns
   d.res_ptr = p->res_ptr; d.res_dtype = p->res_dtype;
   d.res_sN = p->res_sN; d.res_sD = p->res_sD; d.res_sH = p->res_sH; d.res_sW = p->res_sW;
   {
@@ -1397,6 +1449,7 @@ extern "C" int b200_igemm(const b200_igemm_params* p, void* stream_v) {
                  (p->out_sD % 16 == 0) && (p->out_sH % 16 == 0) && (p->out_sW % 16 == 0) &&
                  (((uintptr_t)p->out_ptr) % 32 == 0);
   }
+  B200_CHECK_ARG(!geglu || d.out_vec, "igemm: B200_ACT_GEGLU needs a 16-byte-aligned output (out_cols, strides %% 8 == 0)");
   {
     // rows far apart in memory (wide row-major GEMM outputs): stage the tile through smem for coalesced row stores
     const long long esz = (p->out_dtype == B200_DT_H16) ? 2 : 4;

@@ -125,6 +125,20 @@ def packed_linear(owner: nn.Module, name: str) -> ops.PackedLinear:
     return h.packed()
 
 
+def packed_linear_geglu(owner: nn.Module, name: str) -> ops.PackedLinear:
+    """``owner.name`` (linear1 of a GEGLU feed-forward) packed with interleaved a / gate rows (ops.PackedLinear.geglu),
+    cached like packed_linear."""
+    lin = getattr(owner, name)
+    cache = owner.__dict__.setdefault("_pack_cache", {})
+    key = ("geglu", name)
+    k = (key, _key(lin.weight, lin.bias))
+    hit = cache.get(key)
+    if hit is None or hit[0] != k:
+        hit = (k, ops.PackedLinear.geglu(lin.weight, lin.bias))
+        cache[key] = hit
+    return hit[1]
+
+
 def packed_linear_stack(owner: nn.Module, names: Sequence[str]) -> ops.PackedLinear:
     """The linears ``names`` of ``owner`` (same input) as one stacked GEMM weight, cached like packed_linear."""
     lins = [getattr(owner, n) for n in names]

@@ -20,7 +20,8 @@ import torch.nn as nn
 from ... import ops
 from ...ops import ACT_SILU, CL
 from ..blocks.spade_norm import SPADE
-from .._holders import Convolution, f32, on_input_device, packed_linear, packed_linear_stack, require_cuda
+from .._holders import (Convolution, f32, on_input_device, packed_linear, packed_linear_geglu, packed_linear_stack,
+                        require_cuda)
 
 __all__ = ["DiffusionModelUNet"]
 
@@ -111,8 +112,12 @@ class GEGLUFeedForward(nn.Module):
         self.linear2 = nn.Linear(mlp_dim, hidden_size)
 
     def forward(self, x: CL, residual: CL | None = None) -> CL:
-        f = ops.linear(x, packed_linear(self, "linear1"))
-        return ops.linear(ops.geglu(f), packed_linear(self, "linear2"), residual=residual)
+        if self.linear2.in_features % 32 == 0:
+            # linear1 + gating as one GEMM (a * gelu(gate) in the epilogue, on the fp32 accumulators)
+            f = ops.linear_geglu(x, packed_linear_geglu(self, "linear1"))
+        else:
+            f = ops.geglu(ops.linear(x, packed_linear(self, "linear1")))
+        return ops.linear(f, packed_linear(self, "linear2"), residual=residual)
 
 
 class BasicTransformerBlock(nn.Module):

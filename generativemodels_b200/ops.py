@@ -15,14 +15,14 @@ from typing import Sequence
 import torch
 
 from . import _lib
-from ._lib import (ACT_GELU, ACT_LEAKYRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SILU, ACT_TANH, DT_H16, DT_F32, DdimCoef, DdpmCoef, GnApplyParams, GnStatsParams,
+from ._lib import (ACT_GEGLU, ACT_GELU, ACT_LEAKYRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SILU, ACT_TANH, DT_H16, DT_F32, DdimCoef, DdpmCoef, GnApplyParams, GnStatsParams,
                    IgemmParams, PndmCoef, check)
 
 # torch dtype of the library's 16-bit storage type (fp16 unless B200_ACT_DTYPE=h16; see _lib.ACT_DTYPE)
 H16 = torch.float16 if _lib.ACT_DTYPE == "fp16" else torch.bfloat16
 
 __all__ = ["CL", "to_cl", "from_cl", "PackedConv", "PackedConvTranspose", "PackedLinear", "conv", "conv_transpose",
-           "linear", "groupnorm", "layernorm", "upsample_nearest2x", "avgpool2", "axpy", "geglu", "attention",
+           "linear", "linear_geglu", "groupnorm", "layernorm", "upsample_nearest2x", "avgpool2", "axpy", "geglu", "attention",
            "timestep_embedding", "small_linear", "ACT_NONE", "ACT_RELU", "ACT_SILU", "ACT_LEAKYRELU", "ACT_GELU", "ACT_TANH", "ACT_SIGMOID"]
 
 
@@ -243,6 +243,21 @@ class PackedLinear:
             bias = torch.cat([(_src_f32(b) if b is not None else torch.zeros(o, device=ws[0].device))
                               for b, o in zip(biases, outs)]).contiguous()
         return cls.from_packed(w16, sum(outs), K, bias)
+
+    @classmethod
+    def geglu(cls, weight: torch.Tensor, bias: torch.Tensor | None) -> "PackedLinear":
+        """linear1 of a GEGLU feed-forward (weight [2H, K]: rows [0, H) = a, [H, 2H) = gate; monai MLPBlock
+        act="GEGLU") with its rows — and bias — interleaved in groups of 32 ([32 a | 32 gate] per 64 GEMM columns), the
+        layout b200_igemm's B200_ACT_GEGLU epilogue gates in place.  H must be a multiple of 32."""
+        w = _src_f32(weight)
+        H = w.shape[0] // 2
+        if w.shape[0] != 2 * H or H % 32:
+            raise ValueError(f"GEGLU linear needs 2 x (multiple of 32) output features, got {w.shape[0]}")
+        j = torch.arange(2 * H, device=w.device)
+        perm = (j // 64) * 32 + (j % 32) + ((j % 64) // 32) * H          # GEMM column -> source row
+        self = cls(w.index_select(0, perm), None if bias is None else _src_f32(bias).index_select(0, perm))
+        self.geglu_hidden = H
+        return self
 
     @classmethod
     def from_packed(cls, w16: torch.Tensor, cout: int, K: int, bias: torch.Tensor | None) -> "PackedLinear":
@@ -820,6 +835,22 @@ def geglu(x: CL) -> CL:
     out = x.like(Hh)
     M = x.N * x.spatial
     check(lib.b200_geglu(x.t.data_ptr(), M, Hh, x.pitch, out.t.data_ptr(), out.pitch, _stream()), "b200_geglu")
+    return out
+
+
+def linear_geglu(x: CL, pl: PackedLinear) -> CL:
+    """a * gelu(gate) with (a, gate) = chunk(x @ W^T + b, 2): linear1 and the gating of a GEGLU feed-forward as ONE
+    GEMM (``pl`` from :meth:`PackedLinear.geglu`); the 2H-wide intermediate never exists."""
+    H = getattr(pl, "geglu_hidden", None)
+    if H is None:
+        raise ValueError("linear_geglu needs a PackedLinear.geglu weight")
+    if x.C != pl.K:
+        raise ValueError(f"linear expects {pl.K} input features, got {x.C}")
+    out = x.like(H)
+    p = _conv_params([x], pl.w, pl.segs, (1, 1, 1), out.t, (x.D, x.H, x.W), pl.cout, DT_H16, pl.bias, None, ACT_GEGLU,
+                     1.0, None, DT_H16, ACT_NONE)
+    p.out_cols = out.pitch          # H (a multiple of 32) channels are stored per row, not the GEMM's 2H columns
+    igemm_raw(p)
     return out
 
 

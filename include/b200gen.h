@@ -42,6 +42,13 @@ extern "C" {
 #define B200_ACT_TANH 5        /* VQVAE output_act (vqvae.py:263-264, monai Act["TANH"])       */
 #define B200_ACT_SIGMOID 6     /* VQVAE output_act (monai Act["SIGMOID"])                      */
 #define B200_ACT_LEAKYRELU 3   /* nn.LeakyReLU() default slope 0.01 (monai act="LEAKYRELU" in blocks/spade_norm.py:52-60) */
+/* b200_igemm act1 only: the GEGLU feed-forward of the transformer blocks (monai MLPBlock act="GEGLU",
+ * diffusion_model_unet.py:211: linear1 -> a * gelu(gate) with a, gate = chunk(2, -1)) fused into linear1's epilogue.
+ * The GEMM's `cout` columns come in 64-column groups [32 x a | 32 x gate] (the caller interleaves the weight rows and
+ * the bias that way); output channel (col / 64) * 32 + col % 32 = (acc_a + bias_a) * gelu(acc_gate + bias_gate), so
+ * the stored row has cout / 2 channels (out_cols >= cout / 2).  Needs cout % 64 == 0, a h16 16-byte-aligned output,
+ * no residual / scale / act2 / statistics / split. */
+#define B200_ACT_GEGLU 7
 
 #define B200_IGEMM_MAX_SEG 128
 

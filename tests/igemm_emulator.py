@@ -6,8 +6,8 @@ import ctypes as C
 
 import numpy as np
 
-from generativemodels_b200._lib import (ACT_DTYPE, ACT_GELU, ACT_LEAKYRELU, ACT_RELU, ACT_SIGMOID, ACT_SILU, ACT_TANH, DT_H16,
-                                         IgemmParams)
+from generativemodels_b200._lib import (ACT_DTYPE, ACT_GEGLU, ACT_GELU, ACT_LEAKYRELU, ACT_RELU, ACT_SIGMOID, ACT_SILU, ACT_TANH,
+                                         DT_H16, IgemmParams)
 
 
 def _bf16_view(ptr, count):
@@ -71,7 +71,10 @@ def emulate(p: IgemmParams) -> None:
     span = (nwb - 1) * bstride + p.w_rows * p.w_pitch
     wraw = _bf16_to_f32(_bf16_view(p.w_ptr, span).copy())
     OD, OH, OW = p.out_D, p.out_H, p.out_W
-    cols = p.out_cols
+    geglu = p.act1 == ACT_GEGLU          # [32 a | 32 gate] column groups of the GEMM -> a * gelu(gate), cout / 2 channels
+    if geglu:
+        assert p.cout % 64 == 0 and p.out_cols >= p.cout // 2 and not p.res_ptr and p.scale == 1.0 and not p.row_bias
+    cols = p.cout if geglu else p.out_cols
     acc = np.zeros((N, OD, OH, OW, cols), dtype=np.float64)
     od = np.arange(OD)[:, None, None]
     oh = np.arange(OH)[None, :, None]
@@ -113,7 +116,17 @@ def emulate(p: IgemmParams) -> None:
     if p.row_bias:
         rb = _f32_view(p.row_bias, OW).copy()
         v += rb[None, None, None, :, None]
-    v = _act(v, p.act1) * np.float32(p.scale)
+    if geglu:
+        H = p.cout // 2
+        vv = v.reshape(*v.shape[:-1], p.cout // 64, 2, 32)
+        gated = (vv[..., 0, :] * _act(vv[..., 1, :], ACT_GELU)).astype(np.float32).reshape(*v.shape[:-1], H)
+        cols = p.out_cols
+        v = np.zeros((*gated.shape[:-1], cols), dtype=np.float32)
+        v[..., :H] = gated
+        col = np.arange(cols)
+        valid = col < H
+    else:
+        v = _act(v, p.act1) * np.float32(p.scale)
     if p.stat_ptr:       # softmax partials per 256-column tile (GEMM-shaped calls): (max, sum exp(v - max))
         nt = (cols + 255) // 256
         st = _f32_view(p.stat_ptr, OW * nt * 2).reshape(OW, nt, 2)

@@ -222,6 +222,22 @@ def test_linear_and_transposed_host_logic():
         close(vtb[i, :, :M].float(), F.linear(bf(xb)[i, :, 0].t(), bf(w), b).t())
 
 
+def test_linear_geglu_host_logic():
+    """linear1 + GEGLU gating as one GEMM: interleaved [32 a | 32 gate] weight rows, B200_ACT_GEGLU epilogue
+    (MLPBlock act="GEGLU": a * gelu(gate), a, gate = chunk(linear1(x), 2, -1))."""
+    torch.manual_seed(5)
+    for M, K, H in ((37, 40, 32), (130, 64, 160), (9, 256, 1024)):
+        x = torch.randn(1, K, 1, M)
+        w, b = torch.randn(2 * H, K) / K ** 0.5, torch.randn(2 * H)
+        a, gate = F.linear(bf(x)[0, :, 0].t(), bf(w), b).chunk(2, -1)
+        ref = a * F.gelu(gate)
+        out = ops.linear_geglu(cl_cpu(x), ops.PackedLinear.geglu(w, b))
+        assert out.C == H and out.t.shape[-1] == H
+        close(out.t[0, 0, 0, :, :H].float(), ref)
+    with pytest.raises(ValueError):
+        ops.PackedLinear.geglu(torch.randn(2 * 40, 16), None)          # hidden width not a multiple of 32
+
+
 def test_attention_tc_host_logic(monkeypatch):
     """The tensor-core attention parameter blocks (QK^T, PV with V^T) — softmax emulated on CPU."""
     torch.manual_seed(4)

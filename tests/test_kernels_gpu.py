@@ -433,6 +433,14 @@ def test_layernorm_geglu(cuda_device):
     refg = a * F.gelu(gate)
     outg = ops.geglu(ops.to_cl(x.cuda()))
     assert_close(outg.t[0, 0, 0, :, : Cc // 2], refg, 1e-2, "geglu")
+    # linear1 + gating fused into one GEMM (B200_ACT_GEGLU): single-CTA tiles, CTA-pair tiles, a ragged last column tile
+    for M2, K2, H2 in ((300, 256, 1024), (32768, 256, 1024), (1000, 64, 160), (70, 512, 2048)):
+        x2 = torch.randn(1, K2, 1, M2)
+        w2, b2 = torch.randn(2 * H2, K2) / math.sqrt(K2), torch.randn(2 * H2)
+        a2, g2 = F.linear(bf(x2)[0, :, 0].t(), bf(w2), b2).chunk(2, -1)
+        got = ops.linear_geglu(ops.to_cl(x2.cuda()), ops.PackedLinear.geglu(w2.cuda(), b2.cuda()))
+        assert got.C == H2
+        assert_close(got.t[0, 0, 0, :, :H2], a2 * F.gelu(g2), 1e-2, f"fused GEGLU linear {M2}x{K2}x{H2}")
 
 
 # ------------------------------------------------------------------------------------------------ resampling
