@@ -1262,7 +1262,7 @@ struct Plan {
 };
 // dev knobs (read once): the shortest reduction, in 64-element chunks, for which an under-filled grid narrows its
 // column tile within one wave (B200_NARROW_MIN_CHUNKS, default 4), and the fewest ranges a split reduction must have to be worth its
-// fp32 partials + second kernel (B200_SPLIT_MIN, default 2), and the shortest range, in chunks, a split may leave each
+// fp32 partials + second kernel (B200_SPLIT_MIN, default 3: every two-range split measured lost to the one-pass kernel), and the shortest range, in chunks, a split may leave each
 // CTA (B200_SPLIT_RANGE_MIN, default 32: measured per shape and on graph-replayed UNet steps with 4 / 12 / 24 — a
 // split only pays when every range still has ~2 000 elements of reduction to hide its partial stores and the second
 // kernel behind; C2 step 1.74 -> 1.59 ms, C5 5.18 -> 5.08 ms, brain-LDM 6.89 -> 6.65 ms from 4 to 24)
@@ -1271,7 +1271,8 @@ static int env_int(const char* name, int dflt) {
   return (e && *e) ? atoi(e) : dflt;
 }
 static int narrow_min_chunks() { static int v = env_int("B200_NARROW_MIN_CHUNKS", 4); return v; }
-static int split_min() { static int v = env_int("B200_SPLIT_MIN", 2); return v; }
+static int narrow_one_wave() { static int v = env_int("B200_NARROW_ONE_WAVE", 1); return v; }
+static int split_min() { static int v = env_int("B200_SPLIT_MIN", 3); return v; }
 static int split_range_min() { static int v = env_int("B200_SPLIT_RANGE_MIN", 32); return v < 1 ? 1 : v; }
 static Plan make_plan(const b200_igemm_params* p, bool allow_split) {
   Plan pl;
@@ -1306,7 +1307,13 @@ static Plan make_plan(const b200_igemm_params* p, bool allow_split) {
   }
   // otherwise narrower tiles, down to 64 columns, to put more CTAs on the problem
   if (pl.splits == 1) {
-    while (!p->stat_ptr && BN > 64 && pl.m_tiles * ((cols16 + BN - 1) / BN) < sm_count() && pl.kchunks >= 8) BN >>= 1;
+    if (!narrow_one_wave())   // the round-1 rule (B200_NARROW_ONE_WAVE=0): narrow while the grid is under-filled, into a second wave
+      while (!p->stat_ptr && BN > 64 && pl.m_tiles * ((cols16 + BN - 1) / BN) < sm_count() && pl.kchunks >= 8) BN >>= 1;
+    else      // stop at ONE wave: a second wave of 64-column tiles streams every A tile four times from L2 — measured
+              // 8192 x 256 x 2304: 24.8 -> 15.5 us, 8192 x 256 x 4608: 43.2 -> 26.4 us (faster than its two-range split:
+              // 36.5), 8192 x 512 x 4608: 47.1 -> 35.6 us; UNet steps: C2 at batch 32 4.30 -> 3.95 ms, brain-LDM 6.18 -> 5.86 ms
+      while (!p->stat_ptr && BN > 64 && pl.kchunks >= 8 &&
+             pl.m_tiles * ((cols16 + BN / 2 - 1) / (BN / 2)) <= sm_count()) BN >>= 1;
     // short reductions (K = 256 / 384: the transformer linears) are epilogue-bound: halve the column tile while the
     // narrower tiles still fit ONE wave (measured: 8192 x 256 x 256 + residual 8.9 -> 7.3 us, 1024 x 256 x 256
     // 7.3 -> 5.2 us; going past one wave — 8192 x 512 — loses)

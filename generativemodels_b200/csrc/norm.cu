@@ -104,11 +104,26 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, int chunks
   const int g = blockIdx.x, n = blockIdx.y;
   const int cpg = C / groups;
   double s = 0.0, q = 0.0;
-  for (int i = threadIdx.x; i < chunks * cpg; i += blockDim.x) {
+  // four (sum, sum of squares) pairs in flight per thread: a plain load -> add loop was ~9 dependent L2 round trips per
+  // thread (10-26 us for a few kilobytes of partials in the ncu lists of C5's 256 x 256 level); same addition order
+  const int total = chunks * cpg;
+  int i = threadIdx.x;
+  for (; i + 3 * (int)blockDim.x < total; i += 4 * blockDim.x) {
+    float2 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int ii = i + u * blockDim.x;
+      const int ch = ii / cpg, c = g * cpg + ii % cpg;
+      v[u] = __ldg(reinterpret_cast<const float2*>(partial + (((long long)n * chunks + ch) * C + c) * 2));
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { s += (double)v[u].x; q += (double)v[u].y; }
+  }
+  for (; i < total; i += blockDim.x) {
     const int ch = i / cpg, c = g * cpg + i % cpg;
-    const float* p = partial + (((long long)n * chunks + ch) * C + c) * 2;
-    s += (double)p[0];
-    q += (double)p[1];
+    const float2 v = __ldg(reinterpret_cast<const float2*>(partial + (((long long)n * chunks + ch) * C + c) * 2));
+    s += (double)v.x;
+    q += (double)v.y;
   }
   __shared__ double ss[32], sq[32];
   for (int o = 16; o > 0; o >>= 1) {
@@ -319,7 +334,10 @@ __device__ __forceinline__ void gn_store_vec(h16* p, const float* f) {
   }
 }
 
-template <int VEC>
+// KREG > 0 (VEC == 8 only): every thread keeps its (at most KREG) row vectors in registers between the statistics and
+// the normalisation, so the tensor is read once (the second pass of the KREG = 0 form re-reads it from L1 / L2 behind
+// one more dependent-latency chain: 4096-row tensors of C5's 64 x 64 level took 15 us per call).
+template <int VEC, int KREG = 0>
 __global__ void __launch_bounds__(512) gn_fused_small_kernel(const h16* __restrict__ x0,
                                                              const h16* __restrict__ x1, int C0, int C1,
                                                              int pitch0, int pitch1, int spatial, int groups, float eps,
@@ -342,13 +360,30 @@ __global__ void __launch_bounds__(512) gn_fused_small_kernel(const h16* __restri
   const int c_off = v * VEC;
 
   float s = 0.f, q = 0.f;
+  uint4 keep[KREG > 0 ? KREG : 1];
   if (active) {
-#pragma unroll 4
-    for (int r = row0; r < spatial; r += rows_per_iter) {
-      float f[VEC];
-      gn_load_vec<VEC>(src + (long long)r * pitch + c_off, f);
+    if constexpr (KREG > 0 && VEC == 8) {
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) { s += f[j]; q = fmaf(f[j], f[j], q); }
+      for (int k = 0; k < KREG; ++k) {
+        const int r = row0 + k * rows_per_iter;
+        keep[k] = r < spatial ? __ldg(reinterpret_cast<const uint4*>(src + (long long)r * pitch + c_off))
+                              : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int k = 0; k < KREG; ++k) {          // same row order as the loop form: identical sums
+        float f[8];
+        unpack8(keep[k], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s += f[j]; q = fmaf(f[j], f[j], q); }
+      }
+    } else {
+#pragma unroll 4
+      for (int r = row0; r < spatial; r += rows_per_iter) {
+        float f[VEC];
+        gn_load_vec<VEC>(src + (long long)r * pitch + c_off, f);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) { s += f[j]; q = fmaf(f[j], f[j], q); }
+      }
     }
   }
   double ds = (double)s, dq = (double)q;
@@ -387,16 +422,33 @@ __global__ void __launch_bounds__(512) gn_fused_small_kernel(const h16* __restri
       a[j] = rstd * gamma[c_first + c_off + j];
       b[j] = beta[c_first + c_off + j] - mean * a[j];
     }
-#pragma unroll 4
-    for (int r = row0; r < spatial; r += rows_per_iter) {
-      float f[VEC];
-      gn_load_vec<VEC>(src + (long long)r * pitch + c_off, f);
+    if constexpr (KREG > 0 && VEC == 8) {
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) {
-        const float t = fmaf(f[j], a[j], b[j]);
-        f[j] = (act == B200_ACT_SILU) ? silu_fast(t) : t;
+      for (int k = 0; k < KREG; ++k) {
+        const int r = row0 + k * rows_per_iter;
+        if (r < spatial) {
+          float f[8];
+          unpack8(keep[k], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float t = fmaf(f[j], a[j], b[j]);
+            f[j] = (act == B200_ACT_SILU) ? silu_fast(t) : t;
+          }
+          gn_store_vec<8>(dst + (long long)r * y_pitch + c_off, f);
+        }
       }
-      gn_store_vec<VEC>(dst + (long long)r * y_pitch + c_off, f);
+    } else {
+#pragma unroll 4
+      for (int r = row0; r < spatial; r += rows_per_iter) {
+        float f[VEC];
+        gn_load_vec<VEC>(src + (long long)r * pitch + c_off, f);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          const float t = fmaf(f[j], a[j], b[j]);
+          f[j] = (act == B200_ACT_SILU) ? silu_fast(t) : t;
+        }
+        gn_store_vec<VEC>(dst + (long long)r * y_pitch + c_off, f);
+      }
     }
   }
   // pad channels [C, y_pitch) stay exact zeros for the consumers' vector loads: the last group's CTA writes them
@@ -713,7 +765,19 @@ extern "C" int b200_groupnorm_fused(const b200_gn_stats_params* sp, const b200_g
 #define B200_GN_FUSED(V)                                                                                           \
   B200_CUDA(b200::launch_pdl(gn_fused_small_kernel<V>, grid, 512, 0, stream, x0, x1, C0, C1, sp->x_pitch[0], sp->x_pitch[1], (int)sp->spatial, \
                                                      sp->groups, sp->eps, sp->gamma, sp->beta, ap->act, y, ap->y_pitch))
-  if (vec == 8) B200_GN_FUSED(8);
+  if (vec == 8) {
+    // rows each thread visits: 512 threads / (cpg / 8) vectors per row
+    const int rows_per_iter = 512 / (cpg / 8);
+    const long long iters = (sp->spatial + rows_per_iter - 1) / rows_per_iter;
+#define B200_GN_FUSED_K(K)                                                                                          \
+  B200_CUDA(b200::launch_pdl(gn_fused_small_kernel<8, K>, grid, 512, 0, stream, x0, x1, C0, C1, sp->x_pitch[0], sp->x_pitch[1], (int)sp->spatial, \
+                                                     sp->groups, sp->eps, sp->gamma, sp->beta, ap->act, y, ap->y_pitch))
+    if (iters <= 2) B200_GN_FUSED_K(2);
+    else if (iters <= 4) B200_GN_FUSED_K(4);
+    else if (iters <= 8) B200_GN_FUSED_K(8);
+    else B200_GN_FUSED(8);
+#undef B200_GN_FUSED_K
+  }
   else if (vec == 4) B200_GN_FUSED(4);
   else if (vec == 2) B200_GN_FUSED(2);
   else B200_GN_FUSED(1);

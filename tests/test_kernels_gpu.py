@@ -296,13 +296,13 @@ def test_split_k_linear_shapes(cuda_device, monkeypatch):
     assert ops._SPLIT_LAUNCHES == n0 + 1
     ref = F.linear(bf(x), bf(w), b) + bf(r)
     assert_close(got.t.float().cpu().reshape(1, M, -1)[..., :O], ref, 1e-2, "split-K linear + residual")
-    xr = bf(torch.randn(2, 200, 4096)).cuda().to(ops.H16)
-    w2, b2 = torch.randn(512, 4096) / math.sqrt(4096), torch.randn(512)
+    xr = bf(torch.randn(2, 200, 6144)).cuda().to(ops.H16)
+    w2, b2 = torch.randn(512, 6144) / math.sqrt(6144), torch.randn(512)
     pl2 = ops.PackedLinear(w2.cuda(), b2.cuda())
-    vt = ops.linear_transposed(xr, 4096, pl2)                         # [B, O, S_pad]
+    vt = ops.linear_transposed(xr, 6144, pl2)                         # [B, O, S_pad]
     assert ops._SPLIT_LAUNCHES == n0 + 2                              # ONE launch for the whole batch (a_broadcast)
     monkeypatch.setattr(ops, "_SPLIT_K", False)
-    vt1 = ops.linear_transposed(xr, 4096, pl2)
+    vt1 = ops.linear_transposed(xr, 6144, pl2)
     ref_vt = (F.linear(xr.float().cpu(), bf(w2), b2)).transpose(1, 2)
     assert_close(vt[..., :200].float().cpu(), ref_vt, 1e-2, "V^T projection")
     assert rel_err(vt.float(), vt1.float())[0] < 2e-3

@@ -19,6 +19,11 @@ if which == "brain":
                              resblock_updown=True, num_head_channels=(0, 512, 768), with_conditioning=True,
                              transformer_num_layers=1, cross_attention_dim=4).cuda().eval()
     x, ctx = torch.randn(1, 7, 20, 28, 20).cuda(), torch.randn(1, 1, 4).cuda()
+elif which == "c3":          # the bench's 3-D UNet at the full 160 x 224 x 160 volume
+    net = DiffusionModelUNet(spatial_dims=3, in_channels=1, out_channels=1, num_channels=(256, 256, 512),
+                             attention_levels=(False, False, True), num_head_channels=(0, 0, 512),
+                             num_res_blocks=2).cuda().eval()
+    x, ctx = torch.randn(1, 1, 160, 224, 160).cuda(), None
 elif which == "c5":          # one guided step's UNet forward on the doubled batch (ControlNet residuals omitted)
     net = DiffusionModelUNet(2, 3, 3, num_res_blocks=1, num_channels=(128, 256, 256),
                              attention_levels=(False, True, True), num_head_channels=256, with_conditioning=True,
