@@ -60,7 +60,7 @@ class IgemmParams(C.Structure):
         ("act2", C.c_int32), ("stat_ptr", C.c_void_p), ("impl", C.c_int32),
         ("gn_partial", C.c_void_p), ("gn_slots", C.c_int32), ("gn_slot0", C.c_int32),
         ("split_ws", C.c_void_p), ("split_ws_bytes", C.c_int64), ("split_counters", C.c_void_p),
-        ("a_broadcast", C.c_int32),
+        ("a_broadcast", C.c_int32), ("gn_group", C.c_int32),
     ]
 
 
@@ -130,6 +130,7 @@ SIGNATURES = {
     "b200_groupnorm_workspace_bytes": [_I32, _I64, _I32],
     "b200_groupnorm_stats": [C.POINTER(GnStatsParams), _P],
     "b200_groupnorm_from_partials": [C.POINTER(GnStatsParams), _P, _P, _P],
+    "b200_groupnorm_from_partials_ex": [C.POINTER(GnStatsParams), _P, _P, _P, _P],
     "b200_spade_apply": [C.POINTER(GnApplyParams), _P, _I32, _P, _P],
     "b200_resize_nearest": [_P, _I32, _I32, _I32, _I32, _I32, _P, _I32, _I32, _I32, _P],
     "b200_groupnorm_apply": [C.POINTER(GnApplyParams), _P],

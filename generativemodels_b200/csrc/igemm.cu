@@ -70,6 +70,7 @@ struct IgemmDev {
   float* stat_ptr;          // optional [rows][tiles_n][2] (max, sum exp) per row and column tile
   float* gn_partial;        // optional [N][gn_slots][cout/8][2] (sum, sum of squares) of the bf16 outputs, 8-channel groups
   int gn_slots, gn_slot0;
+  int gn_sh;                // log2 of the channels per partial group: 3 (8 channels) or 2 (4 channels)
   long long out_sN, out_sD, out_sH, out_sW;
   const float* bias;
   const float* rowvec;
@@ -444,13 +445,26 @@ __device__ __forceinline__ void epilogue_fast(const IgemmDev& p, const uint32_t*
       for (int g = 0; g < CH / 8; ++g) *reinterpret_cast<uint4*>(o + g * 8) = pk[g];
     }
     if constexpr (CH == 32) {
-      if (gs) {   // GroupNorm partials of the values as stored (bf16-rounded), one 8-channel group per 16-byte vector
+      if (gs) {   // GroupNorm partials of the values as stored (16-bit-rounded)
+        if (p.gn_sh == 3) {          // one 8-channel group per 16-byte vector: gs[0..3] sums, gs[4..7] sums of squares
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float f[8];
-          unpack8(pk[g], f);
+          for (int g = 0; g < 4; ++g) {
+            float f[8];
+            unpack8(pk[g], f);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { gs[g] += f[j]; gs[4 + g] = fmaf(f[j], f[j], gs[4 + g]); }
+            for (int j = 0; j < 8; ++j) { gs[g] += f[j]; gs[4 + g] = fmaf(f[j], f[j], gs[4 + g]); }
+          }
+        } else {                     // 4-channel groups (GroupNorm(32) over 128 channels): gs[0..7] sums, gs[8..15] squares
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float f[8];
+            unpack8(pk[g], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              gs[2 * g + (j >> 2)] += f[j];
+              gs[8 + 2 * g + (j >> 2)] = fmaf(f[j], f[j], gs[8 + 2 * g + (j >> 2)]);
+            }
+          }
         }
       }
     }
@@ -721,14 +735,15 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
     int gn_nb = -1, gn_n0 = 0;
     auto gn_flush = [&]() {
       if (gn_nb >= 0) {
+        const int sh = p.gn_sh;
         float* dst = p.gn_partial +
-                     (((long long)gn_nb * p.gn_slots + p.gn_slot0 + blockIdx.x * 4 + (warp - 2)) * (p.cout >> 3)) * 2 +
-                     (gn_n0 >> 3) * 2;
-        for (int e = lane; e < (BN >> 3) * 2; e += 32) {
-          if (gn_n0 + (e >> 1) * 8 < p.cout) dst[e] += gacc[e];
+                     (((long long)gn_nb * p.gn_slots + p.gn_slot0 + blockIdx.x * 4 + (warp - 2)) * (p.cout >> sh)) * 2 +
+                     (gn_n0 >> sh) * 2;
+        for (int e = lane; e < (BN >> sh) * 2; e += 32) {
+          if (gn_n0 + ((e >> 1) << sh) < p.cout) dst[e] += gacc[e];
         }
       }
-      for (int e = lane; e < (BN >> 3) * 2; e += 32) gacc[e] = 0.f;
+      for (int e = lane; e < (BN >> 2) * 2; e += 32) gacc[e] = 0.f;
       __syncwarp();
     };
     if (gn_on) gn_flush();
@@ -976,7 +991,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
           if constexpr (CH == 32) tmem_ld32(taddr + c0, raw);
           else tmem_ld16(taddr + c0, raw);
           tmem_ld_wait();
-          float gs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          float gs[16] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
           if (row_ok) {
             if (p.row_bias) {                       // operand-swapped GEMMs (V^T = W X^T): the bias runs along the rows
               const float rb = __ldg(p.row_bias + ow);
@@ -986,7 +1001,36 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
             epilogue_fast<CH>(p, raw, addv + c0, rv, out_off, n0 + c0, gn_on ? gs : nullptr);
           }
           if constexpr (CH == 32) {
-            if (gn_on) {
+            if (gn_on && p.gn_sh == 2) {
+              // 16 values x 32 lanes -> one total per lane: transpose-reduce over lane bits 4,3,2,1, butterfly over 0;
+              // the lane then holds statistic (lane >> 4) of 4-channel group 4 * bit3 + 2 * bit2 + bit1 of this chunk
+              float a8[8], a4[4], a2[2];
+              bool hi = (lane & 16) != 0;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float send = hi ? gs[i] : gs[8 + i], keep = hi ? gs[8 + i] : gs[i];
+                a8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+              }
+              hi = (lane & 8) != 0;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float send = hi ? a8[i] : a8[4 + i], keep = hi ? a8[4 + i] : a8[i];
+                a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+              }
+              hi = (lane & 4) != 0;
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                const float send = hi ? a4[i] : a4[2 + i], keep = hi ? a4[2 + i] : a4[i];
+                a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+              }
+              hi = (lane & 2) != 0;
+              float c = (hi ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, hi ? a2[0] : a2[1], 2);
+              c += __shfl_xor_sync(0xffffffffu, c, 1);
+              if ((lane & 1) == 0) {
+                const int grp = (c0 >> 2) + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                gacc[grp * 2 + (lane >> 4)] += c;
+              }
+            } else if (gn_on) {
               // 8 values x 32 lanes -> one total per lane: transpose-reduce over lane bits 4,3,2, butterfly over 1,0;
               // the lane then holds statistic (lane >> 4) of group 2 * bit3 + bit2 of this 32-column chunk
               float a[4], b[2];
@@ -1165,7 +1209,8 @@ static TileShape choose_tile(int OW, int OH, int OD, int sw, int sh, int sd) {
 __global__ void gn8_partial_check_kernel(const __grid_constant__ IgemmDev p) {
   pdl_entry();
   const long long rows = (long long)p.N * p.OD * p.OH * p.OW;
-  const int groups = p.cout >> 3;
+  const int gw = 1 << p.gn_sh;                      // channels per partial group (8 or 4)
+  const int groups = p.cout >> p.gn_sh;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * groups) return;
   const int g = (int)(idx % groups);
@@ -1175,9 +1220,9 @@ __global__ void gn8_partial_check_kernel(const __grid_constant__ IgemmDev p) {
   const int od = (int)(m % p.OD); m /= p.OD;
   const int nb = (int)m;
   const h16* o = reinterpret_cast<const h16*>(p.out_ptr) + nb * p.out_sN + od * p.out_sD +
-                           oh * p.out_sH + ow * p.out_sW + g * 8;
+                           oh * p.out_sH + ow * p.out_sW + g * gw;
   float s = 0.f, q = 0.f;
-  for (int j = 0; j < 8; ++j) { const float f = h2f(o[j]); s += f; q = fmaf(f, f, q); }
+  for (int j = 0; j < gw; ++j) { const float f = h2f(o[j]); s += f; q = fmaf(f, f, q); }
   float* dst = p.gn_partial + (((long long)nb * p.gn_slots + p.gn_slot0) * groups + g) * 2;
   atomicAdd(dst, s);
   atomicAdd(dst + 1, q);
@@ -1464,6 +1509,8 @@ extern "C" int b200_igemm(const b200_igemm_params* p, void* stream_v) {
     d.out_staged = (p->out_sW * esz > 2048 && p->out_dtype == B200_DT_F32) ? 1 : 0;
   }
   d.gn_partial = p->gn_partial; d.gn_slots = p->gn_slots; d.gn_slot0 = p->gn_slot0;
+  B200_CHECK_ARG(p->gn_group == 0 || p->gn_group == 8 || p->gn_group == 4, "igemm: gn_group must be 8 (or 0) or 4");
+  d.gn_sh = (p->gn_group == 4) ? 2 : 3;
   if (p->gn_partial) {
     // the partials ride on the vectorised epilogue: every column chunk must be a full 32-wide bf16 vector chunk
     B200_CHECK_ARG(p->out_dtype == B200_DT_H16 && p->cout % 32 == 0 && d.out_vec && !d.out_staged && !p->stat_ptr && p->gn_slot0 >= 0 && p->gn_slot0 + 4 * sm_count() <= p->gn_slots,
@@ -1493,7 +1540,7 @@ extern "C" int b200_igemm(const b200_igemm_params* p, void* stream_v) {
     B200_CUDA(b200::launch_pdl(igemm_check_kernel, (unsigned)blocks, threads, 0, stream, d));
     B200_LAUNCH_CHECK("igemm_check_kernel");
     if (d.gn_partial) {
-      const long long tot = rows * (d.cout >> 3);
+      const long long tot = rows * (d.cout >> d.gn_sh);
       B200_CUDA(b200::launch_pdl(gn8_partial_check_kernel, (unsigned)((tot + 255) / 256), 256, 0, stream, d));
       B200_LAUNCH_CHECK("gn8_partial_check_kernel");
     }

@@ -161,8 +161,8 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, int chunks
 // ---- finalize from igemm-epilogue partials ----------------------------------------------------------
 // partial_i[n][slot][C_i/8][2]; consumer group g spans cpg channels = cpg/8 producer groups of one source.
 __global__ void gn_finalize_partials_kernel(const float* __restrict__ p0, const float* __restrict__ p1, int slots0,
-                                            int slots1, int C0, int C1, int groups, long long spatial, float eps,
-                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                            int slots1, int C0, int C1, int sh0, int sh1, int groups, long long spatial,
+                                            float eps, const float* __restrict__ gamma, const float* __restrict__ beta,
                                             float* __restrict__ affine) {
   pdl_entry();
   const int g = blockIdx.x, n = blockIdx.y;
@@ -170,10 +170,10 @@ __global__ void gn_finalize_partials_kernel(const float* __restrict__ p0, const 
   const int cpg = C / groups;
   const int c_first = g * cpg;
   const float* src;
-  int slots, g8_total, g8_first;
-  if (c_first < C0) { src = p0; slots = slots0; g8_total = C0 >> 3; g8_first = c_first >> 3; }
-  else { src = p1; slots = slots1; g8_total = C1 >> 3; g8_first = (c_first - C0) >> 3; }
-  const int sub = cpg >> 3;
+  int slots, g8_total, g8_first, sh;            // producer groups of 1 << sh channels (8 or 4)
+  if (c_first < C0) { src = p0; slots = slots0; sh = sh0; g8_total = C0 >> sh; g8_first = c_first >> sh; }
+  else { src = p1; slots = slots1; sh = sh1; g8_total = C1 >> sh; g8_first = (c_first - C0) >> sh; }
+  const int sub = cpg >> sh;
   double s = 0.0, q = 0.0;
   for (int i = threadIdx.x; i < slots * sub; i += blockDim.x) {
     const int slot = i / sub, j = i - slot * sub;
@@ -678,21 +678,30 @@ extern "C" int b200_groupnorm_stats(const b200_gn_stats_params* p, void* stream_
   return B200_OK;
 }
 
-extern "C" int b200_groupnorm_from_partials(const b200_gn_stats_params* p, const float* const partial[2],
-                                            const int32_t slots[2], void* stream_v) {
+extern "C" int b200_groupnorm_from_partials_ex(const b200_gn_stats_params* p, const float* const partial[2],
+                                               const int32_t slots[2], const int32_t group[2], void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   B200_CHECK_ARG(p && partial && slots && partial[0] && p->gamma && p->beta && p->affine, "groupnorm_from_partials: null pointer");
   const int C0 = p->x_C[0], C1 = partial[1] ? p->x_C[1] : 0;
   const int C = C0 + C1;
   B200_CHECK_ARG(p->N >= 1 && p->spatial >= 1 && p->groups >= 1 && C % p->groups == 0, "groupnorm_from_partials: bad shape");
   const int cpg = C / p->groups;
-  B200_CHECK_ARG(cpg % 8 == 0 && C0 % cpg == 0 && C0 % 8 == 0 && C1 % 8 == 0 && slots[0] >= 1 && (!C1 || slots[1] >= 1),
-                 "groupnorm_from_partials: groups of %d channels do not tile the 8-channel partials", cpg);
+  const int g0 = (group && group[0]) ? group[0] : 8, g1 = (group && C1 && group[1]) ? group[1] : 8;
+  B200_CHECK_ARG((g0 == 8 || g0 == 4) && (g1 == 8 || g1 == 4), "groupnorm_from_partials: producer groups are 8 or 4 channels wide");
+  B200_CHECK_ARG(cpg % g0 == 0 && (!C1 || cpg % g1 == 0) && C0 % cpg == 0 && C0 % g0 == 0 && C1 % g1 == 0 && slots[0] >= 1 &&
+                     (!C1 || slots[1] >= 1),
+                 "groupnorm_from_partials: groups of %d channels do not tile the %d / %d-channel partials", cpg, g0, g1);
   dim3 grid(p->groups, p->N);
   B200_CUDA(b200::launch_pdl(gn_finalize_partials_kernel, grid, 256, 0, stream, partial[0], partial[1], slots[0], C1 ? slots[1] : 0, C0, C1,
-                                                        p->groups, p->spatial, p->eps, p->gamma, p->beta, p->affine));
+                                                        g0 == 4 ? 2 : 3, g1 == 4 ? 2 : 3, p->groups, p->spatial, p->eps, p->gamma, p->beta,
+                                                        p->affine));
   B200_LAUNCH_CHECK("gn_finalize_partials_kernel");
   return B200_OK;
+}
+
+extern "C" int b200_groupnorm_from_partials(const b200_gn_stats_params* p, const float* const partial[2],
+                                            const int32_t slots[2], void* stream_v) {
+  return b200_groupnorm_from_partials_ex(p, partial, slots, nullptr, stream_v);
 }
 
 extern "C" int b200_groupnorm_apply(const b200_gn_apply_params* p, void* stream_v) {

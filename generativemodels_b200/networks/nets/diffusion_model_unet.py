@@ -50,6 +50,17 @@ def _context_cl(context: torch.Tensor) -> CL:
     return ops.to_cl(context.permute(0, 2, 1).unsqueeze(2).contiguous())
 
 
+def _few_rows_linear(x: CL, pl) -> torch.Tensor:
+    """Projection of a token matrix to packed rows [N, S, pitch].  A handful of tokens in total (the context of a
+    classifier-free-guidance step: one token per sample) goes through the GEMV kernel — a tcgen05 launch costs ~9 us
+    for two rows, 14 of them per C5 UNet forward."""
+    rows = x.N * x.spatial
+    if rows <= 8 and x.C * rows * 2 <= 32 * 1024:
+        y = ops.rows_linear(x.t.reshape(rows, x.pitch), x.C, pl)
+        return y.reshape(x.N, x.spatial, y.shape[-1])
+    return _rows(ops.linear(x, pl))
+
+
 def _sdp(owner: nn.Module, xq: CL, xkv: CL, heads: int, dh: int, scale: float, residual: CL | None,
          bias_qkv: bool) -> CL:
     """scaled-dot-product attention of ``xq`` over ``xkv`` with this module's to_q/to_k/to_v."""
@@ -63,15 +74,14 @@ def _sdp(owner: nn.Module, xq: CL, xkv: CL, heads: int, dh: int, scale: float, r
         q_rows, k_rows = qk_rows[:, :, :inner], qk_rows[:, :, inner:2 * inner]
     else:
         q_rows = _rows(ops.linear(xq, packed_linear(owner, "to_q")))
-        k_rows = _rows(ops.linear(xkv, packed_linear(owner, "to_k")))
+        k_rows = _few_rows_linear(xkv, packed_linear(owner, "to_k"))
     use_tc = dh % 64 == 0 and S >= 64
     if use_tc:
         vt = ops.linear_transposed(_rows(xkv), xkv.C, packed_linear(owner, "to_v"))
         o = ops.attention(q_rows, k_rows, None, heads, dh, scale, vt=vt,
                           residual=None if residual is None else _rows(residual))
         return CL(o.reshape(xq.t.shape[0], xq.D, xq.H, xq.W, o.shape[-1]), heads * dh, xq.spatial_dims)
-    v = ops.linear(xkv, packed_linear(owner, "to_v"))
-    o = ops.attention(q_rows, k_rows, _rows(v), heads, dh, scale)
+    o = ops.attention(q_rows, k_rows, _few_rows_linear(xkv, packed_linear(owner, "to_v")), heads, dh, scale)
     out = CL(o.reshape(xq.t.shape[0], xq.D, xq.H, xq.W, o.shape[-1]), heads * dh, xq.spatial_dims)
     if residual is not None:
         out = ops.axpy(out, residual, 1.0, inplace=True)

@@ -366,6 +366,7 @@ def conv_upsample2x(src: CL, pu: PackedUpsampleConv, impl: int = 0) -> CL:
                          ACT_NONE, 1.0, None, DT_H16, ACT_NONE, out_elem_off=off, out_strides=strides, impl=impl)
         if part is not None:          # every phase launch owns its own range of slots
             p.gn_partial, p.gn_slots, p.gn_slot0 = part.data_ptr(), part.shape[1], i * _gn_slots()
+            p.gn_group = _gn_group(out)
         igemm_raw(p)
     return out
 
@@ -388,8 +389,15 @@ def _gn_partial_for(out: CL, rows: int, n_seg: int, launches: int = 1) -> torch.
     large h16 tensor whose channel count tiles the 32-column epilogue chunks."""
     if not _GN_FUSE or rows < _GN_FUSE_MIN_ROWS or n_seg < 8 or out.C % 32 != 0 or out.pitch != out.C:
         return None
-    out.gn = torch.zeros((out.N, _gn_slots(launches), out.C // 8, 2), dtype=torch.float32, device=out.t.device)
+    # partial groups of 8 channels; of 4 for narrow tensors, whose GroupNorm(32) groups are 4 channels wide (128 channels:
+    # level 0 of the 2-D UNets, the AutoencoderKL) — the consumer reads the width off the buffer's shape
+    gw = 4 if out.C <= 128 else 8
+    out.gn = torch.zeros((out.N, _gn_slots(launches), out.C // gw, 2), dtype=torch.float32, device=out.t.device)
     return out.gn
+
+
+def _gn_group(a: CL) -> int:
+    return a.C // a.gn.shape[2]
 
 
 # --------------------------------------------------------------------------------------------------
@@ -553,6 +561,7 @@ def conv(srcs: CL | Sequence[CL], pc: PackedConv, *, rowvec: torch.Tensor | None
         part = _gn_partial_for(out, rows, len(pc.segs))
         if part is not None:
             p.gn_partial, p.gn_slots, p.gn_slot0 = part.data_ptr(), part.shape[1], 0
+            p.gn_group = _gn_group(out)
     igemm_raw(p)
     return out
 
@@ -644,11 +653,14 @@ def groupnorm_affine(srcs: CL | Sequence[CL], groups: int, eps: float, gamma: to
     sp.gamma, sp.beta = g32.data_ptr(), b32.data_ptr()
     sp.affine = affine.data_ptr()
     cpg = Ct // groups
-    if _GN_FUSE and all(a.gn is not None for a in srcs) and cpg % 8 == 0 and srcs[0].C % cpg == 0:
-        # the producers already summed their outputs (8-channel groups) while writing them: no pass over the data
+    if (_GN_FUSE and all(a.gn is not None for a in srcs) and all(cpg % _gn_group(a) == 0 for a in srcs)
+            and srcs[0].C % cpg == 0):
+        # the producers already summed their outputs (8- or 4-channel groups) while writing them: no pass over the data
         parts = (C.c_void_p * 2)(*[a.gn.data_ptr() for a in srcs], *([None] * (2 - len(srcs))))
         slots = (C.c_int32 * 2)(*[a.gn.shape[1] for a in srcs], *([0] * (2 - len(srcs))))
-        check(lib.b200_groupnorm_from_partials(C.byref(sp), parts, slots, _stream()), "b200_groupnorm_from_partials")
+        gws = (C.c_int32 * 2)(*[_gn_group(a) for a in srcs], *([0] * (2 - len(srcs))))
+        check(lib.b200_groupnorm_from_partials_ex(C.byref(sp), parts, slots, gws, _stream()),
+              "b200_groupnorm_from_partials_ex")
     else:
         ws = torch.empty(lib.b200_groupnorm_workspace_bytes(a0.N, a0.spatial, Ct) // 4, dtype=torch.float32, device=dev)
         sp.partial = ws.data_ptr()

@@ -149,6 +149,10 @@ typedef struct {
    * V^T[n] = W x[n]^T of a whole batch in one launch: A = the shared weight matrix, the per-sample activations are the
    * batched K-major operand, w_batched = 1).  0: sample n reads A at batch index n. */
   int32_t a_broadcast;
+  /* Channels per gn_partial group: 8 (or 0 = 8; the layout described at gn_partial) or 4 — gn_partial[n][slot][cout/4][2],
+   * for consumers whose GroupNorm groups are 4 channels wide (32 groups over 128 channels: level 0 of the 2-D UNets, the
+   * AutoencoderKL). */
+  int32_t gn_group;
 } b200_igemm_params;
 #define B200_IGEMM_SPLIT_COUNTERS 256
 
@@ -184,6 +188,11 @@ int b200_groupnorm_stats(const b200_gn_stats_params* p, void* stream);
  * inside one source ((C0+C1)/groups % 8 == 0 and C0 % ((C0+C1)/groups) == 0). */
 int b200_groupnorm_from_partials(const b200_gn_stats_params* p, const float* const partial[2],
                                  const int32_t slots[2], void* stream);
+/* The same with the producer group width of each source stated (b200_igemm's gn_group: 8 or 4 channels per partial
+ * group): partial[i] = [N][slots[i]][x_C[i] / group[i]][2]; every consumer group must be a whole number of producer
+ * groups inside one source. */
+int b200_groupnorm_from_partials_ex(const b200_gn_stats_params* p, const float* const partial[2],
+                                    const int32_t slots[2], const int32_t group[2], void* stream);
 
 typedef struct {
   const void* x_ptr[2];

@@ -113,18 +113,22 @@ class FakeLib:
             sp.affine, ap.affine = None, None
 
     def b200_groupnorm_from_partials(self, p, partial, slots, stream):
+        return self.b200_groupnorm_from_partials_ex(p, partial, slots, None, stream)
+
+    def b200_groupnorm_from_partials_ex(self, p, partial, slots, group, stream):
         p = _obj(p)
         ptrs = [int(v) if v else 0 for v in partial]
         sl = [int(v) for v in slots]
+        gws = [(int(v) or 8) for v in group] if group is not None else [8, 8]
         N, G = p.N, p.groups
         Cs = [p.x_C[0]] + ([p.x_C[1]] if ptrs[1] else [])
         Cc = sum(Cs)
         cpg = Cc // G
-        assert cpg % 8 == 0 and Cs[0] % cpg == 0
+        assert all(cpg % gw == 0 and gw in (8, 4) for gw in gws[:len(Cs)]) and Cs[0] % cpg == 0
         sums = []
-        for ptr, nslot, Ci in zip(ptrs, sl, Cs):
-            part = f32(ptr, N * nslot * (Ci // 8) * 2).view(N, nslot, Ci // 8, 2).double().sum(1)     # [N, Ci/8, 2]
-            sums.append(part.view(N, Ci // cpg, cpg // 8, 2).sum(2))
+        for ptr, nslot, Ci, gw in zip(ptrs, sl, Cs, gws):
+            part = f32(ptr, N * nslot * (Ci // gw) * 2).view(N, nslot, Ci // gw, 2).double().sum(1)   # [N, Ci/gw, 2]
+            sums.append(part.view(N, Ci // cpg, cpg // gw, 2).sum(2))
         tot = torch.cat(sums, 1)                                                                      # [N, G, 2]
         cnt = float(p.spatial) * cpg
         mean = tot[..., 0] / cnt

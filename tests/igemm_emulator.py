@@ -159,10 +159,11 @@ def emulate(p: IgemmParams) -> None:
         dst = _bf16_view(p.out_ptr, int(idx.max()) + 1)
         dst[idx] = _f32_to_bf16(v)
         if p.gn_partial:
-            # (sum, sum of squares) of the stored bf16 values per 8-channel group, all in slot gn_slot0 of each sample
-            assert p.cout % 32 == 0 and 0 <= p.gn_slot0 < p.gn_slots
-            stored = _bf16_to_f32(_f32_to_bf16(v))[..., :p.cout].reshape(N, -1, p.cout // 8, 8).astype(np.float64)
-            part = _f32_view(p.gn_partial, N * p.gn_slots * (p.cout // 8) * 2).reshape(N, p.gn_slots, p.cout // 8, 2)
+            # (sum, sum of squares) of the stored 16-bit values per gn_group-channel group (8 or 4), all in slot gn_slot0
+            assert p.cout % 32 == 0 and 0 <= p.gn_slot0 < p.gn_slots and p.gn_group in (0, 4, 8)
+            gw = p.gn_group or 8
+            stored = _bf16_to_f32(_f32_to_bf16(v))[..., :p.cout].reshape(N, -1, p.cout // gw, gw).astype(np.float64)
+            part = _f32_view(p.gn_partial, N * p.gn_slots * (p.cout // gw) * 2).reshape(N, p.gn_slots, p.cout // gw, 2)
             part[:, p.gn_slot0, :, 0] += stored.sum((1, 3)).astype(np.float32)
             part[:, p.gn_slot0, :, 1] += (stored * stored).sum((1, 3)).astype(np.float32)
     else:

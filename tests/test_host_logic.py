@@ -113,7 +113,10 @@ def test_groupnorm_from_conv_partials_host_logic(monkeypatch):
     mk = lambda co, ci: ops.PackedConv(torch.randn(co, ci, 3, 3, 3) / math.sqrt(ci * 27), torch.randn(co), 1, 1)
     a = ops.conv(cl_cpu(x), mk(64, 16))
     b = ops.conv(cl_cpu(x), mk(32, 16))
-    assert a.gn is not None and tuple(a.gn.shape) == (2, ops._gn_slots(), 8, 2) and b.gn is not None
+    # narrow tensors (<= 128 channels) leave 4-channel partial groups, wider ones 8-channel groups
+    assert a.gn is not None and tuple(a.gn.shape) == (2, ops._gn_slots(), 16, 2) and b.gn is not None
+    wide = ops.conv(cl_cpu(x), mk(160, 16))
+    assert tuple(wide.gn.shape) == (2, ops._gn_slots(), 20, 2)
 
     def both(srcs, groups):
         Ct = sum(t.C for t in srcs)
@@ -127,8 +130,8 @@ def test_groupnorm_from_conv_partials_host_logic(monkeypatch):
         close(back(fused), ref, 1e-2)
 
     calls = []
-    real = cpu_backend.FakeLib.b200_groupnorm_from_partials
-    monkeypatch.setattr(cpu_backend.FakeLib, "b200_groupnorm_from_partials",
+    real = cpu_backend.FakeLib.b200_groupnorm_from_partials_ex
+    monkeypatch.setattr(cpu_backend.FakeLib, "b200_groupnorm_from_partials_ex",
                         lambda self, *args: (calls.append(1), real(self, *args))[1])
     both([a], 8)                  # 8 channels per group = one producer group
     both([a], 2)                  # 32 channels per group
@@ -136,14 +139,18 @@ def test_groupnorm_from_conv_partials_host_logic(monkeypatch):
     assert len(calls) == 2
     both([a, b], 6)               # groups of 16: 4 groups in a, 2 in b -> fused
     assert len(calls) == 3
+    both([a], 16)                 # GroupNorm groups of 4 channels (32 groups over 128 channels in the 2-D UNets)
+    both([wide, a], 28)           # groups of 8 over an 8-channel-partial source and a 4-channel-partial source
+    both([wide], 40)              # groups of 4 over 8-channel partials: falls back to the statistics pass
+    assert len(calls) == 5
     up = ops.conv_upsample2x(a, ops.PackedUpsampleConv(torch.randn(32, 64, 3, 3, 3) / 40, torch.randn(32)))
     assert up.gn is not None and up.gn.shape[1] == 8 * ops._gn_slots()
     both([up], 4)
-    assert len(calls) == 4
+    assert len(calls) == 6
     c = ops.axpy(a, a, 0.5, inplace=True)
     assert c.gn is None           # an in-place update invalidates the producer's sums
     both([c], 8)
-    assert len(calls) == 4
+    assert len(calls) == 6
 
 
 def test_asym_pad_host_logic():

@@ -163,8 +163,10 @@ def test_conv_groupnorm_partials(cuda_device, monkeypatch, impl):
 
     def check_partials(out):
         t = out.t.float().cpu()[..., :out.C]                                  # [N, D, H, W, C]
-        g = t.reshape(t.shape[0], -1, out.C // 8, 8).double()
-        want = torch.stack([g.sum((1, 3)), (g * g).sum((1, 3))], -1)        # [N, C/8, 2]
+        gw = out.C // out.gn.shape[2]                                         # 8, or 4 for tensors of <= 128 channels
+        assert gw == (4 if out.C <= 128 else 8)
+        g = t.reshape(t.shape[0], -1, out.C // gw, gw).double()
+        want = torch.stack([g.sum((1, 3)), (g * g).sum((1, 3))], -1)        # [N, C/gw, 2]
         got = out.gn.double().sum(1).cpu()
         err = (got - want).abs() / (want.abs() + 1.0)
         assert err.max().item() < 2e-4, err.max().item()
@@ -191,6 +193,17 @@ def test_conv_groupnorm_partials(cuda_device, monkeypatch, impl):
     up = ops.conv_upsample2x(a, ops.PackedUpsampleConv((torch.randn(256, 256, 3, 3, 3) / 80).cuda(), torch.randn(256).cuda()), impl=impl)
     check_partials(up)
     gn_both([up], 32)
+    # 128 channels: 4-channel partial groups (GroupNorm(32) over 128 channels — level 0 of the 2-D UNets, AutoencoderKL),
+    # 128-column tiles; alone, and concatenated with an 8-channel-partial producer
+    c = ops.conv(x, mk(128, 64), rowvec=torch.randn(2, 128).cuda(), impl=impl)
+    d = ops.conv(x, mk(64, 64), impl=impl)
+    assert c.gn is not None and c.gn.shape[2] == 32 and d.gn.shape[2] == 16
+    check_partials(c)
+    check_partials(d)
+    gn_both([c], 32)
+    gn_both([a, c], 32)           # 384 channels -> groups of 12: 8-channel partials cannot tile them -> statistics pass
+    gn_both([a, c], 48)           # groups of 8: fused from an 8-channel and a 4-channel producer
+    gn_both([c, d], 48)           # groups of 4 over two 4-channel producers
 
 
 def test_conv_asym_pad(cuda_device):
