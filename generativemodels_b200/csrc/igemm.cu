@@ -77,6 +77,7 @@ struct IgemmDev {
   long long rowvec_bstride;
   const float* row_bias;
   int act1, act2;
+  int bias_prefetch;        // the next tile's bias / row vector is requested during this tile's epilogue
   int geglu;                // act1 was B200_ACT_GEGLU: [32 a | 32 gate] column groups -> a * gelu(gate), cout / 2 output channels
   float scale;
   const void* res_ptr;
@@ -514,8 +515,13 @@ __device__ __forceinline__ void epilogue_lean(const IgemmDev& p, const uint32_t*
   uint4 pk[CH / 8];
 #pragma unroll
   for (int g = 0; g < CH / 8; ++g) pk[g] = pack8(v + g * 8);
+  if (p.out_v256) {
 #pragma unroll
-  for (int g = 0; g < CH / 16; ++g) stg256(o + g * 16, pk[2 * g], pk[2 * g + 1]);
+    for (int g = 0; g < CH / 16; ++g) stg256(o + g * 16, pk[2 * g], pk[2 * g + 1]);
+  } else {
+#pragma unroll
+    for (int g = 0; g < CH / 8; ++g) *reinterpret_cast<uint4*>(o + g * 8) = pk[g];
+  }
 }
 
 // Row-coalesced store for wide row-major outputs (GEMM-shaped calls whose rows are far apart in memory, e.g. the
@@ -573,7 +579,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
   auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
   float* stage_tiles = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));   // 4 x [32][CH+1]
-  float* add_tiles = stage_tiles + 4 * 32 * 33;                                                      // 4 x [BN]
+  float* add_tiles = stage_tiles + 4 * 32 * 33;                                                      // 4 x 2 x [BN]
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -721,12 +727,14 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
     const int rw = r & (p.BW - 1);
     const int rh = (r >> p.bw_log2) & (p.BH - 1);
     const int rd = r >> (p.bw_log2 + p.bh_log2);
-    float* addv = add_tiles + (warp - 2) * BN;
+    float* addv = add_tiles + (warp - 2) * 2 * BN;      // two buffers: the current vector and the prefetched next one
+    float* addv_other = addv + BN;
+    int next_key = -1;
     int add_key = -1;
     const bool fast_ok = p.out_vec && !p.out_staged && !p.stat_ptr &&
                          (!p.res_ptr || (p.res_vec && p.res_dtype == B200_DT_H16));
     const bool lean_ok = fast_ok && p.act1 == B200_ACT_NONE && p.act2 == B200_ACT_NONE && p.scale == 1.0f &&
-                         !p.row_bias && !p.gn_partial && p.out_dtype == B200_DT_H16 && p.out_v256 && !p.geglu;
+                         !p.row_bias && !p.gn_partial && p.out_dtype == B200_DT_H16 && !p.geglu;
     // GroupNorm partial sums for the consumer of this tensor: per warp [BN/8 groups][sum, sumsq] in shared memory
     // (aliases the staged-store tiles, which this mode excludes), flushed to this warp's private global slot
     // whenever the (sample, column tile) changes and at the end — deterministic, no atomics.
@@ -876,6 +884,14 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
         }
       }
 
+      constexpr int PER = (BN + 31) / 32;
+      if (fast_ok && add_key != nb * p.tiles_n + nt && next_key == nb * p.tiles_n + nt) {
+        // the vector was requested during the previous tile's epilogue and sits in the other buffer
+        if (gn_on) { gn_flush(); gn_nb = nb; gn_n0 = n0; }
+        add_key = next_key;
+        next_key = -1;
+        float* t = addv; addv = addv_other; addv_other = t;
+      }
       if (fast_ok && add_key != nb * p.tiles_n + nt) {
         if (gn_on) { gn_flush(); gn_nb = nb; gn_n0 = n0; }
         // bias + per-sample row vector of this (sample, column tile): shared by all rows, refreshed only on change
@@ -885,7 +901,6 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
           // all loads first: with the column tile as the fastest tile index a GEMM-shaped call refreshes this vector
           // for EVERY tile, and a load -> add chain per element cost eight L2 round trips per tile (a third of the
           // epilogue of the K = 256 linears of the transformer blocks, ncu source view of round 2)
-          constexpr int PER = (BN + 31) / 32;
           float bv[PER], rw[PER];
 #pragma unroll
           for (int i = 0; i < PER; ++i) {
@@ -899,6 +914,23 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
             if (lane + 32 * i < BN) addv[lane + 32 * i] = bv[i] + rw[i];
         }
         __syncwarp();
+      }
+      // the NEXT tile's vector, if it differs: requested now, written to the other buffer after this tile's chunks (one
+      // L2 round trip per tile otherwise — 15 % of the lean epilogue's samples in the ncu source view)
+      float nbv[PER], nrw[PER];
+      int want_key = -1;
+      if (fast_ok && p.bias_prefetch && tile + n_workers < p.num_tiles) {
+        const TileIdx tn = decode_tile(tile + n_workers);
+        if (tn.nb < p.N && tn.nb * p.tiles_n + tn.nt != add_key) {
+          want_key = tn.nb * p.tiles_n + tn.nt;
+#pragma unroll
+          for (int i = 0; i < PER; ++i) {
+            const int col = tn.nt * BN + lane + 32 * i;
+            const bool ok = (lane + 32 * i < BN) && col < p.cout;
+            nbv[i] = (ok && p.bias) ? __ldg(p.bias + col) : 0.f;
+            nrw[i] = (ok && p.rowvec) ? __ldg(p.rowvec + (long long)tn.nb * p.rowvec_bstride + col) : 0.f;
+          }
+        }
       }
 
       // residual of the first full chunk: in flight while this warp waits for the accumulator; every later chunk's
@@ -1088,6 +1120,12 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
       if (p.stat_ptr && row_ok) {
         float2* st = reinterpret_cast<float2*>(p.stat_ptr) + ((long long)ow * p.tiles_n + nt);
         *st = make_float2(run_max, run_sum);
+      }
+      if (want_key >= 0) {
+#pragma unroll
+        for (int i = 0; i < PER; ++i)
+          if (lane + 32 * i < BN) addv_other[lane + 32 * i] = nbv[i] + nrw[i];
+        next_key = want_key;
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -1316,6 +1354,8 @@ static int env_int(const char* name, int dflt) {
   return (e && *e) ? atoi(e) : dflt;
 }
 static int narrow_min_chunks() { static int v = env_int("B200_NARROW_MIN_CHUNKS", 4); return v; }
+static int bias_prefetch_mode() { static int v = env_int("B200_BIAS_PREFETCH", 1); return v; }
+static int no_v256() { static int v = env_int("B200_NO_V256", 0); return v; }
 static int narrow_one_wave() { static int v = env_int("B200_NARROW_ONE_WAVE", 1); return v; }
 static int split_min() { static int v = env_int("B200_SPLIT_MIN", 3); return v; }
 static int split_range_min() { static int v = env_int("B200_SPLIT_RANGE_MIN", 32); return v < 1 ? 1 : v; }
@@ -1374,7 +1414,7 @@ static Plan make_plan(const b200_igemm_params* p, bool allow_split) {
 template <int BN, int STAGES, bool PAIR = false>
 static int launch_tc(const IgemmDev& d, cudaStream_t stream) {
   constexpr int kStageBytes = kABytes + (PAIR ? BN / 2 : BN) * kBK * 2;
-  constexpr int smem = STAGES * kStageBytes + 1024 + 256 + 4 * 32 * 33 * 4 + 4 * BN * 4;
+  constexpr int smem = STAGES * kStageBytes + 1024 + 256 + 4 * 32 * 33 * 4 + 8 * BN * 4;
   static std::once_flag attr_once;          // per instantiation; read-only afterwards (re-entrant entry point)
   static cudaError_t attr_rc = cudaSuccess;
   std::call_once(attr_once, [] {
@@ -1488,6 +1528,7 @@ extern "C" int b200_igemm(const b200_igemm_params* p, void* stream_v) {
   d.bias = p->bias; d.rowvec = p->rowvec; d.rowvec_bstride = p->rowvec_bstride; d.row_bias = p->row_bias;
   d.act1 = geglu ? B200_ACT_NONE : p->act1; d.act2 = p->act2; d.scale = p->scale;
   d.geglu = geglu ? 1 : 0;
+  d.bias_prefetch = bias_prefetch_mode();
   if (geglu) d.out_cols = p->cout;        // the kernel's column loops run over the GEMM's columns
   d.res_ptr = p->res_ptr; d.res_dtype = p->res_dtype;
   d.res_sN = p->res_sN; d.res_sD = p->res_sD; d.res_sH = p->res_sH; d.res_sW = p->res_sW;
@@ -1499,7 +1540,7 @@ extern "C" int b200_igemm(const b200_igemm_params* p, void* stream_v) {
     (void)esz;
     d.out_v256 = d.out_vec && p->out_dtype == B200_DT_H16 && (p->out_cols % 16 == 0) && (p->out_sN % 16 == 0) &&
                  (p->out_sD % 16 == 0) && (p->out_sH % 16 == 0) && (p->out_sW % 16 == 0) &&
-                 (((uintptr_t)p->out_ptr) % 32 == 0);
+                 (((uintptr_t)p->out_ptr) % 32 == 0) && !no_v256();
   }
   B200_CHECK_ARG(!geglu || d.out_vec, "igemm: B200_ACT_GEGLU needs a 16-byte-aligned output (out_cols, strides %% 8 == 0)");
   {
