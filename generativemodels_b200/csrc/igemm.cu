@@ -993,6 +993,9 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_tc_kernel(const __grid_cons
         // (A shared-memory transposed variant — two chunks staged per warp, eight lanes writing each row's whole
         //  128-byte line — measured no faster: 65 -> 71 us on the 32768 x 2048 x 256 feed-forward GEMM; the
         //  row-per-thread 256-bit stores stay.)
+        // (Issuing the accumulator read of chunk k + 1 before chunk k is converted and stored — two register
+        //  buffers, loop unrolled by two — measured neutral: 57.3 vs 58.5 us; the tcgen05.ld latency is not
+        //  what the single epilogue warp per scheduler waits for.)
 #pragma unroll 1
         for (; c0 < BN && n0 + c0 + CH <= p.cout; c0 += CH) {       // warp-uniform: full chunks of real columns
           uint4 rv[CH / 8];
