@@ -652,9 +652,10 @@ def run_b200(args):
                          "frac": achieved / peak_tf if peak_tf else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel (the 256->256
                          # 3x3x3 conv at 160x224x160; algorithmic 5.88e9 B) from the ncu --set full capture
-                         # profiles/r2_ncu_igemm_pair_conv256_fullres_details.txt (3.47 GB read + 2.91 GB written,
-                         # L2 hit rate 94.8 %, tensor pipe 99.8 % of active cycles at 1.28 GHz in that capture)
-                         "traffic": 6.37e9,
+                         # profiles/r2_ncu_igemm_pair_conv256_fullres_final3_details.txt at the round's last commit
+                         # (4.33 GB read + 2.91 GB written, tensor pipe 99.5 % of active cycles, 13.02 ms at 1.31 GHz;
+                         # the capture earlier in the round, r2_ncu_igemm_pair_conv256_fullres_details.txt: 6.37e9)
+                         "traffic": 7.24e9,
                          "kernel": "igemm_tc_kernel<256,6,pair> (3x3x3 convolutions, tcgen05 cta_group::2)",
                          "peak_source": which + " sustained 16-bit GEMM",
                          "share_of_step": times["conv"] / ms_local if ms_local else None,
