@@ -104,6 +104,14 @@ class Convolution(nn.Module, _Cached):
             epilogue.setdefault("act1", self.act)
         return ops.conv(srcs, self.packed([a.C for a in srcs]), **epilogue)
 
+    def empty_output(self, x: CL | Sequence[CL]) -> CL:
+        """The output tensor ``forward(x, out=...)`` would fill (plain convolutions only) — allocated by the caller on
+        the main stream before it forks the convolution onto a side stream (ops.fork)."""
+        srcs = [x] if isinstance(x, CL) else list(x)
+        a0 = srcs[0]
+        pc = self.packed([a.C for a in srcs])
+        return ops.new_cl(a0.N, pc.out_dims(a0.D, a0.H, a0.W), pc.cout, a0.t.device, a0.spatial_dims)
+
 
 class LinearHolder(_Cached):
     """Packs an nn.Linear for the tensor-core GEMM path (the nn.Linear itself lives in the owning module)."""

@@ -66,6 +66,14 @@ def _sdp(owner: nn.Module, xq: CL, xkv: CL, heads: int, dh: int, scale: float, r
     """scaled-dot-product attention of ``xq`` over ``xkv`` with this module's to_q/to_k/to_v."""
     S = xkv.spatial
     inner = heads * dh
+    use_tc = dh % 64 == 0 and S >= 64
+    vt = vt_fork = None
+    if use_tc:
+        # V^T does not depend on q / k: inside a CUDA-graph capture it runs on a side stream next to their GEMM
+        to_v = packed_linear(owner, "to_v")
+        vt = ops.linear_transposed_out(_rows(xkv), to_v)
+        with ops.fork() as vt_fork:
+            ops.linear_transposed(_rows(xkv), xkv.C, to_v, out=vt)
     if xq is xkv and inner % 16 == 0:
         # self-attention: q and k from ONE GEMM over the stacked [to_q; to_k] weights; the attention kernels read
         # them as column slices of the [N, T, 2C] result (row pitch from the stride)
@@ -75,9 +83,8 @@ def _sdp(owner: nn.Module, xq: CL, xkv: CL, heads: int, dh: int, scale: float, r
     else:
         q_rows = _rows(ops.linear(xq, packed_linear(owner, "to_q")))
         k_rows = _few_rows_linear(xkv, packed_linear(owner, "to_k"))
-    use_tc = dh % 64 == 0 and S >= 64
     if use_tc:
-        vt = ops.linear_transposed(_rows(xkv), xkv.C, packed_linear(owner, "to_v"))
+        vt_fork.join()
         o = ops.attention(q_rows, k_rows, None, heads, dh, scale, vt=vt,
                           residual=None if residual is None else _rows(residual))
         return CL(o.reshape(xq.t.shape[0], xq.D, xq.H, xq.W, o.shape[-1]), heads * dh, xq.spatial_dims)
@@ -341,16 +348,23 @@ class ResnetBlock(nn.Module):
             resample = ops.upsample_nearest2x if self.up else ops.avgpool2
             srcs = [resample(srcs[0])]
             h = resample(h)
+        skip_fork = None
+        if isinstance(self.skip_connection, nn.Identity):
+            skip = srcs[0] if len(srcs) == 1 else ops.concat(srcs)
+        else:
+            # the 1x1 skip convolution only needs the block's input: inside a CUDA-graph capture it runs on a side
+            # stream next to conv1 / norm2 (its output is allocated here, on the main stream)
+            skip = self.skip_connection.empty_output(srcs)
+            with ops.fork() as skip_fork:
+                self.skip_connection(srcs, out=skip)
         temb = emb.proj.get(id(self)) if isinstance(emb, TimeEmb) else None
         if temb is None:
             e = emb.emb if isinstance(emb, TimeEmb) else emb
             temb = ops.small_linear(e, self.time_emb_proj.weight, self.time_emb_proj.bias, act_in=ACT_SILU)
         h = self.conv1(h, rowvec=temb)
         h = self._norm(self.norm2, [h], seg)
-        if isinstance(self.skip_connection, nn.Identity):
-            skip = srcs[0] if len(srcs) == 1 else ops.concat(srcs)
-        else:
-            skip = self.skip_connection(srcs)
+        if skip_fork is not None:
+            skip_fork.join()
         return self.conv2(h, residual=skip)
 
 

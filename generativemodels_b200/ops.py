@@ -22,12 +22,54 @@ from ._lib import (ACT_GEGLU, ACT_GELU, ACT_LEAKYRELU, ACT_NONE, ACT_RELU, ACT_S
 H16 = torch.float16 if _lib.ACT_DTYPE == "fp16" else torch.bfloat16
 
 __all__ = ["CL", "to_cl", "from_cl", "PackedConv", "PackedConvTranspose", "PackedLinear", "conv", "conv_transpose",
-           "linear", "linear_geglu", "groupnorm", "layernorm", "upsample_nearest2x", "avgpool2", "axpy", "geglu", "attention",
+           "linear", "linear_geglu", "fork", "groupnorm", "layernorm", "upsample_nearest2x", "avgpool2", "axpy", "geglu", "attention",
            "timestep_embedding", "small_linear", "ACT_NONE", "ACT_RELU", "ACT_SILU", "ACT_LEAKYRELU", "ACT_GELU", "ACT_TANH", "ACT_SIGMOID"]
 
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+_FORK = os.environ.get("B200_FORK", "1") != "0"
+_SIDE_STREAMS: dict = {}
+
+
+class fork:
+    """Run an independent branch on a side stream WHILE THE CURRENT STREAM IS BEING CAPTURED, so that a CUDA-graph replay
+    executes it concurrently with what the main stream does next (a latent-UNet step is a chain of ~150 dependent
+    kernels of 5-10 us; the 1x1 skip convolution of a ResnetBlock and the V^T projection of an attention block do not
+    depend on their neighbours).  Outside a capture it is a no-op (the eager path is host-bound; events would only add
+    to it).  Outputs the main stream reads later must be allocated BEFORE the fork (main-stream ordered frees).
+
+        with ops.fork() as f:
+            side_result = <launches>          # on the side stream when capturing
+        <main-stream launches>
+        f.join()                              # main waits for the branch
+    """
+
+    def __enter__(self):
+        self.active = _FORK and torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+        if self.active:
+            self.main = torch.cuda.current_stream()
+            idx = self.main.device.index
+            side = _SIDE_STREAMS.get(idx)
+            if side is None:
+                side = _SIDE_STREAMS[idx] = torch.cuda.Stream(device=self.main.device)
+            side.wait_stream(self.main)
+            self.side = side
+            self._ctx = torch.cuda.stream(side)
+            self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.active:
+            self._ctx.__exit__(*exc)
+        return False
+
+    def join(self) -> None:
+        if self.active:
+            self.main.wait_stream(self.side)
+            self.active = False
 
 
 def _ptr(t: torch.Tensor | None) -> int | None:
@@ -510,7 +552,7 @@ def _conv_params(srcs: Sequence[CL], w: torch.Tensor, segs, stride, out_t: torch
 
 def conv(srcs: CL | Sequence[CL], pc: PackedConv, *, rowvec: torch.Tensor | None = None, act1: int = ACT_NONE,
          scale: float = 1.0, residual: CL | None = None, act2: int = ACT_NONE, out_f32: bool = False,
-         impl: int = 0) -> CL | torch.Tensor:
+         impl: int = 0, out: CL | None = None) -> CL | torch.Tensor:
     """Fused convolution: act2(residual + scale * act1(conv(cat(srcs)) + bias + rowvec[n])).
 
     Returns a :class:`CL` (h16) or, with ``out_f32``, an fp32 channels-last tensor ``[N, D, H, W, round_up(C, 4)]``.
@@ -527,7 +569,10 @@ def conv(srcs: CL | Sequence[CL], pc: PackedConv, *, rowvec: torch.Tensor | None
         out_t = torch.empty((a0.N, *od, round_up(pc.cout, 4)), dtype=torch.float32, device=a0.t.device)
         out = out_t
     else:
-        out = new_cl(a0.N, od, pc.cout, a0.t.device, a0.spatial_dims)
+        if out is None:
+            out = new_cl(a0.N, od, pc.cout, a0.t.device, a0.spatial_dims)
+        elif tuple(out.t.shape[:4]) != (a0.N, *od) or out.C != pc.cout:
+            raise ValueError("preallocated convolution output has the wrong shape")
         out_t = out.t
     if residual is not None and tuple(residual.t.shape[:4]) != tuple(out_t.shape[:4]):
         raise ValueError("residual shape mismatch")
@@ -988,7 +1033,17 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, dh:
     return out
 
 
-def linear_transposed(x: torch.Tensor, C_in: int, pl: PackedLinear) -> torch.Tensor:
+def linear_transposed_out(x: torch.Tensor, pl: PackedLinear) -> torch.Tensor:
+    """The output buffer of :func:`linear_transposed` (allocate it on the main stream before an ops.fork())."""
+    B, S, _ = x.shape
+    Sp = round_up(S, 8)
+    out = torch.empty((B, pl.cout, Sp), dtype=H16, device=x.device)
+    if Sp > S:
+        out.zero_()
+    return out
+
+
+def linear_transposed(x: torch.Tensor, C_in: int, pl: PackedLinear, out: torch.Tensor | None = None) -> torch.Tensor:
     """V^T = W x^T + b:  x is [B, S, pitch] h16 rows; returns [B, O, round_up(S, 8)] h16.
 
     The projection weight plays the A operand (rows = output features) and the activations play the K-major
@@ -997,9 +1052,10 @@ def linear_transposed(x: torch.Tensor, C_in: int, pl: PackedLinear) -> torch.Ten
     B, S, xp = x.shape
     O = pl.cout
     Sp = round_up(S, 8)
-    out = torch.empty((B, O, Sp), dtype=H16, device=x.device)
-    if Sp > S:
-        out.zero_()
+    if out is None:
+        out = linear_transposed_out(x, pl)
+    elif tuple(out.shape) != (B, O, Sp):
+        raise ValueError("preallocated V^T output has the wrong shape")
     nk = round_up(C_in, 64) // 64
     # ONE launch for the whole batch: the shared projection matrix is the broadcast A operand, sample b's activations
     # are weight batch b, sample b's V^T is output slice b (a per-sample loop was 352 of the 420 GEMM launches of a
