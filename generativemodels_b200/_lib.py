@@ -157,6 +157,7 @@ SIGNATURES = {
     "b200_attention_flash": [C.POINTER(FlashParams), _P],
     "b200_attention_flash_workspace_bytes": [C.POINTER(FlashParams)],
     "b200_igemm_split_workspace_bytes": [C.POINTER(IgemmParams)],
+    "b200_igemm_plan": [C.POINTER(IgemmParams), _I32, _I32, _P],
     "b200_attention_small": [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _F, _P],
     "b200_timestep_embedding": [_P, _I32, _I32, _F, _P, _P],
     "b200_small_linear": [_P, _I32, _I32, _P, _P, _I32, _I32, _I32, _P, _P],

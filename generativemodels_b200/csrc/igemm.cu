@@ -1362,7 +1362,8 @@ static int no_v256() { static int v = env_int("B200_NO_V256", 0); return v; }
 static int narrow_one_wave() { static int v = env_int("B200_NARROW_ONE_WAVE", 1); return v; }
 static int split_min() { static int v = env_int("B200_SPLIT_MIN", 3); return v; }
 static int split_range_min() { static int v = env_int("B200_SPLIT_RANGE_MIN", 32); return v < 1 ? 1 : v; }
-static Plan make_plan(const b200_igemm_params* p, bool allow_split) {
+static Plan make_plan(const b200_igemm_params* p, bool allow_split, int nsm = 0) {
+  if (nsm <= 0) nsm = sm_count();       // nsm > 0: the planning query of a machine of that size (no CUDA call at all)
   Plan pl;
   pl.kchunks = 0;
   for (int s = 0; s < p->n_seg; ++s) pl.kchunks += p->seg[s].nchunks;
@@ -1384,8 +1385,8 @@ static Plan make_plan(const b200_igemm_params* p, bool allow_split) {
   // two ranges of four 64-element chunks.
   const long long wide_tiles = pl.m_tiles * ((cols16 + BN - 1) / BN);
   if (allow_split && !p->stat_ptr && !p->gn_partial && p->impl != 1 && p->act1 != B200_ACT_GEGLU && pl.kchunks >= 16 &&
-      wide_tiles * 2 <= sm_count()) {
-    long long s = sm_count() / wide_tiles;
+      wide_tiles * 2 <= nsm) {
+    long long s = nsm / wide_tiles;
     if (s > pl.kchunks / split_range_min()) s = pl.kchunks / split_range_min();
     if (s > 32) s = 32;
     if (s >= split_min()) {
@@ -1396,17 +1397,17 @@ static Plan make_plan(const b200_igemm_params* p, bool allow_split) {
   // otherwise narrower tiles, down to 64 columns, to put more CTAs on the problem
   if (pl.splits == 1) {
     if (!narrow_one_wave())   // the round-1 rule (B200_NARROW_ONE_WAVE=0): narrow while the grid is under-filled, into a second wave
-      while (!p->stat_ptr && BN > 64 && pl.m_tiles * ((cols16 + BN - 1) / BN) < sm_count() && pl.kchunks >= 8) BN >>= 1;
+      while (!p->stat_ptr && BN > 64 && pl.m_tiles * ((cols16 + BN - 1) / BN) < nsm && pl.kchunks >= 8) BN >>= 1;
     else      // stop at ONE wave: a second wave of 64-column tiles streams every A tile four times from L2 — measured
               // 8192 x 256 x 2304: 24.8 -> 15.5 us, 8192 x 256 x 4608: 43.2 -> 26.4 us (faster than its two-range split:
               // 36.5), 8192 x 512 x 4608: 47.1 -> 35.6 us; UNet steps: C2 at batch 32 4.30 -> 3.95 ms, brain-LDM 6.18 -> 5.86 ms
       while (!p->stat_ptr && BN > 64 && pl.kchunks >= 8 &&
-             pl.m_tiles * ((cols16 + BN / 2 - 1) / (BN / 2)) <= sm_count()) BN >>= 1;
+             pl.m_tiles * ((cols16 + BN / 2 - 1) / (BN / 2)) <= nsm) BN >>= 1;
     // short reductions (K = 256 / 384: the transformer linears) are epilogue-bound: halve the column tile while the
     // narrower tiles still fit ONE wave (measured: 8192 x 256 x 256 + residual 8.9 -> 7.3 us, 1024 x 256 x 256
     // 7.3 -> 5.2 us; going past one wave — 8192 x 512 — loses)
     while (!p->stat_ptr && BN > 64 && pl.kchunks >= narrow_min_chunks() && pl.kchunks < 8 &&
-           pl.m_tiles * ((cols16 + BN / 2 - 1) / (BN / 2)) <= sm_count()) BN >>= 1;
+           pl.m_tiles * ((cols16 + BN / 2 - 1) / (BN / 2)) <= nsm) BN >>= 1;
   }
   pl.BN = BN;
   pl.tiles_n = (cols16 + BN - 1) / BN;
@@ -1468,6 +1469,22 @@ extern "C" int64_t b200_igemm_split_workspace_bytes(const b200_igemm_params* p) 
     return 0;
   if ((p->impl ? p->impl : env_impl()) == 1) return 0;
   return make_plan(p, true).ws_bytes;
+}
+
+// Host-only planning query (no CUDA call): the column tile, the split factor and the tile count b200_igemm would use
+// for this call on a GPU with `sm_count` SMs — lets the binding layer's CPU tests pin the planner's rules.
+extern "C" int b200_igemm_plan(const b200_igemm_params* p, int32_t sm_count_, int32_t with_workspace, int32_t out[4]) {
+  if (!p || !out || sm_count_ < 1 || p->n_seg < 1 || p->n_seg > B200_IGEMM_MAX_SEG || p->out_N < 1 || p->out_D < 1 ||
+      p->out_H < 1 || p->out_W < 1 || p->out_cols < 1)
+    return B200_EINVAL;
+  const Plan pl = make_plan(p, with_workspace != 0, sm_count_);
+  const bool pair = igemm_pair_mode() && (pl.BN == 256 || pl.BN == 128) && pl.splits == 1 && !p->stat_ptr &&
+                    pl.m_tiles >= 2 && pl.ntiles >= sm_count_ && (!p->w_batched || ((pl.m_tiles / p->out_N) % 2 == 0));
+  out[0] = pl.BN;
+  out[1] = pl.splits;
+  out[2] = (int32_t)pl.ntiles;
+  out[3] = pair ? 1 : 0;
+  return B200_OK;
 }
 
 extern "C" int b200_igemm(const b200_igemm_params* p, void* stream_v) {

@@ -157,6 +157,11 @@ typedef struct {
 #define B200_IGEMM_SPLIT_COUNTERS 256
 
 int b200_igemm(const b200_igemm_params* p, void* stream);
+/* Host-only planning query, no CUDA call: what b200_igemm would choose for this call on a GPU with sm_count SMs —
+ * out = {column tile (16..256), split factor (1 = one pass; > 1 only if with_workspace), output tiles, 1 if the CTA-pair
+ * (cta_group::2) kernel would run}.  The rules: an under-filled grid narrows its column tile while
+ * the tiles still fit one wave; a reduction is split only into >= 3 ranges of >= 32 chunks of 64. */
+int b200_igemm_plan(const b200_igemm_params* p, int32_t sm_count, int32_t with_workspace, int32_t out[4]);
 /* Bytes of split_ws with which b200_igemm would split the reduction of this call; 0 when it would not (enough tiles
  * to fill the SMs, short reduction, stat_ptr / gn_partial requested, impl = 1).  Host-only, no launch. */
 int64_t b200_igemm_split_workspace_bytes(const b200_igemm_params* p);

@@ -123,3 +123,42 @@ def test_inferer_error_conventions():
         DiffusionInferer(s).sample(torch.zeros(1, 1, 4, 4), lambda *a, **k: None, s, mode="foo", verbose=False)
     with pytest.raises(ValueError):
         LatentDiffusionInferer(s, ldm_latent_shape=[8, 8], autoencoder_latent_shape=None)
+
+
+def test_igemm_planner_rules():
+    """b200_igemm_plan (host-only, no CUDA call): the planner's column-tile / split-K / CTA-pair decisions for a 148-SM
+    part, pinned on the shapes DESIGN.md section 2 quotes (measured with tools/gemm_probe.py on the B200)."""
+    import ctypes as C
+    lib = _lib.load()
+
+    def plan(rows, cout, K, workspace=True, n=1):
+        p = _lib.IgemmParams()
+        p.in_N = p.out_N = n
+        p.in_D = p.in_H = p.out_D = p.out_H = 1
+        p.in_W = p.out_W = rows // n
+        p.stride_d = p.stride_h = p.stride_w = 1
+        p.cout, p.out_cols = cout, cout
+        p.n_seg = 1
+        p.seg[0].nchunks = K // 64
+        out = (C.c_int32 * 4)()
+        assert lib.b200_igemm_plan(C.byref(p), 148, int(workspace), out) == 0
+        return tuple(out)          # (column tile, splits, tiles, pair kernel)
+
+    # machine-filling convolution-sized calls: widest tile, no split, CTA pairs
+    assert plan(5734400, 256, 6912) == (256, 1, 44800, 1)
+    assert plan(131072, 128, 1152) == (128, 1, 1024, 1)
+    # under-filled grids narrow the column tile only while the tiles still fit ONE wave (8192 x 256 x 2304: 24.8 -> 15.5 us)
+    assert plan(8192, 256, 2304)[:2] == (128, 1)          # 64 M tiles x 2 = 128 <= 148; x 4 would be a second wave
+    assert plan(8192, 512, 4608)[:2] == (256, 1)          # 128 tiles already; narrowing would need 256
+    assert plan(1024, 256, 2304)[:2] == (64, 1)
+    # short reductions (K = 256: the transformer linears) follow the same one-wave rule
+    assert plan(8192, 256, 256)[:2] == (128, 1)
+    assert plan(8192, 512, 256)[:2] == (256, 1)
+    # a reduction is split only into >= 3 ranges of >= 32 chunks (and only with a workspace)
+    assert plan(8192, 256, 4608)[1] == 1                  # two ranges of 36 chunks: lost to the one-pass kernel
+    assert plan(1024, 256, 2304)[1] == 1                  # 36 chunks: never
+    assert plan(1400, 512, 13824)[:2] == (256, 6)         # brain-LDM level 1: 22 wide tiles x 6 ranges of 36 chunks
+    assert plan(1400, 512, 13824, workspace=False)[1] == 1
+    assert plan(175, 768, 20736)[1] == 10                 # 6 wide tiles, 324 chunks -> 10 ranges of >= 32
+    bad = (C.c_int32 * 4)()
+    assert lib.b200_igemm_plan(None, 148, 1, bad) != 0
