@@ -314,3 +314,47 @@ def test_auto_cuda_graph_policy(monkeypatch):
     assert I._maybe_graphed(other, FakeNoise(4096), Sched(50), object()) is other             # SPADE: seg is bound late
     fn = lambda *a, **k: None                                                                 # noqa: E731
     assert I._maybe_graphed(fn, FakeNoise(4096), Sched(50), None) is fn and len(made) == 1
+
+
+def test_transformer_block_host_paths(monkeypatch):
+    """Host choices of the conditioned transformer block (second half of round 2): linear1 + GEGLU as one GEMM when the
+    hidden width is a multiple of 32 (else linear + b200_geglu), the to_k / to_v projections of a handful of context
+    tokens through the GEMV entry point, and ops.fork() as a no-op outside a CUDA-graph capture — each against the
+    plain formulation."""
+    from generativemodels_b200.networks.nets.diffusion_model_unet import (BasicTransformerBlock, GEGLUFeedForward,
+                                                                          _few_rows_linear)
+    from generativemodels_b200.networks._holders import packed_linear
+    torch.manual_seed(9)
+    calls = {"rows_linear": 0, "geglu": 0}
+    real_rl, real_gg = cpu_backend.FakeLib.b200_rows_linear, cpu_backend.FakeLib.b200_geglu
+    monkeypatch.setattr(cpu_backend.FakeLib, "b200_rows_linear",
+                        lambda self, *a: (calls.__setitem__("rows_linear", calls["rows_linear"] + 1), real_rl(self, *a))[1])
+    monkeypatch.setattr(cpu_backend.FakeLib, "b200_geglu",
+                        lambda self, *a: (calls.__setitem__("geglu", calls["geglu"] + 1), real_gg(self, *a))[1])
+
+    # feed-forward: hidden 4 * 16 = 64 (fused) and 4 * 12 = 48 (not a multiple of 32 -> separate gating kernel)
+    for C_, fused in ((16, True), (12, False)):
+        ff = GEGLUFeedForward(C_, 4 * C_).eval()
+        x = torch.randn(1, C_, 1, 23)
+        xs = bf(x)[0, :, 0].t()
+        a, gate = F.linear(xs, bf(ff.linear1.weight), ff.linear1.bias).chunk(2, -1)
+        ref = F.linear(bf(a * F.gelu(gate)), bf(ff.linear2.weight), ff.linear2.bias)
+        before = calls["geglu"]
+        with torch.no_grad():
+            out = ff(cl_cpu(x))
+        assert (calls["geglu"] == before) == fused
+        close(out.t[0, 0, 0, :, :C_].float(), ref, 2e-2)
+
+    # context projections: 2 tokens in total -> GEMV entry point; 9 tokens -> the GEMM path; same numbers
+    blk = BasicTransformerBlock(32, 2, 16, cross_attention_dim=8).eval()
+    pl = packed_linear(blk.attn2, "to_k")
+    for n_tok, gemv in ((2, True), (9, False)):
+        ctx = torch.randn(n_tok, 8, 1, 1)                      # N = n_tok samples, one context token each
+        before = calls["rows_linear"]
+        rows = _few_rows_linear(cl_cpu(ctx), pl)
+        assert (calls["rows_linear"] == before + 1) == gemv
+        close(rows[:, 0, :32].float(), F.linear(bf(ctx)[:, :, 0, 0], bf(blk.attn2.to_k.weight)), 2e-2)
+
+    with ops.fork() as f:                                       # no GPU, no capture: nothing happens
+        assert not f.active
+    f.join()
